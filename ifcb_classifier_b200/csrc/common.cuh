@@ -1,0 +1,62 @@
+// Shared helpers for the ifcb_classifier_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdarg>
+
+namespace ifcb {
+
+// Thread-local last-error string, returned through the C ABI by ifcb_last_error().
+void set_error(const char* fmt, ...);
+const char* get_error();
+
+// Status convention of include/ifcb_b200.h: 0 ok, <0 argument error, >0 cudaError_t.
+#define IFCB_ARG_CHECK(cond, ...)                                  \
+  do {                                                             \
+    if (!(cond)) {                                                 \
+      ::ifcb::set_error(__VA_ARGS__);                              \
+      return -1;                                                   \
+    }                                                              \
+  } while (0)
+
+#define IFCB_CUDA_CHECK(expr)                                                        \
+  do {                                                                               \
+    cudaError_t _e = (expr);                                                         \
+    if (_e != cudaSuccess) {                                                         \
+      ::ifcb::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),      \
+                        __FILE__, __LINE__);                                         \
+      return (int)_e;                                                                \
+    }                                                                                \
+  } while (0)
+
+__device__ __forceinline__ float bf16_round(float x) {
+  return __bfloat162float(__float2bfloat16_rn(x));
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
+  __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
+  return __bfloat1622float2(v);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+int sm_count();
+
+}  // namespace ifcb

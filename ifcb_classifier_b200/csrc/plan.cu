@@ -1,0 +1,288 @@
+// Network plan: host-side C ABI (include/ifcb_b200.h) that records layers over
+// caller-owned device buffers, encodes their TMA descriptors once, and replays
+// them as a fixed launch sequence on a stream (CUDA-graph capturable).
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <memory>
+#include <vector>
+#include "layers.cuh"
+
+namespace ifcb {
+namespace {
+
+enum LayerKind { kConv = 0, kStem = 1, kPool = 2, kHead = 3 };
+
+struct Layer {
+  LayerKind kind;
+  ConvLayer conv;
+  StemLayer stem;
+  PoolLayer pool;
+  HeadLayer head;
+};
+
+// cuTensorMapEncode* resolved through the runtime so that the library has no
+// link-time dependency on libcuda (it must load on a CPU-only build box).
+PFN_cuTensorMapEncodeTiled_v12000 g_encode_tiled = nullptr;
+PFN_cuTensorMapEncodeIm2col_v12000 g_encode_im2col = nullptr;
+
+int resolve_driver() {
+  if (g_encode_tiled && g_encode_im2col) return 0;
+  cudaDriverEntryPointQueryResult q;
+  void* fn = nullptr;
+  IFCB_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+  IFCB_ARG_CHECK(q == cudaDriverEntryPointSuccess && fn, "cuTensorMapEncodeTiled not available");
+  g_encode_tiled = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  fn = nullptr;
+  IFCB_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fn, cudaEnableDefault, &q));
+  IFCB_ARG_CHECK(q == cudaDriverEntryPointSuccess && fn, "cuTensorMapEncodeIm2col not available");
+  g_encode_im2col = reinterpret_cast<PFN_cuTensorMapEncodeIm2col_v12000>(fn);
+  return 0;
+}
+
+inline int out_dim(int in, int k, int stride, int pad) { return (in + 2 * pad - k) / stride + 1; }
+
+int pick_tile_n(int Cout, int hint) {
+  if (hint > 0) return hint;
+  const int c16 = (Cout + 15) & ~15;
+  if (c16 <= 256) return c16;
+  // smallest number of equal tiles of width <= 256 (multiple of 16)
+  for (int t = 2; t <= 64; ++t) {
+    int w = (((c16 + t - 1) / t) + 15) & ~15;
+    if (w <= 256) return w;
+  }
+  return 256;
+}
+
+}  // namespace
+}  // namespace ifcb
+
+struct ifcb_plan {
+  std::vector<ifcb::Layer> layers;
+};
+
+using namespace ifcb;
+
+extern "C" int ifcb_plan_create(ifcb_plan** out) {
+  IFCB_ARG_CHECK(out != nullptr, "ifcb_plan_create: null out");
+  *out = new ifcb_plan();
+  return 0;
+}
+
+extern "C" int ifcb_plan_destroy(ifcb_plan* plan) {
+  delete plan;
+  return 0;
+}
+
+extern "C" int ifcb_plan_num_layers(const ifcb_plan* plan) { return plan ? (int)plan->layers.size() : -1; }
+extern "C" int ifcb_plan_num_launches(const ifcb_plan* plan) { return plan ? (int)plan->layers.size() : -1; }
+
+extern "C" int ifcb_conv_geometry(int Cin, int Cout, int kh, int kw, int tile_n_hint, int32_t* Cin_pad,
+                                  int32_t* K_pad, int32_t* tile_n, int32_t* Cout_pad) {
+  IFCB_ARG_CHECK(Cin > 0 && Cout > 0 && kh > 0 && kw > 0, "ifcb_conv_geometry: bad shape");
+  IFCB_ARG_CHECK(tile_n_hint == 0 || (tile_n_hint % 16 == 0 && tile_n_hint >= 16 && tile_n_hint <= 256),
+                 "ifcb_conv_geometry: tile_n must be a multiple of 16 in [16,256]");
+  const int cp = (Cin + 63) & ~63;
+  const int tn = pick_tile_n(Cout, tile_n_hint);
+  if (Cin_pad) *Cin_pad = cp;
+  if (K_pad) *K_pad = kh * kw * cp;
+  if (tile_n) *tile_n = tn;
+  if (Cout_pad) *Cout_pad = ((Cout + tn - 1) / tn) * tn;
+  return 0;
+}
+
+extern "C" int ifcb_plan_add_conv(ifcb_plan* plan, const ifcb_conv_desc* d) {
+  IFCB_ARG_CHECK(plan && d, "ifcb_plan_add_conv: null argument");
+  IFCB_ARG_CHECK(d->d_in && d->d_weight && d->d_scale && d->d_shift, "conv: null tensor pointer");
+  IFCB_ARG_CHECK(d->Cin > 0 && d->Cin % 8 == 0, "conv: Cin=%d must be a positive multiple of 8", d->Cin);
+  IFCB_ARG_CHECK(d->in_ld >= d->Cin && d->in_ld % 8 == 0, "conv: in_ld=%d must be >= Cin and a multiple of 8",
+                 d->in_ld);
+  IFCB_ARG_CHECK((reinterpret_cast<uintptr_t>(d->d_in) & 15) == 0, "conv: d_in must be 16-byte aligned");
+  IFCB_ARG_CHECK(d->batch_cap > 0 && d->H > 0 && d->W > 0, "conv: bad input shape");
+  IFCB_ARG_CHECK(d->kh >= 1 && d->kw >= 1 && d->kh <= 16 && d->kw <= 16, "conv: bad filter %dx%d", d->kh, d->kw);
+  IFCB_ARG_CHECK(d->stride_h >= 1 && d->stride_w >= 1 && d->stride_h <= 8 && d->stride_w <= 8, "conv: bad stride");
+  IFCB_ARG_CHECK(d->pad_h >= 0 && d->pad_w >= 0 && d->pad_h < d->kh && d->pad_w < d->kw, "conv: bad padding");
+  IFCB_ARG_CHECK(d->n_seg >= 1 && d->n_seg <= IFCB_MAX_SEGMENTS, "conv: n_seg=%d out of range", d->n_seg);
+  IFCB_ARG_CHECK(d->tile_n == 0 || (d->tile_n % 16 == 0 && d->tile_n >= 16 && d->tile_n <= 256),
+                 "conv: tile_n=%d must be a multiple of 16 in [16,256]", d->tile_n);
+  int rc = resolve_driver();
+  if (rc) return rc;
+
+  Layer L{};
+  L.kind = kConv;
+  ConvKernelParams& kp = L.conv.kp;
+  const int P = out_dim(d->H, d->kh, d->stride_h, d->pad_h);
+  const int Q = out_dim(d->W, d->kw, d->stride_w, d->pad_w);
+  IFCB_ARG_CHECK(P > 0 && Q > 0, "conv: empty output");
+  int32_t cin_pad, k_pad, tile_n, cout_pad;
+  ifcb_conv_geometry(d->Cin, d->Cout, d->kh, d->kw, d->tile_n, &cin_pad, &k_pad, &tile_n, &cout_pad);
+  kp.M = 0;
+  kp.PQ = P * Q;
+  kp.Q = Q;
+  kp.kh = d->kh; kp.kw = d->kw;
+  kp.stride_h = d->stride_h; kp.stride_w = d->stride_w;
+  kp.pad_h = d->pad_h; kp.pad_w = d->pad_w;
+  kp.cblocks = cin_pad / 64;
+  const int last = d->Cin - (kp.cblocks - 1) * 64;
+  kp.last_ksteps = (last + 15) / 16;
+  kp.tile_n = tile_n;
+  kp.n_tiles = cout_pad / tile_n;
+  kp.stages = conv_pick_stages(tile_n);
+  IFCB_ARG_CHECK(kp.stages >= 2, "conv: tile_n=%d leaves fewer than 2 pipeline stages", tile_n);
+  kp.scale = d->d_scale;
+  kp.shift = d->d_shift;
+  kp.residual = reinterpret_cast<const __nv_bfloat16*>(d->d_residual);
+  kp.res_ld = d->res_ld;
+  if (d->d_residual) {
+    IFCB_ARG_CHECK(d->res_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(d->d_residual) & 15) == 0,
+                   "conv: residual view must be 16-byte aligned with ld %% 8 == 0");
+    IFCB_ARG_CHECK(d->n_seg == 1 && d->seg[0].n_begin == 0, "conv: residual needs a single segment at column 0");
+  }
+  kp.n_seg = d->n_seg;
+  for (int s = 0; s < d->n_seg; ++s) {
+    const ifcb_conv_segment& sg = d->seg[s];
+    IFCB_ARG_CHECK(sg.n_begin % 16 == 0 && sg.n_end % 16 == 0 && sg.n_begin < sg.n_end && sg.n_end <= cout_pad,
+                   "conv: segment %d [%d,%d) must be 16-aligned and inside [0,%d)", s, sg.n_begin, sg.n_end, cout_pad);
+    IFCB_ARG_CHECK(sg.d_out && sg.ld % 8 == 0 && (reinterpret_cast<uintptr_t>(sg.d_out) & 15) == 0,
+                   "conv: segment %d output must be 16-byte aligned with ld %% 8 == 0", s);
+    IFCB_ARG_CHECK(sg.ld >= sg.n_end - sg.n_begin, "conv: segment %d ld too small", s);
+    kp.seg_begin[s] = sg.n_begin;
+    kp.seg_end[s] = sg.n_end;
+    kp.seg_ld[s] = sg.ld;
+    kp.seg_relu[s] = sg.relu;
+    kp.seg_out[s] = reinterpret_cast<__nv_bfloat16*>(sg.d_out);
+  }
+  L.conv.batch_cap = d->batch_cap;
+
+  // --- A: im2col tensor map over the NHWC input view (dims C, W, H, N) ---
+  {
+    cuuint64_t gdim[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->batch_cap};
+    cuuint64_t gstr[3] = {(cuuint64_t)d->in_ld * 2, (cuuint64_t)d->W * d->in_ld * 2,
+                          (cuuint64_t)d->H * d->W * d->in_ld * 2};
+    int lower[2] = {-d->pad_w, -d->pad_h};
+    int upper[2] = {d->pad_w - (d->kw - 1), d->pad_h - (d->kh - 1)};
+    cuuint32_t estr[4] = {1, (cuuint32_t)d->stride_w, (cuuint32_t)d->stride_h, 1};
+    CUresult r = g_encode_im2col(&L.conv.tmap_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d->d_in),
+                                 gdim, gstr, lower, upper, /*channelsPerPixel=*/64, /*pixelsPerColumn=*/128, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    IFCB_ARG_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeIm2col failed (%d) for conv %dx%d Cin=%d H=%d W=%d", (int)r,
+                   d->kh, d->kw, d->Cin, d->H, d->W);
+    // Small-tensor workaround used by CUTLASS for drivers <= 13.1: tensors under
+    // 128 KiB must not have bit 21 of the second descriptor word set.
+    const unsigned long long bytes = (unsigned long long)d->batch_cap * d->H * d->W * d->in_ld * 2ull;
+    int drv = 0;
+    cudaDriverGetVersion(&drv);
+    if (drv <= 13010 && bytes < 131072ull) reinterpret_cast<uint64_t*>(&L.conv.tmap_a)[1] &= ~(1ull << 21);
+  }
+  // --- B: tiled tensor map over packed weights [Cout_pad, K_pad] ---
+  {
+    cuuint64_t gdim[2] = {(cuuint64_t)k_pad, (cuuint64_t)cout_pad};
+    cuuint64_t gstr[1] = {(cuuint64_t)k_pad * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)tile_n};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode_tiled(&L.conv.tmap_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(d->d_weight),
+                                gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    IFCB_ARG_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) for weights K_pad=%d Cout_pad=%d", (int)r,
+                   k_pad, cout_pad);
+  }
+  plan->layers.push_back(L);
+  return 0;
+}
+
+extern "C" int ifcb_plan_add_stem(ifcb_plan* plan, const ifcb_stem_desc* d) {
+  IFCB_ARG_CHECK(plan && d, "ifcb_plan_add_stem: null argument");
+  IFCB_ARG_CHECK(d->d_in && d->d_weight && d->d_scale && d->d_shift && d->d_out, "stem: null tensor pointer");
+  IFCB_ARG_CHECK(d->Cout == 32 || d->Cout == 64, "stem: Cout=%d unsupported (32 or 64)", d->Cout);
+  IFCB_ARG_CHECK(d->in_kind == IFCB_STEM_IN_U8_GRAY || d->in_kind == IFCB_STEM_IN_F32_NCHW, "stem: bad in_kind");
+  IFCB_ARG_CHECK(d->in_kind != IFCB_STEM_IN_U8_GRAY || d->d_lut, "stem: u8 input needs d_lut");
+  IFCB_ARG_CHECK(d->out_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(d->d_out) & 15) == 0,
+                 "stem: output must be 16-byte aligned with ld %% 8 == 0");
+  Layer L{};
+  L.kind = kStem;
+  L.stem.d = *d;
+  L.stem.P = out_dim(d->H, d->kh, d->stride, d->pad);
+  L.stem.Q = out_dim(d->W, d->kw, d->stride, d->pad);
+  IFCB_ARG_CHECK(L.stem.P > 0 && L.stem.Q > 0, "stem: empty output");
+  plan->layers.push_back(L);
+  return 0;
+}
+
+extern "C" int ifcb_plan_add_pool(ifcb_plan* plan, const ifcb_pool_desc* d) {
+  IFCB_ARG_CHECK(plan && d, "ifcb_plan_add_pool: null argument");
+  IFCB_ARG_CHECK(d->d_in && d->d_out, "pool: null tensor pointer");
+  IFCB_ARG_CHECK(d->kind == IFCB_POOL_MAX || d->kind == IFCB_POOL_AVG_AFFINE, "pool: bad kind %d", d->kind);
+  IFCB_ARG_CHECK(d->kind == IFCB_POOL_MAX || (d->d_scale && d->d_shift), "pool: avg needs scale/shift");
+  IFCB_ARG_CHECK(d->C > 0 && d->C % 8 == 0 && d->in_ld % 8 == 0 && d->out_ld % 8 == 0,
+                 "pool: C, in_ld, out_ld must be multiples of 8");
+  IFCB_ARG_CHECK(((reinterpret_cast<uintptr_t>(d->d_in) | reinterpret_cast<uintptr_t>(d->d_out)) & 15) == 0,
+                 "pool: views must be 16-byte aligned");
+  Layer L{};
+  L.kind = kPool;
+  L.pool.d = *d;
+  L.pool.P = out_dim(d->H, d->k, d->stride, d->pad);
+  L.pool.Q = out_dim(d->W, d->k, d->stride, d->pad);
+  IFCB_ARG_CHECK(L.pool.P > 0 && L.pool.Q > 0, "pool: empty output");
+  plan->layers.push_back(L);
+  return 0;
+}
+
+extern "C" int ifcb_plan_add_head(ifcb_plan* plan, const ifcb_head_desc* d) {
+  IFCB_ARG_CHECK(plan && d, "ifcb_plan_add_head: null argument");
+  IFCB_ARG_CHECK(d->d_in && d->d_weight && d->d_bias && d->d_scores && d->d_top1 && d->d_top1_score,
+                 "head: null tensor pointer");
+  IFCB_ARG_CHECK(d->C > 0 && d->C % 8 == 0 && d->in_ld % 8 == 0, "head: C and in_ld must be multiples of 8");
+  IFCB_ARG_CHECK(d->n_classes > 0 && (d->C + d->n_classes) * 4 <= 200 * 1024, "head: n_classes out of range");
+  IFCB_ARG_CHECK((reinterpret_cast<uintptr_t>(d->d_weight) & 15) == 0, "head: weight must be 16-byte aligned");
+  Layer L{};
+  L.kind = kHead;
+  L.head.d = *d;
+  plan->layers.push_back(L);
+  return 0;
+}
+
+extern "C" int ifcb_plan_run_range(ifcb_plan* plan, int first, int last, int batch, void* stream_v) {
+  IFCB_ARG_CHECK(plan != nullptr, "ifcb_plan_run: null plan");
+  IFCB_ARG_CHECK(first >= 0 && last <= (int)plan->layers.size() && first <= last, "ifcb_plan_run: bad layer range");
+  IFCB_ARG_CHECK(batch >= 0, "ifcb_plan_run: batch < 0");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_v);
+  for (int i = first; i < last; ++i) {
+    const Layer& L = plan->layers[i];
+    int rc = 0;
+    switch (L.kind) {
+      case kConv:
+        IFCB_ARG_CHECK(batch <= L.conv.batch_cap, "layer %d: batch %d exceeds capacity %d", i, batch, L.conv.batch_cap);
+        rc = launch_conv(L.conv, batch, stream);
+        break;
+      case kStem:
+        IFCB_ARG_CHECK(batch <= L.stem.d.batch_cap, "layer %d: batch %d exceeds capacity", i, batch);
+        rc = launch_stem(L.stem, batch, stream);
+        break;
+      case kPool:
+        IFCB_ARG_CHECK(batch <= L.pool.d.batch_cap, "layer %d: batch %d exceeds capacity", i, batch);
+        rc = launch_pool(L.pool, batch, stream);
+        break;
+      case kHead:
+        IFCB_ARG_CHECK(batch <= L.head.d.batch_cap, "layer %d: batch %d exceeds capacity", i, batch);
+        rc = launch_head(L.head, batch, stream);
+        break;
+    }
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+extern "C" int ifcb_plan_run(ifcb_plan* plan, int batch, void* stream) {
+  IFCB_ARG_CHECK(plan != nullptr, "ifcb_plan_run: null plan");
+  return ifcb_plan_run_range(plan, 0, (int)plan->layers.size(), batch, stream);
+}
+
+// Test-only probe: one im2col TMA load through conv layer `layer`'s tensor map;
+// d_out receives the raw (swizzled) 128x64 bf16 tile.
+extern "C" int ifcb_debug_im2col_probe(ifcb_plan* plan, int layer, int c, int w, int h, int n, int off_w, int off_h,
+                                       void* d_out, void* stream) {
+  IFCB_ARG_CHECK(plan && layer >= 0 && layer < (int)plan->layers.size(), "probe: bad layer");
+  IFCB_ARG_CHECK(plan->layers[layer].kind == kConv, "probe: layer %d is not a conv", layer);
+  return launch_im2col_probe(plan->layers[layer].conv, c, w, h, n, off_w, off_h, d_out,
+                             reinterpret_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,271 @@
+// Stem convolution (Cin = 3, direct fp32), pooling (K3/K4) and the fused head
+// (K6: global average pool -> Linear -> softmax -> top-1).  All HBM-bound
+// integer/elementwise work: coalesced 16-byte accesses over NHWC bf16, warp
+// shuffles for the reductions.  See include/ifcb_b200.h for the reference code
+// each replaces.
+#include "layers.cuh"
+
+namespace ifcb {
+namespace {
+
+// ------------------------------------------------------------------------------
+// Stem: direct convolution of the 3-channel network input.
+//   u8 gray input: x_c(pixel) = lut[c][g] where lut holds ToTensor + Normalize
+//   (+ torchvision transform_input) evaluated exactly as torch does in fp32.
+//   One thread = one output pixel x COUT channels (accumulators in registers).
+// ------------------------------------------------------------------------------
+template <int COUT, bool U8>
+__global__ void __launch_bounds__(128) stem_kernel(const ifcb_stem_desc d, const float* __restrict__ lut_g,
+                                                   int P, int Q, long long total) {
+  extern __shared__ float sm[];
+  const int taps = d.kh * d.kw;
+  float* w_s = sm;                       // [taps*3][COUT]
+  float* lut = sm + taps * 3 * COUT;     // [3][256] (U8 only)
+  for (int i = threadIdx.x; i < taps * 3 * COUT; i += blockDim.x) w_s[i] = d.d_weight[i];
+  if (U8)
+    for (int i = threadIdx.x; i < 768; i += blockDim.x) lut[i] = lut_g[i];
+  __syncthreads();
+
+  const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= total) return;
+  const int PQ = P * Q;
+  const int img = (int)(pix / PQ);
+  const int rem = (int)(pix - (long long)img * PQ);
+  const int op = rem / Q, oq = rem - op * Q;
+  const int h0 = op * d.stride - d.pad, w0 = oq * d.stride - d.pad;
+
+  float acc[COUT];
+#pragma unroll
+  for (int c = 0; c < COUT; ++c) acc[c] = 0.f;
+
+  const uint8_t* in_u8 = reinterpret_cast<const uint8_t*>(d.d_in) + (long long)img * d.H * d.W;
+  const float* in_f = reinterpret_cast<const float*>(d.d_in) + (long long)img * 3 * d.H * d.W;
+  const long long plane = (long long)d.H * d.W;
+
+  for (int r = 0; r < d.kh; ++r) {
+    const int hh = h0 + r;
+    if (hh < 0 || hh >= d.H) continue;
+    for (int s = 0; s < d.kw; ++s) {
+      const int ww = w0 + s;
+      if (ww < 0 || ww >= d.W) continue;
+      float x0, x1, x2;
+      if (U8) {
+        const int g = in_u8[(long long)hh * d.W + ww];
+        x0 = lut[g];
+        x1 = lut[256 + g];
+        x2 = lut[512 + g];
+      } else {
+        const long long o = (long long)hh * d.W + ww;
+        x0 = fmaf(in_f[o], d.in_scale[0], d.in_shift[0]);
+        x1 = fmaf(in_f[plane + o], d.in_scale[1], d.in_shift[1]);
+        x2 = fmaf(in_f[2 * plane + o], d.in_scale[2], d.in_shift[2]);
+      }
+      const float* wk = w_s + (r * d.kw + s) * 3 * COUT;
+#pragma unroll
+      for (int c = 0; c < COUT; ++c)
+        acc[c] = fmaf(x2, wk[2 * COUT + c], fmaf(x1, wk[COUT + c], fmaf(x0, wk[c], acc[c])));
+    }
+  }
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(d.d_out) + pix * d.out_ld;
+#pragma unroll
+  for (int c = 0; c < COUT; c += 8) {
+    float y[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      y[j] = fmaf(acc[c + j], d.d_scale[c + j], d.d_shift[c + j]);
+      if (d.relu) y[j] = fmaxf(y[j], 0.f);
+    }
+    uint4 o;
+    o.x = pack_bf16x2(y[0], y[1]);
+    o.y = pack_bf16x2(y[2], y[3]);
+    o.z = pack_bf16x2(y[4], y[5]);
+    o.w = pack_bf16x2(y[6], y[7]);
+    *reinterpret_cast<uint4*>(out + c) = o;
+  }
+}
+
+// ------------------------------------------------------------------------------
+// Pooling over NHWC bf16: one thread = one output pixel x 8 channels (16 bytes).
+// ------------------------------------------------------------------------------
+template <bool AVG>
+__global__ void __launch_bounds__(256) pool_kernel(const ifcb_pool_desc d, int P, int Q, long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c8n = d.C >> 3;
+  const int c8 = (int)(idx % c8n);
+  const long long pix = idx / c8n;
+  const int PQ = P * Q;
+  const int img = (int)(pix / PQ);
+  const int rem = (int)(pix - (long long)img * PQ);
+  const int op = rem / Q, oq = rem - op * Q;
+  const int h0 = op * d.stride - d.pad, w0 = oq * d.stride - d.pad;
+  const __nv_bfloat16* in = reinterpret_cast<const __nv_bfloat16*>(d.d_in) + (long long)img * d.H * d.W * d.in_ld + c8 * 8;
+  float a[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] = AVG ? 0.f : -INFINITY;
+  for (int r = 0; r < d.k; ++r) {
+    const int hh = h0 + r;
+    if (hh < 0 || hh >= d.H) continue;
+    for (int s = 0; s < d.k; ++s) {
+      const int ww = w0 + s;
+      if (ww < 0 || ww >= d.W) continue;
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(in + ((long long)hh * d.W + ww) * d.in_ld));
+      const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16x2(u[j]);
+        if (AVG) {
+          a[2 * j] += f.x;
+          a[2 * j + 1] += f.y;
+        } else {
+          a[2 * j] = fmaxf(a[2 * j], f.x);
+          a[2 * j + 1] = fmaxf(a[2 * j + 1], f.y);
+        }
+      }
+    }
+  }
+  if (AVG) {
+    const float inv = 1.0f / (float)(d.k * d.k);          // count_include_pad=True: always k*k
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = c8 * 8 + j;
+      float y = fmaf(a[j] * inv, d.d_scale[c], d.d_shift[c]);
+      a[j] = d.relu ? fmaxf(y, 0.f) : y;
+    }
+  }
+  uint4 o;
+  o.x = pack_bf16x2(a[0], a[1]);
+  o.y = pack_bf16x2(a[2], a[3]);
+  o.z = pack_bf16x2(a[4], a[5]);
+  o.w = pack_bf16x2(a[6], a[7]);
+  *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(d.d_out) + pix * d.out_ld + c8 * 8) = o;
+}
+
+// ------------------------------------------------------------------------------
+// Head: one CTA per image.  (1) spatial mean per channel (fp32) into shared
+// memory, (2) logits: one warp per class, float4 weight loads + shuffle
+// reduction, (3) numerically stable softmax + first-index argmax by warp 0.
+// ------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) head_kernel(const ifcb_head_desc d) {
+  extern __shared__ float sm[];
+  float* pooled = sm;                    // [C]
+  float* logits = sm + d.C;              // [n_classes]
+  const int img = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const __nv_bfloat16* in = reinterpret_cast<const __nv_bfloat16*>(d.d_in) + (long long)img * d.HW * d.in_ld;
+  const float inv = 1.0f / (float)d.HW;
+  for (int c8 = tid; c8 < (d.C >> 3); c8 += blockDim.x) {
+    float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int px = 0; px < d.HW; ++px) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(in + (long long)px * d.in_ld + c8 * 8));
+      const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16x2(u[j]);
+        a[2 * j] += f.x;
+        a[2 * j + 1] += f.y;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) pooled[c8 * 8 + j] = a[j] * inv;
+  }
+  __syncthreads();
+  const int nw = blockDim.x >> 5;
+  for (int k = warp; k < d.n_classes; k += nw) {
+    const float4* wrow = reinterpret_cast<const float4*>(d.d_weight + (long long)k * d.C);
+    float s = 0.f;
+    for (int c4 = lane; c4 < (d.C >> 2); c4 += 32) {
+      const float4 w = __ldg(wrow + c4);
+      const float4 x = *reinterpret_cast<const float4*>(pooled + c4 * 4);
+      s = fmaf(w.x, x.x, s);
+      s = fmaf(w.y, x.y, s);
+      s = fmaf(w.z, x.z, s);
+      s = fmaf(w.w, x.w, s);
+    }
+    s = warp_sum(s);
+    if (lane == 0) logits[k] = s + d.d_bias[k];
+  }
+  __syncthreads();
+  if (warp == 0) {
+    float mx = -INFINITY;
+    for (int k = lane; k < d.n_classes; k += 32) mx = fmaxf(mx, logits[k]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int k = lane; k < d.n_classes; k += 32) sum += expf(logits[k] - mx);
+    sum = warp_sum(sum);
+    float best = -1.f;
+    int best_k = 0x7fffffff;
+    for (int k = lane; k < d.n_classes; k += 32) {
+      const float l = logits[k];
+      const float pr = expf(l - mx) / sum;
+      d.d_scores[(long long)img * d.n_classes + k] = pr;
+      if (d.d_logits) d.d_logits[(long long)img * d.n_classes + k] = l;
+      if (pr > best) { best = pr; best_k = k; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int ok = __shfl_xor_sync(0xffffffffu, best_k, o);
+      if (ob > best || (ob == best && ok < best_k)) { best = ob; best_k = ok; }
+    }
+    if (lane == 0) {
+      d.d_top1[img] = best_k;
+      d.d_top1_score[img] = best;
+    }
+  }
+}
+
+}  // namespace
+
+int launch_stem(const StemLayer& L, int batch, cudaStream_t stream) {
+  const ifcb_stem_desc& d = L.d;
+  const long long total = (long long)batch * L.P * L.Q;
+  if (total == 0) return 0;
+  const int taps = d.kh * d.kw;
+  const int smem = (taps * 3 * d.Cout + 768) * (int)sizeof(float);
+  const unsigned grid = (unsigned)((total + 127) / 128);
+  const float* lut = reinterpret_cast<const float*>(d.d_lut);
+#define IFCB_STEM_LAUNCH(CO, U8)                                                                     \
+  do {                                                                                               \
+    if (smem > 48 * 1024)                                                                            \
+      IFCB_CUDA_CHECK(cudaFuncSetAttribute(stem_kernel<CO, U8>,                                      \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, smem));      \
+    stem_kernel<CO, U8><<<grid, 128, smem, stream>>>(d, lut, L.P, L.Q, total);                       \
+  } while (0)
+  const bool u8 = d.in_kind == IFCB_STEM_IN_U8_GRAY;
+  if (d.Cout == 32) {
+    if (u8) IFCB_STEM_LAUNCH(32, true); else IFCB_STEM_LAUNCH(32, false);
+  } else if (d.Cout == 64) {
+    if (u8) IFCB_STEM_LAUNCH(64, true); else IFCB_STEM_LAUNCH(64, false);
+  } else {
+    set_error("stem: Cout=%d unsupported (32 or 64)", d.Cout);
+    return -1;
+  }
+#undef IFCB_STEM_LAUNCH
+  IFCB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int launch_pool(const PoolLayer& L, int batch, cudaStream_t stream) {
+  const ifcb_pool_desc& d = L.d;
+  const long long total = (long long)batch * L.P * L.Q * (d.C >> 3);
+  if (total == 0) return 0;
+  const unsigned grid = (unsigned)((total + 255) / 256);
+  if (d.kind == IFCB_POOL_MAX)
+    pool_kernel<false><<<grid, 256, 0, stream>>>(d, L.P, L.Q, total);
+  else
+    pool_kernel<true><<<grid, 256, 0, stream>>>(d, L.P, L.Q, total);
+  IFCB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int launch_head(const HeadLayer& L, int batch, cudaStream_t stream) {
+  const ifcb_head_desc& d = L.d;
+  if (batch == 0) return 0;
+  const int smem = (d.C + d.n_classes) * (int)sizeof(float);
+  head_kernel<<<batch, 256, smem, stream>>>(d);
+  IFCB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace ifcb

@@ -1,0 +1,457 @@
+"""Network plans: torchvision-layout weights -> a fixed sequence of sm_100a kernel
+launches over preallocated NHWC bf16 activation buffers.
+
+Mirrors what ``get_namebrand_model`` + ``NeustonModel.forward``/``test_step``
+compute in eval mode (reference neuston_models.py:22-45, 66-68, 152-157) for the
+model families of BASELINE.json: ``inception_v3`` (torchvision inception.py) and
+``resnet18/34/50/101/152`` (torchvision resnet.py).  torch is used here only for
+device memory and one-off weight repacking at load time; every launch on the
+forward path goes through the C ABI (``_lib``).
+
+B200-first restructuring relative to the torchvision module tree:
+  * BatchNorm is folded into a per-channel (scale, shift) applied in the fp32
+    epilogue of the convolution kernel; ReLU and the bf16 store are fused too.
+  * ``torch.cat`` disappears: every branch writes its channel slice of the block
+    output in place.
+  * Sibling 1x1 convolutions that read the same block input are fused into ONE
+    GEMM (concatenated N) whose epilogue scatters column segments to different
+    destinations -- the block input is read from HBM once instead of 3-4 times.
+  * ``avg_pool2d(3,1,1)`` followed by a 1x1 conv+BN+ReLU is evaluated as
+    1x1 conv (inside the fused GEMM) -> avg-pool + BN + ReLU on the conv OUTPUT
+    channels (the two linear ops commute; count_include_pad=True divides by 9
+    everywhere), which shrinks the pooled tensor 4-10x.
+"""
+import ctypes as C
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import (ConvDesc, StemDesc, PoolDesc, HeadDesc, IFCB_STEM_IN_U8_GRAY, IFCB_STEM_IN_F32_NCHW,
+                   IFCB_POOL_MAX, IFCB_POOL_AVG_AFFINE)
+
+
+class View(object):
+    """Channel slice [c0, c1) of an NHWC bf16 activation tensor [B, H, W, C]."""
+
+    def __init__(self, t, c0=0, c1=None):
+        self.t = t
+        self.c0 = c0
+        self.c1 = t.shape[3] if c1 is None else c1
+
+    @property
+    def H(self): return self.t.shape[1]
+
+    @property
+    def W(self): return self.t.shape[2]
+
+    @property
+    def C(self): return self.c1 - self.c0
+
+    @property
+    def ld(self): return self.t.shape[3]
+
+    @property
+    def ptr(self): return self.t.data_ptr() + 2 * self.c0
+
+    def slice(self, c0, c1):
+        return View(self.t, self.c0 + c0, self.c0 + c1)
+
+
+def fold_bn(sd, prefix, eps):
+    """BatchNorm2d (eval) -> per-channel scale / shift, in float64 then float32."""
+    g = sd[prefix + '.weight'].double()
+    b = sd[prefix + '.bias'].double()
+    m = sd[prefix + '.running_mean'].double()
+    v = sd[prefix + '.running_var'].double()
+    scale = g / torch.sqrt(v + eps)
+    shift = b - m * scale
+    return scale.float(), shift.float()
+
+
+class PlanBuilder(object):
+    def __init__(self, batch_cap, device):
+        self.batch_cap = int(batch_cap)
+        self.device = device
+        self.keep = []                 # every device tensor the plan points into
+        self.layer_names = []
+        handle = C.c_void_p()
+        _lib.check(_lib.lib().ifcb_plan_create(C.byref(handle)), 'plan_create')
+        self.handle = handle
+        self.flops_per_image = 0       # 2*MACs of the reference graph (algorithmic)
+
+    # -- memory ---------------------------------------------------------------
+    def alloc(self, H, W, Cc):
+        t = torch.zeros((self.batch_cap, H, W, Cc), dtype=torch.bfloat16, device=self.device)
+        self.keep.append(t)
+        return View(t)
+
+    def dev(self, x, dtype):
+        t = x.detach().to(device=self.device, dtype=dtype).contiguous()
+        self.keep.append(t)
+        return t
+
+    # -- layers ---------------------------------------------------------------
+    def conv(self, x, members, stride=(1, 1), pad=(0, 0), residual=None, tile_n=0, name='conv'):
+        """One implicit-GEMM launch.  ``members``: list of dicts
+        (weight [Co,Ci,kh,kw] fp32, scale [Co], shift [Co], relu bool, out View) --
+        more than one member = horizontally fused convs sharing input ``x``."""
+        w0 = members[0]['weight']
+        Ci, kh, kw = int(w0.shape[1]), int(w0.shape[2]), int(w0.shape[3])
+        assert Ci == x.C, (name, Ci, x.C)
+        Co = sum(int(m['weight'].shape[0]) for m in members)
+        geo = _lib.conv_geometry(Ci, Co, kh, kw, tile_n)
+        Cp, Kp, Np = geo['Cin_pad'], geo['K_pad'], geo['Cout_pad']
+        wcat = torch.cat([m['weight'].float() for m in members], 0)          # [Co, Ci, kh, kw]
+        packed = torch.zeros((Np, kh * kw, Cp), dtype=torch.float32)
+        packed[:Co, :, :Ci] = wcat.permute(0, 2, 3, 1).reshape(Co, kh * kw, Ci)
+        wdev = self.dev(packed.reshape(Np, Kp), torch.bfloat16)
+        scale = torch.zeros(Np); shift = torch.zeros(Np)
+        scale[:Co] = torch.cat([m['scale'].float() for m in members])
+        shift[:Co] = torch.cat([m['shift'].float() for m in members])
+        sdev, hdev = self.dev(scale, torch.float32), self.dev(shift, torch.float32)
+        P = (x.H + 2 * pad[0] - kh) // stride[0] + 1
+        Q = (x.W + 2 * pad[1] - kw) // stride[1] + 1
+        d = ConvDesc()
+        d.d_in, d.in_ld, d.Cin = x.ptr, x.ld, Ci
+        d.batch_cap, d.H, d.W = self.batch_cap, x.H, x.W
+        d.kh, d.kw, d.stride_h, d.stride_w, d.pad_h, d.pad_w = kh, kw, stride[0], stride[1], pad[0], pad[1]
+        d.Cout = Co
+        d.d_weight, d.d_scale, d.d_shift = wdev.data_ptr(), sdev.data_ptr(), hdev.data_ptr()
+        d.n_seg = len(members)
+        n0 = 0
+        for i, m in enumerate(members):
+            co = int(m['weight'].shape[0])
+            out = m['out']
+            assert out.C == co and out.H == P and out.W == Q, (name, out.C, co, out.H, P, out.W, Q)
+            d.seg[i].n_begin, d.seg[i].n_end = n0, n0 + co
+            d.seg[i].d_out, d.seg[i].ld, d.seg[i].relu = out.ptr, out.ld, 1 if m['relu'] else 0
+            n0 += co
+        if residual is not None:
+            d.d_residual, d.res_ld = residual.ptr, residual.ld
+        d.tile_n = tile_n
+        _lib.check(_lib.lib().ifcb_plan_add_conv(self.handle, C.byref(d)), 'plan_add_conv(%s)' % name)
+        self.layer_names.append(name)
+        self.flops_per_image += 2 * P * Q * Co * Ci * kh * kw
+        return [m['out'] for m in members]
+
+    def stem(self, inp, in_kind, H, W, weight, scale, shift, stride, pad, out, lut=None,
+             in_scale=(1, 1, 1), in_shift=(0, 0, 0), name='stem'):
+        Co, _, kh, kw = [int(v) for v in weight.shape]
+        wk = weight.float().permute(2, 3, 1, 0).reshape(kh * kw * 3, Co)      # k = (r*kw+s)*3 + c
+        d = StemDesc()
+        d.d_in, d.in_kind = inp.data_ptr(), in_kind
+        d.batch_cap, d.H, d.W = self.batch_cap, H, W
+        d.kh, d.kw, d.stride, d.pad, d.Cout = kh, kw, stride, pad, Co
+        d.d_weight = self.dev(wk, torch.float32).data_ptr()
+        d.d_scale = self.dev(scale, torch.float32).data_ptr()
+        d.d_shift = self.dev(shift, torch.float32).data_ptr()
+        d.d_lut = self.dev(lut, torch.float32).data_ptr() if lut is not None else None
+        for c in range(3):
+            d.in_scale[c], d.in_shift[c] = float(in_scale[c]), float(in_shift[c])
+        d.d_out, d.out_ld, d.relu = out.ptr, out.ld, 1
+        _lib.check(_lib.lib().ifcb_plan_add_stem(self.handle, C.byref(d)), 'plan_add_stem')
+        self.layer_names.append(name)
+        self.flops_per_image += 2 * out.H * out.W * Co * 3 * kh * kw
+        return out
+
+    def pool(self, kind, x, k, stride, pad, out, scale=None, shift=None, relu=False, name='pool'):
+        d = PoolDesc()
+        d.kind, d.d_in, d.in_ld, d.C = kind, x.ptr, x.ld, x.C
+        d.batch_cap, d.H, d.W, d.k, d.stride, d.pad = self.batch_cap, x.H, x.W, k, stride, pad
+        d.d_out, d.out_ld = out.ptr, out.ld
+        if scale is not None:
+            d.d_scale = self.dev(scale, torch.float32).data_ptr()
+            d.d_shift = self.dev(shift, torch.float32).data_ptr()
+        d.relu = 1 if relu else 0
+        _lib.check(_lib.lib().ifcb_plan_add_pool(self.handle, C.byref(d)), 'plan_add_pool(%s)' % name)
+        self.layer_names.append(name)
+        return out
+
+    def head(self, x, weight, bias, name='head'):
+        n_classes = int(weight.shape[0])
+        B = self.batch_cap
+        self.scores = torch.zeros((B, n_classes), dtype=torch.float32, device=self.device)
+        self.logits = torch.zeros((B, n_classes), dtype=torch.float32, device=self.device)
+        self.top1 = torch.zeros((B,), dtype=torch.int32, device=self.device)
+        self.top1_score = torch.zeros((B,), dtype=torch.float32, device=self.device)
+        d = HeadDesc()
+        d.d_in, d.in_ld, d.C, d.HW = x.ptr, x.ld, x.C, x.H * x.W
+        d.batch_cap, d.n_classes = B, n_classes
+        d.d_weight = self.dev(weight, torch.float32).data_ptr()
+        d.d_bias = self.dev(bias, torch.float32).data_ptr()
+        d.d_scores, d.d_logits = self.scores.data_ptr(), self.logits.data_ptr()
+        d.d_top1, d.d_top1_score = self.top1.data_ptr(), self.top1_score.data_ptr()
+        _lib.check(_lib.lib().ifcb_plan_add_head(self.handle, C.byref(d)), 'plan_add_head')
+        self.layer_names.append(name)
+        self.flops_per_image += 2 * x.C * n_classes
+        return self.scores
+
+    def run(self, batch, first=None, last=None):
+        stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        if first is None:
+            _lib.check(_lib.lib().ifcb_plan_run(self.handle, int(batch), stream), 'plan_run')
+        else:
+            _lib.check(_lib.lib().ifcb_plan_run_range(self.handle, int(first), int(last), int(batch), stream),
+                       'plan_run_range')
+
+    def close(self):
+        if self.handle is not None:
+            _lib.lib().ifcb_plan_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def input_lut(img_norm=None, transform_input=False):
+    """float32 [3,256]: value the network sees for gray level g in channel c.
+
+    Evaluates exactly the reference's op sequence in float32 (numpy == torch CPU):
+    ToTensor ``g/255``; Normalize ``(x-mean)/std`` (neuston_data.py:462-463);
+    torchvision ``_transform_input`` (inception.py:95-101) when the checkpoint
+    was created with pretrained=True.
+    """
+    g = np.arange(256, dtype=np.float32)
+    x = np.repeat((g / np.float32(255.0))[None], 3, 0)
+    if img_norm:
+        mean, std = img_norm
+        m = np.asarray(mean, np.float32)[:, None]
+        s = np.asarray(std, np.float32)[:, None]
+        x = (x - m) / s
+    if transform_input:
+        ts, tm = transform_input_affine()
+        x = x * np.asarray(ts, np.float32)[:, None] + np.asarray(tm, np.float32)[:, None]
+    return torch.from_numpy(x.astype(np.float32).copy())
+
+
+def transform_input_affine():
+    """(scale[3], shift[3]) of torchvision Inception3._transform_input."""
+    s = [0.229 / 0.5, 0.224 / 0.5, 0.225 / 0.5]
+    b = [(0.485 - 0.5) / 0.5, (0.456 - 0.5) / 0.5, (0.406 - 0.5) / 0.5]
+    return s, b
+
+
+# =============================================================================
+# Inception-v3 (torchvision/models/inception.py), eval mode
+# =============================================================================
+def _basic(sd, prefix, out, relu=True, eps=1e-3):
+    scale, shift = fold_bn(sd, prefix + '.bn', eps)
+    return dict(weight=sd[prefix + '.conv.weight'], scale=scale, shift=shift, relu=relu, out=out)
+
+
+def _raw(sd, prefix, out):
+    """1x1 conv of an avg-pool branch: raw (no BN/ReLU) output, pooled afterwards."""
+    w = sd[prefix + '.conv.weight']
+    co = int(w.shape[0])
+    return dict(weight=w, scale=torch.ones(co), shift=torch.zeros(co), relu=False, out=out)
+
+
+def build_inception_v3(pb, sd, inp, in_kind, R, lut=None, transform_input=False, fuse=True):
+    """Appends the eval-mode Inception-v3 graph to ``pb``; returns the softmax scores tensor."""
+    eps = 1e-3
+    sz = lambda h, k, s, p: (h + 2 * p - k) // s + 1
+
+    def single(x, prefix, k, stride=(1, 1), pad=(0, 0), out=None, name=None):
+        w = sd[prefix + '.conv.weight']
+        co, kh, kw = int(w.shape[0]), int(w.shape[2]), int(w.shape[3])
+        if out is None:
+            out = pb.alloc(sz(x.H, kh, stride[0], pad[0]), sz(x.W, kw, stride[1], pad[1]), co)
+        pb.conv(x, [_basic(sd, prefix, out)], stride, pad, name=name or prefix)
+        return out
+
+    def fused_1x1(x, members, name):
+        if fuse:
+            pb.conv(x, members, name=name)
+        else:
+            for i, m in enumerate(members):
+                pb.conv(x, [m], name='%s.%d' % (name, i))
+
+    def avg_branch(raw, prefix, out, name):
+        scale, shift = fold_bn(sd, prefix + '.bn', eps)
+        pb.pool(IFCB_POOL_AVG_AFFINE, raw, 3, 1, 1, out, scale, shift, relu=True, name=name)
+
+    # ---- stem ----
+    H1 = sz(R, 3, 2, 0)
+    a = pb.alloc(H1, H1, 32)
+    sc, sh = fold_bn(sd, 'Conv2d_1a_3x3.bn', eps)
+    ts, tb = transform_input_affine() if transform_input else ((1, 1, 1), (0, 0, 0))
+    pb.stem(inp, in_kind, R, R, sd['Conv2d_1a_3x3.conv.weight'], sc, sh, 2, 0, a, lut=lut,
+            in_scale=ts, in_shift=tb, name='Conv2d_1a_3x3')
+    a = single(a, 'Conv2d_2a_3x3', 3)
+    a = single(a, 'Conv2d_2b_3x3', 3, pad=(1, 1))
+    p = pb.alloc(sz(a.H, 3, 2, 0), sz(a.W, 3, 2, 0), 64)
+    pb.pool(IFCB_POOL_MAX, a, 3, 2, 0, p, name='maxpool1')
+    a = single(p, 'Conv2d_3b_1x1', 1)
+    a = single(a, 'Conv2d_4a_3x3', 3)
+    p = pb.alloc(sz(a.H, 3, 2, 0), sz(a.W, 3, 2, 0), 192)
+    pb.pool(IFCB_POOL_MAX, a, 3, 2, 0, p, name='maxpool2')
+    x = p
+
+    # ---- InceptionA x3 ----
+    for blk, pf in (('Mixed_5b', 32), ('Mixed_5c', 64), ('Mixed_5d', 64)):
+        H = x.H
+        out = pb.alloc(H, H, 224 + pf)
+        t5, t3, tp = pb.alloc(H, H, 48), pb.alloc(H, H, 64), pb.alloc(H, H, pf)
+        fused_1x1(x, [_basic(sd, blk + '.branch1x1', out.slice(0, 64)),
+                      _basic(sd, blk + '.branch5x5_1', t5),
+                      _basic(sd, blk + '.branch3x3dbl_1', t3),
+                      _raw(sd, blk + '.branch_pool', tp)], blk + '.1x1s')
+        single(t5, blk + '.branch5x5_2', 5, pad=(2, 2), out=out.slice(64, 128))
+        t3b = single(t3, blk + '.branch3x3dbl_2', 3, pad=(1, 1))
+        single(t3b, blk + '.branch3x3dbl_3', 3, pad=(1, 1), out=out.slice(128, 224))
+        avg_branch(tp, blk + '.branch_pool', out.slice(224, 224 + pf), blk + '.branch_pool.avg')
+        x = out
+
+    # ---- InceptionB ----
+    blk = 'Mixed_6a'
+    H2 = sz(x.H, 3, 2, 0)
+    out = pb.alloc(H2, H2, 768)
+    single(x, blk + '.branch3x3', 3, stride=(2, 2), out=out.slice(0, 384))
+    t = single(x, blk + '.branch3x3dbl_1', 1)
+    t = single(t, blk + '.branch3x3dbl_2', 3, pad=(1, 1))
+    single(t, blk + '.branch3x3dbl_3', 3, stride=(2, 2), out=out.slice(384, 480))
+    pb.pool(IFCB_POOL_MAX, x, 3, 2, 0, out.slice(480, 768), name=blk + '.maxpool')
+    x = out
+
+    # ---- InceptionC x4 ----
+    for blk, c7 in (('Mixed_6b', 128), ('Mixed_6c', 160), ('Mixed_6d', 160), ('Mixed_6e', 192)):
+        H = x.H
+        out = pb.alloc(H, H, 768)
+        t7, td, tp = pb.alloc(H, H, c7), pb.alloc(H, H, c7), pb.alloc(H, H, 192)
+        fused_1x1(x, [_basic(sd, blk + '.branch1x1', out.slice(0, 192)),
+                      _basic(sd, blk + '.branch7x7_1', t7),
+                      _basic(sd, blk + '.branch7x7dbl_1', td),
+                      _raw(sd, blk + '.branch_pool', tp)], blk + '.1x1s')
+        t = single(t7, blk + '.branch7x7_2', 7, pad=(0, 3))
+        single(t, blk + '.branch7x7_3', 7, pad=(3, 0), out=out.slice(192, 384))
+        t = single(td, blk + '.branch7x7dbl_2', 7, pad=(3, 0))
+        t = single(t, blk + '.branch7x7dbl_3', 7, pad=(0, 3))
+        t = single(t, blk + '.branch7x7dbl_4', 7, pad=(3, 0))
+        single(t, blk + '.branch7x7dbl_5', 7, pad=(0, 3), out=out.slice(384, 576))
+        avg_branch(tp, blk + '.branch_pool', out.slice(576, 768), blk + '.branch_pool.avg')
+        x = out
+
+    # ---- InceptionD ----
+    blk = 'Mixed_7a'
+    H2 = sz(x.H, 3, 2, 0)
+    out = pb.alloc(H2, H2, 1280)
+    t3, t7 = pb.alloc(x.H, x.H, 192), pb.alloc(x.H, x.H, 192)
+    fused_1x1(x, [_basic(sd, blk + '.branch3x3_1', t3), _basic(sd, blk + '.branch7x7x3_1', t7)], blk + '.1x1s')
+    single(t3, blk + '.branch3x3_2', 3, stride=(2, 2), out=out.slice(0, 320))
+    t = single(t7, blk + '.branch7x7x3_2', 7, pad=(0, 3))
+    t = single(t, blk + '.branch7x7x3_3', 7, pad=(3, 0))
+    single(t, blk + '.branch7x7x3_4', 3, stride=(2, 2), out=out.slice(320, 512))
+    pb.pool(IFCB_POOL_MAX, x, 3, 2, 0, out.slice(512, 1280), name=blk + '.maxpool')
+    x = out
+
+    # ---- InceptionE x2 ----
+    for blk in ('Mixed_7b', 'Mixed_7c'):
+        H = x.H
+        out = pb.alloc(H, H, 2048)
+        t3, td, tp = pb.alloc(H, H, 384), pb.alloc(H, H, 448), pb.alloc(H, H, 192)
+        fused_1x1(x, [_basic(sd, blk + '.branch1x1', out.slice(0, 320)),
+                      _basic(sd, blk + '.branch3x3_1', t3),
+                      _basic(sd, blk + '.branch3x3dbl_1', td),
+                      _raw(sd, blk + '.branch_pool', tp)], blk + '.1x1s')
+        single(t3, blk + '.branch3x3_2a', 3, pad=(0, 1), out=out.slice(320, 704))
+        single(t3, blk + '.branch3x3_2b', 3, pad=(1, 0), out=out.slice(704, 1088))
+        t = single(td, blk + '.branch3x3dbl_2', 3, pad=(1, 1))
+        single(t, blk + '.branch3x3dbl_3a', 3, pad=(0, 1), out=out.slice(1088, 1472))
+        single(t, blk + '.branch3x3dbl_3b', 3, pad=(1, 0), out=out.slice(1472, 1856))
+        avg_branch(tp, blk + '.branch_pool', out.slice(1856, 2048), blk + '.branch_pool.avg')
+        x = out
+
+    return pb.head(x, sd['fc.weight'], sd['fc.bias'])
+
+
+# =============================================================================
+# ResNet (torchvision/models/resnet.py), eval mode
+# =============================================================================
+RESNET_CFG = {
+    'resnet18': ('basic', [2, 2, 2, 2]), 'resnet34': ('basic', [3, 4, 6, 3]),
+    'resnet50': ('bottleneck', [3, 4, 6, 3]), 'resnet101': ('bottleneck', [3, 4, 23, 3]),
+    'resnet152': ('bottleneck', [3, 8, 36, 3]),
+}
+
+
+def build_resnet(pb, sd, arch, inp, in_kind, R, lut=None):
+    eps = 1e-5
+    kind, layers = RESNET_CFG[arch]
+    sz = lambda h, k, s, p: (h + 2 * p - k) // s + 1
+
+    def cbr(x, conv, bn, stride=1, pad=0, relu=True, residual=None, name=None):
+        w = sd[conv + '.weight']
+        co, k = int(w.shape[0]), int(w.shape[2])
+        out = pb.alloc(sz(x.H, k, stride, pad), sz(x.W, k, stride, pad), co)
+        scale, shift = fold_bn(sd, bn, eps)
+        pb.conv(x, [dict(weight=w, scale=scale, shift=shift, relu=relu, out=out)], (stride, stride), (pad, pad),
+                residual=residual, name=name or conv)
+        return out
+
+    H1 = sz(R, 7, 2, 3)
+    a = pb.alloc(H1, H1, 64)
+    sc, sh = fold_bn(sd, 'bn1', eps)
+    pb.stem(inp, in_kind, R, R, sd['conv1.weight'], sc, sh, 2, 3, a, lut=lut, name='conv1')
+    x = pb.alloc(sz(H1, 3, 2, 1), sz(H1, 3, 2, 1), 64)
+    pb.pool(IFCB_POOL_MAX, a, 3, 2, 1, x, name='maxpool')
+    for li, nblocks in enumerate(layers):
+        for bi in range(nblocks):
+            pre = 'layer%d.%d' % (li + 1, bi)
+            stride = 2 if (li > 0 and bi == 0) else 1
+            identity = x
+            if (pre + '.downsample.0.weight') in sd:
+                identity = cbr(x, pre + '.downsample.0', pre + '.downsample.1', stride=stride, relu=False)
+            if kind == 'basic':
+                t = cbr(x, pre + '.conv1', pre + '.bn1', stride=stride, pad=1)
+                x = cbr(t, pre + '.conv2', pre + '.bn2', pad=1, relu=True, residual=identity)
+            else:   # torchvision v1.5: the stride sits on the 3x3
+                t = cbr(x, pre + '.conv1', pre + '.bn1')
+                t = cbr(t, pre + '.conv2', pre + '.bn2', stride=stride, pad=1)
+                x = cbr(t, pre + '.conv3', pre + '.bn3', relu=True, residual=identity)
+    return pb.head(x, sd['fc.weight'], sd['fc.bias'])
+
+
+class CompiledNet(object):
+    """A model compiled for a fixed batch capacity and input kind.
+
+    ``in_kind`` 'u8': input is the resized gray plane uint8 [B, R, R] produced by
+    the preprocess kernel (ToTensor/Normalize/transform_input folded into a LUT);
+    'f32': input is the reference's float32 [B, 3, R, R] tensor (drop-in forward).
+    """
+
+    def __init__(self, arch, state_dict, batch_cap, in_kind='u8', R=None, img_norm=None,
+                 transform_input=False, device='cuda', fuse=True):
+        self.arch = arch
+        self.R = R or (299 if arch == 'inception_v3' else 224)
+        self.in_kind = in_kind
+        self.batch_cap = int(batch_cap)
+        self.device = torch.device(device)
+        sd = {k: v.detach().cpu() for k, v in state_dict.items()}
+        pb = PlanBuilder(batch_cap, self.device)
+        if in_kind == 'u8':
+            self.inp = torch.zeros((batch_cap, self.R, self.R), dtype=torch.uint8, device=self.device)
+            kind = IFCB_STEM_IN_U8_GRAY
+            lut = input_lut(img_norm, transform_input and arch == 'inception_v3')
+        else:
+            self.inp = torch.zeros((batch_cap, 3, self.R, self.R), dtype=torch.float32, device=self.device)
+            kind = IFCB_STEM_IN_F32_NCHW
+            lut = None
+        if arch == 'inception_v3':
+            build_inception_v3(pb, sd, self.inp, kind, self.R, lut=lut, transform_input=transform_input, fuse=fuse)
+        elif arch in RESNET_CFG:
+            build_resnet(pb, sd, arch, self.inp, kind, self.R, lut=lut)
+        else:
+            raise KeyError('model unknown!')
+        self.pb = pb
+        self.n_classes = int(sd['fc.weight'].shape[0])
+        self.flops_per_image = pb.flops_per_image
+        self.num_launches = _lib.lib().ifcb_plan_num_launches(pb.handle)
+
+    def forward(self, n):
+        """Runs the plan on the first ``n`` images of ``self.inp`` (current stream).
+        Returns views (scores, logits, top1, top1_score) of the plan's output buffers."""
+        self.pb.run(n)
+        return self.pb.scores[:n], self.pb.logits[:n], self.pb.top1[:n], self.pb.top1_score[:n]

@@ -1,0 +1,217 @@
+/*
+ * ifcb_b200.h -- C ABI of the B200-native hot path of WHOIGit/ifcb_classifier.
+ *
+ * The reference is pure Python and exposes no C interface; its only "operator
+ * interfaces" on this path are Dataset.__getitem__ and nn.Module.forward.  Each
+ * entry point below names the reference code it replaces (file:line relative to
+ * the upstream repository, v0.3.1) -- INTEGRATION.md shows the ctypes binding a
+ * maintainer would add on the reference side.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no torch / C++ types cross the ABI.
+ *   - Return value: 0 = ok, <0 = argument / shape error, >0 = cudaError_t.
+ *     ifcb_last_error() returns a thread-local description of the last failure.
+ *   - All device buffers are CALLER-OWNED (the Python host passes torch tensor
+ *     storage); the library never allocates or frees device memory on the hot
+ *     path.  Pointers prefixed d_ are device pointers, h_ are host pointers.
+ *   - Every call is asynchronous on the cudaStream_t passed as `stream`
+ *     (a void* so that this header needs no CUDA include).
+ *   - Activations are NHWC bf16; a tensor view is (base pointer, pixel stride
+ *     `ld` in elements, channels) so that a layer can read or write a channel
+ *     slice of a wider (concatenated) tensor in place.
+ */
+#ifndef IFCB_B200_H
+#define IFCB_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IFCB_B200_ABI_VERSION 1
+
+int ifcb_abi_version(void);
+const char* ifcb_last_error(void);
+/* Number of SMs of the current device (148 on B200); <0 on error. */
+int ifcb_sm_count(void);
+
+/* ------------------------------------------------------------------------- *
+ * K1  fused ROI preprocess.
+ * Replaces IfcbBinDataset.__getitem__ (neuston_data.py:456-464):
+ *   ToPILImage('L') -> convert('RGB') -> Resize((R,R)) -> ToTensor() -> [Normalize]
+ * for all ROIs of a bin in one launch, reading the raw .roi file image
+ * (neuston_data.py:446-454 / pyifcb bin.images) straight from device memory.
+ * Bit-exact restatement of Pillow's fixed-point antialiased bilinear resample.
+ *
+ *   d_packed      raw ROI bytes (the .roi file contents), `packed_bytes` long
+ *   d_offsets[n]  START_BYTE of each ROI (int64)
+ *   d_h, d_w[n]   ROI height / width (int32); ROI i is row-major (h, w) u8
+ *   max_h, max_w  host-known upper bounds of d_h / d_w (the IFCB camera frame is
+ *                 1034 x 1380); used to validate the shared-memory budget --
+ *                 a ROI exceeding them is skipped (its output is left untouched)
+ *   R             output side (299 for inception_v3, 224 otherwise)
+ *   h_mean,h_std  3 floats each (--img-norm, neuston_data.py:331-339) or NULL
+ *   out_mode      IFCB_OUT_*; d_out holds n images of that layout
+ *   pass_rule     IFCB_PASS_PILLOW12: Pillow >= 12 pass order (vertical pass
+ *                 first when h > R and h > 100*w), IFCB_PASS_HV: Pillow 8.4.0
+ *                 (the reference's pin; always horizontal first)
+ * ------------------------------------------------------------------------- */
+enum {
+  IFCB_OUT_F32_NCHW = 0,  /* float32 [n,3,R,R]  == the reference's item tensor   */
+  IFCB_OUT_BF16_NCHW = 1, /* bfloat16 [n,3,R,R]                                   */
+  IFCB_OUT_U8_GRAY = 2    /* uint8 [n,R,R] resized gray plane (feeds the stem)    */
+};
+enum { IFCB_PASS_PILLOW12 = 0, IFCB_PASS_HV = 1 };
+
+int ifcb_preprocess(const uint8_t* d_packed, int64_t packed_bytes,
+                    const int64_t* d_offsets, const int32_t* d_h, const int32_t* d_w,
+                    int n, int max_h, int max_w, int R,
+                    const float* h_mean, const float* h_std,
+                    int out_mode, void* d_out, int pass_rule, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * Network plan: an ordered list of layer launches over caller-owned buffers.
+ * Replaces NeustonModel.forward + test_step (neuston_models.py:66-68,152-157),
+ * i.e. the torchvision graph built by get_namebrand_model (neuston_models.py:22-45)
+ * run in eval mode followed by softmax(dim=1), and the argmax/max of
+ * save_run_results (neuston_callbacks.py:161-162).
+ * ------------------------------------------------------------------------- */
+typedef struct ifcb_plan ifcb_plan;
+
+int ifcb_plan_create(ifcb_plan** out);
+int ifcb_plan_destroy(ifcb_plan* plan);
+/* Launches every layer for `batch` images (batch <= the capacity the layers
+ * were created with) on `stream`. */
+int ifcb_plan_run(ifcb_plan* plan, int batch, void* stream);
+/* Runs layers [first, last) only (layer-level tests, profiling). */
+int ifcb_plan_run_range(ifcb_plan* plan, int first, int last, int batch, void* stream);
+int ifcb_plan_num_layers(const ifcb_plan* plan);
+/* Kernel launches one ifcb_plan_run performs. */
+int ifcb_plan_num_launches(const ifcb_plan* plan);
+
+/* One output segment of a (possibly horizontally fused) convolution: GEMM
+ * columns [n_begin, n_end) go to d_out + pixel*ld + (n - n_begin). */
+typedef struct {
+  int32_t n_begin, n_end; /* multiples of 16 */
+  void* d_out;            /* bf16, channel-slice base pointer */
+  int32_t ld;             /* pixel stride of the destination, elements */
+  int32_t relu;           /* 1: max(0, .) after the affine */
+} ifcb_conv_segment;
+
+#define IFCB_MAX_SEGMENTS 4
+
+/* K2  Conv2d(bias=False) + folded BatchNorm + ReLU as a tcgen05 implicit GEMM
+ * (torchvision BasicConv2d, inception.py:398-407; ResNet conv-bn-relu).
+ * y[n, co] = act( scale[co] * sum_{r,s,ci} x[n, r, s, ci] * w[co, r, s, ci] + shift[co] (+ residual) )
+ *   d_in        bf16 NHWC view: [batch_cap, H, W, Cin] with pixel stride in_ld
+ *   d_weight    bf16 [Cout_pad, kh*kw*Cin_pad] packed by the host: K index =
+ *               (r*kw + s)*Cin_pad + ci, Cin_pad = round_up(Cin, 64), zero
+ *               filled; Cout_pad = n_tiles * tile_n
+ *   d_scale/d_shift  float32[Cout_pad] folded BN (gamma/sqrt(var+eps), beta - mean*that)
+ *   d_residual  optional bf16 view added before the activation (ResNet), or NULL
+ *   tile_n      GEMM N tile (multiple of 16, 16..256); 0 = library picks
+ */
+typedef struct {
+  const void* d_in;
+  int32_t in_ld, Cin;
+  int32_t batch_cap, H, W;
+  int32_t kh, kw, stride_h, stride_w, pad_h, pad_w;
+  int32_t Cout;
+  const void* d_weight;
+  const float* d_scale;
+  const float* d_shift;
+  int32_t n_seg;
+  ifcb_conv_segment seg[IFCB_MAX_SEGMENTS];
+  const void* d_residual;
+  int32_t res_ld;
+  int32_t tile_n;
+} ifcb_conv_desc;
+
+int ifcb_plan_add_conv(ifcb_plan* plan, const ifcb_conv_desc* desc);
+/* Packed-weight geometry for a conv: Cin_pad, K_pad = kh*kw*Cin_pad, tile_n and
+ * Cout_pad the library will use (host packs weights / scale / shift to these). */
+int ifcb_conv_geometry(int Cin, int Cout, int kh, int kw, int tile_n_hint,
+                       int32_t* Cin_pad, int32_t* K_pad, int32_t* tile_n, int32_t* Cout_pad);
+
+/* Stem: first convolution (Cin = 3) computed directly in fp32 on CUDA cores
+ * from either the resized gray plane (u8) or a float32 NCHW [batch,3,H,W]
+ * tensor (drop-in forward(x)).  Output bf16 NHWC.
+ *   d_weight float32 [kh*kw*3, Cout] (k = (r*kw+s)*3 + c), d_scale/d_shift [Cout]
+ *   u8 input : x_c = d_lut[c*256 + g]; the host fills the 3x256 float32 table
+ *              with ToTensor (g/255), --img-norm ((x-mean)/std) and torchvision's
+ *              transform_input (inception.py:95-101) evaluated exactly as torch
+ *              does, so the stem sees the same fp32 values as the reference.
+ *   f32 input: x_c = in[c] * in_scale[c] + in_shift[c] (transform_input only).
+ */
+enum { IFCB_STEM_IN_U8_GRAY = 0, IFCB_STEM_IN_F32_NCHW = 1 };
+typedef struct {
+  const void* d_in;
+  int32_t in_kind;
+  int32_t batch_cap, H, W;
+  int32_t kh, kw, stride, pad;
+  int32_t Cout;             /* 32 or 64 */
+  const float* d_weight;
+  const float* d_scale;
+  const float* d_shift;
+  const float* d_lut;       /* u8 input only */
+  float in_scale[3], in_shift[3];
+  void* d_out;
+  int32_t out_ld;
+  int32_t relu;
+} ifcb_stem_desc;
+int ifcb_plan_add_stem(ifcb_plan* plan, const ifcb_stem_desc* desc);
+
+/* K3/K4  pooling over bf16 NHWC views.
+ *   IFCB_POOL_MAX: max over the window (padding ignored, as torch max_pool2d).
+ *   IFCB_POOL_AVG_AFFINE: F.avg_pool2d(count_include_pad=True) (inception.py:204,
+ *     278,356) applied AFTER the branch's 1x1 convolution (the two commute), then
+ *     the branch's folded BN scale/shift and ReLU: y = relu(scale*avg(x)+shift).
+ */
+enum { IFCB_POOL_MAX = 0, IFCB_POOL_AVG_AFFINE = 1 };
+typedef struct {
+  int32_t kind;
+  const void* d_in;
+  int32_t in_ld, C;
+  int32_t batch_cap, H, W;
+  int32_t k, stride, pad;
+  void* d_out;
+  int32_t out_ld;
+  const float* d_scale; /* AVG_AFFINE only */
+  const float* d_shift;
+  int32_t relu;
+} ifcb_pool_desc;
+int ifcb_plan_add_pool(ifcb_plan* plan, const ifcb_pool_desc* desc);
+
+/* K6  head: global average pool -> Linear -> softmax(dim=1) -> top-1
+ * (inception.py:147-153 / resnet avgpool+fc; neuston_models.py:155-156;
+ * neuston_callbacks.py:161-162).
+ *   d_in       bf16 NHWC [batch, HW, C] (pixel stride in_ld)
+ *   d_weight   float32 [n_classes, C], d_bias float32 [n_classes]
+ *   d_scores   float32 [batch, n_classes] softmax probabilities
+ *   d_logits   optional float32 [batch, n_classes] (NULL to skip)
+ *   d_top1     int32 [batch] argmax; d_top1_score float32 [batch]
+ */
+typedef struct {
+  const void* d_in;
+  int32_t in_ld, C, HW;
+  int32_t batch_cap, n_classes;
+  const float* d_weight;
+  const float* d_bias;
+  float* d_scores;
+  float* d_logits;
+  int32_t* d_top1;
+  float* d_top1_score;
+} ifcb_head_desc;
+int ifcb_plan_add_head(ifcb_plan* plan, const ifcb_head_desc* desc);
+
+/* Test-only: issue one im2col TMA load through conv layer `layer`'s tensor map
+ * (base pixel (w,h,n), channel c, filter-tap offsets) and copy the raw 128 x 64
+ * bf16 shared-memory tile (128B-swizzled) to d_out (16 KiB). */
+int ifcb_debug_im2col_probe(ifcb_plan* plan, int layer, int c, int w, int h, int n,
+                            int off_w, int off_h, void* d_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IFCB_B200_H */

@@ -1,0 +1,269 @@
+"""Layer-level parity of the sm_100a kernels against plain PyTorch fp32 (CPU) --
+floating-point kernels keep a torch reference; tolerances are stated per test.
+Everything goes through the C ABI via ifcb_classifier_b200.graph.PlanBuilder."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def bf16r(x):
+    return x.bfloat16().float()
+
+
+def nhwc_dev(x_nchw, dev, c_total=None, c0=0):
+    """NCHW fp32 -> NHWC bf16 cuda tensor (optionally embedded at channel c0 of a wider tensor)."""
+    B, Cc, H, W = x_nchw.shape
+    c_total = c_total or Cc
+    t = torch.full((B, H, W, c_total), 7.0, dtype=torch.bfloat16, device=dev)
+    t[..., c0:c0 + Cc] = x_nchw.permute(0, 2, 3, 1).to(dev).bfloat16()
+    return t
+
+
+def to_nchw(t):
+    return t.float().cpu().permute(0, 3, 1, 2)
+
+
+def swizzle_decode(raw_u8):
+    """raw 16 KiB 128B-swizzled tile -> [128 rows, 64] bf16 values (as float)."""
+    raw = raw_u8.view(128, 8, 16)
+    rows = torch.arange(128)
+    out = torch.empty_like(raw)
+    for j in range(8):
+        out[rows, j] = raw[rows, (j ^ (rows % 8))]
+    return out.reshape(128, 128).contiguous().view(torch.bfloat16).float()
+
+
+CONV_CASES = [
+    # name, B, Cin, H, W, Cout, kh, kw, stride, pad
+    ('1x1_64_80', 3, 64, 13, 13, 80, 1, 1, (1, 1), (0, 0)),
+    ('3x3p1_64_96', 2, 64, 17, 17, 96, 3, 3, (1, 1), (1, 1)),
+    ('3x3s2_288_384', 2, 288, 35, 35, 384, 3, 3, (2, 2), (0, 0)),
+    ('5x5p2_48_64', 1, 48, 35, 35, 64, 5, 5, (1, 1), (2, 2)),
+    ('1x7_128_128', 3, 128, 17, 17, 128, 1, 7, (1, 1), (0, 3)),
+    ('7x1_160_192', 3, 160, 17, 17, 192, 7, 1, (1, 1), (3, 0)),
+    ('3x3p1_448_384', 5, 448, 8, 8, 384, 3, 3, (1, 1), (1, 1)),
+    ('3x3_32_32', 2, 32, 21, 21, 32, 3, 3, (1, 1), (0, 0)),
+    ('3x3_80_192', 1, 80, 23, 23, 192, 3, 3, (1, 1), (0, 0)),
+    ('1x1s2_64_128', 2, 64, 56, 56, 128, 1, 1, (2, 2), (0, 0)),
+    ('3x3s2p1_64_128', 2, 64, 28, 28, 128, 3, 3, (2, 2), (1, 1)),
+    ('1x3_384_384', 2, 384, 8, 8, 384, 1, 3, (1, 1), (0, 1)),
+    ('1x1_2048_320', 9, 2048, 8, 8, 320, 1, 1, (1, 1), (0, 0)),
+]
+
+
+def _ref_conv(x, w, scale, shift, stride, pad, relu, residual=None):
+    y = F.conv2d(bf16r(x), bf16r(w), stride=stride, padding=pad)
+    y = y * scale[None, :, None, None] + shift[None, :, None, None]
+    if residual is not None:
+        y = y + bf16r(residual)
+    return torch.relu(y) if relu else y
+
+
+def _check(got, want, what):
+    # bf16 output rounding (2^-9 relative) + fp32 accumulation-order noise
+    err = (got - want).abs()
+    tol = 1.5e-2 * want.abs() + 2e-2
+    assert bool((err <= tol).all()), '%s: max err %.4g at want %.4g' % (
+        what, float(err.max()), float(want.flatten()[err.argmax()]))
+
+
+def test_im2col_tma_probe(cuda):
+    """The im2col TMA load delivers pixel-major rows of 64 channels with zero fill for padding."""
+    import ctypes as C
+    from ifcb_classifier_b200 import _lib
+    from ifcb_classifier_b200.graph import PlanBuilder, View
+    torch.manual_seed(0)
+    for (Cin, H, W, kh, kw, stride, pad) in [(64, 10, 10, 3, 3, (1, 1), (1, 1)), (32, 9, 11, 3, 3, (2, 2), (0, 0)),
+                                             (80, 7, 7, 1, 7, (1, 1), (0, 3))]:
+        B = 4
+        x = torch.randn(B, Cin, H, W)
+        pb = PlanBuilder(B, cuda)
+        xin = View(nhwc_dev(x, cuda)); pb.keep.append(xin.t)
+        P = (H + 2 * pad[0] - kh) // stride[0] + 1
+        Q = (W + 2 * pad[1] - kw) // stride[1] + 1
+        out = pb.alloc(P, Q, 16)
+        pb.conv(xin, [dict(weight=torch.randn(16, Cin, kh, kw), scale=torch.ones(16), shift=torch.zeros(16),
+                           relu=False, out=out)], stride, pad)
+        raw = torch.zeros(16384, dtype=torch.uint8, device=cuda)
+        xp = F.pad(bf16r(x), (pad[1], pad[1], pad[0], pad[0]))
+        for (m0, r, s, cb) in [(0, 0, 0, 0), (128, kh - 1, kw - 1, 0), (P * Q - 5, 0, kw - 1, (Cin - 1) // 64)]:
+            img, rem = divmod(m0, P * Q)
+            op, oq = divmod(rem, Q)
+            stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+            _lib.check(_lib.lib().ifcb_debug_im2col_probe(pb.handle, 0, cb * 64, oq * stride[1] - pad[1],
+                                                          op * stride[0] - pad[0], img, s, r, raw.data_ptr(), stream))
+            torch.cuda.synchronize()
+            tile = swizzle_decode(raw.cpu())
+            want = torch.zeros(128, 64)
+            for i in range(128):
+                m = m0 + i
+                n_, rem_ = divmod(m, P * Q)
+                p_, q_ = divmod(rem_, Q)
+                if n_ >= B:
+                    continue
+                c1 = min(Cin, cb * 64 + 64)
+                want[i, :c1 - cb * 64] = xp[n_, cb * 64:c1, p_ * stride[0] + r, q_ * stride[1] + s]
+            assert torch.equal(tile, want), (Cin, H, W, kh, kw, m0, r, s, cb, float((tile - want).abs().max()))
+        pb.close()
+
+
+@pytest.mark.parametrize('case', CONV_CASES, ids=[c[0] for c in CONV_CASES])
+def test_conv_bn_relu(cuda, case):
+    from ifcb_classifier_b200.graph import PlanBuilder, View
+    name, B, Cin, H, W, Cout, kh, kw, stride, pad = case
+    g = torch.Generator().manual_seed(sum(name.encode()))
+    x = torch.randn(B, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, kh, kw, generator=g) / np.sqrt(Cin * kh * kw)
+    scale = torch.rand(Cout, generator=g) + 0.5
+    shift = torch.randn(Cout, generator=g) * 0.2
+    cap = B + 1                                            # run with batch < capacity
+    pb = PlanBuilder(cap, cuda)
+    xin_t = torch.zeros((cap, H, W, Cin), dtype=torch.bfloat16, device=cuda)
+    xin_t[:B] = nhwc_dev(x, cuda)
+    pb.keep.append(xin_t)
+    P = (H + 2 * pad[0] - kh) // stride[0] + 1
+    Q = (W + 2 * pad[1] - kw) // stride[1] + 1
+    out = pb.alloc(P, Q, Cout)
+    pb.conv(View(xin_t), [dict(weight=w, scale=scale, shift=shift, relu=True, out=out)], stride, pad, name=name)
+    pb.run(B)
+    torch.cuda.synchronize()
+    got = to_nchw(out.t[:B])
+    want = _ref_conv(x, w, scale, shift, stride, pad, True)
+    _check(got, want, name)
+    assert float(out.t[B:].float().abs().max()) == 0.0     # rows past the batch are untouched
+    pb.close()
+
+
+def test_conv_fused_segments_slices_and_residual(cuda):
+    """Horizontally fused 1x1s scattering to channel slices (one raw segment), input read
+    from a channel slice of a wider tensor, and a residual add (ResNet block tail)."""
+    from ifcb_classifier_b200.graph import PlanBuilder, View
+    g = torch.Generator().manual_seed(5)
+    B, H, W, Cin = 3, 35, 35, 192
+    x = torch.randn(B, Cin, H, W, generator=g)
+    couts = [64, 48, 64, 32]
+    ws = [torch.randn(c, Cin, 1, 1, generator=g) / np.sqrt(Cin) for c in couts]
+    scs = [torch.rand(c, generator=g) + 0.5 for c in couts]
+    shs = [torch.randn(c, generator=g) * 0.2 for c in couts]
+    pb = PlanBuilder(B, cuda)
+    wide = nhwc_dev(x, cuda, c_total=256, c0=32); pb.keep.append(wide)
+    xin = View(wide, 32, 32 + Cin)
+    cat = pb.alloc(H, W, 256)
+    outs = [cat.slice(0, 64), pb.alloc(H, W, 48), cat.slice(128, 192), pb.alloc(H, W, 32)]
+    relus = [True, True, True, False]
+    pb.conv(xin, [dict(weight=ws[i], scale=scs[i], shift=shs[i], relu=relus[i], out=outs[i]) for i in range(4)])
+    # residual: 1x1 64 -> 256 on top of `res`
+    xr = torch.randn(B, 64, 14, 14, generator=g)
+    res = torch.randn(B, 256, 14, 14, generator=g)
+    wr = torch.randn(256, 64, 1, 1, generator=g) / 8
+    xr_d, res_d = View(nhwc_dev(xr, cuda)), View(nhwc_dev(res, cuda))
+    pb.keep += [xr_d.t, res_d.t]
+    out_r = pb.alloc(14, 14, 256)
+    pb.conv(xr_d, [dict(weight=wr, scale=torch.ones(256), shift=torch.zeros(256), relu=True, out=out_r)],
+            residual=res_d)
+    pb.run(B)
+    torch.cuda.synchronize()
+    for i in range(4):
+        want = _ref_conv(x, ws[i], scs[i], shs[i], (1, 1), (0, 0), relus[i])
+        o = outs[i]
+        got = to_nchw(o.t[..., o.c0:o.c1])
+        _check(got, want, 'segment %d' % i)
+    assert float(cat.t[..., 64:128].float().abs().max()) == 0.0     # untouched slice of the concat buffer
+    want = _ref_conv(xr, wr, torch.ones(256), torch.zeros(256), (1, 1), (0, 0), True, residual=res)
+    _check(to_nchw(out_r.t), want, 'residual')
+    pb.close()
+
+
+def test_large_batch_many_tiles(cuda):
+    """More tiles than SMs: exercises the persistent loop, both TMEM stages and phase wrap."""
+    from ifcb_classifier_b200.graph import PlanBuilder, View
+    g = torch.Generator().manual_seed(11)
+    B, H, W, Cin, Cout = 40, 35, 35, 96, 96
+    x = torch.randn(B, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, 3, 3, generator=g) / np.sqrt(Cin * 9)
+    pb = PlanBuilder(B, cuda)
+    xin = View(nhwc_dev(x, cuda)); pb.keep.append(xin.t)
+    out = pb.alloc(H, W, Cout)
+    pb.conv(xin, [dict(weight=w, scale=torch.ones(Cout), shift=torch.zeros(Cout), relu=False, out=out)],
+            (1, 1), (1, 1))
+    pb.run(B)
+    torch.cuda.synchronize()
+    _check(to_nchw(out.t), _ref_conv(x, w, torch.ones(Cout), torch.zeros(Cout), (1, 1), (1, 1), False), 'many tiles')
+    pb.close()
+
+
+def test_pools(cuda):
+    from ifcb_classifier_b200.graph import PlanBuilder, View
+    from ifcb_classifier_b200._lib import IFCB_POOL_MAX, IFCB_POOL_AVG_AFFINE
+    g = torch.Generator().manual_seed(2)
+    B = 3
+    x = torch.randn(B, 64, 37, 37, generator=g)
+    pb = PlanBuilder(B, cuda)
+    xin = View(nhwc_dev(x, cuda)); pb.keep.append(xin.t)
+    o1 = pb.alloc(18, 18, 64)
+    pb.pool(IFCB_POOL_MAX, xin, 3, 2, 0, o1)
+    o2 = pb.alloc(19, 19, 64)
+    pb.pool(IFCB_POOL_MAX, xin, 3, 2, 1, o2)
+    cat = pb.alloc(37, 37, 96)
+    sc, sh = torch.rand(64, generator=g) + 0.5, torch.randn(64, generator=g) * 0.3
+    pb.pool(IFCB_POOL_AVG_AFFINE, xin, 3, 1, 1, cat.slice(16, 80), sc, sh, relu=True)
+    pb.run(B)
+    torch.cuda.synchronize()
+    xb = bf16r(x)
+    assert torch.equal(to_nchw(o1.t), F.max_pool2d(xb, 3, 2, 0))
+    assert torch.equal(to_nchw(o2.t), F.max_pool2d(xb, 3, 2, 1))
+    want = torch.relu(F.avg_pool2d(xb, 3, 1, 1) * sc[None, :, None, None] + sh[None, :, None, None])
+    _check(to_nchw(cat.t[..., 16:80]), want, 'avgpool affine')
+    pb.close()
+
+
+def test_stem_u8_and_f32(cuda):
+    from ifcb_classifier_b200.graph import PlanBuilder, input_lut
+    from ifcb_classifier_b200._lib import IFCB_STEM_IN_U8_GRAY, IFCB_STEM_IN_F32_NCHW
+    g = torch.Generator().manual_seed(3)
+    B, R = 2, 61
+    gray = torch.randint(0, 256, (B, R, R), generator=g, dtype=torch.uint8)
+    mean, std = [0.5, 0.4, 0.3], [0.2, 0.25, 0.3]
+    lut = input_lut((mean, std), False)
+    x = torch.stack([lut[c][gray.long()] for c in range(3)], 1)              # [B,3,R,R] float32
+    for (Co, k, stride, pad) in [(32, 3, 2, 0), (64, 7, 2, 3)]:
+        w = torch.randn(Co, 3, k, k, generator=g) / np.sqrt(3 * k * k)
+        sc, sh = torch.rand(Co, generator=g) + 0.5, torch.randn(Co, generator=g) * 0.2
+        want = torch.relu(F.conv2d(x, w, stride=stride, padding=pad) * sc[None, :, None, None] + sh[None, :, None, None])
+        P = (R + 2 * pad - k) // stride + 1
+        for kind, inp in ((IFCB_STEM_IN_U8_GRAY, gray.to(cuda)), (IFCB_STEM_IN_F32_NCHW, x.to(cuda))):
+            pb = PlanBuilder(B, cuda)
+            pb.keep.append(inp)
+            out = pb.alloc(P, P, Co)
+            pb.stem(inp, kind, R, R, w, sc, sh, stride, pad, out, lut=lut)
+            pb.run(B)
+            torch.cuda.synchronize()
+            _check(to_nchw(out.t), want, 'stem %d kind %d' % (Co, kind))
+            pb.close()
+
+
+def test_head_softmax_top1(cuda):
+    from ifcb_classifier_b200.graph import PlanBuilder, View
+    g = torch.Generator().manual_seed(4)
+    B, Cc, HW, K = 5, 2048, 64, 100
+    x = torch.randn(B, Cc, 8, 8, generator=g)
+    w = torch.randn(K, Cc, generator=g) / np.sqrt(Cc)
+    b = torch.randn(K, generator=g) * 0.1
+    pb = PlanBuilder(B, cuda)
+    xin = View(nhwc_dev(x, cuda)); pb.keep.append(xin.t)
+    pb.head(xin, w, b)
+    pb.run(B)
+    torch.cuda.synchronize()
+    pooled = bf16r(x).mean((2, 3))
+    logits = pooled @ w.t() + b
+    want = torch.softmax(logits, 1)
+    got = pb.scores.cpu()
+    assert float((got - want).abs().max()) < 1e-5          # fp32 head: summation order only
+    assert float((pb.logits.cpu() - logits).abs().max()) < 1e-4
+    assert torch.equal(pb.top1.cpu().long(), got.argmax(1))
+    assert torch.equal(pb.top1_score.cpu(), got.max(1).values)
+    assert float((got.sum(1) - 1).abs().max()) < 1e-5
+    pb.close()
