@@ -14,6 +14,7 @@ IFCB_PASS_PILLOW12, IFCB_PASS_HV = 0, 1
 IFCB_STEM_IN_U8_GRAY, IFCB_STEM_IN_F32_NCHW = 0, 1
 IFCB_POOL_MAX, IFCB_POOL_AVG_AFFINE = 0, 1
 IFCB_MAX_SEGMENTS = 4
+IFCB_ACT_BF16, IFCB_ACT_FP16 = 0, 1
 
 
 class ConvSegment(C.Structure):
@@ -28,7 +29,7 @@ class ConvDesc(C.Structure):
                 ('pad_h', C.c_int32), ('pad_w', C.c_int32), ('Cout', C.c_int32),
                 ('d_weight', C.c_void_p), ('d_scale', C.c_void_p), ('d_shift', C.c_void_p),
                 ('n_seg', C.c_int32), ('seg', ConvSegment * IFCB_MAX_SEGMENTS),
-                ('d_residual', C.c_void_p), ('res_ld', C.c_int32), ('tile_n', C.c_int32)]
+                ('d_residual', C.c_void_p), ('res_ld', C.c_int32), ('tile_n', C.c_int32), ('dtype', C.c_int32)]
 
 
 class StemDesc(C.Structure):
@@ -38,7 +39,7 @@ class StemDesc(C.Structure):
                 ('Cout', C.c_int32), ('d_weight', C.c_void_p), ('d_scale', C.c_void_p),
                 ('d_shift', C.c_void_p), ('d_lut', C.c_void_p),
                 ('in_scale', C.c_float * 3), ('in_shift', C.c_float * 3),
-                ('d_out', C.c_void_p), ('out_ld', C.c_int32), ('relu', C.c_int32)]
+                ('d_out', C.c_void_p), ('out_ld', C.c_int32), ('relu', C.c_int32), ('dtype', C.c_int32)]
 
 
 class PoolDesc(C.Structure):
@@ -46,14 +47,15 @@ class PoolDesc(C.Structure):
                 ('batch_cap', C.c_int32), ('H', C.c_int32), ('W', C.c_int32),
                 ('k', C.c_int32), ('stride', C.c_int32), ('pad', C.c_int32),
                 ('d_out', C.c_void_p), ('out_ld', C.c_int32),
-                ('d_scale', C.c_void_p), ('d_shift', C.c_void_p), ('relu', C.c_int32)]
+                ('d_scale', C.c_void_p), ('d_shift', C.c_void_p), ('relu', C.c_int32), ('dtype', C.c_int32)]
 
 
 class HeadDesc(C.Structure):
     _fields_ = [('d_in', C.c_void_p), ('in_ld', C.c_int32), ('C', C.c_int32), ('HW', C.c_int32),
                 ('batch_cap', C.c_int32), ('n_classes', C.c_int32),
                 ('d_weight', C.c_void_p), ('d_bias', C.c_void_p), ('d_scores', C.c_void_p),
-                ('d_logits', C.c_void_p), ('d_top1', C.c_void_p), ('d_top1_score', C.c_void_p)]
+                ('d_logits', C.c_void_p), ('d_top1', C.c_void_p), ('d_top1_score', C.c_void_p),
+                ('dtype', C.c_int32)]
 
 
 # name -> (restype, argtypes); mirrors include/ifcb_b200.h one to one

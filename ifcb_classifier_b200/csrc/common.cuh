@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cstdint>
 #include <cstdio>
 #include <cstdarg>
@@ -43,6 +44,25 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
   return __bfloat1622float2(v);
+}
+
+// 16-bit activation storage: bf16 (dtype 0) or fp16 (dtype 1, saturating).
+__device__ __forceinline__ uint32_t pack_act2(float lo, float hi, int fp16) {
+  if (fp16) {
+    lo = fminf(fmaxf(lo, -65504.f), 65504.f);
+    hi = fminf(fmaxf(hi, -65504.f), 65504.f);
+    __half2 v = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
+  return pack_bf16x2(lo, hi);
+}
+
+__device__ __forceinline__ float2 unpack_act2(uint32_t u, int fp16) {
+  if (fp16) {
+    __half2 v = *reinterpret_cast<__half2*>(&u);
+    return __half22float2(v);
+  }
+  return unpack_bf16x2(u);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -112,7 +112,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      const uint32_t idesc = ptx::umma_idesc_bf16(kBlockM, p.tile_n);
+      const uint32_t idesc = ptx::umma_idesc_f16(kBlockM, p.tile_n, p.fp16);
       int stage = 0;
       uint32_t phase = 0;
       int local = 0;
@@ -183,7 +183,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float2 f = unpack_bf16x2(rr[j]);
+            const float2 f = unpack_act2(rr[j], p.fp16);
             y[2 * j] += f.x;
             y[2 * j + 1] += f.y;
           }
@@ -194,14 +194,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
         if (do_store) {
           uint4 o0, o1;
-          o0.x = pack_bf16x2(y[0], y[1]);
-          o0.y = pack_bf16x2(y[2], y[3]);
-          o0.z = pack_bf16x2(y[4], y[5]);
-          o0.w = pack_bf16x2(y[6], y[7]);
-          o1.x = pack_bf16x2(y[8], y[9]);
-          o1.y = pack_bf16x2(y[10], y[11]);
-          o1.z = pack_bf16x2(y[12], y[13]);
-          o1.w = pack_bf16x2(y[14], y[15]);
+          o0.x = pack_act2(y[0], y[1], p.fp16);
+          o0.y = pack_act2(y[2], y[3], p.fp16);
+          o0.z = pack_act2(y[4], y[5], p.fp16);
+          o0.w = pack_act2(y[6], y[7], p.fp16);
+          o1.x = pack_act2(y[8], y[9], p.fp16);
+          o1.y = pack_act2(y[10], y[11], p.fp16);
+          o1.z = pack_act2(y[12], y[13], p.fp16);
+          o1.w = pack_act2(y[14], y[15], p.fp16);
           uint4* op = reinterpret_cast<uint4*>(p.seg_out[sidx] + m * p.seg_ld[sidx] + (n - p.seg_begin[sidx]));
           op[0] = o0;
           op[1] = o1;

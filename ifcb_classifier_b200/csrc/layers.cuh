@@ -15,6 +15,7 @@ struct ConvKernelParams {
   int cblocks;                 // ceil(Cin / 64)
   int last_ksteps;             // K=16 MMA steps in the last channel block (1..4)
   int tile_n, n_tiles, stages;
+  int fp16;                    // 16-bit operand/activation format: 0 bf16, 1 fp16
   const float* scale;
   const float* shift;
   const __nv_bfloat16* residual;

@@ -128,6 +128,8 @@ extern "C" int ifcb_plan_add_conv(ifcb_plan* plan, const ifcb_conv_desc* d) {
   kp.n_tiles = cout_pad / tile_n;
   kp.stages = conv_pick_stages(tile_n);
   IFCB_ARG_CHECK(kp.stages >= 2, "conv: tile_n=%d leaves fewer than 2 pipeline stages", tile_n);
+  IFCB_ARG_CHECK(d->dtype == IFCB_ACT_BF16 || d->dtype == IFCB_ACT_FP16, "conv: bad dtype %d", d->dtype);
+  kp.fp16 = d->dtype;
   kp.scale = d->d_scale;
   kp.shift = d->d_shift;
   kp.residual = reinterpret_cast<const __nv_bfloat16*>(d->d_residual);
@@ -161,7 +163,7 @@ extern "C" int ifcb_plan_add_conv(ifcb_plan* plan, const ifcb_conv_desc* d) {
     int lower[2] = {-d->pad_w, -d->pad_h};
     int upper[2] = {d->pad_w - (d->kw - 1), d->pad_h - (d->kh - 1)};
     cuuint32_t estr[4] = {1, (cuuint32_t)d->stride_w, (cuuint32_t)d->stride_h, 1};
-    CUresult r = g_encode_im2col(&L.conv.tmap_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d->d_in),
+    CUresult r = g_encode_im2col(&L.conv.tmap_a, d->dtype == IFCB_ACT_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d->d_in),
                                  gdim, gstr, lower, upper, /*channelsPerPixel=*/64, /*pixelsPerColumn=*/128, estr,
                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -180,7 +182,7 @@ extern "C" int ifcb_plan_add_conv(ifcb_plan* plan, const ifcb_conv_desc* d) {
     cuuint64_t gstr[1] = {(cuuint64_t)k_pad * 2};
     cuuint32_t box[2] = {64, (cuuint32_t)tile_n};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = g_encode_tiled(&L.conv.tmap_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(d->d_weight),
+    CUresult r = g_encode_tiled(&L.conv.tmap_b, d->dtype == IFCB_ACT_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(d->d_weight),
                                 gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     IFCB_ARG_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) for weights K_pad=%d Cout_pad=%d", (int)r,

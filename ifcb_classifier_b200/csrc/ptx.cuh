@@ -129,9 +129,11 @@ __device__ __forceinline__ void tmem_ld_wait() {
 __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
   return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
-// kind::f16 instruction descriptor: fp32 accumulate, bf16 A/B, both K-major, M x N.
-__host__ __device__ inline uint32_t umma_idesc_bf16(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// kind::f16 instruction descriptor: fp32 accumulate, A/B both bf16 (format 1) or both
+// fp16 (format 0), both K-major, M x N.
+__host__ __device__ inline uint32_t umma_idesc_f16(int M, int N, int fp16) {
+  const uint32_t fmt = fp16 ? 0u : 1u;
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 }  // namespace ptx

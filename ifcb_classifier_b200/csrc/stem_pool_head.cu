@@ -76,10 +76,10 @@ __global__ void __launch_bounds__(128) stem_kernel(const ifcb_stem_desc d, const
       if (d.relu) y[j] = fmaxf(y[j], 0.f);
     }
     uint4 o;
-    o.x = pack_bf16x2(y[0], y[1]);
-    o.y = pack_bf16x2(y[2], y[3]);
-    o.z = pack_bf16x2(y[4], y[5]);
-    o.w = pack_bf16x2(y[6], y[7]);
+    o.x = pack_act2(y[0], y[1], d.dtype);
+    o.y = pack_act2(y[2], y[3], d.dtype);
+    o.z = pack_act2(y[4], y[5], d.dtype);
+    o.w = pack_act2(y[6], y[7], d.dtype);
     *reinterpret_cast<uint4*>(out + c) = o;
   }
 }
@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(256) pool_kernel(const ifcb_pool_desc d, int P
       const uint32_t u[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float2 f = unpack_bf16x2(u[j]);
+        const float2 f = unpack_act2(u[j], d.dtype);
         if (AVG) {
           a[2 * j] += f.x;
           a[2 * j + 1] += f.y;
@@ -134,10 +134,10 @@ __global__ void __launch_bounds__(256) pool_kernel(const ifcb_pool_desc d, int P
     }
   }
   uint4 o;
-  o.x = pack_bf16x2(a[0], a[1]);
-  o.y = pack_bf16x2(a[2], a[3]);
-  o.z = pack_bf16x2(a[4], a[5]);
-  o.w = pack_bf16x2(a[6], a[7]);
+  o.x = pack_act2(a[0], a[1], d.dtype);
+  o.y = pack_act2(a[2], a[3], d.dtype);
+  o.z = pack_act2(a[4], a[5], d.dtype);
+  o.w = pack_act2(a[6], a[7], d.dtype);
   *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(d.d_out) + pix * d.out_ld + c8 * 8) = o;
 }
 
@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(256) head_kernel(const ifcb_head_desc d) {
       const uint32_t u[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float2 f = unpack_bf16x2(u[j]);
+        const float2 f = unpack_act2(u[j], d.dtype);
         a[2 * j] += f.x;
         a[2 * j + 1] += f.y;
       }

@@ -31,7 +31,7 @@ from ._lib import (ConvDesc, StemDesc, PoolDesc, HeadDesc, IFCB_STEM_IN_U8_GRAY,
 
 
 class View(object):
-    """Channel slice [c0, c1) of an NHWC bf16 activation tensor [B, H, W, C]."""
+    """Channel slice [c0, c1) of an NHWC 16-bit activation tensor [B, H, W, C]."""
 
     def __init__(self, t, c0=0, c1=None):
         self.t = t
@@ -69,19 +69,34 @@ def fold_bn(sd, prefix, eps):
 
 
 class PlanBuilder(object):
-    def __init__(self, batch_cap, device):
+    def __init__(self, batch_cap, device, dtype='fp16'):
+        """``dtype``: 16-bit storage / tensor-core operand format of activations and
+        conv weights -- 'fp16' (default: 11-bit significand, meets the 1e-2 score
+        gate) or 'bf16' (8-bit significand).  Accumulation is fp32 either way."""
+        assert dtype in ('fp16', 'bf16'), dtype
+        self.dtype = dtype
+        self.tdtype = torch.float16 if dtype == 'fp16' else torch.bfloat16
+        self.cdtype = _lib.IFCB_ACT_FP16 if dtype == 'fp16' else _lib.IFCB_ACT_BF16
         self.batch_cap = int(batch_cap)
         self.device = device
         self.keep = []                 # every device tensor the plan points into
         self.layer_names = []
+        self.layer_kinds = []          # 'conv' | 'stem' | 'pool' | 'head', parallel to layer_names
+        self.layer_flops = []          # algorithmic 2*MACs per image of each layer
         handle = C.c_void_p()
         _lib.check(_lib.lib().ifcb_plan_create(C.byref(handle)), 'plan_create')
         self.handle = handle
         self.flops_per_image = 0       # 2*MACs of the reference graph (algorithmic)
 
+    def _note(self, name, kind, flops):
+        self.layer_names.append(name)
+        self.layer_kinds.append(kind)
+        self.layer_flops.append(flops)
+        self.flops_per_image += flops
+
     # -- memory ---------------------------------------------------------------
     def alloc(self, H, W, Cc):
-        t = torch.zeros((self.batch_cap, H, W, Cc), dtype=torch.bfloat16, device=self.device)
+        t = torch.zeros((self.batch_cap, H, W, Cc), dtype=self.tdtype, device=self.device)
         self.keep.append(t)
         return View(t)
 
@@ -104,7 +119,7 @@ class PlanBuilder(object):
         wcat = torch.cat([m['weight'].float() for m in members], 0)          # [Co, Ci, kh, kw]
         packed = torch.zeros((Np, kh * kw, Cp), dtype=torch.float32)
         packed[:Co, :, :Ci] = wcat.permute(0, 2, 3, 1).reshape(Co, kh * kw, Ci)
-        wdev = self.dev(packed.reshape(Np, Kp), torch.bfloat16)
+        wdev = self.dev(packed.reshape(Np, Kp), self.tdtype)
         scale = torch.zeros(Np); shift = torch.zeros(Np)
         scale[:Co] = torch.cat([m['scale'].float() for m in members])
         shift[:Co] = torch.cat([m['shift'].float() for m in members])
@@ -129,9 +144,9 @@ class PlanBuilder(object):
         if residual is not None:
             d.d_residual, d.res_ld = residual.ptr, residual.ld
         d.tile_n = tile_n
+        d.dtype = self.cdtype
         _lib.check(_lib.lib().ifcb_plan_add_conv(self.handle, C.byref(d)), 'plan_add_conv(%s)' % name)
-        self.layer_names.append(name)
-        self.flops_per_image += 2 * P * Q * Co * Ci * kh * kw
+        self._note(name, 'conv', 2 * P * Q * Co * Ci * kh * kw)
         return [m['out'] for m in members]
 
     def stem(self, inp, in_kind, H, W, weight, scale, shift, stride, pad, out, lut=None,
@@ -149,9 +164,9 @@ class PlanBuilder(object):
         for c in range(3):
             d.in_scale[c], d.in_shift[c] = float(in_scale[c]), float(in_shift[c])
         d.d_out, d.out_ld, d.relu = out.ptr, out.ld, 1
+        d.dtype = self.cdtype
         _lib.check(_lib.lib().ifcb_plan_add_stem(self.handle, C.byref(d)), 'plan_add_stem')
-        self.layer_names.append(name)
-        self.flops_per_image += 2 * out.H * out.W * Co * 3 * kh * kw
+        self._note(name, 'stem', 2 * out.H * out.W * Co * 3 * kh * kw)
         return out
 
     def pool(self, kind, x, k, stride, pad, out, scale=None, shift=None, relu=False, name='pool'):
@@ -163,8 +178,9 @@ class PlanBuilder(object):
             d.d_scale = self.dev(scale, torch.float32).data_ptr()
             d.d_shift = self.dev(shift, torch.float32).data_ptr()
         d.relu = 1 if relu else 0
+        d.dtype = self.cdtype
         _lib.check(_lib.lib().ifcb_plan_add_pool(self.handle, C.byref(d)), 'plan_add_pool(%s)' % name)
-        self.layer_names.append(name)
+        self._note(name, 'pool', 0)
         return out
 
     def head(self, x, weight, bias, name='head'):
@@ -181,9 +197,9 @@ class PlanBuilder(object):
         d.d_bias = self.dev(bias, torch.float32).data_ptr()
         d.d_scores, d.d_logits = self.scores.data_ptr(), self.logits.data_ptr()
         d.d_top1, d.d_top1_score = self.top1.data_ptr(), self.top1_score.data_ptr()
+        d.dtype = self.cdtype
         _lib.check(_lib.lib().ifcb_plan_add_head(self.handle, C.byref(d)), 'plan_add_head')
-        self.layer_names.append(name)
-        self.flops_per_image += 2 * x.C * n_classes
+        self._note(name, 'head', 2 * x.C * n_classes)
         return self.scores
 
     def run(self, batch, first=None, last=None):
@@ -423,14 +439,15 @@ class CompiledNet(object):
     """
 
     def __init__(self, arch, state_dict, batch_cap, in_kind='u8', R=None, img_norm=None,
-                 transform_input=False, device='cuda', fuse=True):
+                 transform_input=False, device='cuda', fuse=True, dtype='fp16'):
         self.arch = arch
         self.R = R or (299 if arch == 'inception_v3' else 224)
         self.in_kind = in_kind
         self.batch_cap = int(batch_cap)
         self.device = torch.device(device)
         sd = {k: v.detach().cpu() for k, v in state_dict.items()}
-        pb = PlanBuilder(batch_cap, self.device)
+        pb = PlanBuilder(batch_cap, self.device, dtype)
+        self.dtype = dtype
         if in_kind == 'u8':
             self.inp = torch.zeros((batch_cap, self.R, self.R), dtype=torch.uint8, device=self.device)
             kind = IFCB_STEM_IN_U8_GRAY

@@ -16,7 +16,8 @@
  *     path.  Pointers prefixed d_ are device pointers, h_ are host pointers.
  *   - Every call is asynchronous on the cudaStream_t passed as `stream`
  *     (a void* so that this header needs no CUDA include).
- *   - Activations are NHWC bf16; a tensor view is (base pointer, pixel stride
+ *   - Activations are NHWC 16-bit floats (bf16 or fp16, one format per plan:
+ *     every layer descriptor carries `dtype` = IFCB_ACT_*); a tensor view is (base pointer, pixel stride
  *     `ld` in elements, channels) so that a layer can read or write a channel
  *     slice of a wider (concatenated) tensor in place.
  */
@@ -79,6 +80,10 @@ int ifcb_preprocess(const uint8_t* d_packed, int64_t packed_bytes,
  * ------------------------------------------------------------------------- */
 typedef struct ifcb_plan ifcb_plan;
 
+/* 16-bit storage / tensor-core operand format of activations and conv weights.
+ * Accumulation is always fp32 (TMEM); BN scale/shift, the stem and the head are fp32. */
+enum { IFCB_ACT_BF16 = 0, IFCB_ACT_FP16 = 1 };
+
 int ifcb_plan_create(ifcb_plan** out);
 int ifcb_plan_destroy(ifcb_plan* plan);
 /* Launches every layer for `batch` images (batch <= the capacity the layers
@@ -126,6 +131,7 @@ typedef struct {
   const void* d_residual;
   int32_t res_ld;
   int32_t tile_n;
+  int32_t dtype; /* IFCB_ACT_* of input, weights, residual and outputs */
 } ifcb_conv_desc;
 
 int ifcb_plan_add_conv(ifcb_plan* plan, const ifcb_conv_desc* desc);
@@ -159,6 +165,7 @@ typedef struct {
   void* d_out;
   int32_t out_ld;
   int32_t relu;
+  int32_t dtype; /* IFCB_ACT_* of the output */
 } ifcb_stem_desc;
 int ifcb_plan_add_stem(ifcb_plan* plan, const ifcb_stem_desc* desc);
 
@@ -180,6 +187,7 @@ typedef struct {
   const float* d_scale; /* AVG_AFFINE only */
   const float* d_shift;
   int32_t relu;
+  int32_t dtype; /* IFCB_ACT_* of input and output */
 } ifcb_pool_desc;
 int ifcb_plan_add_pool(ifcb_plan* plan, const ifcb_pool_desc* desc);
 
@@ -202,6 +210,7 @@ typedef struct {
   float* d_logits;
   int32_t* d_top1;
   float* d_top1_score;
+  int32_t dtype; /* IFCB_ACT_* of the input */
 } ifcb_head_desc;
 int ifcb_plan_add_head(ifcb_plan* plan, const ifcb_head_desc* desc);
 

@@ -80,7 +80,7 @@ def test_im2col_tma_probe(cuda):
                                              (80, 7, 7, 1, 7, (1, 1), (0, 3))]:
         B = 4
         x = torch.randn(B, Cin, H, W)
-        pb = PlanBuilder(B, cuda)
+        pb = PlanBuilder(B, cuda, 'bf16')
         xin = View(nhwc_dev(x, cuda)); pb.keep.append(xin.t)
         P = (H + 2 * pad[0] - kh) // stride[0] + 1
         Q = (W + 2 * pad[1] - kw) // stride[1] + 1
@@ -120,7 +120,7 @@ def test_conv_bn_relu(cuda, case):
     scale = torch.rand(Cout, generator=g) + 0.5
     shift = torch.randn(Cout, generator=g) * 0.2
     cap = B + 1                                            # run with batch < capacity
-    pb = PlanBuilder(cap, cuda)
+    pb = PlanBuilder(cap, cuda, 'bf16')
     xin_t = torch.zeros((cap, H, W, Cin), dtype=torch.bfloat16, device=cuda)
     xin_t[:B] = nhwc_dev(x, cuda)
     pb.keep.append(xin_t)
@@ -148,7 +148,7 @@ def test_conv_fused_segments_slices_and_residual(cuda):
     ws = [torch.randn(c, Cin, 1, 1, generator=g) / np.sqrt(Cin) for c in couts]
     scs = [torch.rand(c, generator=g) + 0.5 for c in couts]
     shs = [torch.randn(c, generator=g) * 0.2 for c in couts]
-    pb = PlanBuilder(B, cuda)
+    pb = PlanBuilder(B, cuda, 'bf16')
     wide = nhwc_dev(x, cuda, c_total=256, c0=32); pb.keep.append(wide)
     xin = View(wide, 32, 32 + Cin)
     cat = pb.alloc(H, W, 256)
@@ -184,7 +184,7 @@ def test_large_batch_many_tiles(cuda):
     B, H, W, Cin, Cout = 40, 35, 35, 96, 96
     x = torch.randn(B, Cin, H, W, generator=g)
     w = torch.randn(Cout, Cin, 3, 3, generator=g) / np.sqrt(Cin * 9)
-    pb = PlanBuilder(B, cuda)
+    pb = PlanBuilder(B, cuda, 'bf16')
     xin = View(nhwc_dev(x, cuda)); pb.keep.append(xin.t)
     out = pb.alloc(H, W, Cout)
     pb.conv(xin, [dict(weight=w, scale=torch.ones(Cout), shift=torch.zeros(Cout), relu=False, out=out)],
@@ -201,7 +201,7 @@ def test_pools(cuda):
     g = torch.Generator().manual_seed(2)
     B = 3
     x = torch.randn(B, 64, 37, 37, generator=g)
-    pb = PlanBuilder(B, cuda)
+    pb = PlanBuilder(B, cuda, 'bf16')
     xin = View(nhwc_dev(x, cuda)); pb.keep.append(xin.t)
     o1 = pb.alloc(18, 18, 64)
     pb.pool(IFCB_POOL_MAX, xin, 3, 2, 0, o1)
@@ -235,7 +235,7 @@ def test_stem_u8_and_f32(cuda):
         want = torch.relu(F.conv2d(x, w, stride=stride, padding=pad) * sc[None, :, None, None] + sh[None, :, None, None])
         P = (R + 2 * pad - k) // stride + 1
         for kind, inp in ((IFCB_STEM_IN_U8_GRAY, gray.to(cuda)), (IFCB_STEM_IN_F32_NCHW, x.to(cuda))):
-            pb = PlanBuilder(B, cuda)
+            pb = PlanBuilder(B, cuda, 'bf16')
             pb.keep.append(inp)
             out = pb.alloc(P, P, Co)
             pb.stem(inp, kind, R, R, w, sc, sh, stride, pad, out, lut=lut)
@@ -252,7 +252,7 @@ def test_head_softmax_top1(cuda):
     x = torch.randn(B, Cc, 8, 8, generator=g)
     w = torch.randn(K, Cc, generator=g) / np.sqrt(Cc)
     b = torch.randn(K, generator=g) * 0.1
-    pb = PlanBuilder(B, cuda)
+    pb = PlanBuilder(B, cuda, 'bf16')
     xin = View(nhwc_dev(x, cuda)); pb.keep.append(xin.t)
     pb.head(xin, w, b)
     pb.run(B)
@@ -266,4 +266,25 @@ def test_head_softmax_top1(cuda):
     assert torch.equal(pb.top1.cpu().long(), got.argmax(1))
     assert torch.equal(pb.top1_score.cpu(), got.max(1).values)
     assert float((got.sum(1) - 1).abs().max()) < 1e-5
+    pb.close()
+
+
+def test_conv_fp16_operands(cuda):
+    """Same kernel with fp16 operands/activations (the default RUN format)."""
+    from ifcb_classifier_b200.graph import PlanBuilder, View
+    g = torch.Generator().manual_seed(21)
+    B, Cin, H, W, Cout = 3, 160, 17, 17, 192
+    x = torch.randn(B, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, 1, 7, generator=g) / np.sqrt(Cin * 7)
+    sc, sh = torch.rand(Cout, generator=g) + 0.5, torch.randn(Cout, generator=g) * 0.2
+    pb = PlanBuilder(B, cuda, 'fp16')
+    xin = View(x.permute(0, 2, 3, 1).contiguous().to(cuda).half()); pb.keep.append(xin.t)
+    out = pb.alloc(H, W, Cout)
+    pb.conv(xin, [dict(weight=w, scale=sc, shift=sh, relu=True, out=out)], (1, 1), (0, 3))
+    pb.run(B)
+    torch.cuda.synchronize()
+    y = F.conv2d(x.half().float(), w.half().float(), padding=(0, 3))
+    want = torch.relu(y * sc[None, :, None, None] + sh[None, :, None, None])
+    err = (to_nchw(out.t) - want).abs()
+    assert bool((err <= 2e-3 * want.abs() + 2e-3).all()), float(err.max())      # fp16: 2^-11 relative
     pb.close()
