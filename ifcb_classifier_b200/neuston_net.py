@@ -1,0 +1,219 @@
+#!/usr/bin/env python
+"""``neuston_net.py``-compatible command line (reference neuston_net.py:311-452).
+
+  python -m ifcb_classifier_b200.neuston_net [--batch N] [--loaders N] RUN SRC MODEL RUN_ID
+         [--type bin|img] [--outdir ...] [--outfile ...]... [--filter IN|OUT KW...] [--clobber] [--gobig]
+  torchrun --nproc-per-node 8 -m ifcb_classifier_b200.neuston_net RUN ...   # bins sharded across GPUs
+
+Same flags, defaults and path templates ({RUN_ID} {RUN_DATE} {MODEL_ID} {BIN_ID} {BIN_YEAR}
+{BIN_DATE} {INPUT_SUBDIRS}).  The loop that pytorch_lightning's Trainer ran is
+``engine.BinClassifier``; per-bin error isolation and skip-if-exists are preserved
+(neuston_net.py:242-251,258-268).  TRAIN's flags parse, but the training step is not built
+in this round and exits with a clear message.
+"""
+import argparse
+import datetime as dt
+import os
+import sys
+import time
+
+
+def argparse_nn(parser=None):
+    if parser is None:
+        parser = argparse.ArgumentParser(description='Train and run IFCB image classifiers on B200 GPUs')
+    sub = parser.add_subparsers(dest='cmd_mode', help='optional arguments below must precede TRAIN / RUN')
+    train = sub.add_parser('TRAIN', help='Train a new model')
+    run = sub.add_parser('RUN', help='Run a previously trained model')
+    common = parser.add_argument_group(title='NN Common Args')
+    common.add_argument('--batch', dest='batch_size', metavar='SIZE', default=108, type=int)
+    common.add_argument('--loaders', metavar='N', default=4, type=int)
+    common.add_argument('--dtype', default='fp16', choices=['fp16', 'bf16'],
+                        help='tensor-core operand format (B200 extension; default fp16)')
+    _train_args(train)
+    _run_args(run)
+    return parser
+
+
+def _train_args(p):
+    p.add_argument('SRC'); p.add_argument('MODEL'); p.add_argument('TRAIN_ID')
+    p.add_argument('--untrain', dest='pretrained', default=True, action='store_false')
+    p.add_argument('--img-norm', nargs=2, metavar=('MEAN', 'STD'))
+    p.add_argument('--seed', default=0, type=int)
+    p.add_argument('--split', metavar='T:V', default='80:20')
+    p.add_argument('--class-config', metavar=('CSV', 'COL'), nargs=2)
+    p.add_argument('--class-min', metavar='MIN', default=2, type=int)
+    p.add_argument('--class-max', metavar='MAX', default=None, type=int)
+    p.add_argument('--swap', default=False, action='store_true', help=argparse.SUPPRESS)
+    p.add_argument('--emax', metavar='MAX', default=60, type=int)
+    p.add_argument('--emin', metavar='MIN', default=10, type=int)
+    p.add_argument('--estop', metavar='STOP', default=10, type=int)
+    p.add_argument('--flip', choices=['x', 'y', 'xy', 'x+V', 'y+V', 'xy+V'])
+    p.add_argument('--outdir', default='training-output/{TRAIN_ID}')
+    p.add_argument('--model-id', default='{TRAIN_ID}')
+    p.add_argument('--epochs-log', metavar='ELOG', default='epochs.csv')
+    p.add_argument('--args-log', metavar='ALOG', default='args.yml')
+    p.add_argument('--onnx', action='store_true')
+    p.add_argument('--results', dest='result_files', metavar=('FNAME', 'SERIES'), nargs='+', action='append')
+    p.add_argument('--dataset-id'); p.add_argument('--notes')
+
+
+def _run_args(p):
+    p.add_argument('SRC'); p.add_argument('MODEL'); p.add_argument('RUN_ID')
+    p.add_argument('--type', dest='src_type', default='bin', choices=['bin', 'img'])
+    p.add_argument('--outdir', default='run-output/{RUN_ID}/v3/{MODEL_ID}')
+    p.add_argument('--outfile', action='append')
+    p.add_argument('--filter', nargs='+', metavar=('IN|OUT', 'KEYWORD'))
+    p.add_argument('--clobber', action='store_true')
+    p.add_argument('--gobig', action='store_true', help=argparse.SUPPRESS)
+
+
+def argparse_nn_runtimeparams(args, classifier=None):
+    args.cmd_timestamp = dt.datetime.now(dt.timezone.utc).isoformat(timespec='seconds')
+    try:
+        with open('version') as f:
+            args.version = f.read().strip()
+    except FileNotFoundError:
+        args.version = None
+    import torch
+    if torch.cuda.is_available():
+        vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+        args.gpus = [int(g) for g in vis.split(',')] if vis else list(range(torch.cuda.device_count()))
+    else:
+        args.gpus = None
+    date_str = args.cmd_timestamp.split('T')[0]
+    if args.cmd_mode == 'TRAIN':
+        args.outdir = args.outdir.format(TRAIN_DATE=date_str, TRAIN_ID=args.TRAIN_ID)
+    elif args.cmd_mode == 'RUN':
+        model_id = getattr(classifier.hparams, 'model_id', None) if classifier is not None else None
+        args.outdir = args.outdir.format(RUN_DATE=date_str, RUN_ID=args.RUN_ID, MODEL_ID=model_id)
+
+
+def do_run(args, classifier=None):
+    import torch
+    from . import ifcb_io, results, sharding
+    from .engine import BinClassifier
+    from .neuston_models import NeustonModel
+    from .preprocess import parse_imgnorm
+
+    if args.filter:
+        if args.filter[0] not in ['IN', 'OUT']:
+            raise argparse.ArgumentTypeError('IN|OUT must be either "IN" or "OUT"')
+        if len(args.filter) < 2:
+            raise argparse.ArgumentTypeError('Must be at least one KEYWORD')
+    if args.src_type != 'bin':
+        raise NotImplementedError('--type img is outside the per-bin hot path (DESIGN.md, out of scope)')
+    if classifier is None:
+        classifier = NeustonModel.load_from_checkpoint(args.MODEL)
+    hp = classifier.hparams
+    torch.manual_seed(getattr(hp, 'seed', 0) or 0)
+    if os.path.isdir(args.SRC) and not args.SRC.endswith(os.sep):
+        args.SRC = args.SRC + os.sep
+    if not args.outfile:
+        args.outfile = ['D{BIN_YEAR}/D{BIN_DATE}/{BIN_ID}_class.h5']
+
+    rank, world, local_rank = sharding.env_rank_world()
+    if not torch.cuda.is_available():
+        raise RuntimeError('RUN needs a CUDA device: the B200 path has no CPU fallback')
+    torch.cuda.set_device(local_rank)
+    if world > 1 and not torch.distributed.is_initialized():
+        torch.distributed.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+
+    filter_mode, keywords = None, []
+    if args.filter:
+        filter_mode = args.filter[0]
+        for kw in args.filter[1:]:
+            if os.path.isfile(kw):
+                with open(kw) as f:
+                    keywords.extend(f.read().splitlines())
+            else:
+                keywords.append(kw)
+    if os.path.isdir(args.SRC):
+        root = args.SRC
+        dd = ifcb_io.DataDirectory(root, whitelist=keywords if filter_mode == 'IN' else None,
+                                   blacklist=keywords if filter_mode == 'OUT' else None)
+    elif os.path.isfile(args.SRC) and args.SRC.endswith('.txt'):
+        with open(args.SRC) as f:
+            bins = f.read().splitlines()
+        root = os.path.commonpath(bins)
+        dd = ifcb_io.DataDirectory(root, whitelist=bins)
+    else:
+        root = os.path.dirname(args.SRC)
+        dd = ifcb_io.DataDirectory(root, whitelist=[os.path.basename(args.SRC)])
+
+    todo = []
+    for base in dd.basepaths():
+        pid = ifcb_io.Pid(os.path.basename(base))
+        pid.namespace = os.path.dirname(base.replace(args.SRC, '')) + os.sep
+        if filter_mode == 'IN' and not any(k in str(pid) for k in keywords):
+            continue
+        if filter_mode == 'OUT' and any(k in str(pid) for k in keywords):
+            continue
+        if not args.clobber:
+            outs = [results.outfile_path(args.outdir, of, pid) for of in args.outfile]
+            if all(os.path.isfile(o) for o in outs):
+                if rank == 0:
+                    print('{} result-file(s) already exist - skipping this bin'.format(pid))
+                continue
+        todo.append((base, pid))
+    mine = set(sharding.my_bins([b for b, _ in todo], rank, world))
+
+    img_norm = parse_imgnorm(hp.img_norm) if getattr(hp, 'img_norm', None) else None
+    eng = BinClassifier(hp.MODEL, classifier.model.state_dict(), img_norm=img_norm,
+                        transform_input=classifier.model.transform_input, device=torch.device('cuda', local_rank),
+                        batch_cap=max(args.batch_size, 16), dtype=args.dtype)
+    error_bins, n_bins, n_rois, t0 = [], 0, 0, time.time()
+    for base, pid in todo:
+        if base not in mine:
+            continue
+        try:
+            rb = ifcb_io.RawBin(base)
+            rb.pid.namespace = pid.namespace
+            if len(rb) == 0:
+                error_bins.append((str(pid), 'AssertionError', 'Bin is Empty'))
+                continue
+            scores, top1 = eng.classify_bin(rb.roi, rb.offsets, rb.heights, rb.widths)
+            for of in args.outfile:
+                results.save_run_results(rb.pids, scores.copy(), hp.classes, args.cmd_timestamp, args.outdir, of,
+                                         getattr(hp, 'model_id', None), rb.pid, output_classes=top1.copy())
+            n_bins += 1
+            n_rois += len(rb)
+        except Exception as e:      # per-bin isolation, as the reference
+            error_bins.append((str(pid), type(e).__name__, str(e)))
+    summary = dict(rank=rank, n_bins=n_bins, n_rois=n_rois, seconds=time.time() - t0, error_bins=error_bins)
+    allsum = sharding.gather_summary(summary, world)
+    if rank == 0:
+        print('RUN IS DONE')
+        tot_b, tot_r = sum(s['n_bins'] for s in allsum), sum(s['n_rois'] for s in allsum)
+        print('%d bins, %d ROIs on %d GPU(s) in %.1f s' % (tot_b, tot_r, world, max(s['seconds'] for s in allsum)))
+        errs = [e for s in allsum for e in s['error_bins']]
+        if errs:
+            print('The following bins failed; they were not processed:')
+            for b, t, m in errs:
+                print(b, t, m)
+    return allsum
+
+
+def do_training(args):
+    raise NotImplementedError('TRAIN (forward/backward/Adam + NCCL all-reduce on sm_100a kernels) is not built in '
+                              'this round; see DESIGN.md "Scope and status"')
+
+
+def main(argv=None):
+    parser = argparse_nn()
+    args = parser.parse_args(argv)
+    if args.cmd_mode == 'RUN':
+        from .neuston_models import NeustonModel
+        classifier = NeustonModel.load_from_checkpoint(args.MODEL)
+        argparse_nn_runtimeparams(args, classifier)
+        do_run(args, classifier)
+    elif args.cmd_mode == 'TRAIN':
+        argparse_nn_runtimeparams(args)
+        do_training(args)
+    else:
+        parser.print_help()
+        return 2
+    return 0
+
+
+if __name__ == '__main__':
+    sys.exit(main())
