@@ -33,6 +33,8 @@ constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KB
 constexpr int kThreads = 192;
 constexpr int kTmemCols = 512;
 constexpr int kAccStageCols = 256;
+// barriers (256 B) + scale/shift (2 x cout_pad floats) + 4 x 4 KB staging tiles
+__host__ __device__ constexpr int kEpilogueSmem(int cout_pad) { return 256 + 8 * cout_pad + 4 * 4096; }
 
 __global__ void __launch_bounds__(kThreads, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -48,6 +50,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   uint64_t* tmem_full = empty_bar + p.stages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  // epilogue scratch: folded-BN scale/shift for every GEMM column of this layer, and a
+  // private 32-row x 128-byte staging tile per epilogue warp (swizzled, conflict free)
+  float* s_scale = reinterpret_cast<float*>(bar_base + 256);
+  float* s_shift = s_scale + p.cout_pad;
+  uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_shift + p.cout_pad);      // 4 warps x 4 KB, 16-byte aligned
+  for (int i = threadIdx.x; i < p.cout_pad; i += kThreads) {
+    s_scale[i] = p.scale[i];
+    s_shift[i] = p.shift[i];
+  }
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -143,8 +154,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
+    // TMEM -> registers -> affine/ReLU -> 16-bit -> per-warp swizzled smem tile -> coalesced
+    // 16-byte global stores (4 full 128-byte lines per warp instruction for a 64-column group).
     const int quad = warp & 3;                     // TMEM lane quadrant this warp may access
-    const int row = quad * 32 + lane;
+    uint8_t* stage = s_stage + (warp - 2) * 4096;
+    const uint32_t stage_addr = ptx::smem_u32(stage);
     int local = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
       const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
@@ -152,61 +166,74 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const uint32_t acc_phase = (local >> 1) & 1;
       ptx::mbar_wait(tmem_full + acc, acc_phase);
       ptx::tc_fence_after();
-      const long long m = (long long)m_tile * kBlockM + row;
+      const long long m_warp = (long long)m_tile * kBlockM + quad * 32;      // first row of this warp
+      const long long m = m_warp + lane;
       const bool row_ok = m < p.M;
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * kAccStageCols);
-      for (int c0 = 0; c0 < p.tile_n; c0 += 16) {
-        uint32_t v[16];
-        ptx::tmem_ld_32x32b_x16(taddr + (uint32_t)c0, v);
-        ptx::tmem_ld_wait();
-        const int n = n_tile * p.tile_n + c0;
-        int si = -1;
+      const int n_lo = n_tile * p.tile_n, n_hi = n_lo + p.tile_n;
+      for (int si = 0; si < p.n_seg; ++si) {
+        const int g_lo = max(n_lo, p.seg_begin[si]), g_hi = min(n_hi, p.seg_end[si]);
+        const int relu = p.seg_relu[si];
+        for (int g0 = g_lo; g0 < g_hi; g0 += 64) {            // group of up to 4 chunks of 16 columns
+          const int nch = min(4, (g_hi - g0) >> 4);
+          for (int ch = 0; ch < nch; ++ch) {
+            const int n = g0 + ch * 16;
+            uint32_t v[16];
+            ptx::tmem_ld_32x32b_x16(taddr + (uint32_t)(n - n_lo), v);
+            ptx::tmem_ld_wait();
+            float y[16];
 #pragma unroll
-        for (int s = 0; s < IFCB_MAX_SEGMENTS; ++s)
-          if (s < p.n_seg && n >= p.seg_begin[s] && n < p.seg_end[s]) si = s;
-        const bool do_store = (si >= 0) && row_ok;
-        const int sidx = si < 0 ? 0 : si;
-        const float4* sc4 = reinterpret_cast<const float4*>(p.scale + n);
-        const float4* sh4 = reinterpret_cast<const float4*>(p.shift + n);
-        float y[16];
+            for (int j = 0; j < 4; ++j) {
+              const float4 sc = *reinterpret_cast<const float4*>(s_scale + n + 4 * j);
+              const float4 sh = *reinterpret_cast<const float4*>(s_shift + n + 4 * j);
+              y[4 * j + 0] = fmaf(__uint_as_float(v[4 * j + 0]), sc.x, sh.x);
+              y[4 * j + 1] = fmaf(__uint_as_float(v[4 * j + 1]), sc.y, sh.y);
+              y[4 * j + 2] = fmaf(__uint_as_float(v[4 * j + 2]), sc.z, sh.z);
+              y[4 * j + 3] = fmaf(__uint_as_float(v[4 * j + 3]), sc.w, sh.w);
+            }
+            if (p.residual != nullptr && row_ok) {
+              const uint4* rp = reinterpret_cast<const uint4*>(p.residual + m * p.res_ld + n);
+              const uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+              const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float4 sc = __ldg(sc4 + j), sh = __ldg(sh4 + j);
-          y[4 * j + 0] = fmaf(__uint_as_float(v[4 * j + 0]), sc.x, sh.x);
-          y[4 * j + 1] = fmaf(__uint_as_float(v[4 * j + 1]), sc.y, sh.y);
-          y[4 * j + 2] = fmaf(__uint_as_float(v[4 * j + 2]), sc.z, sh.z);
-          y[4 * j + 3] = fmaf(__uint_as_float(v[4 * j + 3]), sc.w, sh.w);
-        }
-        if (p.residual != nullptr && do_store) {
-          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + m * p.res_ld + n);
-          const uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
-          const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+              for (int j = 0; j < 8; ++j) {
+                const float2 f = unpack_act2(rr[j], p.fp16);
+                y[2 * j] += f.x;
+                y[2 * j + 1] += f.y;
+              }
+            }
+            if (relu) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float2 f = unpack_act2(rr[j], p.fp16);
-            y[2 * j] += f.x;
-            y[2 * j + 1] += f.y;
+              for (int j = 0; j < 16; ++j) y[j] = fmaxf(y[j], 0.f);
+            }
+            uint4 o0, o1;
+            o0.x = pack_act2(y[0], y[1], p.fp16);
+            o0.y = pack_act2(y[2], y[3], p.fp16);
+            o0.z = pack_act2(y[4], y[5], p.fp16);
+            o0.w = pack_act2(y[6], y[7], p.fp16);
+            o1.x = pack_act2(y[8], y[9], p.fp16);
+            o1.y = pack_act2(y[10], y[11], p.fp16);
+            o1.z = pack_act2(y[12], y[13], p.fp16);
+            o1.w = pack_act2(y[14], y[15], p.fp16);
+            // row `lane`, 16-byte pieces 2*ch and 2*ch+1, XOR-swizzled by (row & 7)
+            const uint32_t rbase = stage_addr + (uint32_t)lane * 128u;
+            const uint32_t sw = (uint32_t)(lane & 7);
+            ptx::st_shared_v4(rbase + ((((uint32_t)(2 * ch)) ^ sw) << 4), o0);
+            ptx::st_shared_v4(rbase + ((((uint32_t)(2 * ch + 1)) ^ sw) << 4), o1);
           }
+          __syncwarp();
+          // coalesced write-out: `ppr` 16-byte pieces per row, 32 rows
+          const int ppr = 2 * nch;
+          __nv_bfloat16* gout = p.seg_out[si] + (g0 - p.seg_begin[si]);
+          const int ld = p.seg_ld[si];
+          for (int idx = lane; idx < 32 * ppr; idx += 32) {
+            const int r = idx / ppr, pc = idx - r * ppr;
+            const uint4 val = ptx::ld_shared_v4(stage_addr + (uint32_t)r * 128u + ((((uint32_t)pc) ^ (uint32_t)(r & 7)) << 4));
+            if (m_warp + r < p.M)
+              *reinterpret_cast<uint4*>(gout + (m_warp + r) * ld + pc * 8) = val;
+          }
+          __syncwarp();
         }
-        if (p.seg_relu[sidx]) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) y[j] = fmaxf(y[j], 0.f);
-        }
-        if (do_store) {
-          uint4 o0, o1;
-          o0.x = pack_act2(y[0], y[1], p.fp16);
-          o0.y = pack_act2(y[2], y[3], p.fp16);
-          o0.z = pack_act2(y[4], y[5], p.fp16);
-          o0.w = pack_act2(y[6], y[7], p.fp16);
-          o1.x = pack_act2(y[8], y[9], p.fp16);
-          o1.y = pack_act2(y[10], y[11], p.fp16);
-          o1.z = pack_act2(y[12], y[13], p.fp16);
-          o1.w = pack_act2(y[14], y[15], p.fp16);
-          uint4* op = reinterpret_cast<uint4*>(p.seg_out[sidx] + m * p.seg_ld[sidx] + (n - p.seg_begin[sidx]));
-          op[0] = o0;
-          op[1] = o1;
-        }
-        __syncwarp();
       }
       ptx::tc_fence_before();
       __syncwarp();
@@ -221,13 +248,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
 }  // namespace
 
-int conv_smem_bytes(int tile_n, int stages) {
-  return stages * (kATileBytes + tile_n * kBlockK * 2) + 256 + 1024;
+int conv_smem_bytes(int tile_n, int stages, int cout_pad) {
+  return stages * (kATileBytes + tile_n * kBlockK * 2) + kEpilogueSmem(cout_pad) + 1024;
 }
 
-int conv_pick_stages(int tile_n) {
+int conv_pick_stages(int tile_n, int cout_pad) {
   const int budget = 227 * 1024;
-  int s = (budget - 256 - 1024) / (kATileBytes + tile_n * kBlockK * 2);
+  int s = (budget - kEpilogueSmem(cout_pad) - 1024) / (kATileBytes + tile_n * kBlockK * 2);
   if (s > 8) s = 8;
   return s;
 }
@@ -239,7 +266,7 @@ int launch_conv(const ConvLayer& L, int batch, cudaStream_t stream) {
   const int total = m_tiles * p.n_tiles;
   if (total == 0) return 0;
   int grid = total < sm_count() ? total : sm_count();
-  const int smem = conv_smem_bytes(p.tile_n, p.stages);
+  const int smem = conv_smem_bytes(p.tile_n, p.stages, p.cout_pad);
   static int attr_smem = 0;
   if (smem > attr_smem) {
     IFCB_CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

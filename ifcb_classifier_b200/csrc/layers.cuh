@@ -15,6 +15,7 @@ struct ConvKernelParams {
   int cblocks;                 // ceil(Cin / 64)
   int last_ksteps;             // K=16 MMA steps in the last channel block (1..4)
   int tile_n, n_tiles, stages;
+  int cout_pad;                // n_tiles * tile_n
   int fp16;                    // 16-bit operand/activation format: 0 bf16, 1 fp16
   const float* scale;
   const float* shift;
@@ -48,10 +49,10 @@ struct HeadLayer {
 };
 
 int launch_conv(const ConvLayer& L, int batch, cudaStream_t stream);
-int conv_pick_stages(int tile_n);
+int conv_pick_stages(int tile_n, int cout_pad);
 int launch_im2col_probe(const ConvLayer& L, int c, int w, int h, int n, int off_w, int off_h, void* d_out,
                         cudaStream_t stream);
-int conv_smem_bytes(int tile_n, int stages);
+int conv_smem_bytes(int tile_n, int stages, int cout_pad);
 int launch_stem(const StemLayer& L, int batch, cudaStream_t stream);
 int launch_pool(const PoolLayer& L, int batch, cudaStream_t stream);
 int launch_head(const HeadLayer& L, int batch, cudaStream_t stream);

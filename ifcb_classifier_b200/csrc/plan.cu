@@ -126,7 +126,8 @@ extern "C" int ifcb_plan_add_conv(ifcb_plan* plan, const ifcb_conv_desc* d) {
   kp.last_ksteps = (last + 15) / 16;
   kp.tile_n = tile_n;
   kp.n_tiles = cout_pad / tile_n;
-  kp.stages = conv_pick_stages(tile_n);
+  kp.cout_pad = cout_pad;
+  kp.stages = conv_pick_stages(tile_n, cout_pad);
   IFCB_ARG_CHECK(kp.stages >= 2, "conv: tile_n=%d leaves fewer than 2 pipeline stages", tile_n);
   IFCB_ARG_CHECK(d->dtype == IFCB_ACT_BF16 || d->dtype == IFCB_ACT_FP16, "conv: bad dtype %d", d->dtype);
   kp.fp16 = d->dtype;
