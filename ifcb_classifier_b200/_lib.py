@@ -15,21 +15,24 @@ IFCB_STEM_IN_U8_GRAY, IFCB_STEM_IN_F32_NCHW = 0, 1
 IFCB_POOL_MAX, IFCB_POOL_AVG_AFFINE = 0, 1
 IFCB_MAX_SEGMENTS = 4
 IFCB_ACT_BF16, IFCB_ACT_FP16 = 0, 1
+IFCB_CONV_AUTO, IFCB_CONV_IM2COL, IFCB_CONV_WINDOW = 0, 1, 2
 
 
 class ConvSegment(C.Structure):
     _fields_ = [('n_begin', C.c_int32), ('n_end', C.c_int32), ('d_out', C.c_void_p),
-                ('ld', C.c_int32), ('relu', C.c_int32)]
+                ('ld', C.c_int32), ('relu', C.c_int32), ('pad_h', C.c_int32), ('pad_w', C.c_int32)]
 
 
 class ConvDesc(C.Structure):
     _fields_ = [('d_in', C.c_void_p), ('in_ld', C.c_int32), ('Cin', C.c_int32),
                 ('batch_cap', C.c_int32), ('H', C.c_int32), ('W', C.c_int32),
+                ('in_pad_h', C.c_int32), ('in_pad_w', C.c_int32),
                 ('kh', C.c_int32), ('kw', C.c_int32), ('stride_h', C.c_int32), ('stride_w', C.c_int32),
                 ('pad_h', C.c_int32), ('pad_w', C.c_int32), ('Cout', C.c_int32),
                 ('d_weight', C.c_void_p), ('d_scale', C.c_void_p), ('d_shift', C.c_void_p),
                 ('n_seg', C.c_int32), ('seg', ConvSegment * IFCB_MAX_SEGMENTS),
-                ('d_residual', C.c_void_p), ('res_ld', C.c_int32), ('tile_n', C.c_int32), ('dtype', C.c_int32)]
+                ('d_residual', C.c_void_p), ('res_ld', C.c_int32), ('res_pad_h', C.c_int32), ('res_pad_w', C.c_int32),
+                ('tile_n', C.c_int32), ('algo', C.c_int32), ('dtype', C.c_int32)]
 
 
 class StemDesc(C.Structure):
@@ -39,7 +42,8 @@ class StemDesc(C.Structure):
                 ('Cout', C.c_int32), ('d_weight', C.c_void_p), ('d_scale', C.c_void_p),
                 ('d_shift', C.c_void_p), ('d_lut', C.c_void_p),
                 ('in_scale', C.c_float * 3), ('in_shift', C.c_float * 3),
-                ('d_out', C.c_void_p), ('out_ld', C.c_int32), ('relu', C.c_int32), ('dtype', C.c_int32)]
+                ('d_out', C.c_void_p), ('out_ld', C.c_int32), ('relu', C.c_int32), ('dtype', C.c_int32),
+                ('out_pad_h', C.c_int32), ('out_pad_w', C.c_int32)]
 
 
 class PoolDesc(C.Structure):
@@ -47,7 +51,8 @@ class PoolDesc(C.Structure):
                 ('batch_cap', C.c_int32), ('H', C.c_int32), ('W', C.c_int32),
                 ('k', C.c_int32), ('stride', C.c_int32), ('pad', C.c_int32),
                 ('d_out', C.c_void_p), ('out_ld', C.c_int32),
-                ('d_scale', C.c_void_p), ('d_shift', C.c_void_p), ('relu', C.c_int32), ('dtype', C.c_int32)]
+                ('d_scale', C.c_void_p), ('d_shift', C.c_void_p), ('relu', C.c_int32), ('dtype', C.c_int32),
+                ('in_pad_h', C.c_int32), ('in_pad_w', C.c_int32), ('out_pad_h', C.c_int32), ('out_pad_w', C.c_int32)]
 
 
 class HeadDesc(C.Structure):

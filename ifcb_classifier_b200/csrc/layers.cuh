@@ -9,29 +9,35 @@
 namespace ifcb {
 
 struct ConvKernelParams {
-  int M;                       // batch * P * Q (set per launch)
-  int PQ, Q;                   // output pixels per image, output width
+  long long rows;              // GEMM rows of this launch (set per launch): batch * rows_per_img
+  int rows_per_img, row_w;     // IM2COL: P*Q, Q        WINDOW: Hp*Wp, Wp (padded input)
+  int P, Q;                    // valid output extent per image
   int kh, kw, stride_h, stride_w, pad_h, pad_w;
   int cblocks;                 // ceil(Cin / 64)
   int last_ksteps;             // K=16 MMA steps in the last channel block (1..4)
   int tile_n, n_tiles, stages;
   int cout_pad;                // n_tiles * tile_n
+  int m_sub;                   // 128-row accumulators per tile (WINDOW: 1, 2 or 4)
+  int a_slots, a_slot_bytes, box_rows, n_boxes;   // WINDOW: A patch ring
+  int win_shift0;              // WINDOW: (in_pad_h-pad_h)*Wp + (in_pad_w-pad_w) rows
+  int desc_base_offset_mode;   // WINDOW: how shifted UMMA descriptors encode their start
   int fp16;                    // 16-bit operand/activation format: 0 bf16, 1 fp16
   const float* scale;
   const float* shift;
   const __nv_bfloat16* residual;
-  int res_ld;
+  int res_ld, res_pad_h, res_pad_w;
   int n_seg;
   int seg_begin[IFCB_MAX_SEGMENTS], seg_end[IFCB_MAX_SEGMENTS], seg_ld[IFCB_MAX_SEGMENTS],
-      seg_relu[IFCB_MAX_SEGMENTS];
+      seg_relu[IFCB_MAX_SEGMENTS], seg_pad_h[IFCB_MAX_SEGMENTS], seg_pad_w[IFCB_MAX_SEGMENTS];
   __nv_bfloat16* seg_out[IFCB_MAX_SEGMENTS];
 };
 
 struct ConvLayer {
-  CUtensorMap tmap_a;          // im2col map over the NHWC input view
+  CUtensorMap tmap_a;          // IM2COL: im2col map over the NHWC input; WINDOW: tiled map over [N*Hp*Wp, C]
   CUtensorMap tmap_b;          // tiled map over the packed weights
   ConvKernelParams kp;
   int batch_cap;
+  bool window;
 };
 
 struct StemLayer {
@@ -49,10 +55,10 @@ struct HeadLayer {
 };
 
 int launch_conv(const ConvLayer& L, int batch, cudaStream_t stream);
-int conv_pick_stages(int tile_n, int cout_pad);
+bool conv_plan_smem(ConvKernelParams& kp, bool window, int halo_rows);
 int launch_im2col_probe(const ConvLayer& L, int c, int w, int h, int n, int off_w, int off_h, void* d_out,
                         cudaStream_t stream);
-int conv_smem_bytes(int tile_n, int stages, int cout_pad);
+int conv_smem_bytes(const ConvKernelParams& kp, bool window);
 int launch_stem(const StemLayer& L, int batch, cudaStream_t stream);
 int launch_pool(const PoolLayer& L, int batch, cudaStream_t stream);
 int launch_head(const HeadLayer& L, int batch, cudaStream_t stream);

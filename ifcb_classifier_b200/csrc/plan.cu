@@ -3,6 +3,7 @@
 // them as a fixed launch sequence on a stream (CUDA-graph capturable).
 #include <cuda.h>
 #include <cudaTypedefs.h>
+#include <cstdlib>
 #include <memory>
 #include <vector>
 #include "layers.cuh"
@@ -37,6 +38,17 @@ int resolve_driver() {
   IFCB_ARG_CHECK(q == cudaDriverEntryPointSuccess && fn, "cuTensorMapEncodeIm2col not available");
   g_encode_im2col = reinterpret_cast<PFN_cuTensorMapEncodeIm2col_v12000>(fn);
   return 0;
+}
+
+// Debug knob for the shifted UMMA descriptors of the window algorithm:
+// IFCB_WINDOW_BASE_OFFSET=0 leaves the descriptor base-offset field zero (default 1).
+int g_base_offset_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("IFCB_WINDOW_BASE_OFFSET");
+    mode = (e && e[0] == '0') ? 0 : 1;
+  }
+  return mode;
 }
 
 inline int out_dim(int in, int k, int stride, int pad) { return (in + 2 * pad - k) / stride + 1; }
@@ -101,23 +113,35 @@ extern "C" int ifcb_plan_add_conv(ifcb_plan* plan, const ifcb_conv_desc* d) {
   IFCB_ARG_CHECK(d->kh >= 1 && d->kw >= 1 && d->kh <= 16 && d->kw <= 16, "conv: bad filter %dx%d", d->kh, d->kw);
   IFCB_ARG_CHECK(d->stride_h >= 1 && d->stride_w >= 1 && d->stride_h <= 8 && d->stride_w <= 8, "conv: bad stride");
   IFCB_ARG_CHECK(d->pad_h >= 0 && d->pad_w >= 0 && d->pad_h < d->kh && d->pad_w < d->kw, "conv: bad padding");
+  IFCB_ARG_CHECK(d->in_pad_h >= 0 && d->in_pad_w >= 0 && d->in_pad_h <= 8 && d->in_pad_w <= 8, "conv: bad in_pad");
   IFCB_ARG_CHECK(d->n_seg >= 1 && d->n_seg <= IFCB_MAX_SEGMENTS, "conv: n_seg=%d out of range", d->n_seg);
   IFCB_ARG_CHECK(d->tile_n == 0 || (d->tile_n % 16 == 0 && d->tile_n >= 16 && d->tile_n <= 256),
                  "conv: tile_n=%d must be a multiple of 16 in [16,256]", d->tile_n);
+  IFCB_ARG_CHECK(d->dtype == IFCB_ACT_BF16 || d->dtype == IFCB_ACT_FP16, "conv: bad dtype %d", d->dtype);
+  IFCB_ARG_CHECK(d->algo >= IFCB_CONV_AUTO && d->algo <= IFCB_CONV_WINDOW, "conv: bad algo %d", d->algo);
   int rc = resolve_driver();
   if (rc) return rc;
 
+  const bool can_window = d->stride_h == 1 && d->stride_w == 1 && d->in_pad_h >= d->pad_h && d->in_pad_w >= d->pad_w;
+  IFCB_ARG_CHECK(d->algo != IFCB_CONV_WINDOW || can_window,
+                 "conv: the window algorithm needs stride 1 and an input buffer padded by at least the conv padding");
+  const bool window = d->algo == IFCB_CONV_WINDOW || (d->algo == IFCB_CONV_AUTO && can_window);
+
   Layer L{};
   L.kind = kConv;
+  L.conv.window = window;
   ConvKernelParams& kp = L.conv.kp;
   const int P = out_dim(d->H, d->kh, d->stride_h, d->pad_h);
   const int Q = out_dim(d->W, d->kw, d->stride_w, d->pad_w);
   IFCB_ARG_CHECK(P > 0 && Q > 0, "conv: empty output");
+  const int Hp = d->H + 2 * d->in_pad_h, Wp = d->W + 2 * d->in_pad_w;     // physical input extent
   int32_t cin_pad, k_pad, tile_n, cout_pad;
   ifcb_conv_geometry(d->Cin, d->Cout, d->kh, d->kw, d->tile_n, &cin_pad, &k_pad, &tile_n, &cout_pad);
-  kp.M = 0;
-  kp.PQ = P * Q;
+  kp.rows = 0;
+  kp.P = P;
   kp.Q = Q;
+  kp.rows_per_img = window ? Hp * Wp : P * Q;
+  kp.row_w = window ? Wp : Q;
   kp.kh = d->kh; kp.kw = d->kw;
   kp.stride_h = d->stride_h; kp.stride_w = d->stride_w;
   kp.pad_h = d->pad_h; kp.pad_w = d->pad_w;
@@ -127,14 +151,17 @@ extern "C" int ifcb_plan_add_conv(ifcb_plan* plan, const ifcb_conv_desc* d) {
   kp.tile_n = tile_n;
   kp.n_tiles = cout_pad / tile_n;
   kp.cout_pad = cout_pad;
-  kp.stages = conv_pick_stages(tile_n, cout_pad);
-  IFCB_ARG_CHECK(kp.stages >= 2, "conv: tile_n=%d leaves fewer than 2 pipeline stages", tile_n);
-  IFCB_ARG_CHECK(d->dtype == IFCB_ACT_BF16 || d->dtype == IFCB_ACT_FP16, "conv: bad dtype %d", d->dtype);
   kp.fp16 = d->dtype;
+  kp.desc_base_offset_mode = g_base_offset_mode();
+  kp.win_shift0 = (d->in_pad_h - d->pad_h) * Wp + (d->in_pad_w - d->pad_w);
+  const int halo = kp.win_shift0 + (d->kh - 1) * Wp + (d->kw - 1);
+  IFCB_ARG_CHECK(conv_plan_smem(kp, window, halo), "conv: no shared-memory plan for tile_n=%d halo=%d", tile_n, halo);
   kp.scale = d->d_scale;
   kp.shift = d->d_shift;
   kp.residual = reinterpret_cast<const __nv_bfloat16*>(d->d_residual);
   kp.res_ld = d->res_ld;
+  kp.res_pad_h = d->res_pad_h;
+  kp.res_pad_w = d->res_pad_w;
   if (d->d_residual) {
     IFCB_ARG_CHECK(d->res_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(d->d_residual) & 15) == 0,
                    "conv: residual view must be 16-byte aligned with ld %% 8 == 0");
@@ -148,31 +175,45 @@ extern "C" int ifcb_plan_add_conv(ifcb_plan* plan, const ifcb_conv_desc* d) {
     IFCB_ARG_CHECK(sg.d_out && sg.ld % 8 == 0 && (reinterpret_cast<uintptr_t>(sg.d_out) & 15) == 0,
                    "conv: segment %d output must be 16-byte aligned with ld %% 8 == 0", s);
     IFCB_ARG_CHECK(sg.ld >= sg.n_end - sg.n_begin, "conv: segment %d ld too small", s);
+    IFCB_ARG_CHECK(sg.pad_h >= 0 && sg.pad_w >= 0 && sg.pad_h <= 8 && sg.pad_w <= 8, "conv: segment %d bad pad", s);
     kp.seg_begin[s] = sg.n_begin;
     kp.seg_end[s] = sg.n_end;
     kp.seg_ld[s] = sg.ld;
     kp.seg_relu[s] = sg.relu;
+    kp.seg_pad_h[s] = sg.pad_h;
+    kp.seg_pad_w[s] = sg.pad_w;
     kp.seg_out[s] = reinterpret_cast<__nv_bfloat16*>(sg.d_out);
   }
   L.conv.batch_cap = d->batch_cap;
+  const CUtensorMapDataType dt = d->dtype == IFCB_ACT_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
 
-  // --- A: im2col tensor map over the NHWC input view (dims C, W, H, N) ---
-  {
+  if (window) {
+    // --- A: tiled 2-D map over the padded input viewed as [batch_cap*Hp*Wp, Cin] ---
+    cuuint64_t gdim[2] = {(cuuint64_t)d->Cin, (cuuint64_t)d->batch_cap * Hp * Wp};
+    cuuint64_t gstr[1] = {(cuuint64_t)d->in_ld * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)kp.box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode_tiled(&L.conv.tmap_a, dt, 2, const_cast<void*>(d->d_in), gdim, gstr, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    IFCB_ARG_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) for window input rows=%d", (int)r, kp.box_rows);
+  } else {
+    // --- A: im2col tensor map over the interior of the NHWC input (dims C, W, H, N) ---
+    const char* base = reinterpret_cast<const char*>(d->d_in) + ((size_t)d->in_pad_h * Wp + d->in_pad_w) * d->in_ld * 2;
     cuuint64_t gdim[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->batch_cap};
-    cuuint64_t gstr[3] = {(cuuint64_t)d->in_ld * 2, (cuuint64_t)d->W * d->in_ld * 2,
-                          (cuuint64_t)d->H * d->W * d->in_ld * 2};
+    cuuint64_t gstr[3] = {(cuuint64_t)d->in_ld * 2, (cuuint64_t)Wp * d->in_ld * 2, (cuuint64_t)Hp * Wp * d->in_ld * 2};
     int lower[2] = {-d->pad_w, -d->pad_h};
     int upper[2] = {d->pad_w - (d->kw - 1), d->pad_h - (d->kh - 1)};
     cuuint32_t estr[4] = {1, (cuuint32_t)d->stride_w, (cuuint32_t)d->stride_h, 1};
-    CUresult r = g_encode_im2col(&L.conv.tmap_a, d->dtype == IFCB_ACT_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d->d_in),
-                                 gdim, gstr, lower, upper, /*channelsPerPixel=*/64, /*pixelsPerColumn=*/128, estr,
-                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = g_encode_im2col(&L.conv.tmap_a, dt, 4, const_cast<char*>(base), gdim, gstr, lower, upper,
+                                 /*channelsPerPixel=*/64, /*pixelsPerColumn=*/128, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     IFCB_ARG_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeIm2col failed (%d) for conv %dx%d Cin=%d H=%d W=%d", (int)r,
                    d->kh, d->kw, d->Cin, d->H, d->W);
     // Small-tensor workaround used by CUTLASS for drivers <= 13.1: tensors under
     // 128 KiB must not have bit 21 of the second descriptor word set.
-    const unsigned long long bytes = (unsigned long long)d->batch_cap * d->H * d->W * d->in_ld * 2ull;
+    const unsigned long long bytes = (unsigned long long)d->batch_cap * Hp * Wp * d->in_ld * 2ull;
     int drv = 0;
     cudaDriverGetVersion(&drv);
     if (drv <= 13010 && bytes < 131072ull) reinterpret_cast<uint64_t*>(&L.conv.tmap_a)[1] &= ~(1ull << 21);
@@ -183,8 +224,8 @@ extern "C" int ifcb_plan_add_conv(ifcb_plan* plan, const ifcb_conv_desc* d) {
     cuuint64_t gstr[1] = {(cuuint64_t)k_pad * 2};
     cuuint32_t box[2] = {64, (cuuint32_t)tile_n};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = g_encode_tiled(&L.conv.tmap_b, d->dtype == IFCB_ACT_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(d->d_weight),
-                                gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+    CUresult r = g_encode_tiled(&L.conv.tmap_b, dt, 2, const_cast<void*>(d->d_weight), gdim, gstr, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     IFCB_ARG_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) for weights K_pad=%d Cout_pad=%d", (int)r,
                    k_pad, cout_pad);
@@ -220,6 +261,8 @@ extern "C" int ifcb_plan_add_pool(ifcb_plan* plan, const ifcb_pool_desc* d) {
                  "pool: C, in_ld, out_ld must be multiples of 8");
   IFCB_ARG_CHECK(((reinterpret_cast<uintptr_t>(d->d_in) | reinterpret_cast<uintptr_t>(d->d_out)) & 15) == 0,
                  "pool: views must be 16-byte aligned");
+  IFCB_ARG_CHECK(d->in_pad_h >= 0 && d->in_pad_w >= 0 && d->out_pad_h >= 0 && d->out_pad_w >= 0 &&
+                 d->in_pad_h <= 8 && d->in_pad_w <= 8 && d->out_pad_h <= 8 && d->out_pad_w <= 8, "pool: bad pads");
   Layer L{};
   L.kind = kPool;
   L.pool.d = *d;

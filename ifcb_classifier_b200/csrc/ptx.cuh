@@ -141,6 +141,14 @@ __device__ __forceinline__ void tmem_ld_wait() {
 __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
   return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
+// Same layout, start address shifted by whole 128-byte rows (not 1024-byte aligned): the
+// descriptor's base-offset field (bits 49-51) carries (addr >> 7) & 7 so that the hardware
+// applies the swizzle phase of the absolute address (mode 1); mode 0 leaves it zero.
+__device__ __forceinline__ uint64_t umma_desc_k_sw128_shifted(uint32_t smem_addr, int mode) {
+  uint64_t d = umma_desc_k_sw128(smem_addr);
+  if (mode) d |= (uint64_t)((smem_addr >> 7) & 7u) << 49;
+  return d;
+}
 // kind::f16 instruction descriptor: fp32 accumulate, A/B both bf16 (format 1) or both
 // fp16 (format 0), both K-major, M x N.
 __host__ __device__ inline uint32_t umma_idesc_f16(int M, int N, int fp16) {

@@ -66,7 +66,8 @@ __global__ void __launch_bounds__(128) stem_kernel(const ifcb_stem_desc d, const
         acc[c] = fmaf(x2, wk[2 * COUT + c], fmaf(x1, wk[COUT + c], fmaf(x0, wk[c], acc[c])));
     }
   }
-  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(d.d_out) + pix * d.out_ld;
+  const long long orow = ((long long)img * (P + 2 * d.out_pad_h) + op + d.out_pad_h) * (Q + 2 * d.out_pad_w) + oq + d.out_pad_w;
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(d.d_out) + orow * d.out_ld;
 #pragma unroll
   for (int c = 0; c < COUT; c += 8) {
     float y[8];
@@ -99,7 +100,9 @@ __global__ void __launch_bounds__(256) pool_kernel(const ifcb_pool_desc d, int P
   const int rem = (int)(pix - (long long)img * PQ);
   const int op = rem / Q, oq = rem - op * Q;
   const int h0 = op * d.stride - d.pad, w0 = oq * d.stride - d.pad;
-  const __nv_bfloat16* in = reinterpret_cast<const __nv_bfloat16*>(d.d_in) + (long long)img * d.H * d.W * d.in_ld + c8 * 8;
+  const int Wpi = d.W + 2 * d.in_pad_w;
+  const __nv_bfloat16* in = reinterpret_cast<const __nv_bfloat16*>(d.d_in) +
+      ((long long)img * (d.H + 2 * d.in_pad_h) * Wpi + (long long)d.in_pad_h * Wpi + d.in_pad_w) * d.in_ld + c8 * 8;
   float a[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) a[j] = AVG ? 0.f : -INFINITY;
@@ -109,7 +112,7 @@ __global__ void __launch_bounds__(256) pool_kernel(const ifcb_pool_desc d, int P
     for (int s = 0; s < d.k; ++s) {
       const int ww = w0 + s;
       if (ww < 0 || ww >= d.W) continue;
-      const uint4 v = __ldg(reinterpret_cast<const uint4*>(in + ((long long)hh * d.W + ww) * d.in_ld));
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(in + ((long long)hh * Wpi + ww) * d.in_ld));
       const uint32_t u[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -138,7 +141,8 @@ __global__ void __launch_bounds__(256) pool_kernel(const ifcb_pool_desc d, int P
   o.y = pack_act2(a[2], a[3], d.dtype);
   o.z = pack_act2(a[4], a[5], d.dtype);
   o.w = pack_act2(a[6], a[7], d.dtype);
-  *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(d.d_out) + pix * d.out_ld + c8 * 8) = o;
+  const long long orow = ((long long)img * (P + 2 * d.out_pad_h) + op + d.out_pad_h) * (Q + 2 * d.out_pad_w) + oq + d.out_pad_w;
+  *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(d.d_out) + orow * d.out_ld + c8 * 8) = o;
 }
 
 // ------------------------------------------------------------------------------

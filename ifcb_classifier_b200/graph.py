@@ -31,18 +31,21 @@ from ._lib import (ConvDesc, StemDesc, PoolDesc, HeadDesc, IFCB_STEM_IN_U8_GRAY,
 
 
 class View(object):
-    """Channel slice [c0, c1) of an NHWC 16-bit activation tensor [B, H, W, C]."""
+    """Channel slice [c0, c1) of an NHWC 16-bit activation tensor.  The tensor is stored with a
+    zero border of ``pad`` = (pad_h, pad_w) pixels: physical shape [B, H+2*pad_h, W+2*pad_w, C];
+    H / W are the logical extent.  (The border is what the WINDOW convolution reads as padding.)"""
 
-    def __init__(self, t, c0=0, c1=None):
+    def __init__(self, t, c0=0, c1=None, pad=(0, 0)):
         self.t = t
         self.c0 = c0
         self.c1 = t.shape[3] if c1 is None else c1
+        self.pad = (int(pad[0]), int(pad[1]))
 
     @property
-    def H(self): return self.t.shape[1]
+    def H(self): return self.t.shape[1] - 2 * self.pad[0]
 
     @property
-    def W(self): return self.t.shape[2]
+    def W(self): return self.t.shape[2] - 2 * self.pad[1]
 
     @property
     def C(self): return self.c1 - self.c0
@@ -54,7 +57,12 @@ class View(object):
     def ptr(self): return self.t.data_ptr() + 2 * self.c0
 
     def slice(self, c0, c1):
-        return View(self.t, self.c0 + c0, self.c0 + c1)
+        return View(self.t, self.c0 + c0, self.c0 + c1, self.pad)
+
+    def interior(self):
+        """Logical [B, H, W, C] torch view (tests / debugging)."""
+        ph, pw = self.pad
+        return self.t[:, ph:self.t.shape[1] - ph, pw:self.t.shape[2] - pw, self.c0:self.c1]
 
 
 def fold_bn(sd, prefix, eps):
@@ -95,10 +103,12 @@ class PlanBuilder(object):
         self.flops_per_image += flops
 
     # -- memory ---------------------------------------------------------------
-    def alloc(self, H, W, Cc):
-        t = torch.zeros((self.batch_cap, H, W, Cc), dtype=self.tdtype, device=self.device)
+    def alloc(self, H, W, Cc, pad=(0, 0)):
+        """Zero-initialised activation buffer with logical extent H x W and a zero border ``pad``
+        (kernels only ever write interior pixels, so the border stays zero)."""
+        t = torch.zeros((self.batch_cap, H + 2 * pad[0], W + 2 * pad[1], Cc), dtype=self.tdtype, device=self.device)
         self.keep.append(t)
-        return View(t)
+        return View(t, pad=pad)
 
     def dev(self, x, dtype):
         t = x.detach().to(device=self.device, dtype=dtype).contiguous()
@@ -106,7 +116,7 @@ class PlanBuilder(object):
         return t
 
     # -- layers ---------------------------------------------------------------
-    def conv(self, x, members, stride=(1, 1), pad=(0, 0), residual=None, tile_n=0, name='conv'):
+    def conv(self, x, members, stride=(1, 1), pad=(0, 0), residual=None, tile_n=0, name='conv', algo=0):
         """One implicit-GEMM launch.  ``members``: list of dicts
         (weight [Co,Ci,kh,kw] fp32, scale [Co], shift [Co], relu bool, out View) --
         more than one member = horizontally fused convs sharing input ``x``."""
@@ -129,6 +139,7 @@ class PlanBuilder(object):
         d = ConvDesc()
         d.d_in, d.in_ld, d.Cin = x.ptr, x.ld, Ci
         d.batch_cap, d.H, d.W = self.batch_cap, x.H, x.W
+        d.in_pad_h, d.in_pad_w = x.pad
         d.kh, d.kw, d.stride_h, d.stride_w, d.pad_h, d.pad_w = kh, kw, stride[0], stride[1], pad[0], pad[1]
         d.Cout = Co
         d.d_weight, d.d_scale, d.d_shift = wdev.data_ptr(), sdev.data_ptr(), hdev.data_ptr()
@@ -140,10 +151,13 @@ class PlanBuilder(object):
             assert out.C == co and out.H == P and out.W == Q, (name, out.C, co, out.H, P, out.W, Q)
             d.seg[i].n_begin, d.seg[i].n_end = n0, n0 + co
             d.seg[i].d_out, d.seg[i].ld, d.seg[i].relu = out.ptr, out.ld, 1 if m['relu'] else 0
+            d.seg[i].pad_h, d.seg[i].pad_w = out.pad
             n0 += co
         if residual is not None:
             d.d_residual, d.res_ld = residual.ptr, residual.ld
+            d.res_pad_h, d.res_pad_w = residual.pad
         d.tile_n = tile_n
+        d.algo = algo
         d.dtype = self.cdtype
         _lib.check(_lib.lib().ifcb_plan_add_conv(self.handle, C.byref(d)), 'plan_add_conv(%s)' % name)
         self._note(name, 'conv', 2 * P * Q * Co * Ci * kh * kw)
@@ -165,6 +179,7 @@ class PlanBuilder(object):
             d.in_scale[c], d.in_shift[c] = float(in_scale[c]), float(in_shift[c])
         d.d_out, d.out_ld, d.relu = out.ptr, out.ld, 1
         d.dtype = self.cdtype
+        d.out_pad_h, d.out_pad_w = out.pad
         _lib.check(_lib.lib().ifcb_plan_add_stem(self.handle, C.byref(d)), 'plan_add_stem')
         self._note(name, 'stem', 2 * out.H * out.W * Co * 3 * kh * kw)
         return out
@@ -179,12 +194,15 @@ class PlanBuilder(object):
             d.d_shift = self.dev(shift, torch.float32).data_ptr()
         d.relu = 1 if relu else 0
         d.dtype = self.cdtype
+        d.in_pad_h, d.in_pad_w = x.pad
+        d.out_pad_h, d.out_pad_w = out.pad
         _lib.check(_lib.lib().ifcb_plan_add_pool(self.handle, C.byref(d)), 'plan_add_pool(%s)' % name)
         self._note(name, 'pool', 0)
         return out
 
     def head(self, x, weight, bias, name='head'):
         n_classes = int(weight.shape[0])
+        assert x.pad == (0, 0), 'head input must be unpadded'
         B = self.batch_cap
         self.scores = torch.zeros((B, n_classes), dtype=torch.float32, device=self.device)
         self.logits = torch.zeros((B, n_classes), dtype=torch.float32, device=self.device)
@@ -270,11 +288,12 @@ def build_inception_v3(pb, sd, inp, in_kind, R, lut=None, transform_input=False,
     eps = 1e-3
     sz = lambda h, k, s, p: (h + 2 * p - k) // s + 1
 
-    def single(x, prefix, k, stride=(1, 1), pad=(0, 0), out=None, name=None):
+    def single(x, prefix, k, stride=(1, 1), pad=(0, 0), out=None, name=None, out_pad=(0, 0)):
+        """conv+bn+relu; ``out_pad`` = zero border the NEXT conv wants around the output."""
         w = sd[prefix + '.conv.weight']
         co, kh, kw = int(w.shape[0]), int(w.shape[2]), int(w.shape[3])
         if out is None:
-            out = pb.alloc(sz(x.H, kh, stride[0], pad[0]), sz(x.W, kw, stride[1], pad[1]), co)
+            out = pb.alloc(sz(x.H, kh, stride[0], pad[0]), sz(x.W, kw, stride[1], pad[1]), co, out_pad)
         pb.conv(x, [_basic(sd, prefix, out)], stride, pad, name=name or prefix)
         return out
 
@@ -296,7 +315,7 @@ def build_inception_v3(pb, sd, inp, in_kind, R, lut=None, transform_input=False,
     ts, tb = transform_input_affine() if transform_input else ((1, 1, 1), (0, 0, 0))
     pb.stem(inp, in_kind, R, R, sd['Conv2d_1a_3x3.conv.weight'], sc, sh, 2, 0, a, lut=lut,
             in_scale=ts, in_shift=tb, name='Conv2d_1a_3x3')
-    a = single(a, 'Conv2d_2a_3x3', 3)
+    a = single(a, 'Conv2d_2a_3x3', 3, out_pad=(1, 1))
     a = single(a, 'Conv2d_2b_3x3', 3, pad=(1, 1))
     p = pb.alloc(sz(a.H, 3, 2, 0), sz(a.W, 3, 2, 0), 64)
     pb.pool(IFCB_POOL_MAX, a, 3, 2, 0, p, name='maxpool1')
@@ -310,13 +329,13 @@ def build_inception_v3(pb, sd, inp, in_kind, R, lut=None, transform_input=False,
     for blk, pf in (('Mixed_5b', 32), ('Mixed_5c', 64), ('Mixed_5d', 64)):
         H = x.H
         out = pb.alloc(H, H, 224 + pf)
-        t5, t3, tp = pb.alloc(H, H, 48), pb.alloc(H, H, 64), pb.alloc(H, H, pf)
+        t5, t3, tp = pb.alloc(H, H, 48, (2, 2)), pb.alloc(H, H, 64, (1, 1)), pb.alloc(H, H, pf)
         fused_1x1(x, [_basic(sd, blk + '.branch1x1', out.slice(0, 64)),
                       _basic(sd, blk + '.branch5x5_1', t5),
                       _basic(sd, blk + '.branch3x3dbl_1', t3),
                       _raw(sd, blk + '.branch_pool', tp)], blk + '.1x1s')
         single(t5, blk + '.branch5x5_2', 5, pad=(2, 2), out=out.slice(64, 128))
-        t3b = single(t3, blk + '.branch3x3dbl_2', 3, pad=(1, 1))
+        t3b = single(t3, blk + '.branch3x3dbl_2', 3, pad=(1, 1), out_pad=(1, 1))
         single(t3b, blk + '.branch3x3dbl_3', 3, pad=(1, 1), out=out.slice(128, 224))
         avg_branch(tp, blk + '.branch_pool', out.slice(224, 224 + pf), blk + '.branch_pool.avg')
         x = out
@@ -326,7 +345,7 @@ def build_inception_v3(pb, sd, inp, in_kind, R, lut=None, transform_input=False,
     H2 = sz(x.H, 3, 2, 0)
     out = pb.alloc(H2, H2, 768)
     single(x, blk + '.branch3x3', 3, stride=(2, 2), out=out.slice(0, 384))
-    t = single(x, blk + '.branch3x3dbl_1', 1)
+    t = single(x, blk + '.branch3x3dbl_1', 1, out_pad=(1, 1))
     t = single(t, blk + '.branch3x3dbl_2', 3, pad=(1, 1))
     single(t, blk + '.branch3x3dbl_3', 3, stride=(2, 2), out=out.slice(384, 480))
     pb.pool(IFCB_POOL_MAX, x, 3, 2, 0, out.slice(480, 768), name=blk + '.maxpool')
@@ -336,16 +355,16 @@ def build_inception_v3(pb, sd, inp, in_kind, R, lut=None, transform_input=False,
     for blk, c7 in (('Mixed_6b', 128), ('Mixed_6c', 160), ('Mixed_6d', 160), ('Mixed_6e', 192)):
         H = x.H
         out = pb.alloc(H, H, 768)
-        t7, td, tp = pb.alloc(H, H, c7), pb.alloc(H, H, c7), pb.alloc(H, H, 192)
+        t7, td, tp = pb.alloc(H, H, c7, (0, 3)), pb.alloc(H, H, c7, (3, 0)), pb.alloc(H, H, 192)
         fused_1x1(x, [_basic(sd, blk + '.branch1x1', out.slice(0, 192)),
                       _basic(sd, blk + '.branch7x7_1', t7),
                       _basic(sd, blk + '.branch7x7dbl_1', td),
                       _raw(sd, blk + '.branch_pool', tp)], blk + '.1x1s')
-        t = single(t7, blk + '.branch7x7_2', 7, pad=(0, 3))
+        t = single(t7, blk + '.branch7x7_2', 7, pad=(0, 3), out_pad=(3, 0))
         single(t, blk + '.branch7x7_3', 7, pad=(3, 0), out=out.slice(192, 384))
-        t = single(td, blk + '.branch7x7dbl_2', 7, pad=(3, 0))
-        t = single(t, blk + '.branch7x7dbl_3', 7, pad=(0, 3))
-        t = single(t, blk + '.branch7x7dbl_4', 7, pad=(3, 0))
+        t = single(td, blk + '.branch7x7dbl_2', 7, pad=(3, 0), out_pad=(0, 3))
+        t = single(t, blk + '.branch7x7dbl_3', 7, pad=(0, 3), out_pad=(3, 0))
+        t = single(t, blk + '.branch7x7dbl_4', 7, pad=(3, 0), out_pad=(0, 3))
         single(t, blk + '.branch7x7dbl_5', 7, pad=(0, 3), out=out.slice(384, 576))
         avg_branch(tp, blk + '.branch_pool', out.slice(576, 768), blk + '.branch_pool.avg')
         x = out
@@ -354,10 +373,10 @@ def build_inception_v3(pb, sd, inp, in_kind, R, lut=None, transform_input=False,
     blk = 'Mixed_7a'
     H2 = sz(x.H, 3, 2, 0)
     out = pb.alloc(H2, H2, 1280)
-    t3, t7 = pb.alloc(x.H, x.H, 192), pb.alloc(x.H, x.H, 192)
+    t3, t7 = pb.alloc(x.H, x.H, 192), pb.alloc(x.H, x.H, 192, (0, 3))
     fused_1x1(x, [_basic(sd, blk + '.branch3x3_1', t3), _basic(sd, blk + '.branch7x7x3_1', t7)], blk + '.1x1s')
     single(t3, blk + '.branch3x3_2', 3, stride=(2, 2), out=out.slice(0, 320))
-    t = single(t7, blk + '.branch7x7x3_2', 7, pad=(0, 3))
+    t = single(t7, blk + '.branch7x7x3_2', 7, pad=(0, 3), out_pad=(3, 0))
     t = single(t, blk + '.branch7x7x3_3', 7, pad=(3, 0))
     single(t, blk + '.branch7x7x3_4', 3, stride=(2, 2), out=out.slice(320, 512))
     pb.pool(IFCB_POOL_MAX, x, 3, 2, 0, out.slice(512, 1280), name=blk + '.maxpool')
@@ -367,14 +386,14 @@ def build_inception_v3(pb, sd, inp, in_kind, R, lut=None, transform_input=False,
     for blk in ('Mixed_7b', 'Mixed_7c'):
         H = x.H
         out = pb.alloc(H, H, 2048)
-        t3, td, tp = pb.alloc(H, H, 384), pb.alloc(H, H, 448), pb.alloc(H, H, 192)
+        t3, td, tp = pb.alloc(H, H, 384, (1, 1)), pb.alloc(H, H, 448, (1, 1)), pb.alloc(H, H, 192)
         fused_1x1(x, [_basic(sd, blk + '.branch1x1', out.slice(0, 320)),
                       _basic(sd, blk + '.branch3x3_1', t3),
                       _basic(sd, blk + '.branch3x3dbl_1', td),
                       _raw(sd, blk + '.branch_pool', tp)], blk + '.1x1s')
         single(t3, blk + '.branch3x3_2a', 3, pad=(0, 1), out=out.slice(320, 704))
         single(t3, blk + '.branch3x3_2b', 3, pad=(1, 0), out=out.slice(704, 1088))
-        t = single(td, blk + '.branch3x3dbl_2', 3, pad=(1, 1))
+        t = single(td, blk + '.branch3x3dbl_2', 3, pad=(1, 1), out_pad=(1, 1))
         single(t, blk + '.branch3x3dbl_3a', 3, pad=(0, 1), out=out.slice(1088, 1472))
         single(t, blk + '.branch3x3dbl_3b', 3, pad=(1, 0), out=out.slice(1472, 1856))
         avg_branch(tp, blk + '.branch_pool', out.slice(1856, 2048), blk + '.branch_pool.avg')
@@ -398,35 +417,40 @@ def build_resnet(pb, sd, arch, inp, in_kind, R, lut=None):
     kind, layers = RESNET_CFG[arch]
     sz = lambda h, k, s, p: (h + 2 * p - k) // s + 1
 
-    def cbr(x, conv, bn, stride=1, pad=0, relu=True, residual=None, name=None):
+    def cbr(x, conv, bn, stride=1, pad=0, relu=True, residual=None, name=None, out_pad=(0, 0)):
         w = sd[conv + '.weight']
         co, k = int(w.shape[0]), int(w.shape[2])
-        out = pb.alloc(sz(x.H, k, stride, pad), sz(x.W, k, stride, pad), co)
+        out = pb.alloc(sz(x.H, k, stride, pad), sz(x.W, k, stride, pad), co, out_pad)
         scale, shift = fold_bn(sd, bn, eps)
         pb.conv(x, [dict(weight=w, scale=scale, shift=shift, relu=relu, out=out)], (stride, stride), (pad, pad),
                 residual=residual, name=name or conv)
         return out
 
+    # a tensor carries the zero border its 3x3 consumer needs (basic blocks: block inputs/outputs)
+    blk_pad = (1, 1) if kind == 'basic' else (0, 0)
     H1 = sz(R, 7, 2, 3)
     a = pb.alloc(H1, H1, 64)
     sc, sh = fold_bn(sd, 'bn1', eps)
     pb.stem(inp, in_kind, R, R, sd['conv1.weight'], sc, sh, 2, 3, a, lut=lut, name='conv1')
-    x = pb.alloc(sz(H1, 3, 2, 1), sz(H1, 3, 2, 1), 64)
+    x = pb.alloc(sz(H1, 3, 2, 1), sz(H1, 3, 2, 1), 64, blk_pad)
     pb.pool(IFCB_POOL_MAX, a, 3, 2, 1, x, name='maxpool')
+    nlayers = len(layers)
     for li, nblocks in enumerate(layers):
         for bi in range(nblocks):
             pre = 'layer%d.%d' % (li + 1, bi)
             stride = 2 if (li > 0 and bi == 0) else 1
+            last = (li == nlayers - 1 and bi == nblocks - 1)
+            opad = (0, 0) if last else blk_pad
             identity = x
             if (pre + '.downsample.0.weight') in sd:
                 identity = cbr(x, pre + '.downsample.0', pre + '.downsample.1', stride=stride, relu=False)
             if kind == 'basic':
-                t = cbr(x, pre + '.conv1', pre + '.bn1', stride=stride, pad=1)
-                x = cbr(t, pre + '.conv2', pre + '.bn2', pad=1, relu=True, residual=identity)
+                t = cbr(x, pre + '.conv1', pre + '.bn1', stride=stride, pad=1, out_pad=(1, 1))
+                x = cbr(t, pre + '.conv2', pre + '.bn2', pad=1, relu=True, residual=identity, out_pad=opad)
             else:   # torchvision v1.5: the stride sits on the 3x3
-                t = cbr(x, pre + '.conv1', pre + '.bn1')
+                t = cbr(x, pre + '.conv1', pre + '.bn1', out_pad=(1, 1))
                 t = cbr(t, pre + '.conv2', pre + '.bn2', stride=stride, pad=1)
-                x = cbr(t, pre + '.conv3', pre + '.bn3', relu=True, residual=identity)
+                x = cbr(t, pre + '.conv3', pre + '.bn3', relu=True, residual=identity, out_pad=opad)
     return pb.head(x, sd['fc.weight'], sd['fc.bias'])
 
 

@@ -102,14 +102,25 @@ typedef struct {
   void* d_out;            /* bf16, channel-slice base pointer */
   int32_t ld;             /* pixel stride of the destination, elements */
   int32_t relu;           /* 1: max(0, .) after the affine */
+  int32_t pad_h, pad_w;   /* physical zero border of the destination tensor: it is
+                             [batch, P+2*pad_h, Q+2*pad_w, ld] and d_out points at its
+                             first (border) pixel; only interior pixels are written */
 } ifcb_conv_segment;
 
 #define IFCB_MAX_SEGMENTS 4
+enum { IFCB_CONV_AUTO = 0, IFCB_CONV_IM2COL = 1, IFCB_CONV_WINDOW = 2 };
 
 /* K2  Conv2d(bias=False) + folded BatchNorm + ReLU as a tcgen05 implicit GEMM
  * (torchvision BasicConv2d, inception.py:398-407; ResNet conv-bn-relu).
  * y[n, co] = act( scale[co] * sum_{r,s,ci} x[n, r, s, ci] * w[co, r, s, ci] + shift[co] (+ residual) )
- *   d_in        bf16 NHWC view: [batch_cap, H, W, Cin] with pixel stride in_ld
+ *   d_in        NHWC view with pixel stride in_ld; logical extent [batch_cap, H, W, Cin],
+ *               stored with a zero border of in_pad_h / in_pad_w pixels (physical
+ *               [batch_cap, H+2*in_pad_h, W+2*in_pad_w, in_ld]); d_in = first border pixel
+ *   algo        IFCB_CONV_IM2COL: one TMA im2col load per filter tap (any stride);
+ *               IFCB_CONV_WINDOW: stride 1 and in_pad == pad -- the padded input patch
+ *               of a tile is loaded ONCE and filter taps are shifted UMMA descriptors;
+ *               IFCB_CONV_AUTO picks WINDOW whenever it applies
+ *   d_residual  view with the output's logical extent and its own zero border res_pad_*
  *   d_weight    bf16 [Cout_pad, kh*kw*Cin_pad] packed by the host: K index =
  *               (r*kw + s)*Cin_pad + ci, Cin_pad = round_up(Cin, 64), zero
  *               filled; Cout_pad = n_tiles * tile_n
@@ -121,6 +132,7 @@ typedef struct {
   const void* d_in;
   int32_t in_ld, Cin;
   int32_t batch_cap, H, W;
+  int32_t in_pad_h, in_pad_w;
   int32_t kh, kw, stride_h, stride_w, pad_h, pad_w;
   int32_t Cout;
   const void* d_weight;
@@ -129,8 +141,9 @@ typedef struct {
   int32_t n_seg;
   ifcb_conv_segment seg[IFCB_MAX_SEGMENTS];
   const void* d_residual;
-  int32_t res_ld;
+  int32_t res_ld, res_pad_h, res_pad_w;
   int32_t tile_n;
+  int32_t algo;  /* IFCB_CONV_* */
   int32_t dtype; /* IFCB_ACT_* of input, weights, residual and outputs */
 } ifcb_conv_desc;
 
@@ -166,6 +179,7 @@ typedef struct {
   int32_t out_ld;
   int32_t relu;
   int32_t dtype; /* IFCB_ACT_* of the output */
+  int32_t out_pad_h, out_pad_w; /* zero border of the output tensor (see ifcb_conv_segment) */
 } ifcb_stem_desc;
 int ifcb_plan_add_stem(ifcb_plan* plan, const ifcb_stem_desc* desc);
 
@@ -188,6 +202,7 @@ typedef struct {
   const float* d_shift;
   int32_t relu;
   int32_t dtype; /* IFCB_ACT_* of input and output */
+  int32_t in_pad_h, in_pad_w, out_pad_h, out_pad_w; /* zero borders of the two tensors */
 } ifcb_pool_desc;
 int ifcb_plan_add_pool(ifcb_plan* plan, const ifcb_pool_desc* desc);
 

@@ -26,6 +26,23 @@ def to_nchw(t):
     return t.float().cpu().permute(0, 3, 1, 2)
 
 
+def padded_view(x_nchw, dev, pad, cap=None, dtype=torch.bfloat16):
+    """NCHW fp32 -> View over a zero-bordered NHWC device tensor (batch capacity `cap`)."""
+    from ifcb_classifier_b200.graph import View
+    B, Cc, H, W = x_nchw.shape
+    cap = cap or B
+    t = torch.zeros((cap, H + 2 * pad[0], W + 2 * pad[1], Cc), dtype=dtype, device=dev)
+    t[:B, pad[0]:pad[0] + H, pad[1]:pad[1] + W] = x_nchw.permute(0, 2, 3, 1).to(dev).to(dtype)
+    return View(t, pad=pad)
+
+
+def border_is_zero(v):
+    t = v.t.float().clone()
+    ph, pw = v.pad
+    t[:, ph:t.shape[1] - ph, pw:t.shape[2] - pw] = 0
+    return float(t.abs().max()) == 0.0
+
+
 def swizzle_decode(raw_u8):
     """raw 16 KiB 128B-swizzled tile -> [128 rows, 64] bf16 values (as float)."""
     raw = raw_u8.view(128, 8, 16)
@@ -86,7 +103,7 @@ def test_im2col_tma_probe(cuda):
         Q = (W + 2 * pad[1] - kw) // stride[1] + 1
         out = pb.alloc(P, Q, 16)
         pb.conv(xin, [dict(weight=torch.randn(16, Cin, kh, kw), scale=torch.ones(16), shift=torch.zeros(16),
-                           relu=False, out=out)], stride, pad)
+                           relu=False, out=out)], stride, pad, algo=1)
         raw = torch.zeros(16384, dtype=torch.uint8, device=cuda)
         xp = F.pad(bf16r(x), (pad[1], pad[1], pad[0], pad[0]))
         for (m0, r, s, cb) in [(0, 0, 0, 0), (128, kh - 1, kw - 1, 0), (P * Q - 5, 0, kw - 1, (Cin - 1) // 64)]:
@@ -110,10 +127,14 @@ def test_im2col_tma_probe(cuda):
         pb.close()
 
 
+@pytest.mark.parametrize('algo', ['im2col', 'window'])
 @pytest.mark.parametrize('case', CONV_CASES, ids=[c[0] for c in CONV_CASES])
-def test_conv_bn_relu(cuda, case):
-    from ifcb_classifier_b200.graph import PlanBuilder, View
+def test_conv_bn_relu(cuda, case, algo):
+    from ifcb_classifier_b200.graph import PlanBuilder
+    from ifcb_classifier_b200._lib import IFCB_CONV_IM2COL, IFCB_CONV_WINDOW
     name, B, Cin, H, W, Cout, kh, kw, stride, pad = case
+    if algo == 'window' and stride != (1, 1):
+        pytest.skip('window algorithm is stride-1 only')
     g = torch.Generator().manual_seed(sum(name.encode()))
     x = torch.randn(B, Cin, H, W, generator=g)
     w = torch.randn(Cout, Cin, kh, kw, generator=g) / np.sqrt(Cin * kh * kw)
@@ -121,19 +142,44 @@ def test_conv_bn_relu(cuda, case):
     shift = torch.randn(Cout, generator=g) * 0.2
     cap = B + 1                                            # run with batch < capacity
     pb = PlanBuilder(cap, cuda, 'bf16')
-    xin_t = torch.zeros((cap, H, W, Cin), dtype=torch.bfloat16, device=cuda)
-    xin_t[:B] = nhwc_dev(x, cuda)
-    pb.keep.append(xin_t)
+    xin = padded_view(x, cuda, pad if algo == 'window' else (0, 0), cap)
+    pb.keep.append(xin.t)
     P = (H + 2 * pad[0] - kh) // stride[0] + 1
     Q = (W + 2 * pad[1] - kw) // stride[1] + 1
-    out = pb.alloc(P, Q, Cout)
-    pb.conv(View(xin_t), [dict(weight=w, scale=scale, shift=shift, relu=True, out=out)], stride, pad, name=name)
+    out = pb.alloc(P, Q, Cout, pad=(1, 2) if algo == 'window' else (0, 0))     # padded destination
+    pb.conv(xin, [dict(weight=w, scale=scale, shift=shift, relu=True, out=out)], stride, pad, name=name,
+            algo=IFCB_CONV_WINDOW if algo == 'window' else IFCB_CONV_IM2COL)
     pb.run(B)
     torch.cuda.synchronize()
-    got = to_nchw(out.t[:B])
+    got = to_nchw(out.interior()[:B])
     want = _ref_conv(x, w, scale, shift, stride, pad, True)
     _check(got, want, name)
     assert float(out.t[B:].float().abs().max()) == 0.0     # rows past the batch are untouched
+    assert border_is_zero(out)                             # junk rows never reach the zero border
+    pb.close()
+
+
+def test_window_input_padded_more_than_conv(cuda):
+    """Inception-E pattern: one (1,1)-padded tensor feeds a 1x3 (pad 0,1) and a 3x1 (pad 1,0) conv."""
+    from ifcb_classifier_b200.graph import PlanBuilder
+    from ifcb_classifier_b200._lib import IFCB_CONV_WINDOW
+    g = torch.Generator().manual_seed(31)
+    B, Cin, H, W, Cout = 5, 384, 8, 8, 384
+    x = torch.randn(B, Cin, H, W, generator=g)
+    pb = PlanBuilder(B, cuda, 'bf16')
+    xin = padded_view(x, cuda, (1, 1)); pb.keep.append(xin.t)
+    cat = pb.alloc(H, W, 2 * Cout)
+    ws = []
+    for i, (k, pad) in enumerate((((1, 3), (0, 1)), ((3, 1), (1, 0)))):
+        w = torch.randn(Cout, Cin, k[0], k[1], generator=g) / np.sqrt(Cin * 3)
+        ws.append((w, pad))
+        pb.conv(xin, [dict(weight=w, scale=torch.ones(Cout), shift=torch.zeros(Cout), relu=True,
+                           out=cat.slice(i * Cout, (i + 1) * Cout))], (1, 1), pad, algo=IFCB_CONV_WINDOW)
+    pb.run(B)
+    torch.cuda.synchronize()
+    for i, (w, pad) in enumerate(ws):
+        want = _ref_conv(x, w, torch.ones(Cout), torch.zeros(Cout), (1, 1), pad, True)
+        _check(to_nchw(cat.t[..., i * Cout:(i + 1) * Cout]), want, 'E-branch %d' % i)
     pb.close()
 
 
@@ -152,14 +198,14 @@ def test_conv_fused_segments_slices_and_residual(cuda):
     wide = nhwc_dev(x, cuda, c_total=256, c0=32); pb.keep.append(wide)
     xin = View(wide, 32, 32 + Cin)
     cat = pb.alloc(H, W, 256)
-    outs = [cat.slice(0, 64), pb.alloc(H, W, 48), cat.slice(128, 192), pb.alloc(H, W, 32)]
+    outs = [cat.slice(0, 64), pb.alloc(H, W, 48, pad=(2, 2)), cat.slice(128, 192), pb.alloc(H, W, 32, pad=(0, 3))]
     relus = [True, True, True, False]
     pb.conv(xin, [dict(weight=ws[i], scale=scs[i], shift=shs[i], relu=relus[i], out=outs[i]) for i in range(4)])
     # residual: 1x1 64 -> 256 on top of `res`
     xr = torch.randn(B, 64, 14, 14, generator=g)
     res = torch.randn(B, 256, 14, 14, generator=g)
     wr = torch.randn(256, 64, 1, 1, generator=g) / 8
-    xr_d, res_d = View(nhwc_dev(xr, cuda)), View(nhwc_dev(res, cuda))
+    xr_d, res_d = View(nhwc_dev(xr, cuda)), padded_view(res, cuda, (1, 1))
     pb.keep += [xr_d.t, res_d.t]
     out_r = pb.alloc(14, 14, 256)
     pb.conv(xr_d, [dict(weight=wr, scale=torch.ones(256), shift=torch.zeros(256), relu=True, out=out_r)],
@@ -169,26 +215,28 @@ def test_conv_fused_segments_slices_and_residual(cuda):
     for i in range(4):
         want = _ref_conv(x, ws[i], scs[i], shs[i], (1, 1), (0, 0), relus[i])
         o = outs[i]
-        got = to_nchw(o.t[..., o.c0:o.c1])
+        got = to_nchw(o.interior())
         _check(got, want, 'segment %d' % i)
+        assert border_is_zero(o) or o.t is cat.t
     assert float(cat.t[..., 64:128].float().abs().max()) == 0.0     # untouched slice of the concat buffer
     want = _ref_conv(xr, wr, torch.ones(256), torch.zeros(256), (1, 1), (0, 0), True, residual=res)
     _check(to_nchw(out_r.t), want, 'residual')
     pb.close()
 
 
-def test_large_batch_many_tiles(cuda):
-    """More tiles than SMs: exercises the persistent loop, both TMEM stages and phase wrap."""
-    from ifcb_classifier_b200.graph import PlanBuilder, View
+@pytest.mark.parametrize('algo', ['im2col', 'window'])
+def test_large_batch_many_tiles(cuda, algo):
+    """More tiles than SMs: exercises the persistent loop, both TMEM buffers and phase wrap."""
+    from ifcb_classifier_b200.graph import PlanBuilder
     g = torch.Generator().manual_seed(11)
     B, H, W, Cin, Cout = 40, 35, 35, 96, 96
     x = torch.randn(B, Cin, H, W, generator=g)
     w = torch.randn(Cout, Cin, 3, 3, generator=g) / np.sqrt(Cin * 9)
     pb = PlanBuilder(B, cuda, 'bf16')
-    xin = View(nhwc_dev(x, cuda)); pb.keep.append(xin.t)
+    xin = padded_view(x, cuda, (1, 1) if algo == 'window' else (0, 0)); pb.keep.append(xin.t)
     out = pb.alloc(H, W, Cout)
     pb.conv(xin, [dict(weight=w, scale=torch.ones(Cout), shift=torch.zeros(Cout), relu=False, out=out)],
-            (1, 1), (1, 1))
+            (1, 1), (1, 1), algo=2 if algo == 'window' else 1)
     pb.run(B)
     torch.cuda.synchronize()
     _check(to_nchw(out.t), _ref_conv(x, w, torch.ones(Cout), torch.zeros(Cout), (1, 1), (1, 1), False), 'many tiles')
@@ -205,8 +253,11 @@ def test_pools(cuda):
     xin = View(nhwc_dev(x, cuda)); pb.keep.append(xin.t)
     o1 = pb.alloc(18, 18, 64)
     pb.pool(IFCB_POOL_MAX, xin, 3, 2, 0, o1)
-    o2 = pb.alloc(19, 19, 64)
+    o2 = pb.alloc(19, 19, 64, pad=(1, 1))
     pb.pool(IFCB_POOL_MAX, xin, 3, 2, 1, o2)
+    xin_p = padded_view(x, cuda, (2, 1)); pb.keep.append(xin_p.t)
+    o3 = pb.alloc(18, 18, 64)
+    pb.pool(IFCB_POOL_MAX, xin_p, 3, 2, 0, o3)
     cat = pb.alloc(37, 37, 96)
     sc, sh = torch.rand(64, generator=g) + 0.5, torch.randn(64, generator=g) * 0.3
     pb.pool(IFCB_POOL_AVG_AFFINE, xin, 3, 1, 1, cat.slice(16, 80), sc, sh, relu=True)
@@ -214,7 +265,8 @@ def test_pools(cuda):
     torch.cuda.synchronize()
     xb = bf16r(x)
     assert torch.equal(to_nchw(o1.t), F.max_pool2d(xb, 3, 2, 0))
-    assert torch.equal(to_nchw(o2.t), F.max_pool2d(xb, 3, 2, 1))
+    assert torch.equal(to_nchw(o2.interior()), F.max_pool2d(xb, 3, 2, 1)) and border_is_zero(o2)
+    assert torch.equal(to_nchw(o3.t), F.max_pool2d(xb, 3, 2, 0))
     want = torch.relu(F.avg_pool2d(xb, 3, 1, 1) * sc[None, :, None, None] + sh[None, :, None, None])
     _check(to_nchw(cat.t[..., 16:80]), want, 'avgpool affine')
     pb.close()
