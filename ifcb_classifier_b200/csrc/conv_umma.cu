@@ -233,16 +233,24 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           for (int cb = 0; cb < p.cblocks; ++cb) {
             ptx::mbar_wait(a_empty + aslot, aphase ^ 1);
             uint8_t* dst = a_base + (size_t)aslot * p.a_slot_bytes;
-            ptx::mbar_arrive_expect_tx(a_full + aslot, (uint32_t)(p.n_boxes * p.box_rows * 128));
-            for (int b = 0; b < p.n_boxes; ++b)
-              ptx::tma_load_2d(dst + (size_t)b * p.box_rows * 128, &tmap_a, a_full + aslot, cb * kBlockK,
-                               i0 + b * p.box_rows);
+            if (p.debug_flags & 1) {
+              ptx::mbar_arrive(a_full + aslot);
+            } else {
+              ptx::mbar_arrive_expect_tx(a_full + aslot, (uint32_t)(p.n_boxes * p.box_rows * 128));
+              for (int b = 0; b < p.n_boxes; ++b)
+                ptx::tma_load_2d(dst + (size_t)b * p.box_rows * 128, &tmap_a, a_full + aslot, cb * kBlockK,
+                                 i0 + b * p.box_rows);
+            }
             if (++aslot == p.a_slots) { aslot = 0; aphase ^= 1; }
             for (int t = 0; t < taps; ++t) {
               ptx::mbar_wait(empty_bar + stage, phase ^ 1);
-              ptx::mbar_arrive_expect_tx(full_bar + stage, (uint32_t)b_tile_bytes);
-              ptx::tma_load_2d(b_base + (size_t)stage * b_stride, &tmap_b, full_bar + stage,
-                               (t * p.cblocks + cb) * kBlockK, n_tile * p.tile_n);
+              if (p.debug_flags & 1) {
+                ptx::mbar_arrive(full_bar + stage);
+              } else {
+                ptx::mbar_arrive_expect_tx(full_bar + stage, (uint32_t)b_tile_bytes);
+                ptx::tma_load_2d(b_base + (size_t)stage * b_stride, &tmap_b, full_bar + stage,
+                                 (t * p.cblocks + cb) * kBlockK, n_tile * p.tile_n);
+              }
               if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
           }
@@ -258,11 +266,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               for (int cb = 0; cb < p.cblocks; ++cb) {
                 ptx::mbar_wait(empty_bar + stage, phase ^ 1);
                 uint8_t* a_dst = a_base + (size_t)stage * b_stride;
-                ptx::mbar_arrive_expect_tx(full_bar + stage, (uint32_t)(kATileBytes + b_tile_bytes));
-                ptx::tma_load_im2col_4d(a_dst, &tmap_a, full_bar + stage, cb * kBlockK, w0, h0, img,
-                                        (uint16_t)s, (uint16_t)r);
-                ptx::tma_load_2d(a_dst + kATileBytes, &tmap_b, full_bar + stage,
-                                 ((r * p.kw + s) * p.cblocks + cb) * kBlockK, n_tile * p.tile_n);
+                if (p.debug_flags & 1) {
+                  ptx::mbar_arrive(full_bar + stage);
+                } else {
+                  ptx::mbar_arrive_expect_tx(full_bar + stage, (uint32_t)(kATileBytes + b_tile_bytes));
+                  ptx::tma_load_im2col_4d(a_dst, &tmap_a, full_bar + stage, cb * kBlockK, w0, h0, img,
+                                          (uint16_t)s, (uint16_t)r);
+                  ptx::tma_load_2d(a_dst + kATileBytes, &tmap_b, full_bar + stage,
+                                   ((r * p.kw + s) * p.cblocks + cb) * kBlockK, n_tile * p.tile_n);
+                }
                 if (++stage == p.stages) { stage = 0; phase ^= 1; }
               }
             }
@@ -298,9 +310,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               for (int j = 0; j < p.m_sub; ++j) {
                 const uint32_t a_start = a_addr + (shift_rows + (uint32_t)(j * kBlockM)) * 128u;
                 const uint64_t adesc = ptx::umma_desc_k_sw128_shifted(a_start, p.desc_base_offset_mode);
-                for (int k = 0; k < ksteps; ++k)
-                  ptx::umma_f16(d_tmem + (uint32_t)(j * p.tile_n), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k),
-                                idesc, (cb > 0 || t > 0 || k > 0) ? 1u : 0u);
+                if (!(p.debug_flags & 2))
+                  for (int k = 0; k < ksteps; ++k)
+                    ptx::umma_f16(d_tmem + (uint32_t)(j * p.tile_n), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k),
+                                  idesc, (cb > 0 || t > 0 || k > 0) ? 1u : 0u);
               }
               ptx::umma_commit(empty_bar + stage);
               if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -318,9 +331,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const uint64_t bdesc = ptx::umma_desc_k_sw128(a_addr + kATileBytes);
             const int cb = kb % p.cblocks;
             const int ksteps = (cb == p.cblocks - 1) ? p.last_ksteps : (kBlockK / 16);
-            for (int k = 0; k < ksteps; ++k)
-              ptx::umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                            (kb > 0 || k > 0) ? 1u : 0u);
+            if (!(p.debug_flags & 2))
+              for (int k = 0; k < ksteps; ++k)
+                ptx::umma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                              (kb > 0 || k > 0) ? 1u : 0u);
             ptx::umma_commit(empty_bar + stage);     // frees the smem slot when these MMAs retire
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
@@ -340,7 +354,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const uint32_t acc_phase = (local >> 1) & 1;
       ptx::mbar_wait(tmem_full + acc, acc_phase);
       ptx::tc_fence_after();
-      for (int j = 0; j < p.m_sub; ++j) {
+      for (int j = 0; j < p.m_sub && !(p.debug_flags & 4); ++j) {
         const long long row0 = (long long)m_tile * tile_rows + j * kBlockM + quad * 32;
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * kAccBufCols + j * p.tile_n);
         epilogue_128rows(p, taddr, row0, n_tile * p.tile_n, lane, half, stage_addr, s_scale, s_shift);
@@ -376,16 +390,17 @@ bool conv_plan_smem(ConvKernelParams& kp, bool window, int halo_rows) {
   }
   // WINDOW: choose m (accumulators per tile) as large as TMEM double buffering and smem allow
   for (int m = 4; m >= 1; m >>= 1) {
+    if (m > kp.m_sub_cap) continue;
     if (m * kp.tile_n > kAccBufCols) continue;
     const int rows = kBlockM * m + halo_rows;
     const int n_boxes = (rows + 255) / 256;
     int box_rows = ((rows + n_boxes - 1) / n_boxes + 7) & ~7;
     const int slot = (n_boxes * box_rows * 128 + 1023) & ~1023;
-    for (int slots = 2; slots >= 1; --slots) {
+    for (int slots = kp.a_slots_pref; slots >= 1; --slots) {
       const int left = kSmemBudget - fixed - slots * slot;
       int s = left / b_tile;
       if (s > 10) s = 10;
-      const int need = slots == 2 ? 3 : 4;
+      const int need = slots >= 2 ? 3 : 4;
       if (s >= need) {
         kp.m_sub = m;
         kp.a_slots = slots;

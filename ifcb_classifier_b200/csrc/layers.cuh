@@ -20,7 +20,9 @@ struct ConvKernelParams {
   int m_sub;                   // 128-row accumulators per tile (WINDOW: 1, 2 or 4)
   int a_slots, a_slot_bytes, box_rows, n_boxes;   // WINDOW: A patch ring
   int win_shift0;              // WINDOW: (in_pad_h-pad_h)*Wp + (in_pad_w-pad_w) rows
-  int desc_base_offset_mode;   // WINDOW: how shifted UMMA descriptors encode their start
+  int desc_base_offset_mode;
+  int m_sub_cap, a_slots_pref; // tuning knobs (env IFCB_CONV_MSUB / IFCB_CONV_ASLOTS)
+  int debug_flags;             // profiling only (IFCB_CONV_DEBUG): 1 skip TMA loads, 2 skip MMAs, 4 skip epilogue   // WINDOW: how shifted UMMA descriptors encode their start
   int fp16;                    // 16-bit operand/activation format: 0 bf16, 1 fp16
   const float* scale;
   const float* shift;

@@ -41,12 +41,14 @@ int resolve_driver() {
 }
 
 // Debug knob for the shifted UMMA descriptors of the window algorithm:
-// IFCB_WINDOW_BASE_OFFSET=0 leaves the descriptor base-offset field zero (default 1).
+// the hardware applies the 128B swizzle to ABSOLUTE shared-memory address bits, so the
+// descriptor base-offset field must stay zero (measured on B200: setting it to
+// (addr>>7)&7 corrupts every shifted tap).  IFCB_WINDOW_BASE_OFFSET=1 re-enables it.
 int g_base_offset_mode() {
   static int mode = -1;
   if (mode < 0) {
     const char* e = getenv("IFCB_WINDOW_BASE_OFFSET");
-    mode = (e && e[0] == '0') ? 0 : 1;
+    mode = (e && e[0] == '1') ? 1 : 0;
   }
   return mode;
 }
@@ -153,6 +155,14 @@ extern "C" int ifcb_plan_add_conv(ifcb_plan* plan, const ifcb_conv_desc* d) {
   kp.cout_pad = cout_pad;
   kp.fp16 = d->dtype;
   kp.desc_base_offset_mode = g_base_offset_mode();
+  {
+    const char* e = getenv("IFCB_CONV_DEBUG");
+    kp.debug_flags = e ? atoi(e) : 0;
+    const char* ms = getenv("IFCB_CONV_MSUB");
+    kp.m_sub_cap = ms ? atoi(ms) : 4;
+    const char* as = getenv("IFCB_CONV_ASLOTS");
+    kp.a_slots_pref = as ? atoi(as) : 2;
+  }
   kp.win_shift0 = (d->in_pad_h - d->pad_h) * Wp + (d->in_pad_w - d->pad_w);
   const int halo = kp.win_shift0 + (d->kh - 1) * Wp + (d->kw - 1);
   IFCB_ARG_CHECK(conv_plan_smem(kp, window, halo), "conv: no shared-memory plan for tile_n=%d halo=%d", tile_n, halo);
