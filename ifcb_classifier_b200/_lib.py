@@ -40,7 +40,7 @@ class StemDesc(C.Structure):
                 ('batch_cap', C.c_int32), ('H', C.c_int32), ('W', C.c_int32),
                 ('kh', C.c_int32), ('kw', C.c_int32), ('stride', C.c_int32), ('pad', C.c_int32),
                 ('Cout', C.c_int32), ('d_weight', C.c_void_p), ('d_scale', C.c_void_p),
-                ('d_shift', C.c_void_p), ('d_lut', C.c_void_p),
+                ('d_shift', C.c_void_p), ('d_wgray', C.c_void_p), ('d_wconst', C.c_void_p),
                 ('in_scale', C.c_float * 3), ('in_shift', C.c_float * 3),
                 ('d_out', C.c_void_p), ('out_ld', C.c_int32), ('relu', C.c_int32), ('dtype', C.c_int32),
                 ('out_pad_h', C.c_int32), ('out_pad_w', C.c_int32)]

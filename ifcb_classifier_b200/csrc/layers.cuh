@@ -11,18 +11,21 @@ namespace ifcb {
 struct ConvKernelParams {
   long long rows;              // GEMM rows of this launch (set per launch): batch * rows_per_img
   int rows_per_img, row_w;     // IM2COL: P*Q, Q        WINDOW: Hp*Wp, Wp (padded input)
+  unsigned long long magic_img, magic_w;   // floor((2^64-1)/d)+1 for d = rows_per_img, row_w (0: d == 1)
+  int identity_rows;           // GEMM row i is output pixel i of every (unpadded) destination: skip the row mapping
   int P, Q;                    // valid output extent per image
   int kh, kw, stride_h, stride_w, pad_h, pad_w;
-  int cblocks;                 // ceil(Cin / 64)
+  int row_bytes;               // operand row = one swizzle span: 128 (64 channels) or 64 (32 channels, Cin <= 32)
+  int cblocks;                 // ceil(Cin / channels per row)
   int last_ksteps;             // K=16 MMA steps in the last channel block (1..4)
   int tile_n, n_tiles, stages;
   int cout_pad;                // n_tiles * tile_n
   int m_sub;                   // 128-row accumulators per tile (WINDOW: 1, 2 or 4)
   int a_slots, a_slot_bytes, box_rows, n_boxes;   // WINDOW: A patch ring
+  int b_group;                 // WINDOW: filter taps per weight pipeline stage
   int win_shift0;              // WINDOW: (in_pad_h-pad_h)*Wp + (in_pad_w-pad_w) rows
-  int desc_base_offset_mode;
-  int m_sub_cap, a_slots_pref; // tuning knobs (env IFCB_CONV_MSUB / IFCB_CONV_ASLOTS)
-  int debug_flags;             // profiling only (IFCB_CONV_DEBUG): 1 skip TMA loads, 2 skip MMAs, 4 skip epilogue   // WINDOW: how shifted UMMA descriptors encode their start
+  int m_sub_cap, a_slots_pref, b_group_cap;   // tuning knobs (env IFCB_CONV_MSUB / _ASLOTS / _BGROUP)
+  int debug_flags;             // profiling only (IFCB_CONV_DEBUG): 1 skip TMA loads, 2 skip MMAs, 4 skip epilogue
   int fp16;                    // 16-bit operand/activation format: 0 bf16, 1 fp16
   const float* scale;
   const float* shift;

@@ -40,19 +40,6 @@ int resolve_driver() {
   return 0;
 }
 
-// Debug knob for the shifted UMMA descriptors of the window algorithm:
-// the hardware applies the 128B swizzle to ABSOLUTE shared-memory address bits, so the
-// descriptor base-offset field must stay zero (measured on B200: setting it to
-// (addr>>7)&7 corrupts every shifted tap).  IFCB_WINDOW_BASE_OFFSET=1 re-enables it.
-int g_base_offset_mode() {
-  static int mode = -1;
-  if (mode < 0) {
-    const char* e = getenv("IFCB_WINDOW_BASE_OFFSET");
-    mode = (e && e[0] == '1') ? 1 : 0;
-  }
-  return mode;
-}
-
 inline int out_dim(int in, int k, int stride, int pad) { return (in + 2 * pad - k) / stride + 1; }
 
 int pick_tile_n(int Cout, int hint) {
@@ -95,7 +82,7 @@ extern "C" int ifcb_conv_geometry(int Cin, int Cout, int kh, int kw, int tile_n_
   IFCB_ARG_CHECK(Cin > 0 && Cout > 0 && kh > 0 && kw > 0, "ifcb_conv_geometry: bad shape");
   IFCB_ARG_CHECK(tile_n_hint == 0 || (tile_n_hint % 16 == 0 && tile_n_hint >= 16 && tile_n_hint <= 256),
                  "ifcb_conv_geometry: tile_n must be a multiple of 16 in [16,256]");
-  const int cp = (Cin + 63) & ~63;
+  const int cp = Cin <= 32 ? 32 : ((Cin + 63) & ~63);      // 64-byte operand rows for the thin first layers
   const int tn = pick_tile_n(Cout, tile_n_hint);
   if (Cin_pad) *Cin_pad = cp;
   if (K_pad) *K_pad = kh * kw * cp;
@@ -147,14 +134,15 @@ extern "C" int ifcb_plan_add_conv(ifcb_plan* plan, const ifcb_conv_desc* d) {
   kp.kh = d->kh; kp.kw = d->kw;
   kp.stride_h = d->stride_h; kp.stride_w = d->stride_w;
   kp.pad_h = d->pad_h; kp.pad_w = d->pad_w;
-  kp.cblocks = cin_pad / 64;
-  const int last = d->Cin - (kp.cblocks - 1) * 64;
+  const int row_elems = cin_pad == 32 ? 32 : 64;
+  kp.row_bytes = row_elems * 2;
+  kp.cblocks = cin_pad / row_elems;
+  const int last = d->Cin - (kp.cblocks - 1) * row_elems;
   kp.last_ksteps = (last + 15) / 16;
   kp.tile_n = tile_n;
   kp.n_tiles = cout_pad / tile_n;
   kp.cout_pad = cout_pad;
   kp.fp16 = d->dtype;
-  kp.desc_base_offset_mode = g_base_offset_mode();
   {
     const char* e = getenv("IFCB_CONV_DEBUG");
     kp.debug_flags = e ? atoi(e) : 0;
@@ -162,6 +150,8 @@ extern "C" int ifcb_plan_add_conv(ifcb_plan* plan, const ifcb_conv_desc* d) {
     kp.m_sub_cap = ms ? atoi(ms) : 4;
     const char* as = getenv("IFCB_CONV_ASLOTS");
     kp.a_slots_pref = as ? atoi(as) : 2;
+    const char* bg = getenv("IFCB_CONV_BGROUP");
+    kp.b_group_cap = bg ? atoi(bg) : 0;
   }
   kp.win_shift0 = (d->in_pad_h - d->pad_h) * Wp + (d->in_pad_w - d->pad_w);
   const int halo = kp.win_shift0 + (d->kh - 1) * Wp + (d->kw - 1);
@@ -194,17 +184,26 @@ extern "C" int ifcb_plan_add_conv(ifcb_plan* plan, const ifcb_conv_desc* d) {
     kp.seg_pad_w[s] = sg.pad_w;
     kp.seg_out[s] = reinterpret_cast<__nv_bfloat16*>(sg.d_out);
   }
+  {
+    auto magic = [](int dv) -> unsigned long long { return dv <= 1 ? 0ull : (~0ull) / (unsigned long long)dv + 1ull; };
+    kp.magic_img = magic(kp.rows_per_img);
+    kp.magic_w = magic(kp.row_w);
+    bool ident = !window && (!d->d_residual || (d->res_pad_h == 0 && d->res_pad_w == 0));
+    for (int sgi = 0; sgi < d->n_seg; ++sgi) ident = ident && d->seg[sgi].pad_h == 0 && d->seg[sgi].pad_w == 0;
+    kp.identity_rows = ident ? 1 : 0;
+  }
   L.conv.batch_cap = d->batch_cap;
   const CUtensorMapDataType dt = d->dtype == IFCB_ACT_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  const CUtensorMapSwizzle swz = kp.row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
 
   if (window) {
     // --- A: tiled 2-D map over the padded input viewed as [batch_cap*Hp*Wp, Cin] ---
     cuuint64_t gdim[2] = {(cuuint64_t)d->Cin, (cuuint64_t)d->batch_cap * Hp * Wp};
     cuuint64_t gstr[1] = {(cuuint64_t)d->in_ld * 2};
-    cuuint32_t box[2] = {64, (cuuint32_t)kp.box_rows};
+    cuuint32_t box[2] = {(cuuint32_t)row_elems, (cuuint32_t)kp.box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = g_encode_tiled(&L.conv.tmap_a, dt, 2, const_cast<void*>(d->d_in), gdim, gstr, box, estr,
-                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     IFCB_ARG_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) for window input rows=%d", (int)r, kp.box_rows);
   } else {
@@ -216,8 +215,8 @@ extern "C" int ifcb_plan_add_conv(ifcb_plan* plan, const ifcb_conv_desc* d) {
     int upper[2] = {d->pad_w - (d->kw - 1), d->pad_h - (d->kh - 1)};
     cuuint32_t estr[4] = {1, (cuuint32_t)d->stride_w, (cuuint32_t)d->stride_h, 1};
     CUresult r = g_encode_im2col(&L.conv.tmap_a, dt, 4, const_cast<char*>(base), gdim, gstr, lower, upper,
-                                 /*channelsPerPixel=*/64, /*pixelsPerColumn=*/128, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                 /*channelsPerPixel=*/(cuuint32_t)row_elems, /*pixelsPerColumn=*/128, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     IFCB_ARG_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeIm2col failed (%d) for conv %dx%d Cin=%d H=%d W=%d", (int)r,
                    d->kh, d->kw, d->Cin, d->H, d->W);
@@ -232,10 +231,10 @@ extern "C" int ifcb_plan_add_conv(ifcb_plan* plan, const ifcb_conv_desc* d) {
   {
     cuuint64_t gdim[2] = {(cuuint64_t)k_pad, (cuuint64_t)cout_pad};
     cuuint64_t gstr[1] = {(cuuint64_t)k_pad * 2};
-    cuuint32_t box[2] = {64, (cuuint32_t)tile_n};
+    cuuint32_t box[2] = {(cuuint32_t)row_elems, (cuuint32_t)tile_n};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = g_encode_tiled(&L.conv.tmap_b, dt, 2, const_cast<void*>(d->d_weight), gdim, gstr, box, estr,
-                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     IFCB_ARG_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) for weights K_pad=%d Cout_pad=%d", (int)r,
                    k_pad, cout_pad);
@@ -246,10 +245,12 @@ extern "C" int ifcb_plan_add_conv(ifcb_plan* plan, const ifcb_conv_desc* d) {
 
 extern "C" int ifcb_plan_add_stem(ifcb_plan* plan, const ifcb_stem_desc* d) {
   IFCB_ARG_CHECK(plan && d, "ifcb_plan_add_stem: null argument");
-  IFCB_ARG_CHECK(d->d_in && d->d_weight && d->d_scale && d->d_shift && d->d_out, "stem: null tensor pointer");
+  IFCB_ARG_CHECK(d->d_in && d->d_scale && d->d_shift && d->d_out, "stem: null tensor pointer");
   IFCB_ARG_CHECK(d->Cout == 32 || d->Cout == 64, "stem: Cout=%d unsupported (32 or 64)", d->Cout);
   IFCB_ARG_CHECK(d->in_kind == IFCB_STEM_IN_U8_GRAY || d->in_kind == IFCB_STEM_IN_F32_NCHW, "stem: bad in_kind");
-  IFCB_ARG_CHECK(d->in_kind != IFCB_STEM_IN_U8_GRAY || d->d_lut, "stem: u8 input needs d_lut");
+  IFCB_ARG_CHECK(d->in_kind != IFCB_STEM_IN_U8_GRAY || (d->d_wgray && (d->pad == 0 || d->d_wconst)),
+                 "stem: u8 input needs d_wgray (and d_wconst when pad > 0)");
+  IFCB_ARG_CHECK(d->in_kind != IFCB_STEM_IN_F32_NCHW || d->d_weight, "stem: f32 input needs d_weight");
   IFCB_ARG_CHECK(d->out_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(d->d_out) & 15) == 0,
                  "stem: output must be 16-byte aligned with ld %% 8 == 0");
   Layer L{};

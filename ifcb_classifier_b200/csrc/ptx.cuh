@@ -12,6 +12,22 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// One lane of the (converged) warp: elect.sync.  Loops around it stay warp-uniform so the
+// compiler keeps descriptors / coordinates in uniform registers (no per-instruction
+// R2UR waterfall, which costs ~25 instructions per tcgen05.mma when issued under
+// `if (lane == 0)`).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- mbarrier ------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -32,6 +48,20 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity
       "{\n"
       ".reg .pred p;\n"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok;
+}
+// Non-blocking phase test (no suspend): lets a consumer peek at the NEXT stage early.
+__device__ __forceinline__ uint32_t mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
       "selp.u32 %0, 1, 0, p;\n"
       "}\n"
       : "=r"(ok)
@@ -116,6 +146,35 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same, descriptors passed as 32-bit halves: only the low word (start address, 14 bits of
+// addr >> 4, plus LBO) changes between MMAs; the high word (SBO, version, swizzle mode) is
+// a constant -- keeps the issue loop to a couple of integer adds per MMA.
+__device__ __forceinline__ void umma_f16_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi,
+                                              uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 da, db;\n"
+      "mov.b64 da, {%1, %3};\n"
+      "mov.b64 db, {%2, %3};\n"
+      "setp.ne.b32 p, %5, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// low / high words of the K-major swizzled operand descriptor: rows of `row_bytes` (one
+// swizzle span: 128 -> SWIZZLE_128B, 64 -> SWIZZLE_64B), 8-row groups 8*row_bytes apart.
+// lo: start address >> 4 (14 bits) | LBO = 1 (unused for swizzled K-major);
+// hi: SBO = (8*row_bytes) >> 4 | descriptor version 1 (bit 46) | layout type (bits 61-63:
+// 2 = SWIZZLE_128B, 4 = SWIZZLE_64B).  The base-offset field stays 0: the hardware applies
+// the swizzle to absolute shared-memory address bits (measured on B200), so a start
+// address shifted by whole rows needs no correction.
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr) { return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16); }
+__device__ __forceinline__ uint32_t umma_desc_hi(int row_bytes) {
+  return (uint32_t)((8 * row_bytes) >> 4) | (1u << 14) | ((row_bytes == 128 ? 2u : 4u) << 29);
+}
+
 // Arrive on an mbarrier once all previously issued MMAs of this thread complete.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -135,20 +194,6 @@ __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// K-major, 128-byte-swizzled shared-memory operand descriptor (rows of 64 bf16 =
-// 128 B, 8-row groups 1024 B apart): start>>4 | LBO=1 | SBO=1024>>4 | version 1 |
-// layout SWIZZLE_128B (2).  Tile base must be 1024-byte aligned.
-__device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
-  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-}
-// Same layout, start address shifted by whole 128-byte rows (not 1024-byte aligned): the
-// descriptor's base-offset field (bits 49-51) carries (addr >> 7) & 7 so that the hardware
-// applies the swizzle phase of the absolute address (mode 1); mode 0 leaves it zero.
-__device__ __forceinline__ uint64_t umma_desc_k_sw128_shifted(uint32_t smem_addr, int mode) {
-  uint64_t d = umma_desc_k_sw128(smem_addr);
-  if (mode) d |= (uint64_t)((smem_addr >> 7) & 7u) << 49;
-  return d;
-}
 // kind::f16 instruction descriptor: fp32 accumulate, A/B both bf16 (format 1) or both
 // fp16 (format 0), both K-major, M x N.
 __host__ __device__ inline uint32_t umma_idesc_f16(int M, int N, int fp16) {

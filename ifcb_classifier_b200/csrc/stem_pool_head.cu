@@ -86,6 +86,83 @@ __global__ void __launch_bounds__(128) stem_kernel(const ifcb_stem_desc d, const
 }
 
 // ------------------------------------------------------------------------------
+// Stem, gray fast path.  The three network input channels are affine functions of
+// the SAME gray level g: x_c = a_c * g/255 + b_c (ToTensor, --img-norm, transform_input).
+// So sum_c w[co][c][tap] * x_c = wg[tap][co] * g + wc[tap][co] with host-folded
+//   wg = sum_c w*a_c/255,  wc = sum_c w*b_c   (computed in float64):
+// a 1-channel convolution with kh*kw FMAs per output instead of 3*kh*kw.  For pad == 0
+// every tap is in bounds and sum_tap wc is folded into the BN shift by the host
+// (HASPAD = false); with padding the constant is added per in-bounds tap.
+// ------------------------------------------------------------------------------
+template <int COUT, bool HASPAD>
+__global__ void __launch_bounds__(128) stem_gray_kernel(const ifcb_stem_desc d, int P, int Q, long long total) {
+  extern __shared__ float sm[];
+  const int taps = d.kh * d.kw;
+  float* wg = sm;                        // [taps][COUT]
+  float* wc = sm + taps * COUT;          // [taps][COUT] (HASPAD only)
+  for (int i = threadIdx.x; i < taps * COUT; i += blockDim.x) {
+    wg[i] = d.d_wgray[i];
+    if (HASPAD) wc[i] = d.d_wconst[i];
+  }
+  __syncthreads();
+  const long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= total) return;
+  const int PQ = P * Q;
+  const int img = (int)(pix / PQ);
+  const int rem = (int)(pix - (long long)img * PQ);
+  const int op = rem / Q, oq = rem - op * Q;
+  const int h0 = op * d.stride - d.pad, w0 = oq * d.stride - d.pad;
+  const uint8_t* in = reinterpret_cast<const uint8_t*>(d.d_in) + (long long)img * d.H * d.W;
+  float acc[COUT];
+#pragma unroll
+  for (int c = 0; c < COUT; ++c) acc[c] = 0.f;
+  for (int r = 0; r < d.kh; ++r) {
+    const int hh = h0 + r;
+    if (HASPAD && (hh < 0 || hh >= d.H)) continue;
+    for (int s = 0; s < d.kw; ++s) {
+      const int ww = w0 + s;
+      if (HASPAD && (ww < 0 || ww >= d.W)) continue;
+      const float g = (float)in[(long long)hh * d.W + ww];
+      const float4* wk = reinterpret_cast<const float4*>(wg + (r * d.kw + s) * COUT);
+      const float4* ck = reinterpret_cast<const float4*>(wc + (r * d.kw + s) * COUT);
+#pragma unroll
+      for (int c4 = 0; c4 < COUT / 4; ++c4) {
+        const float4 w = wk[c4];
+        if (HASPAD) {
+          const float4 k = ck[c4];
+          acc[4 * c4 + 0] += fmaf(g, w.x, k.x);
+          acc[4 * c4 + 1] += fmaf(g, w.y, k.y);
+          acc[4 * c4 + 2] += fmaf(g, w.z, k.z);
+          acc[4 * c4 + 3] += fmaf(g, w.w, k.w);
+        } else {
+          acc[4 * c4 + 0] = fmaf(g, w.x, acc[4 * c4 + 0]);
+          acc[4 * c4 + 1] = fmaf(g, w.y, acc[4 * c4 + 1]);
+          acc[4 * c4 + 2] = fmaf(g, w.z, acc[4 * c4 + 2]);
+          acc[4 * c4 + 3] = fmaf(g, w.w, acc[4 * c4 + 3]);
+        }
+      }
+    }
+  }
+  const long long orow = ((long long)img * (P + 2 * d.out_pad_h) + op + d.out_pad_h) * (Q + 2 * d.out_pad_w) + oq + d.out_pad_w;
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(d.d_out) + orow * d.out_ld;
+#pragma unroll
+  for (int c = 0; c < COUT; c += 8) {
+    float y[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      y[j] = fmaf(acc[c + j], __ldg(d.d_scale + c + j), __ldg(d.d_shift + c + j));
+      if (d.relu) y[j] = fmaxf(y[j], 0.f);
+    }
+    uint4 o;
+    o.x = pack_act2(y[0], y[1], d.dtype);
+    o.y = pack_act2(y[2], y[3], d.dtype);
+    o.z = pack_act2(y[4], y[5], d.dtype);
+    o.w = pack_act2(y[6], y[7], d.dtype);
+    *reinterpret_cast<uint4*>(out + c) = o;
+  }
+}
+
+// ------------------------------------------------------------------------------
 // Pooling over NHWC bf16: one thread = one output pixel x 8 channels (16 bytes).
 // ------------------------------------------------------------------------------
 template <bool AVG>
@@ -226,26 +303,39 @@ int launch_stem(const StemLayer& L, int batch, cudaStream_t stream) {
   const long long total = (long long)batch * L.P * L.Q;
   if (total == 0) return 0;
   const int taps = d.kh * d.kw;
-  const int smem = (taps * 3 * d.Cout + 768) * (int)sizeof(float);
   const unsigned grid = (unsigned)((total + 127) / 128);
-  const float* lut = reinterpret_cast<const float*>(d.d_lut);
-#define IFCB_STEM_LAUNCH(CO, U8)                                                                     \
-  do {                                                                                               \
-    if (smem > 48 * 1024)                                                                            \
-      IFCB_CUDA_CHECK(cudaFuncSetAttribute(stem_kernel<CO, U8>,                                      \
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, smem));      \
-    stem_kernel<CO, U8><<<grid, 128, smem, stream>>>(d, lut, L.P, L.Q, total);                       \
-  } while (0)
-  const bool u8 = d.in_kind == IFCB_STEM_IN_U8_GRAY;
-  if (d.Cout == 32) {
-    if (u8) IFCB_STEM_LAUNCH(32, true); else IFCB_STEM_LAUNCH(32, false);
-  } else if (d.Cout == 64) {
-    if (u8) IFCB_STEM_LAUNCH(64, true); else IFCB_STEM_LAUNCH(64, false);
-  } else {
+  if (d.Cout != 32 && d.Cout != 64) {
     set_error("stem: Cout=%d unsupported (32 or 64)", d.Cout);
     return -1;
   }
+  if (d.in_kind == IFCB_STEM_IN_U8_GRAY) {
+    const bool haspad = d.pad > 0;
+    const int smem = taps * d.Cout * (haspad ? 2 : 1) * (int)sizeof(float);
+#define IFCB_GRAY_LAUNCH(CO, HP)                                                                          \
+  do {                                                                                                    \
+    if (smem > 48 * 1024)                                                                                 \
+      IFCB_CUDA_CHECK(cudaFuncSetAttribute(stem_gray_kernel<CO, HP>,                                      \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, smem));           \
+    stem_gray_kernel<CO, HP><<<grid, 128, smem, stream>>>(d, L.P, L.Q, total);                            \
+  } while (0)
+    if (d.Cout == 32) {
+      if (haspad) IFCB_GRAY_LAUNCH(32, true); else IFCB_GRAY_LAUNCH(32, false);
+    } else {
+      if (haspad) IFCB_GRAY_LAUNCH(64, true); else IFCB_GRAY_LAUNCH(64, false);
+    }
+#undef IFCB_GRAY_LAUNCH
+  } else {
+    const int smem = (taps * 3 * d.Cout + 768) * (int)sizeof(float);
+#define IFCB_STEM_LAUNCH(CO)                                                                              \
+  do {                                                                                                    \
+    if (smem > 48 * 1024)                                                                                 \
+      IFCB_CUDA_CHECK(cudaFuncSetAttribute(stem_kernel<CO, false>,                                        \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, smem));           \
+    stem_kernel<CO, false><<<grid, 128, smem, stream>>>(d, nullptr, L.P, L.Q, total);                     \
+  } while (0)
+    if (d.Cout == 32) IFCB_STEM_LAUNCH(32); else IFCB_STEM_LAUNCH(64);
 #undef IFCB_STEM_LAUNCH
+  }
   IFCB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

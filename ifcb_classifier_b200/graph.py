@@ -163,18 +163,32 @@ class PlanBuilder(object):
         self._note(name, 'conv', 2 * P * Q * Co * Ci * kh * kw)
         return [m['out'] for m in members]
 
-    def stem(self, inp, in_kind, H, W, weight, scale, shift, stride, pad, out, lut=None,
+    def stem(self, inp, in_kind, H, W, weight, scale, shift, stride, pad, out, affine=None,
              in_scale=(1, 1, 1), in_shift=(0, 0, 0), name='stem'):
+        """First conv.  ``affine`` = (a[3], b[3]) with x_c = a_c * g/255 + b_c for the u8 gray
+        input (see ``input_affine``); f32 input uses in_scale / in_shift (transform_input)."""
         Co, _, kh, kw = [int(v) for v in weight.shape]
-        wk = weight.float().permute(2, 3, 1, 0).reshape(kh * kw * 3, Co)      # k = (r*kw+s)*3 + c
         d = StemDesc()
         d.d_in, d.in_kind = inp.data_ptr(), in_kind
         d.batch_cap, d.H, d.W = self.batch_cap, H, W
         d.kh, d.kw, d.stride, d.pad, d.Cout = kh, kw, stride, pad, Co
-        d.d_weight = self.dev(wk, torch.float32).data_ptr()
+        scale, shift = scale.double(), shift.double()
+        if in_kind == IFCB_STEM_IN_U8_GRAY:
+            a = torch.tensor(affine[0], dtype=torch.float64)
+            b = torch.tensor(affine[1], dtype=torch.float64)
+            w64 = weight.double()                                               # [Co, 3, kh, kw]
+            wg = (w64 * a[None, :, None, None]).sum(1) / 255.0                  # [Co, kh, kw]
+            wc = (w64 * b[None, :, None, None]).sum(1)
+            d.d_wgray = self.dev(wg.permute(1, 2, 0).reshape(kh * kw, Co), torch.float32).data_ptr()
+            if pad > 0:
+                d.d_wconst = self.dev(wc.permute(1, 2, 0).reshape(kh * kw, Co), torch.float32).data_ptr()
+            else:
+                shift = shift + scale * wc.sum((1, 2))                          # every tap in bounds
+        else:
+            wk = weight.float().permute(2, 3, 1, 0).reshape(kh * kw * 3, Co)    # k = (r*kw+s)*3 + c
+            d.d_weight = self.dev(wk, torch.float32).data_ptr()
         d.d_scale = self.dev(scale, torch.float32).data_ptr()
         d.d_shift = self.dev(shift, torch.float32).data_ptr()
-        d.d_lut = self.dev(lut, torch.float32).data_ptr() if lut is not None else None
         for c in range(3):
             d.in_scale[c], d.in_shift[c] = float(in_scale[c]), float(in_shift[c])
         d.d_out, d.out_ld, d.relu = out.ptr, out.ld, 1
@@ -261,6 +275,21 @@ def input_lut(img_norm=None, transform_input=False):
     return torch.from_numpy(x.astype(np.float32).copy())
 
 
+def input_affine(img_norm=None, transform_input=False):
+    """(a[3], b[3]) in float64 with  x_c = a_c * (g/255) + b_c  -- the composition of ToTensor,
+    Normalize (neuston_data.py:462-463) and torchvision's _transform_input (inception.py:95-101)."""
+    a, b = [1.0, 1.0, 1.0], [0.0, 0.0, 0.0]
+    if img_norm:
+        mean, std = img_norm
+        a = [1.0 / float(s_) for s_ in std]
+        b = [-float(m_) / float(s_) for m_, s_ in zip(mean, std)]
+    if transform_input:
+        ts, tb = transform_input_affine()
+        a = [a_ * t_ for a_, t_ in zip(a, ts)]
+        b = [b_ * t_ + o_ for b_, t_, o_ in zip(b, ts, tb)]
+    return a, b
+
+
 def transform_input_affine():
     """(scale[3], shift[3]) of torchvision Inception3._transform_input."""
     s = [0.229 / 0.5, 0.224 / 0.5, 0.225 / 0.5]
@@ -283,7 +312,7 @@ def _raw(sd, prefix, out):
     return dict(weight=w, scale=torch.ones(co), shift=torch.zeros(co), relu=False, out=out)
 
 
-def build_inception_v3(pb, sd, inp, in_kind, R, lut=None, transform_input=False, fuse=True):
+def build_inception_v3(pb, sd, inp, in_kind, R, affine=None, transform_input=False, fuse=True):
     """Appends the eval-mode Inception-v3 graph to ``pb``; returns the softmax scores tensor."""
     eps = 1e-3
     sz = lambda h, k, s, p: (h + 2 * p - k) // s + 1
@@ -313,7 +342,7 @@ def build_inception_v3(pb, sd, inp, in_kind, R, lut=None, transform_input=False,
     a = pb.alloc(H1, H1, 32)
     sc, sh = fold_bn(sd, 'Conv2d_1a_3x3.bn', eps)
     ts, tb = transform_input_affine() if transform_input else ((1, 1, 1), (0, 0, 0))
-    pb.stem(inp, in_kind, R, R, sd['Conv2d_1a_3x3.conv.weight'], sc, sh, 2, 0, a, lut=lut,
+    pb.stem(inp, in_kind, R, R, sd['Conv2d_1a_3x3.conv.weight'], sc, sh, 2, 0, a, affine=affine,
             in_scale=ts, in_shift=tb, name='Conv2d_1a_3x3')
     a = single(a, 'Conv2d_2a_3x3', 3, out_pad=(1, 1))
     a = single(a, 'Conv2d_2b_3x3', 3, pad=(1, 1))
@@ -412,7 +441,7 @@ RESNET_CFG = {
 }
 
 
-def build_resnet(pb, sd, arch, inp, in_kind, R, lut=None):
+def build_resnet(pb, sd, arch, inp, in_kind, R, affine=None):
     eps = 1e-5
     kind, layers = RESNET_CFG[arch]
     sz = lambda h, k, s, p: (h + 2 * p - k) // s + 1
@@ -431,7 +460,7 @@ def build_resnet(pb, sd, arch, inp, in_kind, R, lut=None):
     H1 = sz(R, 7, 2, 3)
     a = pb.alloc(H1, H1, 64)
     sc, sh = fold_bn(sd, 'bn1', eps)
-    pb.stem(inp, in_kind, R, R, sd['conv1.weight'], sc, sh, 2, 3, a, lut=lut, name='conv1')
+    pb.stem(inp, in_kind, R, R, sd['conv1.weight'], sc, sh, 2, 3, a, affine=affine, name='conv1')
     x = pb.alloc(sz(H1, 3, 2, 1), sz(H1, 3, 2, 1), 64, blk_pad)
     pb.pool(IFCB_POOL_MAX, a, 3, 2, 1, x, name='maxpool')
     nlayers = len(layers)
@@ -475,15 +504,15 @@ class CompiledNet(object):
         if in_kind == 'u8':
             self.inp = torch.zeros((batch_cap, self.R, self.R), dtype=torch.uint8, device=self.device)
             kind = IFCB_STEM_IN_U8_GRAY
-            lut = input_lut(img_norm, transform_input and arch == 'inception_v3')
+            affine = input_affine(img_norm, transform_input and arch == 'inception_v3')
         else:
             self.inp = torch.zeros((batch_cap, 3, self.R, self.R), dtype=torch.float32, device=self.device)
             kind = IFCB_STEM_IN_F32_NCHW
-            lut = None
+            affine = None
         if arch == 'inception_v3':
-            build_inception_v3(pb, sd, self.inp, kind, self.R, lut=lut, transform_input=transform_input, fuse=fuse)
+            build_inception_v3(pb, sd, self.inp, kind, self.R, affine=affine, transform_input=transform_input, fuse=fuse)
         elif arch in RESNET_CFG:
-            build_resnet(pb, sd, arch, self.inp, kind, self.R, lut=lut)
+            build_resnet(pb, sd, arch, self.inp, kind, self.R, affine=affine)
         else:
             raise KeyError('model unknown!')
         self.pb = pb

@@ -121,9 +121,10 @@ enum { IFCB_CONV_AUTO = 0, IFCB_CONV_IM2COL = 1, IFCB_CONV_WINDOW = 2 };
  *               of a tile is loaded ONCE and filter taps are shifted UMMA descriptors;
  *               IFCB_CONV_AUTO picks WINDOW whenever it applies
  *   d_residual  view with the output's logical extent and its own zero border res_pad_*
- *   d_weight    bf16 [Cout_pad, kh*kw*Cin_pad] packed by the host: K index =
- *               (r*kw + s)*Cin_pad + ci, Cin_pad = round_up(Cin, 64), zero
- *               filled; Cout_pad = n_tiles * tile_n
+ *   d_weight    16-bit [Cout_pad, kh*kw*Cin_pad] packed by the host: K index =
+ *               (r*kw + s)*Cin_pad + ci, zero filled; Cin_pad = 32 for Cin <= 32 (64-byte
+ *               operand rows), else round_up(Cin, 64); Cout_pad = n_tiles * tile_n
+ *               (ifcb_conv_geometry returns all four)
  *   d_scale/d_shift  float32[Cout_pad] folded BN (gamma/sqrt(var+eps), beta - mean*that)
  *   d_residual  optional bf16 view added before the activation (ResNet), or NULL
  *   tile_n      GEMM N tile (multiple of 16, 16..256); 0 = library picks
@@ -153,15 +154,18 @@ int ifcb_plan_add_conv(ifcb_plan* plan, const ifcb_conv_desc* desc);
 int ifcb_conv_geometry(int Cin, int Cout, int kh, int kw, int tile_n_hint,
                        int32_t* Cin_pad, int32_t* K_pad, int32_t* tile_n, int32_t* Cout_pad);
 
-/* Stem: first convolution (Cin = 3) computed directly in fp32 on CUDA cores
- * from either the resized gray plane (u8) or a float32 NCHW [batch,3,H,W]
- * tensor (drop-in forward(x)).  Output bf16 NHWC.
+/* Stem: first convolution (Cin = 3) computed directly in fp32 on CUDA cores from either
+ * the resized gray plane (u8) or a float32 NCHW [batch,3,H,W] tensor (drop-in forward(x)).
+ * Output 16-bit NHWC.
  *   d_weight float32 [kh*kw*3, Cout] (k = (r*kw+s)*3 + c), d_scale/d_shift [Cout]
- *   u8 input : x_c = d_lut[c*256 + g]; the host fills the 3x256 float32 table
- *              with ToTensor (g/255), --img-norm ((x-mean)/std) and torchvision's
- *              transform_input (inception.py:95-101) evaluated exactly as torch
- *              does, so the stem sees the same fp32 values as the reference.
- *   f32 input: x_c = in[c] * in_scale[c] + in_shift[c] (transform_input only).
+ *   f32 input: x_c = in[c] * in_scale[c] + in_shift[c] (torchvision transform_input,
+ *              inception.py:95-101; identity otherwise).
+ *   u8 input : the three channels are affine in the gray level g,
+ *              x_c = a_c * g/255 + b_c (ToTensor, --img-norm, transform_input), so the host
+ *              folds the weights to one channel: d_wgray[tap][co] = sum_c w*a_c/255 and
+ *              d_wconst[tap][co] = sum_c w*b_c (float64 -> float32).  d_wconst is read only
+ *              when pad > 0 (per in-bounds tap); for pad == 0 the host adds
+ *              scale*sum_tap wconst to d_shift.  d_weight is unused for u8 input.
  */
 enum { IFCB_STEM_IN_U8_GRAY = 0, IFCB_STEM_IN_F32_NCHW = 1 };
 typedef struct {
@@ -173,7 +177,8 @@ typedef struct {
   const float* d_weight;
   const float* d_scale;
   const float* d_shift;
-  const float* d_lut;       /* u8 input only */
+  const float* d_wgray;     /* u8 input only: [kh*kw, Cout] */
+  const float* d_wconst;    /* u8 input with pad > 0: [kh*kw, Cout] */
   float in_scale[3], in_shift[3];
   void* d_out;
   int32_t out_ld;

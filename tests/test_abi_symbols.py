@@ -41,6 +41,8 @@ def test_argument_errors_are_status_codes(built_lib):
     assert rc < 0 and b'tile_n' in built_lib.ifcb_last_error()
     g = _lib.conv_geometry(80, 192, 3, 3)
     assert g == dict(Cin_pad=128, K_pad=1152, tile_n=192, Cout_pad=192)
+    assert _lib.conv_geometry(32, 64, 3, 3) == dict(Cin_pad=32, K_pad=288, tile_n=64, Cout_pad=64)
+    assert _lib.conv_geometry(48, 64, 5, 5)['Cin_pad'] == 64
     g = _lib.conv_geometry(2048, 1344, 1, 1)
     assert g['tile_n'] == 224 and g['Cout_pad'] == 1344
     assert built_lib.ifcb_plan_num_layers(None) == -1

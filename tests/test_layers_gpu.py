@@ -43,14 +43,18 @@ def border_is_zero(v):
     return float(t.abs().max()) == 0.0
 
 
-def swizzle_decode(raw_u8):
-    """raw 16 KiB 128B-swizzled tile -> [128 rows, 64] bf16 values (as float)."""
-    raw = raw_u8.view(128, 8, 16)
+def swizzle_decode(raw_u8, row_bytes=128):
+    """raw swizzled operand tile (128 rows of one swizzle span: 128 B = SWIZZLE_128B, 64 B =
+    SWIZZLE_64B) -> [128 rows, row_bytes/2] bf16 values (as float).  16-byte chunk j of the row
+    at byte address a sits at chunk j ^ ((a >> 7) & (chunks - 1))."""
+    chunks = row_bytes // 16
+    raw = raw_u8[:128 * row_bytes].view(128, chunks, 16)
     rows = torch.arange(128)
+    phase = ((rows * row_bytes) >> 7) & (chunks - 1)
     out = torch.empty_like(raw)
-    for j in range(8):
-        out[rows, j] = raw[rows, (j ^ (rows % 8))]
-    return out.reshape(128, 128).contiguous().view(torch.bfloat16).float()
+    for j in range(chunks):
+        out[rows, j] = raw[rows, (j ^ phase)]
+    return out.reshape(128, row_bytes).contiguous().view(torch.bfloat16).float()
 
 
 CONV_CASES = [
@@ -63,6 +67,8 @@ CONV_CASES = [
     ('7x1_160_192', 3, 160, 17, 17, 192, 7, 1, (1, 1), (3, 0)),
     ('3x3p1_448_384', 5, 448, 8, 8, 384, 3, 3, (1, 1), (1, 1)),
     ('3x3_32_32', 2, 32, 21, 21, 32, 3, 3, (1, 1), (0, 0)),
+    ('3x3p1_32_64', 2, 32, 19, 19, 64, 3, 3, (1, 1), (1, 1)),
+    ('3x3s2_16_48', 2, 16, 19, 19, 48, 3, 3, (2, 2), (0, 0)),
     ('3x3_80_192', 1, 80, 23, 23, 192, 3, 3, (1, 1), (0, 0)),
     ('1x1s2_64_128', 2, 64, 56, 56, 128, 1, 1, (2, 2), (0, 0)),
     ('3x3s2p1_64_128', 2, 64, 28, 28, 128, 3, 3, (2, 2), (1, 1)),
@@ -106,15 +112,16 @@ def test_im2col_tma_probe(cuda):
                            relu=False, out=out)], stride, pad, algo=1)
         raw = torch.zeros(16384, dtype=torch.uint8, device=cuda)
         xp = F.pad(bf16r(x), (pad[1], pad[1], pad[0], pad[0]))
-        for (m0, r, s, cb) in [(0, 0, 0, 0), (128, kh - 1, kw - 1, 0), (P * Q - 5, 0, kw - 1, (Cin - 1) // 64)]:
+        for (m0, r, s, cb) in [(0, 0, 0, 0), (128, kh - 1, kw - 1, 0), (P * Q - 5, 0, kw - 1, 0 if Cin <= 32 else (Cin - 1) // 64)]:
             img, rem = divmod(m0, P * Q)
             op, oq = divmod(rem, Q)
             stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
             _lib.check(_lib.lib().ifcb_debug_im2col_probe(pb.handle, 0, cb * 64, oq * stride[1] - pad[1],
                                                           op * stride[0] - pad[0], img, s, r, raw.data_ptr(), stream))
             torch.cuda.synchronize()
-            tile = swizzle_decode(raw.cpu())
-            want = torch.zeros(128, 64)
+            relems = 32 if Cin <= 32 else 64          # thin layers use 64-byte operand rows
+            tile = swizzle_decode(raw.cpu(), 2 * relems)
+            want = torch.zeros(128, relems)
             for i in range(128):
                 m = m0 + i
                 n_, rem_ = divmod(m, P * Q)
@@ -273,7 +280,7 @@ def test_pools(cuda):
 
 
 def test_stem_u8_and_f32(cuda):
-    from ifcb_classifier_b200.graph import PlanBuilder, input_lut
+    from ifcb_classifier_b200.graph import PlanBuilder, input_lut, input_affine
     from ifcb_classifier_b200._lib import IFCB_STEM_IN_U8_GRAY, IFCB_STEM_IN_F32_NCHW
     g = torch.Generator().manual_seed(3)
     B, R = 2, 61
@@ -290,7 +297,7 @@ def test_stem_u8_and_f32(cuda):
             pb = PlanBuilder(B, cuda, 'bf16')
             pb.keep.append(inp)
             out = pb.alloc(P, P, Co)
-            pb.stem(inp, kind, R, R, w, sc, sh, stride, pad, out, lut=lut)
+            pb.stem(inp, kind, R, R, w, sc, sh, stride, pad, out, affine=input_affine((mean, std), False))
             pb.run(B)
             torch.cuda.synchronize()
             _check(to_nchw(out.t), want, 'stem %d kind %d' % (Co, kind))

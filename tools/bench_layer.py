@@ -27,7 +27,7 @@ LAYERS = [
 
 
 def time_layer(layer, algo, env):
-    for k in ('IFCB_CONV_DEBUG', 'IFCB_CONV_MSUB', 'IFCB_CONV_ASLOTS'):
+    for k in ('IFCB_CONV_DEBUG', 'IFCB_CONV_MSUB', 'IFCB_CONV_ASLOTS', 'IFCB_CONV_BGROUP'):
         os.environ.pop(k, None)
     os.environ.update(env)
     name, Cin, H, W, Cout, kh, kw, pad = layer
@@ -59,21 +59,17 @@ def time_layer(layer, algo, env):
 
 CONFIGS = [
     ('im2col', 1, {}),
-    ('im2col noload', 1, {'IFCB_CONV_DEBUG': '1'}),
     ('im2col nomma', 1, {'IFCB_CONV_DEBUG': '2'}),
     ('im2col noepi', 1, {'IFCB_CONV_DEBUG': '4'}),
     ('im2col mma-only', 1, {'IFCB_CONV_DEBUG': '5'}),
     ('window', 2, {}),
-    ('window noload', 2, {'IFCB_CONV_DEBUG': '1'}),
     ('window nomma', 2, {'IFCB_CONV_DEBUG': '2'}),
     ('window noepi', 2, {'IFCB_CONV_DEBUG': '4'}),
     ('window mma-only', 2, {'IFCB_CONV_DEBUG': '5'}),
     ('window load-only', 2, {'IFCB_CONV_DEBUG': '6'}),
     ('window m1', 2, {'IFCB_CONV_MSUB': '1'}),
     ('window m2', 2, {'IFCB_CONV_MSUB': '2'}),
-    ('window m1 a3', 2, {'IFCB_CONV_MSUB': '1', 'IFCB_CONV_ASLOTS': '3'}),
-    ('window m1 a4', 2, {'IFCB_CONV_MSUB': '1', 'IFCB_CONV_ASLOTS': '4'}),
-    ('window m2 a3', 2, {'IFCB_CONV_MSUB': '2', 'IFCB_CONV_ASLOTS': '3'}),
+    ('window g1', 2, {'IFCB_CONV_BGROUP': '1'}),
 ]
 print('%-26s' % 'layer (us @ batch %d)' % B + ''.join('%17s' % c[0] for c in CONFIGS))
 for layer in LAYERS:
