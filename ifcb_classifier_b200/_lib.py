@@ -82,6 +82,7 @@ _SIGNATURES = {
     'ifcb_conv_geometry': (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                      C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                      C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    'ifcb_conv_auto_config': (C.c_int, [C.c_int] * 9 + [C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     'ifcb_plan_add_stem': (C.c_int, [C.c_void_p, C.POINTER(StemDesc)]),
     'ifcb_plan_add_pool': (C.c_int, [C.c_void_p, C.POINTER(PoolDesc)]),
     'ifcb_plan_add_head': (C.c_int, [C.c_void_p, C.POINTER(HeadDesc)]),
@@ -121,3 +122,11 @@ def conv_geometry(Cin, Cout, kh, kw, tile_n=0):
     check(lib().ifcb_conv_geometry(Cin, Cout, kh, kw, tile_n, C.byref(a), C.byref(b), C.byref(c), C.byref(d)),
           'conv_geometry')
     return dict(Cin_pad=a.value, K_pad=b.value, tile_n=c.value, Cout_pad=d.value)
+
+
+def conv_auto_config(H, W, Cout, kh, kw, stride=(1, 1), pad=(0, 0)):
+    """(algo, tile_n) the library prefers for this conv shape (IFCB_CONV_IM2COL / _WINDOW)."""
+    a, t = C.c_int32(), C.c_int32()
+    check(lib().ifcb_conv_auto_config(H, W, Cout, kh, kw, stride[0], stride[1], pad[0], pad[1], C.byref(a), C.byref(t)),
+          'conv_auto_config')
+    return a.value, t.value

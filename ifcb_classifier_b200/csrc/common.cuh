@@ -77,6 +77,19 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// floor(n / d) for 0 <= n < 2^31 through the host-computed magic = floor((2^64 - 1) / d) + 1
+// (exact while n * d < 2^64; magic == 0 encodes d == 1).  ~5 integer instructions
+// instead of the ~40 of an emulated 32-bit division -- map_row runs per accumulator.
+__device__ __forceinline__ uint32_t fast_div(uint32_t n, unsigned long long magic) {
+  if (magic == 0ull) return n;
+  const uint32_t m_lo = (uint32_t)magic, m_hi = (uint32_t)(magic >> 32);
+  const unsigned long long t = (unsigned long long)n * m_hi + (((unsigned long long)n * m_lo) >> 32);
+  return (uint32_t)(t >> 32);
+}
+
+// host side of fast_div
+inline unsigned long long div_magic(int d) { return d <= 1 ? 0ull : (~0ull) / (unsigned long long)d + 1ull; }
+
 int sm_count();
 
 }  // namespace ifcb

@@ -45,32 +45,27 @@ namespace ifcb {
 namespace {
 
 constexpr int kBlockM = 128;
-constexpr int kEpiWarps = 8;
-constexpr int kThreads = 64 + 32 * kEpiWarps;       // 320
+#ifndef IFCB_EPI_WARPS
+#define IFCB_EPI_WARPS 12
+#endif
+constexpr int kEpiWarps = IFCB_EPI_WARPS;           // 3-4 per TMEM lane quadrant: the epilogue is latency-bound, TLP hides it
+constexpr int kEpiPerQuad = kEpiWarps / 4;
+constexpr int kThreads = 64 + 32 * kEpiWarps;       // 576
+constexpr int kStageTile = 2048;                    // per-warp staging tile: 32 rows x 64 B
 constexpr int kTmemCols = 512;
 constexpr int kAccBufCols = 256;
 constexpr int kBarBytes = 512;
 constexpr int kMaxStages = 12;
 
-// barriers + scale/shift (2 x cout_pad floats) + one 4 KB staging tile per epilogue warp
+// barriers + scale/shift (2 x cout_pad floats) + one 2 KB staging tile per epilogue warp
 __host__ __device__ constexpr int epilogue_smem(int cout_pad) {
-  return kBarBytes + 8 * cout_pad + kEpiWarps * 4096;
+  return kBarBytes + 8 * cout_pad + kEpiWarps * kStageTile;
 }
 
 struct RowMap {           // where a GEMM row lands
   int n, p, q;
   bool valid;
 };
-
-// floor(n / d) for 0 <= n < 2^31 through the host-computed magic = floor((2^64 - 1) / d) + 1
-// (exact while n * d < 2^64; magic == 0 encodes d == 1).  ~5 integer instructions
-// instead of the ~40 of an emulated 32-bit division -- map_row runs per accumulator.
-__device__ __forceinline__ uint32_t fast_div(uint32_t n, unsigned long long magic) {
-  if (magic == 0ull) return n;
-  const uint32_t m_lo = (uint32_t)magic, m_hi = (uint32_t)(magic >> 32);
-  const unsigned long long t = (unsigned long long)n * m_hi + (((unsigned long long)n * m_lo) >> 32);
-  return (uint32_t)(t >> 32);
-}
 
 __device__ __forceinline__ RowMap map_row(const ConvKernelParams& p, int i) {
   RowMap r;
@@ -110,118 +105,146 @@ __device__ __forceinline__ void pack16(const float (&y)[16], uint4& o0, uint4& o
   o1.w = cvt_pack<FP16, RELU>(y[14], y[15]);
 }
 
-// coalesced write-out of one staged group: 32 rows x PPR 16-byte pieces, fully unrolled
+// y = a * b + c on two packed fp32 lanes (sm_100 FFMA2): halves the epilogue's FMA count
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b0, float b1, float c0, float c1) {
+  asm("{\n.reg .b64 a, b, c, d;\nmov.b64 a, {%2, %3};\nmov.b64 b, {%4, %5};\nmov.b64 c, {%6, %7};\n"
+      "fma.rn.f32x2 d, a, b, c;\nmov.b64 {%0, %1}, d;\n}"
+      : "=f"(d0), "=f"(d1)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c0), "f"(c1));
+}
+
+constexpr uint32_t kNoRow = 0xFFFFFFFFu;
+
+// coalesced write-out of one staged unit: 32 rows x PPR 16-byte pieces (row pitch 64 B, chunk
+// XOR-swizzled by (row >> 1) & 3), fully unrolled.  `off` = this lane's destination row as an
+// ELEMENT offset (row * ld), kNoRow = dropped row.
 template <int PPR>
-__device__ __forceinline__ void write_out(uint32_t stage_addr, int lane, int drow, __nv_bfloat16* gout, int ld) {
+__device__ __forceinline__ void write_out(const uint8_t* stage, int lane, uint32_t off, __nv_bfloat16* gout) {
   uint4 val[PPR];
-  int dr[PPR], pcs[PPR];
+  uint32_t ro[PPR];
 #pragma unroll
   for (int it = 0; it < PPR; ++it) {
     const int idx = lane + 32 * it;
-    const int r = PPR == 8 ? idx >> 3 : PPR == 4 ? idx >> 2 : PPR == 2 ? idx >> 1 : (idx * 171) >> 10;   // idx / PPR
+    const int r = PPR == 4 ? idx >> 2 : idx >> 1;
     const int pc = idx - r * PPR;
-    pcs[it] = pc;
-    dr[it] = __shfl_sync(0xffffffffu, drow, r);
-    val[it] = ptx::ld_shared_v4(stage_addr + (uint32_t)r * 128u + ((((uint32_t)pc) ^ (uint32_t)(r & 7)) << 4));
+    ro[it] = __shfl_sync(0xffffffffu, off, r);
+    val[it] = *reinterpret_cast<const uint4*>(stage + r * 64 + ((pc ^ ((r >> 1) & 3)) << 4));
   }
 #pragma unroll
-  for (int it = 0; it < PPR; ++it)
-    if (dr[it] >= 0) *reinterpret_cast<uint4*>(gout + (long long)dr[it] * ld + pcs[it] * 8) = val[it];
+  for (int it = 0; it < PPR; ++it) {
+    const int idx = lane + 32 * it;
+    const int r = PPR == 4 ? idx >> 2 : idx >> 1;
+    const int pc = idx - r * PPR;
+    if (ro[it] != kNoRow) *reinterpret_cast<uint4*>(gout + ro[it] + pc * 8) = val[it];
+  }
 }
 
 // ---------------------------------------------------------------------------------------
-// Epilogue for one 128-row accumulator (TMEM columns [tcol, tcol + tile_n)), executed by
-// the two warps of one lane quadrant; `gcount` numbers the 64-column groups of the whole
-// tile and warp `half` (0/1) takes the even/odd ones.  The row mapping (two divisions) is
-// only evaluated by a warp that actually owns a group of this accumulator.
+// Epilogue of one tile (m_sub accumulators of 128 rows x tile_n columns), executed by the four
+// warps of one TMEM lane quadrant.  Work unit = (32-column slice, accumulator); the four warps
+// take units round-robin.  Row mapping (two magic divisions) once per accumulator and tile;
+// destination rows travel as 32-bit element offsets so that the write-out loop is
+// shuffle + ld.shared + one wide multiply-add + store.
 // ---------------------------------------------------------------------------------------
 template <bool FP16>
-__device__ __forceinline__ void epilogue_128rows(const ConvKernelParams& p, uint32_t taddr, int row0, int n_lo,
-                                                 int lane, int half, int& gcount, uint32_t stage_addr,
-                                                 const float* s_scale, const float* s_shift) {
+__device__ __forceinline__ void epilogue_tile(const ConvKernelParams& p, uint32_t tmem_acc, int tile_row0, int n_lo, int lane,
+                                              int sub, uint8_t* stage, const float* s_scale, const float* s_shift) {
+  // ---- where do this lane's rows land?  (n, p, q) per accumulator, n = -1: dropped ----
+  int rn[4], rp[4], rq[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    rn[j] = -1; rp[j] = 0; rq[j] = 0;
+    if (j < p.m_sub) {
+      const int i = tile_row0 + j * kBlockM + lane;
+      if (p.identity_rows) {
+        if (i < (int)p.rows) { rn[j] = 0; rq[j] = i; }
+      } else {
+        const RowMap rm = map_row(p, i);
+        if (rm.valid) { rn[j] = rm.n; rp[j] = rm.p; rq[j] = rm.q; }
+      }
+    }
+  }
+  uint32_t roff[4] = {kNoRow, kNoRow, kNoRow, kNoRow};
+  if (p.residual != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (rn[j] >= 0)
+        roff[j] = p.identity_rows ? (uint32_t)rq[j] * (uint32_t)p.res_ld
+                                  : (uint32_t)((rn[j] * (p.P + 2 * p.res_pad_h) + rp[j] + p.res_pad_h) * (p.Q + 2 * p.res_pad_w) + rq[j] + p.res_pad_w) * (uint32_t)p.res_ld;
+  }
   const int n_hi = n_lo + p.tile_n;
-  const uint32_t rbase = stage_addr + (uint32_t)lane * 128u;
-  const uint32_t sw = (uint32_t)(lane & 7);
-  bool mapped = false;
-  RowMap rm;
-  long long res_row = 0;
+  uint4* srow = reinterpret_cast<uint4*>(stage + lane * 64);
+  const int sw = (lane >> 1) & 3;
+  int unit = 0;
   for (int si = 0; si < p.n_seg; ++si) {
     const int g_lo = max(n_lo, p.seg_begin[si]), g_hi = min(n_hi, p.seg_end[si]);
     if (g_lo >= g_hi) continue;
-    const int ngroups = (g_hi - g_lo + 63) >> 6;
-    // does this warp own any group of the segment?  (groups alternate between the two warps)
-    if (ngroups == 1 && (gcount & 1) != half) { ++gcount; continue; }
-    if (!mapped) {
-      mapped = true;
-      if (p.identity_rows) {
-        rm.n = 0; rm.p = 0; rm.q = row0 + lane;
-        rm.valid = (row0 + lane) < (int)p.rows;
-      } else {
-        rm = map_row(p, row0 + lane);
-      }
-      if (p.residual != nullptr)
-        res_row = p.identity_rows ? (long long)(row0 + lane)
-                                  : ((long long)rm.n * (p.P + 2 * p.res_pad_h) + rm.p + p.res_pad_h) * (p.Q + 2 * p.res_pad_w) + rm.q + p.res_pad_w;
-    }
     const int relu = p.seg_relu[si];
-    // destination row of this lane's GEMM row inside the (possibly padded) output tensor
-    int drow;
-    if (p.identity_rows) {
-      drow = rm.valid ? rm.q : -1;
-    } else {
-      const int Hd = p.P + 2 * p.seg_pad_h[si], Wd = p.Q + 2 * p.seg_pad_w[si];
-      drow = rm.valid ? ((rm.n * Hd + rm.p + p.seg_pad_h[si]) * Wd + rm.q + p.seg_pad_w[si]) : -1;
+    const uint32_t ld = (uint32_t)p.seg_ld[si];
+    // destination row offsets (elements) of this lane's rows inside the (possibly padded) output
+    uint32_t off[4];
+    {
+      const int ph = p.seg_pad_h[si], pw = p.seg_pad_w[si];
+      const int Hd = p.P + 2 * ph, Wd = p.Q + 2 * pw;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        off[j] = rn[j] < 0 ? kNoRow
+                           : (p.identity_rows ? (uint32_t)rq[j] : (uint32_t)((rn[j] * Hd + rp[j] + ph) * Wd + rq[j] + pw)) * ld;
     }
-    const int ld = p.seg_ld[si];
-    for (int g0 = g_lo; g0 < g_hi; g0 += 64, ++gcount) {
-      if ((gcount & 1) != half) continue;
-      const int nch = min(4, (g_hi - g0) >> 4);
-      uint32_t v[4][16];
-#pragma unroll
-      for (int ch = 0; ch < 4; ++ch)
-        if (ch < nch) ptx::tmem_ld_32x32b_x16(taddr + (uint32_t)(g0 + ch * 16 - n_lo), v[ch]);
-      ptx::tmem_ld_wait();
-#pragma unroll
-      for (int ch = 0; ch < 4; ++ch) {
-        if (ch < nch) {
-          const int n = g0 + ch * 16;
-          float y[16];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float4 sc = *reinterpret_cast<const float4*>(s_scale + n + 4 * j);
-            const float4 sh = *reinterpret_cast<const float4*>(s_shift + n + 4 * j);
-            y[4 * j + 0] = fmaf(__uint_as_float(v[ch][4 * j + 0]), sc.x, sh.x);
-            y[4 * j + 1] = fmaf(__uint_as_float(v[ch][4 * j + 1]), sc.y, sh.y);
-            y[4 * j + 2] = fmaf(__uint_as_float(v[ch][4 * j + 2]), sc.z, sh.z);
-            y[4 * j + 3] = fmaf(__uint_as_float(v[ch][4 * j + 3]), sc.w, sh.w);
-          }
-          if (p.residual != nullptr && rm.valid) {
-            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + res_row * p.res_ld + n);
-            const uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
-            const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float2 f = unpack_act2(rr[j], FP16 ? 1 : 0);
-              y[2 * j] += f.x;
-              y[2 * j + 1] += f.y;
-            }
-          }
-          uint4 o0, o1;
-          if (relu) pack16<FP16, true>(y, o0, o1);
-          else pack16<FP16, false>(y, o0, o1);
-          // row `lane`, 16-byte pieces 2*ch and 2*ch+1, XOR-swizzled by (row & 7)
-          ptx::st_shared_v4(rbase + ((((uint32_t)(2 * ch)) ^ sw) << 4), o0);
-          ptx::st_shared_v4(rbase + ((((uint32_t)(2 * ch + 1)) ^ sw) << 4), o1);
-        }
-      }
-      __syncwarp();
-      // coalesced write-out: 2*nch 16-byte pieces per row, 32 rows
+    for (int g0 = g_lo; g0 < g_hi; g0 += 32) {
+      const bool wide = (g_hi - g0) >= 32;                 // 32 columns, or a 16-column tail
       __nv_bfloat16* gout = p.seg_out[si] + (g0 - p.seg_begin[si]);
-      if (nch == 4) write_out<8>(stage_addr, lane, drow, gout, ld);
-      else if (nch == 2) write_out<4>(stage_addr, lane, drow, gout, ld);
-      else if (nch == 3) write_out<6>(stage_addr, lane, drow, gout, ld);
-      else write_out<2>(stage_addr, lane, drow, gout, ld);
-      __syncwarp();
+      for (int j = 0; j < p.m_sub; ++j, ++unit) {
+        if ((unit % kEpiPerQuad) != sub) continue;
+        const uint32_t off_j = j == 0 ? off[0] : j == 1 ? off[1] : j == 2 ? off[2] : off[3];
+        const uint32_t roff_j = j == 0 ? roff[0] : j == 1 ? roff[1] : j == 2 ? roff[2] : roff[3];
+        const uint32_t taddr = tmem_acc + (uint32_t)(j * p.tile_n + g0 - n_lo);
+        uint32_t v[2][16];
+        ptx::tmem_ld_32x32b_x16(taddr, v[0]);
+        if (wide) ptx::tmem_ld_32x32b_x16(taddr + 16u, v[1]);
+        ptx::tmem_ld_wait();
+        uint4 o[4];
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+          if (ch == 0 || wide) {
+            const int n = g0 + ch * 16;
+            float y[16];
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+              const float4 sc = *reinterpret_cast<const float4*>(s_scale + n + 4 * q4);
+              const float4 sh = *reinterpret_cast<const float4*>(s_shift + n + 4 * q4);
+              ffma2(y[4 * q4 + 0], y[4 * q4 + 1], __uint_as_float(v[ch][4 * q4 + 0]), __uint_as_float(v[ch][4 * q4 + 1]),
+                    sc.x, sc.y, sh.x, sh.y);
+              ffma2(y[4 * q4 + 2], y[4 * q4 + 3], __uint_as_float(v[ch][4 * q4 + 2]), __uint_as_float(v[ch][4 * q4 + 3]),
+                    sc.z, sc.w, sh.z, sh.w);
+            }
+            if (p.residual != nullptr && roff_j != kNoRow) {
+              const uint4* rp4 = reinterpret_cast<const uint4*>(p.residual + roff_j + n);
+              const uint4 r0 = __ldg(rp4), r1 = __ldg(rp4 + 1);
+              const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const float2 f = unpack_act2(rr[e], FP16 ? 1 : 0);
+                y[2 * e] += f.x;
+                y[2 * e + 1] += f.y;
+              }
+            }
+            if (relu) pack16<FP16, true>(y, o[2 * ch], o[2 * ch + 1]);
+            else pack16<FP16, false>(y, o[2 * ch], o[2 * ch + 1]);
+          }
+        }
+        // stage: row `lane` (64 B), 16-byte pieces XOR-swizzled by (row >> 1) & 3
+        srow[0 ^ sw] = o[0];
+        srow[1 ^ sw] = o[1];
+        if (wide) {
+          srow[2 ^ sw] = o[2];
+          srow[3 ^ sw] = o[3];
+        }
+        __syncwarp();
+        if (wide) write_out<4>(stage, lane, off_j, gout);
+        else write_out<2>(stage, lane, off_j, gout);
+        __syncwarp();
+      }
     }
   }
 }
@@ -283,7 +306,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_full + 12);
   float* s_scale = reinterpret_cast<float*>(bar_base + kBarBytes);
   float* s_shift = s_scale + p.cout_pad;
-  uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_shift + p.cout_pad);      // 8 x 4 KB, 128-byte aligned
+  uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_shift + p.cout_pad);      // 16 x 2 KB, 128-byte aligned
   for (int i = threadIdx.x; i < p.cout_pad; i += kThreads) {
     s_scale[i] = p.scale[i];
     s_shift[i] = p.shift[i];
@@ -428,10 +451,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           const uint32_t a_lo0 = ptx::umma_desc_lo(a_addr);
           for (int t0 = 0; t0 < taps; t0 += p.b_group) {
             const int nt = min(p.b_group, taps - t0);
-            ptx::mbar_wait(full_bar + stage, phase);
+            if (!ready) ptx::mbar_wait(full_bar + stage, phase);
             ptx::tc_fence_after();
             const uint32_t b_lo0 = ptx::umma_desc_lo(ptx::smem_u32(b_base + (size_t)stage * b_stage_bytes));
             const bool first_stage = (cb == 0 && t0 == 0);
+            const int cur = stage;
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            ready = ptx::mbar_test_wait(full_bar + stage, phase) != 0;     // early peek at the next stage
             if (!skip_mma) {
 #define IFCB_ISSUE(KS, MS)                                                                                        \
   issue_stage<KS, MS>(leader, nt, first_stage, a_lo0, b_lo0, b_tap16, row16, jstride, d_tmem, (uint32_t)p.tile_n, \
@@ -452,9 +478,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               }
 #undef IFCB_ISSUE
             }
-            if (leader) ptx::umma_commit(empty_bar + stage);
+            if (leader) ptx::umma_commit(empty_bar + cur);
             __syncwarp();
-            if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
           if (leader) ptx::umma_commit(a_empty + aslot);
           __syncwarp();
@@ -494,8 +519,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   } else {
     // ===================== epilogue (warps 2..9) =====================
     const int quad = warp & 3;                       // TMEM lane quadrant this warp may access
-    const int half = (warp - 2) >> 2;                // which of the quadrant's two warps
-    const uint32_t stage_addr = ptx::smem_u32(s_stage + (warp - 2) * 4096);
+    const int sub = (warp - 2) >> 2;                 // which of the quadrant's four warps
+    uint8_t* stage = s_stage + (warp - 2) * kStageTile;
     int local = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
       const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
@@ -503,11 +528,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const uint32_t acc_phase = (local >> 1) & 1;
       ptx::mbar_wait(tmem_full + acc, acc_phase);
       ptx::tc_fence_after();
-      int gcount = 0;
-      for (int j = 0; j < p.m_sub && !(p.debug_flags & 4); ++j) {
-        const int row0 = m_tile * tile_rows + j * kBlockM + quad * 32;
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * kAccBufCols + j * p.tile_n);
-        epilogue_128rows<FP16>(p, taddr, row0, n_tile * p.tile_n, lane, half, gcount, stage_addr, s_scale, s_shift);
+      if (!(p.debug_flags & 4)) {
+        const uint32_t tmem_acc = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * kAccBufCols);
+        epilogue_tile<FP16>(p, tmem_acc, m_tile * tile_rows + quad * 32, n_tile * p.tile_n, lane, sub, stage, s_scale, s_shift);
       }
       ptx::tc_fence_before();
       __syncwarp();
@@ -542,15 +565,9 @@ bool conv_plan_smem(ConvKernelParams& kp, bool window, int halo_rows) {
     kp.stages = s;
     return s >= 2;
   }
-  // taps per B pipeline stage: about 24 KB per stage, balanced over the groups
-  int g = 24576 / b_tap;
-  if (g < 1) g = 1;
-  if (g > taps) g = taps;
-  if (kp.b_group_cap > 0 && g > kp.b_group_cap) g = kp.b_group_cap;
-  const int n_groups = (taps + g - 1) / g;
-  g = (taps + n_groups - 1) / n_groups;
-  const int b_stage = g * b_tap;
-  // choose m (accumulators per tile) as large as TMEM double buffering and smem allow
+  // m (accumulators per tile): as large as TMEM double buffering and smem allow; taps per weight
+  // pipeline stage (b_group): as many as fit (<= 48 KB per stage, >= 2 stages) -- every stage
+  // costs the MMA warp a barrier round trip (~250 clk) against 4 MMAs of run-ahead
   for (int m = 4; m >= 1; m >>= 1) {
     if (m > kp.m_sub_cap) continue;
     if (m * kp.tile_n > kAccBufCols) continue;
@@ -560,18 +577,27 @@ bool conv_plan_smem(ConvKernelParams& kp, bool window, int halo_rows) {
     const int slot = (n_boxes * box_rows * row_bytes + 1023) & ~1023;
     for (int slots = kp.a_slots_pref; slots >= 1; --slots) {
       const int left = kSmemBudget - fixed - slots * slot;
-      int s = left / b_stage;
-      if (s > 8) s = 8;
-      const int need = (g >= 2 || slots >= 2) ? 2 : 3;
-      if (s >= need) {
-        kp.m_sub = m;
-        kp.a_slots = slots;
-        kp.a_slot_bytes = slot;
-        kp.box_rows = box_rows;
-        kp.n_boxes = n_boxes;
-        kp.stages = s;
-        kp.b_group = g;
-        return true;
+      int g = 49152 / b_tap;
+      if (g < 1) g = 1;
+      if (g > taps) g = taps;
+      if (kp.b_group_cap > 0 && g > kp.b_group_cap) g = kp.b_group_cap;
+      for (; g >= 1; --g) {
+        const int n_groups = (taps + g - 1) / g;
+        const int gb = (taps + n_groups - 1) / n_groups;      // balanced group size
+        const int b_stage = gb * b_tap;
+        int s = left / b_stage;
+        if (s > 6) s = 6;
+        const int need = (gb >= 2 || slots >= 2) ? 2 : 3;
+        if (s >= need) {
+          kp.m_sub = m;
+          kp.a_slots = slots;
+          kp.a_slot_bytes = slot;
+          kp.box_rows = box_rows;
+          kp.n_boxes = n_boxes;
+          kp.stages = s;
+          kp.b_group = gb;
+          return true;
+        }
       }
       if (m > 1) break;      // prefer a smaller m with two slots over a single-slot large m
     }

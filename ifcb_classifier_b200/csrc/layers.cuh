@@ -48,6 +48,7 @@ struct ConvLayer {
 struct StemLayer {
   ifcb_stem_desc d;
   int P, Q;
+  std::vector<float> h_const;  // gray 3x3 fast path: host copy of [9*Cout] weights, [Cout] scale, [Cout] shift (kernel parameter)
 };
 
 struct PoolLayer {

@@ -54,6 +54,31 @@ int pick_tile_n(int Cout, int hint) {
   return 256;
 }
 
+// Heuristic algorithm / N-tile choice (measured on B200, profiles/r01_layer_matrix_v3.txt).
+//  * WINDOW pays for every padded anchor row (junk = Hp*Wp / (P*Q)) but reads the input patch
+//    once for all taps and lets m accumulators share a weight tile; it wins for >= 4 taps on
+//    large images.  1x1 convs and small images (17x17 1x7, 8x8 3x3) stay on IM2COL.
+//  * A 128-row tile streams the whole weight matrix at 64 B per MMA clock -- the L2 limit --
+//    so WINDOW layers wider than 128 channels are split into N tiles <= 128 to make room in
+//    TMEM for two accumulators per weight tile.
+void auto_config(int H, int W, int Cout, int kh, int kw, int stride_h, int stride_w, int pad_h, int pad_w,
+                 int* algo, int* tile_n) {
+  const int P = out_dim(H, kh, stride_h, pad_h), Q = out_dim(W, kw, stride_w, pad_w);
+  const int taps = kh * kw;
+  const double junk = (double)(H + 2 * pad_h) * (W + 2 * pad_w) / ((double)P * Q);
+  const bool window = stride_h == 1 && stride_w == 1 && taps >= 4 && junk <= 1.30;
+  if (algo) *algo = window ? IFCB_CONV_WINDOW : IFCB_CONV_IM2COL;
+  if (tile_n) {
+    const int c16 = (Cout + 15) & ~15;
+    int tn = pick_tile_n(Cout, 0);
+    if (window && c16 > 128) {
+      const int t = (c16 + 127) / 128;
+      tn = (((c16 + t - 1) / t) + 15) & ~15;
+    }
+    *tile_n = tn;
+  }
+}
+
 }  // namespace
 }  // namespace ifcb
 
@@ -91,6 +116,19 @@ extern "C" int ifcb_conv_geometry(int Cin, int Cout, int kh, int kw, int tile_n_
   return 0;
 }
 
+extern "C" int ifcb_conv_auto_config(int H, int W, int Cout, int kh, int kw, int stride_h, int stride_w, int pad_h,
+                                     int pad_w, int32_t* algo, int32_t* tile_n) {
+  IFCB_ARG_CHECK(H > 0 && W > 0 && Cout > 0 && kh > 0 && kw > 0 && stride_h > 0 && stride_w > 0 && pad_h >= 0 && pad_w >= 0,
+                 "ifcb_conv_auto_config: bad shape");
+  IFCB_ARG_CHECK(out_dim(H, kh, stride_h, pad_h) > 0 && out_dim(W, kw, stride_w, pad_w) > 0,
+                 "ifcb_conv_auto_config: empty output");
+  int a = 0, t = 0;
+  auto_config(H, W, Cout, kh, kw, stride_h, stride_w, pad_h, pad_w, &a, &t);
+  if (algo) *algo = a;
+  if (tile_n) *tile_n = t;
+  return 0;
+}
+
 extern "C" int ifcb_plan_add_conv(ifcb_plan* plan, const ifcb_conv_desc* d) {
   IFCB_ARG_CHECK(plan && d, "ifcb_plan_add_conv: null argument");
   IFCB_ARG_CHECK(d->d_in && d->d_weight && d->d_scale && d->d_shift, "conv: null tensor pointer");
@@ -114,7 +152,10 @@ extern "C" int ifcb_plan_add_conv(ifcb_plan* plan, const ifcb_conv_desc* d) {
   const bool can_window = d->stride_h == 1 && d->stride_w == 1 && d->in_pad_h >= d->pad_h && d->in_pad_w >= d->pad_w;
   IFCB_ARG_CHECK(d->algo != IFCB_CONV_WINDOW || can_window,
                  "conv: the window algorithm needs stride 1 and an input buffer padded by at least the conv padding");
-  const bool window = d->algo == IFCB_CONV_WINDOW || (d->algo == IFCB_CONV_AUTO && can_window);
+  int auto_algo = IFCB_CONV_IM2COL, auto_tile_n = 0;
+  auto_config(d->H, d->W, d->Cout, d->kh, d->kw, d->stride_h, d->stride_w, d->pad_h, d->pad_w, &auto_algo, &auto_tile_n);
+  const bool window = d->algo == IFCB_CONV_WINDOW || (d->algo == IFCB_CONV_AUTO && can_window && auto_algo == IFCB_CONV_WINDOW);
+  const int tile_n_req = d->tile_n ? d->tile_n : (window ? auto_tile_n : 0);
 
   Layer L{};
   L.kind = kConv;
@@ -125,7 +166,7 @@ extern "C" int ifcb_plan_add_conv(ifcb_plan* plan, const ifcb_conv_desc* d) {
   IFCB_ARG_CHECK(P > 0 && Q > 0, "conv: empty output");
   const int Hp = d->H + 2 * d->in_pad_h, Wp = d->W + 2 * d->in_pad_w;     // physical input extent
   int32_t cin_pad, k_pad, tile_n, cout_pad;
-  ifcb_conv_geometry(d->Cin, d->Cout, d->kh, d->kw, d->tile_n, &cin_pad, &k_pad, &tile_n, &cout_pad);
+  ifcb_conv_geometry(d->Cin, d->Cout, d->kh, d->kw, tile_n_req, &cin_pad, &k_pad, &tile_n, &cout_pad);
   kp.rows = 0;
   kp.P = P;
   kp.Q = Q;
@@ -166,6 +207,8 @@ extern "C" int ifcb_plan_add_conv(ifcb_plan* plan, const ifcb_conv_desc* d) {
     IFCB_ARG_CHECK(d->res_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(d->d_residual) & 15) == 0,
                    "conv: residual view must be 16-byte aligned with ld %% 8 == 0");
     IFCB_ARG_CHECK(d->n_seg == 1 && d->seg[0].n_begin == 0, "conv: residual needs a single segment at column 0");
+    IFCB_ARG_CHECK((unsigned long long)d->batch_cap * (P + 2 * d->res_pad_h) * (Q + 2 * d->res_pad_w) * (unsigned long long)d->res_ld < (1ull << 32) - 1,
+                   "conv: residual exceeds the 32-bit element offsets of the epilogue");
   }
   kp.n_seg = d->n_seg;
   for (int s = 0; s < d->n_seg; ++s) {
@@ -176,6 +219,8 @@ extern "C" int ifcb_plan_add_conv(ifcb_plan* plan, const ifcb_conv_desc* d) {
                    "conv: segment %d output must be 16-byte aligned with ld %% 8 == 0", s);
     IFCB_ARG_CHECK(sg.ld >= sg.n_end - sg.n_begin, "conv: segment %d ld too small", s);
     IFCB_ARG_CHECK(sg.pad_h >= 0 && sg.pad_w >= 0 && sg.pad_h <= 8 && sg.pad_w <= 8, "conv: segment %d bad pad", s);
+    IFCB_ARG_CHECK((unsigned long long)d->batch_cap * (P + 2 * sg.pad_h) * (Q + 2 * sg.pad_w) * (unsigned long long)sg.ld < (1ull << 32) - 1,
+                   "conv: segment %d destination exceeds the 32-bit element offsets of the epilogue", s);
     kp.seg_begin[s] = sg.n_begin;
     kp.seg_end[s] = sg.n_end;
     kp.seg_ld[s] = sg.ld;
@@ -185,9 +230,8 @@ extern "C" int ifcb_plan_add_conv(ifcb_plan* plan, const ifcb_conv_desc* d) {
     kp.seg_out[s] = reinterpret_cast<__nv_bfloat16*>(sg.d_out);
   }
   {
-    auto magic = [](int dv) -> unsigned long long { return dv <= 1 ? 0ull : (~0ull) / (unsigned long long)dv + 1ull; };
-    kp.magic_img = magic(kp.rows_per_img);
-    kp.magic_w = magic(kp.row_w);
+    kp.magic_img = div_magic(kp.rows_per_img);
+    kp.magic_w = div_magic(kp.row_w);
     bool ident = !window && (!d->d_residual || (d->res_pad_h == 0 && d->res_pad_w == 0));
     for (int sgi = 0; sgi < d->n_seg; ++sgi) ident = ident && d->seg[sgi].pad_h == 0 && d->seg[sgi].pad_w == 0;
     kp.identity_rows = ident ? 1 : 0;
@@ -259,6 +303,15 @@ extern "C" int ifcb_plan_add_stem(ifcb_plan* plan, const ifcb_stem_desc* d) {
   L.stem.P = out_dim(d->H, d->kh, d->stride, d->pad);
   L.stem.Q = out_dim(d->W, d->kw, d->stride, d->pad);
   IFCB_ARG_CHECK(L.stem.P > 0 && L.stem.Q > 0, "stem: empty output");
+  if (d->in_kind == IFCB_STEM_IN_U8_GRAY && d->kh == 3 && d->kw == 3 && d->pad == 0) {
+    // fast path: the folded gray weights + BN affine become a kernel parameter (constant bank);
+    // one synchronous device->host copy at plan-build time
+    const int co = d->Cout;
+    L.stem.h_const.resize(9 * co + 2 * co);
+    IFCB_CUDA_CHECK(cudaMemcpy(L.stem.h_const.data(), d->d_wgray, sizeof(float) * 9 * co, cudaMemcpyDeviceToHost));
+    IFCB_CUDA_CHECK(cudaMemcpy(L.stem.h_const.data() + 9 * co, d->d_scale, sizeof(float) * co, cudaMemcpyDeviceToHost));
+    IFCB_CUDA_CHECK(cudaMemcpy(L.stem.h_const.data() + 10 * co, d->d_shift, sizeof(float) * co, cudaMemcpyDeviceToHost));
+  }
   plan->layers.push_back(L);
   return 0;
 }

@@ -4,6 +4,7 @@
 // shuffles for the reductions.  See include/ifcb_b200.h for the reference code
 // each replaces.
 #include "layers.cuh"
+#include <cstring>
 
 namespace ifcb {
 namespace {
@@ -163,6 +164,144 @@ __global__ void __launch_bounds__(128) stem_gray_kernel(const ifcb_stem_desc d, 
 }
 
 // ------------------------------------------------------------------------------
+// Stem, gray 3x3 / pad 0 (Inception Conv2d_1a): one thread = one output pixel x COUT
+// channels.  The 9 x COUT folded gray weights and the BN scale/shift travel as a kernel
+// PARAMETER (constant bank): every FFMA reads its weight as a constant operand, so the inner
+// loop is 9 byte loads + 9*COUT FFMA with no shared-memory or register traffic for weights
+// (FMA-pipe bound).
+// ------------------------------------------------------------------------------
+template <int COUT>
+struct StemConst {
+  float w[9 * COUT];
+  float scale[COUT], shift[COUT];
+};
+
+template <int COUT>
+__global__ void __launch_bounds__(128) stem_gray3x3_kernel(const ifcb_stem_desc d, const __grid_constant__ StemConst<COUT> k,
+                                                           int P, int Q, int total, unsigned long long magic_pq,
+                                                           unsigned long long magic_q) {
+  const int pix = blockIdx.x * 128 + threadIdx.x;
+  if (pix >= total) return;
+  const int PQ = P * Q;
+  const int img = (int)fast_div((uint32_t)pix, magic_pq);
+  const int rem = pix - img * PQ;
+  const int op = (int)fast_div((uint32_t)rem, magic_q), oq = rem - op * Q;
+  const uint8_t* in = reinterpret_cast<const uint8_t*>(d.d_in) + (long long)img * d.H * d.W + (op * d.stride) * d.W + oq * d.stride;
+  float g[9];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int s2 = 0; s2 < 3; ++s2) g[r * 3 + s2] = (float)__ldg(in + r * d.W + s2);
+  float acc[COUT];
+#pragma unroll
+  for (int c = 0; c < COUT; ++c) acc[c] = 0.f;
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) acc[c] = fmaf(g[t], k.w[t * COUT + c], acc[c]);
+  const long long orow = ((long long)img * (P + 2 * d.out_pad_h) + op + d.out_pad_h) * (Q + 2 * d.out_pad_w) + oq + d.out_pad_w;
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(d.d_out) + orow * d.out_ld;
+#pragma unroll
+  for (int c = 0; c < COUT; c += 8) {
+    float y[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      y[j] = fmaf(acc[c + j], k.scale[c + j], k.shift[c + j]);
+      if (d.relu) y[j] = fmaxf(y[j], 0.f);
+    }
+    uint4 o;
+    o.x = pack_act2(y[0], y[1], d.dtype);
+    o.y = pack_act2(y[2], y[3], d.dtype);
+    o.z = pack_act2(y[4], y[5], d.dtype);
+    o.w = pack_act2(y[6], y[7], d.dtype);
+    *reinterpret_cast<uint4*>(out + c) = o;
+  }
+}
+
+// ------------------------------------------------------------------------------
+// 3x3 pooling over NHWC 16-bit (every pool of Inception-v3 / ResNet): one thread = one output
+// pixel x 8 channels (16 bytes); index math by magic division, all nine 16-byte loads in
+// flight before the reduction; max is taken on packed 16-bit pairs (exact), avg in fp32.
+// ------------------------------------------------------------------------------
+template <bool FP16>
+__device__ __forceinline__ uint32_t max2(uint32_t a, uint32_t b) {
+  if (FP16) {
+    const __half2 r = __hmax2(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
+    return *reinterpret_cast<const uint32_t*>(&r);
+  }
+  const __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
+
+template <bool AVG, bool FP16>
+__global__ void __launch_bounds__(256) pool3_kernel(const ifcb_pool_desc d, int P, int Q, int total, unsigned long long magic_c8,
+                                                    unsigned long long magic_pq, unsigned long long magic_q) {
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  if (idx >= total) return;
+  const int c8n = d.C >> 3;
+  const int pix = (int)fast_div((uint32_t)idx, magic_c8);
+  const int c8 = idx - pix * c8n;
+  const int PQ = P * Q;
+  const int img = (int)fast_div((uint32_t)pix, magic_pq);
+  const int rem = pix - img * PQ;
+  const int op = (int)fast_div((uint32_t)rem, magic_q), oq = rem - op * Q;
+  const int h0 = op * d.stride - d.pad, w0 = oq * d.stride - d.pad;
+  const int Wpi = d.W + 2 * d.in_pad_w;
+  const __nv_bfloat16* in = reinterpret_cast<const __nv_bfloat16*>(d.d_in) +
+      ((long long)img * (d.H + 2 * d.in_pad_h) * Wpi + (long long)(d.in_pad_h + h0) * Wpi + d.in_pad_w + w0) * d.in_ld + c8 * 8;
+  const uint32_t ninf = FP16 ? 0xFC00FC00u : 0xFF80FF80u;        // packed -inf pair
+  const uint32_t fill = AVG ? 0u : ninf;
+  uint4 v[9];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int s2 = 0; s2 < 3; ++s2) {
+      const bool ok = (unsigned)(h0 + r) < (unsigned)d.H && (unsigned)(w0 + s2) < (unsigned)d.W;
+      v[r * 3 + s2] = ok ? __ldg(reinterpret_cast<const uint4*>(in + ((long long)r * Wpi + s2) * d.in_ld))
+                         : make_uint4(fill, fill, fill, fill);
+    }
+  uint4 o;
+  if (AVG) {
+    float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const uint32_t u[4] = {v[t].x, v[t].y, v[t].z, v[t].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_act2(u[j], FP16 ? 1 : 0);
+        a[2 * j] += f.x;
+        a[2 * j + 1] += f.y;
+      }
+    }
+    const float inv = 1.0f / 9.0f;                      // count_include_pad=True: always k*k
+    const float4 s0 = __ldg(reinterpret_cast<const float4*>(d.d_scale + c8 * 8)), s1 = __ldg(reinterpret_cast<const float4*>(d.d_scale + c8 * 8 + 4));
+    const float4 h0v = __ldg(reinterpret_cast<const float4*>(d.d_shift + c8 * 8)), h1v = __ldg(reinterpret_cast<const float4*>(d.d_shift + c8 * 8 + 4));
+    const float scv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    const float shv[8] = {h0v.x, h0v.y, h0v.z, h0v.w, h1v.x, h1v.y, h1v.z, h1v.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float y = fmaf(a[j] * inv, scv[j], shv[j]);
+      a[j] = d.relu ? fmaxf(y, 0.f) : y;
+    }
+    o.x = pack_act2(a[0], a[1], FP16 ? 1 : 0);
+    o.y = pack_act2(a[2], a[3], FP16 ? 1 : 0);
+    o.z = pack_act2(a[4], a[5], FP16 ? 1 : 0);
+    o.w = pack_act2(a[6], a[7], FP16 ? 1 : 0);
+  } else {
+    o = v[0];
+#pragma unroll
+    for (int t = 1; t < 9; ++t) {
+      o.x = max2<FP16>(o.x, v[t].x);
+      o.y = max2<FP16>(o.y, v[t].y);
+      o.z = max2<FP16>(o.z, v[t].z);
+      o.w = max2<FP16>(o.w, v[t].w);
+    }
+  }
+  const long long orow = ((long long)img * (P + 2 * d.out_pad_h) + op + d.out_pad_h) * (Q + 2 * d.out_pad_w) + oq + d.out_pad_w;
+  *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(d.d_out) + orow * d.out_ld + c8 * 8) = o;
+}
+
+// ------------------------------------------------------------------------------
 // Pooling over NHWC bf16: one thread = one output pixel x 8 channels (16 bytes).
 // ------------------------------------------------------------------------------
 template <bool AVG>
@@ -308,7 +447,19 @@ int launch_stem(const StemLayer& L, int batch, cudaStream_t stream) {
     set_error("stem: Cout=%d unsupported (32 or 64)", d.Cout);
     return -1;
   }
-  if (d.in_kind == IFCB_STEM_IN_U8_GRAY) {
+  if (d.in_kind == IFCB_STEM_IN_U8_GRAY && d.kh == 3 && d.kw == 3 && d.pad == 0 && total < (1ll << 31) && !L.h_const.empty()) {
+    const unsigned long long mpq = div_magic(L.P * L.Q), mq = div_magic(L.Q);
+    const unsigned blocks = (unsigned)((total + 127) / 128);
+    if (d.Cout == 32) {
+      StemConst<32> k;
+      memcpy(&k, L.h_const.data(), sizeof(k));
+      stem_gray3x3_kernel<32><<<blocks, 128, 0, stream>>>(d, k, L.P, L.Q, (int)total, mpq, mq);
+    } else {
+      StemConst<64> k;
+      memcpy(&k, L.h_const.data(), sizeof(k));
+      stem_gray3x3_kernel<64><<<blocks, 128, 0, stream>>>(d, k, L.P, L.Q, (int)total, mpq, mq);
+    }
+  } else if (d.in_kind == IFCB_STEM_IN_U8_GRAY) {
     const bool haspad = d.pad > 0;
     const int smem = taps * d.Cout * (haspad ? 2 : 1) * (int)sizeof(float);
 #define IFCB_GRAY_LAUNCH(CO, HP)                                                                          \
@@ -345,10 +496,22 @@ int launch_pool(const PoolLayer& L, int batch, cudaStream_t stream) {
   const long long total = (long long)batch * L.P * L.Q * (d.C >> 3);
   if (total == 0) return 0;
   const unsigned grid = (unsigned)((total + 255) / 256);
-  if (d.kind == IFCB_POOL_MAX)
+  const bool avg = d.kind != IFCB_POOL_MAX;
+  if (d.k == 3 && total < (1ll << 31)) {
+    const unsigned long long mc = div_magic(d.C >> 3), mpq = div_magic(L.P * L.Q), mq = div_magic(L.Q);
+    const int t = (int)total;
+    if (avg) {
+      if (d.dtype) pool3_kernel<true, true><<<grid, 256, 0, stream>>>(d, L.P, L.Q, t, mc, mpq, mq);
+      else pool3_kernel<true, false><<<grid, 256, 0, stream>>>(d, L.P, L.Q, t, mc, mpq, mq);
+    } else {
+      if (d.dtype) pool3_kernel<false, true><<<grid, 256, 0, stream>>>(d, L.P, L.Q, t, mc, mpq, mq);
+      else pool3_kernel<false, false><<<grid, 256, 0, stream>>>(d, L.P, L.Q, t, mc, mpq, mq);
+    }
+  } else if (!avg) {
     pool_kernel<false><<<grid, 256, 0, stream>>>(d, L.P, L.Q, total);
-  else
+  } else {
     pool_kernel<true><<<grid, 256, 0, stream>>>(d, L.P, L.Q, total);
+  }
   IFCB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -115,6 +115,13 @@ class PlanBuilder(object):
         self.keep.append(t)
         return t
 
+    @staticmethod
+    def border_for(H, W, Co, k, stride=(1, 1), pad=(0, 0)):
+        """Zero border the INPUT of a conv should be allocated with: its padding when the library
+        will run the conv with the WINDOW algorithm (which reads padding from memory), else none."""
+        algo, _ = _lib.conv_auto_config(H, W, Co, k[0], k[1], stride, pad)
+        return tuple(pad) if algo == _lib.IFCB_CONV_WINDOW else (0, 0)
+
     # -- layers ---------------------------------------------------------------
     def conv(self, x, members, stride=(1, 1), pad=(0, 0), residual=None, tile_n=0, name='conv', algo=0):
         """One implicit-GEMM launch.  ``members``: list of dicts
@@ -124,6 +131,15 @@ class PlanBuilder(object):
         Ci, kh, kw = int(w0.shape[1]), int(w0.shape[2]), int(w0.shape[3])
         assert Ci == x.C, (name, Ci, x.C)
         Co = sum(int(m['weight'].shape[0]) for m in members)
+        # resolve AUTO / tile_n here so that weight packing (tile_n) and the plan agree
+        a_pref, tn_pref = _lib.conv_auto_config(x.H, x.W, Co, kh, kw, stride, pad)
+        if algo == _lib.IFCB_CONV_AUTO:
+            can_window = tuple(stride) == (1, 1) and x.pad[0] >= pad[0] and x.pad[1] >= pad[1]
+            algo = _lib.IFCB_CONV_WINDOW if (a_pref == _lib.IFCB_CONV_WINDOW and can_window) else _lib.IFCB_CONV_IM2COL
+        if algo == _lib.IFCB_CONV_WINDOW and tile_n == 0:
+            c16 = (Co + 15) // 16 * 16
+            t = (c16 + 127) // 128
+            tile_n = ((c16 + t - 1) // t + 15) // 16 * 16 if c16 > 128 else 0
         geo = _lib.conv_geometry(Ci, Co, kh, kw, tile_n)
         Cp, Kp, Np = geo['Cin_pad'], geo['K_pad'], geo['Cout_pad']
         wcat = torch.cat([m['weight'].float() for m in members], 0)          # [Co, Ci, kh, kw]
@@ -344,7 +360,7 @@ def build_inception_v3(pb, sd, inp, in_kind, R, affine=None, transform_input=Fal
     ts, tb = transform_input_affine() if transform_input else ((1, 1, 1), (0, 0, 0))
     pb.stem(inp, in_kind, R, R, sd['Conv2d_1a_3x3.conv.weight'], sc, sh, 2, 0, a, affine=affine,
             in_scale=ts, in_shift=tb, name='Conv2d_1a_3x3')
-    a = single(a, 'Conv2d_2a_3x3', 3, out_pad=(1, 1))
+    a = single(a, 'Conv2d_2a_3x3', 3, out_pad=pb.border_for(a.H - 2, a.W - 2, 64, (3, 3), pad=(1, 1)))
     a = single(a, 'Conv2d_2b_3x3', 3, pad=(1, 1))
     p = pb.alloc(sz(a.H, 3, 2, 0), sz(a.W, 3, 2, 0), 64)
     pb.pool(IFCB_POOL_MAX, a, 3, 2, 0, p, name='maxpool1')
@@ -358,13 +374,14 @@ def build_inception_v3(pb, sd, inp, in_kind, R, affine=None, transform_input=Fal
     for blk, pf in (('Mixed_5b', 32), ('Mixed_5c', 64), ('Mixed_5d', 64)):
         H = x.H
         out = pb.alloc(H, H, 224 + pf)
-        t5, t3, tp = pb.alloc(H, H, 48, (2, 2)), pb.alloc(H, H, 64, (1, 1)), pb.alloc(H, H, pf)
+        b5, b3 = pb.border_for(H, H, 64, (5, 5), pad=(2, 2)), pb.border_for(H, H, 96, (3, 3), pad=(1, 1))
+        t5, t3, tp = pb.alloc(H, H, 48, b5), pb.alloc(H, H, 64, b3), pb.alloc(H, H, pf)
         fused_1x1(x, [_basic(sd, blk + '.branch1x1', out.slice(0, 64)),
                       _basic(sd, blk + '.branch5x5_1', t5),
                       _basic(sd, blk + '.branch3x3dbl_1', t3),
                       _raw(sd, blk + '.branch_pool', tp)], blk + '.1x1s')
         single(t5, blk + '.branch5x5_2', 5, pad=(2, 2), out=out.slice(64, 128))
-        t3b = single(t3, blk + '.branch3x3dbl_2', 3, pad=(1, 1), out_pad=(1, 1))
+        t3b = single(t3, blk + '.branch3x3dbl_2', 3, pad=(1, 1), out_pad=b3)
         single(t3b, blk + '.branch3x3dbl_3', 3, pad=(1, 1), out=out.slice(128, 224))
         avg_branch(tp, blk + '.branch_pool', out.slice(224, 224 + pf), blk + '.branch_pool.avg')
         x = out
@@ -374,7 +391,7 @@ def build_inception_v3(pb, sd, inp, in_kind, R, affine=None, transform_input=Fal
     H2 = sz(x.H, 3, 2, 0)
     out = pb.alloc(H2, H2, 768)
     single(x, blk + '.branch3x3', 3, stride=(2, 2), out=out.slice(0, 384))
-    t = single(x, blk + '.branch3x3dbl_1', 1, out_pad=(1, 1))
+    t = single(x, blk + '.branch3x3dbl_1', 1, out_pad=pb.border_for(x.H, x.W, 96, (3, 3), pad=(1, 1)))
     t = single(t, blk + '.branch3x3dbl_2', 3, pad=(1, 1))
     single(t, blk + '.branch3x3dbl_3', 3, stride=(2, 2), out=out.slice(384, 480))
     pb.pool(IFCB_POOL_MAX, x, 3, 2, 0, out.slice(480, 768), name=blk + '.maxpool')
@@ -384,16 +401,17 @@ def build_inception_v3(pb, sd, inp, in_kind, R, affine=None, transform_input=Fal
     for blk, c7 in (('Mixed_6b', 128), ('Mixed_6c', 160), ('Mixed_6d', 160), ('Mixed_6e', 192)):
         H = x.H
         out = pb.alloc(H, H, 768)
-        t7, td, tp = pb.alloc(H, H, c7, (0, 3)), pb.alloc(H, H, c7, (3, 0)), pb.alloc(H, H, 192)
+        bw, bh = pb.border_for(H, H, c7, (1, 7), pad=(0, 3)), pb.border_for(H, H, c7, (7, 1), pad=(3, 0))
+        t7, td, tp = pb.alloc(H, H, c7, bw), pb.alloc(H, H, c7, bh), pb.alloc(H, H, 192)
         fused_1x1(x, [_basic(sd, blk + '.branch1x1', out.slice(0, 192)),
                       _basic(sd, blk + '.branch7x7_1', t7),
                       _basic(sd, blk + '.branch7x7dbl_1', td),
                       _raw(sd, blk + '.branch_pool', tp)], blk + '.1x1s')
-        t = single(t7, blk + '.branch7x7_2', 7, pad=(0, 3), out_pad=(3, 0))
+        t = single(t7, blk + '.branch7x7_2', 7, pad=(0, 3), out_pad=bh)
         single(t, blk + '.branch7x7_3', 7, pad=(3, 0), out=out.slice(192, 384))
-        t = single(td, blk + '.branch7x7dbl_2', 7, pad=(3, 0), out_pad=(0, 3))
-        t = single(t, blk + '.branch7x7dbl_3', 7, pad=(0, 3), out_pad=(3, 0))
-        t = single(t, blk + '.branch7x7dbl_4', 7, pad=(3, 0), out_pad=(0, 3))
+        t = single(td, blk + '.branch7x7dbl_2', 7, pad=(3, 0), out_pad=bw)
+        t = single(t, blk + '.branch7x7dbl_3', 7, pad=(0, 3), out_pad=bh)
+        t = single(t, blk + '.branch7x7dbl_4', 7, pad=(3, 0), out_pad=bw)
         single(t, blk + '.branch7x7dbl_5', 7, pad=(0, 3), out=out.slice(384, 576))
         avg_branch(tp, blk + '.branch_pool', out.slice(576, 768), blk + '.branch_pool.avg')
         x = out
@@ -402,10 +420,11 @@ def build_inception_v3(pb, sd, inp, in_kind, R, affine=None, transform_input=Fal
     blk = 'Mixed_7a'
     H2 = sz(x.H, 3, 2, 0)
     out = pb.alloc(H2, H2, 1280)
-    t3, t7 = pb.alloc(x.H, x.H, 192), pb.alloc(x.H, x.H, 192, (0, 3))
+    bw, bh = pb.border_for(x.H, x.H, 192, (1, 7), pad=(0, 3)), pb.border_for(x.H, x.H, 192, (7, 1), pad=(3, 0))
+    t3, t7 = pb.alloc(x.H, x.H, 192), pb.alloc(x.H, x.H, 192, bw)
     fused_1x1(x, [_basic(sd, blk + '.branch3x3_1', t3), _basic(sd, blk + '.branch7x7x3_1', t7)], blk + '.1x1s')
     single(t3, blk + '.branch3x3_2', 3, stride=(2, 2), out=out.slice(0, 320))
-    t = single(t7, blk + '.branch7x7x3_2', 7, pad=(0, 3), out_pad=(3, 0))
+    t = single(t7, blk + '.branch7x7x3_2', 7, pad=(0, 3), out_pad=bh)
     t = single(t, blk + '.branch7x7x3_3', 7, pad=(3, 0))
     single(t, blk + '.branch7x7x3_4', 3, stride=(2, 2), out=out.slice(320, 512))
     pb.pool(IFCB_POOL_MAX, x, 3, 2, 0, out.slice(512, 1280), name=blk + '.maxpool')
@@ -415,14 +434,15 @@ def build_inception_v3(pb, sd, inp, in_kind, R, affine=None, transform_input=Fal
     for blk in ('Mixed_7b', 'Mixed_7c'):
         H = x.H
         out = pb.alloc(H, H, 2048)
-        t3, td, tp = pb.alloc(H, H, 384, (1, 1)), pb.alloc(H, H, 448, (1, 1)), pb.alloc(H, H, 192)
+        b3 = pb.border_for(H, H, 384, (3, 3), pad=(1, 1))       # (1x3 / 3x1 siblings share the t3 buffer)
+        t3, td, tp = pb.alloc(H, H, 384, b3), pb.alloc(H, H, 448, b3), pb.alloc(H, H, 192)
         fused_1x1(x, [_basic(sd, blk + '.branch1x1', out.slice(0, 320)),
                       _basic(sd, blk + '.branch3x3_1', t3),
                       _basic(sd, blk + '.branch3x3dbl_1', td),
                       _raw(sd, blk + '.branch_pool', tp)], blk + '.1x1s')
         single(t3, blk + '.branch3x3_2a', 3, pad=(0, 1), out=out.slice(320, 704))
         single(t3, blk + '.branch3x3_2b', 3, pad=(1, 0), out=out.slice(704, 1088))
-        t = single(td, blk + '.branch3x3dbl_2', 3, pad=(1, 1), out_pad=(1, 1))
+        t = single(td, blk + '.branch3x3dbl_2', 3, pad=(1, 1), out_pad=b3)
         single(t, blk + '.branch3x3dbl_3a', 3, pad=(0, 1), out=out.slice(1088, 1472))
         single(t, blk + '.branch3x3dbl_3b', 3, pad=(1, 0), out=out.slice(1472, 1856))
         avg_branch(tp, blk + '.branch_pool', out.slice(1856, 2048), blk + '.branch_pool.avg')
@@ -456,30 +476,41 @@ def build_resnet(pb, sd, arch, inp, in_kind, R, affine=None):
         return out
 
     # a tensor carries the zero border its 3x3 consumer needs (basic blocks: block inputs/outputs)
-    blk_pad = (1, 1) if kind == 'basic' else (0, 0)
     H1 = sz(R, 7, 2, 3)
     a = pb.alloc(H1, H1, 64)
     sc, sh = fold_bn(sd, 'bn1', eps)
     pb.stem(inp, in_kind, R, R, sd['conv1.weight'], sc, sh, 2, 3, a, affine=affine, name='conv1')
-    x = pb.alloc(sz(H1, 3, 2, 1), sz(H1, 3, 2, 1), 64, blk_pad)
+    H2 = sz(H1, 3, 2, 1)
+    width0 = 64
+    x = pb.alloc(H2, H2, 64, pb.border_for(H2, H2, width0, (3, 3), pad=(1, 1)) if kind == 'basic' else (0, 0))
     pb.pool(IFCB_POOL_MAX, a, 3, 2, 1, x, name='maxpool')
-    nlayers = len(layers)
-    for li, nblocks in enumerate(layers):
-        for bi in range(nblocks):
-            pre = 'layer%d.%d' % (li + 1, bi)
-            stride = 2 if (li > 0 and bi == 0) else 1
-            last = (li == nlayers - 1 and bi == nblocks - 1)
-            opad = (0, 0) if last else blk_pad
-            identity = x
-            if (pre + '.downsample.0.weight') in sd:
-                identity = cbr(x, pre + '.downsample.0', pre + '.downsample.1', stride=stride, relu=False)
-            if kind == 'basic':
-                t = cbr(x, pre + '.conv1', pre + '.bn1', stride=stride, pad=1, out_pad=(1, 1))
-                x = cbr(t, pre + '.conv2', pre + '.bn2', pad=1, relu=True, residual=identity, out_pad=opad)
-            else:   # torchvision v1.5: the stride sits on the 3x3
-                t = cbr(x, pre + '.conv1', pre + '.bn1', out_pad=(1, 1))
-                t = cbr(t, pre + '.conv2', pre + '.bn2', stride=stride, pad=1)
-                x = cbr(t, pre + '.conv3', pre + '.bn3', relu=True, residual=identity, out_pad=opad)
+    # a tensor carries the zero border its 3x3 consumer wants (only when that conv will run the
+    # WINDOW algorithm: PlanBuilder.border_for)
+    blocks = [(li, bi) for li, nb in enumerate(layers) for bi in range(nb)]
+    for idx, (li, bi) in enumerate(blocks):
+        pre = 'layer%d.%d' % (li + 1, bi)
+        stride = 2 if (li > 0 and bi == 0) else 1
+        width = 64 << li
+        Ho = sz(x.H, 3, stride, 1)
+        identity = x
+        if (pre + '.downsample.0.weight') in sd:
+            identity = cbr(x, pre + '.downsample.0', pre + '.downsample.1', stride=stride, relu=False)
+        if kind == 'basic':
+            # border of the block output = what the NEXT block's conv1 (3x3, maybe stride 2) wants
+            if idx + 1 < len(blocks):
+                nli, nbi = blocks[idx + 1]
+                nstride = 2 if (nli > 0 and nbi == 0) else 1
+                opad = pb.border_for(Ho, Ho, 64 << nli, (3, 3), (nstride, nstride), (1, 1))
+            else:
+                opad = (0, 0)
+            t = cbr(x, pre + '.conv1', pre + '.bn1', stride=stride, pad=1,
+                    out_pad=pb.border_for(Ho, Ho, width, (3, 3), pad=(1, 1)))
+            x = cbr(t, pre + '.conv2', pre + '.bn2', pad=1, relu=True, residual=identity, out_pad=opad)
+        else:   # torchvision v1.5: the stride sits on the 3x3
+            t = cbr(x, pre + '.conv1', pre + '.bn1',
+                    out_pad=pb.border_for(x.H, x.W, width, (3, 3), (stride, stride), (1, 1)))
+            t = cbr(t, pre + '.conv2', pre + '.bn2', stride=stride, pad=1)
+            x = cbr(t, pre + '.conv3', pre + '.bn3', relu=True, residual=identity)
     return pb.head(x, sd['fc.weight'], sd['fc.bias'])
 
 

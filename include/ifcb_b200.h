@@ -119,7 +119,7 @@ enum { IFCB_CONV_AUTO = 0, IFCB_CONV_IM2COL = 1, IFCB_CONV_WINDOW = 2 };
  *   algo        IFCB_CONV_IM2COL: one TMA im2col load per filter tap (any stride);
  *               IFCB_CONV_WINDOW: stride 1 and in_pad == pad -- the padded input patch
  *               of a tile is loaded ONCE and filter taps are shifted UMMA descriptors;
- *               IFCB_CONV_AUTO picks WINDOW whenever it applies
+ *               IFCB_CONV_AUTO picks per shape (ifcb_conv_auto_config) among those that apply
  *   d_residual  view with the output's logical extent and its own zero border res_pad_*
  *   d_weight    16-bit [Cout_pad, kh*kw*Cin_pad] packed by the host: K index =
  *               (r*kw + s)*Cin_pad + ci, zero filled; Cin_pad = 32 for Cin <= 32 (64-byte
@@ -149,6 +149,13 @@ typedef struct {
 } ifcb_conv_desc;
 
 int ifcb_plan_add_conv(ifcb_plan* plan, const ifcb_conv_desc* desc);
+/* The algorithm (IFCB_CONV_IM2COL / IFCB_CONV_WINDOW) and N tile the library prefers for a
+ * conv over an H x W input -- what IFCB_CONV_AUTO / tile_n = 0 resolve to when the input
+ * buffer carries the padding WINDOW needs.  The host asks BEFORE allocating the producer's
+ * output so that only WINDOW inputs get a zero border, and passes tile_n on to
+ * ifcb_conv_geometry for weight packing. */
+int ifcb_conv_auto_config(int H, int W, int Cout, int kh, int kw, int stride_h, int stride_w,
+                          int pad_h, int pad_w, int32_t* algo, int32_t* tile_n);
 /* Packed-weight geometry for a conv: Cin_pad, K_pad = kh*kw*Cin_pad, tile_n and
  * Cout_pad the library will use (host packs weights / scale / shift to these). */
 int ifcb_conv_geometry(int Cin, int Cout, int kh, int kw, int tile_n_hint,

@@ -32,7 +32,7 @@ def time_layer(layer, algo, env):
     os.environ.update(env)
     name, Cin, H, W, Cout, kh, kw, pad = layer
     pb = PlanBuilder(B, dev, 'fp16')
-    ipad = pad if algo == 2 else (0, 0)
+    ipad = pad if algo == 2 else (PlanBuilder.border_for(H, W, Cout, (kh, kw), pad=pad) if algo == 0 else (0, 0))
     x = torch.randn((B, H + 2 * ipad[0], W + 2 * ipad[1], Cin), device=dev).half()
     pb.keep.append(x)
     P, Q = H + 2 * pad[0] - kh + 1, W + 2 * pad[1] - kw + 1
@@ -70,6 +70,7 @@ CONFIGS = [
     ('window m1', 2, {'IFCB_CONV_MSUB': '1'}),
     ('window m2', 2, {'IFCB_CONV_MSUB': '2'}),
     ('window g1', 2, {'IFCB_CONV_BGROUP': '1'}),
+    ('auto', 0, {}),
 ]
 print('%-26s' % 'layer (us @ batch %d)' % B + ''.join('%17s' % c[0] for c in CONFIGS))
 for layer in LAYERS:
