@@ -15,7 +15,7 @@ IFCB_STEM_IN_U8_GRAY, IFCB_STEM_IN_F32_NCHW = 0, 1
 IFCB_POOL_MAX, IFCB_POOL_AVG_AFFINE = 0, 1
 IFCB_MAX_SEGMENTS = 4
 IFCB_ACT_BF16, IFCB_ACT_FP16 = 0, 1
-IFCB_CONV_AUTO, IFCB_CONV_IM2COL, IFCB_CONV_WINDOW = 0, 1, 2
+IFCB_CONV_AUTO, IFCB_CONV_IM2COL, IFCB_CONV_WINDOW, IFCB_CONV_IM2COL_PAIR = 0, 1, 2, 3
 
 
 class ConvSegment(C.Structure):
@@ -82,7 +82,8 @@ _SIGNATURES = {
     'ifcb_conv_geometry': (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                      C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                      C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
-    'ifcb_conv_auto_config': (C.c_int, [C.c_int] * 9 + [C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    'ifcb_conv_auto_config': (C.c_int, [C.c_int] * 10 + [C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    'ifcb_conv_auto_tile_n': (C.c_int, [C.c_int, C.c_int]),
     'ifcb_plan_add_stem': (C.c_int, [C.c_void_p, C.POINTER(StemDesc)]),
     'ifcb_plan_add_pool': (C.c_int, [C.c_void_p, C.POINTER(PoolDesc)]),
     'ifcb_plan_add_head': (C.c_int, [C.c_void_p, C.POINTER(HeadDesc)]),
@@ -124,9 +125,9 @@ def conv_geometry(Cin, Cout, kh, kw, tile_n=0):
     return dict(Cin_pad=a.value, K_pad=b.value, tile_n=c.value, Cout_pad=d.value)
 
 
-def conv_auto_config(H, W, Cout, kh, kw, stride=(1, 1), pad=(0, 0)):
+def conv_auto_config(H, W, Cin, Cout, kh, kw, stride=(1, 1), pad=(0, 0)):
     """(algo, tile_n) the library prefers for this conv shape (IFCB_CONV_IM2COL / _WINDOW)."""
     a, t = C.c_int32(), C.c_int32()
-    check(lib().ifcb_conv_auto_config(H, W, Cout, kh, kw, stride[0], stride[1], pad[0], pad[1], C.byref(a), C.byref(t)),
+    check(lib().ifcb_conv_auto_config(H, W, Cin, Cout, kh, kw, stride[0], stride[1], pad[0], pad[1], C.byref(a), C.byref(t)),
           'conv_auto_config')
     return a.value, t.value

@@ -149,103 +149,93 @@ __device__ __forceinline__ void write_out(const uint8_t* stage, int lane, uint32
 template <bool FP16>
 __device__ __forceinline__ void epilogue_tile(const ConvKernelParams& p, uint32_t tmem_acc, int tile_row0, int n_lo, int lane,
                                               int sub, uint8_t* stage, const float* s_scale, const float* s_shift) {
-  // ---- where do this lane's rows land?  (n, p, q) per accumulator, n = -1: dropped ----
-  int rn[4], rp[4], rq[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    rn[j] = -1; rp[j] = 0; rq[j] = 0;
-    if (j < p.m_sub) {
-      const int i = tile_row0 + j * kBlockM + lane;
-      if (p.identity_rows) {
-        if (i < (int)p.rows) { rn[j] = 0; rq[j] = i; }
-      } else {
-        const RowMap rm = map_row(p, i);
-        if (rm.valid) { rn[j] = rm.n; rp[j] = rm.p; rq[j] = rm.q; }
-      }
-    }
-  }
-  uint32_t roff[4] = {kNoRow, kNoRow, kNoRow, kNoRow};
-  if (p.residual != nullptr) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-      if (rn[j] >= 0)
-        roff[j] = p.identity_rows ? (uint32_t)rq[j] * (uint32_t)p.res_ld
-                                  : (uint32_t)((rn[j] * (p.P + 2 * p.res_pad_h) + rp[j] + p.res_pad_h) * (p.Q + 2 * p.res_pad_w) + rq[j] + p.res_pad_w) * (uint32_t)p.res_ld;
-  }
   const int n_hi = n_lo + p.tile_n;
+  const int ms_shift = p.m_sub == 1 ? 0 : p.m_sub == 2 ? 1 : 2;
   uint4* srow = reinterpret_cast<uint4*>(stage + lane * 64);
   const int sw = (lane >> 1) & 3;
-  int unit = 0;
+  int next = sub;                                    // tile-wide index of this warp's next unit
+  int ubase = 0;                                     // tile-wide index of the segment's first unit
   for (int si = 0; si < p.n_seg; ++si) {
     const int g_lo = max(n_lo, p.seg_begin[si]), g_hi = min(n_hi, p.seg_end[si]);
     if (g_lo >= g_hi) continue;
+    const int nunits = ((g_hi - g_lo + 31) >> 5) << ms_shift;
+    if (next >= ubase + nunits) { ubase += nunits; continue; }     // none of this segment's units is ours
     const int relu = p.seg_relu[si];
     const uint32_t ld = (uint32_t)p.seg_ld[si];
-    // destination row offsets (elements) of this lane's rows inside the (possibly padded) output
-    uint32_t off[4];
-    {
-      const int ph = p.seg_pad_h[si], pw = p.seg_pad_w[si];
-      const int Hd = p.P + 2 * ph, Wd = p.Q + 2 * pw;
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        off[j] = rn[j] < 0 ? kNoRow
-                           : (p.identity_rows ? (uint32_t)rq[j] : (uint32_t)((rn[j] * Hd + rp[j] + ph) * Wd + rq[j] + pw)) * ld;
-    }
-    for (int g0 = g_lo; g0 < g_hi; g0 += 32) {
+    const int ph = p.seg_pad_h[si], pw = p.seg_pad_w[si];
+    const int Hd = p.P + 2 * ph, Wd = p.Q + 2 * pw;
+    __nv_bfloat16* seg_out = p.seg_out[si] + (g_lo - p.seg_begin[si]);
+    for (; next < ubase + nunits; next += kEpiPerQuad) {
+      const int u = next - ubase;
+      const int gi = u >> ms_shift;
+      const int j = u - (gi << ms_shift);
+      const int g0 = g_lo + gi * 32;
       const bool wide = (g_hi - g0) >= 32;                 // 32 columns, or a 16-column tail
-      __nv_bfloat16* gout = p.seg_out[si] + (g0 - p.seg_begin[si]);
-      for (int j = 0; j < p.m_sub; ++j, ++unit) {
-        if ((unit % kEpiPerQuad) != sub) continue;
-        const uint32_t off_j = j == 0 ? off[0] : j == 1 ? off[1] : j == 2 ? off[2] : off[3];
-        const uint32_t roff_j = j == 0 ? roff[0] : j == 1 ? roff[1] : j == 2 ? roff[2] : roff[3];
-        const uint32_t taddr = tmem_acc + (uint32_t)(j * p.tile_n + g0 - n_lo);
-        uint32_t v[2][16];
-        ptx::tmem_ld_32x32b_x16(taddr, v[0]);
-        if (wide) ptx::tmem_ld_32x32b_x16(taddr + 16u, v[1]);
-        ptx::tmem_ld_wait();
-        uint4 o[4];
-#pragma unroll
-        for (int ch = 0; ch < 2; ++ch) {
-          if (ch == 0 || wide) {
-            const int n = g0 + ch * 16;
-            float y[16];
-#pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4) {
-              const float4 sc = *reinterpret_cast<const float4*>(s_scale + n + 4 * q4);
-              const float4 sh = *reinterpret_cast<const float4*>(s_shift + n + 4 * q4);
-              ffma2(y[4 * q4 + 0], y[4 * q4 + 1], __uint_as_float(v[ch][4 * q4 + 0]), __uint_as_float(v[ch][4 * q4 + 1]),
-                    sc.x, sc.y, sh.x, sh.y);
-              ffma2(y[4 * q4 + 2], y[4 * q4 + 3], __uint_as_float(v[ch][4 * q4 + 2]), __uint_as_float(v[ch][4 * q4 + 3]),
-                    sc.z, sc.w, sh.z, sh.w);
-            }
-            if (p.residual != nullptr && roff_j != kNoRow) {
-              const uint4* rp4 = reinterpret_cast<const uint4*>(p.residual + roff_j + n);
-              const uint4 r0 = __ldg(rp4), r1 = __ldg(rp4 + 1);
-              const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                const float2 f = unpack_act2(rr[e], FP16 ? 1 : 0);
-                y[2 * e] += f.x;
-                y[2 * e + 1] += f.y;
-              }
-            }
-            if (relu) pack16<FP16, true>(y, o[2 * ch], o[2 * ch + 1]);
-            else pack16<FP16, false>(y, o[2 * ch], o[2 * ch + 1]);
+      // where does this lane's row of accumulator j land?  element offsets, kNoRow = dropped
+      uint32_t off_j = kNoRow, roff_j = kNoRow;
+      {
+        const int i = tile_row0 + j * kBlockM + lane;
+        if (p.identity_rows) {
+          if (i < (int)p.rows) {
+            off_j = (uint32_t)i * ld;
+            roff_j = (uint32_t)i * (uint32_t)p.res_ld;
+          }
+        } else {
+          const RowMap rm = map_row(p, i);
+          if (rm.valid) {
+            off_j = (uint32_t)((rm.n * Hd + rm.p + ph) * Wd + rm.q + pw) * ld;
+            roff_j = (uint32_t)((rm.n * (p.P + 2 * p.res_pad_h) + rm.p + p.res_pad_h) * (p.Q + 2 * p.res_pad_w) + rm.q + p.res_pad_w) * (uint32_t)p.res_ld;
           }
         }
-        // stage: row `lane` (64 B), 16-byte pieces XOR-swizzled by (row >> 1) & 3
-        srow[0 ^ sw] = o[0];
-        srow[1 ^ sw] = o[1];
-        if (wide) {
-          srow[2 ^ sw] = o[2];
-          srow[3 ^ sw] = o[3];
-        }
-        __syncwarp();
-        if (wide) write_out<4>(stage, lane, off_j, gout);
-        else write_out<2>(stage, lane, off_j, gout);
-        __syncwarp();
       }
+      const uint32_t taddr = tmem_acc + (uint32_t)(j * p.tile_n + g0 - n_lo);
+      uint32_t v[2][16];
+      ptx::tmem_ld_32x32b_x16(taddr, v[0]);
+      if (wide) ptx::tmem_ld_32x32b_x16(taddr + 16u, v[1]);
+      ptx::tmem_ld_wait();
+      uint4 o[4];
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch) {
+        if (ch == 0 || wide) {
+          const int n = g0 + ch * 16;
+          float y[16];
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const float4 sc = *reinterpret_cast<const float4*>(s_scale + n + 4 * q4);
+            const float4 sh = *reinterpret_cast<const float4*>(s_shift + n + 4 * q4);
+            ffma2(y[4 * q4 + 0], y[4 * q4 + 1], __uint_as_float(v[ch][4 * q4 + 0]), __uint_as_float(v[ch][4 * q4 + 1]),
+                  sc.x, sc.y, sh.x, sh.y);
+            ffma2(y[4 * q4 + 2], y[4 * q4 + 3], __uint_as_float(v[ch][4 * q4 + 2]), __uint_as_float(v[ch][4 * q4 + 3]),
+                  sc.z, sc.w, sh.z, sh.w);
+          }
+          if (p.residual != nullptr && roff_j != kNoRow) {
+            const uint4* rp4 = reinterpret_cast<const uint4*>(p.residual + roff_j + n);
+            const uint4 r0 = __ldg(rp4), r1 = __ldg(rp4 + 1);
+            const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float2 f = unpack_act2(rr[e], FP16 ? 1 : 0);
+              y[2 * e] += f.x;
+              y[2 * e + 1] += f.y;
+            }
+          }
+          if (relu) pack16<FP16, true>(y, o[2 * ch], o[2 * ch + 1]);
+          else pack16<FP16, false>(y, o[2 * ch], o[2 * ch + 1]);
+        }
+      }
+      // stage: row `lane` (64 B), 16-byte pieces XOR-swizzled by (row >> 1) & 3
+      srow[0 ^ sw] = o[0];
+      srow[1 ^ sw] = o[1];
+      if (wide) {
+        srow[2 ^ sw] = o[2];
+        srow[3 ^ sw] = o[3];
+      }
+      __syncwarp();
+      if (wide) write_out<4>(stage, lane, off_j, seg_out + gi * 32);
+      else write_out<2>(stage, lane, off_j, seg_out + gi * 32);
+      __syncwarp();
     }
+    ubase += nunits;
   }
 }
 
@@ -254,16 +244,21 @@ __device__ __forceinline__ void epilogue_tile(const ConvKernelParams& p, uint32_
 // (MS) so that every tcgen05.mma of a filter tap is straight-line code on the uniform
 // datapath: one tap = MS x KS MMAs, operands a_lo + j*jstride + 2k / b_lo + 2k.
 // ---------------------------------------------------------------------------------------
-template <int KS, int MS>
+template <int KS, int MS, bool PAIR = false>
 __device__ __forceinline__ void issue_tap(bool leader, uint32_t a_lo, uint32_t b_lo, uint32_t jstride, uint32_t d0,
                                           uint32_t dstep, uint32_t desc_hi, uint32_t idesc, uint32_t first) {
 #pragma unroll
   for (int j = 0; j < MS; ++j) {
 #pragma unroll
     for (int k = 0; k < KS; ++k)
-      if (leader)
-        ptx::umma_f16_lohi(d0 + (uint32_t)j * dstep, a_lo + (uint32_t)j * jstride + (uint32_t)(2 * k),
-                           b_lo + (uint32_t)(2 * k), desc_hi, idesc, k > 0 ? 1u : first);
+      if (leader) {
+        if (PAIR)
+          ptx::umma_f16_lohi_pair(d0 + (uint32_t)j * dstep, a_lo + (uint32_t)j * jstride + (uint32_t)(2 * k),
+                                  b_lo + (uint32_t)(2 * k), desc_hi, idesc, k > 0 ? 1u : first);
+        else
+          ptx::umma_f16_lohi(d0 + (uint32_t)j * dstep, a_lo + (uint32_t)j * jstride + (uint32_t)(2 * k),
+                             b_lo + (uint32_t)(2 * k), desc_hi, idesc, k > 0 ? 1u : first);
+      }
   }
 }
 
@@ -288,7 +283,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                  const ConvKernelParams p) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the swizzled operand tiles
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment by pointer arithmetic on the __shared__ array (keeps the address space known: LDS/STS, not generic)
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   const int row_bytes = p.row_bytes;                                  // 128 or 64
   const int a_tile_bytes = kBlockM * row_bytes;                       // IM2COL stage A part
   const int b_tap_bytes = p.tile_n * row_bytes;
@@ -543,12 +539,192 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   if (warp == 1) ptx::tmem_dealloc(tmem_base, kTmemCols);
 }
 
+// ---------------------------------------------------------------------------------------
+// IM2COL on CTA PAIRS (cluster of 2, tcgen05 cta_group::2): one tile = 256 output pixels x
+// tile_n.  Each CTA loads its own 128 pixel rows of A and HALF of the weight tile; the leader
+// CTA issues M = 256 MMAs that drive both SMs' tensor cores.  Per SM and k-block this halves
+// the weight bytes both fetched from L2 and read from shared memory -- a 128-row tile streams
+// weights at 64 B per MMA clock, which is the L2 -> SM limit (profiles/r01_layer_matrix_*.txt).
+//   full[s]   leader only: expect_tx covers both CTAs' loads (peer TMA signals it remotely)
+//   empty[s], tmem_full[a]   in each CTA, armed by multicast tcgen05.commit
+//   tmem_empty[a]   leader only: every epilogue warp of both CTAs arrives on it
+// ---------------------------------------------------------------------------------------
+template <bool FP16>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+conv_umma_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                      const ConvKernelParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment by pointer arithmetic on the __shared__ array (keeps the address space known: LDS/STS, not generic)
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int row_bytes = p.row_bytes;
+  const int a_tile_bytes = kBlockM * row_bytes;
+  const int b_half_bytes = (p.tile_n >> 1) * row_bytes;
+  const int stage_bytes = a_tile_bytes + b_half_bytes;
+  uint8_t* bar_base = smem + (size_t)p.stages * stage_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_base);
+  uint64_t* empty_bar = full_bar + kMaxStages;
+  uint64_t* tmem_full = full_bar + 2 * kMaxStages + 8;
+  uint64_t* tmem_empty = full_bar + 2 * kMaxStages + 10;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(full_bar + 2 * kMaxStages + 12);
+  float* s_scale = reinterpret_cast<float*>(bar_base + kBarBytes);
+  float* s_shift = s_scale + p.cout_pad;
+  uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_shift + p.cout_pad);
+  for (int i = threadIdx.x; i < p.cout_pad; i += kThreads) {
+    s_scale[i] = p.scale[i];
+    s_shift[i] = p.shift[i];
+  }
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tmap_a);
+    ptx::prefetch_tensormap(&tmap_b);
+    for (int s = 0; s < p.stages; ++s) {
+      ptx::mbar_init(full_bar + s, 1);
+      ptx::mbar_init(empty_bar + s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(tmem_full + s, 1);
+      ptx::mbar_init(tmem_empty + s, 2 * kEpiWarps);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc_pair(tmem_slot, kTmemCols);
+    ptx::tmem_relinquish_pair();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int m_tiles = (int)((p.rows + 2 * kBlockM - 1) / (2 * kBlockM));
+  const int total_tiles = m_tiles * p.n_tiles;
+  const int taps = p.kh * p.kw;
+  const int row_elems = row_bytes >> 1;
+  const bool skip_loads = (p.debug_flags & 1) != 0;
+  const bool skip_mma = (p.debug_flags & 2) != 0;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = pair; tile < total_tiles; tile += npairs) {
+      const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
+      const int n0 = n_tile * p.tile_n + (int)rank * (p.tile_n >> 1);
+      const int m0 = m_tile * 2 * kBlockM + (int)rank * kBlockM;
+      const int img = m0 / p.rows_per_img;
+      const int rem = m0 - img * p.rows_per_img;
+      const int op = rem / p.row_w, oq = rem - op * p.row_w;
+      const int w0 = oq * p.stride_w - p.pad_w;
+      const int h0 = op * p.stride_h - p.pad_h;
+      int kcol = 0;
+      for (int r = 0; r < p.kh; ++r) {
+        for (int s = 0; s < p.kw; ++s) {
+          for (int cb = 0; cb < p.cblocks; ++cb, kcol += row_elems) {
+            ptx::mbar_wait(empty_bar + stage, phase ^ 1);
+            if (ptx::elect_one()) {
+              uint8_t* a_dst = smem + (size_t)stage * stage_bytes;
+              const uint32_t lead_full = ptx::mapa(ptx::smem_u32(full_bar + stage), 0u);
+              if (skip_loads) {
+                if (rank == 0) ptx::mbar_arrive(full_bar + stage);
+              } else {
+                if (rank == 0) ptx::mbar_arrive_expect_tx(full_bar + stage, (uint32_t)(2 * stage_bytes));
+                ptx::tma_load_im2col_4d_pair(a_dst, &tmap_a, lead_full, cb * row_elems, w0, h0, img, (uint16_t)s, (uint16_t)r);
+                ptx::tma_load_2d_pair(a_dst + a_tile_bytes, &tmap_b, lead_full, kcol, n0);
+              }
+            }
+            __syncwarp();
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (rank == 0) {
+      const uint32_t idesc = ptx::umma_idesc_f16(2 * kBlockM, p.tile_n, FP16 ? 1 : 0);
+      const uint32_t desc_hi = ptx::umma_desc_hi(row_bytes);
+      const int full_ksteps = row_bytes >> 5;
+      const bool leader = ptx::elect_one();
+      bool ready = false;
+      int stage = 0;
+      uint32_t phase = 0;
+      int local = 0;
+      const int kblocks = taps * p.cblocks;
+      for (int tile = pair; tile < total_tiles; tile += npairs, ++local) {
+        const int acc = local & 1;
+        const uint32_t acc_phase = (local >> 1) & 1;
+        ptx::mbar_wait(tmem_empty + acc, acc_phase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kAccBufCols);
+        int cb = 0;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          if (!ready) ptx::mbar_wait(full_bar + stage, phase);
+          ptx::tc_fence_after();
+          const uint32_t a_lo = ptx::umma_desc_lo(ptx::smem_u32(smem + (size_t)stage * stage_bytes));
+          const uint32_t b_lo = a_lo + (uint32_t)(a_tile_bytes >> 4);
+          const int ksteps = (cb == p.cblocks - 1) ? p.last_ksteps : full_ksteps;
+          const int cur = stage;
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          ready = ptx::mbar_test_wait(full_bar + stage, phase) != 0;
+          const uint32_t first = kb > 0 ? 1u : 0u;
+          if (!skip_mma) {
+            switch (ksteps) {
+              case 1: issue_tap<1, 1, true>(leader, a_lo, b_lo, 0u, d_tmem, 0u, desc_hi, idesc, first); break;
+              case 2: issue_tap<2, 1, true>(leader, a_lo, b_lo, 0u, d_tmem, 0u, desc_hi, idesc, first); break;
+              case 3: issue_tap<3, 1, true>(leader, a_lo, b_lo, 0u, d_tmem, 0u, desc_hi, idesc, first); break;
+              default: issue_tap<4, 1, true>(leader, a_lo, b_lo, 0u, d_tmem, 0u, desc_hi, idesc, first); break;
+            }
+          }
+          if (leader) ptx::umma_commit_pair(empty_bar + cur);
+          __syncwarp();
+          if (++cb == p.cblocks) cb = 0;
+        }
+        if (leader) ptx::umma_commit_pair(tmem_full + acc);
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===================== epilogue (both CTAs, own 128 rows) =====================
+    const int quad = warp & 3;
+    const int sub = (warp - 2) >> 2;
+    uint8_t* stage = s_stage + (warp - 2) * kStageTile;
+    const uint32_t lead_empty0 = ptx::mapa(ptx::smem_u32(tmem_empty), 0u);
+    int local = 0;
+    for (int tile = pair; tile < total_tiles; tile += npairs, ++local) {
+      const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
+      const int acc = local & 1;
+      const uint32_t acc_phase = (local >> 1) & 1;
+      ptx::mbar_wait(tmem_full + acc, acc_phase);
+      ptx::tc_fence_after();
+      if (!(p.debug_flags & 4)) {
+        const uint32_t tmem_acc = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * kAccBufCols);
+        epilogue_tile<FP16>(p, tmem_acc, m_tile * 2 * kBlockM + (int)rank * kBlockM + quad * 32, n_tile * p.tile_n, lane, sub, stage,
+                               s_scale, s_shift);
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive_cluster(lead_empty0 + (uint32_t)(acc * 8));
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync();
+  if (warp == 1) ptx::tmem_dealloc_pair(tmem_base, kTmemCols);
+}
+
 constexpr int kSmemBudget = 227 * 1024;
 
 }  // namespace
 
-// Shared-memory plan of a layer (kp.row_bytes, tile_n, cout_pad, kh, kw set).  Returns false if nothing fits.
-bool conv_plan_smem(ConvKernelParams& kp, bool window, int halo_rows) {
+// Shared-memory plan of a layer (kp.row_bytes, tile_n, cout_pad, kh, kw, cblocks, last_ksteps set).
+// Returns false if nothing fits.
+bool conv_plan_smem(ConvKernelParams& kp, bool window, bool pair, int halo_rows) {
   const int row_bytes = kp.row_bytes;
   const int b_tap = kp.tile_n * row_bytes;
   const int a_tile = kBlockM * row_bytes;
@@ -560,35 +736,50 @@ bool conv_plan_smem(ConvKernelParams& kp, bool window, int halo_rows) {
     kp.a_slot_bytes = 0;
     kp.box_rows = kp.n_boxes = 0;
     kp.b_group = 1;
-    int s = (kSmemBudget - fixed) / (a_tile + b_tap);
+    int s = (kSmemBudget - fixed) / (a_tile + (pair ? b_tap / 2 : b_tap));
     if (s > 10) s = 10;
     kp.stages = s;
     return s >= 2;
   }
-  // m (accumulators per tile): as large as TMEM double buffering and smem allow; taps per weight
-  // pipeline stage (b_group): as many as fit (<= 48 KB per stage, >= 2 stages) -- every stage
-  // costs the MMA warp a barrier round trip (~250 clk) against 4 MMAs of run-ahead
+  // WINDOW: enumerate (m accumulators per tile, A slots, taps per weight stage) and keep the
+  // cheapest by a small cycle model per 128 output rows (constants measured on B200):
+  //   MMA      taps * ksteps * max(N/2, 32 + N/4)           (smem operand port: 128 B/clk)
+  //   loads    smem fill bytes / 60 B/clk                   (L2 -> SM)
+  //   barriers ~250 clk of issue stall per pipeline stage   (4 MMAs of run-ahead)
+  const int full_ks = row_bytes >> 5;
+  const int ks_total = (kp.cblocks - 1) * full_ks + kp.last_ksteps;
+  const int t_mma = kp.tile_n / 2 > 32 + kp.tile_n / 4 ? kp.tile_n / 2 : 32 + kp.tile_n / 4;
+  const double mma_clk = (double)taps * ks_total * t_mma;
+  double best = 1e30;
+  bool found = false;
   for (int m = 4; m >= 1; m >>= 1) {
     if (m > kp.m_sub_cap) continue;
     if (m * kp.tile_n > kAccBufCols) continue;
     const int rows = kBlockM * m + halo_rows;
     const int n_boxes = (rows + 255) / 256;
-    int box_rows = ((rows + n_boxes - 1) / n_boxes + 7) & ~7;
+    const int box_rows = ((rows + n_boxes - 1) / n_boxes + 7) & ~7;
     const int slot = (n_boxes * box_rows * row_bytes + 1023) & ~1023;
     for (int slots = kp.a_slots_pref; slots >= 1; --slots) {
       const int left = kSmemBudget - fixed - slots * slot;
-      int g = 49152 / b_tap;
-      if (g < 1) g = 1;
-      if (g > taps) g = taps;
-      if (kp.b_group_cap > 0 && g > kp.b_group_cap) g = kp.b_group_cap;
-      for (; g >= 1; --g) {
+      int gmax = 49152 / b_tap;
+      if (gmax < 1) gmax = 1;
+      if (gmax > taps) gmax = taps;
+      if (kp.b_group_cap > 0 && gmax > kp.b_group_cap) gmax = kp.b_group_cap;
+      for (int g = gmax; g >= 1; --g) {
         const int n_groups = (taps + g - 1) / g;
         const int gb = (taps + n_groups - 1) / n_groups;      // balanced group size
         const int b_stage = gb * b_tap;
         int s = left / b_stage;
         if (s > 6) s = 6;
-        const int need = (gb >= 2 || slots >= 2) ? 2 : 3;
-        if (s >= need) {
+        if (s < 2) continue;
+        const double load_clk = ((double)kp.cblocks * slot + (double)kp.cblocks * taps * b_tap) / m / 60.0;
+        const double bar_clk = (double)kp.cblocks * (n_groups + 1) * 250.0 / m;
+        double score = (mma_clk > load_clk ? mma_clk : load_clk) + bar_clk;
+        if (slots == 1) score += (double)kp.cblocks * slot / m / 60.0;     // A load not overlapped
+        if (s == 2 && n_groups > 1) score += 0.25 * bar_clk;                // shallow weight ring
+        if (score < best) {
+          best = score;
+          found = true;
           kp.m_sub = m;
           kp.a_slots = slots;
           kp.a_slot_bytes = slot;
@@ -596,19 +787,17 @@ bool conv_plan_smem(ConvKernelParams& kp, bool window, int halo_rows) {
           kp.n_boxes = n_boxes;
           kp.stages = s;
           kp.b_group = gb;
-          return true;
         }
       }
-      if (m > 1) break;      // prefer a smaller m with two slots over a single-slot large m
     }
   }
-  return false;
+  return found;
 }
 
-int conv_smem_bytes(const ConvKernelParams& kp, bool window) {
+int conv_smem_bytes(const ConvKernelParams& kp, bool window, bool pair) {
   const int b_tap = kp.tile_n * kp.row_bytes;
   const int ops = window ? kp.a_slots * kp.a_slot_bytes + kp.stages * kp.b_group * b_tap
-                         : kp.stages * (kBlockM * kp.row_bytes + b_tap);
+                         : kp.stages * (kBlockM * kp.row_bytes + (pair ? b_tap / 2 : b_tap));
   return ops + epilogue_smem(kp.cout_pad) + 1024;
 }
 
@@ -626,10 +815,25 @@ int launch_variant(const ConvLayer& L, const ConvKernelParams& p, int grid, int 
 }
 }  // namespace
 
+namespace {
+template <bool FP16>
+int launch_pair(const ConvLayer& L, const ConvKernelParams& p, int grid, int smem, cudaStream_t stream) {
+  static int attr_smem = 0;
+  if (smem > attr_smem) {
+    IFCB_CUDA_CHECK(cudaFuncSetAttribute(conv_umma_pair_kernel<FP16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_smem = smem;
+  }
+  // cluster dimensions (2,1,1) are compiled into the kernel (__cluster_dims__); grid is even
+  conv_umma_pair_kernel<FP16><<<grid, kThreads, smem, stream>>>(L.tmap_a, L.tmap_b, p);
+  IFCB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+}  // namespace
+
 int launch_conv(const ConvLayer& L, int batch, cudaStream_t stream) {
   ConvKernelParams p = L.kp;
   p.rows = (long long)batch * p.rows_per_img;
-  const int tile_rows = kBlockM * p.m_sub;
+  const int tile_rows = kBlockM * p.m_sub * (L.pair ? 2 : 1);
   const long long m_tiles = (p.rows + tile_rows - 1) / tile_rows;
   const long long total = m_tiles * p.n_tiles;
   if (total == 0) return 0;
@@ -637,8 +841,13 @@ int launch_conv(const ConvLayer& L, int batch, cudaStream_t stream) {
     set_error("conv: %lld GEMM rows exceed the 32-bit row index", p.rows);
     return -1;
   }
+  const int smem = conv_smem_bytes(p, L.window, L.pair);
+  if (L.pair) {
+    const int pairs = sm_count() / 2;
+    const int grid = 2 * (int)(total < pairs ? total : pairs);
+    return p.fp16 ? launch_pair<true>(L, p, grid, smem, stream) : launch_pair<false>(L, p, grid, smem, stream);
+  }
   const int grid = (int)(total < sm_count() ? total : sm_count());
-  const int smem = conv_smem_bytes(p, L.window);
   if (L.window) return p.fp16 ? launch_variant<true, true>(L, p, grid, smem, stream) : launch_variant<true, false>(L, p, grid, smem, stream);
   return p.fp16 ? launch_variant<false, true>(L, p, grid, smem, stream) : launch_variant<false, false>(L, p, grid, smem, stream);
 }
@@ -652,7 +861,8 @@ namespace {
 __global__ void im2col_probe_kernel(const __grid_constant__ CUtensorMap tmap_a, int c, int w, int h, int n,
                                     int off_w, int off_h, int tile_bytes, uint8_t* out) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment by pointer arithmetic on the __shared__ array (keeps the address space known: LDS/STS, not generic)
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + tile_bytes);
   if (threadIdx.x == 0) {
     ptx::mbar_init(bar, 1);

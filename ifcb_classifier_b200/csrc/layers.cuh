@@ -43,6 +43,7 @@ struct ConvLayer {
   ConvKernelParams kp;
   int batch_cap;
   bool window;
+  bool pair;                   // IM2COL on CTA pairs (cta_group::2): tmap_b box holds tile_n/2 rows
 };
 
 struct StemLayer {
@@ -61,10 +62,10 @@ struct HeadLayer {
 };
 
 int launch_conv(const ConvLayer& L, int batch, cudaStream_t stream);
-bool conv_plan_smem(ConvKernelParams& kp, bool window, int halo_rows);
+bool conv_plan_smem(ConvKernelParams& kp, bool window, bool pair, int halo_rows);
 int launch_im2col_probe(const ConvLayer& L, int c, int w, int h, int n, int off_w, int off_h, void* d_out,
                         cudaStream_t stream);
-int conv_smem_bytes(const ConvKernelParams& kp, bool window);
+int conv_smem_bytes(const ConvKernelParams& kp, bool window, bool pair);
 int launch_stem(const StemLayer& L, int batch, cudaStream_t stream);
 int launch_pool(const PoolLayer& L, int batch, cudaStream_t stream);
 int launch_head(const HeadLayer& L, int batch, cudaStream_t stream);

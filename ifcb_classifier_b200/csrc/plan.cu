@@ -61,22 +61,32 @@ int pick_tile_n(int Cout, int hint) {
 //  * A 128-row tile streams the whole weight matrix at 64 B per MMA clock -- the L2 limit --
 //    so WINDOW layers wider than 128 channels are split into N tiles <= 128 to make room in
 //    TMEM for two accumulators per weight tile.
-void auto_config(int H, int W, int Cout, int kh, int kw, int stride_h, int stride_w, int pad_h, int pad_w,
+//  * IM2COL runs on CTA pairs (256-pixel tiles, N tile <= 256 split over the two SMs).
+int auto_tile_n(int Cout, int algo) {
+  const int c16 = (Cout + 15) & ~15;
+  if (algo == IFCB_CONV_WINDOW && c16 > 128) {
+    const int t = (c16 + 127) / 128;
+    return (((c16 + t - 1) / t) + 15) & ~15;
+  }
+  if (algo == IFCB_CONV_IM2COL_PAIR) {
+    const int t = (c16 + 255) / 256;
+    return (((c16 + t - 1) / t) + 15) & ~15;        // multiple of 16: each SM holds tile_n/2 rows
+  }
+  return pick_tile_n(Cout, 0);
+}
+
+void auto_config(int H, int W, int Cin, int Cout, int kh, int kw, int stride_h, int stride_w, int pad_h, int pad_w,
                  int* algo, int* tile_n) {
   const int P = out_dim(H, kh, stride_h, pad_h), Q = out_dim(W, kw, stride_w, pad_w);
   const int taps = kh * kw;
   const double junk = (double)(H + 2 * pad_h) * (W + 2 * pad_w) / ((double)P * Q);
   const bool window = stride_h == 1 && stride_w == 1 && taps >= 4 && junk <= 1.30;
-  if (algo) *algo = window ? IFCB_CONV_WINDOW : IFCB_CONV_IM2COL;
-  if (tile_n) {
-    const int c16 = (Cout + 15) & ~15;
-    int tn = pick_tile_n(Cout, 0);
-    if (window && c16 > 128) {
-      const int t = (c16 + 127) / 128;
-      tn = (((c16 + t - 1) / t) + 15) & ~15;
-    }
-    *tile_n = tn;
-  }
+  static const bool nopair = getenv("IFCB_CONV_NOPAIR") != nullptr;
+  // CTA pairs pay off only with a deep K loop and a wide N tile (measured: K >= 512, Cout >= 128)
+  const bool pair = !nopair && taps * ((Cin + 63) / 64) >= 8 && Cout >= 128;
+  const int a = window ? IFCB_CONV_WINDOW : (pair ? IFCB_CONV_IM2COL_PAIR : IFCB_CONV_IM2COL);
+  if (algo) *algo = a;
+  if (tile_n) *tile_n = auto_tile_n(Cout, a);
 }
 
 }  // namespace
@@ -116,17 +126,22 @@ extern "C" int ifcb_conv_geometry(int Cin, int Cout, int kh, int kw, int tile_n_
   return 0;
 }
 
-extern "C" int ifcb_conv_auto_config(int H, int W, int Cout, int kh, int kw, int stride_h, int stride_w, int pad_h,
+extern "C" int ifcb_conv_auto_config(int H, int W, int Cin, int Cout, int kh, int kw, int stride_h, int stride_w, int pad_h,
                                      int pad_w, int32_t* algo, int32_t* tile_n) {
-  IFCB_ARG_CHECK(H > 0 && W > 0 && Cout > 0 && kh > 0 && kw > 0 && stride_h > 0 && stride_w > 0 && pad_h >= 0 && pad_w >= 0,
+  IFCB_ARG_CHECK(H > 0 && W > 0 && Cin > 0 && Cout > 0 && kh > 0 && kw > 0 && stride_h > 0 && stride_w > 0 && pad_h >= 0 && pad_w >= 0,
                  "ifcb_conv_auto_config: bad shape");
   IFCB_ARG_CHECK(out_dim(H, kh, stride_h, pad_h) > 0 && out_dim(W, kw, stride_w, pad_w) > 0,
                  "ifcb_conv_auto_config: empty output");
   int a = 0, t = 0;
-  auto_config(H, W, Cout, kh, kw, stride_h, stride_w, pad_h, pad_w, &a, &t);
+  auto_config(H, W, Cin, Cout, kh, kw, stride_h, stride_w, pad_h, pad_w, &a, &t);
   if (algo) *algo = a;
   if (tile_n) *tile_n = t;
   return 0;
+}
+
+extern "C" int ifcb_conv_auto_tile_n(int Cout, int algo) {
+  if (Cout <= 0 || algo < IFCB_CONV_IM2COL || algo > IFCB_CONV_IM2COL_PAIR) return -1;
+  return ifcb::auto_tile_n(Cout, algo);
 }
 
 extern "C" int ifcb_plan_add_conv(ifcb_plan* plan, const ifcb_conv_desc* d) {
@@ -145,7 +160,7 @@ extern "C" int ifcb_plan_add_conv(ifcb_plan* plan, const ifcb_conv_desc* d) {
   IFCB_ARG_CHECK(d->tile_n == 0 || (d->tile_n % 16 == 0 && d->tile_n >= 16 && d->tile_n <= 256),
                  "conv: tile_n=%d must be a multiple of 16 in [16,256]", d->tile_n);
   IFCB_ARG_CHECK(d->dtype == IFCB_ACT_BF16 || d->dtype == IFCB_ACT_FP16, "conv: bad dtype %d", d->dtype);
-  IFCB_ARG_CHECK(d->algo >= IFCB_CONV_AUTO && d->algo <= IFCB_CONV_WINDOW, "conv: bad algo %d", d->algo);
+  IFCB_ARG_CHECK(d->algo >= IFCB_CONV_AUTO && d->algo <= IFCB_CONV_IM2COL_PAIR, "conv: bad algo %d", d->algo);
   int rc = resolve_driver();
   if (rc) return rc;
 
@@ -153,13 +168,16 @@ extern "C" int ifcb_plan_add_conv(ifcb_plan* plan, const ifcb_conv_desc* d) {
   IFCB_ARG_CHECK(d->algo != IFCB_CONV_WINDOW || can_window,
                  "conv: the window algorithm needs stride 1 and an input buffer padded by at least the conv padding");
   int auto_algo = IFCB_CONV_IM2COL, auto_tile_n = 0;
-  auto_config(d->H, d->W, d->Cout, d->kh, d->kw, d->stride_h, d->stride_w, d->pad_h, d->pad_w, &auto_algo, &auto_tile_n);
+  auto_config(d->H, d->W, d->Cin, d->Cout, d->kh, d->kw, d->stride_h, d->stride_w, d->pad_h, d->pad_w, &auto_algo, &auto_tile_n);
   const bool window = d->algo == IFCB_CONV_WINDOW || (d->algo == IFCB_CONV_AUTO && can_window && auto_algo == IFCB_CONV_WINDOW);
-  const int tile_n_req = d->tile_n ? d->tile_n : (window ? auto_tile_n : 0);
+  const bool pair = !window && (d->algo == IFCB_CONV_IM2COL_PAIR || (d->algo == IFCB_CONV_AUTO && auto_algo == IFCB_CONV_IM2COL_PAIR));
+  const int tile_n_req = d->tile_n ? d->tile_n
+                                   : ifcb::auto_tile_n(d->Cout, window ? IFCB_CONV_WINDOW : pair ? IFCB_CONV_IM2COL_PAIR : IFCB_CONV_IM2COL);
 
   Layer L{};
   L.kind = kConv;
   L.conv.window = window;
+  L.conv.pair = pair;
   ConvKernelParams& kp = L.conv.kp;
   const int P = out_dim(d->H, d->kh, d->stride_h, d->pad_h);
   const int Q = out_dim(d->W, d->kw, d->stride_w, d->pad_w);
@@ -196,7 +214,7 @@ extern "C" int ifcb_plan_add_conv(ifcb_plan* plan, const ifcb_conv_desc* d) {
   }
   kp.win_shift0 = (d->in_pad_h - d->pad_h) * Wp + (d->in_pad_w - d->pad_w);
   const int halo = kp.win_shift0 + (d->kh - 1) * Wp + (d->kw - 1);
-  IFCB_ARG_CHECK(conv_plan_smem(kp, window, halo), "conv: no shared-memory plan for tile_n=%d halo=%d", tile_n, halo);
+  IFCB_ARG_CHECK(conv_plan_smem(kp, window, pair, halo), "conv: no shared-memory plan for tile_n=%d halo=%d", tile_n, halo);
   kp.scale = d->d_scale;
   kp.shift = d->d_shift;
   kp.residual = reinterpret_cast<const __nv_bfloat16*>(d->d_residual);
@@ -275,7 +293,7 @@ extern "C" int ifcb_plan_add_conv(ifcb_plan* plan, const ifcb_conv_desc* d) {
   {
     cuuint64_t gdim[2] = {(cuuint64_t)k_pad, (cuuint64_t)cout_pad};
     cuuint64_t gstr[1] = {(cuuint64_t)k_pad * 2};
-    cuuint32_t box[2] = {(cuuint32_t)row_elems, (cuuint32_t)tile_n};
+    cuuint32_t box[2] = {(cuuint32_t)row_elems, (cuuint32_t)(pair ? tile_n / 2 : tile_n)};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = g_encode_tiled(&L.conv.tmap_b, dt, 2, const_cast<void*>(d->d_weight), gdim, gstr, box, estr,
                                 CU_TENSOR_MAP_INTERLEAVE_NONE, swz,

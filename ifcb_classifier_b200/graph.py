@@ -116,10 +116,10 @@ class PlanBuilder(object):
         return t
 
     @staticmethod
-    def border_for(H, W, Co, k, stride=(1, 1), pad=(0, 0)):
+    def border_for(H, W, Co, k, stride=(1, 1), pad=(0, 0), Ci=64):
         """Zero border the INPUT of a conv should be allocated with: its padding when the library
         will run the conv with the WINDOW algorithm (which reads padding from memory), else none."""
-        algo, _ = _lib.conv_auto_config(H, W, Co, k[0], k[1], stride, pad)
+        algo, _ = _lib.conv_auto_config(H, W, Ci, Co, k[0], k[1], stride, pad)
         return tuple(pad) if algo == _lib.IFCB_CONV_WINDOW else (0, 0)
 
     # -- layers ---------------------------------------------------------------
@@ -132,14 +132,15 @@ class PlanBuilder(object):
         assert Ci == x.C, (name, Ci, x.C)
         Co = sum(int(m['weight'].shape[0]) for m in members)
         # resolve AUTO / tile_n here so that weight packing (tile_n) and the plan agree
-        a_pref, tn_pref = _lib.conv_auto_config(x.H, x.W, Co, kh, kw, stride, pad)
         if algo == _lib.IFCB_CONV_AUTO:
+            a_pref, _ = _lib.conv_auto_config(x.H, x.W, Ci, Co, kh, kw, stride, pad)
             can_window = tuple(stride) == (1, 1) and x.pad[0] >= pad[0] and x.pad[1] >= pad[1]
-            algo = _lib.IFCB_CONV_WINDOW if (a_pref == _lib.IFCB_CONV_WINDOW and can_window) else _lib.IFCB_CONV_IM2COL
-        if algo == _lib.IFCB_CONV_WINDOW and tile_n == 0:
-            c16 = (Co + 15) // 16 * 16
-            t = (c16 + 127) // 128
-            tile_n = ((c16 + t - 1) // t + 15) // 16 * 16 if c16 > 128 else 0
+            if a_pref == _lib.IFCB_CONV_WINDOW:
+                algo = _lib.IFCB_CONV_WINDOW if can_window else _lib.IFCB_CONV_IM2COL
+            else:
+                algo = a_pref
+        if tile_n == 0:
+            tile_n = _lib.lib().ifcb_conv_auto_tile_n(Co, algo)
         geo = _lib.conv_geometry(Ci, Co, kh, kw, tile_n)
         Cp, Kp, Np = geo['Cin_pad'], geo['K_pad'], geo['Cout_pad']
         wcat = torch.cat([m['weight'].float() for m in members], 0)          # [Co, Ci, kh, kw]

@@ -108,7 +108,7 @@ typedef struct {
 } ifcb_conv_segment;
 
 #define IFCB_MAX_SEGMENTS 4
-enum { IFCB_CONV_AUTO = 0, IFCB_CONV_IM2COL = 1, IFCB_CONV_WINDOW = 2 };
+enum { IFCB_CONV_AUTO = 0, IFCB_CONV_IM2COL = 1, IFCB_CONV_WINDOW = 2, IFCB_CONV_IM2COL_PAIR = 3 };
 
 /* K2  Conv2d(bias=False) + folded BatchNorm + ReLU as a tcgen05 implicit GEMM
  * (torchvision BasicConv2d, inception.py:398-407; ResNet conv-bn-relu).
@@ -117,6 +117,8 @@ enum { IFCB_CONV_AUTO = 0, IFCB_CONV_IM2COL = 1, IFCB_CONV_WINDOW = 2 };
  *               stored with a zero border of in_pad_h / in_pad_w pixels (physical
  *               [batch_cap, H+2*in_pad_h, W+2*in_pad_w, in_ld]); d_in = first border pixel
  *   algo        IFCB_CONV_IM2COL: one TMA im2col load per filter tap (any stride);
+ *               IFCB_CONV_IM2COL_PAIR: the same on CTA pairs (cluster of 2, tcgen05
+ *               cta_group::2): 256-pixel tiles, each SM loads half of every weight tile;
  *               IFCB_CONV_WINDOW: stride 1 and in_pad == pad -- the padded input patch
  *               of a tile is loaded ONCE and filter taps are shifted UMMA descriptors;
  *               IFCB_CONV_AUTO picks per shape (ifcb_conv_auto_config) among those that apply
@@ -154,8 +156,10 @@ int ifcb_plan_add_conv(ifcb_plan* plan, const ifcb_conv_desc* desc);
  * buffer carries the padding WINDOW needs.  The host asks BEFORE allocating the producer's
  * output so that only WINDOW inputs get a zero border, and passes tile_n on to
  * ifcb_conv_geometry for weight packing. */
-int ifcb_conv_auto_config(int H, int W, int Cout, int kh, int kw, int stride_h, int stride_w,
+int ifcb_conv_auto_config(int H, int W, int Cin, int Cout, int kh, int kw, int stride_h, int stride_w,
                           int pad_h, int pad_w, int32_t* algo, int32_t* tile_n);
+/* N tile the library uses for `Cout` output channels under a given (non-AUTO) algorithm. */
+int ifcb_conv_auto_tile_n(int Cout, int algo);
 /* Packed-weight geometry for a conv: Cin_pad, K_pad = kh*kw*Cin_pad, tile_n and
  * Cout_pad the library will use (host packs weights / scale / shift to these). */
 int ifcb_conv_geometry(int Cin, int Cout, int kh, int kw, int tile_n_hint,

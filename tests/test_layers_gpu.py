@@ -134,11 +134,11 @@ def test_im2col_tma_probe(cuda):
         pb.close()
 
 
-@pytest.mark.parametrize('algo', ['im2col', 'window'])
+@pytest.mark.parametrize('algo', ['im2col', 'window', 'pair'])
 @pytest.mark.parametrize('case', CONV_CASES, ids=[c[0] for c in CONV_CASES])
 def test_conv_bn_relu(cuda, case, algo):
     from ifcb_classifier_b200.graph import PlanBuilder
-    from ifcb_classifier_b200._lib import IFCB_CONV_IM2COL, IFCB_CONV_WINDOW
+    from ifcb_classifier_b200._lib import IFCB_CONV_IM2COL, IFCB_CONV_WINDOW, IFCB_CONV_IM2COL_PAIR
     name, B, Cin, H, W, Cout, kh, kw, stride, pad = case
     if algo == 'window' and stride != (1, 1):
         pytest.skip('window algorithm is stride-1 only')
@@ -153,9 +153,9 @@ def test_conv_bn_relu(cuda, case, algo):
     pb.keep.append(xin.t)
     P = (H + 2 * pad[0] - kh) // stride[0] + 1
     Q = (W + 2 * pad[1] - kw) // stride[1] + 1
-    out = pb.alloc(P, Q, Cout, pad=(1, 2) if algo == 'window' else (0, 0))     # padded destination
+    out = pb.alloc(P, Q, Cout, pad=(1, 2) if algo != 'im2col' else (0, 0))     # padded destination
     pb.conv(xin, [dict(weight=w, scale=scale, shift=shift, relu=True, out=out)], stride, pad, name=name,
-            algo=IFCB_CONV_WINDOW if algo == 'window' else IFCB_CONV_IM2COL)
+            algo={'window': IFCB_CONV_WINDOW, 'im2col': IFCB_CONV_IM2COL, 'pair': IFCB_CONV_IM2COL_PAIR}[algo])
     pb.run(B)
     torch.cuda.synchronize()
     got = to_nchw(out.interior()[:B])
@@ -231,7 +231,7 @@ def test_conv_fused_segments_slices_and_residual(cuda):
     pb.close()
 
 
-@pytest.mark.parametrize('algo', ['im2col', 'window'])
+@pytest.mark.parametrize('algo', ['im2col', 'window', 'pair'])
 def test_large_batch_many_tiles(cuda, algo):
     """More tiles than SMs: exercises the persistent loop, both TMEM buffers and phase wrap."""
     from ifcb_classifier_b200.graph import PlanBuilder
@@ -243,7 +243,7 @@ def test_large_batch_many_tiles(cuda, algo):
     xin = padded_view(x, cuda, (1, 1) if algo == 'window' else (0, 0)); pb.keep.append(xin.t)
     out = pb.alloc(H, W, Cout)
     pb.conv(xin, [dict(weight=w, scale=torch.ones(Cout), shift=torch.zeros(Cout), relu=False, out=out)],
-            (1, 1), (1, 1), algo=2 if algo == 'window' else 1)
+            (1, 1), (1, 1), algo={'window': 2, 'im2col': 1, 'pair': 3}[algo])
     pb.run(B)
     torch.cuda.synchronize()
     _check(to_nchw(out.t), _ref_conv(x, w, torch.ones(Cout), torch.zeros(Cout), (1, 1), (1, 1), False), 'many tiles')

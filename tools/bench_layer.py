@@ -66,10 +66,11 @@ CONFIGS = [
     ('window nomma', 2, {'IFCB_CONV_DEBUG': '2'}),
     ('window noepi', 2, {'IFCB_CONV_DEBUG': '4'}),
     ('window mma-only', 2, {'IFCB_CONV_DEBUG': '5'}),
-    ('window load-only', 2, {'IFCB_CONV_DEBUG': '6'}),
-    ('window m1', 2, {'IFCB_CONV_MSUB': '1'}),
     ('window m2', 2, {'IFCB_CONV_MSUB': '2'}),
-    ('window g1', 2, {'IFCB_CONV_BGROUP': '1'}),
+    ('pair', 3, {}),
+    ('pair nomma', 3, {'IFCB_CONV_DEBUG': '2'}),
+    ('pair noepi', 3, {'IFCB_CONV_DEBUG': '4'}),
+    ('pair mma-only', 3, {'IFCB_CONV_DEBUG': '5'}),
     ('auto', 0, {}),
 ]
 print('%-26s' % 'layer (us @ batch %d)' % B + ''.join('%17s' % c[0] for c in CONFIGS))

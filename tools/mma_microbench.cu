@@ -18,17 +18,20 @@ struct Cfg {
   int iters;      // MMAs per CTA
   int a_tiles;    // distinct A tiles rotated over (smem footprint)
   int shift;      // A start shifted by this many rows (window-style unaligned start)
+  int commit_every;  // issue a tcgen05.commit (to a scratch mbarrier) after every this many MMAs (0: never)
 };
 
 __global__ void __launch_bounds__(128, 1) mma_bench(Cfg c, long long* out_cycles) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t bar;
+  __shared__ uint64_t scratch_bar;
   __shared__ uint32_t tmem_slot;
   const int warp = threadIdx.x >> 5;
   for (int i = threadIdx.x; i < 160 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
   if (threadIdx.x == 0) {
     ptx::mbar_init(&bar, 1);
+    ptx::mbar_init(&scratch_bar, 1);
     ptx::fence_barrier_init();
   }
   if (warp == 0) {
@@ -61,10 +64,20 @@ __global__ void __launch_bounds__(128, 1) mma_bench(Cfg c, long long* out_cycles
       }
     }
     long long t0 = clock64();
-    for (int i = 0; i < c.iters; i += 8) {
+    if (c.commit_every == 0) {
+      for (int i = 0; i < c.iters; i += 8) {
 #pragma unroll
-      for (int u = 0; u < 8; ++u)
-        if (leader) ptx::umma_f16_lohi(dd[u], al[u], bl[u], hi, idesc, i > 0 ? 1u : 0u);
+        for (int u = 0; u < 8; ++u)
+          if (leader) ptx::umma_f16_lohi(dd[u], al[u], bl[u], hi, idesc, i > 0 ? 1u : 0u);
+      }
+    } else {
+      for (int i = 0; i < c.iters; i += 8) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          if (leader) ptx::umma_f16_lohi(dd[u], al[u], bl[u], hi, idesc, i > 0 ? 1u : 0u);
+          if (((u + 1) % c.commit_every) == 0 && leader) ptx::umma_commit(&scratch_bar);
+        }
+      }
     }
     long long t1 = clock64();
     if (leader) ptx::umma_commit(&bar);
@@ -92,7 +105,7 @@ int main() {
   printf("%5s %5s %4s %5s %7s %6s %6s | %10s %10s | %10s\n", "N", "accs", "run", "rowB", "a_tiles", "shift", "grid", "issue clk", "total clk",
          "floor N/2");
   const int grids[2] = {1, sms};
-  for (int gi = 1; gi < 2; ++gi) {
+  for (int gi = 2; gi < 2; ++gi) {
     for (int rb = 128; rb >= 64; rb -= 64) {
       for (int n : {32, 64, 96, 128, 192, 256}) {
         for (int accs : {1, 2, 4}) {
@@ -101,7 +114,7 @@ int main() {
             if (accs == 1 && run > 1) continue;
             for (int shift : {0, 3}) {
               if (shift && (accs != 2 || run != 2)) continue;
-              Cfg c{n, accs, run, rb, iters, 2, shift};
+              Cfg c{n, accs, run, rb, iters, 2, shift, 0};
               mma_bench<<<grids[gi], 128, smem>>>(c, d);
               cudaError_t e = cudaDeviceSynchronize();
               if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
@@ -121,7 +134,7 @@ int main() {
   // queue depth probe: how far can the issuing thread run ahead of execution?
   printf("\nqueue depth probe (N=256, 128B rows, 1 CTA): iters | issue clk total | exec clk total\n");
   for (int it : {8, 16, 32, 64, 128, 256}) {
-    Cfg c{256, 1, 1, 128, it, 2, 0};
+    Cfg c{256, 1, 1, 128, it, 2, 0, 0};
     mma_bench<<<1, 128, smem>>>(c, d);
     cudaDeviceSynchronize();
     long long h[2];
@@ -129,12 +142,23 @@ int main() {
     printf("%5d | %8lld | %8lld\n", it, h[0], h[1]);
   }
   for (int it : {8, 16, 32, 64, 128, 256}) {
-    Cfg c{32, 1, 1, 128, it, 2, 0};
+    Cfg c{32, 1, 1, 128, it, 2, 0, 0};
     mma_bench<<<1, 128, smem>>>(c, d);
     cudaDeviceSynchronize();
     long long h[2];
     cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
     printf("N=32 %5d | %8lld | %8lld\n", it, h[0], h[1]);
+  }
+  printf("\ncommit cost probe (1 CTA, 128B rows): N | commit every g MMAs | clk per MMA\n");
+  for (int n : {32, 64, 128, 240}) {
+    for (int g : {0, 8, 4, 2, 1}) {
+      Cfg c{n, 1, 1, 128, 4096, 2, 0, g};
+      mma_bench<<<1, 128, smem>>>(c, d);
+      cudaDeviceSynchronize();
+      long long h[2];
+      cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+      printf("%5d | %3d | %8.1f\n", n, g, h[1] / 4096.0);
+    }
   }
   return 0;
 }
