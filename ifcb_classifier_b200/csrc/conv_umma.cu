@@ -288,7 +288,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const int row_bytes = p.row_bytes;                                  // 128 or 64
   const int a_tile_bytes = kBlockM * row_bytes;                       // IM2COL stage A part
   const int b_tap_bytes = p.tile_n * row_bytes;
-  const int b_stage_bytes = WINDOW ? p.b_group * b_tap_bytes : a_tile_bytes + b_tap_bytes;
+  const int kb_bytes = a_tile_bytes + b_tap_bytes;                    // IM2COL: one k-block (A tile + B tile)
+  const int b_stage_bytes = WINDOW ? p.b_group * b_tap_bytes : p.b_group * kb_bytes;
   // IM2COL: `stages` x [A | B]          WINDOW: a_slots x A patch, then `stages` x (b_group B tiles)
   uint8_t* a_base = smem;
   uint8_t* b_base = WINDOW ? smem + (size_t)p.a_slots * p.a_slot_bytes : smem + a_tile_bytes;
@@ -396,26 +397,30 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const int op = rem / p.row_w, oq = rem - op * p.row_w;
         const int w0 = oq * p.stride_w - p.pad_w;
         const int h0 = op * p.stride_h - p.pad_h;
-        int kcol = 0;
-        for (int r = 0; r < p.kh; ++r) {
-          for (int s = 0; s < p.kw; ++s) {
-            for (int cb = 0; cb < p.cblocks; ++cb, kcol += row_elems) {
-              ptx::mbar_wait(empty_bar + stage, phase ^ 1);
-              if (ptx::elect_one()) {
-                uint8_t* a_dst = smem + (size_t)stage * b_stage_bytes;
-                if (skip_loads) {
-                  ptx::mbar_arrive(full_bar + stage);
-                } else {
-                  ptx::mbar_arrive_expect_tx(full_bar + stage, (uint32_t)b_stage_bytes);
-                  ptx::tma_load_im2col_4d(a_dst, &tmap_a, full_bar + stage, cb * row_elems, w0, h0, img,
-                                          (uint16_t)s, (uint16_t)r);
-                  ptx::tma_load_2d(a_dst + a_tile_bytes, &tmap_b, full_bar + stage, kcol, n0);
-                }
-              }
-              __syncwarp();
-              if (++stage == p.stages) { stage = 0; phase ^= 1; }
-            }
+        // k-blocks (filter tap x channel block) travel in groups of p.b_group per pipeline stage:
+        // one barrier round trip per group
+        const int kblocks = taps * p.cblocks;
+        int kcol = 0, r = 0, s = 0, cb = 0;
+        for (int kb = 0; kb < kblocks; kb += p.b_group) {
+          const int nk = min(p.b_group, kblocks - kb);
+          ptx::mbar_wait(empty_bar + stage, phase ^ 1);
+          uint8_t* dst = smem + (size_t)stage * b_stage_bytes;
+          const bool el = ptx::elect_one();
+          if (el) {
+            if (skip_loads) ptx::mbar_arrive(full_bar + stage);
+            else ptx::mbar_arrive_expect_tx(full_bar + stage, (uint32_t)(nk * kb_bytes));
           }
+          for (int i = 0; i < nk; ++i) {
+            if (el && !skip_loads) {
+              ptx::tma_load_im2col_4d(dst + (size_t)i * kb_bytes, &tmap_a, full_bar + stage, cb * row_elems, w0, h0, img,
+                                      (uint16_t)s, (uint16_t)r);
+              ptx::tma_load_2d(dst + (size_t)i * kb_bytes + a_tile_bytes, &tmap_b, full_bar + stage, kcol, n0);
+            }
+            kcol += row_elems;
+            if (++cb == p.cblocks) { cb = 0; if (++s == p.kw) { s = 0; ++r; } }
+          }
+          __syncwarp();
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -483,30 +488,34 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
       } else {
         const int kblocks = taps * p.cblocks;
+        const uint32_t kb16 = (uint32_t)kb_bytes >> 4;
         int cb = 0;
-        for (int kb = 0; kb < kblocks; ++kb) {
-          // `ready` = a non-blocking peek taken one k-block earlier: its latency hides behind
-          // the previous block's MMA issue
+        for (int kb = 0; kb < kblocks; kb += p.b_group) {
+          const int nk = min(p.b_group, kblocks - kb);
+          // `ready` = a non-blocking peek taken one stage earlier: its latency hides behind
+          // the previous stage's MMA issue
           if (!ready) ptx::mbar_wait(full_bar + stage, phase);
           ptx::tc_fence_after();
-          const uint32_t a_lo = ptx::umma_desc_lo(ptx::smem_u32(smem + (size_t)stage * b_stage_bytes));
-          const uint32_t b_lo = a_lo + (uint32_t)(a_tile_bytes >> 4);
-          const int ksteps = (cb == p.cblocks - 1) ? p.last_ksteps : full_ksteps;
+          uint32_t a_lo = ptx::umma_desc_lo(ptx::smem_u32(smem + (size_t)stage * b_stage_bytes));
           const int cur = stage;
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
           ready = ptx::mbar_test_wait(full_bar + stage, phase) != 0;
-          const uint32_t first = kb > 0 ? 1u : 0u;
-          if (!skip_mma) {
-            switch (ksteps) {
-              case 1: issue_tap<1, 1>(leader, a_lo, b_lo, 0u, d_tmem, 0u, desc_hi, idesc, first); break;
-              case 2: issue_tap<2, 1>(leader, a_lo, b_lo, 0u, d_tmem, 0u, desc_hi, idesc, first); break;
-              case 3: issue_tap<3, 1>(leader, a_lo, b_lo, 0u, d_tmem, 0u, desc_hi, idesc, first); break;
-              default: issue_tap<4, 1>(leader, a_lo, b_lo, 0u, d_tmem, 0u, desc_hi, idesc, first); break;
+          for (int i = 0; i < nk; ++i, a_lo += kb16) {
+            const uint32_t b_lo = a_lo + (uint32_t)(a_tile_bytes >> 4);
+            const int ksteps = (cb == p.cblocks - 1) ? p.last_ksteps : full_ksteps;
+            const uint32_t first = (kb + i) > 0 ? 1u : 0u;
+            if (!skip_mma) {
+              switch (ksteps) {
+                case 1: issue_tap<1, 1>(leader, a_lo, b_lo, 0u, d_tmem, 0u, desc_hi, idesc, first); break;
+                case 2: issue_tap<2, 1>(leader, a_lo, b_lo, 0u, d_tmem, 0u, desc_hi, idesc, first); break;
+                case 3: issue_tap<3, 1>(leader, a_lo, b_lo, 0u, d_tmem, 0u, desc_hi, idesc, first); break;
+                default: issue_tap<4, 1>(leader, a_lo, b_lo, 0u, d_tmem, 0u, desc_hi, idesc, first); break;
+              }
             }
+            if (++cb == p.cblocks) cb = 0;
           }
           if (leader) ptx::umma_commit(empty_bar + cur);     // frees the smem slot when these MMAs retire
           __syncwarp();
-          if (++cb == p.cblocks) cb = 0;
         }
       }
       if (leader) ptx::umma_commit(tmem_full + acc);           // accumulators ready for the epilogue
@@ -559,7 +568,8 @@ conv_umma_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
   const int row_bytes = p.row_bytes;
   const int a_tile_bytes = kBlockM * row_bytes;
   const int b_half_bytes = (p.tile_n >> 1) * row_bytes;
-  const int stage_bytes = a_tile_bytes + b_half_bytes;
+  const int kb_bytes = a_tile_bytes + b_half_bytes;                   // one k-block of this CTA
+  const int stage_bytes = p.b_group * kb_bytes;                       // p.b_group k-blocks per pipeline stage
   uint8_t* bar_base = smem + (size_t)p.stages * stage_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_base);
   uint64_t* empty_bar = full_bar + kMaxStages;
@@ -621,26 +631,29 @@ conv_umma_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       const int op = rem / p.row_w, oq = rem - op * p.row_w;
       const int w0 = oq * p.stride_w - p.pad_w;
       const int h0 = op * p.stride_h - p.pad_h;
-      int kcol = 0;
-      for (int r = 0; r < p.kh; ++r) {
-        for (int s = 0; s < p.kw; ++s) {
-          for (int cb = 0; cb < p.cblocks; ++cb, kcol += row_elems) {
-            ptx::mbar_wait(empty_bar + stage, phase ^ 1);
-            if (ptx::elect_one()) {
-              uint8_t* a_dst = smem + (size_t)stage * stage_bytes;
-              const uint32_t lead_full = ptx::mapa(ptx::smem_u32(full_bar + stage), 0u);
-              if (skip_loads) {
-                if (rank == 0) ptx::mbar_arrive(full_bar + stage);
-              } else {
-                if (rank == 0) ptx::mbar_arrive_expect_tx(full_bar + stage, (uint32_t)(2 * stage_bytes));
-                ptx::tma_load_im2col_4d_pair(a_dst, &tmap_a, lead_full, cb * row_elems, w0, h0, img, (uint16_t)s, (uint16_t)r);
-                ptx::tma_load_2d_pair(a_dst + a_tile_bytes, &tmap_b, lead_full, kcol, n0);
-              }
-            }
-            __syncwarp();
-            if (++stage == p.stages) { stage = 0; phase ^= 1; }
-          }
+      const int kblocks = taps * p.cblocks;
+      int kcol = 0, r = 0, s = 0, cb = 0;
+      for (int kb = 0; kb < kblocks; kb += p.b_group) {
+        const int nk = min(p.b_group, kblocks - kb);
+        ptx::mbar_wait(empty_bar + stage, phase ^ 1);
+        uint8_t* dst = smem + (size_t)stage * stage_bytes;
+        const uint32_t lead_full = ptx::mapa(ptx::smem_u32(full_bar + stage), 0u);
+        const bool el = ptx::elect_one();
+        if (el && rank == 0) {
+          if (skip_loads) ptx::mbar_arrive(full_bar + stage);
+          else ptx::mbar_arrive_expect_tx(full_bar + stage, (uint32_t)(2 * nk * kb_bytes));
         }
+        for (int i = 0; i < nk; ++i) {
+          if (el && !skip_loads) {
+            ptx::tma_load_im2col_4d_pair(dst + (size_t)i * kb_bytes, &tmap_a, lead_full, cb * row_elems, w0, h0, img, (uint16_t)s,
+                                         (uint16_t)r);
+            ptx::tma_load_2d_pair(dst + (size_t)i * kb_bytes + a_tile_bytes, &tmap_b, lead_full, kcol, n0);
+          }
+          kcol += row_elems;
+          if (++cb == p.cblocks) { cb = 0; if (++s == p.kw) { s = 0; ++r; } }
+        }
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -655,6 +668,7 @@ conv_umma_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       uint32_t phase = 0;
       int local = 0;
       const int kblocks = taps * p.cblocks;
+      const uint32_t kb16 = (uint32_t)kb_bytes >> 4;
       for (int tile = pair; tile < total_tiles; tile += npairs, ++local) {
         const int acc = local & 1;
         const uint32_t acc_phase = (local >> 1) & 1;
@@ -662,27 +676,30 @@ conv_umma_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kAccBufCols);
         int cb = 0;
-        for (int kb = 0; kb < kblocks; ++kb) {
+        for (int kb = 0; kb < kblocks; kb += p.b_group) {
+          const int nk = min(p.b_group, kblocks - kb);
           if (!ready) ptx::mbar_wait(full_bar + stage, phase);
           ptx::tc_fence_after();
-          const uint32_t a_lo = ptx::umma_desc_lo(ptx::smem_u32(smem + (size_t)stage * stage_bytes));
-          const uint32_t b_lo = a_lo + (uint32_t)(a_tile_bytes >> 4);
-          const int ksteps = (cb == p.cblocks - 1) ? p.last_ksteps : full_ksteps;
+          uint32_t a_lo = ptx::umma_desc_lo(ptx::smem_u32(smem + (size_t)stage * stage_bytes));
           const int cur = stage;
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
           ready = ptx::mbar_test_wait(full_bar + stage, phase) != 0;
-          const uint32_t first = kb > 0 ? 1u : 0u;
-          if (!skip_mma) {
-            switch (ksteps) {
-              case 1: issue_tap<1, 1, true>(leader, a_lo, b_lo, 0u, d_tmem, 0u, desc_hi, idesc, first); break;
-              case 2: issue_tap<2, 1, true>(leader, a_lo, b_lo, 0u, d_tmem, 0u, desc_hi, idesc, first); break;
-              case 3: issue_tap<3, 1, true>(leader, a_lo, b_lo, 0u, d_tmem, 0u, desc_hi, idesc, first); break;
-              default: issue_tap<4, 1, true>(leader, a_lo, b_lo, 0u, d_tmem, 0u, desc_hi, idesc, first); break;
+          for (int i = 0; i < nk; ++i, a_lo += kb16) {
+            const uint32_t b_lo = a_lo + (uint32_t)(a_tile_bytes >> 4);
+            const int ksteps = (cb == p.cblocks - 1) ? p.last_ksteps : full_ksteps;
+            const uint32_t first = (kb + i) > 0 ? 1u : 0u;
+            if (!skip_mma) {
+              switch (ksteps) {
+                case 1: issue_tap<1, 1, true>(leader, a_lo, b_lo, 0u, d_tmem, 0u, desc_hi, idesc, first); break;
+                case 2: issue_tap<2, 1, true>(leader, a_lo, b_lo, 0u, d_tmem, 0u, desc_hi, idesc, first); break;
+                case 3: issue_tap<3, 1, true>(leader, a_lo, b_lo, 0u, d_tmem, 0u, desc_hi, idesc, first); break;
+                default: issue_tap<4, 1, true>(leader, a_lo, b_lo, 0u, d_tmem, 0u, desc_hi, idesc, first); break;
+              }
             }
+            if (++cb == p.cblocks) cb = 0;
           }
           if (leader) ptx::umma_commit_pair(empty_bar + cur);
           __syncwarp();
-          if (++cb == p.cblocks) cb = 0;
         }
         if (leader) ptx::umma_commit_pair(tmem_full + acc);
         __syncwarp();
@@ -735,8 +752,14 @@ bool conv_plan_smem(ConvKernelParams& kp, bool window, bool pair, int halo_rows)
     kp.a_slots = 0;
     kp.a_slot_bytes = 0;
     kp.box_rows = kp.n_boxes = 0;
-    kp.b_group = 1;
-    int s = (kSmemBudget - fixed) / (a_tile + (pair ? b_tap / 2 : b_tap));
+    // k-blocks per pipeline stage: two only when at least five such stages fit -- measured: prefetch
+    // depth matters more than the barrier round trips saved (3 stages x 2 k-blocks lost 5-10 %)
+    const int kb = a_tile + (pair ? b_tap / 2 : b_tap);
+    const int kblocks = taps * kp.cblocks;
+    int g = (kblocks >= 2 && (kSmemBudget - fixed) / (2 * kb) >= 5) ? 2 : 1;
+    if (kp.b_group_cap > 0 && g > kp.b_group_cap) g = kp.b_group_cap;
+    kp.b_group = g;
+    int s = (kSmemBudget - fixed) / (g * kb);
     if (s > 10) s = 10;
     kp.stages = s;
     return s >= 2;
@@ -797,7 +820,7 @@ bool conv_plan_smem(ConvKernelParams& kp, bool window, bool pair, int halo_rows)
 int conv_smem_bytes(const ConvKernelParams& kp, bool window, bool pair) {
   const int b_tap = kp.tile_n * kp.row_bytes;
   const int ops = window ? kp.a_slots * kp.a_slot_bytes + kp.stages * kp.b_group * b_tap
-                         : kp.stages * (kBlockM * kp.row_bytes + (pair ? b_tap / 2 : b_tap));
+                         : kp.stages * kp.b_group * (kBlockM * kp.row_bytes + (pair ? b_tap / 2 : b_tap));
   return ops + epilogue_smem(kp.cout_pad) + 1024;
 }
 

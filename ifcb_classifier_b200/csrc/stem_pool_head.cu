@@ -178,43 +178,60 @@ struct StemConst {
 
 template <int COUT>
 __global__ void __launch_bounds__(128) stem_gray3x3_kernel(const ifcb_stem_desc d, const __grid_constant__ StemConst<COUT> k,
-                                                           int P, int Q, int total, unsigned long long magic_pq,
-                                                           unsigned long long magic_q) {
-  const int pix = blockIdx.x * 128 + threadIdx.x;
-  if (pix >= total) return;
-  const int PQ = P * Q;
-  const int img = (int)fast_div((uint32_t)pix, magic_pq);
-  const int rem = pix - img * PQ;
-  const int op = (int)fast_div((uint32_t)rem, magic_q), oq = rem - op * Q;
+                                                           int P, int Q, int q2n, int total, unsigned long long magic_pq2,
+                                                           unsigned long long magic_q2) {
+  // one thread = TWO horizontally adjacent output pixels: every constant-bank weight feeds two FFMAs
+  const int idx = blockIdx.x * 128 + threadIdx.x;
+  if (idx >= total) return;
+  const int img = (int)fast_div((uint32_t)idx, magic_pq2);
+  const int rem = idx - img * (P * q2n);
+  const int op = (int)fast_div((uint32_t)rem, magic_q2);
+  const int oq = (rem - op * q2n) * 2;
+  const bool two = oq + 1 < Q;
+  const int ncol = 3 + (two ? d.stride : 0);           // input columns this thread touches (<= 5 for stride 2)
   const uint8_t* in = reinterpret_cast<const uint8_t*>(d.d_in) + (long long)img * d.H * d.W + (op * d.stride) * d.W + oq * d.stride;
-  float g[9];
+  float g[3][5];
 #pragma unroll
   for (int r = 0; r < 3; ++r)
 #pragma unroll
-    for (int s2 = 0; s2 < 3; ++s2) g[r * 3 + s2] = (float)__ldg(in + r * d.W + s2);
-  float acc[COUT];
+    for (int c = 0; c < 5; ++c) g[r][c] = c < ncol ? (float)__ldg(in + r * d.W + c) : 0.f;
+  const int st = d.stride;                             // 1 or 2 (checked by the launcher)
+  float acc0[COUT], acc1[COUT];
 #pragma unroll
-  for (int c = 0; c < COUT; ++c) acc[c] = 0.f;
+  for (int c = 0; c < COUT; ++c) { acc0[c] = 0.f; acc1[c] = 0.f; }
 #pragma unroll
-  for (int t = 0; t < 9; ++t)
+  for (int r = 0; r < 3; ++r)
 #pragma unroll
-    for (int c = 0; c < COUT; ++c) acc[c] = fmaf(g[t], k.w[t * COUT + c], acc[c]);
+    for (int s2 = 0; s2 < 3; ++s2) {
+      const float ga = g[r][s2];
+      const float gb = st == 2 ? g[r][s2 + 2] : g[r][s2 + 1];
+#pragma unroll
+      for (int c = 0; c < COUT; ++c) {
+        const float w = k.w[(r * 3 + s2) * COUT + c];
+        acc0[c] = fmaf(ga, w, acc0[c]);
+        acc1[c] = fmaf(gb, w, acc1[c]);
+      }
+    }
   const long long orow = ((long long)img * (P + 2 * d.out_pad_h) + op + d.out_pad_h) * (Q + 2 * d.out_pad_w) + oq + d.out_pad_w;
   __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(d.d_out) + orow * d.out_ld;
 #pragma unroll
-  for (int c = 0; c < COUT; c += 8) {
-    float y[8];
+  for (int px = 0; px < 2; ++px) {
+    if (px == 1 && !two) break;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      y[j] = fmaf(acc[c + j], k.scale[c + j], k.shift[c + j]);
-      if (d.relu) y[j] = fmaxf(y[j], 0.f);
+    for (int c = 0; c < COUT; c += 8) {
+      float y[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        y[j] = fmaf(px == 0 ? acc0[c + j] : acc1[c + j], k.scale[c + j], k.shift[c + j]);
+        if (d.relu) y[j] = fmaxf(y[j], 0.f);
+      }
+      uint4 o;
+      o.x = pack_act2(y[0], y[1], d.dtype);
+      o.y = pack_act2(y[2], y[3], d.dtype);
+      o.z = pack_act2(y[4], y[5], d.dtype);
+      o.w = pack_act2(y[6], y[7], d.dtype);
+      *reinterpret_cast<uint4*>(out + (long long)px * d.out_ld + c) = o;
     }
-    uint4 o;
-    o.x = pack_act2(y[0], y[1], d.dtype);
-    o.y = pack_act2(y[2], y[3], d.dtype);
-    o.z = pack_act2(y[4], y[5], d.dtype);
-    o.w = pack_act2(y[6], y[7], d.dtype);
-    *reinterpret_cast<uint4*>(out + c) = o;
   }
 }
 
@@ -435,6 +452,78 @@ __global__ void __launch_bounds__(256) head_kernel(const ifcb_head_desc d) {
   }
 }
 
+// ------------------------------------------------------------------------------
+// 3x3 / stride 1 / pad 1 average pool (+ BN affine + ReLU): the Inception branch_pool path.
+// One thread = FOUR horizontally adjacent output pixels x 8 channels: the 6 x 3 input window is
+// loaded and converted once, summed by column, and each output adds three column sums --
+// half the loads, conversions and adds of one-output-per-thread.  fp32 accumulation;
+// count_include_pad=True (torch default, inception.py:271): always divide by 9.
+// ------------------------------------------------------------------------------
+template <bool FP16>
+__global__ void __launch_bounds__(256) avgpool3_s1_kernel(const ifcb_pool_desc d, int total, int q4n, unsigned long long magic_c8,
+                                                          unsigned long long magic_q4, unsigned long long magic_h) {
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  if (idx >= total) return;
+  const int c8n = d.C >> 3;
+  const int t0 = (int)fast_div((uint32_t)idx, magic_c8);
+  const int c8 = idx - t0 * c8n;
+  const int t1 = (int)fast_div((uint32_t)t0, magic_q4);
+  const int q0 = (t0 - t1 * q4n) * 4;                 // first output column of this thread
+  const int img = (int)fast_div((uint32_t)t1, magic_h);
+  const int op = t1 - img * d.H;
+  const int Wpi = d.W + 2 * d.in_pad_w;
+  const __nv_bfloat16* in = reinterpret_cast<const __nv_bfloat16*>(d.d_in) +
+      ((long long)img * (d.H + 2 * d.in_pad_h) * Wpi + (long long)(d.in_pad_h + op - 1) * Wpi + d.in_pad_w + q0 - 1) * d.in_ld + c8 * 8;
+  float col[6][8];
+#pragma unroll
+  for (int cidx = 0; cidx < 6; ++cidx) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) col[cidx][j] = 0.f;
+    const int ww = q0 - 1 + cidx;
+    const bool wok = (unsigned)ww < (unsigned)d.W;
+    uint4 v[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const bool ok = wok && (unsigned)(op - 1 + r) < (unsigned)d.H;
+      v[r] = ok ? __ldg(reinterpret_cast<const uint4*>(in + ((long long)r * Wpi + cidx) * d.in_ld)) : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const uint32_t u[4] = {v[r].x, v[r].y, v[r].z, v[r].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_act2(u[j], FP16 ? 1 : 0);
+        col[cidx][2 * j] += f.x;
+        col[cidx][2 * j + 1] += f.y;
+      }
+    }
+  }
+  const float4 s0 = __ldg(reinterpret_cast<const float4*>(d.d_scale + c8 * 8)), s1 = __ldg(reinterpret_cast<const float4*>(d.d_scale + c8 * 8 + 4));
+  const float4 h0 = __ldg(reinterpret_cast<const float4*>(d.d_shift + c8 * 8)), h1 = __ldg(reinterpret_cast<const float4*>(d.d_shift + c8 * 8 + 4));
+  const float inv = 1.0f / 9.0f;
+  const float scv[8] = {s0.x * inv, s0.y * inv, s0.z * inv, s0.w * inv, s1.x * inv, s1.y * inv, s1.z * inv, s1.w * inv};
+  const float shv[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(d.d_out) +
+      (((long long)img * (d.H + 2 * d.out_pad_h) + op + d.out_pad_h) * (d.W + 2 * d.out_pad_w) + d.out_pad_w + q0) * d.out_ld + c8 * 8;
+#pragma unroll
+  for (int o = 0; o < 4; ++o) {
+    if (q0 + o < d.W) {
+      float y[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        y[j] = fmaf(col[o][j] + col[o + 1][j] + col[o + 2][j], scv[j], shv[j]);
+        if (d.relu) y[j] = fmaxf(y[j], 0.f);
+      }
+      uint4 w;
+      w.x = pack_act2(y[0], y[1], FP16 ? 1 : 0);
+      w.y = pack_act2(y[2], y[3], FP16 ? 1 : 0);
+      w.z = pack_act2(y[4], y[5], FP16 ? 1 : 0);
+      w.w = pack_act2(y[6], y[7], FP16 ? 1 : 0);
+      *reinterpret_cast<uint4*>(out + (long long)o * d.out_ld) = w;
+    }
+  }
+}
+
 }  // namespace
 
 int launch_stem(const StemLayer& L, int batch, cudaStream_t stream) {
@@ -447,18 +536,14 @@ int launch_stem(const StemLayer& L, int batch, cudaStream_t stream) {
     set_error("stem: Cout=%d unsupported (32 or 64)", d.Cout);
     return -1;
   }
-  if (d.in_kind == IFCB_STEM_IN_U8_GRAY && d.kh == 3 && d.kw == 3 && d.pad == 0 && total < (1ll << 31) && !L.h_const.empty()) {
-    const unsigned long long mpq = div_magic(L.P * L.Q), mq = div_magic(L.Q);
-    const unsigned blocks = (unsigned)((total + 127) / 128);
-    if (d.Cout == 32) {
-      StemConst<32> k;
-      memcpy(&k, L.h_const.data(), sizeof(k));
-      stem_gray3x3_kernel<32><<<blocks, 128, 0, stream>>>(d, k, L.P, L.Q, (int)total, mpq, mq);
-    } else {
-      StemConst<64> k;
-      memcpy(&k, L.h_const.data(), sizeof(k));
-      stem_gray3x3_kernel<64><<<blocks, 128, 0, stream>>>(d, k, L.P, L.Q, (int)total, mpq, mq);
-    }
+  if (d.in_kind == IFCB_STEM_IN_U8_GRAY && d.kh == 3 && d.kw == 3 && d.pad == 0 && (d.stride == 1 || d.stride == 2) && d.Cout == 32 &&
+      total < (1ll << 31) && !L.h_const.empty()) {
+    const int q2n = (L.Q + 1) / 2;
+    const long long t2 = (long long)batch * L.P * q2n;
+    const unsigned blocks = (unsigned)((t2 + 127) / 128);
+    StemConst<32> k;
+    memcpy(&k, L.h_const.data(), sizeof(k));
+    stem_gray3x3_kernel<32><<<blocks, 128, 0, stream>>>(d, k, L.P, L.Q, q2n, (int)t2, div_magic(L.P * q2n), div_magic(q2n));
   } else if (d.in_kind == IFCB_STEM_IN_U8_GRAY) {
     const bool haspad = d.pad > 0;
     const int smem = taps * d.Cout * (haspad ? 2 : 1) * (int)sizeof(float);
@@ -497,7 +582,13 @@ int launch_pool(const PoolLayer& L, int batch, cudaStream_t stream) {
   if (total == 0) return 0;
   const unsigned grid = (unsigned)((total + 255) / 256);
   const bool avg = d.kind != IFCB_POOL_MAX;
-  if (d.k == 3 && total < (1ll << 31)) {
+  if (avg && d.k == 3 && d.stride == 1 && d.pad == 1 && total < (1ll << 31)) {
+    const int q4n = (d.W + 3) / 4;
+    const long long t4 = (long long)batch * d.H * q4n * (d.C >> 3);
+    const unsigned g4 = (unsigned)((t4 + 255) / 256);
+    if (d.dtype) avgpool3_s1_kernel<true><<<g4, 256, 0, stream>>>(d, (int)t4, q4n, div_magic(d.C >> 3), div_magic(q4n), div_magic(d.H));
+    else avgpool3_s1_kernel<false><<<g4, 256, 0, stream>>>(d, (int)t4, q4n, div_magic(d.C >> 3), div_magic(q4n), div_magic(d.H));
+  } else if (d.k == 3 && total < (1ll << 31)) {
     const unsigned long long mc = div_magic(d.C >> 3), mpq = div_magic(L.P * L.Q), mq = div_magic(L.Q);
     const int t = (int)total;
     if (avg) {
