@@ -35,6 +35,15 @@ class ConvDesc(C.Structure):
                 ('tile_n', C.c_int32), ('algo', C.c_int32), ('dtype', C.c_int32)]
 
 
+class WgradDesc(C.Structure):
+    _fields_ = [('d_in', C.c_void_p), ('in_ld', C.c_int32), ('Cin', C.c_int32),
+                ('batch', C.c_int32), ('H', C.c_int32), ('W', C.c_int32),
+                ('kh', C.c_int32), ('kw', C.c_int32), ('stride_h', C.c_int32), ('stride_w', C.c_int32),
+                ('pad_h', C.c_int32), ('pad_w', C.c_int32),
+                ('d_dout', C.c_void_p), ('dout_ld', C.c_int32), ('Cout', C.c_int32),
+                ('d_dweight', C.c_void_p), ('dtype', C.c_int32)]
+
+
 class StemDesc(C.Structure):
     _fields_ = [('d_in', C.c_void_p), ('in_kind', C.c_int32),
                 ('batch_cap', C.c_int32), ('H', C.c_int32), ('W', C.c_int32),
@@ -84,6 +93,7 @@ _SIGNATURES = {
                                      C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     'ifcb_conv_auto_config': (C.c_int, [C.c_int] * 10 + [C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     'ifcb_conv_auto_tile_n': (C.c_int, [C.c_int, C.c_int]),
+    'ifcb_conv_wgrad': (C.c_int, [C.POINTER(WgradDesc), C.c_void_p]),
     'ifcb_plan_add_stem': (C.c_int, [C.c_void_p, C.POINTER(StemDesc)]),
     'ifcb_plan_add_pool': (C.c_int, [C.c_void_p, C.POINTER(PoolDesc)]),
     'ifcb_plan_add_head': (C.c_int, [C.c_void_p, C.POINTER(HeadDesc)]),

@@ -1,0 +1,300 @@
+// Weight gradient of Conv2d as a tcgen05 GEMM with the PIXEL axis as K (sm_100a only).
+//
+// Replaces the conv weight-gradient of loss.backward() inside NeustonModel.training_step
+// (reference neuston_models.py:70-86; torch autograd / cuDNN wgrad upstream).
+//
+//   dW[co, (r,s), ci] = sum over output pixels m = (n,p,q) of  dz[m, co] * x[n, p*sh + r - ph, q*sw + s - pw, ci]
+//
+// Both operands live in HBM pixel-major (NHWC), i.e. the reduction index is the slow one: the
+// tensor core takes them as MN-MAJOR operands (instruction-descriptor major bits), so the tiles
+// TMA delivers are used as they land -- no transposes:
+//   A = dz tile  [128 pixels x 128 co]  two 64-channel boxes of a plain 2-D map (rows = pixels)
+//   B = x  tile  [128 pixels x  64 ci]  the SAME im2col map the forward kernel loads as its A
+// One MMA = M 128 (co) x N 64 (ci) x K 16 (pixels); a 128-pixel tile is 8 MMAs per
+// (filter tap, channel block) accumulator.  TMEM holds 8 accumulators of 64 fp32 columns (all
+// 512 columns); a work item = (co tile, group of <= 8 (tap, channel block) pairs, pixel range):
+// the CTA sweeps its pixel range once, loading each dz tile once and one x tile per accumulator,
+// then adds its partial sums into the fp32 gradient with red.global (split-K over CTAs).
+// Warp roles as in conv_umma.cu: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 drain TMEM.
+#include "layers.cuh"
+#include "ptx.cuh"
+
+namespace ifcb {
+namespace {
+
+constexpr int kPix = 128;                 // pixels (K) per tile
+constexpr int kATile = 2 * kPix * 128;    // dz tile: two 64-channel blocks of 128 rows x 128 B
+constexpr int kBTile = kPix * 128;        // x tile: 128 rows x 128 B
+constexpr int kMaxAcc = 8;                // accumulators (64 TMEM columns each)
+constexpr int kWThreads = 64 + 128;
+
+struct WgradParams {
+  int rows;                 // batch * P * Q
+  int rows_per_img, row_w;  // P*Q, Q
+  int kh, kw, stride_h, stride_w, pad_h, pad_w;
+  int Cin, Cout, cblocks, taps;
+  int n_pairs;              // taps * cblocks
+  int n_groups;             // ceil(n_pairs / 8)
+  int co_tiles;             // ceil(Cout / 128)
+  int splits;               // pixel-range splits
+  int tiles_per_split;      // 128-pixel tiles per split
+  int a_slots, b_stages;
+  int fp16;
+  float* dW;                // [Cout][taps][Cin] fp32, accumulated into
+};
+
+__global__ void __launch_bounds__(kWThreads, 1)
+conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_constant__ CUtensorMap tmap_x, const WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* a_base = smem;
+  uint8_t* b_base = smem + (size_t)p.a_slots * kATile;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b_base + (size_t)p.b_stages * kBTile);
+  uint64_t* a_full = bars;            // [a_slots]
+  uint64_t* a_empty = bars + 4;
+  uint64_t* b_full = bars + 8;        // [b_stages]
+  uint64_t* b_empty = bars + 24;
+  uint64_t* acc_full = bars + 40;     // accumulators complete -> epilogue
+  uint64_t* acc_empty = bars + 41;    // epilogue drained -> next item may overwrite
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 42);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tmap_dz);
+    ptx::prefetch_tensormap(&tmap_x);
+    for (int s = 0; s < p.a_slots; ++s) { ptx::mbar_init(a_full + s, 1); ptx::mbar_init(a_empty + s, 1); }
+    for (int s = 0; s < p.b_stages; ++s) { ptx::mbar_init(b_full + s, 1); ptx::mbar_init(b_empty + s, 1); }
+    ptx::mbar_init(acc_full, 1);
+    ptx::mbar_init(acc_empty, 4);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int items = p.co_tiles * p.n_groups * p.splits;
+  const int total_ptiles = (p.rows + kPix - 1) / kPix;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    int aslot = 0, bstage = 0;
+    uint32_t aphase = 0, bphase = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+      const int split = item % p.splits;
+      const int rest = item / p.splits;
+      const int group = rest % p.n_groups;
+      const int co_tile = rest / p.n_groups;
+      const int pair0 = group * kMaxAcc;
+      const int npair = min(kMaxAcc, p.n_pairs - pair0);
+      const int t_begin = split * p.tiles_per_split;
+      const int t_end = min(total_ptiles, t_begin + p.tiles_per_split);
+      for (int pt = t_begin; pt < t_end; ++pt) {
+        const int m0 = pt * kPix;
+        const int img = m0 / p.rows_per_img;
+        const int rem = m0 - img * p.rows_per_img;
+        const int op = rem / p.row_w, oq = rem - op * p.row_w;
+        const int w0 = oq * p.stride_w - p.pad_w, h0 = op * p.stride_h - p.pad_h;
+        ptx::mbar_wait(a_empty + aslot, aphase ^ 1);
+        if (ptx::elect_one()) {
+          uint8_t* dst = a_base + (size_t)aslot * kATile;
+          ptx::mbar_arrive_expect_tx(a_full + aslot, (uint32_t)kATile);
+          ptx::tma_load_2d(dst, &tmap_dz, a_full + aslot, co_tile * 128, m0);
+          ptx::tma_load_2d(dst + kPix * 128, &tmap_dz, a_full + aslot, co_tile * 128 + 64, m0);
+        }
+        __syncwarp();
+        if (++aslot == p.a_slots) { aslot = 0; aphase ^= 1; }
+        for (int g = 0; g < npair; ++g) {
+          const int pr = pair0 + g;
+          const int tap = pr / p.cblocks, cb = pr - tap * p.cblocks;
+          const int r = tap / p.kw, s = tap - r * p.kw;
+          ptx::mbar_wait(b_empty + bstage, bphase ^ 1);
+          if (ptx::elect_one()) {
+            ptx::mbar_arrive_expect_tx(b_full + bstage, (uint32_t)kBTile);
+            ptx::tma_load_im2col_4d(b_base + (size_t)bstage * kBTile, &tmap_x, b_full + bstage, cb * 64, w0, h0, img,
+                                    (uint16_t)s, (uint16_t)r);
+          }
+          __syncwarp();
+          if (++bstage == p.b_stages) { bstage = 0; bphase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    // both operands MN-major (bits 15/16), fp32 accumulate, M = 128, N = 64
+    const uint32_t fmt = p.fp16 ? 0u : 1u;
+    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 15) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+    // MN-major SWIZZLE_128B: 128-byte rows indexed by k (64 consecutive M/N elements each), groups of
+    // 8 k-rows SBO = 1024 B apart, next 64-element M/N block LBO bytes away (A: 16 KB; B: single block)
+    const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+    const uint32_t a_lbo = ((uint32_t)(kPix * 128) >> 4) << 16;
+    const uint32_t b_lbo = 1u << 16;
+    const bool leader = ptx::elect_one();
+    int aslot = 0, bstage = 0;
+    uint32_t aphase = 0, bphase = 0;
+    int local = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x, ++local) {
+      const int split = item % p.splits;
+      const int rest = item / p.splits;
+      const int group = rest % p.n_groups;
+      const int npair = min(kMaxAcc, p.n_pairs - group * kMaxAcc);
+      const int t_begin = split * p.tiles_per_split;
+      const int t_end = min(total_ptiles, t_begin + p.tiles_per_split);
+      ptx::mbar_wait(acc_empty, (uint32_t)((local & 1) ^ 1));
+      ptx::tc_fence_after();
+      for (int pt = t_begin; pt < t_end; ++pt) {
+        ptx::mbar_wait(a_full + aslot, aphase);
+        const uint32_t a_lo0 = ((ptx::smem_u32(a_base + (size_t)aslot * kATile) & 0x3FFFFu) >> 4) | a_lbo;
+        for (int g = 0; g < npair; ++g) {
+          ptx::mbar_wait(b_full + bstage, bphase);
+          ptx::tc_fence_after();
+          const uint32_t b_lo0 = ((ptx::smem_u32(b_base + (size_t)bstage * kBTile) & 0x3FFFFu) >> 4) | b_lbo;
+          const uint32_t d = tmem_base + (uint32_t)(g * 64);
+#pragma unroll
+          for (int k = 0; k < kPix / 16; ++k)
+            if (leader)
+              ptx::umma_f16_lohi(d, a_lo0 + (uint32_t)(k * 128), b_lo0 + (uint32_t)(k * 128), hi, idesc,
+                                 (pt > t_begin || k > 0) ? 1u : 0u);
+          if (leader) ptx::umma_commit(b_empty + bstage);
+          __syncwarp();
+          if (++bstage == p.b_stages) { bstage = 0; bphase ^= 1; }
+        }
+        if (leader) ptx::umma_commit(a_empty + aslot);
+        __syncwarp();
+        if (++aslot == p.a_slots) { aslot = 0; aphase ^= 1; }
+      }
+      if (leader) ptx::umma_commit(acc_full);
+      __syncwarp();
+    }
+  } else {
+    // ===================== epilogue: TMEM -> red.global.add.f32 =====================
+    const int quad = warp & 3;
+    int local = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x, ++local) {
+      const int split = item % p.splits;
+      const int rest = item / p.splits;
+      const int group = rest % p.n_groups;
+      const int co_tile = rest / p.n_groups;
+      const int pair0 = group * kMaxAcc;
+      const int npair = min(kMaxAcc, p.n_pairs - pair0);
+      const int t_begin = split * p.tiles_per_split;
+      const bool has_work = t_begin < min(total_ptiles, t_begin + p.tiles_per_split);
+      ptx::mbar_wait(acc_full, (uint32_t)(local & 1));
+      ptx::tc_fence_after();
+      const int co = co_tile * 128 + quad * 32 + lane;
+      if (has_work) {
+        for (int g = 0; g < npair; ++g) {
+          const int pr = pair0 + g;
+          const int tap = pr / p.cblocks, cb = pr - tap * p.cblocks;
+          const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(g * 64);
+          float* dst = p.dW + ((size_t)co * p.taps + tap) * p.Cin + cb * 64;
+#pragma unroll
+          for (int c0 = 0; c0 < 64; c0 += 16) {
+            uint32_t v[16];
+            ptx::tmem_ld_32x32b_x16(taddr + (uint32_t)c0, v);
+            ptx::tmem_ld_wait();
+            if (co < p.Cout) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (cb * 64 + c0 + j < p.Cin) atomicAdd(dst + c0 + j, __uint_as_float(v[j]));
+            }
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(acc_empty);
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace
+}  // namespace ifcb
+
+using namespace ifcb;
+
+extern "C" int ifcb_conv_wgrad(const ifcb_wgrad_desc* d, void* stream_v) {
+  IFCB_ARG_CHECK(d != nullptr, "ifcb_conv_wgrad: null descriptor");
+  IFCB_ARG_CHECK(d->d_in && d->d_dout && d->d_dweight, "wgrad: null tensor pointer");
+  IFCB_ARG_CHECK(d->Cin > 0 && d->Cin % 8 == 0 && d->in_ld >= d->Cin && d->in_ld % 8 == 0, "wgrad: Cin / in_ld must be multiples of 8");
+  IFCB_ARG_CHECK(d->Cout > 0 && d->Cout % 8 == 0 && d->dout_ld >= d->Cout && d->dout_ld % 8 == 0, "wgrad: Cout / dout_ld must be multiples of 8");
+  IFCB_ARG_CHECK(((reinterpret_cast<uintptr_t>(d->d_in) | reinterpret_cast<uintptr_t>(d->d_dout)) & 15) == 0, "wgrad: views must be 16-byte aligned");
+  IFCB_ARG_CHECK(d->batch > 0 && d->H > 0 && d->W > 0 && d->kh >= 1 && d->kw >= 1 && d->kh <= 16 && d->kw <= 16, "wgrad: bad shape");
+  IFCB_ARG_CHECK(d->stride_h >= 1 && d->stride_w >= 1 && d->pad_h >= 0 && d->pad_w >= 0 && d->pad_h < d->kh && d->pad_w < d->kw, "wgrad: bad stride / padding");
+  IFCB_ARG_CHECK(d->dtype == IFCB_ACT_BF16 || d->dtype == IFCB_ACT_FP16, "wgrad: bad dtype");
+  int rc = resolve_driver();
+  if (rc) return rc;
+  const int P = (d->H + 2 * d->pad_h - d->kh) / d->stride_h + 1, Q = (d->W + 2 * d->pad_w - d->kw) / d->stride_w + 1;
+  IFCB_ARG_CHECK(P > 0 && Q > 0, "wgrad: empty output");
+  const long long rows = (long long)d->batch * P * Q;
+  IFCB_ARG_CHECK(rows < (1ll << 31) - 256, "wgrad: too many output pixels");
+  const CUtensorMapDataType dt = d->dtype == IFCB_ACT_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  CUtensorMap tmap_dz, tmap_x;
+  {
+    cuuint64_t gdim[2] = {(cuuint64_t)d->Cout, (cuuint64_t)rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)d->dout_ld * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)kPix};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode_tiled(&tmap_dz, dt, 2, const_cast<void*>(d->d_dout), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    IFCB_ARG_CHECK(r == CUDA_SUCCESS, "wgrad: cuTensorMapEncodeTiled failed (%d)", (int)r);
+  }
+  {
+    cuuint64_t gdim[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->batch};
+    cuuint64_t gstr[3] = {(cuuint64_t)d->in_ld * 2, (cuuint64_t)d->W * d->in_ld * 2, (cuuint64_t)d->H * d->W * d->in_ld * 2};
+    int lower[2] = {-d->pad_w, -d->pad_h};
+    int upper[2] = {d->pad_w - (d->kw - 1), d->pad_h - (d->kh - 1)};
+    cuuint32_t estr[4] = {1, (cuuint32_t)d->stride_w, (cuuint32_t)d->stride_h, 1};
+    CUresult r = g_encode_im2col(&tmap_x, dt, 4, const_cast<void*>(d->d_in), gdim, gstr, lower, upper, 64, kPix, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    IFCB_ARG_CHECK(r == CUDA_SUCCESS, "wgrad: cuTensorMapEncodeIm2col failed (%d)", (int)r);
+    const unsigned long long bytes = (unsigned long long)d->batch * d->H * d->W * d->in_ld * 2ull;
+    int drv = 0;
+    cudaDriverGetVersion(&drv);
+    if (drv <= 13010 && bytes < 131072ull) reinterpret_cast<uint64_t*>(&tmap_x)[1] &= ~(1ull << 21);
+  }
+  WgradParams p{};
+  p.rows = (int)rows;
+  p.rows_per_img = P * Q;
+  p.row_w = Q;
+  p.kh = d->kh; p.kw = d->kw;
+  p.stride_h = d->stride_h; p.stride_w = d->stride_w;
+  p.pad_h = d->pad_h; p.pad_w = d->pad_w;
+  p.Cin = d->Cin; p.Cout = d->Cout;
+  p.cblocks = (d->Cin + 63) / 64;
+  p.taps = d->kh * d->kw;
+  p.n_pairs = p.taps * p.cblocks;
+  p.n_groups = (p.n_pairs + kMaxAcc - 1) / kMaxAcc;
+  p.co_tiles = (d->Cout + 127) / 128;
+  const int ptiles = (int)((rows + kPix - 1) / kPix);
+  const int base_items = p.co_tiles * p.n_groups;
+  int splits = (2 * sm_count() + base_items - 1) / base_items;     // about two waves of work items
+  if (splits > ptiles) splits = ptiles;
+  if (splits < 1) splits = 1;
+  p.tiles_per_split = (ptiles + splits - 1) / splits;
+  p.splits = (ptiles + p.tiles_per_split - 1) / p.tiles_per_split;
+  p.a_slots = 2;
+  p.b_stages = 8;
+  p.fp16 = d->dtype;
+  p.dW = d->d_dweight;
+  const int smem = p.a_slots * kATile + p.b_stages * kBTile + 512 + 1024;
+  static int attr = 0;
+  if (smem > attr) {
+    IFCB_CUDA_CHECK(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr = smem;
+  }
+  const int items = p.co_tiles * p.n_groups * p.splits;
+  const int grid = items < sm_count() ? items : sm_count();
+  conv_wgrad_kernel<<<grid, kWThreads, smem, reinterpret_cast<cudaStream_t>(stream_v)>>>(tmap_dz, tmap_x, p);
+  IFCB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}

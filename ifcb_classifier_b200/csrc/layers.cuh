@@ -61,6 +61,12 @@ struct HeadLayer {
   ifcb_head_desc d;
 };
 
+// cuTensorMapEncode* entry points (resolved through the runtime: no link-time libcuda dependency)
+#include <cudaTypedefs.h>
+extern PFN_cuTensorMapEncodeTiled_v12000 g_encode_tiled;
+extern PFN_cuTensorMapEncodeIm2col_v12000 g_encode_im2col;
+int resolve_driver();
+
 int launch_conv(const ConvLayer& L, int batch, cudaStream_t stream);
 bool conv_plan_smem(ConvKernelParams& kp, bool window, bool pair, int halo_rows);
 int launch_im2col_probe(const ConvLayer& L, int c, int w, int h, int n, int off_w, int off_h, void* d_out,

@@ -9,17 +9,6 @@
 #include "layers.cuh"
 
 namespace ifcb {
-namespace {
-
-enum LayerKind { kConv = 0, kStem = 1, kPool = 2, kHead = 3 };
-
-struct Layer {
-  LayerKind kind;
-  ConvLayer conv;
-  StemLayer stem;
-  PoolLayer pool;
-  HeadLayer head;
-};
 
 // cuTensorMapEncode* resolved through the runtime so that the library has no
 // link-time dependency on libcuda (it must load on a CPU-only build box).
@@ -39,6 +28,18 @@ int resolve_driver() {
   g_encode_im2col = reinterpret_cast<PFN_cuTensorMapEncodeIm2col_v12000>(fn);
   return 0;
 }
+
+namespace {
+
+enum LayerKind { kConv = 0, kStem = 1, kPool = 2, kHead = 3 };
+
+struct Layer {
+  LayerKind kind;
+  ConvLayer conv;
+  StemLayer stem;
+  PoolLayer pool;
+  HeadLayer head;
+};
 
 inline int out_dim(int in, int k, int stride, int pad) { return (in + 2 * pad - k) / stride + 1; }
 

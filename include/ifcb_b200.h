@@ -165,6 +165,31 @@ int ifcb_conv_auto_tile_n(int Cout, int algo);
 int ifcb_conv_geometry(int Cin, int Cout, int kh, int kw, int tile_n_hint,
                        int32_t* Cin_pad, int32_t* K_pad, int32_t* tile_n, int32_t* Cout_pad);
 
+/* ------------------------------------------------------------------------- *
+ * TRAIN step primitives.  Replace what loss.backward() + optimizer.step() run for
+ * NeustonModel.training_step (neuston_models.py:70-86, configure_optimizers :63-64):
+ * torch autograd's conv / batch-norm / pooling backward kernels and Adam.
+ * ------------------------------------------------------------------------- */
+
+/* Conv2d weight gradient on the tensor cores (pixel axis = GEMM K, MN-major operands):
+ *   dW[co, r, s, ci] += sum_{n,p,q} dout[n,p,q,co] * in[n, p*stride_h + r - pad_h, q*stride_w + s - pad_w, ci]
+ *   d_in       NHWC 16-bit view [batch, H, W, Cin] (no border), pixel stride in_ld
+ *   d_dout     NHWC 16-bit view [batch, P, Q, Cout], pixel stride dout_ld
+ *   d_dweight  float32 [Cout, kh*kw, Cin]; the kernel ACCUMULATES (split-K over CTAs with
+ *              red.global.add.f32): zero it first for a plain gradient
+ */
+typedef struct {
+  const void* d_in;
+  int32_t in_ld, Cin;
+  int32_t batch, H, W;
+  int32_t kh, kw, stride_h, stride_w, pad_h, pad_w;
+  const void* d_dout;
+  int32_t dout_ld, Cout;
+  float* d_dweight;
+  int32_t dtype; /* IFCB_ACT_* of d_in and d_dout */
+} ifcb_wgrad_desc;
+int ifcb_conv_wgrad(const ifcb_wgrad_desc* desc, void* stream);
+
 /* Stem: first convolution (Cin = 3) computed directly in fp32 on CUDA cores from either
  * the resized gray plane (u8) or a float32 NCHW [batch,3,H,W] tensor (drop-in forward(x)).
  * Output 16-bit NHWC.
