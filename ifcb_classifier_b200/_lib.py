@@ -41,7 +41,12 @@ class WgradDesc(C.Structure):
                 ('kh', C.c_int32), ('kw', C.c_int32), ('stride_h', C.c_int32), ('stride_w', C.c_int32),
                 ('pad_h', C.c_int32), ('pad_w', C.c_int32),
                 ('d_dout', C.c_void_p), ('dout_ld', C.c_int32), ('Cout', C.c_int32),
-                ('d_dweight', C.c_void_p), ('dtype', C.c_int32)]
+                ('d_dweight', C.c_void_p), ('dtype', C.c_int32), ('in_pad_h', C.c_int32), ('in_pad_w', C.c_int32)]
+
+
+class ViewDesc(C.Structure):
+    _fields_ = [('d', C.c_void_p), ('ld', C.c_int32), ('C', C.c_int32), ('H', C.c_int32), ('W', C.c_int32),
+                ('pad_h', C.c_int32), ('pad_w', C.c_int32)]
 
 
 class StemDesc(C.Structure):
@@ -73,6 +78,7 @@ class HeadDesc(C.Structure):
 
 
 # name -> (restype, argtypes); mirrors include/ifcb_b200.h one to one
+_V = C.POINTER(ViewDesc)
 _SIGNATURES = {
     'ifcb_abi_version': (C.c_int, []),
     'ifcb_last_error': (C.c_char_p, []),
@@ -94,6 +100,29 @@ _SIGNATURES = {
     'ifcb_conv_auto_config': (C.c_int, [C.c_int] * 10 + [C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     'ifcb_conv_auto_tile_n': (C.c_int, [C.c_int, C.c_int]),
     'ifcb_conv_wgrad': (C.c_int, [C.POINTER(WgradDesc), C.c_void_p]),
+    'ifcb_memset_zero': (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p]),
+    'ifcb_bn_stats': (C.c_int, [_V, C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
+                                C.c_void_p, C.c_void_p, C.c_void_p]),
+    'ifcb_bn_apply': (C.c_int, [_V, _V, _V, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                C.c_int, C.c_void_p]),
+    'ifcb_bn_backward': (C.c_int, [_V, _V, _V, _V, _V, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'ifcb_maxpool_fwd_train': (C.c_int, [_V, _V, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    'ifcb_maxpool_bwd': (C.c_int, [_V, C.c_void_p, _V, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    'ifcb_avgpool_fwd': (C.c_int, [_V, _V, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    'ifcb_avgpool_bwd': (C.c_int, [_V, _V, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    'ifcb_dilate': (C.c_int, [_V, _V, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    'ifcb_nchw_to_nhwc': (C.c_int, [C.c_void_p, C.c_int, _V, C.c_int, C.c_int, C.c_void_p]),
+    'ifcb_head_train_fwd': (C.c_int, [_V, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                      C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'ifcb_head_bwd': (C.c_int, [_V, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                C.c_void_p, C.c_void_p, C.c_void_p]),
+    'ifcb_dropout_scale': (C.c_int, [C.c_void_p, C.c_int64, C.c_float, C.c_uint64, C.c_void_p]),
+    'ifcb_adam_step': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_float,
+                                 C.c_float, C.c_float, C.c_int, C.c_float, C.c_void_p]),
+    'ifcb_conv_repack': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                   C.c_int, C.c_void_p]),
+    'ifcb_stem_repack': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     'ifcb_plan_add_stem': (C.c_int, [C.c_void_p, C.POINTER(StemDesc)]),
     'ifcb_plan_add_pool': (C.c_int, [C.c_void_p, C.POINTER(PoolDesc)]),
     'ifcb_plan_add_head': (C.c_int, [C.c_void_p, C.POINTER(HeadDesc)]),

@@ -230,6 +230,7 @@ extern "C" int ifcb_conv_wgrad(const ifcb_wgrad_desc* d, void* stream_v) {
   IFCB_ARG_CHECK(d->batch > 0 && d->H > 0 && d->W > 0 && d->kh >= 1 && d->kw >= 1 && d->kh <= 16 && d->kw <= 16, "wgrad: bad shape");
   IFCB_ARG_CHECK(d->stride_h >= 1 && d->stride_w >= 1 && d->pad_h >= 0 && d->pad_w >= 0 && d->pad_h < d->kh && d->pad_w < d->kw, "wgrad: bad stride / padding");
   IFCB_ARG_CHECK(d->dtype == IFCB_ACT_BF16 || d->dtype == IFCB_ACT_FP16, "wgrad: bad dtype");
+  IFCB_ARG_CHECK(d->in_pad_h >= 0 && d->in_pad_w >= 0 && d->in_pad_h <= 8 && d->in_pad_w <= 8, "wgrad: bad in_pad");
   int rc = resolve_driver();
   if (rc) return rc;
   const int P = (d->H + 2 * d->pad_h - d->kh) / d->stride_h + 1, Q = (d->W + 2 * d->pad_w - d->kw) / d->stride_w + 1;
@@ -249,15 +250,17 @@ extern "C" int ifcb_conv_wgrad(const ifcb_wgrad_desc* d, void* stream_v) {
   }
   {
     cuuint64_t gdim[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->batch};
-    cuuint64_t gstr[3] = {(cuuint64_t)d->in_ld * 2, (cuuint64_t)d->W * d->in_ld * 2, (cuuint64_t)d->H * d->W * d->in_ld * 2};
+    const int Hp = d->H + 2 * d->in_pad_h, Wp = d->W + 2 * d->in_pad_w;
+    const char* base = reinterpret_cast<const char*>(d->d_in) + ((size_t)d->in_pad_h * Wp + d->in_pad_w) * d->in_ld * 2;
+    cuuint64_t gstr[3] = {(cuuint64_t)d->in_ld * 2, (cuuint64_t)Wp * d->in_ld * 2, (cuuint64_t)Hp * Wp * d->in_ld * 2};
     int lower[2] = {-d->pad_w, -d->pad_h};
     int upper[2] = {d->pad_w - (d->kw - 1), d->pad_h - (d->kh - 1)};
     cuuint32_t estr[4] = {1, (cuuint32_t)d->stride_w, (cuuint32_t)d->stride_h, 1};
-    CUresult r = g_encode_im2col(&tmap_x, dt, 4, const_cast<void*>(d->d_in), gdim, gstr, lower, upper, 64, kPix, estr,
+    CUresult r = g_encode_im2col(&tmap_x, dt, 4, const_cast<char*>(base), gdim, gstr, lower, upper, 64, kPix, estr,
                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     IFCB_ARG_CHECK(r == CUDA_SUCCESS, "wgrad: cuTensorMapEncodeIm2col failed (%d)", (int)r);
-    const unsigned long long bytes = (unsigned long long)d->batch * d->H * d->W * d->in_ld * 2ull;
+    const unsigned long long bytes = (unsigned long long)d->batch * Hp * Wp * d->in_ld * 2ull;
     int drv = 0;
     cudaDriverGetVersion(&drv);
     if (drv <= 13010 && bytes < 131072ull) reinterpret_cast<uint64_t*>(&tmap_x)[1] &= ~(1ull << 21);

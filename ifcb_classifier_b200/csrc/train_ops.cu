@@ -1,0 +1,830 @@
+// TRAIN-step kernels around the tensor-core GEMMs (sm_100a): batch-norm statistics / apply /
+// backward, pooling forward-with-index and backward, gradient dilation for strided convs,
+// the classifier head with cross-entropy, Adam and the weight repack that feeds the tcgen05
+// forward / data-gradient kernels.
+//
+// Replaces what torch autograd + torch.optim.Adam run for NeustonModel.training_step
+// (reference neuston_models.py:63-86: train-mode forward of the torchvision graph,
+// CrossEntropyLoss (+0.4 * aux), loss.backward(), Adam.step()).
+//
+// All of these are HBM-bound streaming kernels: one thread = one pixel x 8 channels (16 bytes),
+// NHWC 16-bit views with an optional physical zero border (include/ifcb_b200.h: ifcb_view).
+#include "layers.cuh"
+
+namespace ifcb {
+namespace {
+
+struct DV {   // device copy of an ifcb_view
+  uint16_t* p;
+  int ld, C, H, W, ph, pw;
+};
+
+inline DV dv(const ifcb_view* v) {
+  DV d;
+  d.p = reinterpret_cast<uint16_t*>(v->d);
+  d.ld = v->ld; d.C = v->C; d.H = v->H; d.W = v->W; d.ph = v->pad_h; d.pw = v->pad_w;
+  return d;
+}
+
+__device__ __forceinline__ long long pix_off(const DV& v, int n, int h, int w) {
+  return (((long long)n * (v.H + 2 * v.ph) + h + v.ph) * (v.W + 2 * v.pw) + w + v.pw) * v.ld;
+}
+
+// logical pixel index m = (n*H + h)*W + w  ->  element offset of that pixel in the view
+__device__ __forceinline__ long long pix_off_m(const DV& v, long long m) {
+  if ((v.ph | v.pw) == 0) return m * v.ld;
+  const int w = (int)(m % v.W);
+  const long long t = m / v.W;
+  const int h = (int)(t % v.H);
+  const int n = (int)(t / v.H);
+  return pix_off(v, n, h, w);
+}
+
+__device__ __forceinline__ void load8(const uint16_t* p, int fp16, float* f) {
+  const uint4 v = *reinterpret_cast<const uint4*>(p);
+  const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 t = unpack_act2(u[j], fp16);
+    f[2 * j] = t.x;
+    f[2 * j + 1] = t.y;
+  }
+}
+
+__device__ __forceinline__ void store8(uint16_t* p, int fp16, const float* f) {
+  uint4 o;
+  o.x = pack_act2(f[0], f[1], fp16);
+  o.y = pack_act2(f[2], f[3], fp16);
+  o.z = pack_act2(f[4], f[5], fp16);
+  o.w = pack_act2(f[6], f[7], fp16);
+  *reinterpret_cast<uint4*>(p) = o;
+}
+
+bool view_ok(const ifcb_view* v) {
+  return v && v->d && v->C > 0 && v->C % 8 == 0 && v->ld >= v->C && v->ld % 8 == 0 && v->H > 0 && v->W > 0 &&
+         v->pad_h >= 0 && v->pad_w >= 0 && (reinterpret_cast<uintptr_t>(v->d) & 15) == 0;
+}
+
+int grid_for(long long total, int threads, int cap_per_sm = 16) {
+  long long g = (total + threads - 1) / threads;
+  const long long cap = (long long)sm_count() * cap_per_sm;
+  if (g > cap) g = cap;
+  return g < 1 ? 1 : (int)g;
+}
+
+// ------------------------------------------------------------------------------------------
+// Per-channel reductions over all pixels of a view.  Block = rows x (C/8) threads; every thread
+// keeps fp32 partials of its 8 channels over its pixel rows (grid-stride), the block reduces
+// over rows in shared memory and adds into float64 accumulators (order-insensitive to fp32).
+//   MODE 0 (bn_stats):      acc[c] += z, acc[C + c] += z*z
+//   MODE 1 (bn_bwd_reduce): dy' = relu-masked dy; acc[c] += dy', acc[C + c] += dy' * (z - mean) * invstd
+// ------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(256) channel_reduce_kernel(DV z, DV dy, DV a, int use_mask, const float* __restrict__ mean,
+                                                             const float* __restrict__ invstd, long long M, int rows, int fp16,
+                                                             double* __restrict__ acc) {
+  __shared__ float red[256 * 16];
+  const int c8n = z.C >> 3;
+  const int tid = threadIdx.x;
+  const int row = tid / c8n, c8 = tid - row * c8n;
+  float s1[8], s2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+  if (row < rows) {
+    float mu[8], is[8];
+    if (MODE == 1) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        mu[j] = mean[c8 * 8 + j];
+        is[j] = invstd[c8 * 8 + j];
+      }
+    }
+    for (long long m = (long long)blockIdx.x * rows + row; m < M; m += (long long)gridDim.x * rows) {
+      float zv[8];
+      load8(z.p + pix_off_m(z, m) + c8 * 8, fp16, zv);
+      if (MODE == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          s1[j] += zv[j];
+          s2[j] = fmaf(zv[j], zv[j], s2[j]);
+        }
+      } else {
+        float g[8];
+        load8(dy.p + pix_off_m(dy, m) + c8 * 8, fp16, g);
+        if (use_mask) {
+          float av[8];
+          load8(a.p + pix_off_m(a, m) + c8 * 8, fp16, av);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) g[j] = av[j] > 0.f ? g[j] : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          s1[j] += g[j];
+          s2[j] = fmaf(g[j], (zv[j] - mu[j]) * is[j], s2[j]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    red[tid * 16 + j] = s1[j];
+    red[tid * 16 + 8 + j] = s2[j];
+  }
+  __syncthreads();
+  // thread t < 2*C sums one (quantity, channel) over the rows
+  for (int t = tid; t < 2 * z.C; t += 256) {
+    const int which = t / z.C, c = t - which * z.C;
+    const int cc8 = c >> 3, j = c & 7;
+    float s = 0.f;
+    for (int r = 0; r < rows; ++r) s += red[(r * c8n + cc8) * 16 + which * 8 + j];
+    atomicAdd(acc + t, (double)s);
+  }
+}
+
+// mean / invstd from the float64 sums, running-stat update as torch.nn.BatchNorm2d in train
+// mode (momentum 0.1, UNBIASED variance into running_var); clears the accumulators.
+__global__ void bn_finalize_kernel(double* __restrict__ acc, int C, double M, float eps, float momentum, float* __restrict__ mean,
+                                   float* __restrict__ invstd, float* __restrict__ run_mean, float* __restrict__ run_var) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double mu = acc[c] / M;
+  double var = acc[C + c] / M - mu * mu;
+  if (var < 0.0) var = 0.0;
+  mean[c] = (float)mu;
+  invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+  if (run_mean) run_mean[c] = (1.f - momentum) * run_mean[c] + momentum * (float)mu;
+  if (run_var) {
+    const double unb = M > 1.0 ? var * M / (M - 1.0) : var;
+    run_var[c] = (1.f - momentum) * run_var[c] + momentum * (float)unb;
+  }
+  acc[c] = 0.0;
+  acc[C + c] = 0.0;
+}
+
+// a = act(gamma * (z - mean) * invstd + beta (+ residual))
+__global__ void __launch_bounds__(256) bn_apply_kernel(DV z, DV out, DV res, int has_res, const float* __restrict__ mean,
+                                                       const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                                       const float* __restrict__ beta, int relu, long long total, int fp16) {
+  const int c8n = z.C >> 3;
+  for (long long idx = (long long)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (long long)gridDim.x * 256) {
+    const long long m = idx / c8n;
+    const int c8 = (int)(idx - m * c8n);
+    float v[8];
+    load8(z.p + pix_off_m(z, m) + c8 * 8, fp16, v);
+    const float4 m0 = __ldg(reinterpret_cast<const float4*>(mean + c8 * 8)), m1 = __ldg(reinterpret_cast<const float4*>(mean + c8 * 8 + 4));
+    const float4 i0 = __ldg(reinterpret_cast<const float4*>(invstd + c8 * 8)), i1 = __ldg(reinterpret_cast<const float4*>(invstd + c8 * 8 + 4));
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c8 * 8)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c8 * 8 + 4));
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c8 * 8)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c8 * 8 + 4));
+    const float mu[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+    const float is[8] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
+    const float ga[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float be[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    float r[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (has_res) load8(res.p + pix_off_m(res, m) + c8 * 8, fp16, r);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float y = fmaf((v[j] - mu[j]) * is[j], ga[j], be[j]) + r[j];
+      v[j] = relu ? fmaxf(y, 0.f) : y;
+    }
+    store8(out.p + pix_off_m(out, m) + c8 * 8, fp16, v);
+  }
+}
+
+// dz = gamma * invstd * (dy' - sum(dy')/M - xhat * sum(dy' * xhat)/M);  dy' = relu-masked dy.
+// Optionally routes dy' to the residual branch (written or accumulated); block 0 stores
+// dgamma = sum(dy' * xhat), dbeta = sum(dy').  dz may alias dy (in place).
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(DV dy, DV a, int use_mask, DV z, DV dz, DV dres, int res_mode,
+                                                           const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                           const float* __restrict__ gamma, const double* __restrict__ acc,
+                                                           float inv_m, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                           long long total, int fp16) {
+  const int C = z.C, c8n = C >> 3;
+  if (blockIdx.x == 0) {
+    for (int c = threadIdx.x; c < C; c += 256) {
+      if (dbeta) dbeta[c] += (float)acc[c];
+      if (dgamma) dgamma[c] += (float)acc[C + c];
+    }
+  }
+  for (long long idx = (long long)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (long long)gridDim.x * 256) {
+    const long long m = idx / c8n;
+    const int c8 = (int)(idx - m * c8n);
+    float g[8], zv[8];
+    const long long o_dy = pix_off_m(dy, m) + c8 * 8;
+    load8(dy.p + o_dy, fp16, g);
+    load8(z.p + pix_off_m(z, m) + c8 * 8, fp16, zv);
+    if (use_mask) {
+      float av[8];
+      load8(a.p + pix_off_m(a, m) + c8 * 8, fp16, av);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] = av[j] > 0.f ? g[j] : 0.f;
+    }
+    if (res_mode) {
+      uint16_t* rp = dres.p + pix_off_m(dres, m) + c8 * 8;
+      float r[8];
+      if (res_mode == 2) {
+        load8(rp, fp16, r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] += g[j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = g[j];
+      }
+      store8(rp, fp16, r);
+    }
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = c8 * 8 + j;
+      const float is = __ldg(invstd + c);
+      const float xh = (zv[j] - __ldg(mean + c)) * is;
+      const float s1 = (float)acc[c] * inv_m, s2 = (float)acc[C + c] * inv_m;
+      o[j] = __ldg(gamma + c) * is * (g[j] - s1 - xh * s2);
+    }
+    store8(dz.p + pix_off_m(dz, m) + c8 * 8, fp16, o);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Pooling.
+// ------------------------------------------------------------------------------------------
+// max pool forward that also records the winning tap (first maximum in window scan order, as
+// torch.nn.functional.max_pool2d) for the backward pass.  idx: uint8 [B, P, Q, C].
+__global__ void __launch_bounds__(256) maxpool_fwd_kernel(DV x, DV y, uint8_t* __restrict__ idx, int k, int stride, int pad,
+                                                          int P, int Q, long long total, int fp16) {
+  const int c8n = x.C >> 3;
+  for (long long t = (long long)blockIdx.x * 256 + threadIdx.x; t < total; t += (long long)gridDim.x * 256) {
+    const long long m = t / c8n;
+    const int c8 = (int)(t - m * c8n);
+    const int oq = (int)(m % Q);
+    const long long t2 = m / Q;
+    const int op = (int)(t2 % P), n = (int)(t2 / P);
+    const int h0 = op * stride - pad, w0 = oq * stride - pad;
+    float best[8];
+    int bi[8];
+    bool first = true;
+    for (int r = 0; r < k; ++r) {
+      const int hh = h0 + r;
+      if (hh < 0 || hh >= x.H) continue;
+      for (int s = 0; s < k; ++s) {
+        const int ww = w0 + s;
+        if (ww < 0 || ww >= x.W) continue;
+        float v[8];
+        load8(x.p + pix_off(x, n, hh, ww) + c8 * 8, fp16, v);
+        const int tap = r * k + s;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (first || v[j] > best[j] || v[j] != v[j]) {
+            best[j] = v[j];
+            bi[j] = tap;
+          }
+        }
+        first = false;
+      }
+    }
+    store8(y.p + pix_off(y, n, op, oq) + c8 * 8, fp16, best);
+    uint2 pk;
+    pk.x = (uint32_t)bi[0] | ((uint32_t)bi[1] << 8) | ((uint32_t)bi[2] << 16) | ((uint32_t)bi[3] << 24);
+    pk.y = (uint32_t)bi[4] | ((uint32_t)bi[5] << 8) | ((uint32_t)bi[6] << 16) | ((uint32_t)bi[7] << 24);
+    *reinterpret_cast<uint2*>(idx + m * x.C + c8 * 8) = pk;
+  }
+}
+
+// gather form of the max-pool / avg-pool backward: one thread = one INPUT pixel x 8 channels,
+// sums the gradients of the output windows that cover it (deterministic, no atomics).
+template <bool AVG>
+__global__ void __launch_bounds__(256) pool_bwd_kernel(DV dy, const uint8_t* __restrict__ idx, DV dx, int accumulate, int k,
+                                                       int stride, int pad, int P, int Q, long long total, int fp16) {
+  const int c8n = dx.C >> 3;
+  const float inv = 1.f / (float)(k * k);
+  for (long long t = (long long)blockIdx.x * 256 + threadIdx.x; t < total; t += (long long)gridDim.x * 256) {
+    const long long m = t / c8n;
+    const int c8 = (int)(t - m * c8n);
+    const int w = (int)(m % dx.W);
+    const long long t2 = m / dx.W;
+    const int h = (int)(t2 % dx.H), n = (int)(t2 / dx.H);
+    float g[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    // windows op with op*stride - pad <= h <= op*stride - pad + k - 1
+    int p_lo = h + pad - k + 1;
+    p_lo = p_lo <= 0 ? 0 : (p_lo + stride - 1) / stride;
+    int p_hi = (h + pad) / stride;
+    if (p_hi > P - 1) p_hi = P - 1;
+    int q_lo = w + pad - k + 1;
+    q_lo = q_lo <= 0 ? 0 : (q_lo + stride - 1) / stride;
+    int q_hi = (w + pad) / stride;
+    if (q_hi > Q - 1) q_hi = Q - 1;
+    for (int op = p_lo; op <= p_hi; ++op) {
+      const int r = h + pad - op * stride;
+      for (int oq = q_lo; oq <= q_hi; ++oq) {
+        const int s = w + pad - oq * stride;
+        float v[8];
+        load8(dy.p + pix_off(dy, n, op, oq) + c8 * 8, fp16, v);
+        if (AVG) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) g[j] += v[j];
+        } else {
+          const uint2 pk = *reinterpret_cast<const uint2*>(idx + (((long long)n * P + op) * Q + oq) * dx.C + c8 * 8);
+          const int tap = r * k + s;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int w8 = (int)(((j < 4 ? pk.x : pk.y) >> (8 * (j & 3))) & 0xffu);
+            if (w8 == tap) g[j] += v[j];
+          }
+        }
+      }
+    }
+    if (AVG) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] *= inv;
+    }
+    uint16_t* dst = dx.p + pix_off(dx, n, h, w) + c8 * 8;
+    if (accumulate) {
+      float o[8];
+      load8(dst, fp16, o);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] += o[j];
+    }
+    store8(dst, fp16, g);
+  }
+}
+
+// plain average pool (count_include_pad=True, divisor k*k): F.avg_pool2d in Inception blocks / aux head
+__global__ void __launch_bounds__(256) avgpool_fwd_kernel(DV x, DV y, int k, int stride, int pad, int P, int Q, long long total,
+                                                          int fp16) {
+  const int c8n = x.C >> 3;
+  const float inv = 1.f / (float)(k * k);
+  for (long long t = (long long)blockIdx.x * 256 + threadIdx.x; t < total; t += (long long)gridDim.x * 256) {
+    const long long m = t / c8n;
+    const int c8 = (int)(t - m * c8n);
+    const int oq = (int)(m % Q);
+    const long long t2 = m / Q;
+    const int op = (int)(t2 % P), n = (int)(t2 / P);
+    const int h0 = op * stride - pad, w0 = oq * stride - pad;
+    float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int r = 0; r < k; ++r) {
+      const int hh = h0 + r;
+      if (hh < 0 || hh >= x.H) continue;
+      for (int s = 0; s < k; ++s) {
+        const int ww = w0 + s;
+        if (ww < 0 || ww >= x.W) continue;
+        float v[8];
+        load8(x.p + pix_off(x, n, hh, ww) + c8 * 8, fp16, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] += v[j];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] *= inv;
+    store8(y.p + pix_off(y, n, op, oq) + c8 * 8, fp16, a);
+  }
+}
+
+// out[n, p*sh, q*sw, :] = in[n, p, q, :]  (out is zero elsewhere and stays so): the data gradient
+// of a strided conv is the stride-1 transposed conv of the zero-dilated output gradient.
+__global__ void __launch_bounds__(256) dilate_kernel(DV in, DV out, int sh, int sw, long long total) {
+  const int c8n = in.C >> 3;
+  for (long long t = (long long)blockIdx.x * 256 + threadIdx.x; t < total; t += (long long)gridDim.x * 256) {
+    const long long m = t / c8n;
+    const int c8 = (int)(t - m * c8n);
+    const int q = (int)(m % in.W);
+    const long long t2 = m / in.W;
+    const int p = (int)(t2 % in.H), n = (int)(t2 / in.H);
+    const uint4 v = *reinterpret_cast<const uint4*>(in.p + pix_off(in, n, p, q) + c8 * 8);
+    *reinterpret_cast<uint4*>(out.p + pix_off(out, n, p * sh, q * sw) + c8 * 8) = v;
+  }
+}
+
+// float32 NCHW [B, Cin, H, W] -> 16-bit NHWC view with C >= Cin channels (extra channels zero):
+// the stem's input in the layout the tensor-core weight-gradient kernel reads.
+__global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ in, int Cin, DV out, long long total, int fp16) {
+  for (long long m = (long long)blockIdx.x * 256 + threadIdx.x; m < total; m += (long long)gridDim.x * 256) {
+    const int w = (int)(m % out.W);
+    const long long t2 = m / out.W;
+    const int h = (int)(t2 % out.H), n = (int)(t2 / out.H);
+    const long long plane = (long long)out.H * out.W;
+    const float* src = in + (long long)n * Cin * plane + (long long)h * out.W + w;
+    uint16_t* dst = out.p + pix_off(out, n, h, w);
+    for (int c0 = 0; c0 < out.C; c0 += 8) {
+      float f[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = (c0 + j) < Cin ? __ldg(src + (long long)(c0 + j) * plane) : 0.f;
+      store8(dst + c0, fp16, f);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Classifier head, train mode: global average pool (x dropout scale) -> Linear -> CE loss.
+// ------------------------------------------------------------------------------------------
+// One CTA per image.  pooled[b, c] = dropscale[b, c] * mean_hw x[b, hw, c]; logits = W pooled + bias;
+// loss_b = logsumexp(logits) - logits[label]; dlogits = weight/B * (softmax - onehot);
+// loss_acc += weight/B * loss_b.
+__global__ void __launch_bounds__(256) head_train_fwd_kernel(DV x, const float* __restrict__ dropscale, const float* __restrict__ W,
+                                                             const float* __restrict__ bias, const long long* __restrict__ labels,
+                                                             int n_classes, int batch, float loss_weight, float* __restrict__ pooled_out,
+                                                             float* __restrict__ logits_out, float* __restrict__ dlogits,
+                                                             float* __restrict__ loss_acc, int fp16) {
+  extern __shared__ float sm[];
+  float* pooled = sm;            // [C]
+  float* logits = sm + x.C;      // [n_classes]
+  const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int HW = x.H * x.W;
+  const float inv = 1.f / (float)HW;
+  for (int c8 = tid; c8 < (x.C >> 3); c8 += 256) {
+    float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int px = 0; px < HW; ++px) {
+      float v[8];
+      load8(x.p + pix_off(x, img, px / x.W, px % x.W) + c8 * 8, fp16, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[j] += v[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = c8 * 8 + j;
+      const float ds = dropscale ? dropscale[(long long)img * x.C + c] : 1.f;
+      const float pv = a[j] * inv * ds;
+      pooled[c] = pv;
+      pooled_out[(long long)img * x.C + c] = pv;
+    }
+  }
+  __syncthreads();
+  for (int k = warp; k < n_classes; k += 8) {
+    const float4* wrow = reinterpret_cast<const float4*>(W + (long long)k * x.C);
+    float s = 0.f;
+    for (int c4 = lane; c4 < (x.C >> 2); c4 += 32) {
+      const float4 w = __ldg(wrow + c4);
+      const float4 xv = *reinterpret_cast<const float4*>(pooled + c4 * 4);
+      s = fmaf(w.x, xv.x, s);
+      s = fmaf(w.y, xv.y, s);
+      s = fmaf(w.z, xv.z, s);
+      s = fmaf(w.w, xv.w, s);
+    }
+    s = warp_sum(s);
+    if (lane == 0) logits[k] = s + bias[k];
+  }
+  __syncthreads();
+  if (warp == 0) {
+    float mx = -INFINITY;
+    for (int k = lane; k < n_classes; k += 32) mx = fmaxf(mx, logits[k]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int k = lane; k < n_classes; k += 32) sum += expf(logits[k] - mx);
+    sum = warp_sum(sum);
+    const int label = (int)labels[img];
+    const float wb = loss_weight / (float)batch;
+    for (int k = lane; k < n_classes; k += 32) {
+      const float l = logits[k];
+      const float pr = expf(l - mx) / sum;
+      if (logits_out) logits_out[(long long)img * n_classes + k] = l;
+      dlogits[(long long)img * n_classes + k] = wb * (pr - (k == label ? 1.f : 0.f));
+    }
+    if (lane == 0 && label >= 0 && label < n_classes) atomicAdd(loss_acc, wb * (logf(sum) + mx - logits[label]));
+  }
+}
+
+// dW[k, c] += sum_b dlogits[b, k] * pooled[b, c];  db[k] += sum_b dlogits[b, k]
+__global__ void __launch_bounds__(256) head_wgrad_kernel(const float* __restrict__ dlogits, const float* __restrict__ pooled, int batch,
+                                                         int n_classes, int C, float* __restrict__ dW, float* __restrict__ db) {
+  const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (t < (long long)n_classes * C) {
+    const int k = (int)(t / C), c = (int)(t - (long long)k * C);
+    float s = 0.f;
+    for (int b = 0; b < batch; ++b) s = fmaf(__ldg(dlogits + (long long)b * n_classes + k), __ldg(pooled + (long long)b * C + c), s);
+    dW[t] += s;
+  }
+  if (t < n_classes) {
+    float s = 0.f;
+    for (int b = 0; b < batch; ++b) s += dlogits[(long long)b * n_classes + t];
+    db[t] += s;
+  }
+}
+
+// dx[b, hw, c] (+)= dropscale[b, c] / HW * sum_k dlogits[b, k] * W[k, c]
+__global__ void __launch_bounds__(256) head_dgrad_kernel(const float* __restrict__ dlogits, const float* __restrict__ W,
+                                                         const float* __restrict__ dropscale, int n_classes, DV dx, int accumulate,
+                                                         long long total, int fp16) {
+  const int c8n = dx.C >> 3;
+  const int HW = dx.H * dx.W;
+  for (long long t = (long long)blockIdx.x * 256 + threadIdx.x; t < total; t += (long long)gridDim.x * 256) {
+    const int b = (int)(t / c8n), c8 = (int)(t - (long long)b * c8n);
+    float g[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int k = 0; k < n_classes; ++k) {
+      const float dl = __ldg(dlogits + (long long)b * n_classes + k);
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(W + (long long)k * dx.C + c8 * 8));
+      const float4 w1 = __ldg(reinterpret_cast<const float4*>(W + (long long)k * dx.C + c8 * 8 + 4));
+      g[0] = fmaf(dl, w0.x, g[0]); g[1] = fmaf(dl, w0.y, g[1]); g[2] = fmaf(dl, w0.z, g[2]); g[3] = fmaf(dl, w0.w, g[3]);
+      g[4] = fmaf(dl, w1.x, g[4]); g[5] = fmaf(dl, w1.y, g[5]); g[6] = fmaf(dl, w1.z, g[6]); g[7] = fmaf(dl, w1.w, g[7]);
+    }
+    const float inv = 1.f / (float)HW;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] *= inv * (dropscale ? dropscale[(long long)b * dx.C + c8 * 8 + j] : 1.f);
+    for (int px = 0; px < HW; ++px) {
+      uint16_t* dst = dx.p + pix_off(dx, b, px / dx.W, px % dx.W) + c8 * 8;
+      float o[8];
+      if (accumulate) {
+        load8(dst, fp16, o);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] += g[j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = g[j];
+      }
+      store8(dst, fp16, o);
+    }
+  }
+}
+
+// inverted-dropout scale per element: 0 with probability p, else 1/(1-p).  Counter-based
+// (splitmix64 of seed + index) -- its own stream; torch's Philox sequence is not reproduced.
+__global__ void __launch_bounds__(256) dropout_scale_kernel(float* __restrict__ out, long long n, float p, unsigned long long seed) {
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    unsigned long long x = seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(i + 1);
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    x ^= x >> 31;
+    const float u = (float)(x >> 40) * (1.0f / 16777216.0f);
+    out[i] = u < p ? 0.f : 1.f / (1.f - p);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Adam (torch.optim.Adam defaults: no weight decay, no amsgrad) over a flat fp32 arena.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ m,
+                                                   float* __restrict__ v, long long n, float lr, float b1, float b2, float eps,
+                                                   float bc1, float bc2_sqrt, float grad_scale) {
+  const long long n4 = n >> 2;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
+    float4 w4 = reinterpret_cast<float4*>(w)[i], m4 = reinterpret_cast<float4*>(m)[i], v4 = reinterpret_cast<float4*>(v)[i];
+    const float4 g4 = reinterpret_cast<const float4*>(g)[i];
+    float* wp = &w4.x; float* mp = &m4.x; float* vp = &v4.x; const float* gp = &g4.x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float gj = gp[j] * grad_scale;
+      mp[j] = b1 * mp[j] + (1.f - b1) * gj;
+      vp[j] = b2 * vp[j] + (1.f - b2) * gj * gj;
+      const float denom = sqrtf(vp[j]) / bc2_sqrt + eps;
+      wp[j] -= (lr / bc1) * (mp[j] / denom);
+    }
+    reinterpret_cast<float4*>(w)[i] = w4;
+    reinterpret_cast<float4*>(m)[i] = m4;
+    reinterpret_cast<float4*>(v)[i] = v4;
+  }
+  // tail (n not a multiple of 4)
+  const long long i = n4 * 4 + (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i < n) {
+    const float gj = g[i] * grad_scale;
+    m[i] = b1 * m[i] + (1.f - b1) * gj;
+    v[i] = b2 * v[i] + (1.f - b2) * gj * gj;
+    w[i] -= (lr / bc1) * (m[i] / (sqrtf(v[i]) / bc2_sqrt + eps));
+  }
+}
+
+// fp32 master weights [Cout, taps, Cin] -> (1) forward operand [Cout_pad, taps*Cin_pad] 16-bit,
+// (2) data-gradient operand [Cin_padN, taps*Cout_padK] 16-bit with the taps reversed:
+//     wd[ci, (taps-1-t)*Cout_padK + co] = w[co, t, ci]   (conv of dz with the flipped, transposed filter)
+__global__ void __launch_bounds__(256) conv_repack_kernel(const float* __restrict__ w, int Cout, int taps, int Cin, uint16_t* __restrict__ wf,
+                                                          int cin_pad, uint16_t* __restrict__ wd, int cout_padk, int fp16) {
+  const long long total = (long long)Cout * taps * Cin;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int ci = (int)(i % Cin);
+    const long long r = i / Cin;
+    const int t = (int)(r % taps), co = (int)(r / taps);
+    const float v = w[i];
+    uint16_t h;
+    if (fp16) {
+      const __half hv = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
+      h = *reinterpret_cast<const uint16_t*>(&hv);
+    } else {
+      const __nv_bfloat16 bv = __float2bfloat16_rn(v);
+      h = *reinterpret_cast<const uint16_t*>(&bv);
+    }
+    if (wf) wf[(long long)co * taps * cin_pad + (long long)t * cin_pad + ci] = h;
+    if (wd) wd[(long long)ci * taps * cout_padk + (long long)(taps - 1 - t) * cout_padk + co] = h;
+  }
+}
+
+// stem master weights [Cout, taps, Cin8] fp32 -> the fp32 stem kernel's [taps*3, Cout]
+__global__ void stem_repack_kernel(const float* __restrict__ w, int Cout, int taps, int cin8, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Cout * taps * 3) return;
+  const int c = i % 3, t = (i / 3) % taps, co = i / (3 * taps);
+  out[(t * 3 + c) * Cout + co] = w[((long long)co * taps + t) * cin8 + c];
+}
+
+}  // namespace
+}  // namespace ifcb
+
+using namespace ifcb;
+#define STREAM(s) reinterpret_cast<cudaStream_t>(s)
+#define DT_OK(dt) ((dt) == IFCB_ACT_BF16 || (dt) == IFCB_ACT_FP16)
+
+extern "C" int ifcb_memset_zero(void* d, int64_t bytes, void* stream) {
+  IFCB_ARG_CHECK(d != nullptr && bytes >= 0, "memset_zero: bad argument");
+  IFCB_CUDA_CHECK(cudaMemsetAsync(d, 0, (size_t)bytes, STREAM(stream)));
+  return 0;
+}
+
+static int reduce_rows(int C) {
+  const int c8n = C / 8;
+  int rows = 256 / c8n;
+  return rows < 1 ? 1 : rows;
+}
+
+extern "C" int ifcb_bn_stats(const ifcb_view* z, int batch, int dtype, float eps, float momentum, double* d_acc, float* d_mean,
+                             float* d_invstd, float* d_running_mean, float* d_running_var, void* stream) {
+  IFCB_ARG_CHECK(view_ok(z) && batch > 0 && DT_OK(dtype), "bn_stats: bad view / batch / dtype");
+  IFCB_ARG_CHECK(z->C <= 2048, "bn_stats: C=%d > 2048", z->C);
+  IFCB_ARG_CHECK(d_acc && d_mean && d_invstd, "bn_stats: null pointer");
+  const long long M = (long long)batch * z->H * z->W;
+  const int rows = reduce_rows(z->C);
+  const int grid = grid_for((M + rows - 1) / rows, 8, 4);       // ~8 pixel rows per thread at least
+  DV zz = dv(z);
+  channel_reduce_kernel<0><<<grid, 256, 0, STREAM(stream)>>>(zz, zz, zz, 0, nullptr, nullptr, M, rows, dtype, d_acc);
+  bn_finalize_kernel<<<(z->C + 127) / 128, 128, 0, STREAM(stream)>>>(d_acc, z->C, (double)M, eps, momentum, d_mean, d_invstd,
+                                                                      d_running_mean, d_running_var);
+  IFCB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int ifcb_bn_apply(const ifcb_view* z, const ifcb_view* out, const ifcb_view* residual, int batch, int dtype,
+                             const float* d_mean, const float* d_invstd, const float* d_gamma, const float* d_beta, int relu,
+                             void* stream) {
+  IFCB_ARG_CHECK(view_ok(z) && view_ok(out) && batch > 0 && DT_OK(dtype), "bn_apply: bad view / batch / dtype");
+  IFCB_ARG_CHECK(out->C == z->C && out->H == z->H && out->W == z->W, "bn_apply: output extent differs");
+  IFCB_ARG_CHECK(!residual || (view_ok(residual) && residual->C == z->C && residual->H == z->H && residual->W == z->W),
+                 "bn_apply: residual extent differs");
+  IFCB_ARG_CHECK(d_mean && d_invstd && d_gamma && d_beta, "bn_apply: null pointer");
+  const long long total = (long long)batch * z->H * z->W * (z->C / 8);
+  DV zz = dv(z);
+  bn_apply_kernel<<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(zz, dv(out), residual ? dv(residual) : zz, residual ? 1 : 0, d_mean,
+                                                                     d_invstd, d_gamma, d_beta, relu, total, dtype);
+  IFCB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int ifcb_bn_backward(const ifcb_view* dy, const ifcb_view* a, const ifcb_view* z, const ifcb_view* dz,
+                                const ifcb_view* dres, int dres_accumulate, int batch, int dtype, const float* d_mean,
+                                const float* d_invstd, const float* d_gamma, double* d_acc, float* d_dgamma, float* d_dbeta,
+                                void* stream) {
+  IFCB_ARG_CHECK(view_ok(dy) && view_ok(z) && view_ok(dz) && batch > 0 && DT_OK(dtype), "bn_backward: bad view / batch / dtype");
+  IFCB_ARG_CHECK(z->C <= 2048, "bn_backward: C=%d > 2048", z->C);
+  IFCB_ARG_CHECK(dy->C == z->C && dz->C == z->C && dy->H == z->H && dy->W == z->W && dz->H == z->H && dz->W == z->W,
+                 "bn_backward: extents differ");
+  IFCB_ARG_CHECK(!a || (view_ok(a) && a->C == z->C && a->H == z->H && a->W == z->W), "bn_backward: mask extent differs");
+  IFCB_ARG_CHECK(!dres || (view_ok(dres) && dres->C == z->C && dres->H == z->H && dres->W == z->W), "bn_backward: dres extent differs");
+  IFCB_ARG_CHECK(d_mean && d_invstd && d_gamma && d_acc, "bn_backward: null pointer");
+  const long long M = (long long)batch * z->H * z->W;
+  const int rows = reduce_rows(z->C);
+  DV zz = dv(z), dyy = dv(dy);
+  IFCB_CUDA_CHECK(cudaMemsetAsync(d_acc, 0, sizeof(double) * 2 * z->C, STREAM(stream)));
+  channel_reduce_kernel<1><<<grid_for((M + rows - 1) / rows, 8, 4), 256, 0, STREAM(stream)>>>(zz, dyy, a ? dv(a) : zz, a ? 1 : 0, d_mean,
+                                                                                                d_invstd, M, rows, dtype, d_acc);
+  const long long total = M * (z->C / 8);
+  bn_bwd_apply_kernel<<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(dyy, a ? dv(a) : zz, a ? 1 : 0, zz, dv(dz), dres ? dv(dres) : zz,
+                                                                         dres ? (dres_accumulate ? 2 : 1) : 0, d_mean, d_invstd, d_gamma,
+                                                                         d_acc, 1.f / (float)M, d_dgamma, d_dbeta, total, dtype);
+  IFCB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+static int pool_out(int in, int k, int s, int p) { return (in + 2 * p - k) / s + 1; }
+
+extern "C" int ifcb_maxpool_fwd_train(const ifcb_view* x, const ifcb_view* y, uint8_t* d_idx, int batch, int k, int stride, int pad,
+                                      int dtype, void* stream) {
+  IFCB_ARG_CHECK(view_ok(x) && view_ok(y) && d_idx && batch > 0 && DT_OK(dtype), "maxpool_fwd_train: bad argument");
+  IFCB_ARG_CHECK(k >= 1 && k <= 15 && stride >= 1 && pad >= 0 && pad < k, "maxpool_fwd_train: bad window");
+  const int P = pool_out(x->H, k, stride, pad), Q = pool_out(x->W, k, stride, pad);
+  IFCB_ARG_CHECK(y->C == x->C && y->H == P && y->W == Q, "maxpool_fwd_train: output extent %dx%dx%d, expected %dx%dx%d", y->H, y->W, y->C,
+                 P, Q, x->C);
+  const long long total = (long long)batch * P * Q * (x->C / 8);
+  maxpool_fwd_kernel<<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(dv(x), dv(y), d_idx, k, stride, pad, P, Q, total, dtype);
+  IFCB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int ifcb_maxpool_bwd(const ifcb_view* dy, const uint8_t* d_idx, const ifcb_view* dx, int accumulate, int batch, int k,
+                                int stride, int pad, int dtype, void* stream) {
+  IFCB_ARG_CHECK(view_ok(dy) && view_ok(dx) && d_idx && batch > 0 && DT_OK(dtype), "maxpool_bwd: bad argument");
+  IFCB_ARG_CHECK(k >= 1 && k <= 15 && stride >= 1 && pad >= 0 && pad < k, "maxpool_bwd: bad window");
+  const int P = pool_out(dx->H, k, stride, pad), Q = pool_out(dx->W, k, stride, pad);
+  IFCB_ARG_CHECK(dy->C == dx->C && dy->H == P && dy->W == Q, "maxpool_bwd: gradient extent differs");
+  const long long total = (long long)batch * dx->H * dx->W * (dx->C / 8);
+  pool_bwd_kernel<false><<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(dv(dy), d_idx, dv(dx), accumulate, k, stride, pad, P, Q, total,
+                                                                            dtype);
+  IFCB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int ifcb_avgpool_fwd(const ifcb_view* x, const ifcb_view* y, int batch, int k, int stride, int pad, int dtype, void* stream) {
+  IFCB_ARG_CHECK(view_ok(x) && view_ok(y) && batch > 0 && DT_OK(dtype), "avgpool_fwd: bad argument");
+  IFCB_ARG_CHECK(k >= 1 && k <= 15 && stride >= 1 && pad >= 0 && pad < k, "avgpool_fwd: bad window");
+  const int P = pool_out(x->H, k, stride, pad), Q = pool_out(x->W, k, stride, pad);
+  IFCB_ARG_CHECK(y->C == x->C && y->H == P && y->W == Q, "avgpool_fwd: output extent differs");
+  const long long total = (long long)batch * P * Q * (x->C / 8);
+  avgpool_fwd_kernel<<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(dv(x), dv(y), k, stride, pad, P, Q, total, dtype);
+  IFCB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int ifcb_avgpool_bwd(const ifcb_view* dy, const ifcb_view* dx, int accumulate, int batch, int k, int stride, int pad,
+                                int dtype, void* stream) {
+  IFCB_ARG_CHECK(view_ok(dy) && view_ok(dx) && batch > 0 && DT_OK(dtype), "avgpool_bwd: bad argument");
+  IFCB_ARG_CHECK(k >= 1 && k <= 15 && stride >= 1 && pad >= 0 && pad < k, "avgpool_bwd: bad window");
+  const int P = pool_out(dx->H, k, stride, pad), Q = pool_out(dx->W, k, stride, pad);
+  IFCB_ARG_CHECK(dy->C == dx->C && dy->H == P && dy->W == Q, "avgpool_bwd: gradient extent differs");
+  const long long total = (long long)batch * dx->H * dx->W * (dx->C / 8);
+  pool_bwd_kernel<true><<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(dv(dy), nullptr, dv(dx), accumulate, k, stride, pad, P, Q, total,
+                                                                           dtype);
+  IFCB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int ifcb_dilate(const ifcb_view* in, const ifcb_view* out, int batch, int stride_h, int stride_w, void* stream) {
+  IFCB_ARG_CHECK(view_ok(in) && view_ok(out) && batch > 0, "dilate: bad argument");
+  IFCB_ARG_CHECK(stride_h >= 1 && stride_w >= 1 && out->C == in->C && out->H >= (in->H - 1) * stride_h + 1 &&
+                 out->W >= (in->W - 1) * stride_w + 1, "dilate: output too small");
+  const long long total = (long long)batch * in->H * in->W * (in->C / 8);
+  dilate_kernel<<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(dv(in), dv(out), stride_h, stride_w, total);
+  IFCB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int ifcb_nchw_to_nhwc(const float* d_in, int Cin, const ifcb_view* out, int batch, int dtype, void* stream) {
+  IFCB_ARG_CHECK(d_in && view_ok(out) && batch > 0 && Cin > 0 && Cin <= out->C && DT_OK(dtype), "nchw_to_nhwc: bad argument");
+  const long long total = (long long)batch * out->H * out->W;
+  nchw_to_nhwc_kernel<<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(d_in, Cin, dv(out), total, dtype);
+  IFCB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int ifcb_head_train_fwd(const ifcb_view* x, int batch, int dtype, const float* d_dropscale, const float* d_weight,
+                                   const float* d_bias, const int64_t* d_labels, int n_classes, float loss_weight, float* d_pooled,
+                                   float* d_logits, float* d_dlogits, float* d_loss, void* stream) {
+  IFCB_ARG_CHECK(view_ok(x) && batch > 0 && DT_OK(dtype), "head_train_fwd: bad view / batch / dtype");
+  IFCB_ARG_CHECK(d_weight && d_bias && d_labels && d_pooled && d_dlogits && d_loss, "head_train_fwd: null pointer");
+  IFCB_ARG_CHECK(n_classes > 0 && (x->C + n_classes) * 4 <= 200 * 1024, "head_train_fwd: n_classes out of range");
+  IFCB_ARG_CHECK((reinterpret_cast<uintptr_t>(d_weight) & 15) == 0, "head_train_fwd: weight must be 16-byte aligned");
+  const int smem = (x->C + n_classes) * 4;
+  static int attr = 48 * 1024;
+  if (smem > attr) {
+    IFCB_CUDA_CHECK(cudaFuncSetAttribute(head_train_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr = smem;
+  }
+  head_train_fwd_kernel<<<batch, 256, smem, STREAM(stream)>>>(dv(x), d_dropscale, d_weight, d_bias, reinterpret_cast<const long long*>(d_labels),
+                                                               n_classes, batch, loss_weight, d_pooled, d_logits, d_dlogits, d_loss, dtype);
+  IFCB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int ifcb_head_bwd(const ifcb_view* dx, int dx_accumulate, int batch, int dtype, const float* d_dropscale, const float* d_weight,
+                             const float* d_pooled, const float* d_dlogits, int n_classes, float* d_dweight, float* d_dbias, void* stream) {
+  IFCB_ARG_CHECK(view_ok(dx) && batch > 0 && DT_OK(dtype), "head_bwd: bad view / batch / dtype");
+  IFCB_ARG_CHECK(d_weight && d_pooled && d_dlogits && d_dweight && d_dbias && n_classes > 0, "head_bwd: null pointer");
+  const long long nw = (long long)n_classes * dx->C;
+  head_wgrad_kernel<<<(int)((nw + 255) / 256), 256, 0, STREAM(stream)>>>(d_dlogits, d_pooled, batch, n_classes, dx->C, d_dweight, d_dbias);
+  const long long total = (long long)batch * (dx->C / 8);
+  head_dgrad_kernel<<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(d_dlogits, d_weight, d_dropscale, n_classes, dv(dx), dx_accumulate,
+                                                                       total, dtype);
+  IFCB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int ifcb_dropout_scale(float* d_out, int64_t n, float p, uint64_t seed, void* stream) {
+  IFCB_ARG_CHECK(d_out && n > 0 && p >= 0.f && p < 1.f, "dropout_scale: bad argument");
+  dropout_scale_kernel<<<grid_for(n, 256), 256, 0, STREAM(stream)>>>(d_out, n, p, seed);
+  IFCB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int ifcb_adam_step(float* d_param, const float* d_grad, float* d_m, float* d_v, int64_t n, float lr, float beta1,
+                              float beta2, float eps, int step, float grad_scale, void* stream) {
+  IFCB_ARG_CHECK(d_param && d_grad && d_m && d_v && n > 0 && step >= 1, "adam_step: bad argument");
+  IFCB_ARG_CHECK(((reinterpret_cast<uintptr_t>(d_param) | reinterpret_cast<uintptr_t>(d_grad) | reinterpret_cast<uintptr_t>(d_m) |
+                   reinterpret_cast<uintptr_t>(d_v)) & 15) == 0, "adam_step: arenas must be 16-byte aligned");
+  const float bc1 = 1.f - (float)pow((double)beta1, (double)step);
+  const float bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
+  adam_kernel<<<grid_for((n + 3) / 4 + 4, 256), 256, 0, STREAM(stream)>>>(d_param, d_grad, d_m, d_v, n, lr, beta1, beta2, eps, bc1,
+                                                                           bc2_sqrt, grad_scale);
+  IFCB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int ifcb_conv_repack(const float* d_master, int Cout, int taps, int Cin, void* d_wfwd, int Cin_pad, void* d_wdgrad,
+                                int Cout_padk, int dtype, void* stream) {
+  IFCB_ARG_CHECK(d_master && Cout > 0 && taps > 0 && Cin > 0 && DT_OK(dtype), "conv_repack: bad argument");
+  IFCB_ARG_CHECK(!d_wfwd || Cin_pad >= Cin, "conv_repack: Cin_pad < Cin");
+  IFCB_ARG_CHECK(!d_wdgrad || Cout_padk >= Cout, "conv_repack: Cout_padk < Cout");
+  const long long total = (long long)Cout * taps * Cin;
+  conv_repack_kernel<<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(d_master, Cout, taps, Cin, reinterpret_cast<uint16_t*>(d_wfwd), Cin_pad,
+                                                                        reinterpret_cast<uint16_t*>(d_wdgrad), Cout_padk, dtype);
+  IFCB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int ifcb_stem_repack(const float* d_master, int Cout, int taps, int Cin8, float* d_wstem, void* stream) {
+  IFCB_ARG_CHECK(d_master && d_wstem && Cout > 0 && taps > 0 && Cin8 >= 3, "stem_repack: bad argument");
+  const int total = Cout * taps * 3;
+  stem_repack_kernel<<<(total + 255) / 256, 256, 0, STREAM(stream)>>>(d_master, Cout, taps, Cin8, d_wstem);
+  IFCB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}

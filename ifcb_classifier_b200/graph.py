@@ -181,7 +181,7 @@ class PlanBuilder(object):
         return [m['out'] for m in members]
 
     def stem(self, inp, in_kind, H, W, weight, scale, shift, stride, pad, out, affine=None,
-             in_scale=(1, 1, 1), in_shift=(0, 0, 0), name='stem'):
+             in_scale=(1, 1, 1), in_shift=(0, 0, 0), name='stem', relu=True):
         """First conv.  ``affine`` = (a[3], b[3]) with x_c = a_c * g/255 + b_c for the u8 gray
         input (see ``input_affine``); f32 input uses in_scale / in_shift (transform_input)."""
         Co, _, kh, kw = [int(v) for v in weight.shape]
@@ -208,7 +208,7 @@ class PlanBuilder(object):
         d.d_shift = self.dev(shift, torch.float32).data_ptr()
         for c in range(3):
             d.in_scale[c], d.in_shift[c] = float(in_scale[c]), float(in_shift[c])
-        d.d_out, d.out_ld, d.relu = out.ptr, out.ld, 1
+        d.d_out, d.out_ld, d.relu = out.ptr, out.ld, 1 if relu else 0
         d.dtype = self.cdtype
         d.out_pad_h, d.out_pad_w = out.pad
         _lib.check(_lib.lib().ifcb_plan_add_stem(self.handle, C.byref(d)), 'plan_add_stem')

@@ -1,0 +1,581 @@
+"""TRAIN step on the B200 kernels: train-mode forward, backward and Adam for the torchvision
+graphs ``get_namebrand_model`` builds (reference neuston_models.py:22-45) as
+``NeustonModel.training_step`` / ``loss`` / ``configure_optimizers`` run them
+(neuston_models.py:63-86): CrossEntropyLoss (+ 0.4 * aux loss for Inception-v3), Adam(lr=1e-3),
+per-rank BatchNorm statistics, gradient mean over ranks (Lightning DDP, neuston_net.py:101-107).
+
+torch supplies device memory, streams and ``torch.distributed``; every kernel on the step goes
+through the C ABI (``_lib``): tcgen05 implicit-GEMM convolutions for the forward and the data
+gradient (the same kernel, fed the flipped/transposed filter), the tcgen05 weight-gradient kernel,
+and the streaming kernels of ``csrc/train_ops.cu``.
+
+Layout.  Parameters live in ONE flat fp32 arena (``params``) with a parallel gradient arena and
+the two Adam moment arenas, so that the optimizer is a single launch and the gradient exchange a
+handful of NCCL all-reduces over contiguous buckets launched while the backward pass is still
+running.  Conv master weights are stored ``[Cout, kh*kw, Cin]`` (the layout the weight-gradient
+kernel accumulates into); ``state_dict()`` converts back to torchvision's ``[Cout, Cin, kh, kw]``.
+Activations are NHWC 16-bit (bf16 by default for training); for each conv+BN unit both the conv
+output ``z`` and the activation ``a`` are kept for the backward pass.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import ViewDesc, WgradDesc, IFCB_STEM_IN_F32_NCHW
+from .graph import PlanBuilder, View, RESNET_CFG
+
+
+def _vd(v):
+    d = ViewDesc()
+    d.d, d.ld, d.C, d.H, d.W = v.ptr, v.ld, v.C, v.H, v.W
+    d.pad_h, d.pad_w = v.pad
+    return d
+
+
+def build_dgrad(bp, dy, dx, Co, Ci, kh, kw, stride, pad, accumulate, name='dgrad'):
+    """Appends the data-gradient of a Conv2d(Ci -> Co, kh x kw, stride, pad) to plan ``bp``:
+    dx (=|+=) conv_transpose(dy, W).  The transposed conv is the forward tcgen05 kernel run at stride 1
+    over the (zero-dilated, for stride > 1) output gradient with padding k-1-pad and the operand
+    ``ifcb_conv_repack`` writes (taps reversed, Cin/Cout swapped).  ``dy`` / ``dx``: gradient Views
+    (no border).  Returns dict(run=[closures], weight=<16-bit operand tensor>, Cin_pad=<its channel padding>)."""
+    B, lib = bp.batch_cap, _lib.lib()
+    run = []
+    stream = lambda: C.c_void_p(torch.cuda.current_stream(bp.device).cuda_stream)
+    if tuple(stride) != (1, 1):
+        Hd, Wd = dx.H + 2 * pad[0] - kh + 1, dx.W + 2 * pad[1] - kw + 1
+        src = View(torch.zeros((B, Hd, Wd, Co), dtype=bp.tdtype, device=bp.device))
+        bp.keep.append(src.t)
+        sd_, dd_ = _vd(dy), _vd(src)
+        run.append(lambda: _lib.check(lib.ifcb_dilate(C.byref(sd_), C.byref(dd_), B, stride[0], stride[1], stream()), 'dilate'))
+    else:
+        src = dy
+    li = len(bp.layer_names)
+    wflip = torch.zeros((Ci, Co, kh, kw))                           # placeholder: ifcb_conv_repack fills the operand
+    bp.conv(src, [dict(weight=wflip, scale=torch.ones(Ci), shift=torch.zeros(Ci), relu=False, out=dx)], (1, 1),
+            (kh - 1 - pad[0], kw - 1 - pad[1]), residual=dx if accumulate else None, name=name)
+    wdg = bp.keep[-3]
+    cin_pad = _lib.conv_geometry(Co, Ci, kh, kw)['Cin_pad']
+    assert wdg.shape[1] == kh * kw * cin_pad, wdg.shape
+    run.append(lambda: bp.run(B, li, li + 1))
+    return dict(run=run, weight=wdg, Cin_pad=cin_pad)
+
+
+class _Param(object):
+    """A slice of the flat parameter / gradient arenas."""
+
+    def __init__(self, net, name, off, shape, kind, meta=None):
+        self.net, self.name, self.off, self.shape, self.kind, self.meta = net, name, off, tuple(shape), kind, meta or {}
+        self.n = 1
+        for s in shape:
+            self.n *= int(s)
+
+    @property
+    def w(self): return self.net.params[self.off:self.off + self.n].view(self.shape)
+
+    @property
+    def g(self): return self.net.grads[self.off:self.off + self.n].view(self.shape)
+
+    @property
+    def wptr(self): return self.net.params.data_ptr() + 4 * self.off
+
+    @property
+    def gptr(self): return self.net.grads.data_ptr() + 4 * self.off
+
+
+class TrainNet(object):
+    """``arch`` in train mode for a fixed per-GPU batch.
+
+    ``step(x, labels)`` = one ``training_step`` + ``backward`` + ``optimizer.step``:
+    x float32 [B,3,R,R] (what the reference's DataLoader yields), labels int64 [B]; returns the
+    loss as a 0-dim device tensor (no host sync).  ``forward_backward`` stops before Adam.
+    """
+
+    def __init__(self, arch, state_dict, batch, device='cuda', dtype='bf16', lr=1e-3, betas=(0.9, 0.999), eps=1e-8,
+                 dropout=True, seed=0, R=None, bucket_mb=32, keep_dy=False):
+        self.arch, self.batch, self.device = arch, int(batch), torch.device(device)
+        if self.device.type != 'cuda':
+            raise RuntimeError('TrainNet: a CUDA device is required (there is no CPU path)')
+        self.R = R or (299 if arch == 'inception_v3' else 224)
+        self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
+        self.dropout, self.seed = bool(dropout), int(seed)
+        self.keep_dy = bool(keep_dy)        # tests: keep d(activation) next to d(conv output) instead of overwriting it
+        self.step_count = 0
+        self.lib = _lib.lib()
+        sd = {k: v.detach().cpu() for k, v in state_dict.items()}
+        self.sd_keys = list(sd.keys())
+        self.fp = PlanBuilder(batch, self.device, dtype)       # forward convs (+ stem)
+        self.bp = PlanBuilder(batch, self.device, dtype)       # data-gradient convs
+        self.cdtype, self.tdtype = self.fp.cdtype, self.fp.tdtype
+        total = sum(((v.numel() * (3 if v.dim() == 4 and v.shape[1] == 3 else 1) + 63) // 64) * 64
+                    for v in sd.values() if v.is_floating_point())
+        self.params = torch.zeros(total, dtype=torch.float32, device=self.device)
+        self._cursor = 0
+        self.plist = []                 # _Param in forward order
+        self.buffers = {}               # running_mean / running_var / num_batches_tracked
+        self.records = []               # forward records, replayed backwards by _finalize
+        self.fwd = []                   # closures
+        self.bwd = []                   # closures, already in execution order
+        self.repacks = []               # closures refreshing the 16-bit operands from the arena
+        self.keep = []
+        self._grad_t = {}               # id(activation tensor) -> gradient tensor (no border)
+        self.inp = torch.zeros((batch, 3, self.R, self.R), dtype=torch.float32, device=self.device)
+        self.labels = torch.zeros((batch,), dtype=torch.int64, device=self.device)
+        self.loss = torch.zeros((2,), dtype=torch.float32, device=self.device)     # [main + aux (weighted), unused]
+        self.acc = torch.zeros((2 * 2048,), dtype=torch.float64, device=self.device)
+        if arch == 'inception_v3':
+            _build_inception_train(self, sd)
+        elif arch in RESNET_CFG:
+            _build_resnet_train(self, sd, arch)
+        else:
+            raise KeyError('model unknown!')
+        self.n_params = self._cursor
+        self.params = self.params[:self.n_params]
+        self.grads = torch.zeros_like(self.params)
+        self.m = torch.zeros_like(self.params)
+        self.v = torch.zeros_like(self.params)
+        self._finalize(int(bucket_mb) << 20)
+        self.repack()
+
+    # ---- plumbing ---------------------------------------------------------------------------
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _call(self, name, *args):
+        _lib.check(getattr(self.lib, name)(*args), name)
+
+    def _param(self, name, init, kind, meta=None):
+        n = init.numel()
+        off = self._cursor
+        assert off + n <= self.params.numel(), 'parameter arena overflow'
+        self.params[off:off + n].copy_(init.reshape(-1).float())
+        self._cursor = ((off + n + 3) // 4) * 4                 # 16-byte aligned slices
+        p = _Param(self, name, off, init.shape, kind, meta)
+        self.plist.append(p)
+        return p
+
+    def _f32(self, n, fill=0.0):
+        t = torch.full((n,), fill, dtype=torch.float32, device=self.device)
+        self.keep.append(t)
+        return t
+
+    def alloc(self, H, W, Cc, pad=(0, 0)):
+        return self.fp.alloc(H, W, Cc, pad)
+
+    def grad_of(self, v):
+        """Gradient view matching activation view ``v`` (gradient tensors carry no border)."""
+        g = self._grad_t.get(id(v.t))
+        if g is None:
+            g = torch.zeros((self.batch, v.H, v.W, v.t.shape[3]), dtype=self.tdtype, device=self.device)
+            self._grad_t[id(v.t)] = g
+            self.keep.append(v.t)
+        return View(g, v.c0, v.c1)
+
+    # ---- graph construction (forward order) -------------------------------------------------------
+    def conv_bn(self, x, sd, conv, bn, stride=(1, 1), pad=(0, 0), relu=True, residual=None, out=None, out_pad=(0, 0),
+                eps=1e-5, stem=False):
+        """Conv2d(bias=False) -> BatchNorm2d(train) [-> + residual] [-> ReLU]; returns the activation view."""
+        w = sd[conv + '.weight'].float()
+        Co, Ci, kh, kw = [int(s) for s in w.shape]
+        H, W = (self.R, self.R) if stem else (x.H, x.W)
+        P = (H + 2 * pad[0] - kh) // stride[0] + 1
+        Q = (W + 2 * pad[1] - kw) // stride[1] + 1
+        if out is None:
+            out = self.alloc(P, Q, Co, out_pad)
+        z = self.alloc(P, Q, Co)
+        ci_m = 8 if stem else Ci
+        master = torch.zeros((Co, kh * kw, ci_m))
+        master[:, :, :Ci] = w.permute(0, 2, 3, 1).reshape(Co, kh * kw, Ci)
+        pw = self._param(conv + '.weight', master, 'conv', dict(Ci=Ci, kh=kh, kw=kw))
+        pg = self._param(bn + '.weight', sd[bn + '.weight'], 'vec')
+        pb = self._param(bn + '.bias', sd[bn + '.bias'], 'vec')
+        rm = self._f32(Co); rm.copy_(sd[bn + '.running_mean'])
+        rv = self._f32(Co); rv.copy_(sd[bn + '.running_var'])
+        self.buffers[bn + '.running_mean'], self.buffers[bn + '.running_var'] = rm, rv
+        self.buffers[bn + '.num_batches_tracked'] = sd.get(bn + '.num_batches_tracked', torch.zeros((), dtype=torch.long)).clone()
+        mean, invstd = self._f32(Co), self._f32(Co)
+        ones, zeros = torch.ones(Co), torch.zeros(Co)
+        li = len(self.fp.layer_names)
+        if stem:
+            self.fp.stem(self.inp, IFCB_STEM_IN_F32_NCHW, H, W, w, ones, zeros, stride[0], pad[0], z, name=conv, relu=False)
+            wstem = self.fp.keep[-3]                                 # the [taps*3, Co] fp32 operand pb.stem uploaded
+            assert wstem.shape == (kh * kw * 3, Co)
+            x8 = self.alloc(H, W, 8)
+            self.repacks.append(lambda: self._call('ifcb_stem_repack', pw.wptr, Co, kh * kw, 8, wstem.data_ptr(), self._stream()))
+            wf = None
+        else:
+            self.fp.conv(x, [dict(weight=w, scale=ones, shift=zeros, relu=False, out=z)], stride, pad, name=conv)
+            wf = self.fp.keep[-3]                                    # packed [Cout_pad, K_pad] 16-bit operand
+            x8 = None
+        zd, od = _vd(z), _vd(out)
+        rd = _vd(residual) if residual is not None else None
+        B, dt = self.batch, self.cdtype
+        bn_key = bn + '.num_batches_tracked'
+
+        def fwd():
+            self.fp.run(B, li, li + 1)
+            self._call('ifcb_bn_stats', C.byref(zd), B, dt, eps, 0.1, self.acc.data_ptr(), mean.data_ptr(), invstd.data_ptr(),
+                       rm.data_ptr(), rv.data_ptr(), self._stream())
+            self._call('ifcb_bn_apply', C.byref(zd), C.byref(od), C.byref(rd) if rd is not None else None, B, dt, mean.data_ptr(),
+                       invstd.data_ptr(), pg.wptr, pb.wptr, 1 if relu else 0, self._stream())
+            self.buffers[bn_key] += 1
+        self.fwd.append(fwd)
+        self.records.append(dict(kind='conv_bn', x=x, x8=x8, z=z, out=out, residual=residual, relu=relu, stride=stride, pad=pad,
+                                 pw=pw, pg=pg, pb=pb, mean=mean, invstd=invstd, wf=wf, Co=Co, Ci=Ci, kh=kh, kw=kw, stem=stem,
+                                 H=H, W=W, name=conv))
+        return out
+
+    def maxpool(self, x, k, stride, pad, out=None, out_pad=(0, 0)):
+        P = (x.H + 2 * pad - k) // stride + 1
+        Q = (x.W + 2 * pad - k) // stride + 1
+        if out is None:
+            out = self.alloc(P, Q, x.C, out_pad)
+        idx = torch.zeros((self.batch, P, Q, x.C), dtype=torch.uint8, device=self.device)
+        self.keep.append(idx)
+        xd, od, B, dt = _vd(x), _vd(out), self.batch, self.cdtype
+        self.fwd.append(lambda: self._call('ifcb_maxpool_fwd_train', C.byref(xd), C.byref(od), idx.data_ptr(), B, k, stride, pad, dt,
+                                           self._stream()))
+        self.records.append(dict(kind='maxpool', x=x, out=out, idx=idx, k=k, stride=stride, pad=pad))
+        return out
+
+    def avgpool(self, x, k, stride, pad, out=None):
+        P = (x.H + 2 * pad - k) // stride + 1
+        Q = (x.W + 2 * pad - k) // stride + 1
+        if out is None:
+            out = self.alloc(P, Q, x.C)
+        xd, od, B, dt = _vd(x), _vd(out), self.batch, self.cdtype
+        self.fwd.append(lambda: self._call('ifcb_avgpool_fwd', C.byref(xd), C.byref(od), B, k, stride, pad, dt, self._stream()))
+        self.records.append(dict(kind='avgpool', x=x, out=out, k=k, stride=stride, pad=pad))
+        return out
+
+    def head(self, x, sd, fc, loss_weight=1.0, dropout_p=0.0, which='main'):
+        """adaptive_avg_pool2d(1) -> dropout -> Linear -> loss_weight * CrossEntropyLoss."""
+        Wt, bias = sd[fc + '.weight'].float(), sd[fc + '.bias'].float()
+        n_classes, Cc = int(Wt.shape[0]), int(Wt.shape[1])
+        assert Cc == x.C
+        pw = self._param(fc + '.weight', Wt, 'fc')
+        pb = self._param(fc + '.bias', bias, 'vec')
+        B, dt = self.batch, self.cdtype
+        pooled = self._f32(B * Cc)
+        logits = self._f32(B * n_classes)
+        dlogits = self._f32(B * n_classes)
+        drop = self._f32(B * Cc, 1.0) if dropout_p > 0 else None
+        xd = _vd(x)
+        rec = dict(kind='head', x=x, pw=pw, pb=pb, pooled=pooled, dlogits=dlogits, logits=logits, drop=drop, n_classes=n_classes,
+                   dropout_p=dropout_p, which=which)
+
+        def fwd():
+            if drop is not None and self.dropout and not rec.get('fixed_mask'):
+                seed = (self.seed * 1000003 + self.step_count * 7919 + (1 if which == 'aux' else 0)) & ((1 << 63) - 1)
+                self._call('ifcb_dropout_scale', drop.data_ptr(), B * Cc, dropout_p, seed, self._stream())
+            use_drop = drop is not None and (self.dropout or rec.get('fixed_mask'))
+            self._call('ifcb_head_train_fwd', C.byref(xd), B, dt, drop.data_ptr() if use_drop else None, pw.wptr, pb.wptr,
+                       self.labels.data_ptr(), n_classes, loss_weight, pooled.data_ptr(), logits.data_ptr(), dlogits.data_ptr(),
+                       self.loss.data_ptr(), self._stream())
+        self.fwd.append(fwd)
+        self.records.append(rec)
+        if which == 'main':
+            self.logits = logits.view(B, n_classes)
+            self.n_classes = n_classes
+            self.main_head = rec
+        return rec
+
+    # ---- backward construction (reverse order) ------------------------------------------------------
+    def _finalize(self, bucket_bytes):
+        B, dt = self.batch, self.cdtype
+        written = set()
+
+        def claim(v):
+            """True if a gradient was already written into v's tensor slice (=> accumulate)."""
+            key = (id(v.t), v.c0, v.c1)
+            for (t, a, b) in written:
+                if t == key[0] and (a, b) != (key[1], key[2]) and a < key[2] and key[1] < b:
+                    raise RuntimeError('partially overlapping gradient consumers are not supported')
+            acc = key in written
+            written.add(key)
+            return acc
+
+        # gradient buckets for the all-reduce: contiguous arena ranges, closed from the END of the arena
+        # (backward produces gradients in reverse parameter order)
+        self.bucket_marks = []          # (index into self.bwd after which [lo, hi) is complete, lo, hi)
+        hi = self.n_params
+        for rec in reversed(self.records):
+            kind = rec['kind']
+            if kind == 'head':
+                x = rec['x']
+                dx = self.grad_of(x)
+                acc = claim(x)
+                dxd = _vd(dx)
+                use = rec
+
+                def bwd(rec=rec, dxd=dxd, acc=acc):
+                    use_drop = rec['drop'] is not None and (self.dropout or rec.get('fixed_mask'))
+                    self._call('ifcb_head_bwd', C.byref(dxd), 1 if acc else 0, B, dt, rec['drop'].data_ptr() if use_drop else None,
+                               rec['pw'].wptr, rec['pooled'].data_ptr(), rec['dlogits'].data_ptr(), rec['n_classes'],
+                               rec['pw'].gptr, rec['pb'].gptr, self._stream())
+                self.bwd.append(bwd)
+                lo = rec['pw'].off
+            elif kind in ('maxpool', 'avgpool'):
+                x, out = rec['x'], rec['out']
+                dy, dx = self.grad_of(out), self.grad_of(x)
+                acc = claim(x)
+                dyd, dxd = _vd(dy), _vd(dx)
+                k, s, p = rec['k'], rec['stride'], rec['pad']
+                if kind == 'maxpool':
+                    idx = rec['idx']
+                    self.bwd.append(lambda dyd=dyd, dxd=dxd, idx=idx, acc=acc, k=k, s=s, p=p: self._call(
+                        'ifcb_maxpool_bwd', C.byref(dyd), idx.data_ptr(), C.byref(dxd), 1 if acc else 0, B, k, s, p, dt, self._stream()))
+                else:
+                    self.bwd.append(lambda dyd=dyd, dxd=dxd, acc=acc, k=k, s=s, p=p: self._call(
+                        'ifcb_avgpool_bwd', C.byref(dyd), C.byref(dxd), 1 if acc else 0, B, k, s, p, dt, self._stream()))
+                lo = None
+            else:
+                lo = self._finalize_conv(rec, claim)
+            if lo is not None and (hi - lo) * 4 >= bucket_bytes:
+                self.bucket_marks.append((len(self.bwd), lo, hi))
+                hi = lo
+        if hi > 0:
+            self.bucket_marks.append((len(self.bwd), 0, hi))
+
+    def _finalize_conv(self, rec, claim):
+        B, dt = self.batch, self.cdtype
+        x, z, out, residual = rec['x'], rec['z'], rec['out'], rec['residual']
+        Co, Ci, kh, kw = rec['Co'], rec['Ci'], rec['kh'], rec['kw']
+        stride, pad = rec['stride'], rec['pad']
+        dy = self.grad_of(out)
+        dyd, zd, od = _vd(dy), _vd(z), _vd(out)
+        if self.keep_dy:
+            dz = View(torch.zeros((B, out.H, out.W, Co), dtype=self.tdtype, device=self.device))
+            self.keep.append(dz.t)
+        else:
+            dz = dy                                                  # in place
+        dzd = _vd(dz)
+        rec['dy'], rec['dz'] = dy, dz
+        dres_d, res_acc = None, False
+        if residual is not None:
+            dres = self.grad_of(residual)
+            res_acc = claim(residual)
+            dres_d = _vd(dres)
+        pw, pg, pb, mean, invstd = rec['pw'], rec['pg'], rec['pb'], rec['mean'], rec['invstd']
+        relu = rec['relu']
+
+        def bn_bwd():
+            self._call('ifcb_bn_backward', C.byref(dyd), C.byref(od) if relu else None, C.byref(zd),
+                       C.byref(dzd), C.byref(dres_d) if dres_d is not None else None, 1 if res_acc else 0, B, dt, mean.data_ptr(),
+                       invstd.data_ptr(), pg.wptr, self.acc.data_ptr(), pg.gptr, pb.gptr, self._stream())
+        self.bwd.append(bn_bwd)
+        # weight gradient: dW[co, tap, ci] += sum dz * x
+        wd = WgradDesc()
+        xin = rec['x8'] if rec['stem'] else x
+        wd.d_in, wd.in_ld, wd.Cin = xin.ptr, xin.ld, xin.C
+        wd.batch, wd.H, wd.W = B, rec['H'], rec['W']
+        wd.in_pad_h, wd.in_pad_w = xin.pad
+        wd.kh, wd.kw, wd.stride_h, wd.stride_w, wd.pad_h, wd.pad_w = kh, kw, stride[0], stride[1], pad[0], pad[1]
+        wd.d_dout, wd.dout_ld, wd.Cout = dz.ptr, dz.ld, Co
+        wd.dtype = dt
+        if rec['stem']:
+            x8d = _vd(xin)
+
+            def wgrad():
+                self._call('ifcb_nchw_to_nhwc', self.inp.data_ptr(), 3, C.byref(x8d), B, dt, self._stream())
+                wd.d_dweight = pw.gptr
+                self._call('ifcb_conv_wgrad', C.byref(wd), self._stream())
+            self.bwd.append(wgrad)
+            return pw.off
+
+        def wgrad():
+            wd.d_dweight = pw.gptr
+            self._call('ifcb_conv_wgrad', C.byref(wd), self._stream())
+        self.bwd.append(wgrad)
+        # data gradient: stride-1 conv of (dilated) dz with the flipped, transposed filter
+        dx = self.grad_of(x)
+        acc = claim(x)
+        dg = build_dgrad(self.bp, dz, dx, Co, Ci, kh, kw, stride, pad, acc, name='dgrad.' + rec['name'])
+        self.bwd.extend(dg['run'])
+        wdg = dg['weight']
+        geo_f = _lib.conv_geometry(Ci, Co, kh, kw)
+        wf = rec['wf']
+        assert wf.shape[1] == kh * kw * geo_f['Cin_pad'], wf.shape
+        self.repacks.append(lambda: self._call('ifcb_conv_repack', pw.wptr, Co, kh * kw, Ci, wf.data_ptr(), geo_f['Cin_pad'],
+                                               wdg.data_ptr(), dg['Cin_pad'], dt, self._stream()))
+        return pw.off
+
+    # ---- execution ---------------------------------------------------------------------------------
+    def repack(self):
+        """Refresh every 16-bit tensor-core operand (forward + data-gradient) from the fp32 arena."""
+        for r in self.repacks:
+            r()
+
+    def forward(self):
+        self._call('ifcb_memset_zero', self.loss.data_ptr(), 8, self._stream())
+        for f in self.fwd:
+            f()
+
+    def backward(self, allreduce=None):
+        """Runs the backward pass; ``allreduce(lo, hi)`` is called as soon as gradient range [lo, hi) is final."""
+        self._call('ifcb_memset_zero', self.grads.data_ptr(), 4 * self.n_params, self._stream())
+        marks = {m[0]: (m[1], m[2]) for m in self.bucket_marks}
+        for i, b in enumerate(self.bwd):
+            b()
+            if allreduce is not None and (i + 1) in marks:
+                allreduce(*marks[i + 1])
+
+    def forward_backward(self, x=None, labels=None, allreduce=None):
+        if x is not None:
+            self.inp.copy_(x)
+        if labels is not None:
+            self.labels.copy_(labels)
+        self.forward()
+        self.backward(allreduce)
+        return self.loss[0]
+
+    def adam(self, grad_scale=1.0):
+        self.step_count += 1
+        self._call('ifcb_adam_step', self.params.data_ptr(), self.grads.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
+                   self.n_params, self.lr, self.betas[0], self.betas[1], self.eps, self.step_count, float(grad_scale), self._stream())
+        self.repack()
+
+    def step(self, x=None, labels=None):
+        """training_step + backward + (gradient mean over ranks) + Adam.  Returns the loss (device scalar)."""
+        import torch.distributed as dist
+        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        works = []
+        hook = None
+        if world > 1:
+            def hook(lo, hi):
+                works.append(dist.all_reduce(self.grads[lo:hi], op=dist.ReduceOp.SUM, async_op=True))
+        loss = self.forward_backward(x, labels, hook)
+        for w in works:
+            w.wait()
+        self.adam(1.0 / world)
+        return loss
+
+    # ---- parameter import / export (torchvision layout) -----------------------------------------------
+    def _export(self, arena):
+        out = {}
+        for p in self.plist:
+            t = arena[p.off:p.off + p.n].view(p.shape)
+            if p.kind == 'conv':
+                Ci, kh, kw = p.meta['Ci'], p.meta['kh'], p.meta['kw']
+                t = t[:, :, :Ci].reshape(p.shape[0], kh, kw, Ci).permute(0, 3, 1, 2)
+            out[p.name] = t.detach().clone().contiguous()
+        return out
+
+    def state_dict(self):
+        out = self._export(self.params)
+        for k, v in self.buffers.items():
+            out[k] = v.detach().clone()
+        return {k: out[k].cpu() for k in self.sd_keys if k in out}
+
+    def grad_dict(self):
+        return self._export(self.grads)
+
+    def launches_per_step(self):
+        return None
+
+
+# =====================================================================================================
+# graphs (train mode; same module order / names as torchvision so that parameters line up)
+# =====================================================================================================
+def _build_resnet_train(tn, sd, arch):
+    kind, layers = RESNET_CFG[arch]
+    a = tn.conv_bn(None, sd, 'conv1', 'bn1', (2, 2), (3, 3), stem=True)
+    x = tn.maxpool(a, 3, 2, 1)
+    for li, nb in enumerate(layers):
+        for bi in range(nb):
+            pre = 'layer%d.%d' % (li + 1, bi)
+            s = 2 if (li > 0 and bi == 0) else 1
+            identity = x
+            if (pre + '.downsample.0.weight') in sd:
+                identity = tn.conv_bn(x, sd, pre + '.downsample.0', pre + '.downsample.1', (s, s), (0, 0), relu=False)
+            if kind == 'basic':
+                t = tn.conv_bn(x, sd, pre + '.conv1', pre + '.bn1', (s, s), (1, 1))
+                x = tn.conv_bn(t, sd, pre + '.conv2', pre + '.bn2', (1, 1), (1, 1), residual=identity)
+            else:
+                t = tn.conv_bn(x, sd, pre + '.conv1', pre + '.bn1')
+                t = tn.conv_bn(t, sd, pre + '.conv2', pre + '.bn2', (s, s), (1, 1))
+                x = tn.conv_bn(t, sd, pre + '.conv3', pre + '.bn3', residual=identity)
+    tn.head(x, sd, 'fc')
+
+
+def _build_inception_train(tn, sd):
+    eps = 1e-3
+
+    def cb(x, prefix, stride=(1, 1), pad=(0, 0), out=None, stem=False):
+        return tn.conv_bn(x, sd, prefix + '.conv', prefix + '.bn', stride, pad, out=out, eps=eps, stem=stem)
+
+    a = cb(None, 'Conv2d_1a_3x3', (2, 2), stem=True)
+    a = cb(a, 'Conv2d_2a_3x3')
+    a = cb(a, 'Conv2d_2b_3x3', pad=(1, 1))
+    a = tn.maxpool(a, 3, 2, 0)
+    a = cb(a, 'Conv2d_3b_1x1')
+    a = cb(a, 'Conv2d_4a_3x3')
+    x = tn.maxpool(a, 3, 2, 0)
+    for blk, pf in (('Mixed_5b', 32), ('Mixed_5c', 64), ('Mixed_5d', 64)):
+        H = x.H
+        out = tn.alloc(H, H, 224 + pf)
+        cb(x, blk + '.branch1x1', out=out.slice(0, 64))
+        t = cb(x, blk + '.branch5x5_1')
+        cb(t, blk + '.branch5x5_2', pad=(2, 2), out=out.slice(64, 128))
+        t = cb(x, blk + '.branch3x3dbl_1')
+        t = cb(t, blk + '.branch3x3dbl_2', pad=(1, 1))
+        cb(t, blk + '.branch3x3dbl_3', pad=(1, 1), out=out.slice(128, 224))
+        t = tn.avgpool(x, 3, 1, 1)
+        cb(t, blk + '.branch_pool', out=out.slice(224, 224 + pf))
+        x = out
+    blk = 'Mixed_6a'
+    H2 = (x.H - 3) // 2 + 1
+    out = tn.alloc(H2, H2, 768)
+    cb(x, blk + '.branch3x3', (2, 2), out=out.slice(0, 384))
+    t = cb(x, blk + '.branch3x3dbl_1')
+    t = cb(t, blk + '.branch3x3dbl_2', pad=(1, 1))
+    cb(t, blk + '.branch3x3dbl_3', (2, 2), out=out.slice(384, 480))
+    tn.maxpool(x, 3, 2, 0, out=out.slice(480, 768))
+    x = out
+    for blk in ('Mixed_6b', 'Mixed_6c', 'Mixed_6d', 'Mixed_6e'):
+        H = x.H
+        out = tn.alloc(H, H, 768)
+        cb(x, blk + '.branch1x1', out=out.slice(0, 192))
+        t = cb(x, blk + '.branch7x7_1')
+        t = cb(t, blk + '.branch7x7_2', pad=(0, 3))
+        cb(t, blk + '.branch7x7_3', pad=(3, 0), out=out.slice(192, 384))
+        t = cb(x, blk + '.branch7x7dbl_1')
+        t = cb(t, blk + '.branch7x7dbl_2', pad=(3, 0))
+        t = cb(t, blk + '.branch7x7dbl_3', pad=(0, 3))
+        t = cb(t, blk + '.branch7x7dbl_4', pad=(3, 0))
+        cb(t, blk + '.branch7x7dbl_5', pad=(0, 3), out=out.slice(384, 576))
+        t = tn.avgpool(x, 3, 1, 1)
+        cb(t, blk + '.branch_pool', out=out.slice(576, 768))
+        x = out
+    # AuxLogits (train mode only, inception.py:130-134, InceptionAux :361-395)
+    if 'AuxLogits.conv0.conv.weight' in sd:
+        t = tn.avgpool(x, 5, 3, 0)
+        t = cb(t, 'AuxLogits.conv0')
+        t = cb(t, 'AuxLogits.conv1')
+        tn.head(t, sd, 'AuxLogits.fc', loss_weight=0.4, which='aux')
+    blk = 'Mixed_7a'
+    H2 = (x.H - 3) // 2 + 1
+    out = tn.alloc(H2, H2, 1280)
+    t = cb(x, blk + '.branch3x3_1')
+    cb(t, blk + '.branch3x3_2', (2, 2), out=out.slice(0, 320))
+    t = cb(x, blk + '.branch7x7x3_1')
+    t = cb(t, blk + '.branch7x7x3_2', pad=(0, 3))
+    t = cb(t, blk + '.branch7x7x3_3', pad=(3, 0))
+    cb(t, blk + '.branch7x7x3_4', (2, 2), out=out.slice(320, 512))
+    tn.maxpool(x, 3, 2, 0, out=out.slice(512, 1280))
+    x = out
+    for blk in ('Mixed_7b', 'Mixed_7c'):
+        H = x.H
+        out = tn.alloc(H, H, 2048)
+        cb(x, blk + '.branch1x1', out=out.slice(0, 320))
+        t = cb(x, blk + '.branch3x3_1')
+        cb(t, blk + '.branch3x3_2a', pad=(0, 1), out=out.slice(320, 704))
+        cb(t, blk + '.branch3x3_2b', pad=(1, 0), out=out.slice(704, 1088))
+        t = cb(x, blk + '.branch3x3dbl_1')
+        t = cb(t, blk + '.branch3x3dbl_2', pad=(1, 1))
+        cb(t, blk + '.branch3x3dbl_3a', pad=(0, 1), out=out.slice(1088, 1472))
+        cb(t, blk + '.branch3x3dbl_3b', pad=(1, 0), out=out.slice(1472, 1856))
+        t = tn.avgpool(x, 3, 1, 1)
+        cb(t, blk + '.branch_pool', out=out.slice(1856, 2048))
+        x = out
+    tn.head(x, sd, 'fc', dropout_p=0.5)

@@ -173,7 +173,8 @@ int ifcb_conv_geometry(int Cin, int Cout, int kh, int kw, int tile_n_hint,
 
 /* Conv2d weight gradient on the tensor cores (pixel axis = GEMM K, MN-major operands):
  *   dW[co, r, s, ci] += sum_{n,p,q} dout[n,p,q,co] * in[n, p*stride_h + r - pad_h, q*stride_w + s - pad_w, ci]
- *   d_in       NHWC 16-bit view [batch, H, W, Cin] (no border), pixel stride in_ld
+ *   d_in       NHWC 16-bit view, logical extent [batch, H, W, Cin], pixel stride in_ld, stored with a
+ *              zero border of in_pad_h / in_pad_w pixels (d_in = first border pixel), as ifcb_conv_desc
  *   d_dout     NHWC 16-bit view [batch, P, Q, Cout], pixel stride dout_ld
  *   d_dweight  float32 [Cout, kh*kw, Cin]; the kernel ACCUMULATES (split-K over CTAs with
  *              red.global.add.f32): zero it first for a plain gradient
@@ -187,8 +188,97 @@ typedef struct {
   int32_t dout_ld, Cout;
   float* d_dweight;
   int32_t dtype; /* IFCB_ACT_* of d_in and d_dout */
+  int32_t in_pad_h, in_pad_w;
 } ifcb_wgrad_desc;
 int ifcb_conv_wgrad(const ifcb_wgrad_desc* desc, void* stream);
+
+/* A channel slice of an NHWC 16-bit activation (or gradient) tensor, as the Python host's
+ * graph.View: logical extent [batch, H, W, C], stored with a zero border of pad_h / pad_w pixels
+ * (physical [batch, H+2*pad_h, W+2*pad_w, ld]); d = first (border) pixel of the slice.
+ * Kernels only ever write interior pixels. */
+typedef struct {
+  void* d;
+  int32_t ld, C;
+  int32_t H, W;
+  int32_t pad_h, pad_w;
+} ifcb_view;
+
+/* cudaMemsetAsync(d, 0, bytes) on `stream` (gradient arena / accumulators at step start). */
+int ifcb_memset_zero(void* d, int64_t bytes, void* stream);
+
+/* BatchNorm2d, train mode (torch.nn.BatchNorm2d.forward with track_running_stats: batch mean and
+ * BIASED variance normalise; running_mean/var updated with `momentum`, running_var with the
+ * UNBIASED variance).  Split in two launches so that the conv output z is read twice and the
+ * activation written once:
+ *   ifcb_bn_stats   z -> d_mean[C], d_invstd[C] = 1/sqrt(var+eps)  (+ running stats when non-NULL)
+ *                   d_acc: 2*C float64 accumulators, zero on entry, zero again on exit
+ *   ifcb_bn_apply   out = act(gamma*(z-mean)*invstd + beta (+ residual)); relu: 0/1
+ *                   (ResNet: bn3 + identity + ReLU, resnet.py Bottleneck/BasicBlock.forward) */
+int ifcb_bn_stats(const ifcb_view* z, int batch, int dtype, float eps, float momentum, double* d_acc,
+                  float* d_mean, float* d_invstd, float* d_running_mean, float* d_running_var, void* stream);
+int ifcb_bn_apply(const ifcb_view* z, const ifcb_view* out, const ifcb_view* residual, int batch, int dtype,
+                  const float* d_mean, const float* d_invstd, const float* d_gamma, const float* d_beta,
+                  int relu, void* stream);
+/* Backward of (BN train -> [+residual] -> [ReLU]) -- autograd's threshold_backward +
+ * native_batch_norm_backward:
+ *   dy' = dy * [a > 0]            (a = the forward output; NULL: no ReLU)
+ *   dz  = gamma*invstd*(dy' - mean(dy') - xhat*mean(dy'*xhat)),  xhat = (z-mean)*invstd
+ *   d_dgamma[C] += sum(dy'*xhat), d_dbeta[C] += sum(dy')
+ *   dres (optional, the residual branch's gradient) = or += dy'
+ * dz may alias dy.  d_acc: 2*C float64 scratch. */
+int ifcb_bn_backward(const ifcb_view* dy, const ifcb_view* a, const ifcb_view* z, const ifcb_view* dz,
+                     const ifcb_view* dres, int dres_accumulate, int batch, int dtype,
+                     const float* d_mean, const float* d_invstd, const float* d_gamma, double* d_acc,
+                     float* d_dgamma, float* d_dbeta, void* stream);
+
+/* Pooling for the TRAIN step.  max: F.max_pool2d forward recording the winning tap (first maximum
+ * in row-major window order, uint8 [batch,P,Q,C]) and its backward; avg: F.avg_pool2d with
+ * count_include_pad=True (divisor k*k) and its backward.  Backward kernels gather (no atomics) and
+ * either write dx or add to it (`accumulate`). */
+int ifcb_maxpool_fwd_train(const ifcb_view* x, const ifcb_view* y, uint8_t* d_idx, int batch, int k, int stride,
+                           int pad, int dtype, void* stream);
+int ifcb_maxpool_bwd(const ifcb_view* dy, const uint8_t* d_idx, const ifcb_view* dx, int accumulate, int batch,
+                     int k, int stride, int pad, int dtype, void* stream);
+int ifcb_avgpool_fwd(const ifcb_view* x, const ifcb_view* y, int batch, int k, int stride, int pad, int dtype,
+                     void* stream);
+int ifcb_avgpool_bwd(const ifcb_view* dy, const ifcb_view* dx, int accumulate, int batch, int k, int stride,
+                     int pad, int dtype, void* stream);
+
+/* out[n, p*stride_h, q*stride_w, :] = in[n,p,q,:] into a zero tensor: the data gradient of a strided
+ * conv is the stride-1 conv of the zero-dilated output gradient with the flipped filter, which runs
+ * on the forward tcgen05 kernel (ifcb_plan_add_conv with weights from ifcb_conv_repack). */
+int ifcb_dilate(const ifcb_view* in, const ifcb_view* out, int batch, int stride_h, int stride_w, void* stream);
+/* float32 NCHW [batch,Cin,H,W] -> 16-bit NHWC view (channels >= Cin zero): stem input for ifcb_conv_wgrad. */
+int ifcb_nchw_to_nhwc(const float* d_in, int Cin, const ifcb_view* out, int batch, int dtype, void* stream);
+
+/* Train-mode head: adaptive_avg_pool2d(1) -> dropout scale -> Linear -> CrossEntropyLoss(mean)
+ * (inception.py:147-153 / resnet.py avgpool+fc; NeustonModel.loss neuston_models.py:70-80).
+ *   d_dropscale  float32 [batch,C] inverted-dropout scale (ifcb_dropout_scale) or NULL
+ *   d_labels     int64 [batch]
+ *   loss_weight  1.0 for the main head, 0.4 for Inception's AuxLogits (neuston_models.py:76)
+ *   d_pooled [batch,C], d_logits [batch,n_classes] (optional), d_dlogits [batch,n_classes] =
+ *   loss_weight/batch * (softmax - onehot); *d_loss += loss_weight * mean CE. */
+int ifcb_head_train_fwd(const ifcb_view* x, int batch, int dtype, const float* d_dropscale, const float* d_weight,
+                        const float* d_bias, const int64_t* d_labels, int n_classes, float loss_weight,
+                        float* d_pooled, float* d_logits, float* d_dlogits, float* d_loss, void* stream);
+/* d_dweight[n_classes,C] += dlogits^T pooled; d_dbias += sum_b dlogits; dx (=|+=) W^T dlogits * dropscale / HW */
+int ifcb_head_bwd(const ifcb_view* dx, int dx_accumulate, int batch, int dtype, const float* d_dropscale,
+                  const float* d_weight, const float* d_pooled, const float* d_dlogits, int n_classes,
+                  float* d_dweight, float* d_dbias, void* stream);
+int ifcb_dropout_scale(float* d_out, int64_t n, float p, uint64_t seed, void* stream);
+
+/* torch.optim.Adam(lr, betas, eps; no weight decay) over a flat fp32 arena (configure_optimizers,
+ * neuston_models.py:63-64); grad_scale multiplies the gradient first (1/world_size after a SUM all-reduce). */
+int ifcb_adam_step(float* d_param, const float* d_grad, float* d_m, float* d_v, int64_t n, float lr, float beta1,
+                   float beta2, float eps, int step, float grad_scale, void* stream);
+/* fp32 master conv weights [Cout, kh*kw, Cin] -> 16-bit tensor-core operands:
+ *   d_wfwd    [*, kh*kw*Cin_pad]   forward operand of ifcb_plan_add_conv (NULL to skip)
+ *   d_wdgrad  [*, kh*kw*Cout_padk] data-gradient operand: taps reversed, Cin/Cout swapped (NULL to skip)
+ * Padding entries are never written (allocate zeroed). */
+int ifcb_conv_repack(const float* d_master, int Cout, int taps, int Cin, void* d_wfwd, int Cin_pad, void* d_wdgrad,
+                     int Cout_padk, int dtype, void* stream);
+/* stem master weights [Cout, taps, Cin8] -> the fp32 stem kernel's d_weight [taps*3, Cout] */
+int ifcb_stem_repack(const float* d_master, int Cout, int taps, int Cin8, float* d_wstem, void* stream);
 
 /* Stem: first convolution (Cin = 3) computed directly in fp32 on CUDA cores from either
  * the resized gray plane (u8) or a float32 NCHW [batch,3,H,W] tensor (drop-in forward(x)).

@@ -9,6 +9,10 @@ import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
 
+# torch references below are fp32: no TF32 in cuDNN / cuBLAS
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+
 WGRAD_CASES = [
     # name, B, Cin, H, W, Cout, kh, kw, stride, pad
     ('3x3p1_64_64', 3, 64, 14, 14, 64, 3, 3, (1, 1), (1, 1)),
@@ -53,3 +57,401 @@ def test_conv_wgrad(cuda, case, dt):
     # exact products of 16-bit operands, fp32 accumulation in a different order: 1e-3 of the largest entry
     err = float((got - want).abs().max())
     assert err <= 1e-3 * float(want.abs().max()) + 1e-5, (name, err, float(want.abs().max()))
+
+
+# ------------------------------------------------------------------------------------------------
+# streaming TRAIN kernels (csrc/train_ops.cu) against torch autograd, fp32 on the same 16-bit inputs
+# ------------------------------------------------------------------------------------------------
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _mk(cuda, B, H, W, Cc, tdt, pad=(0, 0), ld=None, c0=0, gen=None, scale=1.0, fill=True):
+    """Random NHWC view (optionally a channel slice of a wider, bordered tensor) + its fp32 NCHW value."""
+    from ifcb_classifier_b200.graph import View
+    ld = ld or Cc
+    t = torch.zeros(B, H + 2 * pad[0], W + 2 * pad[1], ld, dtype=tdt, device=cuda)
+    v = View(t, c0, c0 + Cc, pad)
+    if fill:
+        val = (torch.randn(B, H, W, Cc, generator=gen) * scale).to(tdt)
+        v.interior().copy_(val.to(cuda))
+        return v, val.float().permute(0, 3, 1, 2).contiguous().to(cuda)
+    return v, None
+
+
+def _read(v):
+    return v.interior().float().permute(0, 3, 1, 2).contiguous()
+
+
+BN_CASES = [
+    # name, B, H, W, C, relu, residual, in/out pad, ld, c0
+    ('c64_relu', 4, 9, 9, 64, True, False, (0, 0), None, 0),
+    ('c80_slice_pad', 3, 7, 5, 80, True, False, (1, 1), 160, 32),
+    ('c256_res_relu', 2, 6, 6, 256, True, True, (0, 0), None, 0),
+    ('c128_norelu', 5, 4, 4, 128, False, False, (0, 0), None, 0),
+    ('c2048', 2, 3, 3, 2048, True, False, (0, 0), None, 0),
+    ('c48_big', 8, 35, 35, 48, True, False, (2, 2), None, 0),
+]
+
+
+@pytest.mark.parametrize('dt', ['bf16', 'fp16'])
+@pytest.mark.parametrize('case', BN_CASES, ids=[c[0] for c in BN_CASES])
+def test_bn_train_fwd_bwd(cuda, case, dt):
+    from ifcb_classifier_b200 import _lib
+    from ifcb_classifier_b200.train import _vd
+    name, B, H, W, Cc, relu, has_res, pad, ld, c0 = case
+    tdt = torch.bfloat16 if dt == 'bf16' else torch.float16
+    cdt = _lib.IFCB_ACT_BF16 if dt == 'bf16' else _lib.IFCB_ACT_FP16
+    g = torch.Generator().manual_seed(sum(name.encode()))
+    L = _lib.lib()
+    z, z32 = _mk(cuda, B, H, W, Cc, tdt, gen=g, scale=2.0)
+    z32 = z32 + 0.0
+    out, _ = _mk(cuda, B, H, W, Cc, tdt, pad=pad, ld=ld, c0=c0, fill=False)
+    res, res32 = _mk(cuda, B, H, W, Cc, tdt, pad=pad, gen=g) if has_res else (None, None)
+    gamma = (torch.rand(Cc, generator=g) + 0.5).to(cuda)
+    beta = (torch.randn(Cc, generator=g) * 0.2).to(cuda)
+    rm, rv = torch.zeros(Cc, device=cuda), torch.ones(Cc, device=cuda)
+    mean, invstd = torch.zeros(Cc, device=cuda), torch.zeros(Cc, device=cuda)
+    acc = torch.zeros(2 * Cc, dtype=torch.float64, device=cuda)
+    zd, od = _vd(z), _vd(out)
+    rd = _vd(res) if has_res else None
+    _lib.check(L.ifcb_bn_stats(C.byref(zd), B, cdt, 1e-3, 0.1, acc.data_ptr(), mean.data_ptr(), invstd.data_ptr(), rm.data_ptr(),
+                               rv.data_ptr(), _stream()), 'bn_stats')
+    _lib.check(L.ifcb_bn_apply(C.byref(zd), C.byref(od), C.byref(rd) if rd is not None else None, B, cdt, mean.data_ptr(), invstd.data_ptr(),
+                               gamma.data_ptr(), beta.data_ptr(), 1 if relu else 0, _stream()), 'bn_apply')
+    # reference
+    zr = z32.clone().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    rr = res32.clone().requires_grad_(True) if has_res else None
+    rm_r, rv_r = torch.zeros(Cc, device=cuda), torch.ones(Cc, device=cuda)
+    y = F.batch_norm(zr, rm_r, rv_r, gr, br, training=True, momentum=0.1, eps=1e-3)
+    if has_res:
+        y = y + rr
+    if relu:
+        y = F.relu(y)
+    got = _read(out)
+    tol = 2.0 ** (-8 if dt == 'bf16' else -11)               # one 16-bit rounding of the output
+    assert float((got - y.detach()).abs().max()) <= tol * (1.0 + float(y.detach().abs().max())), name
+    assert float(acc.abs().max()) == 0.0                      # accumulators cleared for the next layer
+    assert torch.allclose(rm, rm_r, rtol=1e-4, atol=1e-5) and torch.allclose(rv, rv_r, rtol=1e-4, atol=1e-5)
+    # backward: dy arrives as a 16-bit tensor; mask from OUR forward output so both sides agree on it
+    dy, dy32 = _mk(cuda, B, H, W, Cc, tdt, gen=g, scale=0.5)
+    dres, _ = _mk(cuda, B, H, W, Cc, tdt, gen=g) if has_res else (None, None)
+    dres0 = _read(dres) if has_res else None
+    dyd = _vd(dy)
+    dgam, dbet = torch.zeros(Cc, device=cuda), torch.zeros(Cc, device=cuda)
+    y.backward(dy32)
+    _lib.check(L.ifcb_bn_backward(C.byref(dyd), C.byref(od) if relu else None, C.byref(zd), C.byref(dyd),
+                                  C.byref(_vd(dres)) if has_res else None, 1, B, cdt, mean.data_ptr(), invstd.data_ptr(),
+                                  gamma.data_ptr(), acc.data_ptr(), dgam.data_ptr(), dbet.data_ptr(), _stream()), 'bn_backward')
+    torch.cuda.synchronize()
+    dz = _read(dy)
+    scale = float(zr.grad.abs().max())
+    # (an element whose pre-activation is within fp32 noise of zero may land on the other side of the ReLU)
+    bad = float(((dz - zr.grad).abs() > 2 * tol * scale + 1e-6).float().mean())
+    assert bad <= 1e-4, (name, bad, float((dz - zr.grad).abs().max()), scale)
+    assert torch.allclose(dgam, gr.grad, rtol=2e-3, atol=2e-3 * float(gr.grad.abs().max()))
+    assert torch.allclose(dbet, br.grad, rtol=2e-3, atol=2e-3 * float(br.grad.abs().max()))
+    if has_res:
+        want = dres0 + rr.grad
+        assert float((_read(dres) - want).abs().max()) <= 2 * tol * float(want.abs().max())
+
+
+POOL_CASES = [
+    # name, kind, B, H, W, C, k, s, p, in pad, out (ld, c0)
+    ('max3s2', 'max', 3, 15, 15, 64, 3, 2, 0, (0, 0), (64, 0)),
+    ('max3s2p1', 'max', 2, 14, 14, 64, 3, 2, 1, (0, 0), (64, 0)),
+    ('max3s2_slice', 'max', 2, 17, 17, 96, 3, 2, 0, (1, 1), (192, 96)),
+    ('avg3s1p1', 'avg', 2, 9, 9, 192, 3, 1, 1, (1, 1), (192, 0)),
+    ('avg5s3', 'avg', 3, 17, 17, 768, 5, 3, 0, (0, 0), (768, 0)),
+]
+
+
+@pytest.mark.parametrize('dt', ['bf16', 'fp16'])
+@pytest.mark.parametrize('case', POOL_CASES, ids=[c[0] for c in POOL_CASES])
+def test_pool_train_fwd_bwd(cuda, case, dt):
+    from ifcb_classifier_b200 import _lib
+    from ifcb_classifier_b200.train import _vd
+    name, kind, B, H, W, Cc, k, s, p, ipad, (old, oc0) = case
+    tdt = torch.bfloat16 if dt == 'bf16' else torch.float16
+    cdt = _lib.IFCB_ACT_BF16 if dt == 'bf16' else _lib.IFCB_ACT_FP16
+    g = torch.Generator().manual_seed(sum(name.encode()))
+    L = _lib.lib()
+    x, x32 = _mk(cuda, B, H, W, Cc, tdt, pad=ipad, gen=g)
+    # post-ReLU-like input: many exact ties at zero exercise torch's first-maximum rule
+    x.interior().clamp_(min=0)
+    x32 = x32.clamp(min=0)
+    P, Q = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+    y, _ = _mk(cuda, B, P, Q, Cc, tdt, ld=old, c0=oc0, fill=False)
+    xr = x32.clone().requires_grad_(True)
+    xd, yd = _vd(x), _vd(y)
+    if kind == 'max':
+        idx = torch.zeros(B, P, Q, Cc, dtype=torch.uint8, device=cuda)
+        _lib.check(L.ifcb_maxpool_fwd_train(C.byref(xd), C.byref(yd), idx.data_ptr(), B, k, s, p, cdt, _stream()), 'maxpool_fwd')
+        yr = F.max_pool2d(xr, k, s, p)
+    else:
+        _lib.check(L.ifcb_avgpool_fwd(C.byref(xd), C.byref(yd), B, k, s, p, cdt, _stream()), 'avgpool_fwd')
+        yr = F.avg_pool2d(xr, k, s, p)
+    tol = 2.0 ** (-8 if dt == 'bf16' else -11)
+    assert float((_read(y) - yr.detach()).abs().max()) <= (tol * float(yr.detach().abs().max()) if kind == 'avg' else 0.0)
+    dy, dy32 = _mk(cuda, B, P, Q, Cc, tdt, ld=old, c0=oc0, gen=g)
+    yr.backward(dy32)
+    for accumulate in (0, 1):
+        dx, dx0 = _mk(cuda, B, H, W, Cc, tdt, gen=g)
+        dyd, dxd = _vd(dy), _vd(dx)
+        if kind == 'max':
+            _lib.check(L.ifcb_maxpool_bwd(C.byref(dyd), idx.data_ptr(), C.byref(dxd), accumulate, B, k, s, p, cdt, _stream()), 'maxpool_bwd')
+        else:
+            _lib.check(L.ifcb_avgpool_bwd(C.byref(dyd), C.byref(dxd), accumulate, B, k, s, p, cdt, _stream()), 'avgpool_bwd')
+        want = xr.grad + (dx0 if accumulate else 0)
+        err = float((_read(dx) - want).abs().max())
+        assert err <= 2 * tol * float(want.abs().max()), (name, accumulate, err)
+
+
+def test_dilate_and_nchw_to_nhwc(cuda):
+    from ifcb_classifier_b200 import _lib
+    from ifcb_classifier_b200.train import _vd
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(5)
+    x, x32 = _mk(cuda, 2, 5, 4, 32, torch.bfloat16, gen=g)
+    out, _ = _mk(cuda, 2, 10, 8, 32, torch.bfloat16, fill=False)
+    _lib.check(L.ifcb_dilate(C.byref(_vd(x)), C.byref(_vd(out)), 2, 2, 2, _stream()), 'dilate')
+    want = torch.zeros(2, 32, 10, 8, device=cuda)
+    want[:, :, 0:9:2, 0:7:2] = x32
+    assert torch.equal(_read(out), want)
+    img = torch.randn(3, 3, 11, 13, generator=g).to(cuda)
+    o8, _ = _mk(cuda, 3, 11, 13, 8, torch.bfloat16, fill=False)
+    _lib.check(L.ifcb_nchw_to_nhwc(img.data_ptr(), 3, C.byref(_vd(o8)), 3, _lib.IFCB_ACT_BF16, _stream()), 'nchw_to_nhwc')
+    got = _read(o8)
+    assert torch.equal(got[:, :3], img.to(torch.bfloat16).float()) and float(got[:, 3:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize('drop', [False, True])
+def test_head_train_fwd_bwd(cuda, drop):
+    from ifcb_classifier_b200 import _lib
+    from ifcb_classifier_b200.train import _vd
+    L = _lib.lib()
+    B, H, W, Cc, K = 6, 3, 3, 512, 37
+    g = torch.Generator().manual_seed(11)
+    x, x32 = _mk(cuda, B, H, W, Cc, torch.bfloat16, gen=g)
+    Wt = (torch.randn(K, Cc, generator=g) * 0.05).to(cuda)
+    bias = (torch.randn(K, generator=g) * 0.1).to(cuda)
+    labels = torch.randint(0, K, (B,), generator=g).to(cuda)
+    ds = None
+    if drop:
+        ds = torch.zeros(B * Cc, device=cuda)
+        _lib.check(L.ifcb_dropout_scale(ds.data_ptr(), B * Cc, 0.5, 1234, _stream()), 'dropout_scale')
+        torch.cuda.synchronize()
+        frac = float((ds == 0).float().mean())
+        assert 0.4 < frac < 0.6 and set(ds.unique().tolist()) == {0.0, 2.0}
+    pooled, logits, dlogits = torch.zeros(B, Cc, device=cuda), torch.zeros(B, K, device=cuda), torch.zeros(B, K, device=cuda)
+    loss = torch.zeros(2, device=cuda)
+    _lib.check(L.ifcb_head_train_fwd(C.byref(_vd(x)), B, _lib.IFCB_ACT_BF16, ds.data_ptr() if drop else None, Wt.data_ptr(), bias.data_ptr(),
+                                     labels.data_ptr(), K, 0.4, pooled.data_ptr(), logits.data_ptr(), dlogits.data_ptr(), loss.data_ptr(),
+                                     _stream()), 'head_train_fwd')
+    xr = x32.clone().requires_grad_(True)
+    Wr, br = Wt.clone().requires_grad_(True), bias.clone().requires_grad_(True)
+    pr = xr.mean((2, 3))
+    if drop:
+        pr = pr * ds.view(B, Cc)
+    lr_ = F.linear(pr, Wr, br)
+    lref = 0.4 * F.cross_entropy(lr_, labels)
+    lref.backward()
+    assert torch.allclose(logits, lr_.detach(), rtol=1e-4, atol=1e-5)
+    assert abs(float(loss[0]) - float(lref)) <= 1e-5 * max(1.0, abs(float(lref)))
+    dW, db = torch.zeros(K, Cc, device=cuda), torch.zeros(K, device=cuda)
+    dx, dx0 = _mk(cuda, B, H, W, Cc, torch.bfloat16, gen=g, scale=1e-3)
+    _lib.check(L.ifcb_head_bwd(C.byref(_vd(dx)), 1, B, _lib.IFCB_ACT_BF16, ds.data_ptr() if drop else None, Wt.data_ptr(), pooled.data_ptr(),
+                               dlogits.data_ptr(), K, dW.data_ptr(), db.data_ptr(), _stream()), 'head_bwd')
+    torch.cuda.synchronize()
+    assert torch.allclose(dW, Wr.grad, rtol=1e-4, atol=1e-6) and torch.allclose(db, br.grad, rtol=1e-4, atol=1e-6)
+    want = dx0 + xr.grad
+    assert float((_read(dx) - want).abs().max()) <= 2.0 ** -7 * float(want.abs().max())
+
+
+def test_adam_matches_torch(cuda):
+    from ifcb_classifier_b200 import _lib
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(3)
+    n = 10007
+    w0 = torch.randn(n, generator=g).to(cuda)
+    p = torch.nn.Parameter(w0.clone())
+    opt = torch.optim.Adam([p], lr=1e-3)
+    w, m, v = w0.clone(), torch.zeros(n, device=cuda), torch.zeros(n, device=cuda)
+    for step in range(1, 6):
+        gr = (torch.randn(n, generator=g) * 10 ** float(torch.randint(-4, 1, (1,), generator=g))).to(cuda)
+        p.grad = gr.clone()
+        opt.step()
+        _lib.check(L.ifcb_adam_step(w.data_ptr(), (gr * 4).data_ptr(), m.data_ptr(), v.data_ptr(), n, 1e-3, 0.9, 0.999, 1e-8, step, 0.25,
+                                    _stream()), 'adam')
+        torch.cuda.synchronize()
+        assert float((w - p.detach()).abs().max()) <= 2e-6, step
+
+
+def test_conv_repack_layouts(cuda):
+    from ifcb_classifier_b200 import _lib
+    L = _lib.lib()
+    Co, Ci, kh, kw = 48, 80, 3, 3
+    g = torch.Generator().manual_seed(2)
+    w = torch.randn(Co, Ci, kh, kw, generator=g)
+    master = w.permute(0, 2, 3, 1).reshape(Co, kh * kw, Ci).contiguous().to(cuda)
+    gf, gd = _lib.conv_geometry(Ci, Co, kh, kw), _lib.conv_geometry(Co, Ci, kh, kw)
+    wf = torch.zeros(gf['Cout_pad'], kh * kw * gf['Cin_pad'], dtype=torch.bfloat16, device=cuda)
+    wd = torch.zeros(gd['Cout_pad'], kh * kw * gd['Cin_pad'], dtype=torch.bfloat16, device=cuda)
+    _lib.check(L.ifcb_conv_repack(master.data_ptr(), Co, kh * kw, Ci, wf.data_ptr(), gf['Cin_pad'], wd.data_ptr(), gd['Cin_pad'],
+                                  _lib.IFCB_ACT_BF16, _stream()), 'repack')
+    torch.cuda.synchronize()
+    wb = w.to(torch.bfloat16).float()
+    got_f = wf.float().view(gf['Cout_pad'], kh * kw, gf['Cin_pad'])[:Co, :, :Ci].cpu()
+    assert torch.equal(got_f, wb.permute(0, 2, 3, 1).reshape(Co, kh * kw, Ci))
+    # data-gradient operand = packed weights of conv_transpose: [ci][flipped tap][co]
+    wt = wb.flip(2, 3).permute(1, 2, 3, 0).reshape(Ci, kh * kw, Co)
+    got_d = wd.float().view(gd['Cout_pad'], kh * kw, gd['Cin_pad'])[:Ci, :, :Co].cpu()
+    assert torch.equal(got_d, wt)
+
+
+# ------------------------------------------------------------------------------------------------
+# whole TRAIN step against the oracle (torchvision fp32 autograd + Adam, oracle/train_ref.py)
+# ------------------------------------------------------------------------------------------------
+DGRAD_CASES = [
+    # name, B, Cin, H, W, Cout, kh, kw, stride, pad
+    ('3x3p1_64_96', 3, 64, 14, 14, 96, 3, 3, (1, 1), (1, 1)),
+    ('1x1_256_64', 2, 256, 9, 9, 64, 1, 1, (1, 1), (0, 0)),
+    ('3x3s2p1_64_128', 2, 64, 28, 28, 128, 3, 3, (2, 2), (1, 1)),
+    ('3x3s2p0_288_384', 2, 288, 35, 35, 384, 3, 3, (2, 2), (0, 0)),
+    ('1x1s2_64_256', 2, 64, 15, 15, 256, 1, 1, (2, 2), (0, 0)),
+    ('1x7_160_192', 2, 160, 17, 17, 192, 1, 7, (1, 1), (0, 3)),
+    ('5x5p2_48_64', 2, 48, 35, 35, 64, 5, 5, (1, 1), (2, 2)),
+    ('3x3p1_512_512_2x2', 4, 512, 2, 2, 512, 3, 3, (1, 1), (1, 1)),
+    ('5x5_128_768_to1x1', 4, 128, 5, 5, 768, 5, 5, (1, 1), (0, 0)),
+]
+
+
+@pytest.mark.parametrize('accumulate', [False, True])
+@pytest.mark.parametrize('case', DGRAD_CASES, ids=[c[0] for c in DGRAD_CASES])
+def test_conv_dgrad(cuda, case, accumulate):
+    """Data gradient = forward tcgen05 kernel + repacked (flipped / transposed) filter (+ dilation)."""
+    from ifcb_classifier_b200 import _lib
+    from ifcb_classifier_b200.graph import PlanBuilder, View
+    from ifcb_classifier_b200.train import build_dgrad
+    name, B, Cin, H, W, Cout, kh, kw, stride, pad = case
+    tdt = torch.bfloat16
+    g = torch.Generator().manual_seed(sum(name.encode()))
+    P = (H + 2 * pad[0] - kh) // stride[0] + 1
+    Q = (W + 2 * pad[1] - kw) // stride[1] + 1
+    w = (torch.randn(Cout, Cin, kh, kw, generator=g) * 0.05).to(tdt).float()
+    dy, dy32 = _mk(cuda, B, P, Q, Cout, tdt, gen=g)
+    dx, dx0 = _mk(cuda, B, H, W, Cin, tdt, gen=g)
+    bp = PlanBuilder(B, cuda, 'bf16')
+    dg = build_dgrad(bp, dy, dx, Cout, Cin, kh, kw, stride, pad, accumulate)
+    master = w.permute(0, 2, 3, 1).reshape(Cout, kh * kw, Cin).contiguous().to(cuda)
+    _lib.check(_lib.lib().ifcb_conv_repack(master.data_ptr(), Cout, kh * kw, Cin, None, 0, dg['weight'].data_ptr(), dg['Cin_pad'],
+                                           _lib.IFCB_ACT_BF16, _stream()), 'repack')
+    for r in dg['run']:
+        r()
+    torch.cuda.synchronize()
+    # float64 reference: cuDNN's fp32 backward-data algorithms are themselves off by > 1 bf16 ulp on some shapes
+    xr = torch.zeros(B, Cin, H, W, device=cuda, dtype=torch.float64, requires_grad=True)
+    F.conv2d(xr, w.to(cuda).double(), stride=stride, padding=pad).backward(dy32.double())
+    want = xr.grad.float() + (dx0 if accumulate else 0)
+    err = float((_read(dx) - want).abs().max())
+    assert err <= 2.0 ** -7 * float(want.abs().max()), (name, err, float(want.abs().max()))
+
+
+def _rel(a, b):
+    return float((a - b).norm() / (b.norm() + 1e-20))
+
+
+def _cos(a, b):
+    return float((a * b).sum() / (a.norm() * b.norm() + 1e-20))
+
+
+STEP_CASES = [('resnet18', 16, 96), ('resnet50', 8, 96), ('inception_v3', 8, 299)]
+
+
+@pytest.mark.parametrize('case', STEP_CASES, ids=[c[0] for c in STEP_CASES])
+def test_forward_backward_vs_oracle(cuda, case):
+    """One training_step (bf16 storage, fp32 accumulate; dropout off on both sides).
+
+    (1) Kernel parity, teacher-forced (tests/train_local.py): every unit of the step recomputed with
+        torch fp32 ops from the tensors the path stored -- conv outputs, BN batch statistics, activations,
+        dz, dW, dgamma, dbeta, fc gradients, and every activation gradient as the sum of its consumers'
+        contributions -- within 2^-7 of the tensor's largest entry (a few bf16 roundings).
+    (2) End to end against the oracle (fp32 autograd of the same torchvision module,
+        oracle/train_ref.py): |loss - ref| <= 2e-2 * ref.  Gradients are REPORTED, not gated, beyond
+        resnet18: a deep ReLU+BN network at random init amplifies one-ulp activation differences
+        layer by layer, so bf16 storage and fp32 disagree on ReLU masks; the same disagreement shows
+        between the oracle and the oracle with bf16 storage rounding inserted (printed as 'rounded vs fp32')."""
+    import copy
+    from oracle import train_ref
+    from tests.fixtures import ref_model
+    from tests.train_local import local_parity
+    from ifcb_classifier_b200.train import TrainNet
+    arch, B, R = case
+    n_classes = 10
+    model = ref_model(arch, n_classes, seed=1).to(cuda)
+    g = torch.Generator().manual_seed(7)
+    x = torch.rand(B, 3, R, R, generator=g).to(cuda)
+    y = torch.randint(0, n_classes, (B,), generator=g).to(cuda)
+    qmodel = copy.deepcopy(model)
+    train_ref.with_storage_rounding(qmodel, torch.bfloat16)
+    model.load_state_dict(qmodel.state_dict())                 # conv weights representable in bf16 on every side
+    net = TrainNet(arch, model.state_dict(), B, device=cuda, dtype='bf16', dropout=False, R=R, keep_dy=True)
+    loss = float(net.forward_backward(x, y))
+    ok, stats = local_parity(net, (lambda nm: 1e-3) if arch == 'inception_v3' else (lambda nm: 1e-5))
+    worst = sorted(stats, key=lambda t: -t[1])[:5]
+    print('%s teacher-forced: %d checks, failing %s, largest rel L2 %s' %
+          (arch, len(stats), [t for t in stats if not t[3]][:8], [(t[0], round(t[1], 5)) for t in worst]))
+    assert ok, [t for t in stats if not t[3]][:20]
+
+    grads = {k: v.to(cuda).float() for k, v in net.grad_dict().items()}
+    q_loss, q_grads = train_ref.forward_backward(qmodel, x, y, dropout=False)
+    f_loss, f_grads = train_ref.forward_backward(model, x, y, dropout=False)
+    assert sorted(grads) == sorted(f_grads)
+
+    def cosine(ga, gb):
+        dot = sum((ga[k] * gb[k]).sum() for k in gb)
+        na = torch.sqrt(sum((v ** 2).sum() for v in ga.values()))
+        nb = torch.sqrt(sum((v ** 2).sum() for v in gb.values()))
+        return float(dot / (na * nb))
+
+    print('%s end to end: loss %.5f, fp32 oracle %.5f, rounded oracle %.5f; gradient cosine ours vs fp32 %.4f, ours vs rounded %.4f, '
+          'rounded vs fp32 %.4f' % (arch, loss, float(f_loss), float(q_loss), cosine(grads, f_grads), cosine(grads, q_grads),
+                                   cosine(q_grads, f_grads)))
+    assert abs(loss - float(f_loss)) <= 2e-2 * abs(float(f_loss)), (loss, float(f_loss))
+    if arch == 'resnet18':
+        assert cosine(grads, f_grads) >= 0.9
+
+
+def test_train_steps_follow_oracle(cuda):
+    """Ten Adam steps of resnet18 on separable synthetic classes: the first losses follow the oracle's
+    within 5 %, both runs converge, running statistics stay within 5e-2 / 2e-2."""
+    from oracle import train_ref
+    from tests.fixtures import ref_model, class_rois
+    from ifcb_classifier_b200.train import TrainNet
+    import numpy as np
+    B, R, n_classes = 32, 64, 4
+    imgs, labels = class_rois(5 * B, n_classes, seed=3, hw=(R, R))
+    X = torch.from_numpy(np.stack(imgs)).float().div(255)[:, None].repeat(1, 3, 1, 1)
+    model = ref_model('resnet18', n_classes, seed=2).to(cuda)
+    net = TrainNet('resnet18', model.state_dict(), B, device=cuda, dtype='bf16', R=R)
+    batches = [(X[i * B:(i + 1) * B].to(cuda), labels[i * B:(i + 1) * B].to(cuda)) for i in range(5)] * 2
+    first = float(net.step(*batches[0]))
+    sd1 = net.state_dict()
+    ours = [first] + [float(net.step(xb, yb)) for xb, yb in batches[1:]]
+    import copy
+    m1 = copy.deepcopy(model)
+    train_ref.train_steps(m1, batches[:1])
+    rsd1 = m1.state_dict()
+    for k in ('bn1.running_mean', 'bn1.running_var', 'layer2.0.bn1.running_var', 'layer4.1.bn2.running_mean'):
+        assert torch.allclose(sd1[k], rsd1[k].cpu(), rtol=2e-2, atol=5e-3), k      # BN statistics of the first batch
+    ref = train_ref.train_steps(model, batches)
+    print('ours', ours, 'ref', ref)
+    # the first updates follow the oracle closely; later the two runs are different (equally valid)
+    # realisations of a chaotic trajectory -- both must converge
+    for a, b in zip(ours[:2], ref[:2]):
+        assert abs(a - b) <= 0.05 * abs(b), (ours, ref)
+    assert max(ours[-3:]) < 0.1 * ours[0] and max(ref[-3:]) < 0.1 * ref[0]
+    sd, rsd = net.state_dict(), model.state_dict()
+    assert list(sd.keys()) == list(rsd.keys())
+    assert int(sd['bn1.num_batches_tracked']) == 10
