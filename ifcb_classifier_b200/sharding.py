@@ -49,3 +49,49 @@ def gather_summary(summary, world, backend_group=None):
 
 def env_rank_world():
     return int(os.environ.get('RANK', '0')), int(os.environ.get('WORLD_SIZE', '1')), int(os.environ.get('LOCAL_RANK', '0'))
+
+
+# ---------------------------------------------------------------------------------------------
+# TRAIN: data-parallel gradient exchange (Lightning DDP in the reference, neuston_net.py:101-107:
+# per-rank batches, gradient MEAN over ranks, per-rank BatchNorm statistics).
+# ---------------------------------------------------------------------------------------------
+def plan_buckets(offsets_backward, n_params, bucket_elems):
+    """Contiguous gradient-arena ranges to all-reduce, in the order the backward pass completes them.
+
+    ``offsets_backward``: for each backward unit in execution order, the arena offset of its first
+    parameter (parameters are laid out in forward order, so offsets decrease), or None for units
+    without parameters.  Returns [(unit index after which the range is final, lo, hi), ...]; the
+    ranges tile [0, n_params) exactly and each (but possibly the last) holds >= bucket_elems."""
+    marks, hi = [], n_params
+    for i, lo in enumerate(offsets_backward):
+        if lo is None:
+            continue
+        assert 0 <= lo <= hi, 'parameters must be registered in forward order'
+        if hi - lo >= bucket_elems:
+            marks.append((i, lo, hi))
+            hi = lo
+    if hi > 0:
+        marks.append((len(offsets_backward) - 1, 0, hi))
+    return marks
+
+
+class GradReducer(object):
+    """Launches one asynchronous SUM all-reduce per finished bucket (NCCL runs them on its own stream
+    while the remaining backward kernels execute) and waits for all of them before the optimizer;
+    the 1/world factor of the mean is applied inside the Adam kernel (``grad_scale``)."""
+
+    def __init__(self, grads, group=None):
+        import torch.distributed as dist
+        self.dist, self.grads, self.group = dist, grads, group
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.works = []
+
+    def __call__(self, lo, hi):
+        if self.world > 1 and hi > lo:
+            self.works.append(self.dist.all_reduce(self.grads[lo:hi], op=self.dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def wait(self):
+        for w in self.works:
+            w.wait()
+        self.works = []
+        return 1.0 / self.world

@@ -24,6 +24,7 @@ import torch
 from . import _lib
 from ._lib import ViewDesc, WgradDesc, IFCB_STEM_IN_F32_NCHW
 from .graph import PlanBuilder, View, RESNET_CFG
+from .sharding import plan_buckets, GradReducer
 
 
 def _vd(v):
@@ -101,6 +102,7 @@ class TrainNet(object):
         self.dropout, self.seed = bool(dropout), int(seed)
         self.keep_dy = bool(keep_dy)        # tests: keep d(activation) next to d(conv output) instead of overwriting it
         self.step_count = 0
+        self._reducer = None
         self.lib = _lib.lib()
         sd = {k: v.detach().cpu() for k, v in state_dict.items()}
         self.sd_keys = list(sd.keys())
@@ -295,10 +297,7 @@ class TrainNet(object):
             written.add(key)
             return acc
 
-        # gradient buckets for the all-reduce: contiguous arena ranges, closed from the END of the arena
-        # (backward produces gradients in reverse parameter order)
-        self.bucket_marks = []          # (index into self.bwd after which [lo, hi) is complete, lo, hi)
-        hi = self.n_params
+        unit_lo = []                    # per backward closure: arena offset its unit's parameters start at (None: none)
         for rec in reversed(self.records):
             kind = rec['kind']
             if kind == 'head':
@@ -331,11 +330,9 @@ class TrainNet(object):
                 lo = None
             else:
                 lo = self._finalize_conv(rec, claim)
-            if lo is not None and (hi - lo) * 4 >= bucket_bytes:
-                self.bucket_marks.append((len(self.bwd), lo, hi))
-                hi = lo
-        if hi > 0:
-            self.bucket_marks.append((len(self.bwd), 0, hi))
+            unit_lo.extend([None] * (len(self.bwd) - len(unit_lo) - 1) + [lo])
+        # contiguous arena ranges to all-reduce as soon as the backward pass has finished them
+        self.bucket_marks = plan_buckets(unit_lo, self.n_params, bucket_bytes // 4)
 
     def _finalize_conv(self, rec, claim):
         B, dt = self.batch, self.cdtype
@@ -414,11 +411,14 @@ class TrainNet(object):
     def backward(self, allreduce=None):
         """Runs the backward pass; ``allreduce(lo, hi)`` is called as soon as gradient range [lo, hi) is final."""
         self._call('ifcb_memset_zero', self.grads.data_ptr(), 4 * self.n_params, self._stream())
-        marks = {m[0]: (m[1], m[2]) for m in self.bucket_marks}
+        marks = {}
+        for m in self.bucket_marks:
+            marks.setdefault(m[0], []).append((m[1], m[2]))
         for i, b in enumerate(self.bwd):
             b()
-            if allreduce is not None and (i + 1) in marks:
-                allreduce(*marks[i + 1])
+            if allreduce is not None:
+                for lo, hi in marks.get(i, ()):
+                    allreduce(lo, hi)
 
     def forward_backward(self, x=None, labels=None, allreduce=None):
         if x is not None:
@@ -437,17 +437,10 @@ class TrainNet(object):
 
     def step(self, x=None, labels=None):
         """training_step + backward + (gradient mean over ranks) + Adam.  Returns the loss (device scalar)."""
-        import torch.distributed as dist
-        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
-        works = []
-        hook = None
-        if world > 1:
-            def hook(lo, hi):
-                works.append(dist.all_reduce(self.grads[lo:hi], op=dist.ReduceOp.SUM, async_op=True))
-        loss = self.forward_backward(x, labels, hook)
-        for w in works:
-            w.wait()
-        self.adam(1.0 / world)
+        if self._reducer is None:
+            self._reducer = GradReducer(self.grads)
+        loss = self.forward_backward(x, labels, self._reducer if self._reducer.world > 1 else None)
+        self.adam(self._reducer.wait())
         return loss
 
     # ---- parameter import / export (torchvision layout) -----------------------------------------------

@@ -139,3 +139,56 @@ def test_cli_surface_matches_reference_flags():
     t = p.parse_args(['TRAIN', 'src', 'inception_v3', 'tid', '--untrain', '--img-norm', '0.667', '0.161', '--flip', 'xy+V'])
     assert (t.batch_size, t.pretrained, t.emax, t.emin, t.estop, t.split, t.class_min) == (108, False, 60, 10, 10, '80:20', 2)
     assert t.outdir == 'training-output/{TRAIN_ID}' and t.model_id == '{TRAIN_ID}' and t.epochs_log == 'epochs.csv'
+
+
+# ---- TRAIN: gradient buckets + data-parallel mean (world_size-2 gloo, CPU) ----
+def test_plan_buckets_tile_the_arena():
+    # offsets of the backward units' first parameter, as TrainNet lays them out (forward order => decreasing)
+    offs = [900, None, 700, None, None, 650, 300, None, 0]
+    marks = sharding.plan_buckets(offs, 1000, 250)
+    assert marks == [(2, 700, 1000), (6, 300, 700), (8, 0, 300)]
+    covered = sorted((lo, hi) for _, lo, hi in marks)
+    assert covered[0][0] == 0 and covered[-1][1] == 1000 and all(a[1] == b[0] for a, b in zip(covered, covered[1:]))
+    assert sharding.plan_buckets(offs, 1000, 10 ** 9) == [(8, 0, 1000)]          # one bucket when the threshold is never met
+    assert sharding.plan_buckets([None, None], 0, 4) == []
+
+
+_GLOO_TRAIN_WORKER = r'''
+import sys, json
+sys.path.insert(0, %(root)r)
+import torch
+import torch.distributed as dist
+from ifcb_classifier_b200 import sharding
+dist.init_process_group('gloo', init_method='tcp://127.0.0.1:%(port)d', rank=int(sys.argv[1]), world_size=2)
+rank = dist.get_rank()
+n = 1000
+g = torch.Generator().manual_seed(100 + rank)
+grads = torch.randn(n, generator=g)
+mine = grads.clone()
+red = sharding.GradReducer(grads)
+offs = [900, None, 700, None, None, 650, 300, None, 0]
+marks = sharding.plan_buckets(offs, n, 250)
+by_unit = {}
+for i, lo, hi in marks:
+    by_unit.setdefault(i, []).append((lo, hi))
+for unit in range(len(offs)):                # the backward pass: a bucket is reduced as soon as its last unit ran
+    for lo, hi in by_unit.get(unit, ()):
+        red(lo, hi)
+scale = red.wait()
+other = torch.randn(n, generator=torch.Generator().manual_seed(100 + (1 - rank)))
+want = (mine + other) * 0.5
+ok = bool(torch.allclose(grads * scale, want, rtol=0, atol=1e-6)) and scale == 0.5 and red.world == 2 and not red.works
+print('RESULT ' + json.dumps(dict(rank=rank, ok=ok)))
+dist.destroy_process_group()
+'''
+
+
+def test_two_rank_gloo_gradient_mean():
+    code = _GLOO_TRAIN_WORKER % dict(root=ROOT, port=31500 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, '-c', code, str(r)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+             for r in range(2)]
+    outs = [p.communicate(timeout=120) for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    for out, _ in outs:
+        line = [l for l in out.splitlines() if l.startswith('RESULT ')][0]
+        assert json.loads(line[len('RESULT '):])['ok']

@@ -455,3 +455,15 @@ def test_train_steps_follow_oracle(cuda):
     sd, rsd = net.state_dict(), model.state_dict()
     assert list(sd.keys()) == list(rsd.keys())
     assert int(sd['bn1.num_batches_tracked']) == 10
+
+
+def test_two_gpu_data_parallel_step(cuda):
+    """NCCL gradient mean across 2 ranks (tools/ddp_check.py); skipped on a single-GPU box."""
+    import os, subprocess, sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr', '127.0.0.1',
+                          '--master-port', str(29600 + os.getpid() % 300), os.path.join(root, 'tools', 'ddp_check.py')],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and 'DDP_CHECK ok' in out.stdout, (out.stdout[-2000:], out.stderr[-2000:])
