@@ -45,3 +45,162 @@ class IfcbBinDataset(object):
 
     def __len__(self):
         return len(self.pids)
+
+
+# =====================================================================================================
+# TRAIN datasets (reference neuston_data.py:20-328): class-per-folder image trees, class thresholds,
+# class-config CSV, seeded train/validation split.  Same names and semantics; items are decoded to
+# uint8 gray planes (IFCB images are 8-bit grayscale PNGs) and transformed by the fused GPU kernel in
+# batches (train_loop.ImageBatcher) instead of per item through torchvision transforms.
+# =====================================================================================================
+import os
+import random
+
+IMG_EXTENSIONS = ('.jpg', '.jpeg', '.png', '.ppm', '.bmp', '.pgm', '.tif', '.tiff', '.webp')
+
+
+class NeustonDataset(object):
+    def __init__(self, src, minimum_images_per_class=1, maximum_images_per_class=None, transforms=None, images_perclass=None):
+        self.src = src
+        if not images_perclass:
+            images_perclass = self.fetch_images_perclass(src)
+        self.minimum_images_per_class = max(1, minimum_images_per_class)
+        kept = {c: imgs for c, imgs in images_perclass.items() if len(imgs) >= self.minimum_images_per_class}
+        ignored = sorted(set(images_perclass) - set(kept))
+        self.classes_ignored_from_too_few_samples = [(c, len(images_perclass[c])) for c in ignored]
+        self.classes = sorted(kept)
+        self.maximum_images_per_class = maximum_images_per_class
+        if maximum_images_per_class:
+            assert maximum_images_per_class > self.minimum_images_per_class
+            limited = {c: sorted(random.sample(imgs, maximum_images_per_class)) if maximum_images_per_class < len(imgs) else imgs
+                       for c, imgs in kept.items()}
+            self.classes_limited_from_too_many_samples = [c for c in self.classes if len(limited[c]) < len(kept[c])]
+            kept = limited
+        else:
+            self.classes_limited_from_too_many_samples = None
+        kept = {c: sorted(imgs) for c, imgs in kept.items()}
+        pairs = [(self.classes.index(c), img) for c in kept for img in kept[c]]
+        self.targets = tuple(p[0] for p in pairs)
+        self.images = tuple(p[1] for p in pairs)
+        self.transforms = transforms      # dict(flip=..., resize=..., img_norm=...) -- consumed by train_loop.ImageBatcher
+
+    @classmethod
+    def fetch_images_perclass(cls, src):
+        """Sub-folders of ``src`` are the classes (neuston_data.py:55-70)."""
+        if not os.path.isdir(src):
+            raise NotImplementedError('dataset-combining config files (SRC as a CSV) are not supported; pass a directory')
+        out = {}
+        for sub in sorted(d.name for d in os.scandir(src) if d.is_dir()):
+            files = sorted(f for f in os.listdir(os.path.join(src, sub)) if os.path.splitext(f)[1].lower() in IMG_EXTENSIONS)
+            out[sub] = [os.path.join(src, sub, f) for f in files]
+        return out
+
+    @property
+    def images_perclass(self):
+        ipc = {c: [] for c in self.classes}
+        for img, trg in zip(self.images, self.targets):
+            ipc[self.classes[trg]].append(img)
+        return ipc
+
+    @property
+    def count_perclass(self):
+        cpc = [0] * len(self.classes)
+        for t in self.targets:
+            cpc[t] += 1
+        return cpc
+
+    def split(self, ratio1, ratio2, seed=None, minimum_images_per_class='scale'):
+        assert ratio1 + ratio2 == 100, 'ratio1:ratio2 must sum to 100, instead got {}:{} (total: {})'.format(ratio1, ratio2, ratio1 + ratio2)
+        d1, d2 = {}, {}
+        for label, images in self.images_perclass.items():
+            n1 = int(ratio1 * len(images) / 100 + 0.5)
+            if n1 == len(images) and self.minimum_images_per_class > 1:
+                n1 -= 1                                         # at least one image goes to the second set
+            if seed:
+                random.seed(seed)
+            d1[label] = random.sample(images, n1)
+            d2[label] = sorted(set(images) - set(d1[label]))
+            assert len(d1[label]) + len(d2[label]) == len(images)
+        a = NeustonDataset(src=self.src, images_perclass=d1, transforms=self.transforms)
+        b = NeustonDataset(src=self.src, images_perclass=d2, transforms=self.transforms)
+        assert a.classes == b.classes, 'd1-d2_classes:{}, d2-d1_classes:{}'.format(set(a.classes) - set(b.classes), set(b.classes) - set(a.classes))
+        assert len(a) + len(b) == len(self), 'd1_len:{}, d2_len:{}'.format(len(a), len(b))
+        return a, b
+
+    @classmethod
+    def from_csv(cls, src, csv_file, column_to_run, transforms=None, minimum_images_per_class=1, maximum_images_per_class=None):
+        """Class-config CSV (neuston_data.py:189-256): first column = folder names; chosen column: 1 keep, 0 drop,
+        any other value = the (possibly shared) class label the folder is grouped under."""
+        import csv
+        with open(csv_file, newline='') as f:
+            rows = list(csv.reader(f))
+        header, rows = rows[0], rows[1:]
+        col = header.index(column_to_run)
+        default = cls.fetch_images_perclass(src)
+        new = {}
+        for row in rows:
+            base, mod = row[0], str(row[col]).strip()
+            if base not in default or mod == '0':
+                continue
+            label = base if mod == '1' else mod
+            new.setdefault(label, [])
+            new[label] = new[label] + default[base]
+        return cls(src=src, images_perclass=new, transforms=transforms, minimum_images_per_class=minimum_images_per_class,
+                   maximum_images_per_class=maximum_images_per_class)
+
+    def __getitem__(self, index):
+        """(uint8 gray plane [h, w], target, path) -- the decoded image BEFORE flips / resize / ToTensor."""
+        return load_gray(self.images[index]), self.targets[index], self.images[index]
+
+    def __len__(self):
+        return len(self.images)
+
+    @property
+    def imgs(self):
+        return self.images
+
+
+def load_gray(path):
+    """Decodes an image file to a uint8 gray plane.  The reference's ``default_loader`` converts to RGB
+    (three identical channels for IFCB's grayscale PNGs); colour files are reduced with PIL's 'L' conversion."""
+    from PIL import Image
+    with Image.open(path) as im:
+        if im.mode != 'L':
+            im = im.convert('L')
+        return np.asarray(im, dtype=np.uint8).copy()
+
+
+def get_trainval_transforms(args):
+    """neuston_data.py:342-371: resize 299 (inception_v3) / 224, optional Normalize, optional random flips
+    ('x' -> vertical flip, 'y' -> horizontal flip, as the reference wires them; '+V' also on validation)."""
+    args.resize = 299 if args.MODEL == 'inception_v3' else 224
+    img_norm = parse_imgnorm(args.img_norm) if args.img_norm else None
+    flips = []
+    if args.flip:
+        if 'x' in args.flip:
+            flips.append('v')
+        if 'y' in args.flip:
+            flips.append('h')
+    train = dict(resize=args.resize, img_norm=img_norm, flips=list(flips))
+    val = dict(resize=args.resize, img_norm=img_norm, flips=list(flips) if (args.flip and '+V' in args.flip) else [])
+    return train, val
+
+
+def get_trainval_datasets(args):
+    print('Initializing Data...')
+    if not args.class_config:
+        nd = NeustonDataset(src=args.SRC, minimum_images_per_class=args.class_min, maximum_images_per_class=args.class_max)
+    else:
+        nd = NeustonDataset.from_csv(src=args.SRC, csv_file=args.class_config[0], column_to_run=args.class_config[1],
+                                     minimum_images_per_class=args.class_min, maximum_images_per_class=args.class_max)
+    ratio1, ratio2 = map(int, args.split.split(':'))
+    pair = nd.split(ratio1, ratio2, seed=args.seed)
+    training_dataset, validation_dataset = pair if not args.swap else pair[::-1]
+    assert validation_dataset.classes_ignored_from_too_few_samples == training_dataset.classes_ignored_from_too_few_samples
+    if nd.classes_ignored_from_too_few_samples:
+        print('\n{} out of {} classes ignored from --class-minimum {}, PRE-SPLIT'.format(
+            len(nd.classes_ignored_from_too_few_samples), len(nd.classes) + len(nd.classes_ignored_from_too_few_samples), args.class_min))
+        for c, l in nd.classes_ignored_from_too_few_samples:
+            print('    ({:2}) {}'.format(l, c))
+    training_dataset.transforms, validation_dataset.transforms = get_trainval_transforms(args)
+    return training_dataset, validation_dataset

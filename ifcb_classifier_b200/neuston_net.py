@@ -8,8 +8,9 @@
 Same flags, defaults and path templates ({RUN_ID} {RUN_DATE} {MODEL_ID} {BIN_ID} {BIN_YEAR}
 {BIN_DATE} {INPUT_SUBDIRS}).  The loop that pytorch_lightning's Trainer ran is
 ``engine.BinClassifier``; per-bin error isolation and skip-if-exists are preserved
-(neuston_net.py:242-251,258-268).  TRAIN's flags parse, but the training step is not built
-in this round and exits with a clear message.
+(neuston_net.py:242-251,258-268).  TRAIN runs ``train_loop.do_training``: the reference's
+dataset / split / epoch / checkpoint flow around the B200 train step (``train.TrainNet``);
+``torchrun --nproc-per-node N ... TRAIN ...`` is data parallel (NCCL gradient mean).
 """
 import argparse
 import datetime as dt
@@ -28,7 +29,9 @@ def argparse_nn(parser=None):
     common.add_argument('--batch', dest='batch_size', metavar='SIZE', default=108, type=int)
     common.add_argument('--loaders', metavar='N', default=4, type=int)
     common.add_argument('--dtype', default='fp16', choices=['fp16', 'bf16'],
-                        help='tensor-core operand format (B200 extension; default fp16)')
+                        help='tensor-core operand format of eval-mode forward passes (B200 extension; default fp16)')
+    common.add_argument('--train-dtype', dest='train_dtype', default='bf16', choices=['bf16'],
+                        help='16-bit storage format of the TRAIN step (B200 extension)')
     _train_args(train)
     _run_args(run)
     return parser
@@ -194,8 +197,9 @@ def do_run(args, classifier=None):
 
 
 def do_training(args):
-    raise NotImplementedError('TRAIN (forward/backward/Adam + NCCL all-reduce on sm_100a kernels) is not built in '
-                              'this round; see DESIGN.md "Scope and status"')
+    """TRAIN (reference neuston_net.py:37-160): see train_loop.do_training."""
+    from .train_loop import do_training as _do_training
+    return _do_training(args)
 
 
 def main(argv=None):

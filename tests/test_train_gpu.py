@@ -467,3 +467,50 @@ def test_two_gpu_data_parallel_step(cuda):
                           '--master-port', str(29600 + os.getpid() % 300), os.path.join(root, 'tools', 'ddp_check.py')],
                          capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and 'DDP_CHECK ok' in out.stdout, (out.stdout[-2000:], out.stderr[-2000:])
+
+
+def test_neuston_net_train_then_run(cuda, tmp_path):
+    """TRAIN entry point end to end on a small class-per-folder PNG tree (separable synthetic classes), then
+    RUN with the checkpoint it wrote: files of the reference's layout appear and the model has learnt."""
+    import json
+    import numpy as np
+    from PIL import Image
+    from scipy.io import loadmat
+    from oracle import synth_bins
+    from tests.fixtures import class_rois
+    from ifcb_classifier_b200 import neuston_net
+    from ifcb_classifier_b200.neuston_models import NeustonModel
+    src = tmp_path / 'dataset'
+    imgs, labels = class_rois(96, 3, seed=5)
+    for i, (im, k) in enumerate(zip(imgs, labels.tolist())):
+        d = src / ('class_%d' % k)
+        d.mkdir(parents=True, exist_ok=True)
+        Image.fromarray(im, mode='L').save(str(d / ('img_%03d.png' % i)))
+    out = tmp_path / 'train_out'
+    # (batch 8 x 12 epochs = ~120 steps: BatchNorm running statistics need a few dozen steps at momentum 0.1
+    #  before the eval-mode forward of the validation pass is meaningful -- same in the reference)
+    rc = neuston_net.main(['--batch', '8', '--loaders', '2', 'TRAIN', str(src), 'resnet18', 'T1', '--untrain', '--seed', '7',
+                           '--emax', '12', '--emin', '12', '--estop', '12', '--flip', 'xy', '--outdir', str(out)])
+    assert rc == 0
+    for f in ('T1.ptl', 'epochs.csv', 'args.yml', 'training_images.list', 'validation_images.list', 'results.mat'):
+        assert (out / f).exists(), f
+    rows = (out / 'epochs.csv').read_text().strip().splitlines()
+    assert rows[0] == 'epoch,best,train_loss,val_loss,f1_macro,f1_weighted' and len(rows) >= 3
+    n_train = len((out / 'training_images.list').read_text().splitlines())
+    n_val = len((out / 'validation_images.list').read_text().splitlines())
+    assert n_train + n_val == 96 and abs(n_val - 19) <= 3                      # --split 80:20 per class
+    m = loadmat(str(out / 'results.mat'))
+    assert m['confusion_matrix'].shape == (3, 3) and int(m['confusion_matrix'].sum()) == n_val
+    assert m['output_scores'].shape == (n_val, 3) and m['input_classes'].min() >= 1        # 1-based for MATLAB
+    model = NeustonModel.load_from_checkpoint(str(out / 'T1.ptl'))
+    assert model.hparams.classes == ['class_0', 'class_1', 'class_2'] and model.hparams.MODEL == 'resnet18'
+    best = [r.split(',') for r in rows[1:] if r.split(',')[1] == 'True'][-1]
+    assert float(best[5]) >= 0.6, rows                                          # weighted F1 of the best epoch: it learnt
+    # RUN with the checkpoint
+    bins = tmp_path / 'bins'
+    synth_bins.write_bin(str(bins), synth_bins.make_bin(0, n_rois=20))
+    rc = neuston_net.main(['--batch', '16', 'RUN', str(bins), str(out / 'T1.ptl'), 'R1', '--outdir', str(tmp_path / 'run_out'),
+                           '--outfile', '{BIN_ID}_class.json'])
+    assert rc == 0
+    j = json.load(open(str(tmp_path / 'run_out' / (synth_bins.bin_lid(0) + '_class.json'))))
+    assert len(j['output_classes']) == 20 and j['class_labels'] == ['class_0', 'class_1', 'class_2']

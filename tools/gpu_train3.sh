@@ -1,3 +1,3 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 300 python tools/dbg_dgrad.py > gpurun_out/dbg_dgrad.txt 2>&1
+timeout 900 python -m pytest tests/test_train_gpu.py -q -m gpu -x -k "train_then_run" 2>&1 | tail -40 > gpurun_out/train5.log
