@@ -105,14 +105,16 @@ _SIGNATURES = {
                                 C.c_void_p, C.c_void_p, C.c_void_p]),
     'ifcb_bn_apply': (C.c_int, [_V, _V, _V, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_int, C.c_void_p]),
-    'ifcb_bn_backward': (C.c_int, [_V, _V, _V, _V, _V, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
-                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'ifcb_bn_backward': (C.c_int, [_V, _V, _V, _V, _V, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'ifcb_maxpool_fwd_train': (C.c_int, [_V, _V, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     'ifcb_maxpool_bwd': (C.c_int, [_V, C.c_void_p, _V, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     'ifcb_avgpool_fwd': (C.c_int, [_V, _V, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     'ifcb_avgpool_bwd': (C.c_int, [_V, _V, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     'ifcb_dilate': (C.c_int, [_V, _V, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     'ifcb_nchw_to_nhwc': (C.c_int, [C.c_void_p, C.c_int, _V, C.c_int, C.c_int, C.c_void_p]),
+    'ifcb_stem_im2col': (C.c_int, [C.c_void_p, C.c_int, C.c_int, _V, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                   C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int, C.c_void_p]),
     'ifcb_head_train_fwd': (C.c_int, [_V, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                       C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'ifcb_head_bwd': (C.c_int, [_V, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,

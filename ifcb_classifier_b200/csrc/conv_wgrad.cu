@@ -35,6 +35,7 @@ struct WgradParams {
   int Cin, Cout, cblocks, taps;
   int n_pairs;              // taps * cblocks
   int n_groups;             // ceil(n_pairs / 8)
+  int group_size;           // (tap, channel block) pairs per group, balanced: ceil(n_pairs / n_groups)
   int co_tiles;             // ceil(Cout / 128)
   int splits;               // pixel-range splits
   int tiles_per_split;      // 128-pixel tiles per split
@@ -90,8 +91,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_cons
       const int rest = item / p.splits;
       const int group = rest % p.n_groups;
       const int co_tile = rest / p.n_groups;
-      const int pair0 = group * kMaxAcc;
-      const int npair = min(kMaxAcc, p.n_pairs - pair0);
+      const int pair0 = group * p.group_size;
+      const int npair = min(p.group_size, p.n_pairs - pair0);
       const int t_begin = split * p.tiles_per_split;
       const int t_end = min(total_ptiles, t_begin + p.tiles_per_split);
       for (int pt = t_begin; pt < t_end; ++pt) {
@@ -142,7 +143,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_cons
       const int split = item % p.splits;
       const int rest = item / p.splits;
       const int group = rest % p.n_groups;
-      const int npair = min(kMaxAcc, p.n_pairs - group * kMaxAcc);
+      const int npair = min(p.group_size, p.n_pairs - group * p.group_size);
       const int t_begin = split * p.tiles_per_split;
       const int t_end = min(total_ptiles, t_begin + p.tiles_per_split);
       ptx::mbar_wait(acc_empty, (uint32_t)((local & 1) ^ 1));
@@ -180,8 +181,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_cons
       const int rest = item / p.splits;
       const int group = rest % p.n_groups;
       const int co_tile = rest / p.n_groups;
-      const int pair0 = group * kMaxAcc;
-      const int npair = min(kMaxAcc, p.n_pairs - pair0);
+      const int pair0 = group * p.group_size;
+      const int npair = min(p.group_size, p.n_pairs - pair0);
       const int t_begin = split * p.tiles_per_split;
       const bool has_work = t_begin < min(total_ptiles, t_begin + p.tiles_per_split);
       ptx::mbar_wait(acc_full, (uint32_t)(local & 1));
@@ -199,9 +200,13 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_cons
             ptx::tmem_ld_32x32b_x16(taddr + (uint32_t)c0, v);
             ptx::tmem_ld_wait();
             if (co < p.Cout) {
+              // 16-byte vector reductions (Cin is a multiple of 8: a group of 4 is all in or all out)
 #pragma unroll
-              for (int j = 0; j < 16; ++j)
-                if (cb * 64 + c0 + j < p.Cin) atomicAdd(dst + c0 + j, __uint_as_float(v[j]));
+              for (int j = 0; j < 16; j += 4)
+                if (cb * 64 + c0 + j < p.Cin)
+                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c0 + j), "f"(__uint_as_float(v[j])),
+                               "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3]))
+                               : "memory");
             }
           }
         }
@@ -224,6 +229,7 @@ using namespace ifcb;
 extern "C" int ifcb_conv_wgrad(const ifcb_wgrad_desc* d, void* stream_v) {
   IFCB_ARG_CHECK(d != nullptr, "ifcb_conv_wgrad: null descriptor");
   IFCB_ARG_CHECK(d->d_in && d->d_dout && d->d_dweight, "wgrad: null tensor pointer");
+  IFCB_ARG_CHECK((reinterpret_cast<uintptr_t>(d->d_dweight) & 15) == 0, "wgrad: d_dweight must be 16-byte aligned");
   IFCB_ARG_CHECK(d->Cin > 0 && d->Cin % 8 == 0 && d->in_ld >= d->Cin && d->in_ld % 8 == 0, "wgrad: Cin / in_ld must be multiples of 8");
   IFCB_ARG_CHECK(d->Cout > 0 && d->Cout % 8 == 0 && d->dout_ld >= d->Cout && d->dout_ld % 8 == 0, "wgrad: Cout / dout_ld must be multiples of 8");
   IFCB_ARG_CHECK(((reinterpret_cast<uintptr_t>(d->d_in) | reinterpret_cast<uintptr_t>(d->d_dout)) & 15) == 0, "wgrad: views must be 16-byte aligned");
@@ -277,6 +283,8 @@ extern "C" int ifcb_conv_wgrad(const ifcb_wgrad_desc* d, void* stream_v) {
   p.taps = d->kh * d->kw;
   p.n_pairs = p.taps * p.cblocks;
   p.n_groups = (p.n_pairs + kMaxAcc - 1) / kMaxAcc;
+  p.group_size = (p.n_pairs + p.n_groups - 1) / p.n_groups;
+  p.n_groups = (p.n_pairs + p.group_size - 1) / p.group_size;
   p.co_tiles = (d->Cout + 127) / 128;
   const int ptiles = (int)((rows + kPix - 1) / kPix);
   const int base_items = p.co_tiles * p.n_groups;

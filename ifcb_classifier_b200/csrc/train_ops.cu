@@ -17,12 +17,15 @@ namespace {
 struct DV {   // device copy of an ifcb_view
   uint16_t* p;
   int ld, C, H, W, ph, pw;
+  unsigned long long magic_w, magic_h;   // fast_div magics of W and H
 };
 
 inline DV dv(const ifcb_view* v) {
   DV d;
   d.p = reinterpret_cast<uint16_t*>(v->d);
   d.ld = v->ld; d.C = v->C; d.H = v->H; d.W = v->W; d.ph = v->pad_h; d.pw = v->pad_w;
+  d.magic_w = div_magic(v->W);
+  d.magic_h = div_magic(v->H);
   return d;
 }
 
@@ -30,14 +33,14 @@ __device__ __forceinline__ long long pix_off(const DV& v, int n, int h, int w) {
   return (((long long)n * (v.H + 2 * v.ph) + h + v.ph) * (v.W + 2 * v.pw) + w + v.pw) * v.ld;
 }
 
-// logical pixel index m = (n*H + h)*W + w  ->  element offset of that pixel in the view
+// logical pixel index m = (n*H + h)*W + w (< 2^31)  ->  element offset of that pixel in the view
 __device__ __forceinline__ long long pix_off_m(const DV& v, long long m) {
   if ((v.ph | v.pw) == 0) return m * v.ld;
-  const int w = (int)(m % v.W);
-  const long long t = m / v.W;
-  const int h = (int)(t % v.H);
-  const int n = (int)(t / v.H);
-  return pix_off(v, n, h, w);
+  const uint32_t t = fast_div((uint32_t)m, v.magic_w);
+  const int w = (int)((uint32_t)m - t * (uint32_t)v.W);
+  const uint32_t n = fast_div(t, v.magic_h);
+  const int h = (int)(t - n * (uint32_t)v.H);
+  return pix_off(v, (int)n, h, w);
 }
 
 __device__ __forceinline__ void load8(const uint16_t* p, int fp16, float* f) {
@@ -79,9 +82,39 @@ int grid_for(long long total, int threads, int cap_per_sm = 16) {
 //   MODE 0 (bn_stats):      acc[c] += z, acc[C + c] += z*z
 //   MODE 1 (bn_bwd_reduce): dy' = relu-masked dy; acc[c] += dy', acc[C + c] += dy' * (z - mean) * invstd
 // ------------------------------------------------------------------------------------------
+// BN output before the activation, shared by forward and backward so that the ReLU mask the
+// backward pass recomputes from z is bit-identical to the forward's:
+//   y = fma((z - mean) * invstd, gamma, beta)      (z - mean first: exact near the mean, as torch)
+// bn_affine8 loads the four per-channel vectors: S = invstd, T = mean, G = gamma, Bt = beta.
+__device__ __forceinline__ void bn_affine8(const float* __restrict__ mean, const float* __restrict__ invstd,
+                                           const float* __restrict__ gamma, const float* __restrict__ beta, int c0, float* S, float* T,
+                                           float* G, float* Bt) {
+  const float4 m0 = __ldg(reinterpret_cast<const float4*>(mean + c0)), m1 = __ldg(reinterpret_cast<const float4*>(mean + c0 + 4));
+  const float4 i0 = __ldg(reinterpret_cast<const float4*>(invstd + c0)), i1 = __ldg(reinterpret_cast<const float4*>(invstd + c0 + 4));
+  const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c0)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c0 + 4));
+  const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c0)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c0 + 4));
+  const float mu[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+  const float is[8] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
+  const float ga[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+  const float be[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    S[j] = is[j];
+    T[j] = mu[j];
+    G[j] = ga[j];
+    Bt[j] = be[j];
+  }
+}
+
+__device__ __forceinline__ float bn_y(float z, float is, float mu, float g, float b) { return fmaf(__fmul_rn(__fsub_rn(z, mu), is), g, b); }
+
+// mask modes of the backward kernels
+enum { kMaskNone = 0, kMaskFromZ = 1, kMaskFromA = 2 };
+
 template <int MODE>
-__global__ void __launch_bounds__(256) channel_reduce_kernel(DV z, DV dy, DV a, int use_mask, const float* __restrict__ mean,
-                                                             const float* __restrict__ invstd, long long M, int rows, int fp16,
+__global__ void __launch_bounds__(256) channel_reduce_kernel(DV z, DV dy, DV a, int mask_mode, const float* __restrict__ mean,
+                                                             const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, long long M, int rows, int fp16,
                                                              double* __restrict__ acc) {
   __shared__ float red[256 * 16];
   const int c8n = z.C >> 3;
@@ -91,14 +124,8 @@ __global__ void __launch_bounds__(256) channel_reduce_kernel(DV z, DV dy, DV a, 
 #pragma unroll
   for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
   if (row < rows) {
-    float mu[8], is[8];
-    if (MODE == 1) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        mu[j] = mean[c8 * 8 + j];
-        is[j] = invstd[c8 * 8 + j];
-      }
-    }
+    float is[8], mu[8], G[8], Bt[8];
+    if (MODE == 1) bn_affine8(mean, invstd, gamma, beta, c8 * 8, is, mu, G, Bt);
     for (long long m = (long long)blockIdx.x * rows + row; m < M; m += (long long)gridDim.x * rows) {
       float zv[8];
       load8(z.p + pix_off_m(z, m) + c8 * 8, fp16, zv);
@@ -111,7 +138,10 @@ __global__ void __launch_bounds__(256) channel_reduce_kernel(DV z, DV dy, DV a, 
       } else {
         float g[8];
         load8(dy.p + pix_off_m(dy, m) + c8 * 8, fp16, g);
-        if (use_mask) {
+        if (mask_mode == kMaskFromZ) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) g[j] = bn_y(zv[j], is[j], mu[j], G[j], Bt[j]) > 0.f ? g[j] : 0.f;
+        } else if (mask_mode == kMaskFromA) {
           float av[8];
           load8(a.p + pix_off_m(a, m) + c8 * 8, fp16, av);
 #pragma unroll
@@ -161,58 +191,68 @@ __global__ void bn_finalize_kernel(double* __restrict__ acc, int C, double M, fl
   acc[C + c] = 0.0;
 }
 
-// a = act(gamma * (z - mean) * invstd + beta (+ residual))
+// a = act(bn_y(z) (+ residual))
 __global__ void __launch_bounds__(256) bn_apply_kernel(DV z, DV out, DV res, int has_res, const float* __restrict__ mean,
                                                        const float* __restrict__ invstd, const float* __restrict__ gamma,
-                                                       const float* __restrict__ beta, int relu, long long total, int fp16) {
-  const int c8n = z.C >> 3;
-  for (long long idx = (long long)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (long long)gridDim.x * 256) {
-    const long long m = idx / c8n;
+                                                       const float* __restrict__ beta, int relu, uint32_t total, unsigned long long magic_c8,
+                                                       int fp16) {
+  const uint32_t c8n = (uint32_t)(z.C >> 3);
+  for (uint32_t idx = blockIdx.x * 256u + threadIdx.x; idx < total; idx += gridDim.x * 256u) {
+    const uint32_t m = fast_div(idx, magic_c8);
     const int c8 = (int)(idx - m * c8n);
-    float v[8];
+    float v[8], S[8], T[8], G[8], Bt[8];
     load8(z.p + pix_off_m(z, m) + c8 * 8, fp16, v);
-    const float4 m0 = __ldg(reinterpret_cast<const float4*>(mean + c8 * 8)), m1 = __ldg(reinterpret_cast<const float4*>(mean + c8 * 8 + 4));
-    const float4 i0 = __ldg(reinterpret_cast<const float4*>(invstd + c8 * 8)), i1 = __ldg(reinterpret_cast<const float4*>(invstd + c8 * 8 + 4));
-    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c8 * 8)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c8 * 8 + 4));
-    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c8 * 8)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c8 * 8 + 4));
-    const float mu[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
-    const float is[8] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
-    const float ga[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-    const float be[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
     float r[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (has_res) load8(res.p + pix_off_m(res, m) + c8 * 8, fp16, r);
+    bn_affine8(mean, invstd, gamma, beta, c8 * 8, S, T, G, Bt);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float y = fmaf((v[j] - mu[j]) * is[j], ga[j], be[j]) + r[j];
+      const float y = bn_y(v[j], S[j], T[j], G[j], Bt[j]) + r[j];
       v[j] = relu ? fmaxf(y, 0.f) : y;
     }
     store8(out.p + pix_off_m(out, m) + c8 * 8, fp16, v);
   }
 }
 
-// dz = gamma * invstd * (dy' - sum(dy')/M - xhat * sum(dy' * xhat)/M);  dy' = relu-masked dy.
-// Optionally routes dy' to the residual branch (written or accumulated); block 0 stores
-// dgamma = sum(dy' * xhat), dbeta = sum(dy').  dz may alias dy (in place).
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(DV dy, DV a, int use_mask, DV z, DV dz, DV dres, int res_mode,
+// per-channel coefficients of the backward elementwise pass from the float64 sums:
+//   dz = A * dy' + Bz * z + D,  A = gamma*invstd, Bz = -A*invstd*s2/M, D = A*(mean*invstd*s2/M - s1/M)
+// coef = [A | Bz | D] (3*C floats); also dgamma += s2, dbeta += s1.
+__global__ void bn_bwd_coef_kernel(const double* __restrict__ acc, int C, double inv_m, const float* __restrict__ mean,
+                                   const float* __restrict__ invstd, const float* __restrict__ gamma, float* __restrict__ coef,
+                                   float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double s1 = acc[c], s2 = acc[C + c];
+  const double is = (double)invstd[c], mu = (double)mean[c];
+  const double A = (double)gamma[c] * is;
+  coef[c] = (float)A;
+  coef[C + c] = (float)(-A * is * s2 * inv_m);
+  coef[2 * C + c] = (float)(A * (mu * is * s2 * inv_m - s1 * inv_m));
+  if (dbeta) dbeta[c] += (float)s1;
+  if (dgamma) dgamma[c] += (float)s2;
+}
+
+// dz = A * dy' + Bz * z + D with dy' = relu-masked dy; optionally routes dy' to the residual branch
+// (written or accumulated).  dz may alias dy (in place).
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(DV dy, DV a, int mask_mode, DV z, DV dz, DV dres, int res_mode,
                                                            const float* __restrict__ mean, const float* __restrict__ invstd,
-                                                           const float* __restrict__ gamma, const double* __restrict__ acc,
-                                                           float inv_m, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                           long long total, int fp16) {
-  const int C = z.C, c8n = C >> 3;
-  if (blockIdx.x == 0) {
-    for (int c = threadIdx.x; c < C; c += 256) {
-      if (dbeta) dbeta[c] += (float)acc[c];
-      if (dgamma) dgamma[c] += (float)acc[C + c];
-    }
-  }
-  for (long long idx = (long long)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (long long)gridDim.x * 256) {
-    const long long m = idx / c8n;
+                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                           const float* __restrict__ coef, uint32_t total, unsigned long long magic_c8,
+                                                           int fp16) {
+  const int C = z.C;
+  const uint32_t c8n = (uint32_t)(C >> 3);
+  for (uint32_t idx = blockIdx.x * 256u + threadIdx.x; idx < total; idx += gridDim.x * 256u) {
+    const uint32_t m = fast_div(idx, magic_c8);
     const int c8 = (int)(idx - m * c8n);
     float g[8], zv[8];
-    const long long o_dy = pix_off_m(dy, m) + c8 * 8;
-    load8(dy.p + o_dy, fp16, g);
+    load8(dy.p + pix_off_m(dy, m) + c8 * 8, fp16, g);
     load8(z.p + pix_off_m(z, m) + c8 * 8, fp16, zv);
-    if (use_mask) {
+    if (mask_mode == kMaskFromZ) {
+      float S[8], T[8], G[8], Bt[8];
+      bn_affine8(mean, invstd, gamma, beta, c8 * 8, S, T, G, Bt);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] = bn_y(zv[j], S[j], T[j], G[j], Bt[j]) > 0.f ? g[j] : 0.f;
+    } else if (mask_mode == kMaskFromA) {
       float av[8];
       load8(a.p + pix_off_m(a, m) + c8 * 8, fp16, av);
 #pragma unroll
@@ -231,15 +271,16 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(DV dy, DV a, int use_
       }
       store8(rp, fp16, r);
     }
+    const float* cA = coef + c8 * 8;
+    const float4 a0 = __ldg(reinterpret_cast<const float4*>(cA)), a1 = __ldg(reinterpret_cast<const float4*>(cA + 4));
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(cA + C)), b1 = __ldg(reinterpret_cast<const float4*>(cA + C + 4));
+    const float4 d0 = __ldg(reinterpret_cast<const float4*>(cA + 2 * C)), d1 = __ldg(reinterpret_cast<const float4*>(cA + 2 * C + 4));
+    const float A[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    const float Bz[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    const float D[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
     float o[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = c8 * 8 + j;
-      const float is = __ldg(invstd + c);
-      const float xh = (zv[j] - __ldg(mean + c)) * is;
-      const float s1 = (float)acc[c] * inv_m, s2 = (float)acc[C + c] * inv_m;
-      o[j] = __ldg(gamma + c) * is * (g[j] - s1 - xh * s2);
-    }
+    for (int j = 0; j < 8; ++j) o[j] = fmaf(A[j], g[j], fmaf(Bz[j], zv[j], D[j]));
     store8(dz.p + pix_off_m(dz, m) + c8 * 8, fp16, o);
   }
 }
@@ -409,6 +450,43 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restri
       for (int j = 0; j < 8; ++j) f[j] = (c0 + j) < Cin ? __ldg(src + (long long)(c0 + j) * plane) : 0.f;
       store8(dst + c0, fp16, f);
     }
+  }
+}
+
+// Patch matrix of the first convolution: out[n, p, q, (r*kw + s)*3 + c] = scale[c] * in[n, c, p*st - pad + r, q*st - pad + s] + shift[c]
+// (0 outside the image and for k >= kh*kw*3).  With it the Cin = 3 stem is a K = kh*kw*3 GEMM for the
+// tensor-core forward and weight-gradient kernels (a 1x1 convolution over the patch tensor).
+__global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restrict__ in, int H, int W, DV out, int kh, int kw, int stride,
+                                                          int pad, float s0, float s1, float s2, float b0, float b1, float b2,
+                                                          uint32_t total, unsigned long long magic_k8, int fp16) {
+  const uint32_t k8n = (uint32_t)(out.C >> 3);
+  const int kmax = kh * kw * 3;
+  const long long plane = (long long)H * W;
+  for (uint32_t idx = blockIdx.x * 256u + threadIdx.x; idx < total; idx += gridDim.x * 256u) {
+    const uint32_t m = fast_div(idx, magic_k8);
+    const int k0 = (int)(idx - m * k8n) * 8;
+    const uint32_t t = fast_div(m, out.magic_w);
+    const int q = (int)(m - t * (uint32_t)out.W);
+    const uint32_t n = fast_div(t, out.magic_h);
+    const int p = (int)(t - n * (uint32_t)out.H);
+    const float* src = in + (long long)n * 3 * plane;
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = k0 + j;
+      float v = 0.f;
+      if (k < kmax) {
+        const int tap = k / 3, c = k - tap * 3;
+        const int r = tap / kw, s = tap - r * kw;
+        const int hh = p * stride - pad + r, ww = q * stride - pad + s;
+        if ((unsigned)hh < (unsigned)H && (unsigned)ww < (unsigned)W) {
+          const float x = __ldg(src + c * plane + (long long)hh * W + ww);
+          v = c == 0 ? fmaf(x, s0, b0) : c == 1 ? fmaf(x, s1, b1) : fmaf(x, s2, b2);
+        }
+      }
+      f[j] = v;
+    }
+    store8(out.p + pix_off(out, (int)n, p, q) + k0, fp16, f);
   }
 }
 
@@ -639,7 +717,8 @@ extern "C" int ifcb_bn_stats(const ifcb_view* z, int batch, int dtype, float eps
   const int rows = reduce_rows(z->C);
   const int grid = grid_for((M + rows - 1) / rows, 8, 4);       // ~8 pixel rows per thread at least
   DV zz = dv(z);
-  channel_reduce_kernel<0><<<grid, 256, 0, STREAM(stream)>>>(zz, zz, zz, 0, nullptr, nullptr, M, rows, dtype, d_acc);
+  IFCB_ARG_CHECK(M < (1ll << 31) / (z->C / 8), "bn_stats: tensor too large for 32-bit indexing");
+  channel_reduce_kernel<0><<<grid, 256, 0, STREAM(stream)>>>(zz, zz, zz, 0, nullptr, nullptr, nullptr, nullptr, M, rows, dtype, d_acc);
   bn_finalize_kernel<<<(z->C + 127) / 128, 128, 0, STREAM(stream)>>>(d_acc, z->C, (double)M, eps, momentum, d_mean, d_invstd,
                                                                       d_running_mean, d_running_var);
   IFCB_CUDA_CHECK(cudaGetLastError());
@@ -655,34 +734,43 @@ extern "C" int ifcb_bn_apply(const ifcb_view* z, const ifcb_view* out, const ifc
                  "bn_apply: residual extent differs");
   IFCB_ARG_CHECK(d_mean && d_invstd && d_gamma && d_beta, "bn_apply: null pointer");
   const long long total = (long long)batch * z->H * z->W * (z->C / 8);
+  IFCB_ARG_CHECK(total < (1ll << 31), "bn_apply: tensor too large for 32-bit indexing");
   DV zz = dv(z);
   bn_apply_kernel<<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(zz, dv(out), residual ? dv(residual) : zz, residual ? 1 : 0, d_mean,
-                                                                     d_invstd, d_gamma, d_beta, relu, total, dtype);
+                                                                     d_invstd, d_gamma, d_beta, relu, (uint32_t)total,
+                                                                     div_magic(z->C / 8), dtype);
   IFCB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
 
 extern "C" int ifcb_bn_backward(const ifcb_view* dy, const ifcb_view* a, const ifcb_view* z, const ifcb_view* dz,
-                                const ifcb_view* dres, int dres_accumulate, int batch, int dtype, const float* d_mean,
-                                const float* d_invstd, const float* d_gamma, double* d_acc, float* d_dgamma, float* d_dbeta,
-                                void* stream) {
+                                const ifcb_view* dres, int dres_accumulate, int relu, int batch, int dtype, const float* d_mean,
+                                const float* d_invstd, const float* d_gamma, const float* d_beta, double* d_acc, float* d_dgamma,
+                                float* d_dbeta, void* stream) {
   IFCB_ARG_CHECK(view_ok(dy) && view_ok(z) && view_ok(dz) && batch > 0 && DT_OK(dtype), "bn_backward: bad view / batch / dtype");
   IFCB_ARG_CHECK(z->C <= 2048, "bn_backward: C=%d > 2048", z->C);
   IFCB_ARG_CHECK(dy->C == z->C && dz->C == z->C && dy->H == z->H && dy->W == z->W && dz->H == z->H && dz->W == z->W,
                  "bn_backward: extents differ");
   IFCB_ARG_CHECK(!a || (view_ok(a) && a->C == z->C && a->H == z->H && a->W == z->W), "bn_backward: mask extent differs");
   IFCB_ARG_CHECK(!dres || (view_ok(dres) && dres->C == z->C && dres->H == z->H && dres->W == z->W), "bn_backward: dres extent differs");
-  IFCB_ARG_CHECK(d_mean && d_invstd && d_gamma && d_acc, "bn_backward: null pointer");
+  IFCB_ARG_CHECK(d_mean && d_invstd && d_gamma && d_beta && d_acc, "bn_backward: null pointer");
+  IFCB_ARG_CHECK(!relu || !dres || a, "bn_backward: ReLU after a residual add needs the forward output `a` for the mask");
   const long long M = (long long)batch * z->H * z->W;
+  const long long total = M * (z->C / 8);
+  IFCB_ARG_CHECK(total < (1ll << 31), "bn_backward: tensor too large for 32-bit indexing");
+  // ReLU mask: recomputed from z (bit-identical to the forward, saves reading `a`) unless a residual was added
+  const int mask_mode = !relu ? kMaskNone : (dres ? kMaskFromA : kMaskFromZ);
   const int rows = reduce_rows(z->C);
   DV zz = dv(z), dyy = dv(dy);
+  float* coef = reinterpret_cast<float*>(d_acc + 2 * z->C);
   IFCB_CUDA_CHECK(cudaMemsetAsync(d_acc, 0, sizeof(double) * 2 * z->C, STREAM(stream)));
-  channel_reduce_kernel<1><<<grid_for((M + rows - 1) / rows, 8, 4), 256, 0, STREAM(stream)>>>(zz, dyy, a ? dv(a) : zz, a ? 1 : 0, d_mean,
-                                                                                                d_invstd, M, rows, dtype, d_acc);
-  const long long total = M * (z->C / 8);
-  bn_bwd_apply_kernel<<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(dyy, a ? dv(a) : zz, a ? 1 : 0, zz, dv(dz), dres ? dv(dres) : zz,
+  channel_reduce_kernel<1><<<grid_for((M + rows - 1) / rows, 8, 4), 256, 0, STREAM(stream)>>>(zz, dyy, a ? dv(a) : zz, mask_mode, d_mean,
+                                                                                                d_invstd, d_gamma, d_beta, M, rows, dtype, d_acc);
+  bn_bwd_coef_kernel<<<(z->C + 127) / 128, 128, 0, STREAM(stream)>>>(d_acc, z->C, 1.0 / (double)M, d_mean, d_invstd, d_gamma, coef, d_dgamma,
+                                                                      d_dbeta);
+  bn_bwd_apply_kernel<<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(dyy, a ? dv(a) : zz, mask_mode, zz, dv(dz), dres ? dv(dres) : zz,
                                                                          dres ? (dres_accumulate ? 2 : 1) : 0, d_mean, d_invstd, d_gamma,
-                                                                         d_acc, 1.f / (float)M, d_dgamma, d_dbeta, total, dtype);
+                                                                         d_beta, coef, (uint32_t)total, div_magic(z->C / 8), dtype);
   IFCB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -753,6 +841,21 @@ extern "C" int ifcb_nchw_to_nhwc(const float* d_in, int Cin, const ifcb_view* ou
   IFCB_ARG_CHECK(d_in && view_ok(out) && batch > 0 && Cin > 0 && Cin <= out->C && DT_OK(dtype), "nchw_to_nhwc: bad argument");
   const long long total = (long long)batch * out->H * out->W;
   nchw_to_nhwc_kernel<<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(d_in, Cin, dv(out), total, dtype);
+  IFCB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int ifcb_stem_im2col(const float* d_in, int H, int W, const ifcb_view* out, int batch, int kh, int kw, int stride, int pad,
+                                const float* h_scale, const float* h_shift, int dtype, void* stream) {
+  IFCB_ARG_CHECK(d_in && view_ok(out) && batch > 0 && DT_OK(dtype), "stem_im2col: bad argument");
+  IFCB_ARG_CHECK(kh >= 1 && kw >= 1 && stride >= 1 && pad >= 0 && out->C >= kh * kw * 3, "stem_im2col: bad window / channel count");
+  IFCB_ARG_CHECK(out->H == (H + 2 * pad - kh) / stride + 1 && out->W == (W + 2 * pad - kw) / stride + 1, "stem_im2col: output extent differs");
+  const long long total = (long long)batch * out->H * out->W * (out->C / 8);
+  IFCB_ARG_CHECK(total < (1ll << 31), "stem_im2col: tensor too large for 32-bit indexing");
+  const float sc[3] = {h_scale ? h_scale[0] : 1.f, h_scale ? h_scale[1] : 1.f, h_scale ? h_scale[2] : 1.f};
+  const float sh[3] = {h_shift ? h_shift[0] : 0.f, h_shift ? h_shift[1] : 0.f, h_shift ? h_shift[2] : 0.f};
+  stem_im2col_kernel<<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(d_in, H, W, dv(out), kh, kw, stride, pad, sc[0], sc[1], sc[2], sh[0],
+                                                                        sh[1], sh[2], (uint32_t)total, div_magic(out->C / 8), dtype);
   IFCB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

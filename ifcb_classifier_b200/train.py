@@ -22,7 +22,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import ViewDesc, WgradDesc, IFCB_STEM_IN_F32_NCHW
+from ._lib import ViewDesc, WgradDesc
 from .graph import PlanBuilder, View, RESNET_CFG
 from .sharding import plan_buckets, GradReducer
 
@@ -124,7 +124,7 @@ class TrainNet(object):
         self.inp = torch.zeros((batch, 3, self.R, self.R), dtype=torch.float32, device=self.device)
         self.labels = torch.zeros((batch,), dtype=torch.int64, device=self.device)
         self.loss = torch.zeros((2,), dtype=torch.float32, device=self.device)     # [main + aux (weighted), unused]
-        self.acc = torch.zeros((2 * 2048,), dtype=torch.float64, device=self.device)
+        self.acc = torch.zeros((4 * 2048,), dtype=torch.float64, device=self.device)   # 2C float64 sums + 3C float32 coefficients
         if arch == 'inception_v3':
             _build_inception_train(self, sd)
         elif arch in RESNET_CFG:
@@ -179,16 +179,30 @@ class TrainNet(object):
         """Conv2d(bias=False) -> BatchNorm2d(train) [-> + residual] [-> ReLU]; returns the activation view."""
         w = sd[conv + '.weight'].float()
         Co, Ci, kh, kw = [int(s) for s in w.shape]
-        H, W = (self.R, self.R) if stem else (x.H, x.W)
+        stem_geom = None
+        if stem:
+            # Cin = 3: build the patch matrix once per step (ifcb_stem_im2col) and run the stem as a 1x1
+            # convolution with Cin = K8 = round_up(kh*kw*3, 8) on the tensor-core forward / wgrad kernels
+            assert Ci == 3 and stride[0] == stride[1] and pad[0] == pad[1]
+            P = (self.R + 2 * pad[0] - kh) // stride[0] + 1
+            K8 = ((kh * kw * 3 + 7) // 8) * 8
+            x = self.alloc(P, P, K8)
+            xd_ = _vd(x)
+            stem_geom = dict(kh=kh, kw=kw, stride=stride, pad=pad)
+            st, pd_, R_ = stride[0], pad[0], self.R
+            self.fwd.append(lambda kh=kh, kw=kw: self._call('ifcb_stem_im2col', self.inp.data_ptr(), R_, R_, C.byref(xd_), self.batch, kh, kw,
+                                                            st, pd_, None, None, self.cdtype, self._stream()))
+            w1 = torch.zeros((Co, K8, 1, 1))
+            w1[:, :kh * kw * 3, 0, 0] = w.permute(0, 2, 3, 1).reshape(Co, kh * kw * 3)      # k = (r*kw + s)*3 + c
+            w, Ci, kh, kw, stride, pad = w1, K8, 1, 1, (1, 1), (0, 0)
+        H, W = x.H, x.W
         P = (H + 2 * pad[0] - kh) // stride[0] + 1
         Q = (W + 2 * pad[1] - kw) // stride[1] + 1
         if out is None:
             out = self.alloc(P, Q, Co, out_pad)
         z = self.alloc(P, Q, Co)
-        ci_m = 8 if stem else Ci
-        master = torch.zeros((Co, kh * kw, ci_m))
-        master[:, :, :Ci] = w.permute(0, 2, 3, 1).reshape(Co, kh * kw, Ci)
-        pw = self._param(conv + '.weight', master, 'conv', dict(Ci=Ci, kh=kh, kw=kw))
+        master = w.permute(0, 2, 3, 1).reshape(Co, kh * kw, Ci).contiguous()
+        pw = self._param(conv + '.weight', master, 'stem' if stem else 'conv', dict(Ci=Ci, kh=kh, kw=kw, stem=stem_geom))
         pg = self._param(bn + '.weight', sd[bn + '.weight'], 'vec')
         pb = self._param(bn + '.bias', sd[bn + '.bias'], 'vec')
         rm = self._f32(Co); rm.copy_(sd[bn + '.running_mean'])
@@ -198,17 +212,8 @@ class TrainNet(object):
         mean, invstd = self._f32(Co), self._f32(Co)
         ones, zeros = torch.ones(Co), torch.zeros(Co)
         li = len(self.fp.layer_names)
-        if stem:
-            self.fp.stem(self.inp, IFCB_STEM_IN_F32_NCHW, H, W, w, ones, zeros, stride[0], pad[0], z, name=conv, relu=False)
-            wstem = self.fp.keep[-3]                                 # the [taps*3, Co] fp32 operand pb.stem uploaded
-            assert wstem.shape == (kh * kw * 3, Co)
-            x8 = self.alloc(H, W, 8)
-            self.repacks.append(lambda: self._call('ifcb_stem_repack', pw.wptr, Co, kh * kw, 8, wstem.data_ptr(), self._stream()))
-            wf = None
-        else:
-            self.fp.conv(x, [dict(weight=w, scale=ones, shift=zeros, relu=False, out=z)], stride, pad, name=conv)
-            wf = self.fp.keep[-3]                                    # packed [Cout_pad, K_pad] 16-bit operand
-            x8 = None
+        self.fp.conv(x, [dict(weight=w, scale=ones, shift=zeros, relu=False, out=z)], stride, pad, name=conv)
+        wf = self.fp.keep[-3]                                        # packed [Cout_pad, K_pad] 16-bit operand
         zd, od = _vd(z), _vd(out)
         rd = _vd(residual) if residual is not None else None
         B, dt = self.batch, self.cdtype
@@ -222,8 +227,8 @@ class TrainNet(object):
                        invstd.data_ptr(), pg.wptr, pb.wptr, 1 if relu else 0, self._stream())
             self.buffers[bn_key] += 1
         self.fwd.append(fwd)
-        self.records.append(dict(kind='conv_bn', x=x, x8=x8, z=z, out=out, residual=residual, relu=relu, stride=stride, pad=pad,
-                                 pw=pw, pg=pg, pb=pb, mean=mean, invstd=invstd, wf=wf, Co=Co, Ci=Ci, kh=kh, kw=kw, stem=stem,
+        self.records.append(dict(kind='conv_bn', x=x, z=z, out=out, residual=residual, relu=relu, stride=stride, pad=pad,
+                                 pw=pw, pg=pg, pb=pb, mean=mean, invstd=invstd, wf=wf, Co=Co, Ci=Ci, kh=kh, kw=kw, stem=stem_geom,
                                  H=H, W=W, name=conv))
         return out
 
@@ -357,42 +362,37 @@ class TrainNet(object):
         relu = rec['relu']
 
         def bn_bwd():
-            self._call('ifcb_bn_backward', C.byref(dyd), C.byref(od) if relu else None, C.byref(zd),
-                       C.byref(dzd), C.byref(dres_d) if dres_d is not None else None, 1 if res_acc else 0, B, dt, mean.data_ptr(),
-                       invstd.data_ptr(), pg.wptr, self.acc.data_ptr(), pg.gptr, pb.gptr, self._stream())
+            self._call('ifcb_bn_backward', C.byref(dyd), C.byref(od) if (relu and dres_d is not None) else None, C.byref(zd),
+                       C.byref(dzd), C.byref(dres_d) if dres_d is not None else None, 1 if res_acc else 0, 1 if relu else 0, B, dt,
+                       mean.data_ptr(), invstd.data_ptr(), pg.wptr, pb.wptr, self.acc.data_ptr(), pg.gptr, pb.gptr, self._stream())
         self.bwd.append(bn_bwd)
         # weight gradient: dW[co, tap, ci] += sum dz * x
         wd = WgradDesc()
-        xin = rec['x8'] if rec['stem'] else x
+        xin = x
         wd.d_in, wd.in_ld, wd.Cin = xin.ptr, xin.ld, xin.C
         wd.batch, wd.H, wd.W = B, rec['H'], rec['W']
         wd.in_pad_h, wd.in_pad_w = xin.pad
         wd.kh, wd.kw, wd.stride_h, wd.stride_w, wd.pad_h, wd.pad_w = kh, kw, stride[0], stride[1], pad[0], pad[1]
         wd.d_dout, wd.dout_ld, wd.Cout = dz.ptr, dz.ld, Co
         wd.dtype = dt
-        if rec['stem']:
-            x8d = _vd(xin)
-
-            def wgrad():
-                self._call('ifcb_nchw_to_nhwc', self.inp.data_ptr(), 3, C.byref(x8d), B, dt, self._stream())
-                wd.d_dweight = pw.gptr
-                self._call('ifcb_conv_wgrad', C.byref(wd), self._stream())
-            self.bwd.append(wgrad)
-            return pw.off
 
         def wgrad():
             wd.d_dweight = pw.gptr
             self._call('ifcb_conv_wgrad', C.byref(wd), self._stream())
         self.bwd.append(wgrad)
+        geo_f = _lib.conv_geometry(Ci, Co, kh, kw)
+        wf = rec['wf']
+        assert wf.shape[1] == kh * kw * geo_f['Cin_pad'], wf.shape
+        if rec['stem'] is not None:                                  # network input: no data gradient
+            self.repacks.append(lambda: self._call('ifcb_conv_repack', pw.wptr, Co, kh * kw, Ci, wf.data_ptr(), geo_f['Cin_pad'],
+                                                   None, 0, dt, self._stream()))
+            return pw.off
         # data gradient: stride-1 conv of (dilated) dz with the flipped, transposed filter
         dx = self.grad_of(x)
         acc = claim(x)
         dg = build_dgrad(self.bp, dz, dx, Co, Ci, kh, kw, stride, pad, acc, name='dgrad.' + rec['name'])
         self.bwd.extend(dg['run'])
         wdg = dg['weight']
-        geo_f = _lib.conv_geometry(Ci, Co, kh, kw)
-        wf = rec['wf']
-        assert wf.shape[1] == kh * kw * geo_f['Cin_pad'], wf.shape
         self.repacks.append(lambda: self._call('ifcb_conv_repack', pw.wptr, Co, kh * kw, Ci, wf.data_ptr(), geo_f['Cin_pad'],
                                                wdg.data_ptr(), dg['Cin_pad'], dt, self._stream()))
         return pw.off
@@ -451,6 +451,9 @@ class TrainNet(object):
             if p.kind == 'conv':
                 Ci, kh, kw = p.meta['Ci'], p.meta['kh'], p.meta['kw']
                 t = t[:, :, :Ci].reshape(p.shape[0], kh, kw, Ci).permute(0, 3, 1, 2)
+            elif p.kind == 'stem':                               # [Co, 1, K8], k = (r*kw + s)*3 + c
+                g = p.meta['stem']
+                t = t[:, 0, :g['kh'] * g['kw'] * 3].reshape(p.shape[0], g['kh'], g['kw'], 3).permute(0, 3, 1, 2)
             out[p.name] = t.detach().clone().contiguous()
         return out
 

@@ -221,15 +221,16 @@ int ifcb_bn_apply(const ifcb_view* z, const ifcb_view* out, const ifcb_view* res
                   int relu, void* stream);
 /* Backward of (BN train -> [+residual] -> [ReLU]) -- autograd's threshold_backward +
  * native_batch_norm_backward:
- *   dy' = dy * [a > 0]            (a = the forward output; NULL: no ReLU)
+ *   dy' = dy * [forward output > 0]   (relu = 1; the mask is recomputed from z with the forward's own
+ *                                      arithmetic, or read from `a` -- required -- when a residual was added)
  *   dz  = gamma*invstd*(dy' - mean(dy') - xhat*mean(dy'*xhat)),  xhat = (z-mean)*invstd
  *   d_dgamma[C] += sum(dy'*xhat), d_dbeta[C] += sum(dy')
  *   dres (optional, the residual branch's gradient) = or += dy'
- * dz may alias dy.  d_acc: 2*C float64 scratch. */
+ * dz may alias dy.  d_acc: scratch of 2*C float64 followed by 3*C float32 (4*C*8 bytes is enough). */
 int ifcb_bn_backward(const ifcb_view* dy, const ifcb_view* a, const ifcb_view* z, const ifcb_view* dz,
-                     const ifcb_view* dres, int dres_accumulate, int batch, int dtype,
-                     const float* d_mean, const float* d_invstd, const float* d_gamma, double* d_acc,
-                     float* d_dgamma, float* d_dbeta, void* stream);
+                     const ifcb_view* dres, int dres_accumulate, int relu, int batch, int dtype,
+                     const float* d_mean, const float* d_invstd, const float* d_gamma, const float* d_beta,
+                     double* d_acc, float* d_dgamma, float* d_dbeta, void* stream);
 
 /* Pooling for the TRAIN step.  max: F.max_pool2d forward recording the winning tap (first maximum
  * in row-major window order, uint8 [batch,P,Q,C]) and its backward; avg: F.avg_pool2d with
@@ -250,6 +251,13 @@ int ifcb_avgpool_bwd(const ifcb_view* dy, const ifcb_view* dx, int accumulate, i
 int ifcb_dilate(const ifcb_view* in, const ifcb_view* out, int batch, int stride_h, int stride_w, void* stream);
 /* float32 NCHW [batch,Cin,H,W] -> 16-bit NHWC view (channels >= Cin zero): stem input for ifcb_conv_wgrad. */
 int ifcb_nchw_to_nhwc(const float* d_in, int Cin, const ifcb_view* out, int batch, int dtype, void* stream);
+
+/* Patch matrix of the first convolution (Cin = 3): float32 NCHW [batch,3,H,W] -> 16-bit NHWC view
+ * [batch, P, Q, K8], channel k = (r*kw + s)*3 + c holds scale[c]*in[n,c,p*stride-pad+r,q*stride-pad+s]+shift[c]
+ * (0 outside the image and for k >= kh*kw*3; h_scale/h_shift: torchvision transform_input, NULL = identity).
+ * The stem then runs as a 1x1 convolution with Cin = K8 on the tcgen05 forward / weight-gradient kernels. */
+int ifcb_stem_im2col(const float* d_in, int H, int W, const ifcb_view* out, int batch, int kh, int kw, int stride,
+                     int pad, const float* h_scale, const float* h_shift, int dtype, void* stream);
 
 /* Train-mode head: adaptive_avg_pool2d(1) -> dropout scale -> Linear -> CrossEntropyLoss(mean)
  * (inception.py:147-153 / resnet.py avgpool+fc; NeustonModel.loss neuston_models.py:70-80).

@@ -57,10 +57,16 @@ def local_parity(net, eps_of, tol=2.0 ** -7):
             pw, pg, pb = rec['pw'], rec['pg'], rec['pb']
             Ci, kh, kw, Co = rec['Ci'], rec['kh'], rec['kw'], rec['Co']
             w = pw.w[:, :, :Ci].reshape(Co, kh, kw, Ci).permute(0, 3, 1, 2).contiguous()
-            if rec['stem']:
-                x_in, w_op = net.inp.clone(), w.clone()                 # fp32 direct conv
-            else:
-                x_in, w_op = _nchw(rec['x']), q(w)
+            if rec['stem'] is not None:
+                # the patch matrix the 1x1 GEMM reads: k = (r*kw + s)*3 + c of the 16-bit rounded input
+                g = rec['stem']
+                taps = g['kh'] * g['kw']
+                u = F.unfold(q(net.inp), (g['kh'], g['kw']), padding=g['pad'], stride=g['stride'])
+                u = u.view(net.batch, 3, taps, rec['H'], rec['W']).permute(0, 2, 1, 3, 4).reshape(net.batch, taps * 3, rec['H'], rec['W'])
+                got = _nchw(rec['x'])
+                _check(nm + ':patches', got[:, :taps * 3], u, 0.0, stats)
+                _check(nm + ':patch_pad', got[:, taps * 3:].abs().sum().view(1), torch.zeros(1, device=got.device), 0.0, stats)
+            x_in, w_op = _nchw(rec['x']), q(w)
             x_in.requires_grad_(True)
             w_op.requires_grad_(True)
             z_exp = F.conv2d(x_in, w_op, stride=rec['stride'], padding=rec['pad'])
@@ -85,14 +91,10 @@ def local_parity(net, eps_of, tol=2.0 ** -7):
             if res is not None:
                 add(rec['residual'], res.grad)
             # conv backward from OUR dz
-            x_w = x_in if not rec['stem'] else q(net.inp).requires_grad_(True)      # the stem's wgrad reads a 16-bit copy
-            if rec['stem']:
-                F.conv2d(x_w, w_op, stride=rec['stride'], padding=rec['pad']).backward(dz_ours)
-            else:
-                z_exp.backward(dz_ours)
+            z_exp.backward(dz_ours)
             dW = pw.g[:, :, :Ci].reshape(Co, kh, kw, Ci).permute(0, 3, 1, 2)
             _check(nm + ':dW', dW, w_op.grad, tol, stats)
-            if not rec['stem']:
+            if rec['stem'] is None:
                 add(rec['x'], x_in.grad)
         elif kind in ('maxpool', 'avgpool'):
             x_in = _nchw(rec['x']).requires_grad_(True)
