@@ -84,38 +84,50 @@ int grid_for(long long total, int threads, int cap_per_sm = 16) {
 // ------------------------------------------------------------------------------------------
 // BN output before the activation, shared by forward and backward so that the ReLU mask the
 // backward pass recomputes from z is bit-identical to the forward's:
-//   y = fma((z - mean) * invstd, gamma, beta)      (z - mean first: exact near the mean, as torch)
-// bn_affine8 loads the four per-channel vectors: S = invstd, T = mean, G = gamma, Bt = beta.
-__device__ __forceinline__ void bn_affine8(const float* __restrict__ mean, const float* __restrict__ invstd,
-                                           const float* __restrict__ gamma, const float* __restrict__ beta, int c0, float* S, float* T,
-                                           float* G, float* Bt) {
-  const float4 m0 = __ldg(reinterpret_cast<const float4*>(mean + c0)), m1 = __ldg(reinterpret_cast<const float4*>(mean + c0 + 4));
-  const float4 i0 = __ldg(reinterpret_cast<const float4*>(invstd + c0)), i1 = __ldg(reinterpret_cast<const float4*>(invstd + c0 + 4));
-  const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c0)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c0 + 4));
-  const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c0)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c0 + 4));
-  const float mu[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
-  const float is[8] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
-  const float ga[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-  const float be[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    S[j] = is[j];
-    T[j] = mu[j];
-    G[j] = ga[j];
-    Bt[j] = be[j];
-  }
+//   y = fma(z - mean, S, beta),  S = gamma * invstd      (z - mean first: exact near the mean)
+// bn_params8 loads the three per-channel vectors a thread keeps in registers.
+__device__ __forceinline__ void ldg8(const float* __restrict__ p, float* f) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p + 4));
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
 }
 
-__device__ __forceinline__ float bn_y(float z, float is, float mu, float g, float b) { return fmaf(__fmul_rn(__fsub_rn(z, mu), is), g, b); }
+__device__ __forceinline__ void bn_params8(const float* __restrict__ mean, const float* __restrict__ invstd,
+                                           const float* __restrict__ gamma, const float* __restrict__ beta, int c0, float* mu, float* S,
+                                           float* Bt) {
+  float is[8], ga[8];
+  ldg8(mean + c0, mu);
+  ldg8(invstd + c0, is);
+  ldg8(gamma + c0, ga);
+  ldg8(beta + c0, Bt);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) S[j] = __fmul_rn(ga[j], is[j]);
+}
+
+__device__ __forceinline__ float bn_y(float z, float mu, float S, float b) { return fmaf(__fsub_rn(z, mu), S, b); }
 
 // mask modes of the backward kernels
 enum { kMaskNone = 0, kMaskFromZ = 1, kMaskFromA = 2 };
 
-template <int MODE>
-__global__ void __launch_bounds__(256) channel_reduce_kernel(DV z, DV dy, DV a, int mask_mode, const float* __restrict__ mean,
-                                                             const float* __restrict__ invstd, const float* __restrict__ gamma,
-                                                             const float* __restrict__ beta, long long M, int rows, int fp16,
-                                                             double* __restrict__ acc) {
+constexpr int kUnroll = 4;   // pixel rows in flight per thread in the streaming kernels
+
+__device__ __forceinline__ uint4 ld16(const uint16_t* p) { return *reinterpret_cast<const uint4*>(p); }
+
+__device__ __forceinline__ void cvt8(const uint4& v, int fp16, float* f) {
+  const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 t = unpack_act2(u[j], fp16);
+    f[2 * j] = t.x;
+    f[2 * j + 1] = t.y;
+  }
+}
+
+// MODE 0: sums of z and z*z.   MODE 1: sums of dy' and dy' * (z - mean) (scaled by invstd at the end).
+template <int MODE, int MASK>
+__global__ void __launch_bounds__(256, 2) channel_reduce_kernel(DV z, DV dy, DV a, const float* __restrict__ mean,
+                                                                const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                                                const float* __restrict__ beta, long long M, int rows, int fp16,
+                                                                double* __restrict__ acc) {
   __shared__ float red[256 * 16];
   const int c8n = z.C >> 3;
   const int tid = threadIdx.x;
@@ -124,35 +136,63 @@ __global__ void __launch_bounds__(256) channel_reduce_kernel(DV z, DV dy, DV a, 
 #pragma unroll
   for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
   if (row < rows) {
-    float is[8], mu[8], G[8], Bt[8];
-    if (MODE == 1) bn_affine8(mean, invstd, gamma, beta, c8 * 8, is, mu, G, Bt);
-    for (long long m = (long long)blockIdx.x * rows + row; m < M; m += (long long)gridDim.x * rows) {
-      float zv[8];
-      load8(z.p + pix_off_m(z, m) + c8 * 8, fp16, zv);
-      if (MODE == 0) {
+    float mu[8], S[8], Bt[8];
+    if (MODE == 1) {
+      if (MASK == kMaskFromZ) bn_params8(mean, invstd, gamma, beta, c8 * 8, mu, S, Bt);
+      else ldg8(mean + c8 * 8, mu);
+    }
+    const long long stride = (long long)gridDim.x * rows;
+    for (long long m0 = (long long)blockIdx.x * rows + row; m0 < M; m0 += stride * kUnroll) {
+      uint4 zr[kUnroll], gr[kUnroll], ar[kUnroll];
+      // all loads of the kUnroll rows first (independent), then the arithmetic
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          s1[j] += zv[j];
-          s2[j] = fmaf(zv[j], zv[j], s2[j]);
-        }
-      } else {
-        float g[8];
-        load8(dy.p + pix_off_m(dy, m) + c8 * 8, fp16, g);
-        if (mask_mode == kMaskFromZ) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) g[j] = bn_y(zv[j], is[j], mu[j], G[j], Bt[j]) > 0.f ? g[j] : 0.f;
-        } else if (mask_mode == kMaskFromA) {
-          float av[8];
-          load8(a.p + pix_off_m(a, m) + c8 * 8, fp16, av);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) g[j] = av[j] > 0.f ? g[j] : 0.f;
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          s1[j] += g[j];
-          s2[j] = fmaf(g[j], (zv[j] - mu[j]) * is[j], s2[j]);
+      for (int u = 0; u < kUnroll; ++u) {
+        const long long m = m0 + u * stride;
+        if (m < M) {
+          zr[u] = ld16(z.p + pix_off_m(z, m) + c8 * 8);
+          if (MODE == 1) {
+            gr[u] = ld16(dy.p + pix_off_m(dy, m) + c8 * 8);
+            if (MASK == kMaskFromA) ar[u] = ld16(a.p + pix_off_m(a, m) + c8 * 8);
+          }
         }
       }
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        if (m0 + u * stride < M) {
+          float zv[8];
+          cvt8(zr[u], fp16, zv);
+          if (MODE == 0) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              s1[j] += zv[j];
+              s2[j] = fmaf(zv[j], zv[j], s2[j]);
+            }
+          } else {
+            float g[8];
+            cvt8(gr[u], fp16, g);
+            if (MASK == kMaskFromZ) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) g[j] = bn_y(zv[j], mu[j], S[j], Bt[j]) > 0.f ? g[j] : 0.f;
+            } else if (MASK == kMaskFromA) {
+              float av[8];
+              cvt8(ar[u], fp16, av);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) g[j] = av[j] > 0.f ? g[j] : 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              s1[j] += g[j];
+              s2[j] = fmaf(g[j], zv[j] - mu[j], s2[j]);
+            }
+          }
+        }
+      }
+    }
+    if (MODE == 1) {
+      float is[8];
+      ldg8(invstd + c8 * 8, is);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s2[j] *= is[j];
     }
   }
 #pragma unroll
@@ -191,26 +231,43 @@ __global__ void bn_finalize_kernel(double* __restrict__ acc, int C, double M, fl
   acc[C + c] = 0.0;
 }
 
-// a = act(bn_y(z) (+ residual))
-__global__ void __launch_bounds__(256) bn_apply_kernel(DV z, DV out, DV res, int has_res, const float* __restrict__ mean,
-                                                       const float* __restrict__ invstd, const float* __restrict__ gamma,
-                                                       const float* __restrict__ beta, int relu, uint32_t total, unsigned long long magic_c8,
-                                                       int fp16) {
-  const uint32_t c8n = (uint32_t)(z.C >> 3);
-  for (uint32_t idx = blockIdx.x * 256u + threadIdx.x; idx < total; idx += gridDim.x * 256u) {
-    const uint32_t m = fast_div(idx, magic_c8);
-    const int c8 = (int)(idx - m * c8n);
-    float v[8], S[8], T[8], G[8], Bt[8];
-    load8(z.p + pix_off_m(z, m) + c8 * 8, fp16, v);
-    float r[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if (has_res) load8(res.p + pix_off_m(res, m) + c8 * 8, fp16, r);
-    bn_affine8(mean, invstd, gamma, beta, c8 * 8, S, T, G, Bt);
+// a = act(bn_y(z) (+ residual)).  Block = rows x (C/8) threads: a thread keeps the parameters of its 8
+// channels in registers and streams pixel rows, kUnroll rows in flight.
+template <bool HAS_RES>
+__global__ void __launch_bounds__(256, 3) bn_apply_kernel(DV z, DV out, DV res, const float* __restrict__ mean,
+                                                          const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta, int relu, long long M, int rows, int fp16) {
+  const int c8n = z.C >> 3;
+  const int row = threadIdx.x / c8n, c8 = threadIdx.x - row * c8n;
+  if (row >= rows) return;
+  float mu[8], S[8], Bt[8];
+  bn_params8(mean, invstd, gamma, beta, c8 * 8, mu, S, Bt);
+  const long long stride = (long long)gridDim.x * rows;
+  for (long long m0 = (long long)blockIdx.x * rows + row; m0 < M; m0 += stride * kUnroll) {
+    uint4 zr[kUnroll], rr[kUnroll];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float y = bn_y(v[j], S[j], T[j], G[j], Bt[j]) + r[j];
-      v[j] = relu ? fmaxf(y, 0.f) : y;
+    for (int u = 0; u < kUnroll; ++u) {
+      const long long m = m0 + u * stride;
+      if (m < M) {
+        zr[u] = ld16(z.p + pix_off_m(z, m) + c8 * 8);
+        if (HAS_RES) rr[u] = ld16(res.p + pix_off_m(res, m) + c8 * 8);
+      }
     }
-    store8(out.p + pix_off_m(out, m) + c8 * 8, fp16, v);
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const long long m = m0 + u * stride;
+      if (m < M) {
+        float v[8], r[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        cvt8(zr[u], fp16, v);
+        if (HAS_RES) cvt8(rr[u], fp16, r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float y = bn_y(v[j], mu[j], S[j], Bt[j]) + r[j];
+          v[j] = relu ? fmaxf(y, 0.f) : y;
+        }
+        store8(out.p + pix_off_m(out, m) + c8 * 8, fp16, v);
+      }
+    }
   }
 }
 
@@ -233,55 +290,69 @@ __global__ void bn_bwd_coef_kernel(const double* __restrict__ acc, int C, double
 }
 
 // dz = A * dy' + Bz * z + D with dy' = relu-masked dy; optionally routes dy' to the residual branch
-// (written or accumulated).  dz may alias dy (in place).
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(DV dy, DV a, int mask_mode, DV z, DV dz, DV dres, int res_mode,
-                                                           const float* __restrict__ mean, const float* __restrict__ invstd,
-                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                           const float* __restrict__ coef, uint32_t total, unsigned long long magic_c8,
-                                                           int fp16) {
-  const int C = z.C;
-  const uint32_t c8n = (uint32_t)(C >> 3);
-  for (uint32_t idx = blockIdx.x * 256u + threadIdx.x; idx < total; idx += gridDim.x * 256u) {
-    const uint32_t m = fast_div(idx, magic_c8);
-    const int c8 = (int)(idx - m * c8n);
-    float g[8], zv[8];
-    load8(dy.p + pix_off_m(dy, m) + c8 * 8, fp16, g);
-    load8(z.p + pix_off_m(z, m) + c8 * 8, fp16, zv);
-    if (mask_mode == kMaskFromZ) {
-      float S[8], T[8], G[8], Bt[8];
-      bn_affine8(mean, invstd, gamma, beta, c8 * 8, S, T, G, Bt);
+// (RES 1: written, 2: accumulated).  dz may alias dy (in place).  Same thread mapping as bn_apply_kernel,
+// two rows in flight (the six per-channel vectors already take 48 registers).
+template <int MASK, int RES>
+__global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(DV dy, DV a, DV z, DV dz, DV dres, const float* __restrict__ mean,
+                                                              const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta, const float* __restrict__ coef,
+                                                              long long M, int rows, int fp16) {
+  constexpr int U = 4;
+  const int C = z.C, c8n = C >> 3;
+  const int row = threadIdx.x / c8n, c8 = threadIdx.x - row * c8n;
+  if (row >= rows) return;
+  float mu[8], S[8], Bt[8], A[8], Bz[8], D[8];
+  if (MASK == kMaskFromZ) bn_params8(mean, invstd, gamma, beta, c8 * 8, mu, S, Bt);
+  ldg8(coef + c8 * 8, A);
+  ldg8(coef + C + c8 * 8, Bz);
+  ldg8(coef + 2 * C + c8 * 8, D);
+  const long long stride = (long long)gridDim.x * rows;
+  for (long long m0 = (long long)blockIdx.x * rows + row; m0 < M; m0 += stride * U) {
+    uint4 gr[U], zr[U], ar[U], rr[U];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) g[j] = bn_y(zv[j], S[j], T[j], G[j], Bt[j]) > 0.f ? g[j] : 0.f;
-    } else if (mask_mode == kMaskFromA) {
-      float av[8];
-      load8(a.p + pix_off_m(a, m) + c8 * 8, fp16, av);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) g[j] = av[j] > 0.f ? g[j] : 0.f;
-    }
-    if (res_mode) {
-      uint16_t* rp = dres.p + pix_off_m(dres, m) + c8 * 8;
-      float r[8];
-      if (res_mode == 2) {
-        load8(rp, fp16, r);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) r[j] += g[j];
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) r[j] = g[j];
+    for (int u = 0; u < U; ++u) {
+      const long long m = m0 + u * stride;
+      if (m < M) {
+        gr[u] = ld16(dy.p + pix_off_m(dy, m) + c8 * 8);
+        zr[u] = ld16(z.p + pix_off_m(z, m) + c8 * 8);
+        if (MASK == kMaskFromA) ar[u] = ld16(a.p + pix_off_m(a, m) + c8 * 8);
+        if (RES == 2) rr[u] = ld16(dres.p + pix_off_m(dres, m) + c8 * 8);
       }
-      store8(rp, fp16, r);
     }
-    const float* cA = coef + c8 * 8;
-    const float4 a0 = __ldg(reinterpret_cast<const float4*>(cA)), a1 = __ldg(reinterpret_cast<const float4*>(cA + 4));
-    const float4 b0 = __ldg(reinterpret_cast<const float4*>(cA + C)), b1 = __ldg(reinterpret_cast<const float4*>(cA + C + 4));
-    const float4 d0 = __ldg(reinterpret_cast<const float4*>(cA + 2 * C)), d1 = __ldg(reinterpret_cast<const float4*>(cA + 2 * C + 4));
-    const float A[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-    const float Bz[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-    const float D[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
-    float o[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = fmaf(A[j], g[j], fmaf(Bz[j], zv[j], D[j]));
-    store8(dz.p + pix_off_m(dz, m) + c8 * 8, fp16, o);
+    for (int u = 0; u < U; ++u) {
+      const long long m = m0 + u * stride;
+      if (m < M) {
+        float g[8], zv[8];
+        cvt8(gr[u], fp16, g);
+        cvt8(zr[u], fp16, zv);
+        if (MASK == kMaskFromZ) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) g[j] = bn_y(zv[j], mu[j], S[j], Bt[j]) > 0.f ? g[j] : 0.f;
+        } else if (MASK == kMaskFromA) {
+          float av[8];
+          cvt8(ar[u], fp16, av);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) g[j] = av[j] > 0.f ? g[j] : 0.f;
+        }
+        if (RES) {
+          float r[8];
+          if (RES == 2) {
+            cvt8(rr[u], fp16, r);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r[j] += g[j];
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r[j] = g[j];
+          }
+          store8(dres.p + pix_off_m(dres, m) + c8 * 8, fp16, r);
+        }
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = fmaf(A[j], g[j], fmaf(Bz[j], zv[j], D[j]));
+        store8(dz.p + pix_off_m(dz, m) + c8 * 8, fp16, o);
+      }
+    }
   }
 }
 
@@ -708,6 +779,15 @@ static int reduce_rows(int C) {
   return rows < 1 ? 1 : rows;
 }
 
+// grid of the streaming BN kernels: blocks of `rows` pixel rows, each thread kUnroll rows per sweep;
+// at most 8 resident blocks per SM (2048 threads), at least one sweep of work per block
+static int stream_grid(long long M, int rows) {
+  long long g = (M + (long long)rows * kUnroll - 1) / ((long long)rows * kUnroll);
+  const long long cap = (long long)sm_count() * 8;
+  if (g > cap) g = cap;
+  return g < 1 ? 1 : (int)g;
+}
+
 extern "C" int ifcb_bn_stats(const ifcb_view* z, int batch, int dtype, float eps, float momentum, double* d_acc, float* d_mean,
                              float* d_invstd, float* d_running_mean, float* d_running_var, void* stream) {
   IFCB_ARG_CHECK(view_ok(z) && batch > 0 && DT_OK(dtype), "bn_stats: bad view / batch / dtype");
@@ -715,10 +795,10 @@ extern "C" int ifcb_bn_stats(const ifcb_view* z, int batch, int dtype, float eps
   IFCB_ARG_CHECK(d_acc && d_mean && d_invstd, "bn_stats: null pointer");
   const long long M = (long long)batch * z->H * z->W;
   const int rows = reduce_rows(z->C);
-  const int grid = grid_for((M + rows - 1) / rows, 8, 4);       // ~8 pixel rows per thread at least
+  const int grid = stream_grid(M, rows);
   DV zz = dv(z);
   IFCB_ARG_CHECK(M < (1ll << 31) / (z->C / 8), "bn_stats: tensor too large for 32-bit indexing");
-  channel_reduce_kernel<0><<<grid, 256, 0, STREAM(stream)>>>(zz, zz, zz, 0, nullptr, nullptr, nullptr, nullptr, M, rows, dtype, d_acc);
+  channel_reduce_kernel<0, kMaskNone><<<grid, 256, 0, STREAM(stream)>>>(zz, zz, zz, nullptr, nullptr, nullptr, nullptr, M, rows, dtype, d_acc);
   bn_finalize_kernel<<<(z->C + 127) / 128, 128, 0, STREAM(stream)>>>(d_acc, z->C, (double)M, eps, momentum, d_mean, d_invstd,
                                                                       d_running_mean, d_running_var);
   IFCB_CUDA_CHECK(cudaGetLastError());
@@ -733,12 +813,17 @@ extern "C" int ifcb_bn_apply(const ifcb_view* z, const ifcb_view* out, const ifc
   IFCB_ARG_CHECK(!residual || (view_ok(residual) && residual->C == z->C && residual->H == z->H && residual->W == z->W),
                  "bn_apply: residual extent differs");
   IFCB_ARG_CHECK(d_mean && d_invstd && d_gamma && d_beta, "bn_apply: null pointer");
-  const long long total = (long long)batch * z->H * z->W * (z->C / 8);
-  IFCB_ARG_CHECK(total < (1ll << 31), "bn_apply: tensor too large for 32-bit indexing");
+  IFCB_ARG_CHECK(z->C <= 2048, "bn_apply: C=%d > 2048", z->C);
+  const long long M = (long long)batch * z->H * z->W;
+  IFCB_ARG_CHECK(M < (1ll << 31), "bn_apply: tensor too large for 32-bit indexing");
+  const int rows = reduce_rows(z->C);
   DV zz = dv(z);
-  bn_apply_kernel<<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(zz, dv(out), residual ? dv(residual) : zz, residual ? 1 : 0, d_mean,
-                                                                     d_invstd, d_gamma, d_beta, relu, (uint32_t)total,
-                                                                     div_magic(z->C / 8), dtype);
+  if (residual)
+    bn_apply_kernel<true><<<stream_grid(M, rows), 256, 0, STREAM(stream)>>>(zz, dv(out), dv(residual), d_mean, d_invstd, d_gamma, d_beta, relu,
+                                                                             M, rows, dtype);
+  else
+    bn_apply_kernel<false><<<stream_grid(M, rows), 256, 0, STREAM(stream)>>>(zz, dv(out), zz, d_mean, d_invstd, d_gamma, d_beta, relu, M, rows,
+                                                                              dtype);
   IFCB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -764,13 +849,22 @@ extern "C" int ifcb_bn_backward(const ifcb_view* dy, const ifcb_view* a, const i
   DV zz = dv(z), dyy = dv(dy);
   float* coef = reinterpret_cast<float*>(d_acc + 2 * z->C);
   IFCB_CUDA_CHECK(cudaMemsetAsync(d_acc, 0, sizeof(double) * 2 * z->C, STREAM(stream)));
-  channel_reduce_kernel<1><<<grid_for((M + rows - 1) / rows, 8, 4), 256, 0, STREAM(stream)>>>(zz, dyy, a ? dv(a) : zz, mask_mode, d_mean,
-                                                                                                d_invstd, d_gamma, d_beta, M, rows, dtype, d_acc);
-  bn_bwd_coef_kernel<<<(z->C + 127) / 128, 128, 0, STREAM(stream)>>>(d_acc, z->C, 1.0 / (double)M, d_mean, d_invstd, d_gamma, coef, d_dgamma,
-                                                                      d_dbeta);
-  bn_bwd_apply_kernel<<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(dyy, a ? dv(a) : zz, mask_mode, zz, dv(dz), dres ? dv(dres) : zz,
-                                                                         dres ? (dres_accumulate ? 2 : 1) : 0, d_mean, d_invstd, d_gamma,
-                                                                         d_beta, coef, (uint32_t)total, div_magic(z->C / 8), dtype);
+  const int grid = stream_grid(M, rows);
+  cudaStream_t st = STREAM(stream);
+  DV av = a ? dv(a) : zz, dzv = dv(dz), drv = dres ? dv(dres) : zz;
+  const int res_mode = dres ? (dres_accumulate ? 2 : 1) : 0;
+#define IFCB_REDUCE1(MK) channel_reduce_kernel<1, MK><<<grid, 256, 0, st>>>(zz, dyy, av, d_mean, d_invstd, d_gamma, d_beta, M, rows, dtype, d_acc)
+  if (mask_mode == kMaskFromZ) IFCB_REDUCE1(kMaskFromZ);
+  else if (mask_mode == kMaskFromA) IFCB_REDUCE1(kMaskFromA);
+  else IFCB_REDUCE1(kMaskNone);
+#undef IFCB_REDUCE1
+  bn_bwd_coef_kernel<<<(z->C + 127) / 128, 128, 0, st>>>(d_acc, z->C, 1.0 / (double)M, d_mean, d_invstd, d_gamma, coef, d_dgamma, d_dbeta);
+#define IFCB_BWD_APPLY(MK, RS) \
+  bn_bwd_apply_kernel<MK, RS><<<grid, 256, 0, st>>>(dyy, av, zz, dzv, drv, d_mean, d_invstd, d_gamma, d_beta, coef, M, rows, dtype)
+  if (mask_mode == kMaskFromZ) IFCB_BWD_APPLY(kMaskFromZ, 0);               // (a residual always comes with kMaskFromA / kMaskNone)
+  else if (mask_mode == kMaskFromA) { if (res_mode == 2) IFCB_BWD_APPLY(kMaskFromA, 2); else if (res_mode == 1) IFCB_BWD_APPLY(kMaskFromA, 1); else IFCB_BWD_APPLY(kMaskFromA, 0); }
+  else { if (res_mode == 2) IFCB_BWD_APPLY(kMaskNone, 2); else if (res_mode == 1) IFCB_BWD_APPLY(kMaskNone, 1); else IFCB_BWD_APPLY(kMaskNone, 0); }
+#undef IFCB_BWD_APPLY
   IFCB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
