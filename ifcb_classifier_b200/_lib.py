@@ -41,7 +41,8 @@ class WgradDesc(C.Structure):
                 ('kh', C.c_int32), ('kw', C.c_int32), ('stride_h', C.c_int32), ('stride_w', C.c_int32),
                 ('pad_h', C.c_int32), ('pad_w', C.c_int32),
                 ('d_dout', C.c_void_p), ('dout_ld', C.c_int32), ('Cout', C.c_int32),
-                ('d_dweight', C.c_void_p), ('dtype', C.c_int32), ('in_pad_h', C.c_int32), ('in_pad_w', C.c_int32)]
+                ('d_dweight', C.c_void_p), ('dtype', C.c_int32), ('in_pad_h', C.c_int32), ('in_pad_w', C.c_int32),
+                ('dout_pad_h', C.c_int32), ('dout_pad_w', C.c_int32)]
 
 
 class ViewDesc(C.Structure):

@@ -41,6 +41,7 @@ struct WgradParams {
   int tiles_per_split;      // 128-pixel tiles per split
   int a_slots, b_stages;
   int fp16;
+  int dz_im2col;            // dz is loaded through a 4-D (1x1 window) im2col map: the gradient tensor has a zero border
   float* dW;                // [Cout][taps][Cin] fp32, accumulated into
 };
 
@@ -105,8 +106,13 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_cons
         if (ptx::elect_one()) {
           uint8_t* dst = a_base + (size_t)aslot * kATile;
           ptx::mbar_arrive_expect_tx(a_full + aslot, (uint32_t)kATile);
-          ptx::tma_load_2d(dst, &tmap_dz, a_full + aslot, co_tile * 128, m0);
-          ptx::tma_load_2d(dst + kPix * 128, &tmap_dz, a_full + aslot, co_tile * 128 + 64, m0);
+          if (p.dz_im2col) {
+            ptx::tma_load_im2col_4d(dst, &tmap_dz, a_full + aslot, co_tile * 128, oq, op, img, 0, 0);
+            ptx::tma_load_im2col_4d(dst + kPix * 128, &tmap_dz, a_full + aslot, co_tile * 128 + 64, oq, op, img, 0, 0);
+          } else {
+            ptx::tma_load_2d(dst, &tmap_dz, a_full + aslot, co_tile * 128, m0);
+            ptx::tma_load_2d(dst + kPix * 128, &tmap_dz, a_full + aslot, co_tile * 128 + 64, m0);
+          }
         }
         __syncwarp();
         if (++aslot == p.a_slots) { aslot = 0; aphase ^= 1; }
@@ -237,6 +243,7 @@ extern "C" int ifcb_conv_wgrad(const ifcb_wgrad_desc* d, void* stream_v) {
   IFCB_ARG_CHECK(d->stride_h >= 1 && d->stride_w >= 1 && d->pad_h >= 0 && d->pad_w >= 0 && d->pad_h < d->kh && d->pad_w < d->kw, "wgrad: bad stride / padding");
   IFCB_ARG_CHECK(d->dtype == IFCB_ACT_BF16 || d->dtype == IFCB_ACT_FP16, "wgrad: bad dtype");
   IFCB_ARG_CHECK(d->in_pad_h >= 0 && d->in_pad_w >= 0 && d->in_pad_h <= 8 && d->in_pad_w <= 8, "wgrad: bad in_pad");
+  IFCB_ARG_CHECK(d->dout_pad_h >= 0 && d->dout_pad_w >= 0 && d->dout_pad_h <= 8 && d->dout_pad_w <= 8, "wgrad: bad dout_pad");
   int rc = resolve_driver();
   if (rc) return rc;
   const int P = (d->H + 2 * d->pad_h - d->kh) / d->stride_h + 1, Q = (d->W + 2 * d->pad_w - d->kw) / d->stride_w + 1;
@@ -245,7 +252,24 @@ extern "C" int ifcb_conv_wgrad(const ifcb_wgrad_desc* d, void* stream_v) {
   IFCB_ARG_CHECK(rows < (1ll << 31) - 256, "wgrad: too many output pixels");
   const CUtensorMapDataType dt = d->dtype == IFCB_ACT_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   CUtensorMap tmap_dz, tmap_x;
-  {
+  const bool dz_border = d->dout_pad_h > 0 || d->dout_pad_w > 0;
+  if (dz_border) {
+    // bordered gradient tensor [batch, P+2ph, Q+2pw, ld]: enumerate its interior pixels with a 1x1-window im2col map
+    const int Pp = P + 2 * d->dout_pad_h, Qp = Q + 2 * d->dout_pad_w;
+    const char* base = reinterpret_cast<const char*>(d->d_dout) + ((size_t)d->dout_pad_h * Qp + d->dout_pad_w) * d->dout_ld * 2;
+    cuuint64_t gdim[4] = {(cuuint64_t)d->Cout, (cuuint64_t)Q, (cuuint64_t)P, (cuuint64_t)d->batch};
+    cuuint64_t gstr[3] = {(cuuint64_t)d->dout_ld * 2, (cuuint64_t)Qp * d->dout_ld * 2, (cuuint64_t)Pp * Qp * d->dout_ld * 2};
+    int lower[2] = {0, 0}, upper[2] = {0, 0};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = g_encode_im2col(&tmap_dz, dt, 4, const_cast<char*>(base), gdim, gstr, lower, upper, 64, kPix, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    IFCB_ARG_CHECK(r == CUDA_SUCCESS, "wgrad: cuTensorMapEncodeIm2col (dz) failed (%d)", (int)r);
+    const unsigned long long bytes = (unsigned long long)d->batch * Pp * Qp * d->dout_ld * 2ull;
+    int drv = 0;
+    cudaDriverGetVersion(&drv);
+    if (drv <= 13010 && bytes < 131072ull) reinterpret_cast<uint64_t*>(&tmap_dz)[1] &= ~(1ull << 21);
+  } else {
     cuuint64_t gdim[2] = {(cuuint64_t)d->Cout, (cuuint64_t)rows};
     cuuint64_t gstr[1] = {(cuuint64_t)d->dout_ld * 2};
     cuuint32_t box[2] = {64, (cuuint32_t)kPix};
@@ -296,6 +320,7 @@ extern "C" int ifcb_conv_wgrad(const ifcb_wgrad_desc* d, void* stream_v) {
   p.a_slots = 2;
   p.b_stages = 8;
   p.fp16 = d->dtype;
+  p.dz_im2col = dz_border ? 1 : 0;
   p.dW = d->d_dweight;
   const int smem = p.a_slots * kATile + p.b_stages * kBTile + 512 + 1024;
   static int attr = 0;

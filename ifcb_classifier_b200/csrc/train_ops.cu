@@ -362,14 +362,15 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(DV dy, DV a, DV z,
 // max pool forward that also records the winning tap (first maximum in window scan order, as
 // torch.nn.functional.max_pool2d) for the backward pass.  idx: uint8 [B, P, Q, C].
 __global__ void __launch_bounds__(256) maxpool_fwd_kernel(DV x, DV y, uint8_t* __restrict__ idx, int k, int stride, int pad,
-                                                          int P, int Q, long long total, int fp16) {
-  const int c8n = x.C >> 3;
-  for (long long t = (long long)blockIdx.x * 256 + threadIdx.x; t < total; t += (long long)gridDim.x * 256) {
-    const long long m = t / c8n;
+                                                          int P, int Q, uint32_t total, unsigned long long magic_c8, int fp16) {
+  const uint32_t c8n = (uint32_t)(x.C >> 3);
+  for (uint32_t t = blockIdx.x * 256u + threadIdx.x; t < total; t += gridDim.x * 256u) {
+    const uint32_t m = fast_div(t, magic_c8);
     const int c8 = (int)(t - m * c8n);
-    const int oq = (int)(m % Q);
-    const long long t2 = m / Q;
-    const int op = (int)(t2 % P), n = (int)(t2 / P);
+    const uint32_t t2 = fast_div(m, y.magic_w);
+    const int oq = (int)(m - t2 * (uint32_t)Q);
+    const uint32_t nn = fast_div(t2, y.magic_h);
+    const int op = (int)(t2 - nn * (uint32_t)P), n = (int)nn;
     const int h0 = op * stride - pad, w0 = oq * stride - pad;
     float best[8];
     int bi[8];
@@ -397,7 +398,7 @@ __global__ void __launch_bounds__(256) maxpool_fwd_kernel(DV x, DV y, uint8_t* _
     uint2 pk;
     pk.x = (uint32_t)bi[0] | ((uint32_t)bi[1] << 8) | ((uint32_t)bi[2] << 16) | ((uint32_t)bi[3] << 24);
     pk.y = (uint32_t)bi[4] | ((uint32_t)bi[5] << 8) | ((uint32_t)bi[6] << 16) | ((uint32_t)bi[7] << 24);
-    *reinterpret_cast<uint2*>(idx + m * x.C + c8 * 8) = pk;
+    *reinterpret_cast<uint2*>(idx + (long long)m * x.C + c8 * 8) = pk;
   }
 }
 
@@ -405,15 +406,17 @@ __global__ void __launch_bounds__(256) maxpool_fwd_kernel(DV x, DV y, uint8_t* _
 // sums the gradients of the output windows that cover it (deterministic, no atomics).
 template <bool AVG>
 __global__ void __launch_bounds__(256) pool_bwd_kernel(DV dy, const uint8_t* __restrict__ idx, DV dx, int accumulate, int k,
-                                                       int stride, int pad, int P, int Q, long long total, int fp16) {
-  const int c8n = dx.C >> 3;
+                                                       int stride, int pad, int P, int Q, uint32_t total, unsigned long long magic_c8,
+                                                       int fp16) {
+  const uint32_t c8n = (uint32_t)(dx.C >> 3);
   const float inv = 1.f / (float)(k * k);
-  for (long long t = (long long)blockIdx.x * 256 + threadIdx.x; t < total; t += (long long)gridDim.x * 256) {
-    const long long m = t / c8n;
+  for (uint32_t t = blockIdx.x * 256u + threadIdx.x; t < total; t += gridDim.x * 256u) {
+    const uint32_t m = fast_div(t, magic_c8);
     const int c8 = (int)(t - m * c8n);
-    const int w = (int)(m % dx.W);
-    const long long t2 = m / dx.W;
-    const int h = (int)(t2 % dx.H), n = (int)(t2 / dx.H);
+    const uint32_t t2 = fast_div(m, dx.magic_w);
+    const int w = (int)(m - t2 * (uint32_t)dx.W);
+    const uint32_t nn = fast_div(t2, dx.magic_h);
+    const int h = (int)(t2 - nn * (uint32_t)dx.H), n = (int)nn;
     float g[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     // windows op with op*stride - pad <= h <= op*stride - pad + k - 1
     int p_lo = h + pad - k + 1;
@@ -460,16 +463,17 @@ __global__ void __launch_bounds__(256) pool_bwd_kernel(DV dy, const uint8_t* __r
 }
 
 // plain average pool (count_include_pad=True, divisor k*k): F.avg_pool2d in Inception blocks / aux head
-__global__ void __launch_bounds__(256) avgpool_fwd_kernel(DV x, DV y, int k, int stride, int pad, int P, int Q, long long total,
-                                                          int fp16) {
-  const int c8n = x.C >> 3;
+__global__ void __launch_bounds__(256) avgpool_fwd_kernel(DV x, DV y, int k, int stride, int pad, int P, int Q, uint32_t total,
+                                                          unsigned long long magic_c8, int fp16) {
+  const uint32_t c8n = (uint32_t)(x.C >> 3);
   const float inv = 1.f / (float)(k * k);
-  for (long long t = (long long)blockIdx.x * 256 + threadIdx.x; t < total; t += (long long)gridDim.x * 256) {
-    const long long m = t / c8n;
+  for (uint32_t t = blockIdx.x * 256u + threadIdx.x; t < total; t += gridDim.x * 256u) {
+    const uint32_t m = fast_div(t, magic_c8);
     const int c8 = (int)(t - m * c8n);
-    const int oq = (int)(m % Q);
-    const long long t2 = m / Q;
-    const int op = (int)(t2 % P), n = (int)(t2 / P);
+    const uint32_t t2 = fast_div(m, y.magic_w);
+    const int oq = (int)(m - t2 * (uint32_t)Q);
+    const uint32_t nn = fast_div(t2, y.magic_h);
+    const int op = (int)(t2 - nn * (uint32_t)P), n = (int)nn;
     const int h0 = op * stride - pad, w0 = oq * stride - pad;
     float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int r = 0; r < k; ++r) {
@@ -542,20 +546,25 @@ __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restric
     const int p = (int)(t - n * (uint32_t)out.H);
     const float* src = in + (long long)n * 3 * plane;
     float f[8];
+    // (tap, channel) of k0 by division once, then incrementally
+    int tap = k0 / 3, c = k0 - tap * 3;
+    int r = tap / kw, sx = tap - r * kw;
+    const int h0 = p * stride - pad, w0 = q * stride - pad;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int k = k0 + j;
       float v = 0.f;
-      if (k < kmax) {
-        const int tap = k / 3, c = k - tap * 3;
-        const int r = tap / kw, s = tap - r * kw;
-        const int hh = p * stride - pad + r, ww = q * stride - pad + s;
+      if (k0 + j < kmax) {
+        const int hh = h0 + r, ww = w0 + sx;
         if ((unsigned)hh < (unsigned)H && (unsigned)ww < (unsigned)W) {
           const float x = __ldg(src + c * plane + (long long)hh * W + ww);
           v = c == 0 ? fmaf(x, s0, b0) : c == 1 ? fmaf(x, s1, b1) : fmaf(x, s2, b2);
         }
       }
       f[j] = v;
+      if (++c == 3) {
+        c = 0;
+        if (++sx == kw) { sx = 0; ++r; }
+      }
     }
     store8(out.p + pix_off(out, (int)n, p, q) + k0, fp16, f);
   }
@@ -879,7 +888,9 @@ extern "C" int ifcb_maxpool_fwd_train(const ifcb_view* x, const ifcb_view* y, ui
   IFCB_ARG_CHECK(y->C == x->C && y->H == P && y->W == Q, "maxpool_fwd_train: output extent %dx%dx%d, expected %dx%dx%d", y->H, y->W, y->C,
                  P, Q, x->C);
   const long long total = (long long)batch * P * Q * (x->C / 8);
-  maxpool_fwd_kernel<<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(dv(x), dv(y), d_idx, k, stride, pad, P, Q, total, dtype);
+  IFCB_ARG_CHECK(total < (1ll << 31), "maxpool_fwd_train: tensor too large for 32-bit indexing");
+  maxpool_fwd_kernel<<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(dv(x), dv(y), d_idx, k, stride, pad, P, Q, (uint32_t)total,
+                                                                        div_magic(x->C / 8), dtype);
   IFCB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -891,8 +902,9 @@ extern "C" int ifcb_maxpool_bwd(const ifcb_view* dy, const uint8_t* d_idx, const
   const int P = pool_out(dx->H, k, stride, pad), Q = pool_out(dx->W, k, stride, pad);
   IFCB_ARG_CHECK(dy->C == dx->C && dy->H == P && dy->W == Q, "maxpool_bwd: gradient extent differs");
   const long long total = (long long)batch * dx->H * dx->W * (dx->C / 8);
-  pool_bwd_kernel<false><<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(dv(dy), d_idx, dv(dx), accumulate, k, stride, pad, P, Q, total,
-                                                                            dtype);
+  IFCB_ARG_CHECK(total < (1ll << 31), "maxpool_bwd: tensor too large for 32-bit indexing");
+  pool_bwd_kernel<false><<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(dv(dy), d_idx, dv(dx), accumulate, k, stride, pad, P, Q,
+                                                                            (uint32_t)total, div_magic(dx->C / 8), dtype);
   IFCB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -903,7 +915,9 @@ extern "C" int ifcb_avgpool_fwd(const ifcb_view* x, const ifcb_view* y, int batc
   const int P = pool_out(x->H, k, stride, pad), Q = pool_out(x->W, k, stride, pad);
   IFCB_ARG_CHECK(y->C == x->C && y->H == P && y->W == Q, "avgpool_fwd: output extent differs");
   const long long total = (long long)batch * P * Q * (x->C / 8);
-  avgpool_fwd_kernel<<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(dv(x), dv(y), k, stride, pad, P, Q, total, dtype);
+  IFCB_ARG_CHECK(total < (1ll << 31), "avgpool_fwd: tensor too large for 32-bit indexing");
+  avgpool_fwd_kernel<<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(dv(x), dv(y), k, stride, pad, P, Q, (uint32_t)total,
+                                                                        div_magic(x->C / 8), dtype);
   IFCB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -915,8 +929,9 @@ extern "C" int ifcb_avgpool_bwd(const ifcb_view* dy, const ifcb_view* dx, int ac
   const int P = pool_out(dx->H, k, stride, pad), Q = pool_out(dx->W, k, stride, pad);
   IFCB_ARG_CHECK(dy->C == dx->C && dy->H == P && dy->W == Q, "avgpool_bwd: gradient extent differs");
   const long long total = (long long)batch * dx->H * dx->W * (dx->C / 8);
-  pool_bwd_kernel<true><<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(dv(dy), nullptr, dv(dx), accumulate, k, stride, pad, P, Q, total,
-                                                                           dtype);
+  IFCB_ARG_CHECK(total < (1ll << 31), "avgpool_bwd: tensor too large for 32-bit indexing");
+  pool_bwd_kernel<true><<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(dv(dy), nullptr, dv(dx), accumulate, k, stride, pad, P, Q,
+                                                                           (uint32_t)total, div_magic(dx->C / 8), dtype);
   IFCB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

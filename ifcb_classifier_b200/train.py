@@ -39,13 +39,15 @@ def build_dgrad(bp, dy, dx, Co, Ci, kh, kw, stride, pad, accumulate, name='dgrad
     dx (=|+=) conv_transpose(dy, W).  The transposed conv is the forward tcgen05 kernel run at stride 1
     over the (zero-dilated, for stride > 1) output gradient with padding k-1-pad and the operand
     ``ifcb_conv_repack`` writes (taps reversed, Cin/Cout swapped).  ``dy`` / ``dx``: gradient Views
-    (no border).  Returns dict(run=[closures], weight=<16-bit operand tensor>, Cin_pad=<its channel padding>)."""
+    (``dy`` may carry the zero border k-1-pad, which lets the WINDOW scheme run the transposed conv).  Returns dict(run=[closures], weight=<16-bit operand tensor>, Cin_pad=<its channel padding>)."""
     B, lib = bp.batch_cap, _lib.lib()
     run = []
     stream = lambda: C.c_void_p(torch.cuda.current_stream(bp.device).cuda_stream)
+    dpad = (kh - 1 - pad[0], kw - 1 - pad[1])                     # padding of the transposed conv
     if tuple(stride) != (1, 1):
         Hd, Wd = dx.H + 2 * pad[0] - kh + 1, dx.W + 2 * pad[1] - kw + 1
-        src = View(torch.zeros((B, Hd, Wd, Co), dtype=bp.tdtype, device=bp.device))
+        bh, bw = bp.border_for(Hd, Wd, Ci, (kh, kw), pad=dpad, Ci=Co)       # zero border if the WINDOW scheme will run it
+        src = View(torch.zeros((B, Hd + 2 * bh, Wd + 2 * bw, Co), dtype=bp.tdtype, device=bp.device), pad=(bh, bw))
         bp.keep.append(src.t)
         sd_, dd_ = _vd(dy), _vd(src)
         run.append(lambda: _lib.check(lib.ifcb_dilate(C.byref(sd_), C.byref(dd_), B, stride[0], stride[1], stream()), 'dilate'))
@@ -53,8 +55,8 @@ def build_dgrad(bp, dy, dx, Co, Ci, kh, kw, stride, pad, accumulate, name='dgrad
         src = dy
     li = len(bp.layer_names)
     wflip = torch.zeros((Ci, Co, kh, kw))                           # placeholder: ifcb_conv_repack fills the operand
-    bp.conv(src, [dict(weight=wflip, scale=torch.ones(Ci), shift=torch.zeros(Ci), relu=False, out=dx)], (1, 1),
-            (kh - 1 - pad[0], kw - 1 - pad[1]), residual=dx if accumulate else None, name=name)
+    bp.conv(src, [dict(weight=wflip, scale=torch.ones(Ci), shift=torch.zeros(Ci), relu=False, out=dx)], (1, 1), dpad,
+            residual=dx if accumulate else None, name=name)
     wdg = bp.keep[-3]
     cin_pad = _lib.conv_geometry(Co, Ci, kh, kw)['Cin_pad']
     assert wdg.shape[1] == kh * kw * cin_pad, wdg.shape
@@ -93,13 +95,15 @@ class TrainNet(object):
     """
 
     def __init__(self, arch, state_dict, batch, device='cuda', dtype='bf16', lr=1e-3, betas=(0.9, 0.999), eps=1e-8,
-                 dropout=True, seed=0, R=None, bucket_mb=32, keep_dy=False):
+                 dropout=True, seed=0, R=None, bucket_mb=32, keep_dy=False, window=True):
         self.arch, self.batch, self.device = arch, int(batch), torch.device(device)
         if self.device.type != 'cuda':
             raise RuntimeError('TrainNet: a CUDA device is required (there is no CPU path)')
         self.R = R or (299 if arch == 'inception_v3' else 224)
         self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
         self.dropout, self.seed = bool(dropout), int(seed)
+        import os
+        self.window = bool(window) and os.environ.get('IFCB_TRAIN_WINDOW', '1') != '0'         # zero borders on activations / gradients so that k > 1 stride-1 convs run the WINDOW scheme
         self.keep_dy = bool(keep_dy)        # tests: keep d(activation) next to d(conv output) instead of overwriting it
         self.step_count = 0
         self._reducer = None
@@ -120,7 +124,8 @@ class TrainNet(object):
         self.bwd = []                   # closures, already in execution order
         self.repacks = []               # closures refreshing the 16-bit operands from the arena
         self.keep = []
-        self._grad_t = {}               # id(activation tensor) -> gradient tensor (no border)
+        self._grad_t = {}               # id(activation tensor) -> gradient tensor
+        self._grad_pad = {}             # id(activation tensor) -> zero border of its gradient tensor
         self.inp = torch.zeros((batch, 3, self.R, self.R), dtype=torch.float32, device=self.device)
         self.labels = torch.zeros((batch,), dtype=torch.int64, device=self.device)
         self.loss = torch.zeros((2,), dtype=torch.float32, device=self.device)     # [main + aux (weighted), unused]
@@ -136,6 +141,7 @@ class TrainNet(object):
         self.grads = torch.zeros_like(self.params)
         self.m = torch.zeros_like(self.params)
         self.v = torch.zeros_like(self.params)
+        self._plan_grad_borders()
         self._finalize(int(bucket_mb) << 20)
         self.repack()
 
@@ -164,19 +170,45 @@ class TrainNet(object):
     def alloc(self, H, W, Cc, pad=(0, 0)):
         return self.fp.alloc(H, W, Cc, pad)
 
+    def border(self, H, W, Ci, Co, k, stride=(1, 1), pad=(0, 0)):
+        """Zero border to allocate a tensor with when its consumer is conv(Ci -> Co, k, stride, pad) over H x W."""
+        if not self.window:
+            return (0, 0)
+        return self.fp.border_for(H, W, Co, k, stride, pad, Ci=Ci)
+
     def grad_of(self, v):
-        """Gradient view matching activation view ``v`` (gradient tensors carry no border)."""
+        """Gradient view matching activation view ``v``.  The gradient tensor carries the zero border the
+        data-gradient convs of v's producers want (``_grad_pad``, filled by ``_plan_grad_borders``)."""
         g = self._grad_t.get(id(v.t))
+        pad = self._grad_pad.get(id(v.t), (0, 0))
         if g is None:
-            g = torch.zeros((self.batch, v.H, v.W, v.t.shape[3]), dtype=self.tdtype, device=self.device)
+            g = torch.zeros((self.batch, v.H + 2 * pad[0], v.W + 2 * pad[1], v.t.shape[3]), dtype=self.tdtype, device=self.device)
             self._grad_t[id(v.t)] = g
             self.keep.append(v.t)
-        return View(g, v.c0, v.c1)
+        return View(g, v.c0, v.c1, pad)
+
+    def _plan_grad_borders(self):
+        """For every conv output tensor: the border (k-1-pad) its stride-1 data-gradient conv reads as padding when
+        the library will run that conv with the WINDOW scheme (max over the producers of a concat buffer)."""
+        for rec in self.records:
+            if rec['kind'] != 'conv_bn' or rec['stem'] is not None or rec['pool_after'] is not None or not self.window:
+                continue
+            if tuple(rec['stride']) != (1, 1):
+                continue                                             # strided: the dilated copy carries the border
+            kh, kw, pad, out = rec['kh'], rec['kw'], rec['pad'], rec['out']
+            dpad = (kh - 1 - pad[0], kw - 1 - pad[1])
+            want = self.bp.border_for(out.H, out.W, rec['Ci'], (kh, kw), pad=dpad, Ci=rec['Co'])
+            cur = self._grad_pad.get(id(out.t), (0, 0))
+            self._grad_pad[id(out.t)] = (max(cur[0], want[0]), max(cur[1], want[1]))
 
     # ---- graph construction (forward order) -------------------------------------------------------
     def conv_bn(self, x, sd, conv, bn, stride=(1, 1), pad=(0, 0), relu=True, residual=None, out=None, out_pad=(0, 0),
-                eps=1e-5, stem=False):
-        """Conv2d(bias=False) -> BatchNorm2d(train) [-> + residual] [-> ReLU]; returns the activation view."""
+                eps=1e-5, stem=False, pool_after=None):
+        """Conv2d(bias=False) -> BatchNorm2d(train) [-> + residual] [-> ReLU]; returns the activation view.
+
+        ``pool_after=(k, stride, pad)``: the module computes avg_pool2d(x) -> 1x1 conv (Inception's
+        branch_pool, inception.py:204,278,356); both are linear and commute, so the path evaluates
+        conv -> avg_pool on the conv's 4-10x fewer output channels (forward and backward)."""
         w = sd[conv + '.weight'].float()
         Co, Ci, kh, kw = [int(s) for s in w.shape]
         stem_geom = None
@@ -198,6 +230,12 @@ class TrainNet(object):
         H, W = x.H, x.W
         P = (H + 2 * pad[0] - kh) // stride[0] + 1
         Q = (W + 2 * pad[1] - kw) // stride[1] + 1
+        raw = None
+        if pool_after is not None:
+            assert (kh, kw) == (1, 1) and stride == (1, 1) and pad == (0, 0) and not stem
+            raw = self.alloc(P, Q, Co)                               # conv output before the pool
+            pk, ps, pp_ = pool_after
+            P, Q = (P + 2 * pp_ - pk) // ps + 1, (Q + 2 * pp_ - pk) // ps + 1
         if out is None:
             out = self.alloc(P, Q, Co, out_pad)
         z = self.alloc(P, Q, Co)
@@ -212,8 +250,9 @@ class TrainNet(object):
         mean, invstd = self._f32(Co), self._f32(Co)
         ones, zeros = torch.ones(Co), torch.zeros(Co)
         li = len(self.fp.layer_names)
-        self.fp.conv(x, [dict(weight=w, scale=ones, shift=zeros, relu=False, out=z)], stride, pad, name=conv)
+        self.fp.conv(x, [dict(weight=w, scale=ones, shift=zeros, relu=False, out=z if raw is None else raw)], stride, pad, name=conv)
         wf = self.fp.keep[-3]                                        # packed [Cout_pad, K_pad] 16-bit operand
+        rawd = _vd(raw) if raw is not None else None
         zd, od = _vd(z), _vd(out)
         rd = _vd(residual) if residual is not None else None
         B, dt = self.batch, self.cdtype
@@ -221,6 +260,8 @@ class TrainNet(object):
 
         def fwd():
             self.fp.run(B, li, li + 1)
+            if rawd is not None:
+                self._call('ifcb_avgpool_fwd', C.byref(rawd), C.byref(zd), B, pool_after[0], pool_after[1], pool_after[2], dt, self._stream())
             self._call('ifcb_bn_stats', C.byref(zd), B, dt, eps, 0.1, self.acc.data_ptr(), mean.data_ptr(), invstd.data_ptr(),
                        rm.data_ptr(), rv.data_ptr(), self._stream())
             self._call('ifcb_bn_apply', C.byref(zd), C.byref(od), C.byref(rd) if rd is not None else None, B, dt, mean.data_ptr(),
@@ -229,7 +270,7 @@ class TrainNet(object):
         self.fwd.append(fwd)
         self.records.append(dict(kind='conv_bn', x=x, z=z, out=out, residual=residual, relu=relu, stride=stride, pad=pad,
                                  pw=pw, pg=pg, pb=pb, mean=mean, invstd=invstd, wf=wf, Co=Co, Ci=Ci, kh=kh, kw=kw, stem=stem_geom,
-                                 H=H, W=W, name=conv))
+                                 H=H, W=W, name=conv, raw=raw, pool_after=pool_after))
         return out
 
     def maxpool(self, x, k, stride, pad, out=None, out_pad=(0, 0)):
@@ -347,7 +388,8 @@ class TrainNet(object):
         dy = self.grad_of(out)
         dyd, zd, od = _vd(dy), _vd(z), _vd(out)
         if self.keep_dy:
-            dz = View(torch.zeros((B, out.H, out.W, Co), dtype=self.tdtype, device=self.device))
+            gp = dy.pad
+            dz = View(torch.zeros((B, out.H + 2 * gp[0], out.W + 2 * gp[1], Co), dtype=self.tdtype, device=self.device), pad=gp)
             self.keep.append(dz.t)
         else:
             dz = dy                                                  # in place
@@ -366,6 +408,14 @@ class TrainNet(object):
                        C.byref(dzd), C.byref(dres_d) if dres_d is not None else None, 1 if res_acc else 0, 1 if relu else 0, B, dt,
                        mean.data_ptr(), invstd.data_ptr(), pg.wptr, pb.wptr, self.acc.data_ptr(), pg.gptr, pb.gptr, self._stream())
         self.bwd.append(bn_bwd)
+        if rec['pool_after'] is not None:                            # d(conv output) = avg_pool backward of dz
+            raw = rec['raw']
+            dr = View(torch.zeros((B, raw.H, raw.W, Co), dtype=self.tdtype, device=self.device))
+            self.keep.append(dr.t)
+            drd, pa = _vd(dr), rec['pool_after']
+            self.bwd.append(lambda: self._call('ifcb_avgpool_bwd', C.byref(dzd), C.byref(drd), 0, B, pa[0], pa[1], pa[2], dt, self._stream()))
+            rec['dr'] = dr
+            dz = dr
         # weight gradient: dW[co, tap, ci] += sum dz * x
         wd = WgradDesc()
         xin = x
@@ -374,6 +424,7 @@ class TrainNet(object):
         wd.in_pad_h, wd.in_pad_w = xin.pad
         wd.kh, wd.kw, wd.stride_h, wd.stride_w, wd.pad_h, wd.pad_w = kh, kw, stride[0], stride[1], pad[0], pad[1]
         wd.d_dout, wd.dout_ld, wd.Cout = dz.ptr, dz.ld, Co
+        wd.dout_pad_h, wd.dout_pad_w = dz.pad
         wd.dtype = dt
 
         def wgrad():
@@ -476,32 +527,52 @@ class TrainNet(object):
 def _build_resnet_train(tn, sd, arch):
     kind, layers = RESNET_CFG[arch]
     a = tn.conv_bn(None, sd, 'conv1', 'bn1', (2, 2), (3, 3), stem=True)
-    x = tn.maxpool(a, 3, 2, 1)
-    for li, nb in enumerate(layers):
-        for bi in range(nb):
-            pre = 'layer%d.%d' % (li + 1, bi)
-            s = 2 if (li > 0 and bi == 0) else 1
-            identity = x
-            if (pre + '.downsample.0.weight') in sd:
-                identity = tn.conv_bn(x, sd, pre + '.downsample.0', pre + '.downsample.1', (s, s), (0, 0), relu=False)
-            if kind == 'basic':
-                t = tn.conv_bn(x, sd, pre + '.conv1', pre + '.bn1', (s, s), (1, 1))
-                x = tn.conv_bn(t, sd, pre + '.conv2', pre + '.bn2', (1, 1), (1, 1), residual=identity)
-            else:
-                t = tn.conv_bn(x, sd, pre + '.conv1', pre + '.bn1')
-                t = tn.conv_bn(t, sd, pre + '.conv2', pre + '.bn2', (s, s), (1, 1))
-                x = tn.conv_bn(t, sd, pre + '.conv3', pre + '.bn3', residual=identity)
+    H = (a.H + 2 - 3) // 2 + 1
+    blocks = [(li, bi) for li, nb in enumerate(layers) for bi in range(nb)]
+    # a tensor carries the zero border its 3x3 stride-1 consumer wants (WINDOW scheme); basic blocks: block inputs
+    x = tn.maxpool(a, 3, 2, 1, out_pad=tn.border(H, H, 64, 64, (3, 3), pad=(1, 1)) if kind == 'basic' else (0, 0))
+    for idx, (li, bi) in enumerate(blocks):
+        pre = 'layer%d.%d' % (li + 1, bi)
+        s = 2 if (li > 0 and bi == 0) else 1
+        width = 64 << li
+        Ho = (x.H + 2 - 3) // s + 1
+        identity = x
+        if (pre + '.downsample.0.weight') in sd:
+            identity = tn.conv_bn(x, sd, pre + '.downsample.0', pre + '.downsample.1', (s, s), (0, 0), relu=False)
+        if kind == 'basic':
+            opad = (0, 0)
+            if idx + 1 < len(blocks):
+                nli, nbi = blocks[idx + 1]
+                ns = 2 if (nli > 0 and nbi == 0) else 1
+                opad = tn.border(Ho, Ho, width, 64 << nli, (3, 3), (ns, ns), (1, 1))
+            t = tn.conv_bn(x, sd, pre + '.conv1', pre + '.bn1', (s, s), (1, 1), out_pad=tn.border(Ho, Ho, width, width, (3, 3), pad=(1, 1)))
+            x = tn.conv_bn(t, sd, pre + '.conv2', pre + '.bn2', (1, 1), (1, 1), residual=identity, out_pad=opad)
+        else:
+            t = tn.conv_bn(x, sd, pre + '.conv1', pre + '.bn1', out_pad=tn.border(x.H, x.W, width, width, (3, 3), (s, s), (1, 1)))
+            t = tn.conv_bn(t, sd, pre + '.conv2', pre + '.bn2', (s, s), (1, 1))
+            x = tn.conv_bn(t, sd, pre + '.conv3', pre + '.bn3', residual=identity)
     tn.head(x, sd, 'fc')
 
 
 def _build_inception_train(tn, sd):
     eps = 1e-3
 
-    def cb(x, prefix, stride=(1, 1), pad=(0, 0), out=None, stem=False):
-        return tn.conv_bn(x, sd, prefix + '.conv', prefix + '.bn', stride, pad, out=out, eps=eps, stem=stem)
+    def cb(x, prefix, stride=(1, 1), pad=(0, 0), out=None, stem=False, pool_after=None, nxt=None):
+        """``nxt`` = (Cout, k, pad) of the stride-1 conv that consumes the output: the output is allocated with the
+        zero border that conv's WINDOW scheme reads as padding."""
+        out_pad = (0, 0)
+        if nxt is not None and out is None:
+            w = sd[prefix + '.conv.weight']
+            kh, kw = int(w.shape[2]), int(w.shape[3])
+            Hin = tn.R if stem else x.H
+            Ho = (Hin + 2 * pad[0] - kh) // stride[0] + 1
+            Wo = (Hin + 2 * pad[1] - kw) // stride[1] + 1
+            out_pad = tn.border(Ho, Wo, int(w.shape[0]), nxt[0], nxt[1], pad=nxt[2])
+        return tn.conv_bn(x, sd, prefix + '.conv', prefix + '.bn', stride, pad, out=out, eps=eps, stem=stem, pool_after=pool_after,
+                          out_pad=out_pad)
 
     a = cb(None, 'Conv2d_1a_3x3', (2, 2), stem=True)
-    a = cb(a, 'Conv2d_2a_3x3')
+    a = cb(a, 'Conv2d_2a_3x3', nxt=(64, (3, 3), (1, 1)))
     a = cb(a, 'Conv2d_2b_3x3', pad=(1, 1))
     a = tn.maxpool(a, 3, 2, 0)
     a = cb(a, 'Conv2d_3b_1x1')
@@ -511,37 +582,36 @@ def _build_inception_train(tn, sd):
         H = x.H
         out = tn.alloc(H, H, 224 + pf)
         cb(x, blk + '.branch1x1', out=out.slice(0, 64))
-        t = cb(x, blk + '.branch5x5_1')
+        t = cb(x, blk + '.branch5x5_1', nxt=(64, (5, 5), (2, 2)))
         cb(t, blk + '.branch5x5_2', pad=(2, 2), out=out.slice(64, 128))
-        t = cb(x, blk + '.branch3x3dbl_1')
-        t = cb(t, blk + '.branch3x3dbl_2', pad=(1, 1))
+        t = cb(x, blk + '.branch3x3dbl_1', nxt=(96, (3, 3), (1, 1)))
+        t = cb(t, blk + '.branch3x3dbl_2', pad=(1, 1), nxt=(96, (3, 3), (1, 1)))
         cb(t, blk + '.branch3x3dbl_3', pad=(1, 1), out=out.slice(128, 224))
-        t = tn.avgpool(x, 3, 1, 1)
-        cb(t, blk + '.branch_pool', out=out.slice(224, 224 + pf))
+        cb(x, blk + '.branch_pool', out=out.slice(224, 224 + pf), pool_after=(3, 1, 1))
         x = out
     blk = 'Mixed_6a'
     H2 = (x.H - 3) // 2 + 1
     out = tn.alloc(H2, H2, 768)
     cb(x, blk + '.branch3x3', (2, 2), out=out.slice(0, 384))
-    t = cb(x, blk + '.branch3x3dbl_1')
+    t = cb(x, blk + '.branch3x3dbl_1', nxt=(96, (3, 3), (1, 1)))
     t = cb(t, blk + '.branch3x3dbl_2', pad=(1, 1))
     cb(t, blk + '.branch3x3dbl_3', (2, 2), out=out.slice(384, 480))
     tn.maxpool(x, 3, 2, 0, out=out.slice(480, 768))
     x = out
-    for blk in ('Mixed_6b', 'Mixed_6c', 'Mixed_6d', 'Mixed_6e'):
+    for blk, c7 in (('Mixed_6b', 128), ('Mixed_6c', 160), ('Mixed_6d', 160), ('Mixed_6e', 192)):
         H = x.H
         out = tn.alloc(H, H, 768)
+        w17, w71 = (1, 7), (7, 1)
         cb(x, blk + '.branch1x1', out=out.slice(0, 192))
-        t = cb(x, blk + '.branch7x7_1')
-        t = cb(t, blk + '.branch7x7_2', pad=(0, 3))
+        t = cb(x, blk + '.branch7x7_1', nxt=(c7, w17, (0, 3)))
+        t = cb(t, blk + '.branch7x7_2', pad=(0, 3), nxt=(192, w71, (3, 0)))
         cb(t, blk + '.branch7x7_3', pad=(3, 0), out=out.slice(192, 384))
-        t = cb(x, blk + '.branch7x7dbl_1')
-        t = cb(t, blk + '.branch7x7dbl_2', pad=(3, 0))
-        t = cb(t, blk + '.branch7x7dbl_3', pad=(0, 3))
-        t = cb(t, blk + '.branch7x7dbl_4', pad=(3, 0))
+        t = cb(x, blk + '.branch7x7dbl_1', nxt=(c7, w71, (3, 0)))
+        t = cb(t, blk + '.branch7x7dbl_2', pad=(3, 0), nxt=(c7, w17, (0, 3)))
+        t = cb(t, blk + '.branch7x7dbl_3', pad=(0, 3), nxt=(c7, w71, (3, 0)))
+        t = cb(t, blk + '.branch7x7dbl_4', pad=(3, 0), nxt=(192, w17, (0, 3)))
         cb(t, blk + '.branch7x7dbl_5', pad=(0, 3), out=out.slice(384, 576))
-        t = tn.avgpool(x, 3, 1, 1)
-        cb(t, blk + '.branch_pool', out=out.slice(576, 768))
+        cb(x, blk + '.branch_pool', out=out.slice(576, 768), pool_after=(3, 1, 1))
         x = out
     # AuxLogits (train mode only, inception.py:130-134, InceptionAux :361-395)
     if 'AuxLogits.conv0.conv.weight' in sd:
@@ -554,8 +624,8 @@ def _build_inception_train(tn, sd):
     out = tn.alloc(H2, H2, 1280)
     t = cb(x, blk + '.branch3x3_1')
     cb(t, blk + '.branch3x3_2', (2, 2), out=out.slice(0, 320))
-    t = cb(x, blk + '.branch7x7x3_1')
-    t = cb(t, blk + '.branch7x7x3_2', pad=(0, 3))
+    t = cb(x, blk + '.branch7x7x3_1', nxt=(192, (1, 7), (0, 3)))
+    t = cb(t, blk + '.branch7x7x3_2', pad=(0, 3), nxt=(192, (7, 1), (3, 0)))
     t = cb(t, blk + '.branch7x7x3_3', pad=(3, 0))
     cb(t, blk + '.branch7x7x3_4', (2, 2), out=out.slice(320, 512))
     tn.maxpool(x, 3, 2, 0, out=out.slice(512, 1280))
@@ -564,14 +634,13 @@ def _build_inception_train(tn, sd):
         H = x.H
         out = tn.alloc(H, H, 2048)
         cb(x, blk + '.branch1x1', out=out.slice(0, 320))
-        t = cb(x, blk + '.branch3x3_1')
+        t = cb(x, blk + '.branch3x3_1', nxt=(384, (3, 3), (1, 1)))        # read by the 1x3 and the 3x1 sibling
         cb(t, blk + '.branch3x3_2a', pad=(0, 1), out=out.slice(320, 704))
         cb(t, blk + '.branch3x3_2b', pad=(1, 0), out=out.slice(704, 1088))
-        t = cb(x, blk + '.branch3x3dbl_1')
-        t = cb(t, blk + '.branch3x3dbl_2', pad=(1, 1))
+        t = cb(x, blk + '.branch3x3dbl_1', nxt=(384, (3, 3), (1, 1)))
+        t = cb(t, blk + '.branch3x3dbl_2', pad=(1, 1), nxt=(384, (3, 3), (1, 1)))
         cb(t, blk + '.branch3x3dbl_3a', pad=(0, 1), out=out.slice(1088, 1472))
         cb(t, blk + '.branch3x3dbl_3b', pad=(1, 0), out=out.slice(1472, 1856))
-        t = tn.avgpool(x, 3, 1, 1)
-        cb(t, blk + '.branch_pool', out=out.slice(1856, 2048))
+        cb(x, blk + '.branch_pool', out=out.slice(1856, 2048), pool_after=(3, 1, 1))
         x = out
     tn.head(x, sd, 'fc', dropout_p=0.5)

@@ -175,7 +175,7 @@ int ifcb_conv_geometry(int Cin, int Cout, int kh, int kw, int tile_n_hint,
  *   dW[co, r, s, ci] += sum_{n,p,q} dout[n,p,q,co] * in[n, p*stride_h + r - pad_h, q*stride_w + s - pad_w, ci]
  *   d_in       NHWC 16-bit view, logical extent [batch, H, W, Cin], pixel stride in_ld, stored with a
  *              zero border of in_pad_h / in_pad_w pixels (d_in = first border pixel), as ifcb_conv_desc
- *   d_dout     NHWC 16-bit view [batch, P, Q, Cout], pixel stride dout_ld
+ *   d_dout     NHWC 16-bit view, logical extent [batch, P, Q, Cout], pixel stride dout_ld, zero border dout_pad_*
  *   d_dweight  float32 [Cout, kh*kw, Cin]; the kernel ACCUMULATES (split-K over CTAs with
  *              red.global.add.f32): zero it first for a plain gradient
  */
@@ -189,6 +189,7 @@ typedef struct {
   float* d_dweight;
   int32_t dtype; /* IFCB_ACT_* of d_in and d_dout */
   int32_t in_pad_h, in_pad_w;
+  int32_t dout_pad_h, dout_pad_w; /* zero border of the d_dout tensor (d_dout = its first border pixel) */
 } ifcb_wgrad_desc;
 int ifcb_conv_wgrad(const ifcb_wgrad_desc* desc, void* stream);
 

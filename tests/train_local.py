@@ -66,12 +66,18 @@ def local_parity(net, eps_of, tol=2.0 ** -7):
                 got = _nchw(rec['x'])
                 _check(nm + ':patches', got[:, :taps * 3], u, 0.0, stats)
                 _check(nm + ':patch_pad', got[:, taps * 3:].abs().sum().view(1), torch.zeros(1, device=got.device), 0.0, stats)
-            x_in, w_op = _nchw(rec['x']), q(w)
+            # the conv reference runs in float64: cuDNN's "fp32" convolutions on this GPU carry ~1e-3 relative
+            # error of the ABSOLUTE sum (tools/dbg_dgrad.py), which swamps weight gradients that are small
+            # differences of large terms (BN backward makes dz zero-mean per channel; the branch_pool gradients
+            # came out 50-90 % off in fp32 while agreeing with an explicit float sum to 1e-3: tools/dbg_poolafter.py)
+            x_in, w_op = _nchw(rec['x']).double(), q(w).double()
             x_in.requires_grad_(True)
             w_op.requires_grad_(True)
             z_exp = F.conv2d(x_in, w_op, stride=rec['stride'], padding=rec['pad'])
+            if rec.get('pool_after') is not None:                 # Inception branch_pool: pool and 1x1 conv commuted
+                z_exp = F.avg_pool2d(z_exp, *rec['pool_after'])
             z_ours = _nchw(rec['z'])
-            _check(nm + ':z', z_ours, z_exp.detach(), tol, stats)
+            _check(nm + ':z', z_ours, z_exp.detach().float(), tol, stats)
             zz = z_ours.clone().requires_grad_(True)
             gamma, beta = pg.w.clone().requires_grad_(True), pb.w.clone().requires_grad_(True)
             y = F.batch_norm(zz, None, None, gamma, beta, training=True, eps=eps_of(nm))
@@ -91,11 +97,11 @@ def local_parity(net, eps_of, tol=2.0 ** -7):
             if res is not None:
                 add(rec['residual'], res.grad)
             # conv backward from OUR dz
-            z_exp.backward(dz_ours)
+            z_exp.backward(dz_ours.double())
             dW = pw.g[:, :, :Ci].reshape(Co, kh, kw, Ci).permute(0, 3, 1, 2)
-            _check(nm + ':dW', dW, w_op.grad, tol, stats)
+            _check(nm + ':dW', dW, w_op.grad.float(), tol, stats)
             if rec['stem'] is None:
-                add(rec['x'], x_in.grad)
+                add(rec['x'], x_in.grad.float())
         elif kind in ('maxpool', 'avgpool'):
             x_in = _nchw(rec['x']).requires_grad_(True)
             k, s, p = rec['k'], rec['stride'], rec['pad']
