@@ -260,8 +260,14 @@ def main():
     conv_flops = float(sum(f for f, k in zip(net.pb.layer_flops, net.pb.layer_kinds) if k == 'conv')) * B
     t_conv = float(conv_ms[is_conv].sum()) * 1e-3
     achieved = conv_flops / t_conv / 1e12
+    # DRAM bytes per conv launch from the committed ncu pass over the 65 conv launches of one batch
+    # (profiles/r01_ncu_conv_traffic.txt; same model / batch / dtype as this run, else null)
+    traffic = None
+    tpath = os.path.join(ROOT, 'profiles', 'r01_conv_traffic.json')
+    if os.path.exists(tpath) and args.model == 'inception_v3' and B == 512:
+        traffic = float(json.load(open(tpath))['dram_bytes_per_launch'])
     roofline = dict(bound='tensor', achieved=achieved, peak=peaks['bf16'], unit='TFLOP/s', frac=achieved / peaks['bf16'],
-                    traffic=None, kernel='conv_umma_kernel', peak_source=peaks['src'] + ' sustained dense bf16',
+                    traffic=traffic, kernel='conv_umma_kernel', peak_source=peaks['src'] + ' sustained dense bf16',
                     conv_launches=int(is_conv.sum()), conv_share_of_network=float(conv_ms[is_conv].sum() / conv_ms.sum()),
                     network_ms_per_batch=float(conv_ms.sum()), batch=B,
                     whole_path_frac=value * net.flops_per_image / 1e12 / peaks['bf16'])

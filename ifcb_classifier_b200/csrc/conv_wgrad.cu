@@ -8,13 +8,16 @@
 // Both operands live in HBM pixel-major (NHWC), i.e. the reduction index is the slow one: the
 // tensor core takes them as MN-MAJOR operands (instruction-descriptor major bits), so the tiles
 // TMA delivers are used as they land -- no transposes:
-//   A = dz tile  [128 pixels x 128 co]  two 64-channel boxes of a plain 2-D map (rows = pixels)
-//   B = x  tile  [128 pixels x  64 ci]  the SAME im2col map the forward kernel loads as its A
-// One MMA = M 128 (co) x N 64 (ci) x K 16 (pixels); a 128-pixel tile is 8 MMAs per
-// (filter tap, channel block) accumulator.  TMEM holds 8 accumulators of 64 fp32 columns (all
-// 512 columns); a work item = (co tile, group of <= 8 (tap, channel block) pairs, pixel range):
-// the CTA sweeps its pixel range once, loading each dz tile once and one x tile per accumulator,
-// then adds its partial sums into the fp32 gradient with red.global (split-K over CTAs).
+//   A = x tiles  [128 pixels x 128 rows]  TWO 64-channel blocks, each one (filter tap, channel block) of the SAME
+//                                         im2col map the forward kernel loads as its A operand (one TMA each)
+//   B = dz tile  [128 pixels x N co]      N = the layer's output channels (<= 256 per tile, any multiple of 16):
+//                                         ceil(N/64) 64-channel boxes of a plain 2-D map (or a 1x1-window im2col map
+//                                         when the gradient tensor carries a zero border)
+// One MMA = M 128 ((tap, ci) rows) x N (co) x K 16 (pixels): the output-channel count never pads the M
+// dimension and N >= 128 runs the tensor pipe at full rate.  TMEM holds floor(512 / N) accumulators;
+// a work item = (co tile, group of that many block pairs, pixel range): the CTA sweeps its pixel range
+// once, loading each dz tile once and two x blocks per accumulator, then adds its partial sums into
+// the fp32 gradient with red.global (split-K over CTAs).
 // Warp roles as in conv_umma.cu: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 drain TMEM.
 #include "layers.cuh"
 #include "ptx.cuh"
@@ -23,23 +26,23 @@ namespace ifcb {
 namespace {
 
 constexpr int kPix = 128;                 // pixels (K) per tile
-constexpr int kATile = 2 * kPix * 128;    // dz tile: two 64-channel blocks of 128 rows x 128 B
-constexpr int kBTile = kPix * 128;        // x tile: 128 rows x 128 B
-constexpr int kMaxAcc = 8;                // accumulators (64 TMEM columns each)
+constexpr int kBlk = kPix * 128;          // one 64-channel block of 128 pixel rows x 128 B = 16 KB
 constexpr int kWThreads = 64 + 128;
+constexpr int kMaxXStages = 16;
 
 struct WgradParams {
   int rows;                 // batch * P * Q
   int rows_per_img, row_w;  // P*Q, Q
   int kh, kw, stride_h, stride_w, pad_h, pad_w;
   int Cin, Cout, cblocks, taps;
-  int n_pairs;              // taps * cblocks
-  int n_groups;             // ceil(n_pairs / 8)
-  int group_size;           // (tap, channel block) pairs per group, balanced: ceil(n_pairs / n_groups)
-  int co_tiles;             // ceil(Cout / 128)
+  int n_blocks;             // taps * cblocks  (x blocks of 64 channels)
+  int n_mpairs;             // ceil(n_blocks / 2): M = 128 rows = two blocks
+  int tile_n, n_cotiles;    // output channels per tile (multiple of 16, <= 256)
+  int nblk_n;               // ceil(tile_n / 64): dz boxes per tile
+  int n_groups, group_size; // block pairs per work item (<= 512 / tile_n accumulators), balanced
   int splits;               // pixel-range splits
   int tiles_per_split;      // 128-pixel tiles per split
-  int a_slots, b_stages;
+  int dz_slots, x_stages;   // x_stages is even: a pair occupies two adjacent stages
   int fp16;
   int dz_im2col;            // dz is loaded through a 4-D (1x1 window) im2col map: the gradient tensor has a zero border
   float* dW;                // [Cout][taps][Cin] fp32, accumulated into
@@ -49,24 +52,25 @@ __global__ void __launch_bounds__(kWThreads, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_constant__ CUtensorMap tmap_x, const WgradParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* a_base = smem;
-  uint8_t* b_base = smem + (size_t)p.a_slots * kATile;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(b_base + (size_t)p.b_stages * kBTile);
-  uint64_t* a_full = bars;            // [a_slots]
-  uint64_t* a_empty = bars + 4;
-  uint64_t* b_full = bars + 8;        // [b_stages]
-  uint64_t* b_empty = bars + 24;
-  uint64_t* acc_full = bars + 40;     // accumulators complete -> epilogue
-  uint64_t* acc_empty = bars + 41;    // epilogue drained -> next item may overwrite
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 42);
+  const int dz_slot_bytes = p.nblk_n * kBlk;
+  uint8_t* dz_base = smem;
+  uint8_t* x_base = smem + (size_t)p.dz_slots * dz_slot_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(x_base + (size_t)p.x_stages * kBlk);
+  uint64_t* dz_full = bars;           // [dz_slots]
+  uint64_t* dz_empty = bars + 4;
+  uint64_t* x_full = bars + 8;        // [x_stages]
+  uint64_t* x_empty = bars + 8 + kMaxXStages;
+  uint64_t* acc_full = bars + 8 + 2 * kMaxXStages;     // accumulators complete -> epilogue
+  uint64_t* acc_empty = acc_full + 1;                  // epilogue drained -> next item may overwrite
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 2);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmap_dz);
     ptx::prefetch_tensormap(&tmap_x);
-    for (int s = 0; s < p.a_slots; ++s) { ptx::mbar_init(a_full + s, 1); ptx::mbar_init(a_empty + s, 1); }
-    for (int s = 0; s < p.b_stages; ++s) { ptx::mbar_init(b_full + s, 1); ptx::mbar_init(b_empty + s, 1); }
+    for (int s = 0; s < p.dz_slots; ++s) { ptx::mbar_init(dz_full + s, 1); ptx::mbar_init(dz_empty + s, 1); }
+    for (int s = 0; s < p.x_stages; ++s) { ptx::mbar_init(x_full + s, 1); ptx::mbar_init(x_empty + s, 1); }
     ptx::mbar_init(acc_full, 1);
     ptx::mbar_init(acc_empty, 4);
     ptx::fence_barrier_init();
@@ -80,20 +84,20 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_cons
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int items = p.co_tiles * p.n_groups * p.splits;
+  const int items = p.n_cotiles * p.n_groups * p.splits;
   const int total_ptiles = (p.rows + kPix - 1) / kPix;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    int aslot = 0, bstage = 0;
-    uint32_t aphase = 0, bphase = 0;
+    int dslot = 0, xstage = 0;
+    uint32_t dphase = 0, xphase = 0;
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
       const int split = item % p.splits;
       const int rest = item / p.splits;
       const int group = rest % p.n_groups;
-      const int co_tile = rest / p.n_groups;
+      const int co0 = (rest / p.n_groups) * p.tile_n;
       const int pair0 = group * p.group_size;
-      const int npair = min(p.group_size, p.n_pairs - pair0);
+      const int npair = min(p.group_size, p.n_mpairs - pair0);
       const int t_begin = split * p.tiles_per_split;
       const int t_end = min(total_ptiles, t_begin + p.tiles_per_split);
       for (int pt = t_begin; pt < t_end; ++pt) {
@@ -102,117 +106,130 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_cons
         const int rem = m0 - img * p.rows_per_img;
         const int op = rem / p.row_w, oq = rem - op * p.row_w;
         const int w0 = oq * p.stride_w - p.pad_w, h0 = op * p.stride_h - p.pad_h;
-        ptx::mbar_wait(a_empty + aslot, aphase ^ 1);
+        ptx::mbar_wait(dz_empty + dslot, dphase ^ 1);
         if (ptx::elect_one()) {
-          uint8_t* dst = a_base + (size_t)aslot * kATile;
-          ptx::mbar_arrive_expect_tx(a_full + aslot, (uint32_t)kATile);
-          if (p.dz_im2col) {
-            ptx::tma_load_im2col_4d(dst, &tmap_dz, a_full + aslot, co_tile * 128, oq, op, img, 0, 0);
-            ptx::tma_load_im2col_4d(dst + kPix * 128, &tmap_dz, a_full + aslot, co_tile * 128 + 64, oq, op, img, 0, 0);
-          } else {
-            ptx::tma_load_2d(dst, &tmap_dz, a_full + aslot, co_tile * 128, m0);
-            ptx::tma_load_2d(dst + kPix * 128, &tmap_dz, a_full + aslot, co_tile * 128 + 64, m0);
+          uint8_t* dst = dz_base + (size_t)dslot * dz_slot_bytes;
+          ptx::mbar_arrive_expect_tx(dz_full + dslot, (uint32_t)dz_slot_bytes);
+          for (int bb = 0; bb < p.nblk_n; ++bb) {
+            if (p.dz_im2col) ptx::tma_load_im2col_4d(dst + bb * kBlk, &tmap_dz, dz_full + dslot, co0 + bb * 64, oq, op, img, 0, 0);
+            else ptx::tma_load_2d(dst + bb * kBlk, &tmap_dz, dz_full + dslot, co0 + bb * 64, m0);
           }
         }
         __syncwarp();
-        if (++aslot == p.a_slots) { aslot = 0; aphase ^= 1; }
+        if (++dslot == p.dz_slots) { dslot = 0; dphase ^= 1; }
         for (int g = 0; g < npair; ++g) {
-          const int pr = pair0 + g;
-          const int tap = pr / p.cblocks, cb = pr - tap * p.cblocks;
-          const int r = tap / p.kw, s = tap - r * p.kw;
-          ptx::mbar_wait(b_empty + bstage, bphase ^ 1);
-          if (ptx::elect_one()) {
-            ptx::mbar_arrive_expect_tx(b_full + bstage, (uint32_t)kBTile);
-            ptx::tma_load_im2col_4d(b_base + (size_t)bstage * kBTile, &tmap_x, b_full + bstage, cb * 64, w0, h0, img,
-                                    (uint16_t)s, (uint16_t)r);
+#pragma unroll
+          for (int b = 0; b < 2; ++b) {
+            const int blk = (pair0 + g) * 2 + b;
+            const int tap = blk / p.cblocks, cb = blk - tap * p.cblocks;
+            const int r = tap / p.kw, s = tap - r * p.kw;
+            ptx::mbar_wait(x_empty + xstage, xphase ^ 1);
+            if (ptx::elect_one()) {
+              if (blk < p.n_blocks) {
+                ptx::mbar_arrive_expect_tx(x_full + xstage, (uint32_t)kBlk);
+                ptx::tma_load_im2col_4d(x_base + (size_t)xstage * kBlk, &tmap_x, x_full + xstage, cb * 64, w0, h0, img, (uint16_t)s,
+                                        (uint16_t)r);
+              } else {
+                // odd block count: the last pair has one block.  The stage still cycles through its barriers (the MMA
+                // reads whatever the slot holds into rows 64-127, which the epilogue never stores)
+                ptx::mbar_arrive(x_full + xstage);
+              }
+            }
+            __syncwarp();
+            if (++xstage == p.x_stages) { xstage = 0; xphase ^= 1; }
           }
-          __syncwarp();
-          if (++bstage == p.b_stages) { bstage = 0; bphase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    // both operands MN-major (bits 15/16), fp32 accumulate, M = 128, N = 64
+    // both operands MN-major (bits 15/16), fp32 accumulate, M = 128, N = tile_n
     const uint32_t fmt = p.fp16 ? 0u : 1u;
-    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 15) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 15) | (1u << 16) | (((uint32_t)p.tile_n >> 3) << 17) | ((128u >> 4) << 24);
     // MN-major SWIZZLE_128B: 128-byte rows indexed by k (64 consecutive M/N elements each), groups of
-    // 8 k-rows SBO = 1024 B apart, next 64-element M/N block LBO bytes away (A: 16 KB; B: single block)
+    // 8 k-rows SBO = 1024 B apart, next 64-element M/N block LBO = one 16 KB block away
     const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
-    const uint32_t a_lbo = ((uint32_t)(kPix * 128) >> 4) << 16;
-    const uint32_t b_lbo = 1u << 16;
+    const uint32_t lbo = ((uint32_t)kBlk >> 4) << 16;
     const bool leader = ptx::elect_one();
-    int aslot = 0, bstage = 0;
-    uint32_t aphase = 0, bphase = 0;
+    int dslot = 0, xstage = 0;
+    uint32_t dphase = 0, xphase = 0;
     int local = 0;
     for (int item = blockIdx.x; item < items; item += gridDim.x, ++local) {
       const int split = item % p.splits;
       const int rest = item / p.splits;
       const int group = rest % p.n_groups;
-      const int npair = min(p.group_size, p.n_pairs - group * p.group_size);
+      const int pair0 = group * p.group_size;
+      const int npair = min(p.group_size, p.n_mpairs - pair0);
       const int t_begin = split * p.tiles_per_split;
       const int t_end = min(total_ptiles, t_begin + p.tiles_per_split);
       ptx::mbar_wait(acc_empty, (uint32_t)((local & 1) ^ 1));
       ptx::tc_fence_after();
       for (int pt = t_begin; pt < t_end; ++pt) {
-        ptx::mbar_wait(a_full + aslot, aphase);
-        const uint32_t a_lo0 = ((ptx::smem_u32(a_base + (size_t)aslot * kATile) & 0x3FFFFu) >> 4) | a_lbo;
+        ptx::mbar_wait(dz_full + dslot, dphase);
+        const uint32_t b_lo0 = ((ptx::smem_u32(dz_base + (size_t)dslot * dz_slot_bytes) & 0x3FFFFu) >> 4) | lbo;
         for (int g = 0; g < npair; ++g) {
-          ptx::mbar_wait(b_full + bstage, bphase);
+          const int st0 = xstage;
+          ptx::mbar_wait(x_full + st0, xphase);
+          ptx::mbar_wait(x_full + st0 + 1, xphase);                // x_stages is even: both stages share the ring phase
           ptx::tc_fence_after();
-          const uint32_t b_lo0 = ((ptx::smem_u32(b_base + (size_t)bstage * kBTile) & 0x3FFFFu) >> 4) | b_lbo;
-          const uint32_t d = tmem_base + (uint32_t)(g * 64);
+          const uint32_t a_lo0 = ((ptx::smem_u32(x_base + (size_t)st0 * kBlk) & 0x3FFFFu) >> 4) | lbo;
+          const uint32_t d = tmem_base + (uint32_t)(g * p.tile_n);
 #pragma unroll
           for (int k = 0; k < kPix / 16; ++k)
             if (leader)
               ptx::umma_f16_lohi(d, a_lo0 + (uint32_t)(k * 128), b_lo0 + (uint32_t)(k * 128), hi, idesc,
                                  (pt > t_begin || k > 0) ? 1u : 0u);
-          if (leader) ptx::umma_commit(b_empty + bstage);
+          if (leader) {
+            ptx::umma_commit(x_empty + st0);
+            ptx::umma_commit(x_empty + st0 + 1);
+          }
           __syncwarp();
-          if (++bstage == p.b_stages) { bstage = 0; bphase ^= 1; }
+          xstage += 2;
+          if (xstage == p.x_stages) { xstage = 0; xphase ^= 1; }
         }
-        if (leader) ptx::umma_commit(a_empty + aslot);
+        if (leader) ptx::umma_commit(dz_empty + dslot);
         __syncwarp();
-        if (++aslot == p.a_slots) { aslot = 0; aphase ^= 1; }
+        if (++dslot == p.dz_slots) { dslot = 0; dphase ^= 1; }
       }
       if (leader) ptx::umma_commit(acc_full);
       __syncwarp();
     }
   } else {
     // ===================== epilogue: TMEM -> red.global.add.f32 =====================
+    // TMEM lane = GEMM row: lanes 0-63 the pair's first block, 64-127 its second; a warp's 32 lanes are 32
+    // consecutive input channels of one (tap, channel block) -> each red instruction covers 128 contiguous bytes
     const int quad = warp & 3;
     int local = 0;
     for (int item = blockIdx.x; item < items; item += gridDim.x, ++local) {
       const int split = item % p.splits;
       const int rest = item / p.splits;
       const int group = rest % p.n_groups;
-      const int co_tile = rest / p.n_groups;
+      const int co0 = (rest / p.n_groups) * p.tile_n;
       const int pair0 = group * p.group_size;
-      const int npair = min(p.group_size, p.n_pairs - pair0);
+      const int npair = min(p.group_size, p.n_mpairs - pair0);
       const int t_begin = split * p.tiles_per_split;
       const bool has_work = t_begin < min(total_ptiles, t_begin + p.tiles_per_split);
       ptx::mbar_wait(acc_full, (uint32_t)(local & 1));
       ptx::tc_fence_after();
-      const int co = co_tile * 128 + quad * 32 + lane;
       if (has_work) {
+        const int ncols = min(p.tile_n, p.Cout - co0);
         for (int g = 0; g < npair; ++g) {
-          const int pr = pair0 + g;
-          const int tap = pr / p.cblocks, cb = pr - tap * p.cblocks;
-          const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(g * 64);
-          float* dst = p.dW + ((size_t)co * p.taps + tap) * p.Cin + cb * 64;
-#pragma unroll
-          for (int c0 = 0; c0 < 64; c0 += 16) {
+          const int blk = (pair0 + g) * 2 + (quad >> 1);
+          if (blk >= p.n_blocks) continue;                       // warp-uniform
+          const int tap = blk / p.cblocks, cb = blk - tap * p.cblocks;
+          const int ci = cb * 64 + (quad & 1) * 32 + lane;
+          const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(g * p.tile_n);
+          float* dst = p.dW + ((size_t)co0 * p.taps + tap) * p.Cin + ci;
+          const size_t co_stride = (size_t)p.taps * p.Cin;
+          for (int c0 = 0; c0 < ncols; c0 += 16) {
             uint32_t v[16];
             ptx::tmem_ld_32x32b_x16(taddr + (uint32_t)c0, v);
             ptx::tmem_ld_wait();
-            if (co < p.Cout) {
-              // 16-byte vector reductions (Cin is a multiple of 8: a group of 4 is all in or all out)
+            if (ci < p.Cin) {
 #pragma unroll
-              for (int j = 0; j < 16; j += 4)
-                if (cb * 64 + c0 + j < p.Cin)
-                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c0 + j), "f"(__uint_as_float(v[j])),
-                               "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3]))
-                               : "memory");
+              for (int j = 0; j < 16; ++j)
+                if (c0 + j < ncols)
+                  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst + (size_t)(c0 + j) * co_stride), "f"(__uint_as_float(v[j])) : "memory");
             }
           }
         }
@@ -305,30 +322,46 @@ extern "C" int ifcb_conv_wgrad(const ifcb_wgrad_desc* d, void* stream_v) {
   p.Cin = d->Cin; p.Cout = d->Cout;
   p.cblocks = (d->Cin + 63) / 64;
   p.taps = d->kh * d->kw;
-  p.n_pairs = p.taps * p.cblocks;
-  p.n_groups = (p.n_pairs + kMaxAcc - 1) / kMaxAcc;
-  p.group_size = (p.n_pairs + p.n_groups - 1) / p.n_groups;
-  p.n_groups = (p.n_pairs + p.group_size - 1) / p.group_size;
-  p.co_tiles = (d->Cout + 127) / 128;
+  p.n_blocks = p.taps * p.cblocks;
+  p.n_mpairs = (p.n_blocks + 1) / 2;
+  {
+    const int c16 = (d->Cout + 15) & ~15;
+    const int t = (c16 + 255) / 256;
+    p.tile_n = (((c16 + t - 1) / t) + 15) & ~15;
+    p.n_cotiles = (d->Cout + p.tile_n - 1) / p.tile_n;
+    p.nblk_n = (p.tile_n + 63) / 64;
+  }
+  int n_acc = 512 / p.tile_n;
+  if (n_acc > 16) n_acc = 16;
+  p.n_groups = (p.n_mpairs + n_acc - 1) / n_acc;
+  p.group_size = (p.n_mpairs + p.n_groups - 1) / p.n_groups;
+  p.n_groups = (p.n_mpairs + p.group_size - 1) / p.group_size;
   const int ptiles = (int)((rows + kPix - 1) / kPix);
-  const int base_items = p.co_tiles * p.n_groups;
+  const int base_items = p.n_cotiles * p.n_groups;
   int splits = (2 * sm_count() + base_items - 1) / base_items;     // about two waves of work items
   if (splits > ptiles) splits = ptiles;
   if (splits < 1) splits = 1;
   p.tiles_per_split = (ptiles + splits - 1) / splits;
   p.splits = (ptiles + p.tiles_per_split - 1) / p.tiles_per_split;
-  p.a_slots = 2;
-  p.b_stages = 8;
+  p.dz_slots = 2;
+  {
+    const int budget = 216 * 1024 - p.dz_slots * p.nblk_n * kBlk;
+    int st = budget / kBlk;
+    st &= ~1;
+    if (st > kMaxXStages) st = kMaxXStages;
+    if (st < 2) st = 2;
+    p.x_stages = st;
+  }
   p.fp16 = d->dtype;
   p.dz_im2col = dz_border ? 1 : 0;
   p.dW = d->d_dweight;
-  const int smem = p.a_slots * kATile + p.b_stages * kBTile + 512 + 1024;
+  const int smem = p.dz_slots * p.nblk_n * kBlk + p.x_stages * kBlk + 512 + 1024;
   static int attr = 0;
   if (smem > attr) {
     IFCB_CUDA_CHECK(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr = smem;
   }
-  const int items = p.co_tiles * p.n_groups * p.splits;
+  const int items = p.n_cotiles * p.n_groups * p.splits;
   const int grid = items < sm_count() ? items : sm_count();
   conv_wgrad_kernel<<<grid, kWThreads, smem, reinterpret_cast<cudaStream_t>(stream_v)>>>(tmap_dz, tmap_x, p);
   IFCB_CUDA_CHECK(cudaGetLastError());
