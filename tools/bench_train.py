@@ -32,6 +32,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
+        if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
+            os.environ['NCCL_DEBUG'] = 'WARN'
         dist.init_process_group('nccl', device_id=dev)
     from ifcb_classifier_b200.neuston_models import get_namebrand_model
     from ifcb_classifier_b200.train import TrainNet
