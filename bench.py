@@ -128,7 +128,7 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--model', default='inception_v3')
     ap.add_argument('--dtype', default='fp16', choices=['fp16', 'bf16'])
-    ap.add_argument('--batch', type=int, default=512, help='ROIs per network launch sequence')
+    ap.add_argument('--batch', type=int, default=1024, help='ROIs per network launch sequence')
     ap.add_argument('--rois', type=int, default=ROIS_PER_BIN)
     ap.add_argument('--bins', type=int, default=4, help='distinct synthetic bins cycled through')
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -266,7 +266,7 @@ def main():
     # (profiles/r01_ncu_conv_traffic.txt; same model / batch / dtype as this run, else null)
     traffic = None
     tpath = os.path.join(ROOT, 'profiles', 'r01_conv_traffic.json')
-    if os.path.exists(tpath) and args.model == 'inception_v3' and B == 512:
+    if os.path.exists(tpath) and args.model == 'inception_v3' and B == int(json.load(open(tpath)).get('batch', 0)):
         traffic = float(json.load(open(tpath))['dram_bytes_per_launch'])
     roofline = dict(bound='tensor', achieved=achieved, peak=peaks['bf16'], unit='TFLOP/s', frac=achieved / peaks['bf16'],
                     traffic=traffic, kernel='conv_umma_kernel', peak_source=peaks['src'] + ' sustained dense bf16',

@@ -338,7 +338,8 @@ extern "C" int ifcb_conv_wgrad(const ifcb_wgrad_desc* d, void* stream_v) {
   p.n_groups = (p.n_mpairs + p.group_size - 1) / p.group_size;
   const int ptiles = (int)((rows + kPix - 1) / kPix);
   const int base_items = p.n_cotiles * p.n_groups;
-  int splits = (2 * sm_count() + base_items - 1) / base_items;     // about two waves of work items
+  static const int waves = getenv("IFCB_WGRAD_WAVES") ? atoi(getenv("IFCB_WGRAD_WAVES")) : 1;   // tuning knob (measured: 1 wave 28.3 / 37.5 ms per step, 2 waves 28.8 / 37.9, 4 waves 30.3 / 40.0)
+  int splits = (waves * sm_count() + base_items - 1) / base_items;     // about one wave of work items: every extra split adds a full tile of red.global traffic
   if (splits > ptiles) splits = ptiles;
   if (splits < 1) splits = 1;
   p.tiles_per_split = (ptiles + splits - 1) / splits;

@@ -797,6 +797,15 @@ static int stream_grid(long long M, int rows) {
   return g < 1 ? 1 : (int)g;
 }
 
+// grid of the reduction kernels: as stream_grid, but every block ends with 2*C float64 atomics on the same 2*C
+// addresses, so a block should stream at least ~256 KB per tensor before it pays for them
+static int reduce_grid(long long M, int rows, int C) {
+  long long g = stream_grid(M, rows);
+  const long long by_bytes = (M * C * 2 + (256 << 10) - 1) / (256 << 10);
+  if (g > by_bytes) g = by_bytes;
+  return g < 1 ? 1 : (int)g;
+}
+
 extern "C" int ifcb_bn_stats(const ifcb_view* z, int batch, int dtype, float eps, float momentum, double* d_acc, float* d_mean,
                              float* d_invstd, float* d_running_mean, float* d_running_var, void* stream) {
   IFCB_ARG_CHECK(view_ok(z) && batch > 0 && DT_OK(dtype), "bn_stats: bad view / batch / dtype");
@@ -804,7 +813,7 @@ extern "C" int ifcb_bn_stats(const ifcb_view* z, int batch, int dtype, float eps
   IFCB_ARG_CHECK(d_acc && d_mean && d_invstd, "bn_stats: null pointer");
   const long long M = (long long)batch * z->H * z->W;
   const int rows = reduce_rows(z->C);
-  const int grid = stream_grid(M, rows);
+  const int grid = reduce_grid(M, rows, z->C);
   DV zz = dv(z);
   IFCB_ARG_CHECK(M < (1ll << 31) / (z->C / 8), "bn_stats: tensor too large for 32-bit indexing");
   channel_reduce_kernel<0, kMaskNone><<<grid, 256, 0, STREAM(stream)>>>(zz, zz, zz, nullptr, nullptr, nullptr, nullptr, M, rows, dtype, d_acc);
@@ -862,7 +871,7 @@ extern "C" int ifcb_bn_backward(const ifcb_view* dy, const ifcb_view* a, const i
   cudaStream_t st = STREAM(stream);
   DV av = a ? dv(a) : zz, dzv = dv(dz), drv = dres ? dv(dres) : zz;
   const int res_mode = dres ? (dres_accumulate ? 2 : 1) : 0;
-#define IFCB_REDUCE1(MK) channel_reduce_kernel<1, MK><<<grid, 256, 0, st>>>(zz, dyy, av, d_mean, d_invstd, d_gamma, d_beta, M, rows, dtype, d_acc)
+#define IFCB_REDUCE1(MK) channel_reduce_kernel<1, MK><<<reduce_grid(M, rows, z->C), 256, 0, st>>>(zz, dyy, av, d_mean, d_invstd, d_gamma, d_beta, M, rows, dtype, d_acc)
   if (mask_mode == kMaskFromZ) IFCB_REDUCE1(kMaskFromZ);
   else if (mask_mode == kMaskFromA) IFCB_REDUCE1(kMaskFromA);
   else IFCB_REDUCE1(kMaskNone);
