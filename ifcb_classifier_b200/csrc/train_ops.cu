@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(256, 3) bn_apply_kernel(DV z, DV out, DV res, 
 // per-channel coefficients of the backward elementwise pass from the float64 sums:
 //   dz = A * dy' + Bz * z + D,  A = gamma*invstd, Bz = -A*invstd*s2/M, D = A*(mean*invstd*s2/M - s1/M)
 // coef = [A | Bz | D] (3*C floats); also dgamma += s2, dbeta += s1.
-__global__ void bn_bwd_coef_kernel(const double* __restrict__ acc, int C, double inv_m, const float* __restrict__ mean,
+__global__ void bn_bwd_coef_kernel(double* __restrict__ acc, int C, double inv_m, const float* __restrict__ mean,
                                    const float* __restrict__ invstd, const float* __restrict__ gamma, float* __restrict__ coef,
                                    float* __restrict__ dgamma, float* __restrict__ dbeta) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -287,6 +287,8 @@ __global__ void bn_bwd_coef_kernel(const double* __restrict__ acc, int C, double
   coef[2 * C + c] = (float)(A * (mu * is * s2 * inv_m - s1 * inv_m));
   if (dbeta) dbeta[c] += (float)s1;
   if (dgamma) dgamma[c] += (float)s2;
+  acc[c] = 0.0;            // leave the accumulators zero for the next user (no memset launch per layer)
+  acc[C + c] = 0.0;
 }
 
 // dz = A * dy' + Bz * z + D with dy' = relu-masked dy; optionally routes dy' to the residual branch
@@ -865,8 +867,9 @@ extern "C" int ifcb_bn_backward(const ifcb_view* dy, const ifcb_view* a, const i
   const int mask_mode = !relu ? kMaskNone : (dres ? kMaskFromA : kMaskFromZ);
   const int rows = reduce_rows(z->C);
   DV zz = dv(z), dyy = dv(dy);
-  float* coef = reinterpret_cast<float*>(d_acc + 2 * z->C);
-  IFCB_CUDA_CHECK(cudaMemsetAsync(d_acc, 0, sizeof(double) * 2 * z->C, STREAM(stream)));
+  // coefficient floats live behind the accumulator area of the LARGEST layer (2 * 2048 float64), never inside it:
+  // a smaller layer's coefficients must not land where a wider layer accumulates next
+  float* coef = reinterpret_cast<float*>(d_acc + 2 * 2048);
   const int grid = stream_grid(M, rows);
   cudaStream_t st = STREAM(stream);
   DV av = a ? dv(a) : zz, dzv = dv(dz), drv = dres ? dv(dres) : zz;

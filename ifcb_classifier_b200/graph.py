@@ -147,6 +147,7 @@ class PlanBuilder(object):
         packed = torch.zeros((Np, kh * kw, Cp), dtype=torch.float32)
         packed[:Co, :, :Ci] = wcat.permute(0, 2, 3, 1).reshape(Co, kh * kw, Ci)
         wdev = self.dev(packed.reshape(Np, Kp), self.tdtype)
+        self.last_weight = wdev            # the packed 16-bit operand of the conv just added (TRAIN refreshes it in place)
         scale = torch.zeros(Np); shift = torch.zeros(Np)
         scale[:Co] = torch.cat([m['scale'].float() for m in members])
         shift[:Co] = torch.cat([m['shift'].float() for m in members])

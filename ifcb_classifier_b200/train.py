@@ -57,7 +57,7 @@ def build_dgrad(bp, dy, dx, Co, Ci, kh, kw, stride, pad, accumulate, name='dgrad
     wflip = torch.zeros((Ci, Co, kh, kw))                           # placeholder: ifcb_conv_repack fills the operand
     bp.conv(src, [dict(weight=wflip, scale=torch.ones(Ci), shift=torch.zeros(Ci), relu=False, out=dx)], (1, 1), dpad,
             residual=dx if accumulate else None, name=name)
-    wdg = bp.keep[-3]
+    wdg = bp.last_weight
     cin_pad = _lib.conv_geometry(Co, Ci, kh, kw)['Cin_pad']
     assert wdg.shape[1] == kh * kw * cin_pad, wdg.shape
     run.append(lambda: bp.run(B, li, li + 1))
@@ -251,7 +251,7 @@ class TrainNet(object):
         ones, zeros = torch.ones(Co), torch.zeros(Co)
         li = len(self.fp.layer_names)
         self.fp.conv(x, [dict(weight=w, scale=ones, shift=zeros, relu=False, out=z if raw is None else raw)], stride, pad, name=conv)
-        wf = self.fp.keep[-3]                                        # packed [Cout_pad, K_pad] 16-bit operand
+        wf = self.fp.last_weight                                     # packed [Cout_pad, K_pad] 16-bit operand
         rawd = _vd(raw) if raw is not None else None
         zd, od = _vd(z), _vd(out)
         rd = _vd(residual) if residual is not None else None
@@ -516,9 +516,6 @@ class TrainNet(object):
 
     def grad_dict(self):
         return self._export(self.grads)
-
-    def launches_per_step(self):
-        return None
 
 
 # =====================================================================================================

@@ -212,7 +212,8 @@ int ifcb_memset_zero(void* d, int64_t bytes, void* stream);
  * UNBIASED variance).  Split in two launches so that the conv output z is read twice and the
  * activation written once:
  *   ifcb_bn_stats   z -> d_mean[C], d_invstd[C] = 1/sqrt(var+eps)  (+ running stats when non-NULL)
- *                   d_acc: 2*C float64 accumulators, zero on entry, zero again on exit
+ *                   d_acc: 2*C float64 accumulators at the start of a 64 KB scratch (8192 float64), zero on entry,
+ *                   zero again on exit
  *   ifcb_bn_apply   out = act(gamma*(z-mean)*invstd + beta (+ residual)); relu: 0/1
  *                   (ResNet: bn3 + identity + ReLU, resnet.py Bottleneck/BasicBlock.forward) */
 int ifcb_bn_stats(const ifcb_view* z, int batch, int dtype, float eps, float momentum, double* d_acc,
@@ -227,7 +228,8 @@ int ifcb_bn_apply(const ifcb_view* z, const ifcb_view* out, const ifcb_view* res
  *   dz  = gamma*invstd*(dy' - mean(dy') - xhat*mean(dy'*xhat)),  xhat = (z-mean)*invstd
  *   d_dgamma[C] += sum(dy'*xhat), d_dbeta[C] += sum(dy')
  *   dres (optional, the residual branch's gradient) = or += dy'
- * dz may alias dy.  d_acc: scratch of 2*C float64 followed by 3*C float32 (4*C*8 bytes is enough). */
+ * dz may alias dy.  d_acc: the 64 KB scratch shared with ifcb_bn_stats: float64 [0, 4096) are per-channel
+ * accumulators (2*C used; zero on entry, zero again on exit), the 3*C coefficient floats go behind them. */
 int ifcb_bn_backward(const ifcb_view* dy, const ifcb_view* a, const ifcb_view* z, const ifcb_view* dz,
                      const ifcb_view* dres, int dres_accumulate, int relu, int batch, int dtype,
                      const float* d_mean, const float* d_invstd, const float* d_gamma, const float* d_beta,

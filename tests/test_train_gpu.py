@@ -112,7 +112,7 @@ def test_bn_train_fwd_bwd(cuda, case, dt):
     beta = (torch.randn(Cc, generator=g) * 0.2).to(cuda)
     rm, rv = torch.zeros(Cc, device=cuda), torch.ones(Cc, device=cuda)
     mean, invstd = torch.zeros(Cc, device=cuda), torch.zeros(Cc, device=cuda)
-    acc = torch.zeros(4 * Cc, dtype=torch.float64, device=cuda)
+    acc = torch.zeros(8192, dtype=torch.float64, device=cuda)       # 64 KB scratch: accumulators + coefficient floats
     zd, od = _vd(z), _vd(out)
     rd = _vd(res) if has_res else None
     _lib.check(L.ifcb_bn_stats(C.byref(zd), B, cdt, 1e-3, 0.1, acc.data_ptr(), mean.data_ptr(), invstd.data_ptr(), rm.data_ptr(),
@@ -132,7 +132,7 @@ def test_bn_train_fwd_bwd(cuda, case, dt):
     got = _read(out)
     tol = 2.0 ** (-8 if dt == 'bf16' else -11)               # one 16-bit rounding of the output
     assert float((got - y.detach()).abs().max()) <= tol * (1.0 + float(y.detach().abs().max())), name
-    assert float(acc[:2 * Cc].abs().max()) == 0.0             # accumulators cleared for the next layer
+    assert float(acc[:4096].abs().max()) == 0.0               # accumulators cleared for the next layer
     assert torch.allclose(rm, rm_r, rtol=1e-4, atol=1e-5) and torch.allclose(rv, rv_r, rtol=1e-4, atol=1e-5)
     # backward: dy arrives as a 16-bit tensor; mask from OUR forward output so both sides agree on it
     dy, dy32 = _mk(cuda, B, H, W, Cc, tdt, gen=g, scale=0.5)
@@ -403,8 +403,17 @@ def test_forward_backward_vs_oracle(cuda, case):
     print('%s teacher-forced: %d checks, failing %s, largest rel L2 %s' %
           (arch, len(stats), [t for t in stats if not t[3]][:8], [(t[0], round(t[1], 5)) for t in worst]))
     assert ok, [t for t in stats if not t[3]][:20]
-
     grads = {k: v.to(cuda).float() for k, v in net.grad_dict().items()}
+    # a SECOND step on new data after an Adam update (operands repacked, scratch buffers and gradient
+    # tensors reused): the same teacher-forced check must still hold
+    net.adam()
+    x2 = torch.rand(B, 3, R, R, generator=g).to(cuda)
+    y2 = torch.randint(0, n_classes, (B,), generator=g).to(cuda)
+    net.forward_backward(x2, y2)
+    ok2, stats2 = local_parity(net, (lambda nm: 1e-3) if arch == 'inception_v3' else (lambda nm: 1e-5))
+    assert ok2, ('second step', [t for t in stats2 if not t[3]][:20])
+    net.inp.copy_(x)
+
     q_loss, q_grads = train_ref.forward_backward(qmodel, x, y, dropout=False)
     f_loss, f_grads = train_ref.forward_backward(model, x, y, dropout=False)
     assert sorted(grads) == sorted(f_grads)
@@ -514,3 +523,78 @@ def test_neuston_net_train_then_run(cuda, tmp_path):
     assert rc == 0
     j = json.load(open(str(tmp_path / 'run_out' / (synth_bins.bin_lid(0) + '_class.json'))))
     assert len(j['output_classes']) == 20 and j['class_labels'] == ['class_0', 'class_1', 'class_2']
+
+
+def test_neuston_net_train_two_gpus(cuda, tmp_path):
+    """`torchrun -m ifcb_classifier_b200.neuston_net ... TRAIN ...` on 2 GPUs: per-rank batches, NCCL gradient mean,
+    rank 0 writes the reference's files; skipped on a single-GPU box."""
+    import os, subprocess, sys
+    from PIL import Image
+    from tests.fixtures import class_rois
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    src = tmp_path / 'dataset'
+    imgs, labels = class_rois(120, 3, seed=9)
+    for i, (im, k) in enumerate(zip(imgs, labels.tolist())):
+        d = src / ('class_%d' % k)
+        d.mkdir(parents=True, exist_ok=True)
+        Image.fromarray(im, mode='L').save(str(d / ('img_%03d.png' % i)))
+    out = tmp_path / 'train_out'
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr', '127.0.0.1',
+           '--master-port', str(29900 + os.getpid() % 90), '-m', 'ifcb_classifier_b200.neuston_net', '--batch', '8', '--loaders', '2',
+           'TRAIN', str(src), 'resnet18', 'T2', '--untrain', '--seed', '5', '--emax', '6', '--emin', '6', '--estop', '6', '--outdir', str(out)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=root)
+    assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-3000:])
+    for f in ('T2.ptl', 'epochs.csv', 'args.yml', 'training_images.list', 'validation_images.list', 'results.mat'):
+        assert (out / f).exists(), f
+    rows = (out / 'epochs.csv').read_text().strip().splitlines()
+    assert len(rows) == 7
+    losses = [float(r_.split(',')[2]) for r_ in rows[1:]]
+    assert losses[-1] < losses[0], rows
+
+
+def test_bn_scratch_is_reusable_across_layers(cuda):
+    """One 64 KB scratch serves every BN layer of a step: a narrow layer's backward (which leaves its coefficient
+    floats in the scratch) must not disturb the accumulators a wider layer uses next, forward or backward."""
+    from ifcb_classifier_b200 import _lib
+    from ifcb_classifier_b200.train import _vd
+    L = _lib.lib()
+    tdt, cdt = torch.bfloat16, _lib.IFCB_ACT_BF16
+    g = torch.Generator().manual_seed(21)
+    acc = torch.zeros(8192, dtype=torch.float64, device=cuda)
+
+    def layer(Cc):
+        z, z32 = _mk(cuda, 4, 6, 6, Cc, tdt, gen=g, scale=2.0)
+        dy, dy32 = _mk(cuda, 4, 6, 6, Cc, tdt, gen=g)
+        return dict(C=Cc, z=z, z32=z32, dy=dy, dy32=dy32, gamma=(torch.rand(Cc, generator=g) + 0.5).to(cuda),
+                    beta=(torch.randn(Cc, generator=g) * 0.2).to(cuda), mean=torch.zeros(Cc, device=cuda), invstd=torch.zeros(Cc, device=cuda),
+                    dgam=torch.zeros(Cc, device=cuda), dbet=torch.zeros(Cc, device=cuda))
+
+    def stats(l):
+        _lib.check(L.ifcb_bn_stats(C.byref(_vd(l['z'])), 4, cdt, 1e-5, 0.1, acc.data_ptr(), l['mean'].data_ptr(), l['invstd'].data_ptr(), None, None,
+                                   _stream()), 'bn_stats')
+
+    def backward(l):
+        _lib.check(L.ifcb_bn_backward(C.byref(_vd(l['dy'])), None, C.byref(_vd(l['z'])), C.byref(_vd(l['dy'])), None, 0, 1, 4, cdt,
+                                      l['mean'].data_ptr(), l['invstd'].data_ptr(), l['gamma'].data_ptr(), l['beta'].data_ptr(), acc.data_ptr(),
+                                      l['dgam'].data_ptr(), l['dbet'].data_ptr(), _stream()), 'bn_backward')
+
+    narrow, wide, wide2 = layer(64), layer(512), layer(2048)
+    for l in (narrow, wide, wide2):
+        stats(l)
+    backward(narrow)                 # leaves 3*64 coefficient floats in the scratch
+    stats(wide)                      # forward of a wider layer right after
+    backward(wide)
+    backward(wide2)
+    torch.cuda.synchronize()
+    for l in (wide, wide2):
+        zr = l['z32'].clone().requires_grad_(True)
+        gr, br = l['gamma'].clone().requires_grad_(True), l['beta'].clone().requires_grad_(True)
+        y = F.relu(F.batch_norm(zr, None, None, gr, br, training=True, eps=1e-5))
+        y.backward(l['dy32'])
+        mean_ref = l['z32'].mean((0, 2, 3))
+        assert torch.allclose(l['mean'], mean_ref, rtol=1e-4, atol=1e-5)
+        assert torch.allclose(l['dbet'], br.grad, rtol=2e-3, atol=2e-3 * float(br.grad.abs().max()))
+        assert torch.allclose(l['dgam'], gr.grad, rtol=2e-3, atol=2e-3 * float(gr.grad.abs().max()))
+    assert float(acc[:4096].abs().max()) == 0.0
