@@ -103,8 +103,6 @@ def do_run(args, classifier=None):
             raise argparse.ArgumentTypeError('IN|OUT must be either "IN" or "OUT"')
         if len(args.filter) < 2:
             raise argparse.ArgumentTypeError('Must be at least one KEYWORD')
-    if args.src_type != 'bin':
-        raise NotImplementedError('--type img is outside the per-bin hot path (DESIGN.md, out of scope)')
     if classifier is None:
         classifier = NeustonModel.load_from_checkpoint(args.MODEL)
     hp = classifier.hparams
@@ -112,7 +110,7 @@ def do_run(args, classifier=None):
     if os.path.isdir(args.SRC) and not args.SRC.endswith(os.sep):
         args.SRC = args.SRC + os.sep
     if not args.outfile:
-        args.outfile = ['D{BIN_YEAR}/D{BIN_DATE}/{BIN_ID}_class.h5']
+        args.outfile = ['D{BIN_YEAR}/D{BIN_DATE}/{BIN_ID}_class.h5'] if args.src_type == 'bin' else ['img_results.json']
 
     rank, world, local_rank = sharding.env_rank_world()
     if not torch.cuda.is_available():
@@ -130,6 +128,8 @@ def do_run(args, classifier=None):
                     keywords.extend(f.read().splitlines())
             else:
                 keywords.append(kw)
+    if args.src_type == 'img':
+        return _run_images(args, classifier, filter_mode, keywords, rank, world, local_rank)
     if os.path.isdir(args.SRC):
         root = args.SRC
         dd = ifcb_io.DataDirectory(root, whitelist=keywords if filter_mode == 'IN' else None,
@@ -194,6 +194,60 @@ def do_run(args, classifier=None):
             for b, t, m in errs:
                 print(b, t, m)
     return allsum
+
+
+def _run_images(args, classifier, filter_mode, keywords, rank, world, local_rank):
+    """RUN --type img (reference neuston_net.py:280-308): classify image files (a directory tree, a .txt list or one
+    file) through the same fused preprocess + network path as bins; images are decoded to gray planes on host
+    threads and packed into one byte buffer per batch."""
+    import concurrent.futures as cf
+    import numpy as np
+    import torch
+    from . import results
+    from .engine import BinClassifier
+    from .neuston_data import IMG_EXTENSIONS, load_gray
+    from .preprocess import parse_imgnorm
+    hp = classifier.hparams
+    ok_ext = lambda p: p.lower().endswith(IMG_EXTENSIONS)
+    paths = []
+    if os.path.isdir(args.SRC):
+        for pardir, _, imgs in os.walk(args.SRC):
+            paths.extend(os.path.join(pardir, i) for i in sorted(imgs) if ok_ext(i))
+    elif os.path.isfile(args.SRC) and args.SRC.endswith('.txt'):
+        with open(args.SRC) as f:
+            paths = [l.strip() for l in f.read().splitlines() if ok_ext(l.strip())]
+    elif ok_ext(args.SRC):
+        paths.append(args.SRC)
+    if filter_mode == 'IN':
+        paths = [p for p in paths if any(k in p for k in keywords)]
+    elif filter_mode == 'OUT':
+        paths = [p for p in paths if not any(k in p for k in keywords)]
+    assert len(paths) > 0, 'No images to process'
+    paths = paths[rank::world] if world > 1 else paths          # multi-GPU: each rank takes a stride of the list
+    img_norm = parse_imgnorm(hp.img_norm) if getattr(hp, 'img_norm', None) else None
+    B = max(args.batch_size, 16)
+    eng = BinClassifier(hp.MODEL, classifier.model.state_dict(), img_norm=img_norm, transform_input=classifier.model.transform_input,
+                        device=torch.device('cuda', local_rank), batch_cap=B, dtype=args.dtype, max_rois=B)
+    scores = []
+    with cf.ThreadPoolExecutor(max_workers=max(1, args.loaders)) as pool:
+        for i in range(0, len(paths), B):
+            imgs = list(pool.map(load_gray, paths[i:i + B]))
+            hs = np.array([im.shape[0] for im in imgs], np.int32)
+            ws = np.array([im.shape[1] for im in imgs], np.int32)
+            sizes = hs.astype(np.int64) * ws
+            offs = np.concatenate([[0], np.cumsum(sizes)[:-1]]).astype(np.int64)
+            roi = np.concatenate([im.reshape(-1) for im in imgs])
+            s, _ = eng.classify_bin(roi, offs, hs, ws)
+            scores.append(s.copy())
+    scores = np.concatenate(scores)
+    outs = []
+    for of in args.outfile:
+        of_r = of if world == 1 else of.replace('.', '.rank%d.' % rank, 1) if '{INPUT_SUBDIRS}' not in of else of
+        outs.append(results.save_run_results(paths, scores, hp.classes, args.cmd_timestamp, args.outdir, of_r, getattr(hp, 'model_id', None),
+                                             args.SRC))
+    if rank == 0:
+        print('RUN IS DONE')
+    return outs
 
 
 def do_training(args):

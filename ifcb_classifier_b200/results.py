@@ -27,12 +27,36 @@ def save_run_results(input_images, output_scores, class_labels, timestamp, outdi
     results = dict(version='v3', model_id=model_id, timestamp=timestamp, class_labels=list(class_labels),
                    input_images=list(input_images), output_classes=np.asarray(output_classes),
                    output_scores=output_scores)
-    results['bin_id'] = input_obj.pid
-    results['roi_numbers'] = [int(str(img).rsplit('_', 1)[1]) for img in input_images]
-    path = outfile_path(outdir, outfile, input_obj)
-    os.makedirs(os.path.dirname(path) or '.', exist_ok=True)
-    _save(path, results)
-    return path
+    if hasattr(input_obj, 'pid'):                                  # a bin (ifcb.Pid upstream)
+        results['bin_id'] = input_obj.pid
+        results['roi_numbers'] = [int(str(img).rsplit('_', 1)[1]) for img in input_images]
+        path = outfile_path(outdir, outfile, input_obj)
+        os.makedirs(os.path.dirname(path) or '.', exist_ok=True)
+        _save(path, results)
+        return path
+    # --type img (neuston_callbacks.py:186-206): one file, or one per sub-directory of the input tree
+    outfile = os.path.join(outdir, outfile)
+    if '{INPUT_SUBDIRS}' in outfile:
+        input_src = input_obj if (isinstance(input_obj, str) and os.path.isdir(input_obj)) else ''
+        groups = {}
+        for path_, cls_, sc_ in zip(input_images, results['output_classes'], output_scores):
+            parent = os.path.dirname(path_.replace(input_src, ''))
+            g = groups.setdefault(parent, dict(results, input_images=[], output_classes=[], output_scores=[]))
+            g['input_images'].append(os.path.basename(path_))
+            g['output_classes'].append(cls_)
+            g['output_scores'].append(sc_)
+        written = []
+        for parent, g in groups.items():
+            sub = outfile.format(INPUT_SUBDIRS=parent)
+            os.makedirs(os.path.dirname(sub) or '.', exist_ok=True)
+            g['output_classes'] = np.asarray(g['output_classes'], dtype=results['output_classes'].dtype)
+            g['output_scores'] = np.asarray(g['output_scores'], dtype=output_scores.dtype)
+            _save(sub, g)
+            written.append(sub)
+        return written
+    os.makedirs(os.path.dirname(outfile) or '.', exist_ok=True)
+    _save(outfile, results)
+    return outfile
 
 
 def _save(path, r):
@@ -41,8 +65,11 @@ def _save(path, r):
     if ext == '.json':
         out = dict(version=r['version'], model_id=r['model_id'], timestamp=r['timestamp'],
                    class_labels=r['class_labels'], output_scores=r['output_scores'].tolist(),
-                   output_classes=[int(c) for c in r['output_classes']], bin_id=r['bin_id'],
-                   roi_numbers=r['roi_numbers'])
+                   output_classes=[int(c) for c in r['output_classes']])
+        if 'bin_id' in r:
+            out['bin_id'], out['roi_numbers'] = r['bin_id'], r['roi_numbers']
+        else:
+            out['input_images'] = r['input_images']
         with open(path, 'w') as f:
             json.dump(out, f)
     elif ext == '.mat':
@@ -50,8 +77,11 @@ def _save(path, r):
         out = dict(output_classes=r['output_classes'].astype('u4') + 1,      # matlab is 1-based
                    version=r['version'], model_id=r['model_id'] if r['model_id'] is not None else '',
                    timestamp=r['timestamp'], output_scores=r['output_scores'].astype('f4'),
-                   class_labels=np.asarray(r['class_labels'], dtype='object'), bin_id=r['bin_id'],
-                   roi_numbers=r['roi_numbers'])
+                   class_labels=np.asarray(r['class_labels'], dtype='object'))
+        if 'bin_id' in r:
+            out['bin_id'], out['roi_numbers'] = r['bin_id'], r['roi_numbers']
+        else:
+            out['input_images'] = np.asarray(r['input_images'], dtype='object')
         savemat(path, out, do_compression=True)
     else:
         try:
@@ -61,9 +91,13 @@ def _save(path, r):
         with h5.File(path, 'w') as f:
             meta = f.create_dataset('metadata', data=h5.Empty('f'))
             meta.attrs['version'], meta.attrs['model_id'] = r['version'], r['model_id']
-            meta.attrs['timestamp'], meta.attrs['bin_id'] = r['timestamp'], r['bin_id']
+            meta.attrs['timestamp'] = r['timestamp']
             f.create_dataset('output_classes', data=r['output_classes'], compression='gzip', dtype='float16')
             f.create_dataset('output_scores', data=r['output_scores'], compression='gzip', dtype='float16')
             f.create_dataset('class_labels', data=np.bytes_(r['class_labels']), compression='gzip',
                              dtype=h5.string_dtype())
-            f.create_dataset('roi_numbers', data=r['roi_numbers'], compression='gzip', dtype='uint16')
+            if 'bin_id' in r:
+                meta.attrs['bin_id'] = r['bin_id']
+                f.create_dataset('roi_numbers', data=r['roi_numbers'], compression='gzip', dtype='uint16')
+            else:
+                f.create_dataset('input_images', data=np.bytes_(r['input_images']), compression='gzip', dtype=h5.string_dtype())

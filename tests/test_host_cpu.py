@@ -192,3 +192,21 @@ def test_two_rank_gloo_gradient_mean():
     for out, _ in outs:
         line = [l for l in out.splitlines() if l.startswith('RESULT ')][0]
         assert json.loads(line[len('RESULT '):])['ok']
+
+
+def test_result_files_for_image_inputs(tmp_path):
+    """RUN --type img (neuston_callbacks.py:186-206): one file with input_images, or one per input sub-directory."""
+    rng = np.random.default_rng(1)
+    scores = rng.random((4, 3)).astype(np.float32)
+    src = str(tmp_path / 'imgs') + os.sep
+    imgs = [src + 'a/x1.png', src + 'a/x2.png', src + 'b/c/y1.png', src + 'b/c/y2.png']
+    for p_ in imgs:
+        os.makedirs(os.path.dirname(p_), exist_ok=True)
+        open(p_, 'wb').close()
+    p = results.save_run_results(imgs, scores, ['u', 'v', 'w'], 'ts', str(tmp_path / 'out'), 'img_results.json', 'm1', src)
+    j = json.load(open(p))
+    assert j['input_images'] == imgs and 'bin_id' not in j and j['output_classes'] == scores.argmax(1).tolist()
+    ps = results.save_run_results(imgs, scores, ['u', 'v', 'w'], 'ts', str(tmp_path / 'out2'), '{INPUT_SUBDIRS}/res.json', 'm1', src)
+    assert sorted(os.path.relpath(q, str(tmp_path / 'out2')) for q in ps) == ['a/res.json', 'b/c/res.json']
+    j = json.load(open([q for q in ps if q.endswith('b/c/res.json')][0]))
+    assert j['input_images'] == ['y1.png', 'y2.png'] and np.allclose(j['output_scores'], scores[2:])

@@ -482,6 +482,7 @@ def test_neuston_net_train_then_run(cuda, tmp_path):
     """TRAIN entry point end to end on a small class-per-folder PNG tree (separable synthetic classes), then
     RUN with the checkpoint it wrote: files of the reference's layout appear and the model has learnt."""
     import json
+    import os
     import numpy as np
     from PIL import Image
     from scipy.io import loadmat
@@ -523,6 +524,14 @@ def test_neuston_net_train_then_run(cuda, tmp_path):
     assert rc == 0
     j = json.load(open(str(tmp_path / 'run_out' / (synth_bins.bin_lid(0) + '_class.json'))))
     assert len(j['output_classes']) == 20 and j['class_labels'] == ['class_0', 'class_1', 'class_2']
+    # RUN --type img over the training tree: the model recognises its own classes
+    rc = neuston_net.main(['--batch', '16', 'RUN', str(src), str(out / 'T1.ptl'), 'R2', '--type', 'img', '--outdir', str(tmp_path / 'run_img')])
+    assert rc == 0
+    j = json.load(open(str(tmp_path / 'run_img' / 'img_results.json')))
+    assert len(j['input_images']) == 96 and 'bin_id' not in j
+    truth = [int(os.path.basename(os.path.dirname(p_)).split('_')[1]) for p_ in j['input_images']]
+    acc = float(np.mean(np.array(truth) == np.array(j['output_classes'])))
+    assert acc >= 0.6, acc
 
 
 def test_neuston_net_train_two_gpus(cuda, tmp_path):
