@@ -516,6 +516,82 @@ def build_resnet(pb, sd, arch, inp, in_kind, R, affine=None):
     return pb.head(x, sd['fc.weight'], sd['fc.bias'])
 
 
+# =============================================================================
+# VGG / AlexNet (torchvision/models/vgg.py, alexnet.py), eval mode: conv(+bias)(+BN)+ReLU stacks, max pools,
+# and the three-layer classifier run as convolutions on the same tcgen05 kernel (Linear over the
+# flattened 7x7 / 6x6 feature map == a 7x7 / 6x6 conv to a 1x1 output; Dropout is the identity in eval).
+# =============================================================================
+VGG_CFG = {
+    'vgg11': [64, 'M', 128, 'M', 256, 256, 'M', 512, 512, 'M', 512, 512, 'M'],
+    'vgg13': [64, 64, 'M', 128, 128, 'M', 256, 256, 'M', 512, 512, 'M', 512, 512, 'M'],
+    'vgg16': [64, 64, 'M', 128, 128, 'M', 256, 256, 256, 'M', 512, 512, 512, 'M', 512, 512, 512, 'M'],
+    'vgg19': [64, 64, 'M', 128, 128, 'M', 256, 256, 256, 256, 'M', 512, 512, 512, 512, 'M', 512, 512, 512, 512, 'M'],
+}
+# AlexNet features: (index in nn.Sequential, kernel, stride, pad) / 'M' = MaxPool2d(3, 2)
+ALEXNET_CFG = [(0, 11, 4, 2), 'M', (3, 5, 1, 2), 'M', (6, 3, 1, 1), (8, 3, 1, 1), (10, 3, 1, 1), 'M']
+PLAIN_ARCHS = tuple(VGG_CFG) + tuple(a + '_bn' for a in VGG_CFG) + ('alexnet',)
+
+
+def build_plain_cnn(pb, sd, arch, inp, in_kind, R, affine=None):
+    """VGG (with or without BatchNorm) and AlexNet."""
+    sz = lambda h, k, s, p: (h + 2 * p - k) // s + 1
+
+    def layer(idx, bn_idx):
+        w, b = sd['features.%d.weight' % idx], sd['features.%d.bias' % idx].float()
+        if bn_idx is not None:                                   # conv bias folds into the BN shift
+            scale, shift = fold_bn(sd, 'features.%d' % bn_idx, 1e-5)
+            return w, scale, shift + scale * b
+        return w, torch.ones(int(w.shape[0])), b
+
+    if arch == 'alexnet':
+        seq = list(ALEXNET_CFG)
+        pool_k, pool_s = 3, 2
+    else:
+        bn = arch.endswith('_bn')
+        seq, idx = [], 0
+        for v in VGG_CFG[arch[:-3] if bn else arch]:
+            if v == 'M':
+                seq.append('M'); idx += 1
+            else:
+                seq.append((idx, 3, 1, 1, idx + 1 if bn else None)); idx += 3 if bn else 2
+        pool_k, pool_s = 2, 2
+    x, H, first = None, R, True
+    for pos, item in enumerate(seq):
+        if item == 'M':
+            Ho = sz(H, pool_k, pool_s, 0)
+            out = pb.alloc(Ho, Ho, x.C)
+            pb.pool(IFCB_POOL_MAX, x, pool_k, pool_s, 0, out, name='features.pool%d' % pos)
+            x, H = out, Ho
+            continue
+        idx, k, stride, pad = item[:4]
+        w, scale, shift = layer(idx, item[4] if len(item) > 4 else None)
+        Ho = sz(H, k, stride, pad)
+        nxt = seq[pos + 1] if pos + 1 < len(seq) else 'M'
+        opad = pb.border_for(Ho, Ho, int(w.shape[0]), (nxt[1], nxt[1]), (nxt[2], nxt[2]), (nxt[3], nxt[3]), Ci=int(w.shape[0])) if nxt != 'M' else (0, 0)
+        out = pb.alloc(Ho, Ho, int(w.shape[0]), opad)
+        if first:
+            pb.stem(inp, in_kind, R, R, w, scale, shift, stride, pad, out, affine=affine, name='features.%d' % idx)
+            first = False
+        else:
+            pb.conv(x, [dict(weight=w, scale=scale, shift=shift, relu=True, out=out)], (stride, stride), (pad, pad), name='features.%d' % idx)
+        x, H = out, Ho
+    # classifier: [Dropout] Linear ReLU [Dropout] Linear ReLU Linear  (AdaptiveAvgPool2d is the identity at 224 px)
+    lin = sorted(int(k.split('.')[1]) for k in sd if k.startswith('classifier.') and k.endswith('.weight'))
+    assert len(lin) == 3
+    feat = int(sd['classifier.%d.weight' % lin[0]].shape[1])
+    assert feat == x.C * H * H, '%s: input size %d gives a %dx%d feature map; the classifier expects %d features (use %d px)' % (
+        arch, R, H, H, feat, 224)
+    w1 = sd['classifier.%d.weight' % lin[0]].view(-1, x.C, H, H)                      # flatten order of NCHW: (c, h, w)
+    h1 = pb.alloc(1, 1, int(w1.shape[0]))
+    pb.conv(x, [dict(weight=w1, scale=torch.ones(int(w1.shape[0])), shift=sd['classifier.%d.bias' % lin[0]].float(), relu=True, out=h1)],
+            name='classifier.%d' % lin[0])
+    w2 = sd['classifier.%d.weight' % lin[1]]
+    h2 = pb.alloc(1, 1, int(w2.shape[0]))
+    pb.conv(h1, [dict(weight=w2.view(w2.shape[0], w2.shape[1], 1, 1), scale=torch.ones(int(w2.shape[0])),
+                      shift=sd['classifier.%d.bias' % lin[1]].float(), relu=True, out=h2)], name='classifier.%d' % lin[1])
+    return pb.head(h2, sd['classifier.%d.weight' % lin[2]], sd['classifier.%d.bias' % lin[2]])
+
+
 class CompiledNet(object):
     """A model compiled for a fixed batch capacity and input kind.
 
@@ -546,10 +622,12 @@ class CompiledNet(object):
             build_inception_v3(pb, sd, self.inp, kind, self.R, affine=affine, transform_input=transform_input, fuse=fuse)
         elif arch in RESNET_CFG:
             build_resnet(pb, sd, arch, self.inp, kind, self.R, affine=affine)
+        elif arch in PLAIN_ARCHS:
+            build_plain_cnn(pb, sd, arch, self.inp, kind, self.R, affine=affine)
         else:
             raise KeyError('model unknown!')
         self.pb = pb
-        self.n_classes = int(sd['fc.weight'].shape[0])
+        self.n_classes = int(pb.scores.shape[1])
         self.flops_per_image = pb.flops_per_image
         self.num_launches = _lib.lib().ifcb_plan_num_launches(pb.handle)
 

@@ -28,6 +28,9 @@ def ref_model(name, n_classes, seed=0):
         elif name.startswith('resnet'):
             m = getattr(M, name)(weights=None)
             m.fc = nn.Linear(m.fc.in_features, n_classes)
+        elif name == 'alexnet' or name.startswith('vgg'):
+            m = getattr(M, name)(weights=None)
+            m.classifier[6] = nn.Linear(m.classifier[6].in_features, n_classes)
         else:
             raise KeyError('model unknown!')
     return m

@@ -109,3 +109,20 @@ def test_partial_batches_and_f32_input(cuda):
     # the u8 stem folds the three identical channels into one gray weight (fp32 reassociation of the
     # same sum), so it matches the 3-channel f32 stem to rounding noise only
     assert float((got - s.cpu()).abs().max()) <= 1e-3
+
+
+@pytest.mark.parametrize('arch', ['alexnet', 'vgg11_bn', 'vgg16'])
+def test_plain_cnn_parity(cuda, arch):
+    """VGG / AlexNet (reference neuston_models.py:27-36) on the same kernels: convs with bias, 2x2 / 3x3 max pools and the
+    three-layer classifier run as convolutions.  Fixture C (briefly trained on separable classes); same gates."""
+    n_classes, R = 10, 224
+    imgs, labels = fixtures.class_rois(192, n_classes, seed=2)
+    x = torch.from_numpy(np.stack([ref_preprocess(im, R, None) for im in imgs]))
+    model = fixtures.ref_model(arch, n_classes)
+    fixtures.brief_train(model, x[:128], labels[:128], cuda, steps=30, batch=32, lr=1e-4)
+    ref = _ref_scores(cuda, model, x)
+    got = _pipeline_scores(cuda, arch, model, imgs, None)
+    agree = float((ref.argmax(1) == got.argmax(1)).float().mean())
+    dmax = float((ref - got).abs().max())
+    print('%s fixture C: top-1 agreement %.4f, max|dscore| %.2e' % (arch, agree, dmax))
+    assert agree >= 0.995 and dmax <= 1e-2, (agree, dmax)
