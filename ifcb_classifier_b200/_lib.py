@@ -67,7 +67,8 @@ class PoolDesc(C.Structure):
                 ('k', C.c_int32), ('stride', C.c_int32), ('pad', C.c_int32),
                 ('d_out', C.c_void_p), ('out_ld', C.c_int32),
                 ('d_scale', C.c_void_p), ('d_shift', C.c_void_p), ('relu', C.c_int32), ('dtype', C.c_int32),
-                ('in_pad_h', C.c_int32), ('in_pad_w', C.c_int32), ('out_pad_h', C.c_int32), ('out_pad_w', C.c_int32)]
+                ('in_pad_h', C.c_int32), ('in_pad_w', C.c_int32), ('out_pad_h', C.c_int32), ('out_pad_w', C.c_int32),
+                ('ceil_mode', C.c_int32)]
 
 
 class HeadDesc(C.Structure):

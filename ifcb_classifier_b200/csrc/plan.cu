@@ -351,6 +351,15 @@ extern "C" int ifcb_plan_add_pool(ifcb_plan* plan, const ifcb_pool_desc* d) {
   L.pool.d = *d;
   L.pool.P = out_dim(d->H, d->k, d->stride, d->pad);
   L.pool.Q = out_dim(d->W, d->k, d->stride, d->pad);
+  if (d->ceil_mode) {      // torch pooling_output_shape: ceil division, and the last window must start inside the (left-padded) input
+    auto ceil_dim = [](int in, int k, int s, int p) {
+      int o = (in + 2 * p - k + s - 1) / s + 1;
+      if ((o - 1) * s >= in + p) --o;
+      return o;
+    };
+    L.pool.P = ceil_dim(d->H, d->k, d->stride, d->pad);
+    L.pool.Q = ceil_dim(d->W, d->k, d->stride, d->pad);
+  }
   IFCB_ARG_CHECK(L.pool.P > 0 && L.pool.Q > 0, "pool: empty output");
   plan->layers.push_back(L);
   return 0;

@@ -216,8 +216,9 @@ class PlanBuilder(object):
         self._note(name, 'stem', 2 * out.H * out.W * Co * 3 * kh * kw)
         return out
 
-    def pool(self, kind, x, k, stride, pad, out, scale=None, shift=None, relu=False, name='pool'):
+    def pool(self, kind, x, k, stride, pad, out, scale=None, shift=None, relu=False, name='pool', ceil_mode=False):
         d = PoolDesc()
+        d.ceil_mode = 1 if ceil_mode else 0
         d.kind, d.d_in, d.in_ld, d.C = kind, x.ptr, x.ld, x.C
         d.batch_cap, d.H, d.W, d.k, d.stride, d.pad = self.batch_cap, x.H, x.W, k, stride, pad
         d.d_out, d.out_ld = out.ptr, out.ld
@@ -592,6 +593,120 @@ def build_plain_cnn(pb, sd, arch, inp, in_kind, R, affine=None):
     return pb.head(h2, sd['classifier.%d.weight' % lin[2]], sd['classifier.%d.bias' % lin[2]])
 
 
+# =============================================================================
+# SqueezeNet 1.1 (torchvision/models/squeezenet.py; the reference's 'squeezenet' = squeezenet1_1 with a
+# 1x1-conv classifier of n_classes outputs, neuston_models.py:30-33), eval mode
+# =============================================================================
+def build_squeezenet(pb, sd, inp, in_kind, R, affine=None):
+    sz = lambda h, k, s, p: (h + 2 * p - k) // s + 1
+
+    def ceil_sz(h, k, s):
+        o = (h - k + s - 1) // s + 1
+        return o - 1 if (o - 1) * s >= h else o
+
+    def cbr(prefix, out):
+        w = sd[prefix + '.weight']
+        return dict(weight=w, scale=torch.ones(int(w.shape[0])), shift=sd[prefix + '.bias'].float(), relu=True, out=out)
+
+    H = sz(R, 3, 2, 0)
+    x = pb.alloc(H, H, 64)
+    w0 = sd['features.0.weight']
+    pb.stem(inp, in_kind, R, R, w0, torch.ones(64), sd['features.0.bias'].float(), 2, 0, x, affine=affine, name='features.0')
+    # features: 0 conv, 1 relu, 2 pool, 3-4 fire, 5 pool, 6-7 fire, 8 pool, 9-12 fire
+    for idx in (2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12):
+        if idx in (2, 5, 8):
+            Ho = ceil_sz(x.H, 3, 2)
+            out = pb.alloc(Ho, Ho, x.C)
+            pb.pool(IFCB_POOL_MAX, x, 3, 2, 0, out, name='features.%d' % idx, ceil_mode=True)
+            x = out
+            continue
+        pre = 'features.%d' % idx
+        sq = int(sd[pre + '.squeeze.weight'].shape[0])
+        e1, e3 = int(sd[pre + '.expand1x1.weight'].shape[0]), int(sd[pre + '.expand3x3.weight'].shape[0])
+        t = pb.alloc(x.H, x.W, sq, pb.border_for(x.H, x.W, e3, (3, 3), pad=(1, 1), Ci=sq))
+        pb.conv(x, [cbr(pre + '.squeeze', t)], name=pre + '.squeeze')
+        out = pb.alloc(x.H, x.W, e1 + e3)
+        pb.conv(t, [cbr(pre + '.expand1x1', out.slice(0, e1))], name=pre + '.expand1x1')
+        pb.conv(t, [cbr(pre + '.expand3x3', out.slice(e1, e1 + e3))], pad=(1, 1), name=pre + '.expand3x3')
+        x = out
+    # classifier: Dropout, Conv2d(512, n_classes, 1), ReLU, AdaptiveAvgPool2d(1)  ->  softmax over the pooled map
+    wc, bc = sd['classifier.1.weight'], sd['classifier.1.bias'].float()
+    n_classes = int(wc.shape[0])
+    c16 = (n_classes + 15) // 16 * 16
+    wp = torch.zeros((c16, int(wc.shape[1]), 1, 1)); wp[:n_classes] = wc
+    bp_ = torch.zeros(c16); bp_[:n_classes] = bc
+    y = pb.alloc(x.H, x.W, c16)
+    pb.conv(x, [dict(weight=wp, scale=torch.ones(c16), shift=bp_, relu=True, out=y)], name='classifier.1')
+    eye = torch.zeros((n_classes, c16)); eye[:, :n_classes] = torch.eye(n_classes)       # head = mean over pixels -> identity "fc" -> softmax
+    return pb.head(y, eye, torch.zeros(n_classes))
+
+
+# =============================================================================
+# DenseNet-121/169/201 (torchvision/models/densenet.py), eval mode.  Pre-activation layers: every dense layer has its
+# own BatchNorm over ALL features so far, so norm1 + relu1 cannot fold into a producer's epilogue -- it runs as a
+# k = 1 affine "pool" launch into a scratch tensor; norm2 + relu2 fold into conv1's epilogue; conv2 writes its growth
+# channels straight into the block's feature buffer (the concat is in place).
+# =============================================================================
+def build_densenet(pb, sd, inp, in_kind, R, affine=None):
+    eps = 1e-5
+    sz = lambda h, k, s, p: (h + 2 * p - k) // s + 1
+    n_init = int(sd['features.conv0.weight'].shape[0])
+    if n_init not in (32, 64):
+        raise NotImplementedError('densenet with %d stem channels (densenet161) has no B200 plan yet' % n_init)
+    blocks = []
+    b = 1
+    while ('features.denseblock%d.denselayer1.conv1.weight' % b) in sd:
+        n = 1
+        while ('features.denseblock%d.denselayer%d.conv1.weight' % (b, n + 1)) in sd:
+            n += 1
+        blocks.append(n)
+        b += 1
+    growth = int(sd['features.denseblock1.denselayer1.conv2.weight'].shape[0])
+    H0 = sz(R, 7, 2, 3)
+    a = pb.alloc(H0, H0, n_init)
+    sc, sh = fold_bn(sd, 'features.norm0', eps)
+    pb.stem(inp, in_kind, R, R, sd['features.conv0.weight'], sc, sh, 2, 3, a, affine=affine, name='features.conv0')
+    H = sz(H0, 3, 2, 1)
+    C_in = n_init
+    buf = pb.alloc(H, H, C_in + blocks[0] * growth)
+    pb.pool(IFCB_POOL_MAX, a, 3, 2, 1, buf.slice(0, C_in), name='features.pool0')
+    for bi, n_layers in enumerate(blocks):
+        for li in range(n_layers):
+            pre = 'features.denseblock%d.denselayer%d' % (bi + 1, li + 1)
+            xin = buf.slice(0, C_in)
+            t1 = pb.alloc(H, H, C_in)
+            s1, h1 = fold_bn(sd, pre + '.norm1', eps)
+            pb.pool(IFCB_POOL_AVG_AFFINE, xin, 1, 1, 0, t1, s1, h1, relu=True, name=pre + '.norm1')
+            w1 = sd[pre + '.conv1.weight']
+            mid = int(w1.shape[0])
+            t2 = pb.alloc(H, H, mid, pb.border_for(H, H, growth, (3, 3), pad=(1, 1), Ci=mid))
+            s2, h2 = fold_bn(sd, pre + '.norm2', eps)
+            pb.conv(t1, [dict(weight=w1, scale=s2, shift=h2, relu=True, out=t2)], name=pre + '.conv1')
+            w2 = sd[pre + '.conv2.weight']
+            pb.conv(t2, [dict(weight=w2, scale=torch.ones(growth), shift=torch.zeros(growth), relu=False,
+                              out=buf.slice(C_in, C_in + growth))], pad=(1, 1), name=pre + '.conv2')
+            C_in += growth
+        if bi + 1 < len(blocks):                       # transition: norm -> relu -> conv 1x1 -> avg_pool 2x2
+            pre = 'features.transition%d' % (bi + 1)
+            t1 = pb.alloc(H, H, C_in)
+            s1, h1 = fold_bn(sd, pre + '.norm', eps)
+            pb.pool(IFCB_POOL_AVG_AFFINE, buf, 1, 1, 0, t1, s1, h1, relu=True, name=pre + '.norm')
+            w = sd[pre + '.conv.weight']
+            Co = int(w.shape[0])
+            t2 = pb.alloc(H, H, Co)
+            pb.conv(t1, [dict(weight=w, scale=torch.ones(Co), shift=torch.zeros(Co), relu=False, out=t2)], name=pre + '.conv')
+            H = sz(H, 2, 2, 0)
+            nbuf = pb.alloc(H, H, Co + blocks[bi + 1] * growth)
+            pb.pool(IFCB_POOL_AVG_AFFINE, t2, 2, 2, 0, nbuf.slice(0, Co), torch.ones(Co), torch.zeros(Co), relu=False, name=pre + '.pool')
+            buf, C_in = nbuf, Co
+    t = pb.alloc(H, H, C_in)
+    s5, h5 = fold_bn(sd, 'features.norm5', eps)
+    pb.pool(IFCB_POOL_AVG_AFFINE, buf, 1, 1, 0, t, s5, h5, relu=True, name='features.norm5')
+    return pb.head(t, sd['classifier.weight'], sd['classifier.bias'])
+
+
+DENSE_ARCHS = ('densenet121', 'densenet169', 'densenet201')
+
 class CompiledNet(object):
     """A model compiled for a fixed batch capacity and input kind.
 
@@ -624,6 +739,10 @@ class CompiledNet(object):
             build_resnet(pb, sd, arch, self.inp, kind, self.R, affine=affine)
         elif arch in PLAIN_ARCHS:
             build_plain_cnn(pb, sd, arch, self.inp, kind, self.R, affine=affine)
+        elif arch == 'squeezenet':
+            build_squeezenet(pb, sd, self.inp, kind, self.R, affine=affine)
+        elif arch.startswith('densenet'):
+            build_densenet(pb, sd, self.inp, kind, self.R, affine=affine)
         else:
             raise KeyError('model unknown!')
         self.pb = pb

@@ -15,9 +15,9 @@ import warnings
 import torch
 import torch.nn as nn
 
-from .graph import CompiledNet, RESNET_CFG, PLAIN_ARCHS
+from .graph import CompiledNet, RESNET_CFG, PLAIN_ARCHS, DENSE_ARCHS
 
-ACCELERATED = ('inception_v3',) + tuple(RESNET_CFG) + tuple(PLAIN_ARCHS)
+ACCELERATED = ('inception_v3',) + tuple(RESNET_CFG) + tuple(PLAIN_ARCHS) + ('squeezenet',) + tuple(DENSE_ARCHS)
 
 
 def _torchvision_module(model_name, num_o_classes, pretrained):

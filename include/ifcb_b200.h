@@ -330,6 +330,8 @@ int ifcb_plan_add_stem(ifcb_plan* plan, const ifcb_stem_desc* desc);
  *   IFCB_POOL_AVG_AFFINE: F.avg_pool2d(count_include_pad=True) (inception.py:204,
  *     278,356) applied AFTER the branch's 1x1 convolution (the two commute), then
  *     the branch's folded BN scale/shift and ReLU: y = relu(scale*avg(x)+shift).
+ *     With k = 1 it is a per-channel affine (+ReLU): DenseNet's pre-activation norm -> relu
+ *     (densenet.py _DenseLayer / _Transition); with k = 2, stride 2, scale 1 its transition pool.
  */
 enum { IFCB_POOL_MAX = 0, IFCB_POOL_AVG_AFFINE = 1 };
 typedef struct {
@@ -345,6 +347,8 @@ typedef struct {
   int32_t relu;
   int32_t dtype; /* IFCB_ACT_* of input and output */
   int32_t in_pad_h, in_pad_w, out_pad_h, out_pad_w; /* zero borders of the two tensors */
+  int32_t ceil_mode; /* 1: output extent as torch's ceil_mode=True (windows may overhang the bottom / right edge;
+                        squeezenet.py MaxPool2d(3, 2, ceil_mode=True)) */
 } ifcb_pool_desc;
 int ifcb_plan_add_pool(ifcb_plan* plan, const ifcb_pool_desc* desc);
 

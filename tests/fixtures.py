@@ -28,6 +28,13 @@ def ref_model(name, n_classes, seed=0):
         elif name.startswith('resnet'):
             m = getattr(M, name)(weights=None)
             m.fc = nn.Linear(m.fc.in_features, n_classes)
+        elif name == 'squeezenet':
+            m = M.squeezenet1_1(weights=None)
+            m.classifier[1] = nn.Conv2d(512, n_classes, kernel_size=(1, 1), stride=(1, 1))
+            m.num_classes = n_classes
+        elif name.startswith('densenet'):
+            m = getattr(M, name)(weights=None)
+            m.classifier = nn.Linear(m.classifier.in_features, n_classes)
         elif name == 'alexnet' or name.startswith('vgg'):
             m = getattr(M, name)(weights=None)
             m.classifier[6] = nn.Linear(m.classifier[6].in_features, n_classes)

@@ -111,10 +111,12 @@ def test_partial_batches_and_f32_input(cuda):
     assert float((got - s.cpu()).abs().max()) <= 1e-3
 
 
-@pytest.mark.parametrize('arch', ['alexnet', 'vgg11_bn', 'vgg16'])
+@pytest.mark.parametrize('arch', ['alexnet', 'vgg11_bn', 'vgg16', 'squeezenet', 'densenet121'])
 def test_plain_cnn_parity(cuda, arch):
-    """VGG / AlexNet (reference neuston_models.py:27-36) on the same kernels: convs with bias, 2x2 / 3x3 max pools and the
-    three-layer classifier run as convolutions.  Fixture C (briefly trained on separable classes); same gates."""
+    """The other model families get_namebrand_model names (reference neuston_models.py:27-42) on the same kernels: convs
+    with bias, 2x2 / 3x3 / ceil-mode max pools, VGG / AlexNet classifiers run as convolutions, SqueezeNet's conv
+    classifier, DenseNet's pre-activation layers with in-place concatenation.  Fixture C (briefly trained on separable
+    classes); same gates as the headline models."""
     n_classes, R = 10, 224
     imgs, labels = fixtures.class_rois(192, n_classes, seed=2)
     x = torch.from_numpy(np.stack([ref_preprocess(im, R, None) for im in imgs]))
