@@ -120,7 +120,10 @@ class TrainNet(object):
         self.plist = []                 # _Param in forward order
         self.buffers = {}               # running_mean / running_var / num_batches_tracked
         self.records = []               # forward records, replayed backwards by _finalize
+        self.pre = []                   # closures that must run eagerly before the forward pass (step-dependent kernel arguments)
         self.fwd = []                   # closures
+        self._nbt_keys = []             # BatchNorm num_batches_tracked buffers (host counters)
+        self._graph = None
         self.bwd = []                   # closures, already in execution order
         self.repacks = []               # closures refreshing the 16-bit operands from the arena
         self.keep = []
@@ -266,8 +269,8 @@ class TrainNet(object):
                        rm.data_ptr(), rv.data_ptr(), self._stream())
             self._call('ifcb_bn_apply', C.byref(zd), C.byref(od), C.byref(rd) if rd is not None else None, B, dt, mean.data_ptr(),
                        invstd.data_ptr(), pg.wptr, pb.wptr, 1 if relu else 0, self._stream())
-            self.buffers[bn_key] += 1
         self.fwd.append(fwd)
+        self._nbt_keys.append(bn_key)
         self.records.append(dict(kind='conv_bn', x=x, z=z, out=out, residual=residual, relu=relu, stride=stride, pad=pad,
                                  pw=pw, pg=pg, pb=pb, mean=mean, invstd=invstd, wf=wf, Co=Co, Ci=Ci, kh=kh, kw=kw, stem=stem_geom,
                                  H=H, W=W, name=conv, raw=raw, pool_after=pool_after))
@@ -312,10 +315,13 @@ class TrainNet(object):
         rec = dict(kind='head', x=x, pw=pw, pb=pb, pooled=pooled, dlogits=dlogits, logits=logits, drop=drop, n_classes=n_classes,
                    dropout_p=dropout_p, which=which)
 
-        def fwd():
+        def pre():
             if drop is not None and self.dropout and not rec.get('fixed_mask'):
                 seed = (self.seed * 1000003 + self.step_count * 7919 + (1 if which == 'aux' else 0)) & ((1 << 63) - 1)
                 self._call('ifcb_dropout_scale', drop.data_ptr(), B * Cc, dropout_p, seed, self._stream())
+        self.pre.append(pre)
+
+        def fwd():
             use_drop = drop is not None and (self.dropout or rec.get('fixed_mask'))
             self._call('ifcb_head_train_fwd', C.byref(xd), B, dt, drop.data_ptr() if use_drop else None, pw.wptr, pb.wptr,
                        self.labels.data_ptr(), n_classes, loss_weight, pooled.data_ptr(), logits.data_ptr(), dlogits.data_ptr(),
@@ -454,10 +460,54 @@ class TrainNet(object):
         for r in self.repacks:
             r()
 
+    def _count_batch(self):
+        for k in self._nbt_keys:
+            self.buffers[k] += 1
+
     def forward(self):
+        for f in self.pre:
+            f()
+        self._forward_kernels()
+        self._count_batch()
+
+    def _forward_kernels(self):
         self._call('ifcb_memset_zero', self.loss.data_ptr(), 8, self._stream())
         for f in self.fwd:
             f()
+
+    def enable_cuda_graph(self):
+        """Captures the step's kernels into CUDA graphs: forward + backward split into one graph per gradient bucket
+        (the NCCL all-reduce of a finished bucket is launched eagerly between replays, so a data-parallel step
+        keeps its overlap), plus one graph for the operand repack.  Kernel arguments that change per step stay
+        outside: the dropout seed (``pre`` closures) and Adam's bias corrections.  Every pointer is fixed at
+        construction, so replays are valid for the life of the object."""
+        saved = {k: v.clone() for k, v in self.buffers.items() if v.is_cuda}     # warm-up passes must not move the running statistics
+        for _ in range(2):                                        # warm-up: function attributes, lazy module loads
+            self._forward_kernels()
+            self.backward()
+            self.repack()
+        for k, v in saved.items():
+            self.buffers[k].copy_(v)
+        torch.cuda.synchronize(self.device)
+        marks = {}
+        for m in self.bucket_marks:
+            marks.setdefault(m[0], []).append((m[1], m[2]))
+        cuts = sorted(marks)
+        segs, start = [], 0
+        for ci, cut in enumerate(cuts + ([len(self.bwd) - 1] if (not cuts or cuts[-1] != len(self.bwd) - 1) else [])):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                if start == 0:
+                    self._forward_kernels()
+                    self._call('ifcb_memset_zero', self.grads.data_ptr(), 4 * self.n_params, self._stream())
+                for b in self.bwd[start:cut + 1]:
+                    b()
+            segs.append((g, marks.get(cut, [])))
+            start = cut + 1
+        g_rp = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g_rp):
+            self.repack()
+        self._graph = (segs, g_rp)
 
     def backward(self, allreduce=None):
         """Runs the backward pass; ``allreduce(lo, hi)`` is called as soon as gradient range [lo, hi) is final."""
@@ -490,6 +540,24 @@ class TrainNet(object):
         """training_step + backward + (gradient mean over ranks) + Adam.  Returns the loss (device scalar)."""
         if self._reducer is None:
             self._reducer = GradReducer(self.grads)
+        if self._graph is not None:
+            if x is not None:
+                self.inp.copy_(x)
+            if labels is not None:
+                self.labels.copy_(labels)
+            for f in self.pre:
+                f()
+            for g, ranges in self._graph[0]:
+                g.replay()
+                for lo, hi in ranges:
+                    self._reducer(lo, hi)
+            self._count_batch()
+            self.step_count += 1
+            self._call('ifcb_adam_step', self.params.data_ptr(), self.grads.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
+                       self.n_params, self.lr, self.betas[0], self.betas[1], self.eps, self.step_count, float(self._reducer.wait()),
+                       self._stream())
+            self._graph[1].replay()
+            return self.loss[0]
         loss = self.forward_backward(x, labels, self._reducer if self._reducer.world > 1 else None)
         self.adam(self._reducer.wait())
         return loss

@@ -176,6 +176,7 @@ def do_training(args):
     B = args.batch_size
     net = TrainNet(args.MODEL, classifier.model.state_dict(), B, device=dev, dtype=getattr(args, 'train_dtype', 'bf16'), seed=args.seed,
                    R=args.resize)
+    net.enable_cuda_graph()                                       # replay the step's ~10^3 launches from CUDA graphs
     train_loader = ImageBatcher(train_ds, B, dev, args.loaders, rank, world, shuffle=True, seed=args.seed, drop_last=False)
     val_loader = ImageBatcher(val_ds, B, dev, args.loaders, 0, 1, shuffle=False, seed=args.seed)
 

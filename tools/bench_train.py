@@ -26,6 +26,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--dtype', default='bf16')
     ap.add_argument('--parts', action='store_true', help='also time forward / backward / adam separately')
+    ap.add_argument('--graph', action='store_true', help='replay the step from CUDA graphs')
     args = ap.parse_args()
     rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
     local = int(os.environ.get('LOCAL_RANK', 0))
@@ -45,6 +46,8 @@ def main():
     y = torch.randint(0, args.classes, (args.batch,), generator=g).to(dev)
     net.inp.copy_(x)
     net.labels.copy_(y)
+    if args.graph:
+        net.enable_cuda_graph()
 
     def sync():
         torch.cuda.synchronize()
@@ -88,7 +91,7 @@ def main():
         peak = float(peaks.get('bf16_tflops_sustained', 1380.2))
         tf = 3 * fwd_flops * args.batch / (ms / 1e3) / 1e12      # per GPU
         print(json.dumps(dict(metric='TRAIN images/sec (%s %dpx, batch %d/GPU)' % (args.arch, net.R, args.batch), value=img_s, unit='img/s',
-                              n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms, dtype=args.dtype, data='synthetic',
+                              n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms, dtype=args.dtype, data='synthetic', cuda_graph=bool(args.graph),
                               gflop_per_img=3 * fwd_flops / 1e9, tflops_per_gpu=tf, frac_of_bf16_peak=tf / peak,
                               params=net.n_params, launches=dict(fwd=len(net.fwd), bwd=len(net.bwd)), loss_first=float(losses[0]),
                               loss_last=float(losses[-1]), mem_gb=torch.cuda.max_memory_allocated() / 2 ** 30, **parts)))
