@@ -59,7 +59,15 @@ class B200Model(object):
         # (inception.py:463-465); it is a module attribute, not part of the state_dict.
         self.transform_input = bool(pretrained) and model_name == 'inception_v3'
         if state_dict is None:
-            state_dict = _torchvision_module(model_name, num_o_classes, pretrained).state_dict()
+            try:
+                state_dict = _torchvision_module(model_name, num_o_classes, pretrained).state_dict()
+            except KeyError:
+                raise
+            except Exception as e:
+                if pretrained:
+                    raise RuntimeError('%s: pretrained torchvision weights are not available on this host (%s: %s); '
+                                       'pass --untrain to start from random init' % (model_name, type(e).__name__, e))
+                raise
         self._sd = {k: v.detach().clone() for k, v in state_dict.items()}
         self._plans = {}
 

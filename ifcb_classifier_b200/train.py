@@ -95,7 +95,7 @@ class TrainNet(object):
     """
 
     def __init__(self, arch, state_dict, batch, device='cuda', dtype='bf16', lr=1e-3, betas=(0.9, 0.999), eps=1e-8,
-                 dropout=True, seed=0, R=None, bucket_mb=32, keep_dy=False, window=True):
+                 dropout=True, seed=0, R=None, bucket_mb=32, keep_dy=False, window=True, transform_input=False):
         self.arch, self.batch, self.device = arch, int(batch), torch.device(device)
         if self.device.type != 'cuda':
             raise RuntimeError('TrainNet: a CUDA device is required (there is no CPU path)')
@@ -104,6 +104,8 @@ class TrainNet(object):
         self.dropout, self.seed = bool(dropout), int(seed)
         import os
         self.window = bool(window) and os.environ.get('IFCB_TRAIN_WINDOW', '1') != '0'         # zero borders on activations / gradients so that k > 1 stride-1 convs run the WINDOW scheme
+        # torchvision Inception3.transform_input (set by the factory when pretrained weights are requested, inception.py:95-101)
+        self.transform_input = bool(transform_input) and arch == 'inception_v3'
         self.keep_dy = bool(keep_dy)        # tests: keep d(activation) next to d(conv output) instead of overwriting it
         self.step_count = 0
         self._reducer = None
@@ -225,8 +227,13 @@ class TrainNet(object):
             xd_ = _vd(x)
             stem_geom = dict(kh=kh, kw=kw, stride=stride, pad=pad)
             st, pd_, R_ = stride[0], pad[0], self.R
+            tsc = tsh = None
+            if self.transform_input:
+                from .graph import transform_input_affine
+                ts_, tb_ = transform_input_affine()
+                tsc, tsh = (C.c_float * 3)(*ts_), (C.c_float * 3)(*tb_)
             self.fwd.append(lambda kh=kh, kw=kw: self._call('ifcb_stem_im2col', self.inp.data_ptr(), R_, R_, C.byref(xd_), self.batch, kh, kw,
-                                                            st, pd_, None, None, self.cdtype, self._stream()))
+                                                            st, pd_, tsc, tsh, self.cdtype, self._stream()))
             w1 = torch.zeros((Co, K8, 1, 1))
             w1[:, :kh * kw * 3, 0, 0] = w.permute(0, 2, 3, 1).reshape(Co, kh * kw * 3)      # k = (r*kw + s)*3 + c
             w, Ci, kh, kw, stride, pad = w1, K8, 1, 1, (1, 1), (0, 0)

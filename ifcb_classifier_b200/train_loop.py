@@ -175,7 +175,7 @@ def do_training(args):
         print('pretrained=True: torchvision weights are taken from the local cache (no network on this host)')
     B = args.batch_size
     net = TrainNet(args.MODEL, classifier.model.state_dict(), B, device=dev, dtype=getattr(args, 'train_dtype', 'bf16'), seed=args.seed,
-                   R=args.resize)
+                   R=args.resize, transform_input=classifier.model.transform_input)
     net.enable_cuda_graph()                                       # replay the step's ~10^3 launches from CUDA graphs
     train_loader = ImageBatcher(train_ds, B, dev, args.loaders, rank, world, shuffle=True, seed=args.seed, drop_last=False)
     val_loader = ImageBatcher(val_ds, B, dev, args.loaders, 0, 1, shuffle=False, seed=args.seed)
@@ -196,7 +196,8 @@ def do_training(args):
         agg_train_loss = float(torch.stack(losses).sum()) if losses else 0.0       # one sync per epoch (reference: .item() per step)
         # ---- validation (rank 0's replica; eval mode = the RUN plan with the current weights) ----
         sd = net.state_dict()
-        ev = CompiledNet(args.MODEL, sd, B, in_kind='f32', R=args.resize, device=dev, dtype=getattr(args, 'dtype', 'fp16'))
+        ev = CompiledNet(args.MODEL, sd, B, in_kind='f32', R=args.resize, device=dev, dtype=getattr(args, 'dtype', 'fp16'),
+                         transform_input=classifier.model.transform_input)
         val_loss, outs, ins, srcs = 0.0, [], [], []
         for x, y, paths in val_loader:
             n = int(x.shape[0])

@@ -633,3 +633,30 @@ def test_cuda_graph_step_matches_eager(cuda):
         assert abs(a - b) <= 2e-2 * abs(a), losses
     for a, b in zip(stats['eager'], stats['graph']):              # capture warm-up leaves the running statistics alone
         assert torch.allclose(a, b, rtol=2e-2, atol=1e-3)
+
+
+def test_stem_im2col_matches_unfold(cuda):
+    """Patch matrix of the first conv (incl. torchvision's transform_input affine, inception.py:95-101): channel k =
+    (r*kw + s)*3 + c of the 16-bit rounded, transformed input; zero outside the image and in the K padding."""
+    from ifcb_classifier_b200 import _lib
+    from ifcb_classifier_b200.graph import transform_input_affine
+    from ifcb_classifier_b200.train import _vd
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(4)
+    for (R, kh, st, pd, use_t) in ((37, 3, 2, 0, True), (30, 7, 2, 3, False)):
+        x = torch.rand(3, 3, R, R, generator=g).to(cuda)
+        P = (R + 2 * pd - kh) // st + 1
+        K8 = (kh * kh * 3 + 7) // 8 * 8
+        out, _ = _mk(cuda, 3, P, P, K8, torch.bfloat16, fill=False)
+        ts, tb = transform_input_affine()
+        sc, sh = ((C.c_float * 3)(*ts), (C.c_float * 3)(*tb)) if use_t else (None, None)
+        _lib.check(L.ifcb_stem_im2col(x.data_ptr(), R, R, C.byref(_vd(out)), 3, kh, kh, st, pd, sc, sh, _lib.IFCB_ACT_BF16, _stream()), 'stem_im2col')
+        xt = x
+        if use_t:
+            xt = torch.stack([torch.addcmul(torch.tensor(tb[c], device=cuda), x[:, c], torch.tensor(ts[c], device=cuda)) for c in range(3)], 1)
+        # zero padding applies to the TRANSFORMED input (the module pads inside the conv)
+        u = F.unfold(xt.to(torch.bfloat16).float(), (kh, kh), padding=pd, stride=st)
+        u = u.view(3, 3, kh * kh, P, P).permute(0, 2, 1, 3, 4).reshape(3, kh * kh * 3, P, P)
+        got = _read(out)
+        assert float((got[:, :kh * kh * 3] - u).abs().max()) <= 2.0 ** -8 * float(u.abs().max())
+        assert float(got[:, kh * kh * 3:].abs().max()) == 0.0
