@@ -210,3 +210,82 @@ def test_result_files_for_image_inputs(tmp_path):
     assert sorted(os.path.relpath(q, str(tmp_path / 'out2')) for q in ps) == ['a/res.json', 'b/c/res.json']
     j = json.load(open([q for q in ps if q.endswith('b/c/res.json')][0]))
     assert j['input_images'] == ['y1.png', 'y2.png'] and np.allclose(j['output_scores'], scores[2:])
+
+
+# ---- TRAIN host logic (neuston_data mirrors), CPU only ----
+def _png_tree(root, counts):
+    from PIL import Image
+    for cls, n in counts.items():
+        d = os.path.join(root, cls)
+        os.makedirs(d, exist_ok=True)
+        for i in range(n):
+            Image.fromarray(np.full((5 + i % 3, 7), i, np.uint8), mode='L').save(os.path.join(d, '%s_%03d.png' % (cls, i)))
+        open(os.path.join(d, 'notes.txt'), 'w').close()              # non-image files are ignored
+
+
+def test_neuston_dataset_thresholds_and_split(tmp_path):
+    """NeustonDataset (reference neuston_data.py:20-187): class folders, --class-min / --class-max, seeded T:V split."""
+    import random
+    import argparse
+    from ifcb_classifier_b200 import neuston_data as nd
+    src = str(tmp_path / 'ds')
+    _png_tree(src, dict(big=20, mid=10, tiny=1))
+    full = nd.NeustonDataset(src, minimum_images_per_class=2)
+    assert full.classes == ['big', 'mid'] and full.classes_ignored_from_too_few_samples == [('tiny', 1)]
+    assert full.count_perclass == [20, 10] and len(full) == 30 and full.imgs is full.images
+    random.seed(0)
+    capped = nd.NeustonDataset(src, minimum_images_per_class=2, maximum_images_per_class=12)
+    assert capped.count_perclass == [12, 10] and capped.classes_limited_from_too_many_samples == ['big']
+    a, b = full.split(80, 20, seed=5)
+    assert a.count_perclass == [16, 8] and b.count_perclass == [4, 2] and a.classes == b.classes
+    assert not set(a.images) & set(b.images) and len(a) + len(b) == len(full)
+    a2, _ = full.split(80, 20, seed=5)
+    assert a2.images == a.images                                        # same seed, same split
+    with pytest.raises(AssertionError):
+        full.split(70, 20)
+    img, target, path = full[0]
+    assert img.dtype == np.uint8 and img.ndim == 2 and target == 0 and path.endswith('.png')
+    # get_trainval_datasets: the reference's flag semantics ('x' -> vertical flip, 'y' -> horizontal, '+V' also on validation)
+    args = argparse.Namespace(SRC=src, class_config=None, class_min=2, class_max=None, split='80:20', seed=5, swap=False,
+                              MODEL='inception_v3', img_norm=['0.5', '0.25'], flip='x+V')
+    tr, va = nd.get_trainval_datasets(args)
+    assert args.resize == 299 and tr.transforms['flips'] == ['v'] and va.transforms['flips'] == ['v']
+    assert tr.transforms['img_norm'] == ([0.5] * 3, [0.25] * 3) and len(tr) == 24 and len(va) == 6
+    args.flip, args.MODEL, args.swap = 'xy', 'resnet18', True
+    tr, va = nd.get_trainval_datasets(args)
+    assert args.resize == 224 and tr.transforms['flips'] == ['v', 'h'] and va.transforms['flips'] == [] and len(tr) == 6
+
+
+def test_neuston_dataset_class_config_csv(tmp_path):
+    """--class-config CSV COL (reference neuston_data.py:189-256): 1 keep, 0 drop, other values rename / group."""
+    from ifcb_classifier_b200 import neuston_data as nd
+    src = str(tmp_path / 'ds')
+    _png_tree(src, dict(a=4, b=3, c=5, d=2))
+    cfg = tmp_path / 'cfg.csv'
+    cfg.write_text('class,run1,run2\na,1,1\nb,0,grp\nc,grp,grp\nd,1,0\nmissing,1,1\n')
+    ds = nd.NeustonDataset.from_csv(src, str(cfg), 'run1')
+    assert ds.classes == ['a', 'd', 'grp'] and ds.count_perclass == [4, 2, 5]
+    ds = nd.NeustonDataset.from_csv(src, str(cfg), 'run2', minimum_images_per_class=5)
+    assert ds.classes == ['grp'] and ds.count_perclass == [8] and ds.classes_ignored_from_too_few_samples == [('a', 4)]
+
+
+def test_image_batcher_indices_are_a_distributed_partition():
+    """train_loop.ImageBatcher: shuffled per epoch, padded to a multiple of the world size and strided by rank."""
+    from ifcb_classifier_b200.train_loop import ImageBatcher
+
+    class DS(object):
+        images, targets, transforms = list(range(10)), [0] * 10, None
+
+        def __len__(self):
+            return 10
+
+    parts = []
+    for r in range(4):
+        b = ImageBatcher(DS(), 2, 'cpu', loaders=1, rank=r, world=4, shuffle=True, seed=3)
+        parts.append(b.indices())
+        assert len(b) == 2 and len(parts[-1]) == 3
+    flat = [i for p_ in parts for i in p_]
+    assert sorted(set(flat)) == list(range(10)) and len(flat) == 12            # complete; 2 wrapped-around items
+    b0 = ImageBatcher(DS(), 2, 'cpu', loaders=1, shuffle=True, seed=3)
+    e0 = b0.indices(); b0.epoch = 1
+    assert sorted(e0) == list(range(10)) and b0.indices() != e0                 # reshuffled every epoch
