@@ -50,6 +50,11 @@ class ViewDesc(C.Structure):
                 ('pad_h', C.c_int32), ('pad_w', C.c_int32)]
 
 
+class RepackItem(C.Structure):
+    _fields_ = [('d_master', C.c_void_p), ('d_wfwd', C.c_void_p), ('d_wdgrad', C.c_void_p), ('Cout', C.c_int32), ('taps', C.c_int32),
+                ('Cin', C.c_int32), ('Cin_pad', C.c_int32), ('Cout_padk', C.c_int32), ('reserved', C.c_int32)]
+
+
 class StemDesc(C.Structure):
     _fields_ = [('d_in', C.c_void_p), ('in_kind', C.c_int32),
                 ('batch_cap', C.c_int32), ('H', C.c_int32), ('W', C.c_int32),
@@ -126,6 +131,7 @@ _SIGNATURES = {
                                  C.c_float, C.c_float, C.c_int, C.c_float, C.c_void_p]),
     'ifcb_conv_repack': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
                                    C.c_int, C.c_void_p]),
+    'ifcb_conv_repack_batch': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     'ifcb_stem_repack': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     'ifcb_plan_add_stem': (C.c_int, [C.c_void_p, C.POINTER(StemDesc)]),
     'ifcb_plan_add_pool': (C.c_int, [C.c_void_p, C.POINTER(PoolDesc)]),

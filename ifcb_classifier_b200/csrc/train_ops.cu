@@ -763,6 +763,32 @@ __global__ void __launch_bounds__(256) conv_repack_kernel(const float* __restric
   }
 }
 
+// every conv of a network in ONE launch: blockIdx.y = conv, blockIdx.x strides over its elements
+__global__ void __launch_bounds__(256) conv_repack_batch_kernel(const ifcb_repack_item* __restrict__ items, int fp16) {
+  const ifcb_repack_item it = items[blockIdx.y];
+  const float* __restrict__ w = it.d_master;
+  uint16_t* __restrict__ wf = reinterpret_cast<uint16_t*>(it.d_wfwd);
+  uint16_t* __restrict__ wd = reinterpret_cast<uint16_t*>(it.d_wdgrad);
+  const int Cin = it.Cin, taps = it.taps;
+  const long long total = (long long)it.Cout * taps * Cin;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int ci = (int)(i % Cin);
+    const long long r = i / Cin;
+    const int t = (int)(r % taps), co = (int)(r / taps);
+    const float v = w[i];
+    uint16_t h;
+    if (fp16) {
+      const __half hv = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
+      h = *reinterpret_cast<const uint16_t*>(&hv);
+    } else {
+      const __nv_bfloat16 bv = __float2bfloat16_rn(v);
+      h = *reinterpret_cast<const uint16_t*>(&bv);
+    }
+    if (wf) wf[(long long)co * taps * it.Cin_pad + (long long)t * it.Cin_pad + ci] = h;
+    if (wd) wd[(long long)ci * taps * it.Cout_padk + (long long)(taps - 1 - t) * it.Cout_padk + co] = h;
+  }
+}
+
 // stem master weights [Cout, taps, Cin8] fp32 -> the fp32 stem kernel's [taps*3, Cout]
 __global__ void stem_repack_kernel(const float* __restrict__ w, int Cout, int taps, int cin8, float* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1041,6 +1067,13 @@ extern "C" int ifcb_conv_repack(const float* d_master, int Cout, int taps, int C
   const long long total = (long long)Cout * taps * Cin;
   conv_repack_kernel<<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(d_master, Cout, taps, Cin, reinterpret_cast<uint16_t*>(d_wfwd), Cin_pad,
                                                                         reinterpret_cast<uint16_t*>(d_wdgrad), Cout_padk, dtype);
+  IFCB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int ifcb_conv_repack_batch(const ifcb_repack_item* d_items, int n_items, int dtype, void* stream) {
+  IFCB_ARG_CHECK(d_items && n_items > 0 && n_items <= 65535 && DT_OK(dtype), "conv_repack_batch: bad argument");
+  conv_repack_batch_kernel<<<dim3(32, n_items), 256, 0, STREAM(stream)>>>(d_items, dtype);
   IFCB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

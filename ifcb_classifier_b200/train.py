@@ -126,8 +126,9 @@ class TrainNet(object):
         self.fwd = []                   # closures
         self._nbt_keys = []             # BatchNorm num_batches_tracked buffers (host counters)
         self._graph = None
+        self._repack_table = None
         self.bwd = []                   # closures, already in execution order
-        self.repacks = []               # closures refreshing the 16-bit operands from the arena
+        self.repacks = []               # (param, Co, taps, Ci, forward operand, Cin_pad, data-gradient operand or None, Cout_padk)
         self.keep = []
         self._grad_t = {}               # id(activation tensor) -> gradient tensor
         self._grad_pad = {}             # id(activation tensor) -> zero border of its gradient tensor
@@ -448,8 +449,7 @@ class TrainNet(object):
         wf = rec['wf']
         assert wf.shape[1] == kh * kw * geo_f['Cin_pad'], wf.shape
         if rec['stem'] is not None:                                  # network input: no data gradient
-            self.repacks.append(lambda: self._call('ifcb_conv_repack', pw.wptr, Co, kh * kw, Ci, wf.data_ptr(), geo_f['Cin_pad'],
-                                                   None, 0, dt, self._stream()))
+            self.repacks.append((pw, Co, kh * kw, Ci, wf, geo_f['Cin_pad'], None, 0))
             return pw.off
         # data gradient: stride-1 conv of (dilated) dz with the flipped, transposed filter
         dx = self.grad_of(x)
@@ -457,15 +457,22 @@ class TrainNet(object):
         dg = build_dgrad(self.bp, dz, dx, Co, Ci, kh, kw, stride, pad, acc, name='dgrad.' + rec['name'])
         self.bwd.extend(dg['run'])
         wdg = dg['weight']
-        self.repacks.append(lambda: self._call('ifcb_conv_repack', pw.wptr, Co, kh * kw, Ci, wf.data_ptr(), geo_f['Cin_pad'],
-                                               wdg.data_ptr(), dg['Cin_pad'], dt, self._stream()))
+        self.repacks.append((pw, Co, kh * kw, Ci, wf, geo_f['Cin_pad'], wdg, dg['Cin_pad']))
         return pw.off
 
     # ---- execution ---------------------------------------------------------------------------------
     def repack(self):
-        """Refresh every 16-bit tensor-core operand (forward + data-gradient) from the fp32 arena."""
-        for r in self.repacks:
-            r()
+        """Refresh every 16-bit tensor-core operand (forward + data-gradient) from the fp32 arena: one launch over a
+        device-resident table of (master slice, operands, geometry) records."""
+        if self._repack_table is None:
+            import numpy as np
+            items = (_lib.RepackItem * len(self.repacks))()
+            for it, (pw, Co, taps, Ci, wf, cin_pad, wdg, cout_padk) in zip(items, self.repacks):
+                it.d_master, it.d_wfwd, it.d_wdgrad = pw.wptr, wf.data_ptr(), (wdg.data_ptr() if wdg is not None else None)
+                it.Cout, it.taps, it.Cin, it.Cin_pad, it.Cout_padk = Co, taps, Ci, cin_pad, cout_padk
+            raw = np.frombuffer(bytes(items), dtype=np.uint8).copy()
+            self._repack_table = torch.from_numpy(raw).to(self.device)
+        self._call('ifcb_conv_repack_batch', self._repack_table.data_ptr(), len(self.repacks), self.cdtype, self._stream())
 
     def _count_batch(self):
         for k in self._nbt_keys:

@@ -288,6 +288,15 @@ int ifcb_adam_step(float* d_param, const float* d_grad, float* d_m, float* d_v, 
  * Padding entries are never written (allocate zeroed). */
 int ifcb_conv_repack(const float* d_master, int Cout, int taps, int Cin, void* d_wfwd, int Cin_pad, void* d_wdgrad,
                      int Cout_padk, int dtype, void* stream);
+/* The same for every conv of a network in one launch: d_items = DEVICE array of n_items records (arguments as
+ * ifcb_conv_repack; NULL operands are skipped). */
+typedef struct {
+  const float* d_master;
+  void* d_wfwd;
+  void* d_wdgrad;
+  int32_t Cout, taps, Cin, Cin_pad, Cout_padk, reserved;
+} ifcb_repack_item;
+int ifcb_conv_repack_batch(const ifcb_repack_item* d_items, int n_items, int dtype, void* stream);
 /* stem master weights [Cout, taps, Cin8] -> the fp32 stem kernel's d_weight [taps*3, Cout] */
 int ifcb_stem_repack(const float* d_master, int Cout, int taps, int Cin8, float* d_wstem, void* stream);
 
