@@ -122,13 +122,33 @@ __device__ __forceinline__ void cvt8(const uint4& v, int fp16, float* f) {
   }
 }
 
+// What the LAST block of a reduction does with the complete float64 sums (saves one tiny launch per layer and pass):
+//   MODE 0 (forward): mean / invstd, running-stat update as torch.nn.BatchNorm2d in train mode (momentum, UNBIASED
+//                     variance into running_var)
+//   MODE 1 (backward): per-channel coefficients of the elementwise pass, dz = A * dy' + Bz * z + D with
+//                     A = gamma*invstd, Bz = -A*invstd*s2/M, D = A*(mean*invstd*s2/M - s1/M); dgamma += s2, dbeta += s1
+// and clears the accumulators for the next user.
+struct FinalizeArgs {
+  double count;            // pixels per channel
+  float eps, momentum;
+  float* mean_out;         // MODE 0 outputs
+  float* invstd_out;
+  float* run_mean;
+  float* run_var;
+  float* coef;             // MODE 1 outputs: [A | Bz | D], 3*C floats
+  float* dgamma;
+  float* dbeta;
+  unsigned int* counter;   // blocks finished so far (zero on entry, zero again on exit)
+};
+
 // MODE 0: sums of z and z*z.   MODE 1: sums of dy' and dy' * (z - mean) (scaled by invstd at the end).
 template <int MODE, int MASK>
 __global__ void __launch_bounds__(256, 2) channel_reduce_kernel(DV z, DV dy, DV a, const float* __restrict__ mean,
                                                                 const float* __restrict__ invstd, const float* __restrict__ gamma,
                                                                 const float* __restrict__ beta, long long M, int rows, int fp16,
-                                                                double* __restrict__ acc) {
+                                                                double* __restrict__ acc, const FinalizeArgs fin) {
   __shared__ float red[256 * 16];
+  __shared__ int s_last;
   const int c8n = z.C >> 3;
   const int tid = threadIdx.x;
   const int row = tid / c8n, c8 = tid - row * c8n;
@@ -209,26 +229,40 @@ __global__ void __launch_bounds__(256, 2) channel_reduce_kernel(DV z, DV dy, DV 
     for (int r = 0; r < rows; ++r) s += red[(r * c8n + cc8) * 16 + which * 8 + j];
     atomicAdd(acc + t, (double)s);
   }
-}
-
-// mean / invstd from the float64 sums, running-stat update as torch.nn.BatchNorm2d in train
-// mode (momentum 0.1, UNBIASED variance into running_var); clears the accumulators.
-__global__ void bn_finalize_kernel(double* __restrict__ acc, int C, double M, float eps, float momentum, float* __restrict__ mean,
-                                   float* __restrict__ invstd, float* __restrict__ run_mean, float* __restrict__ run_var) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  const double mu = acc[c] / M;
-  double var = acc[C + c] / M - mu * mu;
-  if (var < 0.0) var = 0.0;
-  mean[c] = (float)mu;
-  invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
-  if (run_mean) run_mean[c] = (1.f - momentum) * run_mean[c] + momentum * (float)mu;
-  if (run_var) {
-    const double unb = M > 1.0 ? var * M / (M - 1.0) : var;
-    run_var[c] = (1.f - momentum) * run_var[c] + momentum * (float)unb;
+  // ---- last block: finalize (threadFenceReduction pattern) ----
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(fin.counter, 1u) == gridDim.x - 1) ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  const int C = z.C;
+  for (int c = tid; c < C; c += 256) {
+    const double s1 = __ldcg(acc + c), s2 = __ldcg(acc + C + c);
+    if (MODE == 0) {
+      const double mu = s1 / fin.count;
+      double var = s2 / fin.count - mu * mu;
+      if (var < 0.0) var = 0.0;
+      fin.mean_out[c] = (float)mu;
+      fin.invstd_out[c] = (float)(1.0 / sqrt(var + (double)fin.eps));
+      if (fin.run_mean) fin.run_mean[c] = (1.f - fin.momentum) * fin.run_mean[c] + fin.momentum * (float)mu;
+      if (fin.run_var) {
+        const double unb = fin.count > 1.0 ? var * fin.count / (fin.count - 1.0) : var;
+        fin.run_var[c] = (1.f - fin.momentum) * fin.run_var[c] + fin.momentum * (float)unb;
+      }
+    } else {
+      const double inv_m = 1.0 / fin.count;
+      const double is = (double)invstd[c], mu = (double)mean[c];
+      const double A = (double)gamma[c] * is;
+      fin.coef[c] = (float)A;
+      fin.coef[C + c] = (float)(-A * is * s2 * inv_m);
+      fin.coef[2 * C + c] = (float)(A * (mu * is * s2 * inv_m - s1 * inv_m));
+      if (fin.dbeta) fin.dbeta[c] += (float)s1;
+      if (fin.dgamma) fin.dgamma[c] += (float)s2;
+    }
+    acc[c] = 0.0;
+    acc[C + c] = 0.0;
   }
-  acc[c] = 0.0;
-  acc[C + c] = 0.0;
+  if (tid == 0) *fin.counter = 0u;
 }
 
 // a = act(bn_y(z) (+ residual)).  Block = rows x (C/8) threads: a thread keeps the parameters of its 8
@@ -269,26 +303,6 @@ __global__ void __launch_bounds__(256, 3) bn_apply_kernel(DV z, DV out, DV res, 
       }
     }
   }
-}
-
-// per-channel coefficients of the backward elementwise pass from the float64 sums:
-//   dz = A * dy' + Bz * z + D,  A = gamma*invstd, Bz = -A*invstd*s2/M, D = A*(mean*invstd*s2/M - s1/M)
-// coef = [A | Bz | D] (3*C floats); also dgamma += s2, dbeta += s1.
-__global__ void bn_bwd_coef_kernel(double* __restrict__ acc, int C, double inv_m, const float* __restrict__ mean,
-                                   const float* __restrict__ invstd, const float* __restrict__ gamma, float* __restrict__ coef,
-                                   float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  const double s1 = acc[c], s2 = acc[C + c];
-  const double is = (double)invstd[c], mu = (double)mean[c];
-  const double A = (double)gamma[c] * is;
-  coef[c] = (float)A;
-  coef[C + c] = (float)(-A * is * s2 * inv_m);
-  coef[2 * C + c] = (float)(A * (mu * is * s2 * inv_m - s1 * inv_m));
-  if (dbeta) dbeta[c] += (float)s1;
-  if (dgamma) dgamma[c] += (float)s2;
-  acc[c] = 0.0;            // leave the accumulators zero for the next user (no memset launch per layer)
-  acc[C + c] = 0.0;
 }
 
 // dz = A * dy' + Bz * z + D with dy' = relu-masked dy; optionally routes dy' to the residual branch
@@ -844,9 +858,16 @@ extern "C" int ifcb_bn_stats(const ifcb_view* z, int batch, int dtype, float eps
   const int grid = reduce_grid(M, rows, z->C);
   DV zz = dv(z);
   IFCB_ARG_CHECK(M < (1ll << 31) / (z->C / 8), "bn_stats: tensor too large for 32-bit indexing");
-  channel_reduce_kernel<0, kMaskNone><<<grid, 256, 0, STREAM(stream)>>>(zz, zz, zz, nullptr, nullptr, nullptr, nullptr, M, rows, dtype, d_acc);
-  bn_finalize_kernel<<<(z->C + 127) / 128, 128, 0, STREAM(stream)>>>(d_acc, z->C, (double)M, eps, momentum, d_mean, d_invstd,
-                                                                      d_running_mean, d_running_var);
+  FinalizeArgs fin{};
+  fin.count = (double)M;
+  fin.eps = eps;
+  fin.momentum = momentum;
+  fin.mean_out = d_mean;
+  fin.invstd_out = d_invstd;
+  fin.run_mean = d_running_mean;
+  fin.run_var = d_running_var;
+  fin.counter = reinterpret_cast<unsigned int*>(d_acc + 8191);
+  channel_reduce_kernel<0, kMaskNone><<<grid, 256, 0, STREAM(stream)>>>(zz, zz, zz, nullptr, nullptr, nullptr, nullptr, M, rows, dtype, d_acc, fin);
   IFCB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -900,12 +921,17 @@ extern "C" int ifcb_bn_backward(const ifcb_view* dy, const ifcb_view* a, const i
   cudaStream_t st = STREAM(stream);
   DV av = a ? dv(a) : zz, dzv = dv(dz), drv = dres ? dv(dres) : zz;
   const int res_mode = dres ? (dres_accumulate ? 2 : 1) : 0;
-#define IFCB_REDUCE1(MK) channel_reduce_kernel<1, MK><<<reduce_grid(M, rows, z->C), 256, 0, st>>>(zz, dyy, av, d_mean, d_invstd, d_gamma, d_beta, M, rows, dtype, d_acc)
+  FinalizeArgs fin{};
+  fin.count = (double)M;
+  fin.coef = coef;
+  fin.dgamma = d_dgamma;
+  fin.dbeta = d_dbeta;
+  fin.counter = reinterpret_cast<unsigned int*>(d_acc + 8191);
+#define IFCB_REDUCE1(MK) channel_reduce_kernel<1, MK><<<reduce_grid(M, rows, z->C), 256, 0, st>>>(zz, dyy, av, d_mean, d_invstd, d_gamma, d_beta, M, rows, dtype, d_acc, fin)
   if (mask_mode == kMaskFromZ) IFCB_REDUCE1(kMaskFromZ);
   else if (mask_mode == kMaskFromA) IFCB_REDUCE1(kMaskFromA);
   else IFCB_REDUCE1(kMaskNone);
 #undef IFCB_REDUCE1
-  bn_bwd_coef_kernel<<<(z->C + 127) / 128, 128, 0, st>>>(d_acc, z->C, 1.0 / (double)M, d_mean, d_invstd, d_gamma, coef, d_dgamma, d_dbeta);
 #define IFCB_BWD_APPLY(MK, RS) \
   bn_bwd_apply_kernel<MK, RS><<<grid, 256, 0, st>>>(dyy, av, zz, dzv, drv, d_mean, d_invstd, d_gamma, d_beta, coef, M, rows, dtype)
   if (mask_mode == kMaskFromZ) IFCB_BWD_APPLY(kMaskFromZ, 0);               // (a residual always comes with kMaskFromA / kMaskNone)

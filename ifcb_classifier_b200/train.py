@@ -18,6 +18,7 @@ Activations are NHWC 16-bit (bf16 by default for training); for each conv+BN uni
 output ``z`` and the activation ``a`` are kept for the backward pass.
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -102,8 +103,8 @@ class TrainNet(object):
         self.R = R or (299 if arch == 'inception_v3' else 224)
         self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
         self.dropout, self.seed = bool(dropout), int(seed)
-        import os
-        self.window = bool(window) and os.environ.get('IFCB_TRAIN_WINDOW', '1') != '0'         # zero borders on activations / gradients so that k > 1 stride-1 convs run the WINDOW scheme
+        # zero borders on activations / gradients so that k > 1 stride-1 convs run the WINDOW scheme (IFCB_TRAIN_WINDOW=0: A/B switch)
+        self.window = bool(window) and os.environ.get('IFCB_TRAIN_WINDOW', '1') != '0'
         # torchvision Inception3.transform_input (set by the factory when pretrained weights are requested, inception.py:95-101)
         self.transform_input = bool(transform_input) and arch == 'inception_v3'
         self.keep_dy = bool(keep_dy)        # tests: keep d(activation) next to d(conv output) instead of overwriting it
@@ -135,7 +136,7 @@ class TrainNet(object):
         self.inp = torch.zeros((batch, 3, self.R, self.R), dtype=torch.float32, device=self.device)
         self.labels = torch.zeros((batch,), dtype=torch.int64, device=self.device)
         self.loss = torch.zeros((2,), dtype=torch.float32, device=self.device)     # [main + aux (weighted), unused]
-        self.acc = torch.zeros((4 * 2048,), dtype=torch.float64, device=self.device)   # 2C float64 sums + 3C float32 coefficients
+        self.acc = torch.zeros((8192,), dtype=torch.float64, device=self.device)      # 64 KB BN scratch: float64 sums [0,4096), coefficient floats behind
         if arch == 'inception_v3':
             _build_inception_train(self, sd)
         elif arch in RESNET_CFG:

@@ -229,7 +229,8 @@ int ifcb_bn_apply(const ifcb_view* z, const ifcb_view* out, const ifcb_view* res
  *   d_dgamma[C] += sum(dy'*xhat), d_dbeta[C] += sum(dy')
  *   dres (optional, the residual branch's gradient) = or += dy'
  * dz may alias dy.  d_acc: the 64 KB scratch shared with ifcb_bn_stats: float64 [0, 4096) are per-channel
- * accumulators (2*C used; zero on entry, zero again on exit), the 3*C coefficient floats go behind them. */
+ * accumulators (2*C used; zero on entry, zero again on exit), the 3*C coefficient floats go behind them, the last
+ * 8 bytes hold a block counter (zero on entry and exit): the last block of each reduction finalises in place. */
 int ifcb_bn_backward(const ifcb_view* dy, const ifcb_view* a, const ifcb_view* z, const ifcb_view* dz,
                      const ifcb_view* dres, int dres_accumulate, int relu, int batch, int dtype,
                      const float* d_mean, const float* d_invstd, const float* d_gamma, const float* d_beta,
