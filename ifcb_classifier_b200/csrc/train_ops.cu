@@ -1099,7 +1099,7 @@ extern "C" int ifcb_conv_repack(const float* d_master, int Cout, int taps, int C
 
 extern "C" int ifcb_conv_repack_batch(const ifcb_repack_item* d_items, int n_items, int dtype, void* stream) {
   IFCB_ARG_CHECK(d_items && n_items > 0 && n_items <= 65535 && DT_OK(dtype), "conv_repack_batch: bad argument");
-  conv_repack_batch_kernel<<<dim3(32, n_items), 256, 0, STREAM(stream)>>>(d_items, dtype);
+  conv_repack_batch_kernel<<<dim3(sm_count(), n_items), 256, 0, STREAM(stream)>>>(d_items, dtype);   // the largest convs (2.4 M weights) need the whole GPU; blocks of small ones exit at once
   IFCB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
