@@ -90,6 +90,8 @@ _SIGNATURES = {
     'ifcb_abi_version': (C.c_int, []),
     'ifcb_last_error': (C.c_char_p, []),
     'ifcb_sm_count': (C.c_int, []),
+    'ifcb_parse_adc': (C.c_int64, [C.c_char_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p]),
     'ifcb_preprocess': (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_int, C.c_int, C.c_int, C.c_int,
                                   C.POINTER(C.c_float), C.POINTER(C.c_float),

@@ -59,24 +59,22 @@ class Pid(object):
 
 def parse_adc(path, schema=SCHEMA_VERSION_2):
     """``.adc`` CSV -> (targets int32[n], offsets int64[n], heights int32[n], widths int32[n]);
-    rows with zero area are dropped, target = 1-based row number."""
+    rows with zero area are dropped, target = 1-based row number.  Parsed by the library's C++
+    one-pass parser (``ifcb_parse_adc``; the call releases the GIL, so ingest threads overlap)."""
+    from . import _lib
     cw, ch, cb = _ADC_COLS[schema]
-    if os.path.getsize(path) == 0:
-        z = np.zeros(0, np.int64)
-        return z.astype(np.int32), z, z.astype(np.int32), z.astype(np.int32)
-    need = max(cw, ch, cb)
-    rows = []
     with open(path, 'rb') as f:
-        for line in f:
-            parts = line.split(b',')
-            if len(parts) <= need:
-                rows.append((0, 0, 0))
-                continue
-            rows.append((int(float(parts[cw])), int(float(parts[ch])), int(float(parts[cb]))))
-    a = np.asarray(rows, dtype=np.int64).reshape(-1, 3)
-    keep = (a[:, 0] * a[:, 1]) > 0
-    targets = (np.nonzero(keep)[0] + 1).astype(np.int32)
-    return targets, a[keep, 2].copy(), a[keep, 1].astype(np.int32), a[keep, 0].astype(np.int32)
+        buf = f.read()
+    cap = buf.count(b'\n') + 1
+    targets = np.empty(cap, np.int32)
+    offsets = np.empty(cap, np.int64)
+    heights = np.empty(cap, np.int32)
+    widths = np.empty(cap, np.int32)
+    n = _lib.lib().ifcb_parse_adc(buf, len(buf), cw, ch, cb, cap, targets.ctypes.data, offsets.ctypes.data, heights.ctypes.data,
+                                  widths.ctypes.data)
+    if n < 0:
+        _lib.check(-1, 'parse_adc(%s)' % path)
+    return targets[:n].copy(), offsets[:n].copy(), heights[:n].copy(), widths[:n].copy()
 
 
 class RawBin(object):

@@ -37,6 +37,15 @@ const char* ifcb_last_error(void);
 /* Number of SMs of the current device (148 on B200); <0 on error. */
 int ifcb_sm_count(void);
 
+/* Host-side .adc parser (no GPU work): the ROI table of a bin from its .adc file image -- what pyifcb's
+ * bin.images / bin.schema expose upstream (reference neuston_data.py:446-454; pandas CSV parse there).
+ *   buf/len      the file contents (headerless CSV, one row per trigger)
+ *   col_*        0-based column of ROI_WIDTH, ROI_HEIGHT, START_BYTE (schema v2: 15, 16, 17; v1: 11, 12, 13)
+ *   outputs      host arrays with room for max_rows entries; rows with zero area are dropped; targets are
+ *                1-based row numbers.  Returns the number of ROIs kept, or -1 (ifcb_last_error). */
+int64_t ifcb_parse_adc(const char* buf, int64_t len, int col_w, int col_h, int col_b, int64_t max_rows,
+                       int32_t* targets, int64_t* offsets, int32_t* heights, int32_t* widths);
+
 /* ------------------------------------------------------------------------- *
  * K1  fused ROI preprocess.
  * Replaces IfcbBinDataset.__getitem__ (neuston_data.py:456-464):

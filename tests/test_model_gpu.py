@@ -128,3 +128,42 @@ def test_plain_cnn_parity(cuda, arch):
     dmax = float((ref - got).abs().max())
     print('%s fixture C: top-1 agreement %.4f, max|dscore| %.2e' % (arch, agree, dmax))
     assert agree >= 0.995 and dmax <= 1e-2, (agree, dmax)
+
+
+def test_run_cli_pipelines_bins_and_isolates_failures(cuda, tmp_path, capsys):
+    """neuston_net RUN over a directory (reference neuston_net.py:233-278): bins are ingested ahead of the GPU and result
+    files written behind it; an empty bin and a corrupt bin are reported, not fatal; finished bins are skipped on re-run."""
+    import argparse
+    import json
+    import os
+    from oracle import synth_bins
+    from ifcb_classifier_b200 import neuston_net
+    from ifcb_classifier_b200.neuston_models import NeustonModel
+    torch.manual_seed(0)
+    hp = argparse.Namespace(MODEL='resnet18', classes=['c%d' % i for i in range(7)], pretrained=False, resize=224, img_norm=None,
+                            model_id='m7', seed=1)
+    ckpt = str(tmp_path / 'm7.ptl')
+    NeustonModel(hp).save_checkpoint(ckpt)
+    bins = str(tmp_path / 'bins')
+    sizes = [40, 3, 25, 17]
+    for i, n in enumerate(sizes):
+        synth_bins.write_bin(bins, synth_bins.make_bin(i, n_rois=n))
+    empty = synth_bins.make_bin(4, n_rois=2)
+    base = synth_bins.write_bin(bins, empty)
+    open(base + '.adc', 'w').close()                                   # no triggers at all
+    bad = synth_bins.write_bin(bins, synth_bins.make_bin(5, n_rois=4))
+    with open(bad + '.roi', 'r+b') as f:
+        f.truncate(10)                                                 # ADC table points outside the .roi file
+    out = str(tmp_path / 'out')
+    argv = ['--batch', '16', 'RUN', bins, ckpt, 'R1', '--outdir', out, '--outfile', '{BIN_ID}_class.json', '--outfile', 'mat/{BIN_ID}.mat']
+    assert neuston_net.main(argv) == 0
+    txt = capsys.readouterr().out
+    assert 'RUN IS DONE' in txt and '4 bins, %d ROIs' % sum(sizes) in txt
+    assert synth_bins.bin_lid(4) in txt and 'Bin is Empty' in txt and synth_bins.bin_lid(5) in txt and 'ValueError' in txt
+    for i, n in enumerate(sizes):
+        j = json.load(open(os.path.join(out, synth_bins.bin_lid(i) + '_class.json')))
+        assert len(j['roi_numbers']) == n and j['model_id'] == 'm7' and len(j['output_scores'][0]) == 7
+        assert os.path.isfile(os.path.join(out, 'mat', synth_bins.bin_lid(i) + '.mat'))
+    assert neuston_net.main(argv) == 0                                 # second run: everything that succeeded is skipped
+    txt = capsys.readouterr().out
+    assert txt.count('already exist - skipping this bin') == 4 and '0 bins, 0 ROIs' in txt
