@@ -7,6 +7,8 @@ neuston_models.py:152-157 -> neuston_callbacks.py:161-162):
 Only the packed bytes cross PCIe (about 150x less than the reference's float
 tensors); everything else stays in HBM.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -16,10 +18,12 @@ from .graph import CompiledNet
 
 class BinClassifier(object):
     def __init__(self, arch, state_dict, n_classes=None, img_norm=None, transform_input=False,
-                 device='cuda', batch_cap=512, dtype='fp16', max_rois=4096, max_roi_bytes=64 << 20):
+                 device='cuda', batch_cap=512, dtype='fp16', max_rois=4096, max_roi_bytes=64 << 20, cuda_graph=True):
         self.device = torch.device(device)
         self.net = CompiledNet(arch, state_dict, batch_cap, in_kind='u8', img_norm=img_norm,
                                transform_input=transform_input, device=self.device, dtype=dtype)
+        if cuda_graph and os.environ.get('IFCB_RUN_GRAPH', '1') != '0':
+            self.net.enable_cuda_graph()            # full batches replay the plan's launches from one CUDA graph
         self.R, self.batch_cap, self.n_classes = self.net.R, batch_cap, self.net.n_classes
         self._alloc(max_rois, max_roi_bytes)
         self.launches_last = 0

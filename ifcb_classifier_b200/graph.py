@@ -750,8 +750,22 @@ class CompiledNet(object):
         self.flops_per_image = pb.flops_per_image
         self.num_launches = _lib.lib().ifcb_plan_num_launches(pb.handle)
 
+    def enable_cuda_graph(self):
+        """Captures the full-batch forward (every launch of the plan) into a CUDA graph; ``forward(batch_cap)`` then
+        replays it.  All pointers of a plan are fixed at construction, so the graph stays valid."""
+        for _ in range(2):
+            self.pb.run(self.batch_cap)
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.pb.run(self.batch_cap)
+        self._graph = g
+
     def forward(self, n):
         """Runs the plan on the first ``n`` images of ``self.inp`` (current stream).
         Returns views (scores, logits, top1, top1_score) of the plan's output buffers."""
-        self.pb.run(n)
+        if n == self.batch_cap and getattr(self, '_graph', None) is not None:
+            self._graph.replay()
+        else:
+            self.pb.run(n)
         return self.pb.scores[:n], self.pb.logits[:n], self.pb.top1[:n], self.pb.top1_score[:n]
