@@ -265,7 +265,10 @@ def _run_images(args, classifier, filter_mode, keywords, rank, world, local_rank
     scores = np.concatenate(scores)
     outs = []
     for of in args.outfile:
-        of_r = of if world == 1 else of.replace('.', '.rank%d.' % rank, 1) if '{INPUT_SUBDIRS}' not in of else of
+        of_r = of
+        if world > 1:                                              # every rank classified its own stride of the list
+            stem, ext = os.path.splitext(of)
+            of_r = '%s.rank%d%s' % (stem, rank, ext)
         outs.append(results.save_run_results(paths, scores, hp.classes, args.cmd_timestamp, args.outdir, of_r, getattr(hp, 'model_id', None),
                                              args.SRC))
     if rank == 0:
