@@ -309,7 +309,7 @@ extern "C" int ifcb_plan_add_conv(ifcb_plan* plan, const ifcb_conv_desc* d) {
 extern "C" int ifcb_plan_add_stem(ifcb_plan* plan, const ifcb_stem_desc* d) {
   IFCB_ARG_CHECK(plan && d, "ifcb_plan_add_stem: null argument");
   IFCB_ARG_CHECK(d->d_in && d->d_scale && d->d_shift && d->d_out, "stem: null tensor pointer");
-  IFCB_ARG_CHECK(d->Cout == 32 || d->Cout == 64, "stem: Cout=%d unsupported (32 or 64)", d->Cout);
+  IFCB_ARG_CHECK(d->Cout == 32 || d->Cout == 64 || d->Cout == 96, "stem: Cout=%d unsupported (32, 64 or 96)", d->Cout);
   IFCB_ARG_CHECK(d->in_kind == IFCB_STEM_IN_U8_GRAY || d->in_kind == IFCB_STEM_IN_F32_NCHW, "stem: bad in_kind");
   IFCB_ARG_CHECK(d->in_kind != IFCB_STEM_IN_U8_GRAY || (d->d_wgray && (d->pad == 0 || d->d_wconst)),
                  "stem: u8 input needs d_wgray (and d_wconst when pad > 0)");

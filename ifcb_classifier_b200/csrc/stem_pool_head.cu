@@ -532,8 +532,8 @@ int launch_stem(const StemLayer& L, int batch, cudaStream_t stream) {
   if (total == 0) return 0;
   const int taps = d.kh * d.kw;
   const unsigned grid = (unsigned)((total + 127) / 128);
-  if (d.Cout != 32 && d.Cout != 64) {
-    set_error("stem: Cout=%d unsupported (32 or 64)", d.Cout);
+  if (d.Cout != 32 && d.Cout != 64 && d.Cout != 96) {
+    set_error("stem: Cout=%d unsupported (32, 64 or 96)", d.Cout);
     return -1;
   }
   if (d.in_kind == IFCB_STEM_IN_U8_GRAY && d.kh == 3 && d.kw == 3 && d.pad == 0 && (d.stride == 1 || d.stride == 2) && d.Cout == 32 &&
@@ -556,8 +556,10 @@ int launch_stem(const StemLayer& L, int batch, cudaStream_t stream) {
   } while (0)
     if (d.Cout == 32) {
       if (haspad) IFCB_GRAY_LAUNCH(32, true); else IFCB_GRAY_LAUNCH(32, false);
-    } else {
+    } else if (d.Cout == 64) {
       if (haspad) IFCB_GRAY_LAUNCH(64, true); else IFCB_GRAY_LAUNCH(64, false);
+    } else {                      // densenet161
+      if (haspad) IFCB_GRAY_LAUNCH(96, true); else IFCB_GRAY_LAUNCH(96, false);
     }
 #undef IFCB_GRAY_LAUNCH
   } else {
@@ -569,7 +571,7 @@ int launch_stem(const StemLayer& L, int batch, cudaStream_t stream) {
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, smem));           \
     stem_kernel<CO, false><<<grid, 128, smem, stream>>>(d, nullptr, L.P, L.Q, total);                     \
   } while (0)
-    if (d.Cout == 32) IFCB_STEM_LAUNCH(32); else IFCB_STEM_LAUNCH(64);
+    if (d.Cout == 32) IFCB_STEM_LAUNCH(32); else if (d.Cout == 64) IFCB_STEM_LAUNCH(64); else IFCB_STEM_LAUNCH(96);
 #undef IFCB_STEM_LAUNCH
   }
   IFCB_CUDA_CHECK(cudaGetLastError());

@@ -651,8 +651,7 @@ def build_densenet(pb, sd, inp, in_kind, R, affine=None):
     eps = 1e-5
     sz = lambda h, k, s, p: (h + 2 * p - k) // s + 1
     n_init = int(sd['features.conv0.weight'].shape[0])
-    if n_init not in (32, 64):
-        raise NotImplementedError('densenet with %d stem channels (densenet161) has no B200 plan yet' % n_init)
+    assert n_init in (32, 64, 96), n_init
     blocks = []
     b = 1
     while ('features.denseblock%d.denselayer1.conv1.weight' % b) in sd:
@@ -705,7 +704,7 @@ def build_densenet(pb, sd, inp, in_kind, R, affine=None):
     return pb.head(t, sd['classifier.weight'], sd['classifier.bias'])
 
 
-DENSE_ARCHS = ('densenet121', 'densenet169', 'densenet201')
+DENSE_ARCHS = ('densenet121', 'densenet161', 'densenet169', 'densenet201')
 
 class CompiledNet(object):
     """A model compiled for a fixed batch capacity and input kind.

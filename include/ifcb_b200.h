@@ -329,7 +329,7 @@ typedef struct {
   int32_t in_kind;
   int32_t batch_cap, H, W;
   int32_t kh, kw, stride, pad;
-  int32_t Cout;             /* 32 or 64 */
+  int32_t Cout;             /* 32, 64 or 96 */
   const float* d_weight;
   const float* d_scale;
   const float* d_shift;

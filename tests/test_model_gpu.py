@@ -112,7 +112,7 @@ def test_partial_batches_and_f32_input(cuda):
     assert float((got - s.cpu()).abs().max()) <= 1e-3
 
 
-@pytest.mark.parametrize('arch', ['alexnet', 'vgg11_bn', 'vgg16', 'squeezenet', 'densenet121'])
+@pytest.mark.parametrize('arch', ['alexnet', 'vgg11_bn', 'vgg16', 'squeezenet', 'densenet121', 'densenet161'])
 def test_plain_cnn_parity(cuda, arch):
     """The other model families get_namebrand_model names (reference neuston_models.py:27-42) on the same kernels: convs
     with bias, 2x2 / 3x3 / ceil-mode max pools, VGG / AlexNet classifiers run as convolutions, SqueezeNet's conv
