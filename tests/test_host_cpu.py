@@ -289,3 +289,35 @@ def test_image_batcher_indices_are_a_distributed_partition():
     b0 = ImageBatcher(DS(), 2, 'cpu', loaders=1, shuffle=True, seed=3)
     e0 = b0.indices(); b0.epoch = 1
     assert sorted(e0) == list(range(10)) and b0.indices() != e0                 # reshuffled every epoch
+
+
+def test_validation_results_files(tmp_path):
+    """train_loop.save_validation_results (reference SaveValidationResults, neuston_callbacks.py:20-156): chosen series only,
+    1-based class indices in .mat, confusion matrix / F1 from the validation scores."""
+    from scipy.io import loadmat
+    from ifcb_classifier_b200.train_loop import save_validation_results
+
+    class DS(object):
+        def __init__(self, images, targets):
+            self.images, self.targets = images, targets
+            self.count_perclass = [targets.count(0), targets.count(1), targets.count(2)]
+
+    train = DS(['/d/a/t%d.png' % i for i in range(6)], [0, 0, 1, 1, 2, 2])
+    val = DS(['/d/a/v%d.png' % i for i in range(4)], [0, 1, 2, 2])
+    args = argparse.Namespace(classes=['a', 'b', 'c'], model_id='m', cmd_timestamp='ts', outdir=str(tmp_path))
+    scores = np.array([[.8, .1, .1], [.2, .7, .1], [.1, .2, .7], [.6, .3, .1]], np.float32)     # last one is wrong (2 -> 0)
+    series = 'training_image_basenames training_classes image_basenames input_classes output_scores confusion_matrix counts_perclass f1_perclass f1_weighted f1_macro'.split()
+    p = save_validation_results('results.mat', series, args, 3, train, val, np.array([0, 1, 2, 2]), scores, val.images)
+    m = loadmat(p)
+    assert m['input_classes'].ravel().tolist() == [1, 2, 3, 3] and m['output_classes'].ravel().tolist() == [1, 2, 3, 1]
+    assert m['confusion_matrix'].tolist() == [[1, 0, 0], [0, 1, 0], [1, 0, 1]]
+    assert m['counts_perclass'].ravel().tolist() == [3, 3, 4] and m['training_classes'].ravel().tolist() == [1, 1, 2, 2, 3, 3]
+    assert [str(s[0]) for s in m['image_basenames'].ravel()] == ['v0', 'v1', 'v2', 'v3']
+    assert abs(float(m['f1_macro'].ravel()[0]) - (2 / 3 + 1 + 2 / 3) / 3) < 1e-6 and 'recall_macro' not in m
+    p = save_validation_results('e{epoch}/results.json', ['output_winscores', 'classes_by_count'], args, 3, train, val, np.array([0, 1, 2, 2]),
+                                scores, val.images)
+    j = json.load(open(p))
+    assert p.endswith('e3/results.json') and j['classes_by_count'] == [2, 0, 1] and np.allclose(j['output_winscores'], [.8, .7, .7, .6])
+    assert 'confusion_matrix' not in j and j['class_labels'] == ['a', 'b', 'c']
+    with pytest.raises(NotImplementedError):
+        save_validation_results('results.h5', series, args, 0, train, val, np.array([0, 1, 2, 2]), scores, val.images)
