@@ -134,7 +134,6 @@ _SIGNATURES = {
     'ifcb_conv_repack': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
                                    C.c_int, C.c_void_p]),
     'ifcb_conv_repack_batch': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
-    'ifcb_stem_repack': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     'ifcb_plan_add_stem': (C.c_int, [C.c_void_p, C.POINTER(StemDesc)]),
     'ifcb_plan_add_pool': (C.c_int, [C.c_void_p, C.POINTER(PoolDesc)]),
     'ifcb_plan_add_head': (C.c_int, [C.c_void_p, C.POINTER(HeadDesc)]),

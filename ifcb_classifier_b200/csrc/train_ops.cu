@@ -803,14 +803,6 @@ __global__ void __launch_bounds__(256) conv_repack_batch_kernel(const ifcb_repac
   }
 }
 
-// stem master weights [Cout, taps, Cin8] fp32 -> the fp32 stem kernel's [taps*3, Cout]
-__global__ void stem_repack_kernel(const float* __restrict__ w, int Cout, int taps, int cin8, float* __restrict__ out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= Cout * taps * 3) return;
-  const int c = i % 3, t = (i / 3) % taps, co = i / (3 * taps);
-  out[(t * 3 + c) * Cout + co] = w[((long long)co * taps + t) * cin8 + c];
-}
-
 }  // namespace
 }  // namespace ifcb
 
@@ -1104,10 +1096,3 @@ extern "C" int ifcb_conv_repack_batch(const ifcb_repack_item* d_items, int n_ite
   return 0;
 }
 
-extern "C" int ifcb_stem_repack(const float* d_master, int Cout, int taps, int Cin8, float* d_wstem, void* stream) {
-  IFCB_ARG_CHECK(d_master && d_wstem && Cout > 0 && taps > 0 && Cin8 >= 3, "stem_repack: bad argument");
-  const int total = Cout * taps * 3;
-  stem_repack_kernel<<<(total + 255) / 256, 256, 0, STREAM(stream)>>>(d_master, Cout, taps, Cin8, d_wstem);
-  IFCB_CUDA_CHECK(cudaGetLastError());
-  return 0;
-}

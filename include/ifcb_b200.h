@@ -307,8 +307,6 @@ typedef struct {
   int32_t Cout, taps, Cin, Cin_pad, Cout_padk, reserved;
 } ifcb_repack_item;
 int ifcb_conv_repack_batch(const ifcb_repack_item* d_items, int n_items, int dtype, void* stream);
-/* stem master weights [Cout, taps, Cin8] -> the fp32 stem kernel's d_weight [taps*3, Cout] */
-int ifcb_stem_repack(const float* d_master, int Cout, int taps, int Cin8, float* d_wstem, void* stream);
 
 /* Stem: first convolution (Cin = 3) computed directly in fp32 on CUDA cores from either
  * the resized gray plane (u8) or a float32 NCHW [batch,3,H,W] tensor (drop-in forward(x)).
