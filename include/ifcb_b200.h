@@ -46,6 +46,12 @@ int ifcb_sm_count(void);
 int64_t ifcb_parse_adc(const char* buf, int64_t len, int col_w, int col_h, int col_b, int64_t max_rows,
                        int32_t* targets, int64_t* offsets, int32_t* heights, int32_t* widths);
 
+/* Host-side: JSON text "[[s00, s01, ...], [s10, ...], ...]" of a float32 [rows, cols] score matrix, byte-identical to
+ * json.dumps(scores.tolist()) as the reference's .json result files hold it (neuston_callbacks.py:213-230; float32
+ * widened to float64, shortest round-trip digits).  out must hold rows*(cols*28+4)+4 bytes; returns the text length
+ * (no terminator) or -1. */
+int64_t ifcb_format_scores_json(const float* scores, int64_t rows, int64_t cols, char* out, int64_t cap);
+
 /* ------------------------------------------------------------------------- *
  * K1  fused ROI preprocess.
  * Replaces IfcbBinDataset.__getitem__ (neuston_data.py:456-464):

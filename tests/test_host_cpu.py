@@ -321,3 +321,24 @@ def test_validation_results_files(tmp_path):
     assert 'confusion_matrix' not in j and j['class_labels'] == ['a', 'b', 'c']
     with pytest.raises(NotImplementedError):
         save_validation_results('results.h5', series, args, 0, train, val, np.array([0, 1, 2, 2]), scores, val.images)
+
+
+def test_json_score_text_is_byte_identical_to_python(built_lib):
+    """ifcb_format_scores_json == json.dumps(scores.tolist()) byte for byte (float32 widened to float64, shortest repr,
+    Python's fixed / exponent switch), so .json result files are what the reference writes (neuston_callbacks.py:213-230)."""
+    rng = np.random.default_rng(0)
+    cases = [rng.random((64, 100)).astype(np.float32), (10.0 ** rng.uniform(-45, 38, (200, 7))).astype(np.float32),
+             np.array([[0.0, 1.0, 0.5, 1e-4, 9.99e-5, 1e-5, 123456.0, 1e15, 1e16, 1.5e16, 3.4028235e38, 1e-45, -0.0, -2.5, 0.1]], np.float32),
+             -np.exp(rng.normal(0, 8, (50, 11))).astype(np.float32), np.zeros((0, 5), np.float32), np.zeros((3, 0), np.float32)]
+    for a in cases:
+        assert results._scores_json(a) == json.dumps(a.tolist())
+    # whole file: same bytes as the plain encoder would produce
+    pid = ifcb_io.Pid('D20260101T000000_IFCB999'); pid.namespace = ''
+    scores = rng.random((9, 4)).astype(np.float32)
+    imgs = [pid.with_target(t + 1) for t in range(9)]
+    import tempfile
+    d = tempfile.mkdtemp()
+    p = results.save_run_results(imgs, scores, list('abcd'), 'ts', d, '{BIN_ID}.json', 'm', pid)
+    want = json.dumps(dict(version='v3', model_id='m', timestamp='ts', class_labels=list('abcd'), output_scores=scores.tolist(),
+                           output_classes=scores.argmax(1).tolist(), bin_id=pid.pid, roi_numbers=list(range(1, 10))))
+    assert open(p).read() == want
