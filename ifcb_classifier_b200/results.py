@@ -1,9 +1,8 @@
 """Per-bin result files with the reference's layout (neuston_callbacks.py:160-272).
 
 ``save_run_results`` mirrors argument names and the templated path
-(``{BIN_ID} {BIN_YEAR} {BIN_DATE} {INPUT_SUBDIRS}``).  Formats: ``.json`` and ``.mat``
-always; ``.h5`` needs ``h5py`` (absent from this image -- a clear error is raised instead
-of silently writing something else).  The top-1 index / winning score come from the GPU
+(``{BIN_ID} {BIN_YEAR} {BIN_DATE} {INPUT_SUBDIRS}``).  Formats: ``.h5`` (the reference's default; written by
+the in-tree ``h5lite`` module, no h5py needed), ``.mat`` and ``.json``.  The top-1 index / winning score come from the GPU
 head kernel; they equal ``argmax`` / ``max`` of the score rows by construction.
 """
 import json
@@ -103,20 +102,17 @@ def _save(path, r):
             out['input_images'] = np.asarray(r['input_images'], dtype='object')
         savemat(path, out, do_compression=True)
     else:
-        try:
-            import h5py as h5
-        except ImportError:
-            raise RuntimeError('writing %s needs h5py, which is not installed; use --outfile with .mat or .json' % path)
-        with h5.File(path, 'w') as f:
-            meta = f.create_dataset('metadata', data=h5.Empty('f'))
-            meta.attrs['version'], meta.attrs['model_id'] = r['version'], r['model_id']
-            meta.attrs['timestamp'] = r['timestamp']
-            f.create_dataset('output_classes', data=r['output_classes'], compression='gzip', dtype='float16')
-            f.create_dataset('output_scores', data=r['output_scores'], compression='gzip', dtype='float16')
-            f.create_dataset('class_labels', data=np.bytes_(r['class_labels']), compression='gzip',
-                             dtype=h5.string_dtype())
-            if 'bin_id' in r:
-                meta.attrs['bin_id'] = r['bin_id']
-                f.create_dataset('roi_numbers', data=r['roi_numbers'], compression='gzip', dtype='uint16')
-            else:
-                f.create_dataset('input_images', data=np.bytes_(r['input_images']), compression='gzip', dtype=h5.string_dtype())
+        # _save_run_results_hdf (neuston_callbacks.py:252-268): same datasets, dtypes, gzip filter and attributes, written
+        # by the in-tree HDF5 writer (h5lite: h5py / libhdf5 are not needed)
+        from . import h5lite
+        attrs = dict(version=r['version'], model_id=r['model_id'] if r['model_id'] is not None else '', timestamp=r['timestamp'])
+        ds = dict(output_classes=dict(data=r['output_classes'], dtype='float16'),
+                  output_scores=dict(data=r['output_scores'], dtype='float16'),
+                  class_labels=dict(data=[str(c) for c in r['class_labels']], dtype='vlen_str'))
+        if 'bin_id' in r:
+            attrs['bin_id'] = str(r['bin_id'])
+            ds['roi_numbers'] = dict(data=r['roi_numbers'], dtype='uint16')
+        else:
+            ds['input_images'] = dict(data=[str(p_) for p_ in r['input_images']], dtype='vlen_str')
+        ds['metadata'] = dict(data=h5lite.Empty('f'), attrs=attrs)
+        h5lite.write(path, ds)

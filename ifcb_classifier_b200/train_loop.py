@@ -93,7 +93,7 @@ def _validation_stats(input_classes, output_classes, n_classes):
 
 
 def save_validation_results(outfile, series, args, epoch, train_ds, val_ds, input_classes, outputs, input_srcs):
-    """SaveValidationResults.on_validation_end (neuston_callbacks.py:20-156) for .mat / .json outputs."""
+    """SaveValidationResults.on_validation_end (neuston_callbacks.py:20-156): .mat / .json / .h5 outputs."""
     import json
     labels = args.classes
     output_classes = np.argmax(outputs, axis=1)
@@ -130,8 +130,27 @@ def save_validation_results(outfile, series, args, epoch, train_ds, val_ds, inpu
             else:
                 out[k] = v
         savemat(outfile, out, do_compression=True)
-    else:
-        raise NotImplementedError('validation results as %s need h5py (absent here); use .mat or .json' % os.path.splitext(outfile)[1])
+    elif outfile.endswith('.h5'):
+        # _save_validation_results_hdf (neuston_callbacks.py:139-156) through the in-tree HDF5 writer
+        from . import h5lite
+        attrib = ['model_id', 'timestamp'] + 'f1_weighted recall_weighted precision_weighted f1_macro recall_macro precision_macro'.split()
+        int_data = ['input_classes', 'output_classes', 'training_classes', 'counts_perclass', 'val_counts_perclass', 'train_counts_perclass'] + \
+                   ['classes_by_' + s for s in 'f1 recall precision count'.split()]
+        str_data = ['class_labels', 'image_fullpaths', 'image_basenames', 'training_image_fullpaths', 'training_image_basenames']
+        attrs, ds = {}, {}
+        for k, v in res.items():
+            if k in attrib:
+                attrs[k] = (v if v is not None else '') if isinstance(v, (str, type(None))) else float(v)
+            elif k in str_data:
+                ds[k] = dict(data=[str(s) for s in v], dtype='vlen_str')
+            elif k in int_data:
+                ds[k] = dict(data=np.asarray(v), dtype='int16')
+            elif isinstance(v, np.ndarray):
+                ds[k] = dict(data=v, dtype='float16')
+            else:
+                raise UserWarning('hdf results: WE MISSED THIS ONE: {}'.format(k))
+        ds['metadata'] = dict(data=h5lite.Empty('f'), attrs=attrs)
+        h5lite.write(outfile, ds)
     return outfile
 
 

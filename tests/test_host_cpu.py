@@ -102,11 +102,39 @@ def test_result_files_json_and_mat(tmp_path):
     assert m['output_scores'].dtype == np.float32 and m['roi_numbers'].ravel().tolist() == [1, 2, 4, 7, 9]
     with pytest.raises(AssertionError):
         results.save_run_results(imgs, scores, labels + ['d'], 'ts', str(tmp_path), '{BIN_ID}.json', 'm1', pid)
-    try:
-        import h5py  # noqa: F401
-    except ImportError:
-        with pytest.raises(RuntimeError):
-            results.save_run_results(imgs, scores, labels, 'ts', str(tmp_path), '{BIN_ID}_class.h5', 'm1', pid)
+
+
+def test_result_file_h5_default_layout(tmp_path):
+    """The reference's DEFAULT output (neuston_net.py:180-182, _save_run_results_hdf neuston_callbacks.py:252-268): an empty
+    float32 'metadata' dataset with version / model_id / timestamp / bin_id attributes, float16 gzip output_classes and
+    output_scores, variable-length-string class_labels, uint16 roi_numbers -- written without h5py and parsed back by the
+    independent reader (superblock, symbol table, object headers, chunk B-trees, global heap, deflate)."""
+    from ifcb_classifier_b200 import h5lite
+    pid = ifcb_io.Pid('D20260101T000000_IFCB999'); pid.namespace = ''
+    rng = np.random.default_rng(1)
+    scores = rng.random((2048, 100)).astype(np.float32); scores /= scores.sum(1, keepdims=True)
+    targets = np.arange(1, 2049) + (np.arange(2048) // 7)
+    imgs = [pid.with_target(t) for t in targets]
+    labels = ['class_%03d' % i for i in range(99)] + ['Dinobryon_\u00e9']
+    p = results.save_run_results(imgs, scores, labels, '2026-01-01T00:00:00+00:00', str(tmp_path),
+                                 'D{BIN_YEAR}/D{BIN_DATE}/{BIN_ID}_class.h5', 'm1', pid)
+    assert p.endswith('D2026/D20260101/D20260101T000000_IFCB999_class.h5')
+    with open(p, 'rb') as f:
+        assert f.read(8) == b'\x89HDF\r\n\x1a\n'
+    f = h5lite.read(p)
+    assert sorted(f) == ['class_labels', 'metadata', 'output_classes', 'output_scores', 'roi_numbers']
+    assert f['metadata'].shape is None and f['metadata'].dtype == np.float32
+    assert f['metadata'].attrs == dict(version='v3', model_id='m1', timestamp='2026-01-01T00:00:00+00:00', bin_id=pid.pid)
+    assert f['output_scores'].dtype == np.float16 and np.array_equal(f['output_scores'].data, scores.astype(np.float16))
+    assert f['output_classes'].dtype == np.float16 and np.array_equal(f['output_classes'].data, scores.argmax(1).astype(np.float16))
+    assert f['roi_numbers'].dtype == np.uint16 and f['roi_numbers'].data.tolist() == targets.tolist()
+    assert f['class_labels'].data.tolist() == labels
+    assert all(d.filters == [(1, (4,))] for k, d in f.items() if k != 'metadata')            # deflate on every array
+    # --type img files carry input_images instead of bin_id / roi_numbers
+    p2 = results.save_run_results(['/x/a.png', '/x/b.png'], scores[:2], labels, 'ts', str(tmp_path), 'img_results.h5', None, '/x')
+    g = h5lite.read(p2)
+    assert g['input_images'].data.tolist() == ['/x/a.png', '/x/b.png'] and 'bin_id' not in g['metadata'].attrs
+    assert g['metadata'].attrs['model_id'] == ''
 
 
 def test_model_names_and_checkpoint_roundtrip(tmp_path):
@@ -319,8 +347,14 @@ def test_validation_results_files(tmp_path):
     j = json.load(open(p))
     assert p.endswith('e3/results.json') and j['classes_by_count'] == [2, 0, 1] and np.allclose(j['output_winscores'], [.8, .7, .7, .6])
     assert 'confusion_matrix' not in j and j['class_labels'] == ['a', 'b', 'c']
-    with pytest.raises(NotImplementedError):
-        save_validation_results('results.h5', series, args, 0, train, val, np.array([0, 1, 2, 2]), scores, val.images)
+    from ifcb_classifier_b200 import h5lite
+    p = save_validation_results('results.h5', series + ['classes_by_f1'], args, 0, train, val, np.array([0, 1, 2, 2]), scores, val.images)
+    h = h5lite.read(p)
+    assert h['input_classes'].dtype == np.int16 and h['input_classes'].data.tolist() == [0, 1, 2, 2]       # 0-based in .h5
+    assert h['confusion_matrix'].dtype == np.float16 and h['confusion_matrix'].data.tolist() == [[1, 0, 0], [0, 1, 0], [1, 0, 1]]
+    assert h['image_basenames'].data.tolist() == ['v0', 'v1', 'v2', 'v3'] and h['class_labels'].data.tolist() == ['a', 'b', 'c']
+    assert abs(h['metadata'].attrs['f1_macro'] - (2 / 3 + 1 + 2 / 3) / 3) < 1e-9 and h['metadata'].attrs['model_id'] == 'm'
+    assert h['f1_perclass'].dtype == np.float16 and h['counts_perclass'].data.tolist() == [3, 3, 4]
 
 
 def test_json_score_text_is_byte_identical_to_python(built_lib):
