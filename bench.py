@@ -40,18 +40,27 @@ def load_peaks():
     return dict(bf16=1400.0, hbm=6650.0, src='fallback')
 
 
-def synth_bins(n_bins, rois, first=0):
+def _one_bin(arg):
     from oracle import synth_bins as sb      # workload generator only; not on the timed path
-    out = []
-    for i in range(n_bins):
-        b = sb.make_bin(first + i, rois)
-        targets = sorted(b['images'])
-        hs = np.array([b['images'][t].shape[0] for t in targets], np.int32)
-        ws = np.array([b['images'][t].shape[1] for t in targets], np.int32)
-        offs = np.concatenate([[0], np.cumsum(hs.astype(np.int64) * ws)[:-1]]).astype(np.int64)
-        out.append(dict(roi=b['roi'], offsets=offs, heights=hs, widths=ws, images=[b['images'][t] for t in targets],
-                        lid=b['lid']))
-    return out
+    idx, rois, keep_images = arg
+    b = sb.make_bin(idx, rois)
+    targets = sorted(b['images'])
+    hs = np.array([b['images'][t].shape[0] for t in targets], np.int32)
+    ws = np.array([b['images'][t].shape[1] for t in targets], np.int32)
+    offs = np.concatenate([[0], np.cumsum(hs.astype(np.int64) * ws)[:-1]]).astype(np.int64)
+    return dict(roi=b['roi'], offsets=offs, heights=hs, widths=ws, lid=b['lid'],
+                images=[b['images'][t] for t in targets] if keep_images else None)
+
+
+def synth_bins(n_bins, rois, first=0, keep_images=False, workers=1):
+    """``n_bins`` distinct synthetic bins (generator: oracle/synth_bins.py, seeded per bin index); generated on a few
+    worker processes because 64 bins x 2048 ROIs is about a minute of numpy on one core."""
+    jobs = [(first + i, rois, keep_images) for i in range(n_bins)]
+    if workers > 1 and n_bins > 2:
+        import multiprocessing as mp
+        with mp.get_context('fork').Pool(workers) as pool:
+            return pool.map(_one_bin, jobs)
+    return [_one_bin(j) for j in jobs]
 
 
 class ClockSampler(object):
@@ -104,7 +113,7 @@ def cpu_reference(steps, warmup, model_name='inception_v3', sample=REF_SAMPLE):
     R = 299 if model_name == 'inception_v3' else 224
     torch.manual_seed(0)
     model = model_ref.get_namebrand_model(model_name, N_CLASSES, False)
-    b = synth_bins(1, max(sample, 1))[0]
+    b = synth_bins(1, max(sample, 1), keep_images=True)[0]
     imgs, pids = b['images'][:sample], ['%s_%05d' % (b['lid'], i + 1) for i in range(sample)]
     loaders = min(cores, 8)
     for _ in range(warmup):
@@ -116,22 +125,199 @@ def cpu_reference(steps, warmup, model_name='inception_v3', sample=REF_SAMPLE):
     value = steps * sample / dt
     return dict(value=value, unit=UNIT, cores=cores, kind='port',
                 sample='%d steps x %d ROIs of synthetic bin 0 (IfcbBinDataset op sequence via Pillow/torchvision, '
-                       '%d DataLoader workers + %s fp32 forward on %d torch threads, batch %d)'
-                       % (steps, sample, loaders, model_name, cores, REF_SAMPLE)), dt / steps * 1e3
+                       '%d DataLoader workers + %s fp32 forward on %d torch threads, batch %d); the GPU arm classifies whole '
+                       '%d-ROI bins -- both are rates over the same ROI distribution'
+                       % (steps, sample, loaders, model_name, cores, REF_SAMPLE, ROIS_PER_BIN)), dt / steps * 1e3
+
+
+def cpu_config1(rois=ROIS_PER_BIN, budget_s=45.0):
+    """BASELINE config 1 as SURVEY 8(d) writes it: `neuston_net.py RUN`, resnet18 random-init (seed 0), C = 100, 224 px, ONE
+    synthetic bin of 2048 ROIs, batch 108, fp32, through the reference's own op sequence on the host CPU.  Reports the
+    preprocess / forward split and the pipelined whole (DataLoader workers overlapped with the forward, as the reference runs
+    it) with the reference's default 4 loaders and with all cores.  The forward leg is bounded to ``budget_s`` of CPU time
+    (whole 108-ROI batches) and says how many ROIs it covered."""
+    import torch
+    from torch.utils.data import DataLoader
+    from oracle import model_ref, ref_pipeline
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    model = model_ref.get_namebrand_model('resnet18', N_CLASSES, False).eval()
+    b = synth_bins(1, rois, keep_images=True)[0]
+    imgs, pids = b['images'], ['%s_%05d' % (b['lid'], i + 1) for i in range(rois)]
+    out = dict(model='resnet18', resize=224, rois=rois, batch=REF_SAMPLE, cores=cores, torch_threads=torch.get_num_threads())
+    ds = ref_pipeline.RefBinDataset(imgs, pids, 224, None)
+    for tag, nw in (('loaders4', 4), ('loaders_all', cores)):
+        t0 = time.perf_counter()
+        n = 0
+        for x, _ in DataLoader(ds, batch_size=REF_SAMPLE, num_workers=nw):
+            n += int(x.shape[0])
+        out['preprocess_rois_s_' + tag] = n / (time.perf_counter() - t0)
+    x = torch.stack([ds[i][0] for i in range(REF_SAMPLE)])
+    with torch.no_grad():
+        model(x)
+        t0, n = time.perf_counter(), 0
+        while n < rois and time.perf_counter() - t0 < budget_s / 3:
+            torch.softmax(model(x), 1)
+            n += REF_SAMPLE
+    out['forward_rois_s'] = n / (time.perf_counter() - t0)
+    out['forward_rois_timed'] = n
+    # the whole bin, pipelined (bounded: the first `m` ROIs of the bin)
+    m = int(min(rois, max(REF_SAMPLE, out['forward_rois_s'] * budget_s / 3)))
+    for tag, nw in (('loaders4', 4), ('loaders_all', cores)):
+        _, _, dt = ref_pipeline.run_bin(model, imgs[:m], pids[:m], 224, None, batch_size=REF_SAMPLE, loaders=nw)
+        out['run_rois_s_' + tag] = m / dt
+    out['run_rois_timed'] = m
+    return out
+
+
+# =====================================================================================================================
+# TRAIN block (BASELINE configs 4 / 5): data-parallel training step, one process per GPU
+# =====================================================================================================================
+def ddp_check(dev, rank, world):
+    """1-vs-N equivalence of the data-parallel step on a small net, run in process at world > 1:
+    the bucketed all-reduce equals the mean of the ranks' local gradients, replicas stay bit-identical through overlapped
+    (CUDA-graph) steps, and the loss goes down.  Returns 'ok' or the failure text."""
+    import torch
+    import torch.distributed as dist
+    from ifcb_classifier_b200.sharding import GradReducer
+    from ifcb_classifier_b200.train import TrainNet
+    from tests.fixtures import ref_model
+    try:
+        model = ref_model('resnet18', 10, seed=0)
+        B, R = 16, 64
+        net = TrainNet('resnet18', model.state_dict(), B, device=dev, dtype='bf16', R=R, bucket_mb=4)
+        g = torch.Generator().manual_seed(1234 + rank)
+        x = torch.rand(B, 3, R, R, generator=g).to(dev)
+        y = torch.randint(0, 10, (B,), generator=g).to(dev)
+        assert len(net.bucket_marks) >= 3, 'expected >= 3 gradient buckets'
+        net.forward_backward(x, y)
+        local_g = net.grads.clone()
+        gathered = [torch.empty_like(local_g) for _ in range(world)]
+        dist.all_gather(gathered, local_g)
+        want = sum(gathered) / world
+        red = GradReducer(net.grads)
+        for _, lo, hi in net.bucket_marks:
+            red(lo, hi)
+        scale = red.wait()
+        torch.cuda.synchronize(dev)
+        err = float((net.grads * scale - want).abs().max())
+        assert err <= 1e-6 * float(want.abs().max()) + 1e-12, 'all-reduced gradient != mean of local gradients (%g)' % err
+        net.adam(scale)
+        net.enable_cuda_graph()
+        losses = [float(net.step(x, y)) for _ in range(4)]
+        params = [torch.empty_like(net.params) for _ in range(world)]
+        dist.all_gather(params, net.params)
+        assert all(torch.equal(p, params[0]) for p in params[1:]), 'replicas diverged'
+        assert losses[-1] < losses[0], 'loss did not go down: %s' % losses
+        msg = 'ok'
+    except Exception as e:                                      # report, do not kill the bench line
+        msg = '%s: %s' % (type(e).__name__, e)
+    flag = torch.tensor([0 if msg == 'ok' else 1], device=dev)
+    dist.all_reduce(flag)
+    if msg == 'ok' and int(flag.item()):
+        msg = 'failed on another rank'
+    return msg
+
+
+def train_block(arch, dev, rank, world, local_rank, steps, warmup, batch, peaks):
+    """One TRAIN measurement: TrainNet.step (forward + backward + bucketed NCCL gradient all-reduce overlapped with the
+    backward pass + Adam + operand repack) replayed from CUDA graphs, synthetic preprocessed tensors resident on the device
+    (SURVEY 8d configs 4 / 5), CUDA events on the launching stream, barrier on both sides, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from ifcb_classifier_b200.train import TrainNet
+    from tests.fixtures import ref_model
+    model = ref_model(arch, N_CLASSES, seed=0)
+    net = TrainNet(arch, model.state_dict(), batch, device=dev, dtype='bf16', seed=rank)
+    g = torch.Generator().manual_seed(rank)
+    net.inp.copy_(torch.rand(batch, 3, net.R, net.R, generator=g))
+    net.labels.copy_(torch.randint(0, N_CLASSES, (batch,), generator=g))
+    net.enable_cuda_graph()
+    stream = torch.cuda.current_stream(dev)
+
+    def sync():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    def timed(n):
+        sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        last = None
+        for _ in range(n):
+            last = net.step()
+        e1.record(stream)
+        sync()
+        t = torch.tensor([e0.elapsed_time(e1) / n], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), last
+
+    first = None
+    for i in range(warmup):
+        l_ = net.step()
+        if i == 0:
+            first = float(l_)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ms, last = timed(steps)
+    clocks = sampler.stop() if sampler else None
+    loss_last = float(last)
+    out = dict(arch=arch, resize=net.R, batch_per_gpu=batch, dtype='bf16', steps=steps, warmup=warmup, cuda_graph=True,
+               img_s=batch * world / (ms * 1e-3), ms_per_step=ms, loss_first=first, loss_last=loss_last, clocks=clocks,
+               optimizer='Adam lr 1e-3', loss='CE + 0.4 CE_aux' if arch == 'inception_v3' else 'CE',
+               data='synthetic preprocessed tensors resident in HBM, uniform random labels')
+    fwd_flops = net.fp.flops_per_image
+    tf = 3 * fwd_flops * batch / (ms * 1e-3) / 1e12                          # per GPU
+    out.update(gflop_per_img=3 * fwd_flops / 1e9, tflops_per_gpu=tf, frac=tf / peaks['bf16'],
+               launches_per_step=len(net.fwd) + len(net.bwd) + 3)
+    # exposed all-reduce = step time with the exchange minus the same step without it
+    if world > 1:
+        class _NoReduce(object):
+            def __call__(self, lo, hi): pass
+            def wait(self): return 1.0 / world
+        real = net._reducer
+        net._reducer = _NoReduce()
+        ms_local, _ = timed(max(5, steps // 5))
+        net._reducer = real
+        out['allreduce_exposed_ms'] = max(0.0, ms - ms_local)
+        out['allreduce_bytes'] = int(4 * net.n_params)
+    else:
+        out['allreduce_exposed_ms'] = 0.0
+    # forward / backward / optimizer split (eager launches of the same kernels, events between the phases)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    acc = [0.0, 0.0, 0.0]
+    reps = 3
+    for _ in range(reps):
+        ev[0].record(stream); net.forward(); ev[1].record(stream); net.backward(); ev[2].record(stream); net.adam(1.0 / world)
+        ev[3].record(stream)
+        torch.cuda.synchronize(dev)
+        for i in range(3):
+            acc[i] += ev[i].elapsed_time(ev[i + 1]) / reps
+    out.update(forward_ms=acc[0], backward_ms=acc[1], optimizer_ms=acc[2], mem_gb=torch.cuda.max_memory_allocated(dev) / 2 ** 30)
+    del net
+    torch.cuda.empty_cache()
+    return out
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--model', default='inception_v3')
     ap.add_argument('--dtype', default='fp16', choices=['fp16', 'bf16'])
     ap.add_argument('--batch', type=int, default=1024, help='ROIs per network launch sequence')
     ap.add_argument('--rois', type=int, default=ROIS_PER_BIN)
-    ap.add_argument('--bins', type=int, default=4, help='distinct synthetic bins cycled through')
+    ap.add_argument('--bins', type=int, default=64, help='distinct synthetic bins per GPU (SURVEY 8d: >= 64)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-train', action='store_true', help='skip the TRAIN block (BASELINE configs 4 / 5)')
+    ap.add_argument('--train-steps', type=int, default=50)
+    ap.add_argument('--train-warmup', type=int, default=10)
+    ap.add_argument('--train-batch', type=int, default=256)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     rank = int(os.environ.get('RANK', '0'))
@@ -154,6 +340,11 @@ def main():
         print(json.dumps(line))
         return 0
 
+    # synthetic bins first (worker processes are forked before any CUDA / NCCL state exists);
+    # weak scaling: every rank owns its own bins (bins are sharded, no collective on the data path)
+    workers = max(1, min(8, (os.cpu_count() or 1) // max(world, 1)))
+    bins = synth_bins(args.bins, args.rois, first=rank * args.bins, workers=workers)
+
     import torch
     if not torch.cuda.is_available():
         raise SystemExit('bench.py: no CUDA device -- the B200 path has no CPU fallback')
@@ -175,8 +366,6 @@ def main():
     model = ref_model(args.model, N_CLASSES, seed=0)
     eng = BinClassifier(args.model, model.state_dict(), device=dev, batch_cap=args.batch, dtype=args.dtype,
                         max_rois=args.rois)
-    # weak scaling: every rank owns its own bins (bins are sharded, no collective on the data path)
-    bins = synth_bins(args.bins, args.rois, first=rank * args.bins)
     pinned = [dict(roi=torch.from_numpy(b['roi']).pin_memory(), offsets=torch.from_numpy(b['offsets']).pin_memory(),
                    heights=torch.from_numpy(b['heights']).pin_memory(), widths=torch.from_numpy(b['widths']).pin_memory())
               for b in bins]
@@ -189,14 +378,8 @@ def main():
 
     def step_resident(i):
         r = resident[i % len(resident)]
-        n, nb = r['offsets'].shape[0], r['roi'].shape[0]
-        # device-to-device staging copy of the packed bytes is part of the step (tiny vs the network)
-        eng.d_roi[:nb].copy_(r['roi'], non_blocking=True)
-        eng.d_off[:n].copy_(r['offsets'], non_blocking=True)
-        eng.d_h[:n].copy_(r['heights'], non_blocking=True)
-        eng.d_w[:n].copy_(r['widths'], non_blocking=True)
-        eng.classify_device(n, nb)
-        return n
+        eng.classify_resident(r['roi'], r['offsets'], r['heights'], r['widths'])      # no staging copy: the kernel reads the bin in place
+        return int(r['offsets'].shape[0])
 
     def step_e2e(i):
         p = pinned[i % len(pinned)]
@@ -262,17 +445,21 @@ def main():
     conv_flops = float(sum(f for f, k in zip(net.pb.layer_flops, net.pb.layer_kinds) if k == 'conv')) * B
     t_conv = float(conv_ms[is_conv].sum()) * 1e-3
     achieved = conv_flops / t_conv / 1e12
-    # DRAM bytes per conv launch from the committed ncu pass over the 65 conv launches of one batch
-    # (profiles/r01_ncu_conv_traffic.txt; same model / batch / dtype as this run, else null)
+    # DRAM bytes per conv launch from the committed ncu pass over the conv launches of one batch
+    # (same model / batch / dtype as this run, else null)
     traffic = None
-    tpath = os.path.join(ROOT, 'profiles', 'r01_conv_traffic.json')
-    if os.path.exists(tpath) and args.model == 'inception_v3' and B == int(json.load(open(tpath)).get('batch', 0)):
-        traffic = float(json.load(open(tpath))['dram_bytes_per_launch'])
+    for tname in ('r02_conv_traffic.json', 'r01_conv_traffic.json'):
+        tpath = os.path.join(ROOT, 'profiles', tname)
+        if os.path.exists(tpath) and args.model == 'inception_v3':
+            tj = json.load(open(tpath))
+            if B == int(tj.get('batch', 0)):
+                traffic = float(tj['dram_bytes_per_launch'])
+                break
     roofline = dict(bound='tensor', achieved=achieved, peak=peaks['bf16'], unit='TFLOP/s', frac=achieved / peaks['bf16'],
                     traffic=traffic, kernel='conv_umma_kernel', peak_source=peaks['src'] + ' sustained dense bf16',
                     conv_launches=int(is_conv.sum()), conv_share_of_network=float(conv_ms[is_conv].sum() / conv_ms.sum()),
                     network_ms_per_batch=float(conv_ms.sum()), batch=B,
-                    whole_path_frac=value * net.flops_per_image / 1e12 / peaks['bf16'])
+                    whole_path_frac=value / world * net.flops_per_image / 1e12 / peaks['bf16'])      # per GPU
 
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
                 ms_per_step=ms / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
@@ -284,9 +471,30 @@ def main():
                 e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                          ms_per_step=ms_e2e / args.steps),
                 gpu_launches=int(launches), clocks=clocks)
+
+    # ---- TRAIN (BASELINE configs 4 / 5) -------------------------------------------------------------------------
+    if not args.no_train:
+        del eng, net, resident, pinned
+        torch.cuda.empty_cache()
+        train = dict(parallelism='data parallel dp%d: per-rank batches and BatchNorm statistics, bucketed NCCL gradient all-reduce '
+                                 'overlapped with the backward pass, mean folded into Adam' % world,
+                     peak_tflops=peaks['bf16'], frac_definition='3 x forward FLOPs x batch / step time / sustained bf16 peak, per GPU')
+        if world > 1:
+            train['ddp_check'] = ddp_check(dev, rank, world)
+        for arch in ('resnet50', 'inception_v3'):
+            try:
+                train[arch] = train_block(arch, dev, rank, world, local_rank, args.train_steps, args.train_warmup, args.train_batch, peaks)
+            except Exception as e:
+                train[arch] = dict(error='%s: %s' % (type(e).__name__, e))
+        line['train'] = train
+
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             cb, _ = cpu_reference(2, 1, args.model)
+            try:
+                cb['config1'] = cpu_config1()
+            except Exception as e:
+                cb['config1'] = dict(error='%s: %s' % (type(e).__name__, e))
             line['cpu_baseline'] = cb
         print(json.dumps(line))
     if world > 1:

@@ -100,6 +100,7 @@ _SIGNATURES = {
     'ifcb_plan_create': (C.c_int, [C.POINTER(C.c_void_p)]),
     'ifcb_plan_destroy': (C.c_int, [C.c_void_p]),
     'ifcb_plan_run': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    'ifcb_plan_run_at': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     'ifcb_plan_run_range': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     'ifcb_plan_num_layers': (C.c_int, [C.c_void_p]),
     'ifcb_plan_num_launches': (C.c_int, [C.c_void_p]),

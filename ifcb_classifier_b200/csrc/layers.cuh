@@ -74,6 +74,6 @@ int launch_im2col_probe(const ConvLayer& L, int c, int w, int h, int n, int off_
 int conv_smem_bytes(const ConvKernelParams& kp, bool window, bool pair);
 int launch_stem(const StemLayer& L, int batch, cudaStream_t stream);
 int launch_pool(const PoolLayer& L, int batch, cudaStream_t stream);
-int launch_head(const HeadLayer& L, int batch, cudaStream_t stream);
+int launch_head(const HeadLayer& L, int batch, int out_row, cudaStream_t stream);
 
 }  // namespace ifcb

@@ -379,7 +379,19 @@ extern "C" int ifcb_plan_add_head(ifcb_plan* plan, const ifcb_head_desc* d) {
   return 0;
 }
 
+static int plan_run_impl(ifcb_plan* plan, int first, int last, int batch, int out_row, void* stream_v);
+
 extern "C" int ifcb_plan_run_range(ifcb_plan* plan, int first, int last, int batch, void* stream_v) {
+  return plan_run_impl(plan, first, last, batch, 0, stream_v);
+}
+
+extern "C" int ifcb_plan_run_at(ifcb_plan* plan, int batch, int out_row, void* stream_v) {
+  IFCB_ARG_CHECK(plan != nullptr, "ifcb_plan_run_at: null plan");
+  IFCB_ARG_CHECK(out_row >= 0, "ifcb_plan_run_at: out_row < 0");
+  return plan_run_impl(plan, 0, (int)plan->layers.size(), batch, out_row, stream_v);
+}
+
+static int plan_run_impl(ifcb_plan* plan, int first, int last, int batch, int out_row, void* stream_v) {
   IFCB_ARG_CHECK(plan != nullptr, "ifcb_plan_run: null plan");
   IFCB_ARG_CHECK(first >= 0 && last <= (int)plan->layers.size() && first <= last, "ifcb_plan_run: bad layer range");
   IFCB_ARG_CHECK(batch >= 0, "ifcb_plan_run: batch < 0");
@@ -402,7 +414,7 @@ extern "C" int ifcb_plan_run_range(ifcb_plan* plan, int first, int last, int bat
         break;
       case kHead:
         IFCB_ARG_CHECK(batch <= L.head.d.batch_cap, "layer %d: batch %d exceeds capacity", i, batch);
-        rc = launch_head(L.head, batch, stream);
+        rc = launch_head(L.head, batch, out_row, stream);
         break;
     }
     if (rc) return rc;

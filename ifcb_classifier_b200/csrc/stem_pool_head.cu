@@ -609,9 +609,15 @@ int launch_pool(const PoolLayer& L, int batch, cudaStream_t stream) {
   return 0;
 }
 
-int launch_head(const HeadLayer& L, int batch, cudaStream_t stream) {
-  const ifcb_head_desc& d = L.d;
+int launch_head(const HeadLayer& L, int batch, int out_row, cudaStream_t stream) {
+  ifcb_head_desc d = L.d;
   if (batch == 0) return 0;
+  if (out_row) {                  // rows of this batch land at out_row of the caller's per-bin output buffers
+    d.d_scores = static_cast<float*>(d.d_scores) + (size_t)out_row * d.n_classes;
+    if (d.d_logits) d.d_logits = static_cast<float*>(d.d_logits) + (size_t)out_row * d.n_classes;
+    d.d_top1 = static_cast<int32_t*>(d.d_top1) + out_row;
+    d.d_top1_score = static_cast<float*>(d.d_top1_score) + out_row;
+  }
   const int smem = (d.C + d.n_classes) * (int)sizeof(float);
   head_kernel<<<batch, 256, smem, stream>>>(d);
   IFCB_CUDA_CHECK(cudaGetLastError());

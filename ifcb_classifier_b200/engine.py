@@ -20,71 +20,90 @@ class BinClassifier(object):
     def __init__(self, arch, state_dict, n_classes=None, img_norm=None, transform_input=False,
                  device='cuda', batch_cap=512, dtype='fp16', max_rois=4096, max_roi_bytes=64 << 20, cuda_graph=True):
         self.device = torch.device(device)
+        # the head writes each batch at its row of per-bin output buffers (ifcb_plan_run_at): a bin's scores are
+        # contiguous on the device without any copy and leave it in one transfer
+        self.window = max(1, (int(max_rois) + batch_cap - 1) // batch_cap) * batch_cap
         self.net = CompiledNet(arch, state_dict, batch_cap, in_kind='u8', img_norm=img_norm,
-                               transform_input=transform_input, device=self.device, dtype=dtype)
+                               transform_input=transform_input, device=self.device, dtype=dtype, out_rows=self.window)
         if cuda_graph and os.environ.get('IFCB_RUN_GRAPH', '1') != '0':
-            self.net.enable_cuda_graph()            # full batches replay the plan's launches from one CUDA graph
+            self.net.enable_cuda_graph()            # full batches replay the plan's launches from CUDA graphs (one per output slot)
         self.R, self.batch_cap, self.n_classes = self.net.R, batch_cap, self.net.n_classes
-        self._alloc(max_rois, max_roi_bytes)
+        self.d_scores, self.d_top1, self.d_top1_score = self.net.pb.scores, self.net.pb.top1, self.net.pb.top1_score
+        self.max_roi_bytes = 0
+        self._alloc_bytes(max_roi_bytes)
+        d = self.device
+        self.d_off = torch.zeros(self.window, dtype=torch.int64, device=d)
+        self.d_h = torch.zeros(self.window, dtype=torch.int32, device=d)
+        self.d_w = torch.zeros(self.window, dtype=torch.int32, device=d)
+        # pinned staging for the end-to-end path (grown on demand: a bin may hold more ROIs than one window)
+        self.h_scores = torch.zeros((self.window, self.n_classes), dtype=torch.float32).pin_memory()
+        self.h_top1 = torch.zeros(self.window, dtype=torch.int32).pin_memory()
         self.launches_last = 0
 
-    def _alloc(self, max_rois, max_roi_bytes):
-        d = self.device
-        self.max_rois, self.max_roi_bytes = int(max_rois), int(max_roi_bytes)
-        self.d_roi = torch.zeros(self.max_roi_bytes + 16, dtype=torch.uint8, device=d)
-        self.d_off = torch.zeros(self.max_rois, dtype=torch.int64, device=d)
-        self.d_h = torch.zeros(self.max_rois, dtype=torch.int32, device=d)
-        self.d_w = torch.zeros(self.max_rois, dtype=torch.int32, device=d)
-        self.d_scores = torch.zeros((self.max_rois, self.n_classes), dtype=torch.float32, device=d)
-        self.d_top1 = torch.zeros(self.max_rois, dtype=torch.int32, device=d)
-        self.d_top1_score = torch.zeros(self.max_rois, dtype=torch.float32, device=d)
-        # pinned staging for the end-to-end path
-        self.h_scores = torch.zeros((self.max_rois, self.n_classes), dtype=torch.float32).pin_memory()
-        self.h_top1 = torch.zeros(self.max_rois, dtype=torch.int32).pin_memory()
+    def _alloc_bytes(self, nbytes):
+        if nbytes > self.max_roi_bytes:
+            self.max_roi_bytes = int(nbytes)
+            self.d_roi = torch.zeros(self.max_roi_bytes + 16, dtype=torch.uint8, device=self.device)
 
-    def _ensure(self, n, nbytes):
-        if n > self.max_rois or nbytes > self.max_roi_bytes:
-            self._alloc(max(n, self.max_rois), max(nbytes, self.max_roi_bytes))
+    def _ensure_host(self, n):
+        if n > self.h_scores.shape[0]:
+            self.h_scores = torch.zeros((n, self.n_classes), dtype=torch.float32).pin_memory()
+            self.h_top1 = torch.zeros(n, dtype=torch.int32).pin_memory()
 
     # ---- device-resident step -------------------------------------------------
-    def upload(self, roi, offsets, heights, widths):
-        """Host arrays (numpy or pinned torch tensors) -> device staging; returns (n, nbytes)."""
-        n, nbytes = int(len(offsets)), int(roi.shape[0])
-        self._ensure(n, nbytes)
-        as_t = lambda a: a if torch.is_tensor(a) else torch.from_numpy(np.ascontiguousarray(a))
-        self.d_roi[:nbytes].copy_(as_t(roi), non_blocking=True)
-        self.d_off[:n].copy_(as_t(offsets), non_blocking=True)
-        self.d_h[:n].copy_(as_t(heights), non_blocking=True)
-        self.d_w[:n].copy_(as_t(widths), non_blocking=True)
-        return n, nbytes
-
-    def classify_device(self, n, nbytes, max_h=pp.FRAME_H, max_w=pp.FRAME_W):
-        """Runs preprocess + network on the ``n`` ROIs staged by ``upload`` (async on the
-        current stream).  Results land in d_scores / d_top1 / d_top1_score [:n]."""
+    def classify_resident(self, roi, offsets, heights, widths, first=0, count=None, max_h=pp.FRAME_H, max_w=pp.FRAME_W):
+        """Preprocess + network over ROIs [first, first + count) of a bin whose packed bytes and ROI table are DEVICE
+        tensors (read in place, no staging copy).  count <= the output window; asynchronous on the current stream.
+        Results: d_scores / d_top1 / d_top1_score [:count]."""
+        n = int(offsets.shape[0]) - first if count is None else int(count)
+        if n > self.window:
+            raise ValueError('classify_resident: %d ROIs exceed the output window of %d (use classify_bin)' % (n, self.window))
         net, B = self.net, self.batch_cap
         launches = 0
         for i in range(0, n, B):
             m = min(B, n - i)
-            pp.preprocess_rois(self.d_roi[:nbytes], self.d_off[i:i + m], self.d_h[i:i + m], self.d_w[i:i + m],
+            lo = first + i
+            pp.preprocess_rois(roi, offsets[lo:lo + m], heights[lo:lo + m], widths[lo:lo + m],
                                self.R, out_mode=pp.OUT_U8_GRAY, out=net.inp[:m], max_h=max_h, max_w=max_w)
-            s, _, t1, t1s = net.forward(m)
-            self.d_scores[i:i + m].copy_(s, non_blocking=True)
-            self.d_top1[i:i + m].copy_(t1, non_blocking=True)
-            self.d_top1_score[i:i + m].copy_(t1s, non_blocking=True)
+            net.forward(m, out_row=i)
             launches += 1 + net.num_launches
         self.launches_last = launches
         return self.d_scores[:n], self.d_top1[:n], self.d_top1_score[:n]
 
+    def upload(self, roi, offsets, heights, widths, first=0, count=None):
+        """Host arrays (numpy or pinned torch tensors) -> device staging (ROI table rows [first, first+count))."""
+        nbytes = int(roi.shape[0])
+        n = int(len(offsets)) - first if count is None else int(count)
+        as_t = lambda a: a if torch.is_tensor(a) else torch.from_numpy(np.ascontiguousarray(a))
+        if first == 0:
+            self._alloc_bytes(nbytes)
+            self.d_roi[:nbytes].copy_(as_t(roi), non_blocking=True)
+        self.d_off[:n].copy_(as_t(offsets)[first:first + n], non_blocking=True)
+        self.d_h[:n].copy_(as_t(heights)[first:first + n], non_blocking=True)
+        self.d_w[:n].copy_(as_t(widths)[first:first + n], non_blocking=True)
+        return n, nbytes
+
+    def classify_device(self, n, nbytes, max_h=pp.FRAME_H, max_w=pp.FRAME_W):
+        """Runs preprocess + network on the ``n`` ROIs staged by ``upload`` (async on the current stream)."""
+        return self.classify_resident(self.d_roi[:nbytes], self.d_off, self.d_h, self.d_w, 0, n, max_h, max_w)
+
     # ---- end to end -------------------------------------------------------------
     def classify_bin(self, roi, offsets, heights, widths, sync=True):
-        """Host bytes in -> host scores out (float32 [n, C], int32 top-1 [n])."""
-        n, nbytes = self.upload(roi, offsets, heights, widths)
-        if n == 0:
+        """Host bytes in -> host scores out (float32 [n, C], int32 top-1 [n]); views of pinned buffers that the next call
+        overwrites.  Pinned inputs make the upload asynchronous."""
+        n_all = int(len(offsets))
+        if n_all == 0:
             return np.zeros((0, self.n_classes), np.float32), np.zeros(0, np.int32)
-        mh, mw = int(np.max(np.asarray(heights))), int(np.max(np.asarray(widths)))
-        s, t1, _ = self.classify_device(n, nbytes, max(mh, 1), max(mw, 1))
-        self.h_scores[:n].copy_(s, non_blocking=True)
-        self.h_top1[:n].copy_(t1, non_blocking=True)
+        self._ensure_host(n_all)
+        mh, mw = max(int(np.max(np.asarray(heights))), 1), max(int(np.max(np.asarray(widths))), 1)
+        launches = 0
+        for w0 in range(0, n_all, self.window):                    # one pass for any bin up to `window` ROIs
+            n, nbytes = self.upload(roi, offsets, heights, widths, w0, min(self.window, n_all - w0))
+            s, t1, _ = self.classify_device(n, nbytes, mh, mw)
+            self.h_scores[w0:w0 + n].copy_(s, non_blocking=True)
+            self.h_top1[w0:w0 + n].copy_(t1, non_blocking=True)
+            launches += self.launches_last
+        self.launches_last = launches
         if sync:
             torch.cuda.current_stream(self.device).synchronize()
-        return self.h_scores[:n].numpy(), self.h_top1[:n].numpy()
+        return self.h_scores[:n_all].numpy(), self.h_top1[:n_all].numpy()

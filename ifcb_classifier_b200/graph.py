@@ -77,7 +77,7 @@ def fold_bn(sd, prefix, eps):
 
 
 class PlanBuilder(object):
-    def __init__(self, batch_cap, device, dtype='fp16'):
+    def __init__(self, batch_cap, device, dtype='fp16', out_rows=None):
         """``dtype``: 16-bit storage / tensor-core operand format of activations and
         conv weights -- 'fp16' (default: 11-bit significand, meets the 1e-2 score
         gate) or 'bf16' (8-bit significand).  Accumulation is fp32 either way."""
@@ -86,6 +86,8 @@ class PlanBuilder(object):
         self.tdtype = torch.float16 if dtype == 'fp16' else torch.bfloat16
         self.cdtype = _lib.IFCB_ACT_FP16 if dtype == 'fp16' else _lib.IFCB_ACT_BF16
         self.batch_cap = int(batch_cap)
+        # rows of the head's output buffers (>= batch_cap): the batches of one bin are written side by side (run(out_row=...))
+        self.out_rows = max(int(out_rows or 0), self.batch_cap)
         self.device = device
         self.keep = []                 # every device tensor the plan points into
         self.layer_names = []
@@ -236,11 +238,11 @@ class PlanBuilder(object):
     def head(self, x, weight, bias, name='head'):
         n_classes = int(weight.shape[0])
         assert x.pad == (0, 0), 'head input must be unpadded'
-        B = self.batch_cap
-        self.scores = torch.zeros((B, n_classes), dtype=torch.float32, device=self.device)
-        self.logits = torch.zeros((B, n_classes), dtype=torch.float32, device=self.device)
-        self.top1 = torch.zeros((B,), dtype=torch.int32, device=self.device)
-        self.top1_score = torch.zeros((B,), dtype=torch.float32, device=self.device)
+        B, rows = self.batch_cap, self.out_rows
+        self.scores = torch.zeros((rows, n_classes), dtype=torch.float32, device=self.device)
+        self.logits = torch.zeros((rows, n_classes), dtype=torch.float32, device=self.device)
+        self.top1 = torch.zeros((rows,), dtype=torch.int32, device=self.device)
+        self.top1_score = torch.zeros((rows,), dtype=torch.float32, device=self.device)
         d = HeadDesc()
         d.d_in, d.in_ld, d.C, d.HW = x.ptr, x.ld, x.C, x.H * x.W
         d.batch_cap, d.n_classes = B, n_classes
@@ -253,10 +255,11 @@ class PlanBuilder(object):
         self._note(name, 'head', 2 * x.C * n_classes)
         return self.scores
 
-    def run(self, batch, first=None, last=None):
+    def run(self, batch, first=None, last=None, out_row=0):
         stream = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         if first is None:
-            _lib.check(_lib.lib().ifcb_plan_run(self.handle, int(batch), stream), 'plan_run')
+            assert 0 <= out_row and out_row + batch <= self.out_rows, (out_row, batch, self.out_rows)
+            _lib.check(_lib.lib().ifcb_plan_run_at(self.handle, int(batch), int(out_row), stream), 'plan_run')
         else:
             _lib.check(_lib.lib().ifcb_plan_run_range(self.handle, int(first), int(last), int(batch), stream),
                        'plan_run_range')
@@ -715,14 +718,15 @@ class CompiledNet(object):
     """
 
     def __init__(self, arch, state_dict, batch_cap, in_kind='u8', R=None, img_norm=None,
-                 transform_input=False, device='cuda', fuse=True, dtype='fp16'):
+                 transform_input=False, device='cuda', fuse=True, dtype='fp16', out_rows=None):
         self.arch = arch
         self.R = R or (299 if arch == 'inception_v3' else 224)
         self.in_kind = in_kind
         self.batch_cap = int(batch_cap)
         self.device = torch.device(device)
         sd = {k: v.detach().cpu() for k, v in state_dict.items()}
-        pb = PlanBuilder(batch_cap, self.device, dtype)
+        pb = PlanBuilder(batch_cap, self.device, dtype, out_rows=out_rows)
+        self.out_rows = pb.out_rows
         self.dtype = dtype
         if in_kind == 'u8':
             self.inp = torch.zeros((batch_cap, self.R, self.R), dtype=torch.uint8, device=self.device)
@@ -750,21 +754,26 @@ class CompiledNet(object):
         self.num_launches = _lib.lib().ifcb_plan_num_launches(pb.handle)
 
     def enable_cuda_graph(self):
-        """Captures the full-batch forward (every launch of the plan) into a CUDA graph; ``forward(batch_cap)`` then
-        replays it.  All pointers of a plan are fixed at construction, so the graph stays valid."""
+        """Captures the full-batch forward (every launch of the plan) into CUDA graphs, one per output slot
+        (``out_row`` = 0, batch_cap, 2*batch_cap, ... < out_rows); ``forward(batch_cap, out_row)`` then replays the slot's
+        graph.  All pointers of a plan are fixed at construction, so the graphs stay valid."""
         for _ in range(2):
             self.pb.run(self.batch_cap)
         torch.cuda.synchronize(self.device)
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            self.pb.run(self.batch_cap)
-        self._graph = g
+        self._graphs = {}
+        for row in range(0, self.out_rows - self.batch_cap + 1, self.batch_cap):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.pb.run(self.batch_cap, out_row=row)
+            self._graphs[row] = g
 
-    def forward(self, n):
-        """Runs the plan on the first ``n`` images of ``self.inp`` (current stream).
-        Returns views (scores, logits, top1, top1_score) of the plan's output buffers."""
-        if n == self.batch_cap and getattr(self, '_graph', None) is not None:
-            self._graph.replay()
+    def forward(self, n, out_row=0):
+        """Runs the plan on the first ``n`` images of ``self.inp`` (current stream); the head writes rows
+        [out_row, out_row + n) of the output buffers.  Returns views (scores, logits, top1, top1_score) of those rows."""
+        g = getattr(self, '_graphs', {}).get(out_row) if n == self.batch_cap else None
+        if g is not None:
+            g.replay()
         else:
-            self.pb.run(n)
-        return self.pb.scores[:n], self.pb.logits[:n], self.pb.top1[:n], self.pb.top1_score[:n]
+            self.pb.run(n, out_row=out_row)
+        sl = slice(out_row, out_row + n)
+        return self.pb.scores[sl], self.pb.logits[sl], self.pb.top1[sl], self.pb.top1_score[sl]

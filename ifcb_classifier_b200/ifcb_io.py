@@ -80,7 +80,16 @@ def parse_adc(path, schema=SCHEMA_VERSION_2):
 class RawBin(object):
     """One bin as the GPU path wants it: raw ``.roi`` bytes + ROI table."""
 
-    def __init__(self, basepath=None, pid=None, roi=None, targets=None, offsets=None, heights=None, widths=None):
+    def __init__(self, basepath=None, pid=None, roi=None, targets=None, offsets=None, heights=None, widths=None,
+                 into=None, orientation='hw'):
+        """``into``: optional ``f(nbytes) -> writable uint8 ndarray`` (>= nbytes): the ``.roi`` file is read straight into
+        it (``readinto``) -- the RUN driver passes slots of a pinned ring so that the upload is an asynchronous DMA.
+        ``orientation``: how a ROI's ``ROI_WIDTH x ROI_HEIGHT`` byte block is laid out (pyifcb is absent and unpinned
+        upstream): 'hw' = ROI_HEIGHT rows of ROI_WIDTH bytes (default; what oracle/ifcb_stub.py restates),
+        'wh' = ROI_WIDTH rows of ROI_HEIGHT bytes (the table's two columns swap roles; no pixel is moved)."""
+        if orientation not in ('hw', 'wh'):
+            raise ValueError("orientation must be 'hw' or 'wh'")
+        self.orientation = orientation
         if basepath is not None:
             self.basepath = basepath
             self.pid = Pid(os.path.basename(basepath))
@@ -88,13 +97,27 @@ class RawBin(object):
             if self.schema == SCHEMA_VERSION_1:
                 raise NotImplementedError('schema v1 (stitched) bins are not supported yet')
             self.targets, self.offsets, self.heights, self.widths = parse_adc(basepath + '.adc', self.schema)
-            self.roi = np.fromfile(basepath + '.roi', dtype=np.uint8)
+            if into is None:
+                self.roi = np.fromfile(basepath + '.roi', dtype=np.uint8)
+            else:
+                size = os.path.getsize(basepath + '.roi')
+                buf = into(size)
+                with open(basepath + '.roi', 'rb', buffering=0) as f:
+                    got = f.readinto(memoryview(buf)[:size])
+                    while got < size:
+                        more = f.readinto(memoryview(buf)[got:size])
+                        if not more:
+                            break
+                        got += more
+                self.roi = buf[:got]
         else:
             self.basepath = None
             self.pid = pid if isinstance(pid, Pid) else Pid(pid)
             self.schema = self.pid.schema_version
             self.roi, self.targets, self.offsets = roi, targets, offsets
             self.heights, self.widths = heights, widths
+        if orientation == 'wh':
+            self.heights, self.widths = self.widths, self.heights
         end = self.offsets + self.heights.astype(np.int64) * self.widths.astype(np.int64)
         if len(end) and (end.max() > self.roi.size or self.offsets.min() < 0):
             raise ValueError('%s: ADC table points outside the .roi file' % self.pid)

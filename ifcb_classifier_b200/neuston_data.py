@@ -59,6 +59,15 @@ import random
 IMG_EXTENSIONS = ('.jpg', '.jpeg', '.png', '.ppm', '.bmp', '.pgm', '.tif', '.tiff', '.webp')
 
 
+def _csv_cell(text):
+    """A CSV cell as pandas.read_csv would hand it to the reference: integers stay integers, anything else is text."""
+    t = text.strip()
+    try:
+        return int(t)
+    except ValueError:
+        return t
+
+
 class NeustonDataset(object):
     def __init__(self, src, minimum_images_per_class=1, maximum_images_per_class=None, transforms=None, images_perclass=None):
         self.src = src
@@ -85,14 +94,68 @@ class NeustonDataset(object):
         self.transforms = transforms      # dict(flip=..., resize=..., img_norm=...) -- consumed by train_loop.ImageBatcher
 
     @classmethod
-    def fetch_images_perclass(cls, src):
-        """Sub-folders of ``src`` are the classes (neuston_data.py:55-70)."""
-        if not os.path.isdir(src):
-            raise NotImplementedError('dataset-combining config files (SRC as a CSV) are not supported; pass a directory')
+    def fetch_images_perclass(cls, src, include_exclude_rename=None):
+        """Sub-folders of ``src`` are the classes (neuston_data.py:55-70); with ``include_exclude_rename`` the classes of
+        that one dataset are kept (1) / dropped (0) / renamed-merged (any other value) (:73-89); a FILE ``src`` is the
+        dataset-combining CSV (:91-139): first column = class names, every other column = one dataset directory
+        (``priority:path`` or ``path``), cells = 1 / 0 / new name."""
+        if os.path.isdir(src) and include_exclude_rename is None:
+            out = {}
+            for sub in sorted(d.name for d in os.scandir(src) if d.is_dir()):
+                files = sorted(f for f in os.listdir(os.path.join(src, sub)) if os.path.splitext(f)[1] in IMG_EXTENSIONS)
+                out[sub] = [os.path.join(src, sub, f) for f in files]
+            return out
+        if os.path.isdir(src):
+            out = cls.fetch_images_perclass(src)
+            for key, mode in include_exclude_rename:
+                if mode == 1 or mode == '1':
+                    continue
+                if (mode == 0 or mode == '0') and key in out:
+                    del out[key]
+                else:                                           # rename / merge
+                    if key not in out:
+                        continue
+                    if mode in out:
+                        out[mode].extend(out[key])
+                    else:
+                        out[mode] = out[key]
+                    del out[key]
+            return out
+        # dataset-combining config file
+        import csv
+        with open(src, newline='') as f:
+            rows = list(csv.reader(f))
+        cols, index = rows[0][1:], [r[0] for r in rows[1:]]
+        by_priority = []
+        for ci, col in enumerate(cols):
+            parts = col.split(':', 1)
+            priority, dataset = (int(parts[0]), parts[1]) if len(parts) == 2 else (0, parts[0])
+            cells = [_csv_cell(r[ci + 1]) for r in rows[1:]]
+            by_priority.append((priority, dataset, cls.fetch_images_perclass(dataset, include_exclude_rename=zip(index, cells))))
+        priorities = [p for p, _, _ in by_priority]
+        priorities = set(max(priorities) + 1 if p == 0 else p for p in priorities)    # unprioritised datasets go last
+        # NOTE upstream builds this as a GENERATOR and iterates it once per priority level (neuston_data.py:114,127-128):
+        # it is exhausted after the first (lowest-numbered) level, so datasets of later levels never contribute.  Kept
+        # as is -- the drop-in contract is "same dataset as the reference on the same inputs" (pinned by
+        # tests/golden/dataset_golden.json, recorded from the reference's own class).
+        stream = (((max(priorities) if p == 0 else p), d, i) for p, d, i in by_priority)
+
+        def extend(d1, d2):
+            for key in d2:
+                if key in d1:
+                    d1[key].extend(d2[key])
+                else:
+                    d1[key] = d2[key]
+
         out = {}
-        for sub in sorted(d.name for d in os.scandir(src) if d.is_dir()):
-            files = sorted(f for f in os.listdir(os.path.join(src, sub)) if os.path.splitext(f)[1].lower() in IMG_EXTENSIONS)
-            out[sub] = [os.path.join(src, sub, f) for f in files]
+        for level in sorted(priorities):
+            level_ipc = {}
+            for p, _, ipc in stream:
+                if p == level:
+                    extend(level_ipc, ipc)
+            for key in level_ipc:
+                random.shuffle(level_ipc[key])
+            extend(out, level_ipc)
         return out
 
     @property

@@ -91,6 +91,19 @@ def argparse_nn_runtimeparams(args, classifier=None):
         args.outdir = args.outdir.format(RUN_DATE=date_str, RUN_ID=args.RUN_ID, MODEL_ID=model_id)
 
 
+def _engine_batch(args, arch):
+    """ROIs per network launch sequence.  The reference's ``--batch`` (default 108) sizes a DataLoader batch for a 2019
+    GPU; a B200 needs ~1k ROIs in flight to fill 148 SMs, so the default is raised to 1024 -- results do not depend on it.
+    An explicit ``--batch`` (or IFCB_RUN_BATCH) is honoured."""
+    env = os.environ.get('IFCB_RUN_BATCH')
+    if env:
+        return max(int(env), 16)
+    if args.batch_size != 108:
+        return max(args.batch_size, 16)
+    # one activation buffer per layer: keep the deep / wide families within a few tens of GB of HBM
+    return {'inception_v3': 1024, 'resnet18': 1024, 'resnet34': 1024, 'resnet50': 1024, 'resnet101': 512, 'resnet152': 512}.get(arch, 256)
+
+
 def do_run(args, classifier=None):
     import torch
     from . import ifcb_io, results, sharding
@@ -163,47 +176,74 @@ def do_run(args, classifier=None):
     img_norm = parse_imgnorm(hp.img_norm) if getattr(hp, 'img_norm', None) else None
     eng = BinClassifier(hp.MODEL, classifier.model.state_dict(), img_norm=img_norm,
                         transform_input=classifier.model.transform_input, device=torch.device('cuda', local_rank),
-                        batch_cap=max(args.batch_size, 16), dtype=args.dtype)
-    # Host pipeline around the GPU: bin ingest (file read + C++ .adc parse) runs `depth` bins ahead on I/O threads and the
-    # result files are written behind it, so that the GPU path (~33 ms per 2048-ROI bin) is not serialised with
-    # ~14 ms of ingest and the .json / .mat encoding of the previous bin.
+                        batch_cap=_engine_batch(args, hp.MODEL), dtype=args.dtype)
+    # Host pipeline around the GPU: bin ingest (.roi read straight into a slot of a PINNED ring + C++ .adc parse) runs
+    # `depth` bins ahead on I/O threads, the upload is an asynchronous DMA from the slot, and the result files are written
+    # behind the GPU by the same pool with a bounded number of writes in flight (each holds one score matrix).
     import collections
     import concurrent.futures as cf
+    import queue
     error_bins, n_bins, n_rois, t0 = [], 0, 0, time.time()
     work = [(base, pid) for base, pid in todo if base in mine]
+    depth, max_pending = 2, 4
+    orientation = os.environ.get('IFCB_ROI_ORIENTATION', 'hw')
+    ring = queue.Queue()
+    for _ in range(depth + 1):
+        ring.put([torch.empty(32 << 20, dtype=torch.uint8).pin_memory()])
 
     def load(base, pid):
-        rb = ifcb_io.RawBin(base)
-        rb.pid.namespace = pid.namespace
-        return rb
-
-    def save(rb, scores, top1):
-        for of in args.outfile:
-            results.save_run_results(rb.pids, scores, hp.classes, args.cmd_timestamp, args.outdir, of,
-                                     getattr(hp, 'model_id', None), rb.pid, output_classes=top1)
-
-    pool = cf.ThreadPoolExecutor(max_workers=max(2, args.loaders))
-    ahead, writes, nxt, depth = collections.deque(), [], 0, 2
-    for base, pid in work:
-        while len(ahead) < depth and nxt < len(work):
-            ahead.append(pool.submit(load, *work[nxt]))
-            nxt += 1
+        slot = ring.get()
         try:
-            rb = ahead.popleft().result()
-            if len(rb) == 0:
-                error_bins.append((str(pid), 'AssertionError', 'Bin is Empty'))
-                continue
-            scores, top1 = eng.classify_bin(rb.roi, rb.offsets, rb.heights, rb.widths)
-            writes.append((str(pid), len(rb), pool.submit(save, rb, scores.copy(), top1.copy())))
-        except Exception as e:      # per-bin isolation, as the reference
-            error_bins.append((str(pid), type(e).__name__, str(e)))
-    for name, n, w in writes:
+            def into(nbytes):
+                if nbytes + 16 > slot[0].numel():
+                    slot[0] = torch.empty(int(nbytes * 1.25) + 16, dtype=torch.uint8).pin_memory()
+                return slot[0].numpy()
+            rb = ifcb_io.RawBin(base, into=into, orientation=orientation)
+            rb.pid.namespace = pid.namespace
+            rb.roi_t = slot[0][:rb.roi.shape[0]]              # the pinned tensor behind rb.roi
+            return rb, slot
+        except Exception:
+            ring.put(slot)
+            raise
+
+    def save(pids, bin_pid, scores, top1):
+        for of in args.outfile:
+            results.save_run_results(pids, scores, hp.classes, args.cmd_timestamp, args.outdir, of,
+                                     getattr(hp, 'model_id', None), bin_pid, output_classes=top1)
+
+    def collect(item):
+        nonlocal n_bins, n_rois
+        name, n, w = item
         try:
             w.result()
             n_bins += 1
             n_rois += n
         except Exception as e:
             error_bins.append((name, type(e).__name__, str(e)))
+
+    pool = cf.ThreadPoolExecutor(max_workers=max(2, args.loaders))
+    ahead, writes, nxt = collections.deque(), collections.deque(), 0
+    for base, pid in work:
+        while len(ahead) < depth and nxt < len(work):
+            ahead.append(pool.submit(load, *work[nxt]))
+            nxt += 1
+        slot = None
+        try:
+            rb, slot = ahead.popleft().result()
+            if len(rb) == 0:
+                error_bins.append((str(pid), 'AssertionError', 'Bin is Empty'))
+                continue
+            scores, top1 = eng.classify_bin(rb.roi_t, rb.offsets, rb.heights, rb.widths)
+            writes.append((str(pid), len(rb), pool.submit(save, rb.pids, rb.pid, scores.copy(), top1.copy())))
+        except Exception as e:      # per-bin isolation, as the reference
+            error_bins.append((str(pid), type(e).__name__, str(e)))
+        finally:
+            if slot is not None:
+                ring.put(slot)      # classify_bin has synchronised: the DMA out of the slot is complete
+        while len(writes) > max_pending:
+            collect(writes.popleft())
+    while writes:
+        collect(writes.popleft())
     pool.shutdown()
     summary = dict(rank=rank, n_bins=n_bins, n_rois=n_rois, seconds=time.time() - t0, error_bins=error_bins)
     allsum = sharding.gather_summary(summary, world)
@@ -229,9 +269,8 @@ def _run_images(args, classifier, filter_mode, keywords, rank, world, local_rank
     from . import results
     from .engine import BinClassifier
     from .neuston_data import IMG_EXTENSIONS, load_gray
-    from .preprocess import parse_imgnorm
     hp = classifier.hparams
-    ok_ext = lambda p: p.lower().endswith(IMG_EXTENSIONS)
+    ok_ext = lambda p: p.endswith(IMG_EXTENSIONS)             # case-sensitive, as the reference (neuston_net.py:283-292)
     paths = []
     if os.path.isdir(args.SRC):
         for pardir, _, imgs in os.walk(args.SRC):
@@ -246,10 +285,12 @@ def _run_images(args, classifier, filter_mode, keywords, rank, world, local_rank
     elif filter_mode == 'OUT':
         paths = [p for p in paths if not any(k in p for k in keywords)]
     assert len(paths) > 0, 'No images to process'
+    all_paths = paths
     paths = paths[rank::world] if world > 1 else paths          # multi-GPU: each rank takes a stride of the list
-    img_norm = parse_imgnorm(hp.img_norm) if getattr(hp, 'img_norm', None) else None
-    B = max(args.batch_size, 16)
-    eng = BinClassifier(hp.MODEL, classifier.model.state_dict(), img_norm=img_norm, transform_input=classifier.model.transform_input,
+    # The reference's ImageDataset (neuston_data.py:386-388) is Resize + ToTensor only -- NO Normalize, even for a model
+    # trained with --img-norm; kept as is so that scores match upstream (recorded in DESIGN.md).
+    B = _engine_batch(args, hp.MODEL)
+    eng = BinClassifier(hp.MODEL, classifier.model.state_dict(), img_norm=None, transform_input=classifier.model.transform_input,
                         device=torch.device('cuda', local_rank), batch_cap=B, dtype=args.dtype, max_rois=B)
     scores = []
     with cf.ThreadPoolExecutor(max_workers=max(1, args.loaders)) as pool:
@@ -262,17 +303,21 @@ def _run_images(args, classifier, filter_mode, keywords, rank, world, local_rank
             roi = np.concatenate([im.reshape(-1) for im in imgs])
             s, _ = eng.classify_bin(roi, offs, hs, ws)
             scores.append(s.copy())
-    scores = np.concatenate(scores)
+    scores = np.concatenate(scores) if scores else np.zeros((0, eng.n_classes), np.float32)
+    if world > 1:                                                  # one result file, as the reference: rank 0 re-interleaves the strides
+        parts = [None] * world
+        torch.distributed.all_gather_object(parts, scores)
+        if rank != 0:
+            return []
+        scores = np.zeros((len(all_paths), eng.n_classes), np.float32)
+        for r, part in enumerate(parts):
+            scores[r::world] = part
+        paths = all_paths
     outs = []
     for of in args.outfile:
-        of_r = of
-        if world > 1:                                              # every rank classified its own stride of the list
-            stem, ext = os.path.splitext(of)
-            of_r = '%s.rank%d%s' % (stem, rank, ext)
-        outs.append(results.save_run_results(paths, scores, hp.classes, args.cmd_timestamp, args.outdir, of_r, getattr(hp, 'model_id', None),
+        outs.append(results.save_run_results(paths, scores, hp.classes, args.cmd_timestamp, args.outdir, of, getattr(hp, 'model_id', None),
                                              args.SRC))
-    if rank == 0:
-        print('RUN IS DONE')
+    print('RUN IS DONE')
     return outs
 
 

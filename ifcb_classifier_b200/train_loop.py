@@ -96,6 +96,7 @@ def save_validation_results(outfile, series, args, epoch, train_ds, val_ds, inpu
     """SaveValidationResults.on_validation_end (neuston_callbacks.py:20-156): .mat / .json / .h5 outputs."""
     import json
     labels = args.classes
+    input_classes = np.asarray(input_classes)
     output_classes = np.argmax(outputs, axis=1)
     stats = _validation_stats(input_classes, output_classes, len(labels))
     base = lambda p: os.path.splitext(os.path.basename(p))[0]
@@ -109,7 +110,9 @@ def save_validation_results(outfile, series, args, epoch, train_ds, val_ds, inpu
     optional['classes_by_count'] = sorted(range(len(labels)), key=lambda i: optional['counts_perclass'][i], reverse=True)
     res = dict(model_id=args.model_id, timestamp=args.cmd_timestamp, class_labels=labels, input_classes=input_classes,
                output_classes=output_classes)
-    res.update({k: v for k, v in optional.items() if k in series})
+    res.update({k: v for k, v in optional.items() if k in series and k != 'train_counts_perclass'})
+    if 'train_counts_perclass' in series:            # upstream writes the VALIDATION counts under this request (neuston_callbacks.py:100)
+        res['val_counts_perclass'] = vc
     outfile = os.path.join(args.outdir, outfile).format(epoch=epoch)
     os.makedirs(os.path.dirname(outfile) or '.', exist_ok=True)
     if outfile.endswith('.json'):
@@ -120,13 +123,15 @@ def save_validation_results(outfile, series, args, epoch, train_ds, val_ds, inpu
         idx_data = ['input_classes', 'output_classes', 'training_classes'] + ['classes_by_' + s for s in 'f1 recall precision count'.split()]
         str_data = ['class_labels', 'image_fullpaths', 'image_basenames', 'training_image_fullpaths', 'training_image_basenames']
         out = {}
-        for k, v in res.items():
-            if k in idx_data:
-                out[k] = np.asarray(v).astype('u4') + 1            # MATLAB indices are 1-based
+        for k, v in res.items():                                   # same dispatch ORDER as upstream (:129-134): arrays first, so the
+            if isinstance(v, np.ndarray):                          # 0-based input/output_classes arrays are stored as float32 and only
+                out[k] = v.astype('f4')                            # list-typed index series get the 1-based MATLAB shift
+            elif isinstance(v, np.float64):
+                out[k] = v.astype('f4')
             elif k in str_data:
                 out[k] = np.asarray(v, dtype='object')
-            elif isinstance(v, (np.ndarray, np.floating)):
-                out[k] = np.asarray(v).astype('f4')
+            elif k in idx_data:
+                out[k] = np.asarray(v).astype('u4') + 1
             else:
                 out[k] = v
         savemat(outfile, out, do_compression=True)

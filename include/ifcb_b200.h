@@ -104,6 +104,10 @@ int ifcb_plan_destroy(ifcb_plan* plan);
 /* Launches every layer for `batch` images (batch <= the capacity the layers
  * were created with) on `stream`. */
 int ifcb_plan_run(ifcb_plan* plan, int batch, void* stream);
+/* Same, but the head writes its rows at `out_row` of the score / logit / top-1 buffers (which the caller
+ * allocated with >= out_row + batch rows): the batches of one bin land side by side, so test_epoch_end's
+ * concatenation (neuston_models.py:159-180) needs no copy and a bin leaves the device in ONE transfer. */
+int ifcb_plan_run_at(ifcb_plan* plan, int batch, int out_row, void* stream);
 /* Runs layers [first, last) only (layer-level tests, profiling). */
 int ifcb_plan_run_range(ifcb_plan* plan, int first, int last, int batch, void* stream);
 int ifcb_plan_num_layers(const ifcb_plan* plan);

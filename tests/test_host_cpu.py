@@ -321,7 +321,7 @@ def test_image_batcher_indices_are_a_distributed_partition():
 
 def test_validation_results_files(tmp_path):
     """train_loop.save_validation_results (reference SaveValidationResults, neuston_callbacks.py:20-156): chosen series only,
-    1-based class indices in .mat, confusion matrix / F1 from the validation scores."""
+    1-based list-typed class indices in .mat, confusion matrix / F1 from the validation scores."""
     from scipy.io import loadmat
     from ifcb_classifier_b200.train_loop import save_validation_results
 
@@ -337,7 +337,8 @@ def test_validation_results_files(tmp_path):
     series = 'training_image_basenames training_classes image_basenames input_classes output_scores confusion_matrix counts_perclass f1_perclass f1_weighted f1_macro'.split()
     p = save_validation_results('results.mat', series, args, 3, train, val, np.array([0, 1, 2, 2]), scores, val.images)
     m = loadmat(p)
-    assert m['input_classes'].ravel().tolist() == [1, 2, 3, 3] and m['output_classes'].ravel().tolist() == [1, 2, 3, 1]
+    # upstream stores ndarray series as float32 unshifted (neuston_callbacks.py:130); only list-typed index series are 1-based
+    assert m['input_classes'].ravel().tolist() == [0, 1, 2, 2] and m['output_classes'].ravel().tolist() == [0, 1, 2, 0]
     assert m['confusion_matrix'].tolist() == [[1, 0, 0], [0, 1, 0], [1, 0, 1]]
     assert m['counts_perclass'].ravel().tolist() == [3, 3, 4] and m['training_classes'].ravel().tolist() == [1, 1, 2, 2, 3, 3]
     assert [str(s[0]) for s in m['image_basenames'].ravel()] == ['v0', 'v1', 'v2', 'v3']
