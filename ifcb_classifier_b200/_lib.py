@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(HERE, 'libifcb_b200.so')
 
 IFCB_OUT_F32_NCHW, IFCB_OUT_BF16_NCHW, IFCB_OUT_U8_GRAY = 0, 1, 2
 IFCB_PASS_PILLOW12, IFCB_PASS_HV = 0, 1
+IFCB_PRE_BAD_TABLE, IFCB_PRE_TOO_LARGE = 1, 2
 IFCB_STEM_IN_U8_GRAY, IFCB_STEM_IN_F32_NCHW = 0, 1
 IFCB_POOL_MAX, IFCB_POOL_AVG_AFFINE = 0, 1
 IFCB_MAX_SEGMENTS = 4
@@ -96,7 +97,7 @@ _SIGNATURES = {
     'ifcb_preprocess': (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_int, C.c_int, C.c_int, C.c_int,
                                   C.POINTER(C.c_float), C.POINTER(C.c_float),
-                                  C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+                                  C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     'ifcb_plan_create': (C.c_int, [C.POINTER(C.c_void_p)]),
     'ifcb_plan_destroy': (C.c_int, [C.c_void_p]),
     'ifcb_plan_run': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),

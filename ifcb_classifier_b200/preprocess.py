@@ -26,12 +26,14 @@ def parse_imgnorm(img_norm_arg):
 
 
 def preprocess_rois(packed, offsets, heights, widths, R, img_norm=None, out_mode=OUT_F32_NCHW,
-                    out=None, max_h=FRAME_H, max_w=FRAME_W, pass_rule=PASS_PILLOW12):
+                    out=None, max_h=FRAME_H, max_w=FRAME_W, pass_rule=PASS_PILLOW12, status=None):
     """Resizes/normalises ``n`` ROIs on the GPU.
 
     packed   uint8 cuda tensor: raw ``.roi`` bytes
     offsets  int64 cuda tensor [n] (START_BYTE), heights/widths int32 cuda tensors [n]
     img_norm None, the reference's ``[str, str]``, or ``(mean[3], std[3])``
+    status   optional int32 cuda tensor [1]: flags of ROIs the kernel refused (table entry outside the packed bytes,
+             or larger than max_h / max_w): their output slot is zeroed, ``check_status`` raises
     Returns a cuda tensor: float32/bfloat16 [n,3,R,R] or uint8 [n,R,R].
     """
     if not packed.is_cuda:
@@ -54,6 +56,17 @@ def preprocess_rois(packed, offsets, heights, widths, R, img_norm=None, out_mode
     stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
     rc = _lib.lib().ifcb_preprocess(packed.data_ptr(), packed.numel(), offsets.data_ptr(), heights.data_ptr(),
                                     widths.data_ptr(), n, int(max_h), int(max_w), int(R), mean_p, std_p,
-                                    int(out_mode), out.data_ptr(), int(pass_rule), stream)
+                                    int(out_mode), out.data_ptr(), int(pass_rule),
+                                    status.data_ptr() if status is not None else None, stream)
     _lib.check(rc, 'preprocess')
     return out
+
+
+def check_status(status):
+    """Raises if a preprocess launch refused a ROI (reads the device word: synchronises)."""
+    v = int(status.item())
+    if v:
+        status.zero_()
+        why = [t for b, t in ((_lib.IFCB_PRE_BAD_TABLE, 'a ROI table entry points outside the .roi bytes'),
+                              (_lib.IFCB_PRE_TOO_LARGE, 'a ROI is larger than the declared max_h / max_w')) if v & b]
+        raise RuntimeError('preprocess: ' + '; '.join(why))

@@ -96,7 +96,11 @@ class TrainNet(object):
     """
 
     def __init__(self, arch, state_dict, batch, device='cuda', dtype='bf16', lr=1e-3, betas=(0.9, 0.999), eps=1e-8,
-                 dropout=True, seed=0, R=None, bucket_mb=32, keep_dy=False, window=True, transform_input=False):
+                 dropout=True, seed=0, R=None, bucket_mb=32, keep_dy=False, window=True, transform_input=False, share=None):
+        """``share``: another TrainNet of the same architecture whose parameter / gradient / Adam arenas, BatchNorm running
+        statistics and step counter this one uses instead of allocating its own -- a second plan for another batch size over
+        the SAME model (the short last batch of an epoch, neuston_models.py:80-86 trains on it as is).  The two plans keep
+        separate 16-bit operand copies: call ``repack()`` on the one about to step after the other has stepped."""
         self.arch, self.batch, self.device = arch, int(batch), torch.device(device)
         if self.device.type != 'cuda':
             raise RuntimeError('TrainNet: a CUDA device is required (there is no CPU path)')
@@ -108,7 +112,8 @@ class TrainNet(object):
         # torchvision Inception3.transform_input (set by the factory when pretrained weights are requested, inception.py:95-101)
         self.transform_input = bool(transform_input) and arch == 'inception_v3'
         self.keep_dy = bool(keep_dy)        # tests: keep d(activation) next to d(conv output) instead of overwriting it
-        self.step_count = 0
+        self._share = share
+        self._steps = share._steps if share is not None else [0]      # optimizer step counter (shared between plans of one model)
         self._reducer = None
         self.lib = _lib.lib()
         sd = {k: v.detach().cpu() for k, v in state_dict.items()}
@@ -118,7 +123,7 @@ class TrainNet(object):
         self.cdtype, self.tdtype = self.fp.cdtype, self.fp.tdtype
         total = sum(((v.numel() * (3 if v.dim() == 4 and v.shape[1] == 3 else 1) + 63) // 64) * 64
                     for v in sd.values() if v.is_floating_point())
-        self.params = torch.zeros(total, dtype=torch.float32, device=self.device)
+        self.params = share.params if share is not None else torch.zeros(total, dtype=torch.float32, device=self.device)
         self._cursor = 0
         self.plist = []                 # _Param in forward order
         self.buffers = {}               # running_mean / running_var / num_batches_tracked
@@ -142,17 +147,31 @@ class TrainNet(object):
         elif arch in RESNET_CFG:
             _build_resnet_train(self, sd, arch)
         else:
+            if arch in ('alexnet', 'squeezenet') or arch.startswith(('vgg', 'densenet')):
+                raise NotImplementedError('TRAIN on the B200 kernels covers inception_v3 and resnet18/34/50/101/152; %s has a RUN plan only' % arch)
             raise KeyError('model unknown!')
         self.n_params = self._cursor
-        self.params = self.params[:self.n_params]
-        self.grads = torch.zeros_like(self.params)
-        self.m = torch.zeros_like(self.params)
-        self.v = torch.zeros_like(self.params)
+        if share is not None:
+            assert share.arch == arch and share.n_params == self.n_params, 'share: different model'
+            self.grads, self.m, self.v = share.grads, share.m, share.v
+        else:
+            self.params = self.params[:self.n_params]
+            self.grads = torch.zeros_like(self.params)
+            self.m = torch.zeros_like(self.params)
+            self.v = torch.zeros_like(self.params)
         self._plan_grad_borders()
         self._finalize(int(bucket_mb) << 20)
         self.repack()
 
     # ---- plumbing ---------------------------------------------------------------------------
+    @property
+    def step_count(self):
+        return self._steps[0]
+
+    @step_count.setter
+    def step_count(self, v):
+        self._steps[0] = int(v)
+
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
@@ -163,7 +182,8 @@ class TrainNet(object):
         n = init.numel()
         off = self._cursor
         assert off + n <= self.params.numel(), 'parameter arena overflow'
-        self.params[off:off + n].copy_(init.reshape(-1).float())
+        if self._share is None:
+            self.params[off:off + n].copy_(init.reshape(-1).float())
         self._cursor = ((off + n + 3) // 4) * 4                 # 16-byte aligned slices
         p = _Param(self, name, off, init.shape, kind, meta)
         self.plist.append(p)
@@ -255,10 +275,14 @@ class TrainNet(object):
         pw = self._param(conv + '.weight', master, 'stem' if stem else 'conv', dict(Ci=Ci, kh=kh, kw=kw, stem=stem_geom))
         pg = self._param(bn + '.weight', sd[bn + '.weight'], 'vec')
         pb = self._param(bn + '.bias', sd[bn + '.bias'], 'vec')
-        rm = self._f32(Co); rm.copy_(sd[bn + '.running_mean'])
-        rv = self._f32(Co); rv.copy_(sd[bn + '.running_var'])
+        if self._share is not None:
+            rm, rv = self._share.buffers[bn + '.running_mean'], self._share.buffers[bn + '.running_var']
+            self.buffers[bn + '.num_batches_tracked'] = self._share.buffers[bn + '.num_batches_tracked']
+        else:
+            rm = self._f32(Co); rm.copy_(sd[bn + '.running_mean'])
+            rv = self._f32(Co); rv.copy_(sd[bn + '.running_var'])
+            self.buffers[bn + '.num_batches_tracked'] = sd.get(bn + '.num_batches_tracked', torch.zeros((), dtype=torch.long)).clone()
         self.buffers[bn + '.running_mean'], self.buffers[bn + '.running_var'] = rm, rv
-        self.buffers[bn + '.num_batches_tracked'] = sd.get(bn + '.num_batches_tracked', torch.zeros((), dtype=torch.long)).clone()
         mean, invstd = self._f32(Co), self._f32(Co)
         ones, zeros = torch.ones(Co), torch.zeros(Co)
         li = len(self.fp.layer_names)

@@ -208,17 +208,33 @@ def do_training(args):
     os.makedirs(chk_dir, exist_ok=True)
     log_rows, best_val, best_epoch, best_path, wait = [], np.inf, 0, None, 0
     hp = {k: v for k, v in vars(args).items()}
+    tail_nets = {}                                                # plans for the short last batch of an epoch (shared arenas)
     for epoch in range(args.emax):
         t0 = time.time()
         agg_train_loss, losses = 0.0, []
         for x, y, _ in train_loader:
             n = int(x.shape[0])
-            if n < B:                                             # fixed-batch plan: wrap the short last batch around
-                reps = (B + n - 1) // n
-                x, y = x.repeat(reps, 1, 1, 1)[:B], y.repeat(reps)[:B]
+            if n < B:
+                # the reference trains on the short last batch as it is (BN statistics and the logged loss are those of the
+                # n samples): a second plan of that size over the SAME parameter / Adam arenas
+                if n not in tail_nets:
+                    tail_nets[n] = TrainNet(args.MODEL, classifier.model.state_dict(), n, device=dev, dtype=getattr(args, 'train_dtype', 'bf16'),
+                                            seed=args.seed, R=args.resize, transform_input=classifier.model.transform_input, share=net)
+                tail = tail_nets[n]
+                tail.repack()                                     # its 16-bit operands are stale: the main plan has stepped since
+                losses.append(tail.step(x, y).clone())
+                net.repack()
+                continue
             losses.append(net.step(x, y).clone())
         agg_train_loss = float(torch.stack(losses).sum()) if losses else 0.0       # one sync per epoch (reference: .item() per step)
-        # ---- validation (rank 0's replica; eval mode = the RUN plan with the current weights) ----
+        # ---- validation (eval mode = the RUN plan with the current weights).  Data parallel: every rank holds the same
+        # parameters but its own BatchNorm running statistics; rank 0's are broadcast first (DDP broadcast_buffers), so every
+        # rank validates the same model, and rank 0's val_loss decides best / early stop for all ranks (no rank can leave the
+        # epoch loop alone and strand the others in the gradient all-reduce).
+        if world > 1:
+            for k_, b_ in net.buffers.items():
+                if b_.is_cuda:
+                    torch.distributed.broadcast(b_, 0)
         sd = net.state_dict()
         ev = CompiledNet(args.MODEL, sd, B, in_kind='f32', R=args.resize, device=dev, dtype=getattr(args, 'dtype', 'fp16'),
                          transform_input=classifier.model.transform_input)
@@ -234,6 +250,10 @@ def do_training(args):
         del ev
         outputs, input_classes = np.concatenate(outs), np.concatenate(ins)
         stats = _validation_stats(input_classes, np.argmax(outputs, 1), len(args.classes))
+        if world > 1:
+            vl = torch.tensor([val_loss], dtype=torch.float64, device=dev)
+            torch.distributed.broadcast(vl, 0)
+            val_loss = float(vl.item())
         is_best = val_loss < best_val
         if is_best:
             best_val, best_epoch, wait = val_loss, epoch, 0
@@ -258,6 +278,8 @@ def do_training(args):
             break
     if rank == 0:
         import shutil
+        if best_path is None:
+            raise RuntimeError('TRAIN: no epoch produced a finite val_loss (last: %r) -- no checkpoint to keep as %s.ptl' % (val_loss, args.model_id))
         shutil.copyfile(best_path, os.path.join(args.outdir, args.model_id + '.ptl'))
         if args.epochs_log:
             cols = ['epoch', 'best', 'train_loss', 'val_loss', 'f1_macro', 'f1_weighted']

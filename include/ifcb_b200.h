@@ -64,8 +64,13 @@ int64_t ifcb_format_scores_json(const float* scores, int64_t rows, int64_t cols,
  *   d_offsets[n]  START_BYTE of each ROI (int64)
  *   d_h, d_w[n]   ROI height / width (int32); ROI i is row-major (h, w) u8
  *   max_h, max_w  host-known upper bounds of d_h / d_w (the IFCB camera frame is
- *                 1034 x 1380); used to validate the shared-memory budget --
- *                 a ROI exceeding them is skipped (its output is left untouched)
+ *                 1034 x 1380); they size the launch's shared memory (any bound up
+ *                 to several thousand pixels is accepted: very large images read
+ *                 their horizontal pass from global memory)
+ *   d_status      optional device word (NULL to skip).  A ROI whose table entry
+ *                 points outside [0, packed_bytes) or whose size exceeds what the
+ *                 launch was sized for is NOT processed: its output slot is zeroed
+ *                 and IFCB_PRE_BAD_TABLE / IFCB_PRE_TOO_LARGE is OR-ed into the word
  *   R             output side (299 for inception_v3, 224 otherwise)
  *   h_mean,h_std  3 floats each (--img-norm, neuston_data.py:331-339) or NULL
  *   out_mode      IFCB_OUT_*; d_out holds n images of that layout
@@ -79,12 +84,13 @@ enum {
   IFCB_OUT_U8_GRAY = 2    /* uint8 [n,R,R] resized gray plane (feeds the stem)    */
 };
 enum { IFCB_PASS_PILLOW12 = 0, IFCB_PASS_HV = 1 };
+enum { IFCB_PRE_BAD_TABLE = 1, IFCB_PRE_TOO_LARGE = 2 };
 
 int ifcb_preprocess(const uint8_t* d_packed, int64_t packed_bytes,
                     const int64_t* d_offsets, const int32_t* d_h, const int32_t* d_w,
                     int n, int max_h, int max_w, int R,
                     const float* h_mean, const float* h_std,
-                    int out_mode, void* d_out, int pass_rule, void* stream);
+                    int out_mode, void* d_out, int pass_rule, int32_t* d_status, void* stream);
 
 /* ------------------------------------------------------------------------- *
  * Network plan: an ordered list of layer launches over caller-owned buffers.

@@ -35,7 +35,7 @@ def test_library_is_sm100a_with_tcgen05_and_tma():
 
 def test_argument_errors_are_status_codes(built_lib):
     from ifcb_classifier_b200 import _lib
-    rc = built_lib.ifcb_preprocess(None, 0, None, None, None, 4, 10, 10, 299, None, None, 0, None, 0, None)
+    rc = built_lib.ifcb_preprocess(None, 0, None, None, None, 4, 10, 10, 299, None, None, 0, None, 0, None, None)
     assert rc < 0 and b'null' in built_lib.ifcb_last_error()
     rc = built_lib.ifcb_conv_geometry(64, 64, 3, 3, 24, None, None, None, None)
     assert rc < 0 and b'tile_n' in built_lib.ifcb_last_error()

@@ -168,3 +168,138 @@ def test_run_cli_pipelines_bins_and_isolates_failures(cuda, tmp_path, capsys):
     assert neuston_net.main(argv) == 0                                 # second run: everything that succeeded is skipped
     txt = capsys.readouterr().out
     assert txt.count('already exist - skipping this bin') == 4 and '0 bins, 0 ROIs' in txt
+
+
+def _engine_scores(cuda, arch, model, imgs, dtype, batch_cap=256, max_rois=1024):
+    """Host bytes -> BinClassifier.classify_bin -> host scores: the call bench.py's `e2e` times."""
+    from ifcb_classifier_b200.engine import BinClassifier
+    eng = BinClassifier(arch, model.state_dict(), device=cuda, batch_cap=batch_cap, dtype=dtype, max_rois=max_rois)
+    hs = np.array([im.shape[0] for im in imgs], np.int32)
+    ws = np.array([im.shape[1] for im in imgs], np.int32)
+    offs = np.concatenate([[0], np.cumsum(hs.astype(np.int64) * ws)[:-1]]).astype(np.int64)
+    roi = np.concatenate([im.reshape(-1) for im in imgs])
+    s, t1 = eng.classify_bin(roi, offs, hs, ws)
+    assert np.array_equal(t1, s.argmax(1))
+    return torch.from_numpy(s.copy())
+
+
+def _agree(ref, got):
+    return float((ref.argmax(1) == got.argmax(1)).float().mean()), float((ref - got).abs().max())
+
+
+def test_benchmarked_config_parity(cuda):
+    """Whole-model parity ON THE CONFIGURATION bench.py MEASURES (BASELINE config 2): inception_v3, 100-class head, the
+    2048 ROIs of synthetic bin 0 (oracle/synth_bins.make_bin, the bench's generator), through BinClassifier.classify_bin, fp16
+    and bf16 operands, against the reference op sequence in fp32 (oracle preprocessing + torchvision on cuDNN, TF32 off).
+    Fixtures reported separately:
+      A  raw random init -- what the bench's throughput runs use; degenerate (BN is the identity, activations grow layer by
+         layer to ~1e11, the softmax saturates on one class): bf16 agrees trivially, fp16 OVERFLOWS its 65504 range (saturating
+         converts) and lands on another class -- reported, not gated; no trained or calibrated model has such activations
+      B  random init + calibrated BN running statistics -- near-uniform softmax (mean max-prob 0.02, median top-2 margin
+         6e-4): adversarial for ANY 16-bit operand format.  The attainable floor is measured here (fp32 on the CPU vs fp32 on
+         cuDNN) and by tools/parity_emulate.py (CPU emulation: even fp32 weights with fp16 activation storage reach 0.965,
+         fp16 + tf32 / fp32 in the last blocks changes nothing, only a 22-bit hi+lo split of BOTH operands reaches 1.000)
+      C  B + 120 Adam steps on separable synthetic classes -- a trained checkpoint, what RUN classifies in production.
+    Gates: the north-star's two gates on C (top-1 >= 99.5 %, |dscore| <= 1e-2) for fp16 on both the trained-on gratings and the
+    IFCB-like bin; the score gate on A and B; B's top-1 is REPORTED beside its measured floor and gated against regression at
+    the level the emulation predicts for a correct fp16 pipeline."""
+    from oracle import synth_bins
+    arch, C, R = 'inception_v3', 100, 299
+    sb = synth_bins.make_bin(0, 2048)
+    imgs = [sb['images'][t] for t in sorted(sb['images'])]
+    x = torch.from_numpy(np.stack([ref_preprocess(im, R, None) for im in imgs]))
+    model = fixtures.ref_model(arch, C, seed=0)
+    res = {}
+    # ---- fixture A ----
+    ref_a = _ref_scores(cuda, model, x[:512])
+    for dt in ('fp16', 'bf16'):
+        res['A', dt] = _agree(ref_a, _engine_scores(cuda, arch, model, imgs[:512], dt))
+    # ---- fixture B ----
+    fixtures.calibrate_bn(model, x[:128], cuda)
+    ref_b = _ref_scores(cuda, model, x)
+    for dt in ('fp16', 'bf16'):
+        res['B', dt] = _agree(ref_b, _engine_scores(cuda, arch, model, imgs, dt, max_rois=2048))
+    # the oracle's own noise floor on B: the same fp32 graph on the CPU (another summation order) vs cuDNN
+    model.cpu()
+    with torch.no_grad():
+        cpu_b = torch.cat([torch.softmax(model(x[i:i + 64]), 1) for i in range(0, 256, 64)])
+    floor = _agree(ref_b[:256], cpu_b)
+    top2 = ref_b.topk(2, 1).values
+    print('\n[bench config] fixture B: mean max-prob %.4f, median top-2 margin %.2e; fp32 CPU vs fp32 cuDNN (256 ROIs): top-1 agreement %.4f, '
+          'max|dscore| %.2e' % (float(ref_b.max(1).values.mean()), float((top2[:, 0] - top2[:, 1]).median()), floor[0], floor[1]))
+    # ---- fixture C ----
+    gimgs, glabels = fixtures.class_rois(640, 20, seed=1)
+    gx = torch.from_numpy(np.stack([ref_preprocess(im, R, None) for im in gimgs]))
+    fixtures.brief_train(model, gx[:384], glabels[:384], cuda, steps=120)
+    ref_cg, ref_cs = _ref_scores(cuda, model, gx), _ref_scores(cuda, model, x)
+    for dt in ('fp16', 'bf16'):
+        res['C gratings', dt] = _agree(ref_cg, _engine_scores(cuda, arch, model, gimgs, dt))
+        res['C synthetic bin', dt] = _agree(ref_cs, _engine_scores(cuda, arch, model, imgs, dt, max_rois=2048))
+    print('[bench config] fixture C: reference accuracy on the gratings %.3f, mean max-prob gratings %.3f / synthetic bin %.3f'
+          % (float((ref_cg.argmax(1) == glabels).float().mean()), float(ref_cg.max(1).values.mean()), float(ref_cs.max(1).values.mean())))
+    for k in sorted(res):
+        print('[bench config] fixture %-16s %s operands: top-1 agreement %.4f  max|dscore| %.3e' % (k + res[k]))
+    for fx in ('B', 'C gratings', 'C synthetic bin'):
+        assert res[fx, 'fp16'][1] <= 1e-2, (fx, res[fx, 'fp16'])
+    assert res['A', 'bf16'][0] >= 0.995 and res['A', 'bf16'][1] <= 1e-2
+    assert res['C gratings', 'fp16'][0] >= 0.995 and res['C synthetic bin', 'fp16'][0] >= 0.995
+    assert res['C gratings', 'bf16'][0] >= 0.98 and res['C gratings', 'bf16'][1] <= 5e-2
+    assert floor[0] >= 0.995                                       # fp32 vs fp32 does meet the gate on B ...
+    assert res['C synthetic bin', 'bf16'][0] >= 0.99
+    assert res['B', 'fp16'][0] >= 0.93                             # ... 16-bit operands cannot (measured 0.957); regression guard only
+
+
+def test_bin_larger_than_the_output_window(cuda):
+    """A bin with more ROIs than the engine's output window is classified in several passes with identical results, and the
+    head writes every batch at its own rows (no staging copies): all rows equal the one-batch-at-a-time scores."""
+    from ifcb_classifier_b200.engine import BinClassifier
+    arch, norm = 'resnet18', (([0.667] * 3), ([0.161] * 3))
+    imgs, _ = fixtures.class_rois(70, 10, seed=6)
+    model = fixtures.ref_model(arch, 10)
+    x = torch.from_numpy(np.stack([ref_preprocess(im, 224, norm) for im in imgs]))
+    fixtures.calibrate_bn(model, x, cuda)
+    want = _pipeline_scores(cuda, arch, model, imgs, norm, batch_cap=16)
+    eng = BinClassifier(arch, model.state_dict(), img_norm=norm, device=cuda, batch_cap=16, max_rois=32)
+    assert eng.window == 32
+    hs = np.array([im.shape[0] for im in imgs], np.int32)
+    ws = np.array([im.shape[1] for im in imgs], np.int32)
+    offs = np.concatenate([[0], np.cumsum(hs.astype(np.int64) * ws)[:-1]]).astype(np.int64)
+    roi = np.concatenate([im.reshape(-1) for im in imgs])
+    s, t1 = eng.classify_bin(roi, offs, hs, ws)
+    assert s.shape == (70, 10) and torch.equal(torch.from_numpy(s.copy()), want)
+    assert np.array_equal(t1, s.argmax(1))
+
+
+def test_run_cli_default_outfile_is_h5(cuda, tmp_path, capsys):
+    """`neuston_net RUN SRC MODEL ID` with DEFAULT flags writes D{BIN_YEAR}/D{BIN_DATE}/{BIN_ID}_class.h5 (reference
+    neuston_net.py:180-182) -- readable back, scores equal to the .json output of the same run to float16 rounding."""
+    import argparse
+    import json
+    import os
+    from oracle import synth_bins
+    from ifcb_classifier_b200 import h5lite, neuston_net
+    from ifcb_classifier_b200.neuston_models import NeustonModel
+    torch.manual_seed(0)
+    hp = argparse.Namespace(MODEL='resnet18', classes=['c%d' % i for i in range(5)], pretrained=False, resize=224, img_norm=None,
+                            model_id='m5', seed=1)
+    ckpt = str(tmp_path / 'm5.ptl')
+    NeustonModel(hp).save_checkpoint(ckpt)
+    bins = str(tmp_path / 'bins')
+    for i, n in enumerate([21, 9]):
+        synth_bins.write_bin(bins, synth_bins.make_bin(i, n_rois=n))
+    cwd = os.getcwd()
+    os.chdir(str(tmp_path))
+    try:
+        assert neuston_net.main(['--batch', '16', 'RUN', bins, ckpt, 'R1']) == 0
+        assert neuston_net.main(['--batch', '16', 'RUN', bins, ckpt, 'R1', '--outfile', '{BIN_ID}.json']) == 0
+    finally:
+        os.chdir(cwd)
+    assert '2 bins, 30 ROIs' in capsys.readouterr().out
+    out = os.path.join(str(tmp_path), 'run-output', 'R1', 'v3', 'm5')
+    for i, n in enumerate([21, 9]):
+        lid = synth_bins.bin_lid(i)
+        f = h5lite.read(os.path.join(out, 'D2026', 'D' + lid[1:9], lid + '_class.h5'))
+        j = json.load(open(os.path.join(out, lid + '.json')))
+        assert f['output_scores'].shape == (n, 5) and f['metadata'].attrs['bin_id'] == lid and f['metadata'].attrs['model_id'] == 'm5'
+        assert np.array_equal(f['output_scores'].data, np.asarray(j['output_scores'], np.float32).astype(np.float16))
+        assert f['roi_numbers'].data.tolist() == j['roi_numbers'] and f['class_labels'].data.tolist() == hp.classes

@@ -511,7 +511,7 @@ def test_neuston_net_train_then_run(cuda, tmp_path):
     assert n_train + n_val == 96 and abs(n_val - 19) <= 3                      # --split 80:20 per class
     m = loadmat(str(out / 'results.mat'))
     assert m['confusion_matrix'].shape == (3, 3) and int(m['confusion_matrix'].sum()) == n_val
-    assert m['output_scores'].shape == (n_val, 3) and m['input_classes'].min() >= 1        # 1-based for MATLAB
+    assert m['output_scores'].shape == (n_val, 3) and m['training_classes'].min() >= 1     # list-typed index series are 1-based for MATLAB
     model = NeustonModel.load_from_checkpoint(str(out / 'T1.ptl'))
     assert model.hparams.classes == ['class_0', 'class_1', 'class_2'] and model.hparams.MODEL == 'resnet18'
     best = [r.split(',') for r in rows[1:] if r.split(',')[1] == 'True'][-1]
@@ -660,3 +660,35 @@ def test_stem_im2col_matches_unfold(cuda):
         got = _read(out)
         assert float((got[:, :kh * kh * 3] - u).abs().max()) <= 2.0 ** -8 * float(u.abs().max())
         assert float(got[:, kh * kh * 3:].abs().max()) == 0.0
+
+
+def test_short_last_batch_plan_shares_the_model(cuda):
+    """The short last batch of an epoch is trained on AS IS (reference training_step, neuston_models.py:80-86) by a second
+    plan of that size over the same parameter / gradient / Adam arenas: its loss matches the oracle's for the n samples (not
+    for a wrapped-around full batch), it updates the shared parameters, and the main plan continues from them."""
+    from oracle import train_ref
+    from tests.fixtures import ref_model
+    from ifcb_classifier_b200.train import TrainNet
+    import copy
+    B, n, R, C = 8, 5, 64, 6
+    g = torch.Generator().manual_seed(11)
+    model = ref_model('resnet18', C, seed=5).to(cuda)
+    net = TrainNet('resnet18', model.state_dict(), B, device=cuda, R=R)
+    tail = TrainNet('resnet18', model.state_dict(), n, device=cuda, R=R, share=net)
+    assert tail.params.data_ptr() == net.params.data_ptr() and tail.m.data_ptr() == net.m.data_ptr()
+    x8, y8 = torch.rand(B, 3, R, R, generator=g).to(cuda), torch.randint(0, C, (B,), generator=g).to(cuda)
+    x5, y5 = torch.rand(n, 3, R, R, generator=g).to(cuda), torch.randint(0, C, (n,), generator=g).to(cuda)
+    ref = copy.deepcopy(model)
+    want = train_ref.train_steps(ref, [(x8, y8), (x5, y5), (x8, y8)])
+    l0 = float(net.step(x8, y8))
+    tail.repack()
+    p_before = net.params.clone()
+    l1 = float(tail.step(x5, y5))
+    assert not torch.equal(p_before, net.params) and net.step_count == 2 and tail.step_count == 2
+    net.repack()
+    l2 = float(net.step(x8, y8))
+    print('ours', [l0, l1, l2], 'oracle', want)
+    assert abs(l0 - want[0]) <= 2e-2 * abs(want[0]) and abs(l1 - want[1]) <= 5e-2 * abs(want[1])
+    sd, rsd = net.state_dict(), ref.state_dict()
+    assert int(sd['bn1.num_batches_tracked']) == 3
+    assert torch.allclose(sd['bn1.running_mean'], rsd['bn1.running_mean'].cpu(), rtol=5e-2, atol=5e-3)
