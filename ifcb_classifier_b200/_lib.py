@@ -33,7 +33,7 @@ class ConvDesc(C.Structure):
                 ('d_weight', C.c_void_p), ('d_scale', C.c_void_p), ('d_shift', C.c_void_p),
                 ('n_seg', C.c_int32), ('seg', ConvSegment * IFCB_MAX_SEGMENTS),
                 ('d_residual', C.c_void_p), ('res_ld', C.c_int32), ('res_pad_h', C.c_int32), ('res_pad_w', C.c_int32),
-                ('tile_n', C.c_int32), ('algo', C.c_int32), ('dtype', C.c_int32)]
+                ('tile_n', C.c_int32), ('algo', C.c_int32), ('dtype', C.c_int32), ('d_stats', C.c_void_p)]
 
 
 class WgradDesc(C.Structure):
@@ -117,6 +117,8 @@ _SIGNATURES = {
                                 C.c_void_p, C.c_void_p, C.c_void_p]),
     'ifcb_bn_apply': (C.c_int, [_V, _V, _V, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_int, C.c_void_p]),
+    'ifcb_bn_apply_sums': (C.c_int, [_V, _V, _V, C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     'ifcb_bn_backward': (C.c_int, [_V, _V, _V, _V, _V, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'ifcb_maxpool_fwd_train': (C.c_int, [_V, _V, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),

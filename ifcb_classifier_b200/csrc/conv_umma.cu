@@ -26,12 +26,14 @@
 // Cin <= 32, 64 bytes (32 channels, SWIZZLE_64B) -- halves the shared-memory footprint of
 // the first layers.
 //
-// Persistent, warp-specialised CTA (1 per SM, 320 threads):
-//   warp 0     TMA producer
-//   warp 1     TMEM allocator + tcgen05.mma issuer
-//   warps 2-9  epilogue: tcgen05.ld -> scale/shift (+residual) -> ReLU -> 16-bit ->
-//              swizzled smem tile -> coalesced 16-byte stores (two warps per TMEM lane
-//              quadrant, alternating 64-column groups)
+// Persistent, warp-specialised CTA (1 per SM, 448 threads):
+//   warp 0      TMA producer
+//   warp 1      TMEM allocator + tcgen05.mma issuer
+//   warps 2-13  epilogue: tcgen05.ld -> scale/shift (+residual) -> ReLU -> 16-bit ->
+//               swizzled smem tile -> coalesced 16-byte stores (three warps per TMEM lane
+//               quadrant, taking (32-column slice, accumulator) units round-robin)
+// TRAIN (STATS kernels): the epilogue also accumulates, per output channel, the sum and the sum of
+// squares of the 16-bit values it stores -- BatchNorm's batch statistics without a pass over z.
 // Warps 0/1 run their loops warp-uniformly and elect one lane only around the async
 // instructions, so descriptors and coordinates stay in uniform registers (a lane-0 branch
 // around the whole loop costs ~25 SASS instructions per tcgen05.mma, measured).
@@ -50,7 +52,7 @@ constexpr int kBlockM = 128;
 #endif
 constexpr int kEpiWarps = IFCB_EPI_WARPS;           // 3-4 per TMEM lane quadrant: the epilogue is latency-bound, TLP hides it
 constexpr int kEpiPerQuad = kEpiWarps / 4;
-constexpr int kThreads = 64 + 32 * kEpiWarps;       // 576
+constexpr int kThreads = 64 + 32 * kEpiWarps;       // 448
 constexpr int kStageTile = 2048;                    // per-warp staging tile: 32 rows x 64 B
 constexpr int kTmemCols = 512;
 constexpr int kAccBufCols = 256;
@@ -58,8 +60,19 @@ constexpr int kBarBytes = 512;
 constexpr int kMaxStages = 12;
 
 // barriers + scale/shift (2 x cout_pad floats) + one 2 KB staging tile per epilogue warp
-__host__ __device__ constexpr int epilogue_smem(int cout_pad) {
-  return kBarBytes + 8 * cout_pad + kEpiWarps * kStageTile;
+// (+ per-channel sum / sum-of-squares floats when the epilogue gathers BatchNorm statistics)
+__host__ __device__ constexpr int epilogue_smem(int cout_pad, bool stats = false) {
+  return kBarBytes + 8 * cout_pad + kEpiWarps * kStageTile + (stats ? 8 * cout_pad : 0);
+}
+
+__device__ __forceinline__ void decode_tile(const ConvKernelParams& p, int tile, int m_tiles, int& m_tile, int& n_tile) {
+  if (p.n_major) {
+    n_tile = tile / m_tiles;
+    m_tile = tile - n_tile * m_tiles;
+  } else {
+    m_tile = tile / p.n_tiles;
+    n_tile = tile - m_tile * p.n_tiles;
+  }
 }
 
 struct RowMap {           // where a GEMM row lands
@@ -118,8 +131,10 @@ constexpr uint32_t kNoRow = 0xFFFFFFFFu;
 // coalesced write-out of one staged unit: 32 rows x PPR 16-byte pieces (row pitch 64 B, chunk
 // XOR-swizzled by (row >> 1) & 3), fully unrolled.  `off` = this lane's destination row as an
 // ELEMENT offset (row * ld), kNoRow = dropped row.
-template <int PPR>
-__device__ __forceinline__ void write_out(const uint8_t* stage, int lane, uint32_t off, __nv_bfloat16* gout) {
+// STATS: this lane's PPR rows x 8 channels (the 16-bit values that go to memory) are also added into
+// acc[0..8) (sums) / acc[8..16) (sums of squares); dropped rows are skipped.
+template <int PPR, bool FP16, bool STATS>
+__device__ __forceinline__ void write_out(const uint8_t* stage, int lane, uint32_t off, __nv_bfloat16* gout, float (&acc)[16]) {
   uint4 val[PPR];
   uint32_t ro[PPR];
 #pragma unroll
@@ -129,6 +144,22 @@ __device__ __forceinline__ void write_out(const uint8_t* stage, int lane, uint32
     const int pc = idx - r * PPR;
     ro[it] = __shfl_sync(0xffffffffu, off, r);
     val[it] = *reinterpret_cast<const uint4*>(stage + r * 64 + ((pc ^ ((r >> 1) & 3)) << 4));
+  }
+  if (STATS) {
+#pragma unroll
+    for (int it = 0; it < PPR; ++it) {
+      if (ro[it] != kNoRow) {
+        const uint32_t w[4] = {val[it].x, val[it].y, val[it].z, val[it].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = unpack_act2(w[e], FP16 ? 1 : 0);
+          acc[2 * e] += f.x;
+          acc[2 * e + 1] += f.y;
+          acc[8 + 2 * e] = fmaf(f.x, f.x, acc[8 + 2 * e]);
+          acc[8 + 2 * e + 1] = fmaf(f.y, f.y, acc[8 + 2 * e + 1]);
+        }
+      }
+    }
   }
 #pragma unroll
   for (int it = 0; it < PPR; ++it) {
@@ -146,15 +177,17 @@ __device__ __forceinline__ void write_out(const uint8_t* stage, int lane, uint32
 // destination rows travel as 32-bit element offsets so that the write-out loop is
 // shuffle + ld.shared + one wide multiply-add + store.
 // ---------------------------------------------------------------------------------------
-template <bool FP16>
+template <bool FP16, bool STATS>
 __device__ __forceinline__ void epilogue_tile(const ConvKernelParams& p, uint32_t tmem_acc, int tile_row0, int n_lo, int lane,
-                                              int sub, uint8_t* stage, const float* s_scale, const float* s_shift) {
+                                              int sub, uint8_t* stage, const float* s_scale, const float* s_shift,
+                                              float (&sacc)[3][16]) {
   const int n_hi = n_lo + p.tile_n;
   const int ms_shift = p.m_sub == 1 ? 0 : p.m_sub == 2 ? 1 : 2;
   uint4* srow = reinterpret_cast<uint4*>(stage + lane * 64);
   const int sw = (lane >> 1) & 3;
   int next = sub;                                    // tile-wide index of this warp's next unit
   int ubase = 0;                                     // tile-wide index of the segment's first unit
+  int slot = 0;                                      // STATS: how many units this warp has done in this tile (<= 3: one segment)
   for (int si = 0; si < p.n_seg; ++si) {
     const int g_lo = max(n_lo, p.seg_begin[si]), g_hi = min(n_hi, p.seg_end[si]);
     if (g_lo >= g_hi) continue;
@@ -231,11 +264,56 @@ __device__ __forceinline__ void epilogue_tile(const ConvKernelParams& p, uint32_
         srow[3 ^ sw] = o[3];
       }
       __syncwarp();
-      if (wide) write_out<4>(stage, lane, off_j, seg_out + gi * 32);
-      else write_out<2>(stage, lane, off_j, seg_out + gi * 32);
+      if (STATS) {
+        // the unit -> slot assignment is the same in every tile of a column tile, so the per-lane partial sums stay in
+        // registers across tiles (stats_flush reduces them over the lanes once per column tile)
+#define IFCB_WRITE_OUT(SLOT)                                                                   \
+  do {                                                                                         \
+    if (wide) write_out<4, FP16, true>(stage, lane, off_j, seg_out + gi * 32, sacc[SLOT]);     \
+    else write_out<2, FP16, true>(stage, lane, off_j, seg_out + gi * 32, sacc[SLOT]);          \
+  } while (0)
+        if (slot == 0) IFCB_WRITE_OUT(0);
+        else if (slot == 1) IFCB_WRITE_OUT(1);
+        else IFCB_WRITE_OUT(2);
+#undef IFCB_WRITE_OUT
+        ++slot;
+      } else {
+        if (wide) write_out<4, FP16, false>(stage, lane, off_j, seg_out + gi * 32, sacc[0]);
+        else write_out<2, FP16, false>(stage, lane, off_j, seg_out + gi * 32, sacc[0]);
+      }
       __syncwarp();
     }
     ubase += nunits;
+  }
+}
+
+// Reduces a warp's per-lane statistics partials over the lanes and adds them into the CTA's shared per-channel sums; clears
+// the partials.  Mirrors epilogue_tile's unit walk for ONE segment: unit u = sub + 3 * slot covers columns g0 .. g0 + 32 (or a
+// 16-column tail); a lane's partials belong to the 8 channels of its 16-byte piece pc = lane & 3 (wide) / lane & 1 (tail).
+__device__ __forceinline__ void stats_flush(const ConvKernelParams& p, float (&sacc)[3][16], int n_lo, int lane, int sub,
+                                            float* s_sum, float* s_sq) {
+  const int n_hi = n_lo + p.tile_n;
+  const int ms_shift = p.m_sub == 1 ? 0 : p.m_sub == 2 ? 1 : 2;
+  const int g_lo = max(n_lo, p.seg_begin[0]), g_hi = min(n_hi, p.seg_end[0]);
+  const int nunits = g_lo < g_hi ? (((g_hi - g_lo + 31) >> 5) << ms_shift) : 0;
+#pragma unroll
+  for (int slot = 0; slot < 3; ++slot) {
+    const int u = sub + kEpiPerQuad * slot;
+    if (u < nunits) {
+      const int g0 = g_lo + (u >> ms_shift) * 32;
+      const bool wide = (g_hi - g0) >= 32;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float v = sacc[slot][j];
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        if (!wide) v += __shfl_xor_sync(0xffffffffu, v, 2);
+        if (lane < (wide ? 4 : 2)) atomicAdd((j < 8 ? s_sum : s_sq) + g0 + lane * 8 + (j & 7), v);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) sacc[slot][j] = 0.f;
   }
 }
 
@@ -277,7 +355,7 @@ __device__ __forceinline__ void issue_stage(bool leader, int nt, bool first_stag
   }
 }
 
-template <bool WINDOW, bool FP16>
+template <bool WINDOW, bool FP16, bool STATS>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const ConvKernelParams p) {
@@ -303,10 +381,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_full + 12);
   float* s_scale = reinterpret_cast<float*>(bar_base + kBarBytes);
   float* s_shift = s_scale + p.cout_pad;
-  uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_shift + p.cout_pad);      // 16 x 2 KB, 128-byte aligned
+  uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_shift + p.cout_pad);      // 12 x 2 KB, 128-byte aligned
+  float* s_sum = reinterpret_cast<float*>(s_stage + kEpiWarps * kStageTile);  // STATS: [cout_pad] sums, [cout_pad] sums of squares
+  float* s_sq = s_sum + p.cout_pad;
   for (int i = threadIdx.x; i < p.cout_pad; i += kThreads) {
     s_scale[i] = p.scale[i];
     s_shift[i] = p.shift[i];
+    if (STATS) { s_sum[i] = 0.f; s_sq[i] = 0.f; }
   }
 
   // warp index through a shuffle: the compiler then KNOWS it is warp-uniform, keeps the role
@@ -353,7 +434,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     int stage = 0, aslot = 0;
     uint32_t phase = 0, aphase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
+      int m_tile, n_tile;
+      decode_tile(p, tile, m_tiles, m_tile, n_tile);
       const int n0 = n_tile * p.tile_n;
       if (WINDOW) {
         const int i0 = m_tile * tile_rows;
@@ -526,26 +608,47 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int quad = warp & 3;                       // TMEM lane quadrant this warp may access
     const int sub = (warp - 2) >> 2;                 // which of the quadrant's four warps
     uint8_t* stage = s_stage + (warp - 2) * kStageTile;
+    float sacc[STATS ? 3 : 1][16];
+    if (STATS) {
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) sacc[STATS ? a : 0][j] = 0.f;
+    }
+    int cur_n = -1;
     int local = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
-      const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
+      int m_tile, n_tile;
+      decode_tile(p, tile, m_tiles, m_tile, n_tile);
+      if (STATS && n_tile != cur_n) {                 // the column tile changes: hand the finished one's partial sums over
+        if (cur_n >= 0) stats_flush(p, reinterpret_cast<float(&)[3][16]>(sacc), cur_n * p.tile_n, lane, sub, s_sum, s_sq);
+        cur_n = n_tile;
+      }
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
       ptx::mbar_wait(tmem_full + acc, acc_phase);
       ptx::tc_fence_after();
       if (!(p.debug_flags & 4)) {
         const uint32_t tmem_acc = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * kAccBufCols);
-        epilogue_tile<FP16>(p, tmem_acc, m_tile * tile_rows + quad * 32, n_tile * p.tile_n, lane, sub, stage, s_scale, s_shift);
+        epilogue_tile<FP16, STATS>(p, tmem_acc, m_tile * tile_rows + quad * 32, n_tile * p.tile_n, lane, sub, stage, s_scale, s_shift,
+                                   reinterpret_cast<float(&)[3][16]>(sacc));
       }
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(tmem_empty + acc);
     }
+    if (STATS && cur_n >= 0) stats_flush(p, reinterpret_cast<float(&)[3][16]>(sacc), cur_n * p.tile_n, lane, sub, s_sum, s_sq);
   }
 
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 1) ptx::tmem_dealloc(tmem_base, kTmemCols);
+  if (STATS) {            // one float64 atomic per channel, quantity and CTA
+    for (int i = threadIdx.x; i < p.cout; i += kThreads) {
+      atomicAdd(p.stats + i, (double)s_sum[i]);
+      atomicAdd(p.stats + p.cout + i, (double)s_sq[i]);
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -558,7 +661,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 //   empty[s], tmem_full[a]   in each CTA, armed by multicast tcgen05.commit
 //   tmem_empty[a]   leader only: every epilogue warp of both CTAs arrives on it
 // ---------------------------------------------------------------------------------------
-template <bool FP16>
+template <bool FP16, bool STATS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 conv_umma_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                       const ConvKernelParams p) {
@@ -579,9 +682,12 @@ conv_umma_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
   float* s_scale = reinterpret_cast<float*>(bar_base + kBarBytes);
   float* s_shift = s_scale + p.cout_pad;
   uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_shift + p.cout_pad);
+  float* s_sum = reinterpret_cast<float*>(s_stage + kEpiWarps * kStageTile);
+  float* s_sq = s_sum + p.cout_pad;
   for (int i = threadIdx.x; i < p.cout_pad; i += kThreads) {
     s_scale[i] = p.scale[i];
     s_shift[i] = p.shift[i];
+    if (STATS) { s_sum[i] = 0.f; s_sq[i] = 0.f; }
   }
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
@@ -623,7 +729,8 @@ conv_umma_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = pair; tile < total_tiles; tile += npairs) {
-      const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
+      int m_tile, n_tile;
+      decode_tile(p, tile, m_tiles, m_tile, n_tile);
       const int n0 = n_tile * p.tile_n + (int)rank * (p.tile_n >> 1);
       const int m0 = m_tile * 2 * kBlockM + (int)rank * kBlockM;
       const int img = m0 / p.rows_per_img;
@@ -711,28 +818,48 @@ conv_umma_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     const int sub = (warp - 2) >> 2;
     uint8_t* stage = s_stage + (warp - 2) * kStageTile;
     const uint32_t lead_empty0 = ptx::mapa(ptx::smem_u32(tmem_empty), 0u);
+    float sacc[STATS ? 3 : 1][16];
+    if (STATS) {
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) sacc[STATS ? a : 0][j] = 0.f;
+    }
+    int cur_n = -1;
     int local = 0;
     for (int tile = pair; tile < total_tiles; tile += npairs, ++local) {
-      const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
+      int m_tile, n_tile;
+      decode_tile(p, tile, m_tiles, m_tile, n_tile);
+      if (STATS && n_tile != cur_n) {
+        if (cur_n >= 0) stats_flush(p, reinterpret_cast<float(&)[3][16]>(sacc), cur_n * p.tile_n, lane, sub, s_sum, s_sq);
+        cur_n = n_tile;
+      }
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
       ptx::mbar_wait(tmem_full + acc, acc_phase);
       ptx::tc_fence_after();
       if (!(p.debug_flags & 4)) {
         const uint32_t tmem_acc = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * kAccBufCols);
-        epilogue_tile<FP16>(p, tmem_acc, m_tile * 2 * kBlockM + (int)rank * kBlockM + quad * 32, n_tile * p.tile_n, lane, sub, stage,
-                               s_scale, s_shift);
+        epilogue_tile<FP16, STATS>(p, tmem_acc, m_tile * 2 * kBlockM + (int)rank * kBlockM + quad * 32, n_tile * p.tile_n, lane, sub, stage,
+                                   s_scale, s_shift, reinterpret_cast<float(&)[3][16]>(sacc));
       }
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive_cluster(lead_empty0 + (uint32_t)(acc * 8));
     }
+    if (STATS && cur_n >= 0) stats_flush(p, reinterpret_cast<float(&)[3][16]>(sacc), cur_n * p.tile_n, lane, sub, s_sum, s_sq);
   }
 
   ptx::tc_fence_before();
   __syncthreads();
   ptx::cluster_sync();
   if (warp == 1) ptx::tmem_dealloc_pair(tmem_base, kTmemCols);
+  if (STATS) {
+    for (int i = threadIdx.x; i < p.cout; i += kThreads) {
+      atomicAdd(p.stats + i, (double)s_sum[i]);
+      atomicAdd(p.stats + p.cout + i, (double)s_sq[i]);
+    }
+  }
 }
 
 constexpr int kSmemBudget = 227 * 1024;
@@ -745,7 +872,7 @@ bool conv_plan_smem(ConvKernelParams& kp, bool window, bool pair, int halo_rows)
   const int row_bytes = kp.row_bytes;
   const int b_tap = kp.tile_n * row_bytes;
   const int a_tile = kBlockM * row_bytes;
-  const int fixed = epilogue_smem(kp.cout_pad) + 1024;
+  const int fixed = epilogue_smem(kp.cout_pad, kp.stats != nullptr) + 1024;
   const int taps = kp.kh * kp.kw;
   if (!window) {
     kp.m_sub = 1;
@@ -821,33 +948,39 @@ int conv_smem_bytes(const ConvKernelParams& kp, bool window, bool pair) {
   const int b_tap = kp.tile_n * kp.row_bytes;
   const int ops = window ? kp.a_slots * kp.a_slot_bytes + kp.stages * kp.b_group * b_tap
                          : kp.stages * kp.b_group * (kBlockM * kp.row_bytes + (pair ? b_tap / 2 : b_tap));
-  return ops + epilogue_smem(kp.cout_pad) + 1024;
+  return ops + epilogue_smem(kp.cout_pad, kp.stats != nullptr) + 1024;
 }
 
 namespace {
-template <bool WINDOW, bool FP16>
-int launch_variant(const ConvLayer& L, const ConvKernelParams& p, int grid, int smem, cudaStream_t stream) {
-  static int attr_smem = 0;
-  if (smem > attr_smem) {
-    IFCB_CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<WINDOW, FP16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_smem = smem;
+// the opt-in shared-memory limit is a per-device function attribute: set it once per (kernel, device) to the budget
+template <typename K>
+int ensure_smem_attr(K kernel, bool (&done)[64]) {
+  int dev = 0;
+  IFCB_CUDA_CHECK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !done[dev]) {
+    IFCB_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+    if (dev >= 0 && dev < 64) done[dev] = true;
   }
-  conv_umma_kernel<WINDOW, FP16><<<grid, kThreads, smem, stream>>>(L.tmap_a, L.tmap_b, p);
+  return 0;
+}
+
+template <bool WINDOW, bool FP16, bool STATS>
+int launch_variant(const ConvLayer& L, const ConvKernelParams& p, int grid, int smem, cudaStream_t stream) {
+  static bool done[64] = {};
+  if (int rc = ensure_smem_attr(conv_umma_kernel<WINDOW, FP16, STATS>, done)) return rc;
+  conv_umma_kernel<WINDOW, FP16, STATS><<<grid, kThreads, smem, stream>>>(L.tmap_a, L.tmap_b, p);
   IFCB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
 }  // namespace
 
 namespace {
-template <bool FP16>
+template <bool FP16, bool STATS>
 int launch_pair(const ConvLayer& L, const ConvKernelParams& p, int grid, int smem, cudaStream_t stream) {
-  static int attr_smem = 0;
-  if (smem > attr_smem) {
-    IFCB_CUDA_CHECK(cudaFuncSetAttribute(conv_umma_pair_kernel<FP16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_smem = smem;
-  }
+  static bool done[64] = {};
+  if (int rc = ensure_smem_attr(conv_umma_pair_kernel<FP16, STATS>, done)) return rc;
   // cluster dimensions (2,1,1) are compiled into the kernel (__cluster_dims__); grid is even
-  conv_umma_pair_kernel<FP16><<<grid, kThreads, smem, stream>>>(L.tmap_a, L.tmap_b, p);
+  conv_umma_pair_kernel<FP16, STATS><<<grid, kThreads, smem, stream>>>(L.tmap_a, L.tmap_b, p);
   IFCB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -865,14 +998,18 @@ int launch_conv(const ConvLayer& L, int batch, cudaStream_t stream) {
     return -1;
   }
   const int smem = conv_smem_bytes(p, L.window, L.pair);
+  const bool st = p.stats != nullptr;
   if (L.pair) {
     const int pairs = sm_count() / 2;
     const int grid = 2 * (int)(total < pairs ? total : pairs);
-    return p.fp16 ? launch_pair<true>(L, p, grid, smem, stream) : launch_pair<false>(L, p, grid, smem, stream);
+    if (st) return p.fp16 ? launch_pair<true, true>(L, p, grid, smem, stream) : launch_pair<false, true>(L, p, grid, smem, stream);
+    return p.fp16 ? launch_pair<true, false>(L, p, grid, smem, stream) : launch_pair<false, false>(L, p, grid, smem, stream);
   }
   const int grid = (int)(total < sm_count() ? total : sm_count());
-  if (L.window) return p.fp16 ? launch_variant<true, true>(L, p, grid, smem, stream) : launch_variant<true, false>(L, p, grid, smem, stream);
-  return p.fp16 ? launch_variant<false, true>(L, p, grid, smem, stream) : launch_variant<false, false>(L, p, grid, smem, stream);
+#define IFCB_LAUNCH(W, S) (p.fp16 ? launch_variant<W, true, S>(L, p, grid, smem, stream) : launch_variant<W, false, S>(L, p, grid, smem, stream))
+  if (L.window) return st ? IFCB_LAUNCH(true, true) : IFCB_LAUNCH(true, false);
+  return st ? IFCB_LAUNCH(false, true) : IFCB_LAUNCH(false, false);
+#undef IFCB_LAUNCH
 }
 
 // ---------------------------------------------------------------------------------

@@ -35,6 +35,9 @@ struct ConvKernelParams {
   int seg_begin[IFCB_MAX_SEGMENTS], seg_end[IFCB_MAX_SEGMENTS], seg_ld[IFCB_MAX_SEGMENTS],
       seg_relu[IFCB_MAX_SEGMENTS], seg_pad_h[IFCB_MAX_SEGMENTS], seg_pad_w[IFCB_MAX_SEGMENTS];
   __nv_bfloat16* seg_out[IFCB_MAX_SEGMENTS];
+  double* stats;               // TRAIN: float64 [2][cout] accumulators of sum / sum of squares per output channel (NULL: off)
+  int cout;                    // real output channels (stats columns)
+  int n_major;                 // tile order: 0 = pixel tiles outermost (m, n), 1 = channel tiles outermost (stats: a CTA keeps its columns)
 };
 
 struct ConvLayer {

@@ -213,6 +213,10 @@ extern "C" int ifcb_plan_add_conv(ifcb_plan* plan, const ifcb_conv_desc* d) {
     const char* bg = getenv("IFCB_CONV_BGROUP");
     kp.b_group_cap = bg ? atoi(bg) : 0;
   }
+  kp.stats = d->d_stats;
+  kp.cout = d->Cout;
+  kp.n_major = (d->d_stats && kp.n_tiles > 1) ? 1 : 0;
+  IFCB_ARG_CHECK(!d->d_stats || d->n_seg == 1, "conv: d_stats needs a single output segment");
   kp.win_shift0 = (d->in_pad_h - d->pad_h) * Wp + (d->in_pad_w - d->pad_w);
   const int halo = kp.win_shift0 + (d->kh - 1) * Wp + (d->kw - 1);
   IFCB_ARG_CHECK(conv_plan_smem(kp, window, pair, halo), "conv: no shared-memory plan for tile_n=%d halo=%d", tile_n, halo);

@@ -10,6 +10,7 @@
 // All of these are HBM-bound streaming kernels: one thread = one pixel x 8 channels (16 bytes),
 // NHWC 16-bit views with an optional physical zero border (include/ifcb_b200.h: ifcb_view).
 #include "layers.cuh"
+#include <cstdlib>
 
 namespace ifcb {
 namespace {
@@ -146,12 +147,16 @@ template <int MODE, int MASK>
 __global__ void __launch_bounds__(256, 2) channel_reduce_kernel(DV z, DV dy, DV a, const float* __restrict__ mean,
                                                                 const float* __restrict__ invstd, const float* __restrict__ gamma,
                                                                 const float* __restrict__ beta, long long M, int rows, int fp16,
-                                                                double* __restrict__ acc, const FinalizeArgs fin) {
+                                                                double* __restrict__ acc, const FinalizeArgs fin, int c8b) {
+  // grid = (pixel splits, channel blocks): a block owns c8b groups of 8 channels (<= 64 channels = one 128-byte line per pixel)
+  // and `rows` pixel rows per sweep.  Small channel blocks keep the float64 atomics per block at 2 * 8 * c8b whatever C is, so
+  // small tensors can be spread over a full wave of blocks (the first version gave every block ALL channels: 2 * C atomics per
+  // block forced 49-196 blocks on the 7x7 / 14x14 layers -- 22-45 us for tensors that stream in 5 us).
   __shared__ float red[256 * 16];
   __shared__ int s_last;
-  const int c8n = z.C >> 3;
+  const int c8n = c8b;
   const int tid = threadIdx.x;
-  const int row = tid / c8n, c8 = tid - row * c8n;
+  const int row = tid / c8n, c8 = blockIdx.y * c8b + (tid - row * c8n);
   float s1[8], s2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
@@ -221,22 +226,22 @@ __global__ void __launch_bounds__(256, 2) channel_reduce_kernel(DV z, DV dy, DV 
     red[tid * 16 + 8 + j] = s2[j];
   }
   __syncthreads();
-  // thread t < 2*C sums one (quantity, channel) over the rows
-  for (int t = tid; t < 2 * z.C; t += 256) {
-    const int which = t / z.C, c = t - which * z.C;
-    const int cc8 = c >> 3, j = c & 7;
+  // thread t < 2 * (channels of this block) sums one (quantity, channel) over the rows
+  const int C = z.C, cb = 8 * c8b, c_lo = blockIdx.y * cb;
+  for (int t = tid; t < 2 * cb; t += 256) {
+    const int which = t / cb, cl = t - which * cb;
+    const int cc8 = cl >> 3, j = cl & 7;
     float s = 0.f;
     for (int r = 0; r < rows; ++r) s += red[(r * c8n + cc8) * 16 + which * 8 + j];
-    atomicAdd(acc + t, (double)s);
+    atomicAdd(acc + which * C + c_lo + cl, (double)s);
   }
-  // ---- last block: finalize (threadFenceReduction pattern) ----
+  // ---- last block of this channel block: finalize its channels (threadFenceReduction pattern) ----
   __threadfence();
   __syncthreads();
-  if (tid == 0) s_last = (atomicAdd(fin.counter, 1u) == gridDim.x - 1) ? 1 : 0;
+  if (tid == 0) s_last = (atomicAdd(fin.counter + blockIdx.y, 1u) == gridDim.x - 1) ? 1 : 0;
   __syncthreads();
   if (!s_last) return;
-  const int C = z.C;
-  for (int c = tid; c < C; c += 256) {
+  for (int c = c_lo + tid; c < c_lo + cb; c += 256) {
     const double s1 = __ldcg(acc + c), s2 = __ldcg(acc + C + c);
     if (MODE == 0) {
       const double mu = s1 / fin.count;
@@ -262,7 +267,7 @@ __global__ void __launch_bounds__(256, 2) channel_reduce_kernel(DV z, DV dy, DV 
     acc[c] = 0.0;
     acc[C + c] = 0.0;
   }
-  if (tid == 0) *fin.counter = 0u;
+  if (tid == 0) fin.counter[blockIdx.y] = 0u;
 }
 
 // a = act(bn_y(z) (+ residual)).  Block = rows x (C/8) threads: a thread keeps the parameters of its 8
@@ -276,6 +281,73 @@ __global__ void __launch_bounds__(256, 3) bn_apply_kernel(DV z, DV out, DV res, 
   if (row >= rows) return;
   float mu[8], S[8], Bt[8];
   bn_params8(mean, invstd, gamma, beta, c8 * 8, mu, S, Bt);
+  const long long stride = (long long)gridDim.x * rows;
+  for (long long m0 = (long long)blockIdx.x * rows + row; m0 < M; m0 += stride * kUnroll) {
+    uint4 zr[kUnroll], rr[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const long long m = m0 + u * stride;
+      if (m < M) {
+        zr[u] = ld16(z.p + pix_off_m(z, m) + c8 * 8);
+        if (HAS_RES) rr[u] = ld16(res.p + pix_off_m(res, m) + c8 * 8);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const long long m = m0 + u * stride;
+      if (m < M) {
+        float v[8], r[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        cvt8(zr[u], fp16, v);
+        if (HAS_RES) cvt8(rr[u], fp16, r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float y = bn_y(v[j], mu[j], S[j], Bt[j]) + r[j];
+          v[j] = relu ? fmaxf(y, 0.f) : y;
+        }
+        store8(out.p + pix_off_m(out, m) + c8 * 8, fp16, v);
+      }
+    }
+  }
+}
+
+// The same pass when the batch statistics arrive as float64 sums gathered by the convolution's epilogue (ifcb_conv_desc.d_stats):
+// every thread turns the sums of ITS 8 channels into mean / invstd (a handful of float64 operations, redundant across blocks but
+// free next to the streaming), block 0 also publishes mean / invstd for the backward pass and updates the running statistics
+// exactly as the last block of channel_reduce_kernel<0> does.  No pass over z for the statistics, no extra launch.
+template <bool HAS_RES>
+__global__ void __launch_bounds__(256, 3) bn_apply_sums_kernel(DV z, DV out, DV res, const double* __restrict__ sums, double count, float eps,
+                                                               float momentum, float* __restrict__ mean_out, float* __restrict__ invstd_out,
+                                                               float* __restrict__ run_mean, float* __restrict__ run_var,
+                                                               const float* __restrict__ gamma, const float* __restrict__ beta, int relu,
+                                                               long long M, int rows, int fp16) {
+  const int C = z.C, c8n = C >> 3;
+  const int row = threadIdx.x / c8n, c8 = threadIdx.x - row * c8n;
+  if (row >= rows) return;
+  float mu[8], S[8], Bt[8];
+  {
+    float ga[8];
+    ldg8(gamma + c8 * 8, ga);
+    ldg8(beta + c8 * 8, Bt);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = c8 * 8 + j;
+      const double m = sums[c] / count;
+      double var = sums[C + c] / count - m * m;
+      if (var < 0.0) var = 0.0;
+      const float is = (float)(1.0 / sqrt(var + (double)eps));
+      mu[j] = (float)m;
+      S[j] = __fmul_rn(ga[j], is);
+      if (blockIdx.x == 0 && row == 0) {
+        mean_out[c] = (float)m;
+        invstd_out[c] = is;
+        if (run_mean) run_mean[c] = (1.f - momentum) * run_mean[c] + momentum * (float)m;
+        if (run_var) {
+          const double unb = count > 1.0 ? var * count / (count - 1.0) : var;
+          run_var[c] = (1.f - momentum) * run_var[c] + momentum * (float)unb;
+        }
+      }
+    }
+  }
   const long long stride = (long long)gridDim.x * rows;
   for (long long m0 = (long long)blockIdx.x * rows + row; m0 < M; m0 += stride * kUnroll) {
     uint4 zr[kUnroll], rr[kUnroll];
@@ -478,6 +550,64 @@ __global__ void __launch_bounds__(256) pool_bwd_kernel(DV dy, const uint8_t* __r
   }
 }
 
+// max-pool backward, 3x3 window / stride 2 (every max pool of ResNet and Inception-v3): an input pixel lies in at most 2 x 2
+// windows, so the four (gradient, winner-index) loads are issued together and combined afterwards -- the generic gather above
+// walks the windows one by one (1.2 TB/s; this one streams).  Same result bit for bit (same summation order: rows, then columns).
+__global__ void __launch_bounds__(256) maxpool3s2_bwd_kernel(DV dy, const uint8_t* __restrict__ idx, DV dx, int accumulate, int pad, int P,
+                                                             int Q, uint32_t total, unsigned long long magic_c8, int fp16) {
+  const uint32_t c8n = (uint32_t)(dx.C >> 3);
+  for (uint32_t t = blockIdx.x * 256u + threadIdx.x; t < total; t += gridDim.x * 256u) {
+    const uint32_t m = fast_div(t, magic_c8);
+    const int c8 = (int)(t - m * c8n);
+    const uint32_t t2 = fast_div(m, dx.magic_w);
+    const int w = (int)(m - t2 * (uint32_t)dx.W);
+    const uint32_t nn = fast_div(t2, dx.magic_h);
+    const int h = (int)(t2 - nn * (uint32_t)dx.H), n = (int)nn;
+    // windows op with 2*op - pad <= h <= 2*op - pad + 2  =>  op in [ceil((h + pad - 2) / 2), floor((h + pad) / 2)]
+    const int hp = h + pad, wp = w + pad;
+    const int p1 = hp >> 1, p0 = p1 - 1 + (hp & 1);          // hp even: {p1 - 1, p1}; hp odd: {p1} twice
+    const int q1 = wp >> 1, q0 = q1 - 1 + (wp & 1);
+    uint4 gv[4];
+    uint2 iv[4];
+    bool ok[4];
+    int tap[4];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const int op = a ? p1 : p0, oq = b ? q1 : q0;
+        const int k = a * 2 + b;
+        ok[k] = op >= 0 && op < P && oq >= 0 && oq < Q && (a == 1 || p0 != p1) && (b == 1 || q0 != q1);
+        tap[k] = (hp - 2 * op) * 3 + (wp - 2 * oq);
+        if (ok[k]) {
+          gv[k] = ld16(dy.p + pix_off(dy, n, op, oq) + c8 * 8);
+          iv[k] = *reinterpret_cast<const uint2*>(idx + (((long long)n * P + op) * Q + oq) * dx.C + c8 * 8);
+        }
+      }
+    float g[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (ok[k]) {
+        float v[8];
+        cvt8(gv[k], fp16, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int w8 = (int)(((j < 4 ? iv[k].x : iv[k].y) >> (8 * (j & 3))) & 0xffu);
+          if (w8 == tap[k]) g[j] += v[j];
+        }
+      }
+    }
+    uint16_t* dst = dx.p + pix_off(dx, n, h, w) + c8 * 8;
+    if (accumulate) {
+      float o[8];
+      load8(dst, fp16, o);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] += o[j];
+    }
+    store8(dst, fp16, g);
+  }
+}
+
 // plain average pool (count_include_pad=True, divisor k*k): F.avg_pool2d in Inception blocks / aux head
 __global__ void __launch_bounds__(256) avgpool_fwd_kernel(DV x, DV y, int k, int stride, int pad, int P, int Q, uint32_t total,
                                                           unsigned long long magic_c8, int fp16) {
@@ -583,6 +713,69 @@ __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restric
       }
     }
     store8(out.p + pix_off(out, (int)n, p, q) + k0, fp16, f);
+  }
+}
+
+// The same patch matrix, tiled through shared memory: a block owns kTileQ output pixels of one output row.  It loads the
+// input patch those pixels need (3 channels x kh rows x ((kTileQ-1)*stride + kw) columns) with row-contiguous reads, applies the
+// affine and the 16-bit conversion ONCE per input element, and then assembles the [pixel][k] rows from shared memory through a
+// k -> patch-offset table, writing 16-byte pieces that are contiguous across the whole tile (the gather version above issues 8
+// scattered global loads per 16 output bytes: 1.1 ms for ResNet-50's 976 MB patch matrix at batch 256).
+constexpr int kTileQ = 64;
+__global__ void __launch_bounds__(256) stem_im2col_tiled_kernel(const float* __restrict__ in, int H, int W, DV out, int kh, int kw, int stride,
+                                                                int pad, float s0, float s1, float s2, float b0, float b1, float b2,
+                                                                unsigned long long magic_k8, int fp16) {
+  extern __shared__ uint16_t sm16[];
+  const int span = (kTileQ - 1) * stride + kw;            // input columns a tile touches
+  uint16_t* patch = sm16;                                  // [3][kh][span] 16-bit activations (0 outside the image)
+  uint16_t* lut = sm16 + ((3 * kh * span + 7) & ~7);       // [out.C] k -> offset in patch (0xFFFF: zero column)
+  const int n = blockIdx.z, p = blockIdx.y, q0 = blockIdx.x * kTileQ;
+  const int tid = threadIdx.x;
+  const int kmax = kh * kw * 3;
+  const long long plane = (long long)H * W;
+  const float* src = in + (long long)n * 3 * plane;
+  const int h0 = p * stride - pad, w0 = q0 * stride - pad;
+  // one warp per (channel, filter row): lanes walk the input columns (row-contiguous reads, no per-element divisions)
+  for (int cr = tid >> 5; cr < 3 * kh; cr += 8) {
+    const int c = cr / kh, r = cr - c * kh;
+    const int hh = h0 + r;
+    const bool row_ok = (unsigned)hh < (unsigned)H;
+    const float sc = c == 0 ? s0 : c == 1 ? s1 : s2, sh = c == 0 ? b0 : c == 1 ? b1 : b2;
+    const float* rowp = src + c * plane + (long long)hh * W;
+    for (int x = tid & 31; x < span; x += 32) {
+      const int ww = w0 + x;
+      float v = 0.f;
+      if (row_ok && (unsigned)ww < (unsigned)W) v = fmaf(__ldg(rowp + ww), sc, sh);
+      patch[cr * span + x] = (uint16_t)(pack_act2(v, 0.f, fp16) & 0xFFFFu);
+    }
+  }
+  for (int k = tid; k < out.C; k += 256) {
+    uint16_t o = 0xFFFFu;
+    if (k < kmax) {
+      const int tap = k / 3, c = k - tap * 3;
+      const int r = tap / kw, sx = tap - r * kw;
+      o = (uint16_t)((c * kh + r) * span + sx);
+    }
+    lut[k] = o;
+  }
+  __syncthreads();
+  const uint32_t k8n = (uint32_t)(out.C >> 3);
+  const int nq = min(kTileQ, out.W - q0);
+  const uint32_t items = (uint32_t)nq * k8n;
+  uint16_t* orow = out.p + pix_off(out, n, p, q0);
+  for (uint32_t it = tid; it < items; it += 256) {
+    const uint32_t ql = fast_div(it, magic_k8);
+    const int k0 = (int)(it - ql * k8n) * 8;
+    const int xo = (int)ql * stride;
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t l0 = lut[k0 + 2 * j], l1 = lut[k0 + 2 * j + 1];
+      const uint32_t e0 = l0 == 0xFFFFu ? 0u : patch[l0 + xo];
+      const uint32_t e1 = l1 == 0xFFFFu ? 0u : patch[l1 + xo];
+      w[j] = e0 | (e1 << 16);
+    }
+    *reinterpret_cast<uint4*>(orow + (long long)ql * out.ld + k0) = make_uint4(w[0], w[1], w[2], w[3]);
   }
 }
 
@@ -777,29 +970,53 @@ __global__ void __launch_bounds__(256) conv_repack_kernel(const float* __restric
   }
 }
 
-// every conv of a network in ONE launch: blockIdx.y = conv, blockIdx.x strides over its elements
+// every conv of a network in ONE launch: blockIdx.y = conv, blockIdx.x strides over its 32 (co) x 32 (ci) tiles per filter tap.
+// A tile is read once, coalesced along ci (the master layout [co][tap][ci]); the forward operand [co][tap][ci_pad] is written
+// straight away (same order), the data-gradient operand [ci][taps-1-tap][co_pad] goes through a shared-memory transpose so that
+// its stores are coalesced along co.  No per-element divisions: one 32-bit tile decode per 1024 elements.
+// (The first version walked the elements linearly with three 64-bit divisions each and scattered the transposed store:
+// 0.43-0.50 ms per step for 24 M weights; this one moves the same 190 MB at streaming rate.)
 __global__ void __launch_bounds__(256) conv_repack_batch_kernel(const ifcb_repack_item* __restrict__ items, int fp16) {
+  __shared__ uint16_t tile[32][33];
   const ifcb_repack_item it = items[blockIdx.y];
   const float* __restrict__ w = it.d_master;
   uint16_t* __restrict__ wf = reinterpret_cast<uint16_t*>(it.d_wfwd);
   uint16_t* __restrict__ wd = reinterpret_cast<uint16_t*>(it.d_wdgrad);
-  const int Cin = it.Cin, taps = it.taps;
-  const long long total = (long long)it.Cout * taps * Cin;
-  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
-    const int ci = (int)(i % Cin);
-    const long long r = i / Cin;
-    const int t = (int)(r % taps), co = (int)(r / taps);
-    const float v = w[i];
-    uint16_t h;
-    if (fp16) {
-      const __half hv = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
-      h = *reinterpret_cast<const uint16_t*>(&hv);
-    } else {
-      const __nv_bfloat16 bv = __float2bfloat16_rn(v);
-      h = *reinterpret_cast<const uint16_t*>(&bv);
+  const int Cin = it.Cin, Cout = it.Cout, taps = it.taps;
+  const int cit_n = (Cin + 31) >> 5, cot_n = (Cout + 31) >> 5;
+  const int tiles = taps * cot_n * cit_n;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int tl = blockIdx.x; tl < tiles; tl += gridDim.x) {
+    const int cit = tl % cit_n, r = tl / cit_n;
+    const int cot = r % cot_n, t = r / cot_n;
+    const int ci = cit * 32 + tx;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int co = cot * 32 + ty + 8 * k;
+      uint16_t h = 0;
+      if (co < Cout && ci < Cin) {
+        const float v = w[((long long)co * taps + t) * Cin + ci];
+        if (fp16) {
+          const __half hv = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
+          h = *reinterpret_cast<const uint16_t*>(&hv);
+        } else {
+          const __nv_bfloat16 bv = __float2bfloat16_rn(v);
+          h = *reinterpret_cast<const uint16_t*>(&bv);
+        }
+        if (wf) wf[((long long)co * taps + t) * it.Cin_pad + ci] = h;
+      }
+      tile[ty + 8 * k][tx] = h;
     }
-    if (wf) wf[(long long)co * taps * it.Cin_pad + (long long)t * it.Cin_pad + ci] = h;
-    if (wd) wd[(long long)ci * taps * it.Cout_padk + (long long)(taps - 1 - t) * it.Cout_padk + co] = h;
+    __syncthreads();
+    if (wd) {
+      const int co = cot * 32 + tx;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int ci2 = cit * 32 + ty + 8 * k;
+        if (co < Cout && ci2 < Cin) wd[((long long)ci2 * taps + (taps - 1 - t)) * it.Cout_padk + co] = tile[tx][ty + 8 * k];
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -831,13 +1048,34 @@ static int stream_grid(long long M, int rows) {
   return g < 1 ? 1 : (int)g;
 }
 
-// grid of the reduction kernels: as stream_grid, but every block ends with 2*C float64 atomics on the same 2*C
-// addresses, so a block should stream at least ~256 KB per tensor before it pays for them
-static int reduce_grid(long long M, int rows, int C) {
-  long long g = stream_grid(M, rows);
-  const long long by_bytes = (M * C * 2 + (256 << 10) - 1) / (256 << 10);
-  if (g > by_bytes) g = by_bytes;
-  return g < 1 ? 1 : (int)g;
+// Reduction kernels: channel blocks of <= 64 channels (c8b groups of 8) x pixel splits.  A block streams at least ~32 KB per
+// tensor before its 2 * 8 * c8b float64 atomics; the whole grid is at most 8 blocks per SM.
+struct ReduceCfg {
+  int c8b, rows;
+  dim3 grid;
+};
+static ReduceCfg reduce_cfg(long long M, int C) {
+  ReduceCfg r;
+  static const bool whole = getenv("IFCB_BN_REDUCE_WHOLE") != nullptr;      // A/B switch: every block takes all channels
+  const int c8n = C / 8;
+  if (whole || c8n <= 16) {
+    r.c8b = c8n;                                         // narrow tensors: a block reads whole pixel rows
+  } else {
+    r.c8b = 8;                                           // 128 / 64 / 32 / 16-byte channel blocks: always whole sectors
+    while (c8n % r.c8b) r.c8b >>= 1;
+  }
+  r.rows = 256 / r.c8b;
+  if (r.rows < 1) r.rows = 1;
+  const int ychunks = (C / 8) / r.c8b;
+  long long xs = (M + (long long)r.rows * kUnroll - 1) / ((long long)r.rows * kUnroll);          // one sweep per block at most
+  const long long cap = ((long long)sm_count() * 8 + ychunks - 1) / ychunks;
+  if (xs > cap) xs = cap;
+  const long long blk_bytes = whole ? (256 << 10) : (32 << 10);
+  const long long by_bytes = (M * 16 * r.c8b + blk_bytes - 1) / blk_bytes;
+  if (xs > by_bytes) xs = by_bytes;
+  if (xs < 1) xs = 1;
+  r.grid = dim3((unsigned)xs, (unsigned)ychunks, 1);
+  return r;
 }
 
 extern "C" int ifcb_bn_stats(const ifcb_view* z, int batch, int dtype, float eps, float momentum, double* d_acc, float* d_mean,
@@ -846,8 +1084,7 @@ extern "C" int ifcb_bn_stats(const ifcb_view* z, int batch, int dtype, float eps
   IFCB_ARG_CHECK(z->C <= 2048, "bn_stats: C=%d > 2048", z->C);
   IFCB_ARG_CHECK(d_acc && d_mean && d_invstd, "bn_stats: null pointer");
   const long long M = (long long)batch * z->H * z->W;
-  const int rows = reduce_rows(z->C);
-  const int grid = reduce_grid(M, rows, z->C);
+  const ReduceCfg rc = reduce_cfg(M, z->C);
   DV zz = dv(z);
   IFCB_ARG_CHECK(M < (1ll << 31) / (z->C / 8), "bn_stats: tensor too large for 32-bit indexing");
   FinalizeArgs fin{};
@@ -858,8 +1095,9 @@ extern "C" int ifcb_bn_stats(const ifcb_view* z, int batch, int dtype, float eps
   fin.invstd_out = d_invstd;
   fin.run_mean = d_running_mean;
   fin.run_var = d_running_var;
-  fin.counter = reinterpret_cast<unsigned int*>(d_acc + 8191);
-  channel_reduce_kernel<0, kMaskNone><<<grid, 256, 0, STREAM(stream)>>>(zz, zz, zz, nullptr, nullptr, nullptr, nullptr, M, rows, dtype, d_acc, fin);
+  fin.counter = reinterpret_cast<unsigned int*>(d_acc + 7680);       // one arrival counter per channel block (<= 256), behind the coefficients
+  channel_reduce_kernel<0, kMaskNone><<<rc.grid, 256, 0, STREAM(stream)>>>(zz, zz, zz, nullptr, nullptr, nullptr, nullptr, M, rc.rows, dtype, d_acc,
+                                                                           fin, rc.c8b);
   IFCB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -883,6 +1121,32 @@ extern "C" int ifcb_bn_apply(const ifcb_view* z, const ifcb_view* out, const ifc
   else
     bn_apply_kernel<false><<<stream_grid(M, rows), 256, 0, STREAM(stream)>>>(zz, dv(out), zz, d_mean, d_invstd, d_gamma, d_beta, relu, M, rows,
                                                                               dtype);
+  IFCB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int ifcb_bn_apply_sums(const ifcb_view* z, const ifcb_view* out, const ifcb_view* residual, int batch, int dtype,
+                                  const double* d_sums, float eps, float momentum, float* d_mean, float* d_invstd,
+                                  float* d_running_mean, float* d_running_var, const float* d_gamma, const float* d_beta, int relu,
+                                  void* stream) {
+  IFCB_ARG_CHECK(view_ok(z) && view_ok(out) && batch > 0 && DT_OK(dtype), "bn_apply_sums: bad view / batch / dtype");
+  IFCB_ARG_CHECK(out->C == z->C && out->H == z->H && out->W == z->W, "bn_apply_sums: output extent differs");
+  IFCB_ARG_CHECK(!residual || (view_ok(residual) && residual->C == z->C && residual->H == z->H && residual->W == z->W),
+                 "bn_apply_sums: residual extent differs");
+  IFCB_ARG_CHECK(d_sums && d_mean && d_invstd && d_gamma && d_beta, "bn_apply_sums: null pointer");
+  IFCB_ARG_CHECK(z->C <= 2048, "bn_apply_sums: C=%d > 2048", z->C);
+  const long long M = (long long)batch * z->H * z->W;
+  IFCB_ARG_CHECK(M < (1ll << 31), "bn_apply_sums: tensor too large for 32-bit indexing");
+  const int rows = reduce_rows(z->C);
+  DV zz = dv(z);
+  if (residual)
+    bn_apply_sums_kernel<true><<<stream_grid(M, rows), 256, 0, STREAM(stream)>>>(zz, dv(out), dv(residual), d_sums, (double)M, eps, momentum,
+                                                                                  d_mean, d_invstd, d_running_mean, d_running_var, d_gamma,
+                                                                                  d_beta, relu, M, rows, dtype);
+  else
+    bn_apply_sums_kernel<false><<<stream_grid(M, rows), 256, 0, STREAM(stream)>>>(zz, dv(out), zz, d_sums, (double)M, eps, momentum, d_mean,
+                                                                                   d_invstd, d_running_mean, d_running_var, d_gamma, d_beta,
+                                                                                   relu, M, rows, dtype);
   IFCB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -918,8 +1182,9 @@ extern "C" int ifcb_bn_backward(const ifcb_view* dy, const ifcb_view* a, const i
   fin.coef = coef;
   fin.dgamma = d_dgamma;
   fin.dbeta = d_dbeta;
-  fin.counter = reinterpret_cast<unsigned int*>(d_acc + 8191);
-#define IFCB_REDUCE1(MK) channel_reduce_kernel<1, MK><<<reduce_grid(M, rows, z->C), 256, 0, st>>>(zz, dyy, av, d_mean, d_invstd, d_gamma, d_beta, M, rows, dtype, d_acc, fin)
+  fin.counter = reinterpret_cast<unsigned int*>(d_acc + 7680);
+  const ReduceCfg rc = reduce_cfg(M, z->C);
+#define IFCB_REDUCE1(MK) channel_reduce_kernel<1, MK><<<rc.grid, 256, 0, st>>>(zz, dyy, av, d_mean, d_invstd, d_gamma, d_beta, M, rc.rows, dtype, d_acc, fin, rc.c8b)
   if (mask_mode == kMaskFromZ) IFCB_REDUCE1(kMaskFromZ);
   else if (mask_mode == kMaskFromA) IFCB_REDUCE1(kMaskFromA);
   else IFCB_REDUCE1(kMaskNone);
@@ -959,8 +1224,12 @@ extern "C" int ifcb_maxpool_bwd(const ifcb_view* dy, const uint8_t* d_idx, const
   IFCB_ARG_CHECK(dy->C == dx->C && dy->H == P && dy->W == Q, "maxpool_bwd: gradient extent differs");
   const long long total = (long long)batch * dx->H * dx->W * (dx->C / 8);
   IFCB_ARG_CHECK(total < (1ll << 31), "maxpool_bwd: tensor too large for 32-bit indexing");
-  pool_bwd_kernel<false><<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(dv(dy), d_idx, dv(dx), accumulate, k, stride, pad, P, Q,
-                                                                            (uint32_t)total, div_magic(dx->C / 8), dtype);
+  if (k == 3 && stride == 2)
+    maxpool3s2_bwd_kernel<<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(dv(dy), d_idx, dv(dx), accumulate, pad, P, Q, (uint32_t)total,
+                                                                             div_magic(dx->C / 8), dtype);
+  else
+    pool_bwd_kernel<false><<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(dv(dy), d_idx, dv(dx), accumulate, k, stride, pad, P, Q,
+                                                                              (uint32_t)total, div_magic(dx->C / 8), dtype);
   IFCB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -1019,8 +1288,17 @@ extern "C" int ifcb_stem_im2col(const float* d_in, int H, int W, const ifcb_view
   IFCB_ARG_CHECK(total < (1ll << 31), "stem_im2col: tensor too large for 32-bit indexing");
   const float sc[3] = {h_scale ? h_scale[0] : 1.f, h_scale ? h_scale[1] : 1.f, h_scale ? h_scale[2] : 1.f};
   const float sh[3] = {h_shift ? h_shift[0] : 0.f, h_shift ? h_shift[1] : 0.f, h_shift ? h_shift[2] : 0.f};
-  stem_im2col_kernel<<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(d_in, H, W, dv(out), kh, kw, stride, pad, sc[0], sc[1], sc[2], sh[0],
-                                                                        sh[1], sh[2], (uint32_t)total, div_magic(out->C / 8), dtype);
+  const int span = (kTileQ - 1) * stride + kw;
+  const int smem = (((3 * kh * span + 7) & ~7) + out->C) * 2;
+  static const bool gather = getenv("IFCB_STEM_IM2COL_GATHER") != nullptr;       // A/B switch: the first (gather) kernel
+  if (!gather && smem <= 48 * 1024 && out->pad_w == 0 && batch <= 65535 && out->H <= 65535) {
+    dim3 grid((out->W + kTileQ - 1) / kTileQ, out->H, batch);
+    stem_im2col_tiled_kernel<<<grid, 256, smem, STREAM(stream)>>>(d_in, H, W, dv(out), kh, kw, stride, pad, sc[0], sc[1], sc[2], sh[0], sh[1],
+                                                                   sh[2], div_magic(out->C / 8), dtype);
+  } else {
+    stem_im2col_kernel<<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(d_in, H, W, dv(out), kh, kw, stride, pad, sc[0], sc[1], sc[2], sh[0],
+                                                                          sh[1], sh[2], (uint32_t)total, div_magic(out->C / 8), dtype);
+  }
   IFCB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

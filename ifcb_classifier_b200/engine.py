@@ -38,6 +38,8 @@ class BinClassifier(object):
         # pinned staging for the end-to-end path (grown on demand: a bin may hold more ROIs than one window)
         self.h_scores = torch.zeros((self.window, self.n_classes), dtype=torch.float32).pin_memory()
         self.h_top1 = torch.zeros(self.window, dtype=torch.int32).pin_memory()
+        self._slots = [[self.h_scores, self.h_top1, torch.cuda.Event()], None]      # two result slots: one bin in flight, one being consumed
+        self._next_slot = 0
         self.launches_last = 0
 
     def _alloc_bytes(self, nbytes):
@@ -49,6 +51,32 @@ class BinClassifier(object):
         if n > self.h_scores.shape[0]:
             self.h_scores = torch.zeros((n, self.n_classes), dtype=torch.float32).pin_memory()
             self.h_top1 = torch.zeros(n, dtype=torch.int32).pin_memory()
+            self._slots[0] = [self.h_scores, self.h_top1, torch.cuda.Event()]
+
+    # ---- pipelined end-to-end use (the RUN driver keeps one bin in flight while it files the previous bin's results) ----
+    def submit(self, roi, offsets, heights, widths):
+        """Enqueues upload + preprocess + network + download of one bin (asynchronous when ``roi`` is pinned) and returns a
+        ticket for ``fetch``.  At most two tickets may be outstanding."""
+        i = self._next_slot
+        self._next_slot ^= 1
+        n_all = int(len(offsets))
+        slot = self._slots[i]
+        if slot is None or slot[0].shape[0] < max(n_all, 1):
+            rows = max(n_all, self.window)
+            slot = self._slots[i] = [torch.zeros((rows, self.n_classes), dtype=torch.float32).pin_memory(),
+                                     torch.zeros(rows, dtype=torch.int32).pin_memory(), torch.cuda.Event()]
+        if i == 0:
+            self.h_scores, self.h_top1 = slot[0], slot[1]
+        self._classify_into(roi, offsets, heights, widths, slot[0], slot[1])
+        slot[2].record(torch.cuda.current_stream(self.device))
+        return i, n_all
+
+    def fetch(self, ticket):
+        """Waits for a submitted bin; returns (scores float32 [n, C], top-1 int32 [n]) -- views of the slot's pinned buffers,
+        valid until the slot is reused by the second-next ``submit``."""
+        i, n = ticket
+        self._slots[i][2].synchronize()
+        return self._slots[i][0][:n].numpy(), self._slots[i][1][:n].numpy()
 
     # ---- device-resident step -------------------------------------------------
     def classify_resident(self, roi, offsets, heights, widths, first=0, count=None, max_h=pp.FRAME_H, max_w=pp.FRAME_W):
@@ -88,6 +116,20 @@ class BinClassifier(object):
         return self.classify_resident(self.d_roi[:nbytes], self.d_off, self.d_h, self.d_w, 0, n, max_h, max_w)
 
     # ---- end to end -------------------------------------------------------------
+    def _classify_into(self, roi, offsets, heights, widths, h_scores, h_top1):
+        n_all = int(len(offsets))
+        if n_all == 0:
+            return
+        mh, mw = max(int(np.max(np.asarray(heights))), 1), max(int(np.max(np.asarray(widths))), 1)
+        launches = 0
+        for w0 in range(0, n_all, self.window):                    # one pass for any bin up to `window` ROIs
+            n, nbytes = self.upload(roi, offsets, heights, widths, w0, min(self.window, n_all - w0))
+            s, t1, _ = self.classify_device(n, nbytes, mh, mw)
+            h_scores[w0:w0 + n].copy_(s, non_blocking=True)
+            h_top1[w0:w0 + n].copy_(t1, non_blocking=True)
+            launches += self.launches_last
+        self.launches_last = launches
+
     def classify_bin(self, roi, offsets, heights, widths, sync=True):
         """Host bytes in -> host scores out (float32 [n, C], int32 top-1 [n]); views of pinned buffers that the next call
         overwrites.  Pinned inputs make the upload asynchronous."""
@@ -95,15 +137,7 @@ class BinClassifier(object):
         if n_all == 0:
             return np.zeros((0, self.n_classes), np.float32), np.zeros(0, np.int32)
         self._ensure_host(n_all)
-        mh, mw = max(int(np.max(np.asarray(heights))), 1), max(int(np.max(np.asarray(widths))), 1)
-        launches = 0
-        for w0 in range(0, n_all, self.window):                    # one pass for any bin up to `window` ROIs
-            n, nbytes = self.upload(roi, offsets, heights, widths, w0, min(self.window, n_all - w0))
-            s, t1, _ = self.classify_device(n, nbytes, mh, mw)
-            self.h_scores[w0:w0 + n].copy_(s, non_blocking=True)
-            self.h_top1[w0:w0 + n].copy_(t1, non_blocking=True)
-            launches += self.launches_last
-        self.launches_last = launches
+        self._classify_into(roi, offsets, heights, widths, self.h_scores, self.h_top1)
         if sync:
             torch.cuda.current_stream(self.device).synchronize()
         return self.h_scores[:n_all].numpy(), self.h_top1[:n_all].numpy()

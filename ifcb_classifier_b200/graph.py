@@ -125,7 +125,7 @@ class PlanBuilder(object):
         return tuple(pad) if algo == _lib.IFCB_CONV_WINDOW else (0, 0)
 
     # -- layers ---------------------------------------------------------------
-    def conv(self, x, members, stride=(1, 1), pad=(0, 0), residual=None, tile_n=0, name='conv', algo=0):
+    def conv(self, x, members, stride=(1, 1), pad=(0, 0), residual=None, tile_n=0, name='conv', algo=0, stats=None):
         """One implicit-GEMM launch.  ``members``: list of dicts
         (weight [Co,Ci,kh,kw] fp32, scale [Co], shift [Co], relu bool, out View) --
         more than one member = horizontally fused convs sharing input ``x``."""
@@ -179,6 +179,8 @@ class PlanBuilder(object):
         d.tile_n = tile_n
         d.algo = algo
         d.dtype = self.cdtype
+        if stats is not None:            # TRAIN: float64 [2][Co] accumulators the epilogue adds sum / sum of squares into
+            d.d_stats = int(stats)
         _lib.check(_lib.lib().ifcb_plan_add_conv(self.handle, C.byref(d)), 'plan_add_conv(%s)' % name)
         self._note(name, 'conv', 2 * P * Q * Co * Ci * kh * kw)
         return [m['out'] for m in members]

@@ -185,10 +185,12 @@ def do_run(args, classifier=None):
     import queue
     error_bins, n_bins, n_rois, t0 = [], 0, 0, time.time()
     work = [(base, pid) for base, pid in todo if base in mine]
-    depth, max_pending = 2, 4
+    depth = 2
+    n_writers = max(2, min(8, (os.cpu_count() or 4) // max(world, 1) - args.loaders))     # gzip-ing a bin's .h5 / .mat takes about as long as the GPU needs for it
+    max_pending = 3 * n_writers
     orientation = os.environ.get('IFCB_ROI_ORIENTATION', 'hw')
     ring = queue.Queue()
-    for _ in range(depth + 1):
+    for _ in range(depth + 2):                     # prefetched bins + the one in flight + the one being filed
         ring.put([torch.empty(32 << 20, dtype=torch.uint8).pin_memory()])
 
     def load(base, pid):
@@ -221,8 +223,24 @@ def do_run(args, classifier=None):
         except Exception as e:
             error_bins.append((name, type(e).__name__, str(e)))
 
-    pool = cf.ThreadPoolExecutor(max_workers=max(2, args.loaders))
+    pool = cf.ThreadPoolExecutor(max_workers=max(2, args.loaders))          # ingest
+    wpool = cf.ThreadPoolExecutor(max_workers=n_writers)                     # result files
     ahead, writes, nxt = collections.deque(), collections.deque(), 0
+    inflight = None                                # (ticket, RawBin, ring slot) of the bin the GPU is working on
+
+    def finish(item):
+        """Waits for a submitted bin and hands its results to the writer pool; frees its ring slot."""
+        ticket, rb, slot = item
+        try:
+            scores, top1 = eng.fetch(ticket)
+            writes.append((str(rb.pid), len(rb), wpool.submit(save, rb.pids, rb.pid, scores.copy(), top1.copy())))
+        except Exception as e:
+            error_bins.append((str(rb.pid), type(e).__name__, str(e)))
+        finally:
+            ring.put(slot)                         # the event has fired: the DMA out of the slot is complete
+        while len(writes) > max_pending:
+            collect(writes.popleft())
+
     for base, pid in work:
         while len(ahead) < depth and nxt < len(work):
             ahead.append(pool.submit(load, *work[nxt]))
@@ -232,19 +250,23 @@ def do_run(args, classifier=None):
             rb, slot = ahead.popleft().result()
             if len(rb) == 0:
                 error_bins.append((str(pid), 'AssertionError', 'Bin is Empty'))
+                ring.put(slot)
                 continue
-            scores, top1 = eng.classify_bin(rb.roi_t, rb.offsets, rb.heights, rb.widths)
-            writes.append((str(pid), len(rb), pool.submit(save, rb.pids, rb.pid, scores.copy(), top1.copy())))
+            ticket = eng.submit(rb.roi_t, rb.offsets, rb.heights, rb.widths)     # queued behind the bin in flight
         except Exception as e:      # per-bin isolation, as the reference
             error_bins.append((str(pid), type(e).__name__, str(e)))
-        finally:
             if slot is not None:
-                ring.put(slot)      # classify_bin has synchronised: the DMA out of the slot is complete
-        while len(writes) > max_pending:
-            collect(writes.popleft())
+                ring.put(slot)
+            continue
+        if inflight is not None:
+            finish(inflight)        # the GPU already holds the next bin's work while the host files this one
+        inflight = (ticket, rb, slot)
+    if inflight is not None:
+        finish(inflight)
     while writes:
         collect(writes.popleft())
     pool.shutdown()
+    wpool.shutdown()
     summary = dict(rank=rank, n_bins=n_bins, n_rois=n_rois, seconds=time.time() - t0, error_bins=error_bins)
     allsum = sharding.gather_summary(summary, world)
     if rank == 0:

@@ -142,6 +142,17 @@ class TrainNet(object):
         self.labels = torch.zeros((batch,), dtype=torch.int64, device=self.device)
         self.loss = torch.zeros((2,), dtype=torch.float32, device=self.device)     # [main + aux (weighted), unused]
         self.acc = torch.zeros((8192,), dtype=torch.float64, device=self.device)      # 64 KB BN scratch: float64 sums [0,4096), coefficient floats behind
+        # OPTIONAL: BatchNorm batch statistics gathered by the conv epilogues (ifcb_conv_desc.d_stats -> ifcb_bn_apply_sums): float64
+        # [2][Co] per unit, zeroed once per step, no statistics pass over z.  Parity-tested, but OFF by default: the ~60 extra
+        # epilogue instructions per 32x32 unit cost more than the removed pass on this kernel (the training convs are epilogue /
+        # HBM bound, not MMA bound) -- measured at batch 256: ResNet-50 9.46 k img/s without, 9.05 k with it on every conv, 9.31 k
+        # with it on K >= 512 convs only; Inception-v3 7.31 / 7.06 / 7.21 k (profiles/r02_train_epilogue_stats_ab.txt).
+        # IFCB_TRAIN_EPI_STATS=1 switches it on for convs with K = kh*kw*Cin >= IFCB_TRAIN_EPI_STATS_MINK.
+        self.epi_stats = os.environ.get('IFCB_TRAIN_EPI_STATS', '0') == '1'
+        self.epi_stats_mink = int(os.environ.get('IFCB_TRAIN_EPI_STATS_MINK', '512'))
+        n_stat = sum(2 * int(v.shape[0]) + 16 for k, v in sd.items() if v.dim() == 4)
+        self.stat_sums = torch.zeros((n_stat,), dtype=torch.float64, device=self.device)
+        self._stat_cursor = 0
         if arch == 'inception_v3':
             _build_inception_train(self, sd)
         elif arch in RESNET_CFG:
@@ -286,7 +297,12 @@ class TrainNet(object):
         mean, invstd = self._f32(Co), self._f32(Co)
         ones, zeros = torch.ones(Co), torch.zeros(Co)
         li = len(self.fp.layer_names)
-        self.fp.conv(x, [dict(weight=w, scale=ones, shift=zeros, relu=False, out=z if raw is None else raw)], stride, pad, name=conv)
+        sums_ptr = None
+        if self.epi_stats and raw is None and kh * kw * Ci >= self.epi_stats_mink:     # (a pooled branch normalises the POOLED tensor)
+            sums_ptr = self.stat_sums.data_ptr() + 8 * self._stat_cursor
+            self._stat_cursor += 2 * Co + (-(2 * Co) % 2)
+        self.fp.conv(x, [dict(weight=w, scale=ones, shift=zeros, relu=False, out=z if raw is None else raw)], stride, pad, name=conv,
+                     stats=sums_ptr)
         wf = self.fp.last_weight                                     # packed [Cout_pad, K_pad] 16-bit operand
         rawd = _vd(raw) if raw is not None else None
         zd, od = _vd(z), _vd(out)
@@ -298,6 +314,10 @@ class TrainNet(object):
             self.fp.run(B, li, li + 1)
             if rawd is not None:
                 self._call('ifcb_avgpool_fwd', C.byref(rawd), C.byref(zd), B, pool_after[0], pool_after[1], pool_after[2], dt, self._stream())
+            if sums_ptr is not None:
+                self._call('ifcb_bn_apply_sums', C.byref(zd), C.byref(od), C.byref(rd) if rd is not None else None, B, dt, sums_ptr, eps, 0.1,
+                           mean.data_ptr(), invstd.data_ptr(), rm.data_ptr(), rv.data_ptr(), pg.wptr, pb.wptr, 1 if relu else 0, self._stream())
+                return
             self._call('ifcb_bn_stats', C.byref(zd), B, dt, eps, 0.1, self.acc.data_ptr(), mean.data_ptr(), invstd.data_ptr(),
                        rm.data_ptr(), rv.data_ptr(), self._stream())
             self._call('ifcb_bn_apply', C.byref(zd), C.byref(od), C.byref(rd) if rd is not None else None, B, dt, mean.data_ptr(),
@@ -511,6 +531,8 @@ class TrainNet(object):
 
     def _forward_kernels(self):
         self._call('ifcb_memset_zero', self.loss.data_ptr(), 8, self._stream())
+        if self._stat_cursor:
+            self._call('ifcb_memset_zero', self.stat_sums.data_ptr(), 8 * self._stat_cursor, self._stream())
         for f in self.fwd:
             f()
 

@@ -155,6 +155,7 @@ enum { IFCB_CONV_AUTO = 0, IFCB_CONV_IM2COL = 1, IFCB_CONV_WINDOW = 2, IFCB_CONV
  *   d_scale/d_shift  float32[Cout_pad] folded BN (gamma/sqrt(var+eps), beta - mean*that)
  *   d_residual  optional bf16 view added before the activation (ResNet), or NULL
  *   tile_n      GEMM N tile (multiple of 16, 16..256); 0 = library picks
+ *   d_stats     see the field: per-channel sum / sum of squares of the stored outputs, accumulated by the epilogue
  */
 typedef struct {
   const void* d_in;
@@ -173,6 +174,10 @@ typedef struct {
   int32_t tile_n;
   int32_t algo;  /* IFCB_CONV_* */
   int32_t dtype; /* IFCB_ACT_* of input, weights, residual and outputs */
+  double* d_stats; /* optional (TRAIN, one segment): float64 [2][Cout] accumulators.  The epilogue ADDS, per output
+                      channel, the sum and the sum of squares of the 16-bit values it stores (sum over every valid
+                      output pixel of the launch) -- BatchNorm's batch statistics without a pass over the tensor
+                      (torch.nn.BatchNorm2d in train mode, reached from neuston_models.py:80-86).  NULL: off */
 } ifcb_conv_desc;
 
 int ifcb_plan_add_conv(ifcb_plan* plan, const ifcb_conv_desc* desc);
@@ -246,6 +251,14 @@ int ifcb_bn_stats(const ifcb_view* z, int batch, int dtype, float eps, float mom
 int ifcb_bn_apply(const ifcb_view* z, const ifcb_view* out, const ifcb_view* residual, int batch, int dtype,
                   const float* d_mean, const float* d_invstd, const float* d_gamma, const float* d_beta,
                   int relu, void* stream);
+/* The same pass with the batch statistics taken from the float64 sums the producing convolution's epilogue gathered
+ * (ifcb_conv_desc.d_stats: d_sums[c] = sum of z, d_sums[C + c] = sum of z^2 over batch*H*W pixels): mean / invstd are derived
+ * on the fly, written to d_mean / d_invstd for the backward pass, and the running statistics are updated as ifcb_bn_stats does
+ * (torch.nn.BatchNorm2d train mode).  Replaces ifcb_bn_stats + ifcb_bn_apply: no statistics pass over z. */
+int ifcb_bn_apply_sums(const ifcb_view* z, const ifcb_view* out, const ifcb_view* residual, int batch, int dtype,
+                       const double* d_sums, float eps, float momentum, float* d_mean, float* d_invstd,
+                       float* d_running_mean, float* d_running_var, const float* d_gamma, const float* d_beta, int relu,
+                       void* stream);
 /* Backward of (BN train -> [+residual] -> [ReLU]) -- autograd's threshold_backward +
  * native_batch_norm_backward:
  *   dy' = dy * [forward output > 0]   (relu = 1; the mask is recomputed from z with the forward's own
@@ -254,8 +267,9 @@ int ifcb_bn_apply(const ifcb_view* z, const ifcb_view* out, const ifcb_view* res
  *   d_dgamma[C] += sum(dy'*xhat), d_dbeta[C] += sum(dy')
  *   dres (optional, the residual branch's gradient) = or += dy'
  * dz may alias dy.  d_acc: the 64 KB scratch shared with ifcb_bn_stats: float64 [0, 4096) are per-channel
- * accumulators (2*C used; zero on entry, zero again on exit), the 3*C coefficient floats go behind them, the last
- * 8 bytes hold a block counter (zero on entry and exit): the last block of each reduction finalises in place. */
+ * accumulators (2*C used; zero on entry, zero again on exit), the 3*C coefficient floats go behind them, and 1 KB at
+ * float64 index 7680 holds one arrival counter per block of 64 channels (zero on entry and exit): the reductions run on
+ * a (pixel splits x channel blocks) grid and the last block of each channel block finalises its channels in place. */
 int ifcb_bn_backward(const ifcb_view* dy, const ifcb_view* a, const ifcb_view* z, const ifcb_view* dz,
                      const ifcb_view* dres, int dres_accumulate, int relu, int batch, int dtype,
                      const float* d_mean, const float* d_invstd, const float* d_gamma, const float* d_beta,
