@@ -340,6 +340,12 @@ def main():
         print(json.dumps(line))
         return 0
 
+    # rank 0 prints ONE JSON line on stdout: everything else that writes to file descriptor 1 (NCCL's version banner is a C-level
+    # printf) is sent to stderr for the whole run; the line goes out through the saved descriptor at the end
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     # synthetic bins first (worker processes are forked before any CUDA / NCCL state exists);
     # weak scaling: every rank owns its own bins (bins are sharded, no collective on the data path)
     workers = max(1, min(8, (os.cpu_count() or 1) // max(world, 1)))
@@ -496,7 +502,8 @@ def main():
             except Exception as e:
                 cb['config1'] = dict(error='%s: %s' % (type(e).__name__, e))
             line['cpu_baseline'] = cb
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + '\n').encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -103,6 +103,7 @@ _SIGNATURES = {
     'ifcb_plan_run': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     'ifcb_plan_run_at': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     'ifcb_plan_run_range': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    'ifcb_plan_refresh': (C.c_int, [C.c_void_p]),
     'ifcb_plan_num_layers': (C.c_int, [C.c_void_p]),
     'ifcb_plan_num_launches': (C.c_int, [C.c_void_p]),
     'ifcb_plan_add_conv': (C.c_int, [C.c_void_p, C.POINTER(ConvDesc)]),
@@ -112,6 +113,8 @@ _SIGNATURES = {
     'ifcb_conv_auto_config': (C.c_int, [C.c_int] * 10 + [C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     'ifcb_conv_auto_tile_n': (C.c_int, [C.c_int, C.c_int]),
     'ifcb_conv_wgrad': (C.c_int, [C.POINTER(WgradDesc), C.c_void_p]),
+    'ifcb_train_deterministic': (C.c_int, [C.c_void_p, C.c_int64]),
+    'ifcb_conv_wgrad_workspace_bytes': (C.c_int64, [C.POINTER(WgradDesc)]),
     'ifcb_memset_zero': (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p]),
     'ifcb_bn_stats': (C.c_int, [_V, C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -43,8 +43,10 @@ def build(force=False, verbose=False):
             sys.stderr.write(out)
         if p.returncode:
             raise RuntimeError('nvcc failed: ' + ' '.join(cmd))
-    cmd = [nvcc, '-shared', '-o', LIB] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a']
+    tmp = LIB + '.tmp.%d' % os.getpid()              # link aside, then rename: a reader never sees a half-written library
+    cmd = [nvcc, '-shared', '-o', tmp] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a']
     subprocess.check_call(cmd)
+    os.replace(tmp, LIB)
     return LIB
 
 

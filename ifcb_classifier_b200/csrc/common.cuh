@@ -92,4 +92,8 @@ inline unsigned long long div_magic(int d) { return d <= 1 ? 0ull : (~0ull) / (u
 
 int sm_count();
 
+// deterministic TRAIN mode (ifcb_train_deterministic): the workspace if one of at least `need` bytes is set, else NULL
+void* det_workspace(long long need);
+bool det_enabled();
+
 }  // namespace ifcb

@@ -46,7 +46,18 @@ struct WgradParams {
   int fp16;
   int dz_im2col;            // dz is loaded through a 4-D (1x1 window) im2col map: the gradient tensor has a zero border
   float* dW;                // [Cout][taps][Cin] fp32, accumulated into
+  float* ws;                // deterministic mode: [splits][Cout][taps][Cin] partials, STORED (each element by exactly one item)
+  long long ws_stride;      // Cout * taps * Cin
 };
+
+// deterministic mode, second pass: dW += sum over the pixel-range splits, in split order
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ ws, int splits, long long n, float* __restrict__ dW) {
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    float s = 0.f;
+    for (int k = 0; k < splits; ++k) s += ws[(long long)k * n + i];
+    dW[i] += s;
+  }
+}
 
 __global__ void __launch_bounds__(kWThreads, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_constant__ CUtensorMap tmap_x, const WgradParams p) {
@@ -219,7 +230,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_cons
           const int tap = blk / p.cblocks, cb = blk - tap * p.cblocks;
           const int ci = cb * 64 + (quad & 1) * 32 + lane;
           const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(g * p.tile_n);
-          float* dst = p.dW + ((size_t)co0 * p.taps + tap) * p.Cin + ci;
+          float* dst = (p.ws ? p.ws + (size_t)split * p.ws_stride : p.dW) + ((size_t)co0 * p.taps + tap) * p.Cin + ci;
           const size_t co_stride = (size_t)p.taps * p.Cin;
           for (int c0 = 0; c0 < ncols; c0 += 16) {
             uint32_t v[16];
@@ -228,8 +239,10 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_cons
             if (ci < p.Cin) {
 #pragma unroll
               for (int j = 0; j < 16; ++j)
-                if (c0 + j < ncols)
-                  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst + (size_t)(c0 + j) * co_stride), "f"(__uint_as_float(v[j])) : "memory");
+                if (c0 + j < ncols) {
+                  if (p.ws) dst[(size_t)(c0 + j) * co_stride] = __uint_as_float(v[j]);
+                  else asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst + (size_t)(c0 + j) * co_stride), "f"(__uint_as_float(v[j])) : "memory");
+                }
             }
           }
         }
@@ -356,15 +369,58 @@ extern "C" int ifcb_conv_wgrad(const ifcb_wgrad_desc* d, void* stream_v) {
   p.fp16 = d->dtype;
   p.dz_im2col = dz_border ? 1 : 0;
   p.dW = d->d_dweight;
+  p.ws_stride = (long long)d->Cout * p.taps * d->Cin;
+  p.ws = nullptr;
+  if (det_enabled()) {
+    p.ws = static_cast<float*>(det_workspace(4ll * p.splits * p.ws_stride));
+    IFCB_ARG_CHECK(p.ws != nullptr, "wgrad: the deterministic workspace is smaller than the %lld bytes this layer needs (ifcb_conv_wgrad_workspace_bytes)",
+                   4ll * p.splits * p.ws_stride);
+  }
   const int smem = p.dz_slots * p.nblk_n * kBlk + p.x_stages * kBlk + 512 + 1024;
-  static int attr = 0;
-  if (smem > attr) {
-    IFCB_CUDA_CHECK(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr = smem;
+  {   // the opt-in shared-memory limit is a per-device function attribute
+    static bool done[64] = {};
+    int dev = 0;
+    IFCB_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !done[dev]) {
+      IFCB_CUDA_CHECK(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      if (dev >= 0 && dev < 64) done[dev] = true;
+    }
   }
   const int items = p.n_cotiles * p.n_groups * p.splits;
   const int grid = items < sm_count() ? items : sm_count();
   conv_wgrad_kernel<<<grid, kWThreads, smem, reinterpret_cast<cudaStream_t>(stream_v)>>>(tmap_dz, tmap_x, p);
+  if (p.ws) {
+    long long g = (p.ws_stride + 255) / 256;
+    if (g > 8ll * sm_count()) g = 8ll * sm_count();
+    wgrad_reduce_kernel<<<(int)g, 256, 0, reinterpret_cast<cudaStream_t>(stream_v)>>>(p.ws, p.splits, p.ws_stride, p.dW);
+  }
   IFCB_CUDA_CHECK(cudaGetLastError());
   return 0;
+}
+
+// bytes of deterministic workspace ifcb_conv_wgrad needs for this layer (pixel-range splits x the layer's gradient)
+extern "C" int64_t ifcb_conv_wgrad_workspace_bytes(const ifcb_wgrad_desc* d) {
+  if (!d || d->Cin <= 0 || d->Cout <= 0 || d->kh <= 0 || d->kw <= 0) return -1;
+  const int P = (d->H + 2 * d->pad_h - d->kh) / d->stride_h + 1, Q = (d->W + 2 * d->pad_w - d->kw) / d->stride_w + 1;
+  const long long rows = (long long)d->batch * P * Q;
+  const int taps = d->kh * d->kw, cblocks = (d->Cin + 63) / 64;
+  const int n_mpairs = (taps * cblocks + 1) / 2;
+  const int c16 = (d->Cout + 15) & ~15;
+  const int t = (c16 + 255) / 256;
+  const int tile_n = (((c16 + t - 1) / t) + 15) & ~15;
+  const int n_cotiles = (d->Cout + tile_n - 1) / tile_n;
+  int n_acc = 512 / tile_n;
+  if (n_acc > 16) n_acc = 16;
+  int n_groups = (n_mpairs + n_acc - 1) / n_acc;
+  const int group_size = (n_mpairs + n_groups - 1) / n_groups;
+  n_groups = (n_mpairs + group_size - 1) / group_size;
+  const int ptiles = (int)((rows + kPix - 1) / kPix);
+  const int base_items = n_cotiles * n_groups;
+  static const int waves = getenv("IFCB_WGRAD_WAVES") ? atoi(getenv("IFCB_WGRAD_WAVES")) : 1;
+  int splits = (waves * sm_count() + base_items - 1) / base_items;
+  if (splits > ptiles) splits = ptiles;
+  if (splits < 1) splits = 1;
+  const int tiles_per_split = (ptiles + splits - 1) / splits;
+  splits = (ptiles + tiles_per_split - 1) / tiles_per_split;
+  return 4ll * splits * d->Cout * taps * d->Cin;
 }

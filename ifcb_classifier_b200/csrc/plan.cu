@@ -339,6 +339,21 @@ extern "C" int ifcb_plan_add_stem(ifcb_plan* plan, const ifcb_stem_desc* d) {
   return 0;
 }
 
+// After the caller has rewritten weights / folded BN vectors IN PLACE (same device buffers): re-reads the few values the plan
+// keeps on the host (the constant-bank stem's folded gray weights).  Synchronous; the caller has synchronised its stream.
+extern "C" int ifcb_plan_refresh(ifcb_plan* plan) {
+  IFCB_ARG_CHECK(plan != nullptr, "ifcb_plan_refresh: null plan");
+  for (auto& L : plan->layers) {
+    if (L.kind != kStem || L.stem.h_const.empty()) continue;
+    const ifcb_stem_desc& d = L.stem.d;
+    const int co = d.Cout;
+    IFCB_CUDA_CHECK(cudaMemcpy(L.stem.h_const.data(), d.d_wgray, sizeof(float) * 9 * co, cudaMemcpyDeviceToHost));
+    IFCB_CUDA_CHECK(cudaMemcpy(L.stem.h_const.data() + 9 * co, d.d_scale, sizeof(float) * co, cudaMemcpyDeviceToHost));
+    IFCB_CUDA_CHECK(cudaMemcpy(L.stem.h_const.data() + 10 * co, d.d_shift, sizeof(float) * co, cudaMemcpyDeviceToHost));
+  }
+  return 0;
+}
+
 extern "C" int ifcb_plan_add_pool(ifcb_plan* plan, const ifcb_pool_desc* d) {
   IFCB_ARG_CHECK(plan && d, "ifcb_plan_add_pool: null argument");
   IFCB_ARG_CHECK(d->d_in && d->d_out, "pool: null tensor pointer");

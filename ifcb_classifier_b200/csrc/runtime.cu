@@ -15,6 +15,14 @@ void set_error(const char* fmt, ...) {
 }
 const char* get_error() { return g_err; }
 
+// TRAIN deterministic mode (Trainer(deterministic=True) upstream): a caller-owned device workspace; while it is set, the weight
+// gradient's split-K partials and the BatchNorm reductions' per-block partials are STORED there and summed in a fixed order
+// instead of being combined with floating-point atomics.
+static void* g_det_ws = nullptr;
+static long long g_det_bytes = 0;
+void* det_workspace(long long need) { return (g_det_ws && need <= g_det_bytes) ? g_det_ws : nullptr; }
+bool det_enabled() { return g_det_ws != nullptr; }
+
 int sm_count() {
   static int cached = 0;
   if (cached > 0) return cached;
@@ -29,6 +37,13 @@ int sm_count() {
 extern "C" int ifcb_abi_version(void) { return IFCB_B200_ABI_VERSION; }
 extern "C" const char* ifcb_last_error(void) { return ifcb::get_error(); }
 extern "C" int ifcb_sm_count(void) { return ifcb::sm_count(); }
+extern "C" int ifcb_train_deterministic(void* d_workspace, int64_t bytes) {
+  IFCB_ARG_CHECK((d_workspace == nullptr) == (bytes == 0) && bytes >= 0, "ifcb_train_deterministic: pass a workspace and its size, or NULL and 0");
+  IFCB_ARG_CHECK((reinterpret_cast<uintptr_t>(d_workspace) & 255) == 0, "ifcb_train_deterministic: workspace must be 256-byte aligned");
+  ifcb::g_det_ws = d_workspace;
+  ifcb::g_det_bytes = bytes;
+  return 0;
+}
 
 // ---------------------------------------------------------------------------------------------
 // Host-side .adc parser (the CSV pyifcb reads with pandas upstream: reference neuston_data.py:446-454 via

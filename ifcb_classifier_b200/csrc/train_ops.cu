@@ -140,6 +140,8 @@ struct FinalizeArgs {
   float* dgamma;
   float* dbeta;
   unsigned int* counter;   // blocks finished so far (zero on entry, zero again on exit)
+  float* det_part;         // deterministic mode: per-block partial sums [channel block][pixel split][2 * channels of the block],
+                           // stored (no atomics) and summed by the finalising block in pixel-split order
 };
 
 // MODE 0: sums of z and z*z.   MODE 1: sums of dy' and dy' * (z - mean) (scaled by invstd at the end).
@@ -233,7 +235,8 @@ __global__ void __launch_bounds__(256, 2) channel_reduce_kernel(DV z, DV dy, DV 
     const int cc8 = cl >> 3, j = cl & 7;
     float s = 0.f;
     for (int r = 0; r < rows; ++r) s += red[(r * c8n + cc8) * 16 + which * 8 + j];
-    atomicAdd(acc + which * C + c_lo + cl, (double)s);
+    if (fin.det_part) fin.det_part[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * (2 * cb) + t] = s;
+    else atomicAdd(acc + which * C + c_lo + cl, (double)s);
   }
   // ---- last block of this channel block: finalize its channels (threadFenceReduction pattern) ----
   __threadfence();
@@ -242,7 +245,18 @@ __global__ void __launch_bounds__(256, 2) channel_reduce_kernel(DV z, DV dy, DV 
   __syncthreads();
   if (!s_last) return;
   for (int c = c_lo + tid; c < c_lo + cb; c += 256) {
-    const double s1 = __ldcg(acc + c), s2 = __ldcg(acc + C + c);
+    double s1, s2;
+    if (fin.det_part) {                     // fixed-order float64 sum of the blocks' partials
+      s1 = s2 = 0.0;
+      const float* pp = fin.det_part + (size_t)blockIdx.y * gridDim.x * (2 * cb) + (c - c_lo);
+      for (unsigned b = 0; b < gridDim.x; ++b) {
+        s1 += (double)__ldcg(pp + (size_t)b * (2 * cb));
+        s2 += (double)__ldcg(pp + (size_t)b * (2 * cb) + cb);
+      }
+    } else {
+      s1 = __ldcg(acc + c);
+      s2 = __ldcg(acc + C + c);
+    }
     if (MODE == 0) {
       const double mu = s1 / fin.count;
       double var = s2 / fin.count - mu * mu;
@@ -476,6 +490,55 @@ __global__ void __launch_bounds__(256) maxpool_fwd_kernel(DV x, DV y, uint8_t* _
         for (int j = 0; j < 8; ++j) {
           if (first || v[j] > best[j] || v[j] != v[j]) {
             best[j] = v[j];
+            bi[j] = tap;
+          }
+        }
+        first = false;
+      }
+    }
+    store8(y.p + pix_off(y, n, op, oq) + c8 * 8, fp16, best);
+    uint2 pk;
+    pk.x = (uint32_t)bi[0] | ((uint32_t)bi[1] << 8) | ((uint32_t)bi[2] << 16) | ((uint32_t)bi[3] << 24);
+    pk.y = (uint32_t)bi[4] | ((uint32_t)bi[5] << 8) | ((uint32_t)bi[6] << 16) | ((uint32_t)bi[7] << 24);
+    *reinterpret_cast<uint2*>(idx + (long long)m * x.C + c8 * 8) = pk;
+  }
+}
+
+// the same for 3x3 windows (every max pool of ResNet / Inception-v3): the nine 16-byte loads are issued together, then reduced in
+// window-scan order (same winner as the generic kernel: first maximum, NaN propagates)
+__global__ void __launch_bounds__(256) maxpool3_fwd_kernel(DV x, DV y, uint8_t* __restrict__ idx, int stride, int pad, int P, int Q,
+                                                           uint32_t total, unsigned long long magic_c8, int fp16) {
+  const uint32_t c8n = (uint32_t)(x.C >> 3);
+  for (uint32_t t = blockIdx.x * 256u + threadIdx.x; t < total; t += gridDim.x * 256u) {
+    const uint32_t m = fast_div(t, magic_c8);
+    const int c8 = (int)(t - m * c8n);
+    const uint32_t t2 = fast_div(m, y.magic_w);
+    const int oq = (int)(m - t2 * (uint32_t)Q);
+    const uint32_t nn = fast_div(t2, y.magic_h);
+    const int op = (int)(t2 - nn * (uint32_t)P), n = (int)nn;
+    const int h0 = op * stride - pad, w0 = oq * stride - pad;
+    uint4 v[9];
+    bool ok[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int s2 = 0; s2 < 3; ++s2) {
+        const int hh = h0 + r, ww = w0 + s2;
+        ok[r * 3 + s2] = (unsigned)hh < (unsigned)x.H && (unsigned)ww < (unsigned)x.W;
+        if (ok[r * 3 + s2]) v[r * 3 + s2] = ld16(x.p + pix_off(x, n, hh, ww) + c8 * 8);
+      }
+    float best[8];
+    int bi[8];
+    bool first = true;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      if (ok[tap]) {
+        float f[8];
+        cvt8(v[tap], fp16, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (first || f[j] > best[j] || f[j] != f[j]) {
+            best[j] = f[j];
             bi[j] = tap;
           }
         }
@@ -1096,6 +1159,11 @@ extern "C" int ifcb_bn_stats(const ifcb_view* z, int batch, int dtype, float eps
   fin.run_mean = d_running_mean;
   fin.run_var = d_running_var;
   fin.counter = reinterpret_cast<unsigned int*>(d_acc + 7680);       // one arrival counter per channel block (<= 256), behind the coefficients
+  if (det_enabled()) {
+    const long long need = 4ll * rc.grid.x * rc.grid.y * 16 * rc.c8b;
+    fin.det_part = static_cast<float*>(det_workspace(need));
+    IFCB_ARG_CHECK(fin.det_part != nullptr, "bn_stats: the deterministic workspace is smaller than %lld bytes", need);
+  }
   channel_reduce_kernel<0, kMaskNone><<<rc.grid, 256, 0, STREAM(stream)>>>(zz, zz, zz, nullptr, nullptr, nullptr, nullptr, M, rc.rows, dtype, d_acc,
                                                                            fin, rc.c8b);
   IFCB_CUDA_CHECK(cudaGetLastError());
@@ -1184,6 +1252,11 @@ extern "C" int ifcb_bn_backward(const ifcb_view* dy, const ifcb_view* a, const i
   fin.dbeta = d_dbeta;
   fin.counter = reinterpret_cast<unsigned int*>(d_acc + 7680);
   const ReduceCfg rc = reduce_cfg(M, z->C);
+  if (det_enabled()) {
+    const long long need = 4ll * rc.grid.x * rc.grid.y * 16 * rc.c8b;
+    fin.det_part = static_cast<float*>(det_workspace(need));
+    IFCB_ARG_CHECK(fin.det_part != nullptr, "bn_backward: the deterministic workspace is smaller than %lld bytes", need);
+  }
 #define IFCB_REDUCE1(MK) channel_reduce_kernel<1, MK><<<rc.grid, 256, 0, st>>>(zz, dyy, av, d_mean, d_invstd, d_gamma, d_beta, M, rc.rows, dtype, d_acc, fin, rc.c8b)
   if (mask_mode == kMaskFromZ) IFCB_REDUCE1(kMaskFromZ);
   else if (mask_mode == kMaskFromA) IFCB_REDUCE1(kMaskFromA);
@@ -1210,8 +1283,12 @@ extern "C" int ifcb_maxpool_fwd_train(const ifcb_view* x, const ifcb_view* y, ui
                  P, Q, x->C);
   const long long total = (long long)batch * P * Q * (x->C / 8);
   IFCB_ARG_CHECK(total < (1ll << 31), "maxpool_fwd_train: tensor too large for 32-bit indexing");
-  maxpool_fwd_kernel<<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(dv(x), dv(y), d_idx, k, stride, pad, P, Q, (uint32_t)total,
-                                                                        div_magic(x->C / 8), dtype);
+  if (k == 3)
+    maxpool3_fwd_kernel<<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(dv(x), dv(y), d_idx, stride, pad, P, Q, (uint32_t)total,
+                                                                           div_magic(x->C / 8), dtype);
+  else
+    maxpool_fwd_kernel<<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(dv(x), dv(y), d_idx, k, stride, pad, P, Q, (uint32_t)total,
+                                                                          div_magic(x->C / 8), dtype);
   IFCB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -1311,10 +1388,14 @@ extern "C" int ifcb_head_train_fwd(const ifcb_view* x, int batch, int dtype, con
   IFCB_ARG_CHECK(n_classes > 0 && (x->C + n_classes) * 4 <= 200 * 1024, "head_train_fwd: n_classes out of range");
   IFCB_ARG_CHECK((reinterpret_cast<uintptr_t>(d_weight) & 15) == 0, "head_train_fwd: weight must be 16-byte aligned");
   const int smem = (x->C + n_classes) * 4;
-  static int attr = 48 * 1024;
-  if (smem > attr) {
-    IFCB_CUDA_CHECK(cudaFuncSetAttribute(head_train_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr = smem;
+  if (smem > 48 * 1024) {   // per-device function attribute
+    static bool done[64] = {};
+    int dev = 0;
+    IFCB_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !done[dev]) {
+      IFCB_CUDA_CHECK(cudaFuncSetAttribute(head_train_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      if (dev >= 0 && dev < 64) done[dev] = true;
+    }
   }
   head_train_fwd_kernel<<<batch, 256, smem, STREAM(stream)>>>(dv(x), d_dropscale, d_weight, d_bias, reinterpret_cast<const long long*>(d_labels),
                                                                n_classes, batch, loss_weight, d_pooled, d_logits, d_dlogits, d_loss, dtype);

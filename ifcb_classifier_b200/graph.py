@@ -97,8 +97,26 @@ class PlanBuilder(object):
         _lib.check(_lib.lib().ifcb_plan_create(C.byref(handle)), 'plan_create')
         self.handle = handle
         self.flops_per_image = 0       # 2*MACs of the reference graph (algorithmic)
+        self._update = None            # index into self.keep while a weight refresh replays the construction (begin_update)
+
+    # -- weight refresh: replay the same construction sequence over the EXISTING buffers ------------------------
+    def begin_update(self):
+        """After this, re-running the graph builder with another state_dict overwrites the packed weights / folded BN
+        vectors in place (same launches, same pointers: captured CUDA graphs stay valid); nothing is allocated or added."""
+        self._update = 0
+
+    def end_update(self):
+        assert self._update == len(self.keep), 'weight refresh walked %d of %d buffers' % (self._update, len(self.keep))
+        self._update = None
+
+    def _next_kept(self):
+        t = self.keep[self._update]
+        self._update += 1
+        return t
 
     def _note(self, name, kind, flops):
+        if self._update is not None:
+            return
         self.layer_names.append(name)
         self.layer_kinds.append(kind)
         self.layer_flops.append(flops)
@@ -108,11 +126,19 @@ class PlanBuilder(object):
     def alloc(self, H, W, Cc, pad=(0, 0)):
         """Zero-initialised activation buffer with logical extent H x W and a zero border ``pad``
         (kernels only ever write interior pixels, so the border stays zero)."""
+        if self._update is not None:
+            t = self._next_kept()
+            assert tuple(t.shape) == (self.batch_cap, H + 2 * pad[0], W + 2 * pad[1], Cc)
+            return View(t, pad=pad)
         t = torch.zeros((self.batch_cap, H + 2 * pad[0], W + 2 * pad[1], Cc), dtype=self.tdtype, device=self.device)
         self.keep.append(t)
         return View(t, pad=pad)
 
     def dev(self, x, dtype):
+        if self._update is not None:
+            t = self._next_kept()
+            t.copy_(x.detach().to(dtype=dtype).reshape(t.shape))
+            return t
         t = x.detach().to(device=self.device, dtype=dtype).contiguous()
         self.keep.append(t)
         return t
@@ -181,7 +207,8 @@ class PlanBuilder(object):
         d.dtype = self.cdtype
         if stats is not None:            # TRAIN: float64 [2][Co] accumulators the epilogue adds sum / sum of squares into
             d.d_stats = int(stats)
-        _lib.check(_lib.lib().ifcb_plan_add_conv(self.handle, C.byref(d)), 'plan_add_conv(%s)' % name)
+        if self._update is None:
+            _lib.check(_lib.lib().ifcb_plan_add_conv(self.handle, C.byref(d)), 'plan_add_conv(%s)' % name)
         self._note(name, 'conv', 2 * P * Q * Co * Ci * kh * kw)
         return [m['out'] for m in members]
 
@@ -216,7 +243,8 @@ class PlanBuilder(object):
         d.d_out, d.out_ld, d.relu = out.ptr, out.ld, 1 if relu else 0
         d.dtype = self.cdtype
         d.out_pad_h, d.out_pad_w = out.pad
-        _lib.check(_lib.lib().ifcb_plan_add_stem(self.handle, C.byref(d)), 'plan_add_stem')
+        if self._update is None:
+            _lib.check(_lib.lib().ifcb_plan_add_stem(self.handle, C.byref(d)), 'plan_add_stem')
         self._note(name, 'stem', 2 * out.H * out.W * Co * 3 * kh * kw)
         return out
 
@@ -233,7 +261,8 @@ class PlanBuilder(object):
         d.dtype = self.cdtype
         d.in_pad_h, d.in_pad_w = x.pad
         d.out_pad_h, d.out_pad_w = out.pad
-        _lib.check(_lib.lib().ifcb_plan_add_pool(self.handle, C.byref(d)), 'plan_add_pool(%s)' % name)
+        if self._update is None:
+            _lib.check(_lib.lib().ifcb_plan_add_pool(self.handle, C.byref(d)), 'plan_add_pool(%s)' % name)
         self._note(name, 'pool', 0)
         return out
 
@@ -241,6 +270,10 @@ class PlanBuilder(object):
         n_classes = int(weight.shape[0])
         assert x.pad == (0, 0), 'head input must be unpadded'
         B, rows = self.batch_cap, self.out_rows
+        if self._update is not None:
+            self.dev(weight, torch.float32)
+            self.dev(bias, torch.float32)
+            return self.scores
         self.scores = torch.zeros((rows, n_classes), dtype=torch.float32, device=self.device)
         self.logits = torch.zeros((rows, n_classes), dtype=torch.float32, device=self.device)
         self.top1 = torch.zeros((rows,), dtype=torch.int32, device=self.device)
@@ -738,22 +771,39 @@ class CompiledNet(object):
             self.inp = torch.zeros((batch_cap, 3, self.R, self.R), dtype=torch.float32, device=self.device)
             kind = IFCB_STEM_IN_F32_NCHW
             affine = None
-        if arch == 'inception_v3':
-            build_inception_v3(pb, sd, self.inp, kind, self.R, affine=affine, transform_input=transform_input, fuse=fuse)
-        elif arch in RESNET_CFG:
-            build_resnet(pb, sd, arch, self.inp, kind, self.R, affine=affine)
-        elif arch in PLAIN_ARCHS:
-            build_plain_cnn(pb, sd, arch, self.inp, kind, self.R, affine=affine)
-        elif arch == 'squeezenet':
-            build_squeezenet(pb, sd, self.inp, kind, self.R, affine=affine)
-        elif arch.startswith('densenet'):
-            build_densenet(pb, sd, self.inp, kind, self.R, affine=affine)
-        else:
-            raise KeyError('model unknown!')
+        self._build_args = dict(kind=kind, affine=affine, transform_input=transform_input, fuse=fuse)
+        self._build(pb, sd)
         self.pb = pb
         self.n_classes = int(pb.scores.shape[1])
         self.flops_per_image = pb.flops_per_image
         self.num_launches = _lib.lib().ifcb_plan_num_launches(pb.handle)
+
+    def _build(self, pb, sd):
+        arch, a = self.arch, self._build_args
+        if arch == 'inception_v3':
+            build_inception_v3(pb, sd, self.inp, a['kind'], self.R, affine=a['affine'], transform_input=a['transform_input'], fuse=a['fuse'])
+        elif arch in RESNET_CFG:
+            build_resnet(pb, sd, arch, self.inp, a['kind'], self.R, affine=a['affine'])
+        elif arch in PLAIN_ARCHS:
+            build_plain_cnn(pb, sd, arch, self.inp, a['kind'], self.R, affine=a['affine'])
+        elif arch == 'squeezenet':
+            build_squeezenet(pb, sd, self.inp, a['kind'], self.R, affine=a['affine'])
+        elif arch.startswith('densenet'):
+            build_densenet(pb, sd, self.inp, a['kind'], self.R, affine=a['affine'])
+        else:
+            raise KeyError('model unknown!')
+
+    def load_state_dict(self, state_dict):
+        """Refreshes the packed weights and folded BatchNorm vectors IN PLACE from another state_dict of the same architecture
+        (TRAIN validates every epoch with the current weights: no new plan, no new activation buffers, graphs stay valid)."""
+        sd = {k: v.detach().cpu() for k, v in state_dict.items()}
+        self.pb.begin_update()
+        self._build(self.pb, sd)
+        self.pb.end_update()
+        torch.cuda.synchronize(self.device)
+        _lib.check(_lib.lib().ifcb_plan_refresh(self.pb.handle), 'plan_refresh')
+        if getattr(self, '_graphs', None):          # the stem's constant-bank weights are kernel PARAMETERS baked into captured graphs
+            self.enable_cuda_graph()
 
     def enable_cuda_graph(self):
         """Captures the full-batch forward (every launch of the plan) into CUDA graphs, one per output slot

@@ -30,6 +30,9 @@ def argparse_nn(parser=None):
     common.add_argument('--loaders', metavar='N', default=4, type=int)
     common.add_argument('--dtype', default='fp16', choices=['fp16', 'bf16'],
                         help='tensor-core operand format of eval-mode forward passes (B200 extension; default fp16)')
+    common.add_argument('--deterministic', action='store_true',
+                        help='TRAIN: bitwise reproducible steps (ordered reductions instead of floating-point atomics; the reference '
+                             'runs Trainer(deterministic=True)); a few %% slower (B200 extension)')
     common.add_argument('--train-dtype', dest='train_dtype', default='bf16', choices=['bf16'],
                         help='16-bit storage format of the TRAIN step (B200 extension)')
     _train_args(train)

@@ -96,7 +96,8 @@ class TrainNet(object):
     """
 
     def __init__(self, arch, state_dict, batch, device='cuda', dtype='bf16', lr=1e-3, betas=(0.9, 0.999), eps=1e-8,
-                 dropout=True, seed=0, R=None, bucket_mb=32, keep_dy=False, window=True, transform_input=False, share=None):
+                 dropout=True, seed=0, R=None, bucket_mb=32, keep_dy=False, window=True, transform_input=False, share=None,
+                 deterministic=False):
         """``share``: another TrainNet of the same architecture whose parameter / gradient / Adam arenas, BatchNorm running
         statistics and step counter this one uses instead of allocating its own -- a second plan for another batch size over
         the SAME model (the short last batch of an epoch, neuston_models.py:80-86 trains on it as is).  The two plans keep
@@ -113,6 +114,10 @@ class TrainNet(object):
         self.transform_input = bool(transform_input) and arch == 'inception_v3'
         self.keep_dy = bool(keep_dy)        # tests: keep d(activation) next to d(conv output) instead of overwriting it
         self._share = share
+        # Trainer(deterministic=True) upstream (neuston_net.py:101): two-pass split-K weight gradients and ordered BatchNorm
+        # reductions instead of floating-point atomics (ifcb_train_deterministic): bitwise reproducible steps, a few % slower
+        self.deterministic = bool(deterministic)
+        self._det_need = 2 << 20
         self._steps = share._steps if share is not None else [0]      # optimizer step counter (shared between plans of one model)
         self._reducer = None
         self.lib = _lib.lib()
@@ -172,6 +177,9 @@ class TrainNet(object):
             self.v = torch.zeros_like(self.params)
         self._plan_grad_borders()
         self._finalize(int(bucket_mb) << 20)
+        if self.deterministic:
+            self._det_ws = torch.zeros(self._det_need, dtype=torch.uint8, device=self.device)       # (torch allocations are 512-byte aligned)
+            _lib.check(self.lib.ifcb_train_deterministic(self._det_ws.data_ptr(), self._det_ws.numel()), 'train_deterministic')
         self.repack()
 
     # ---- plumbing ---------------------------------------------------------------------------
@@ -485,6 +493,9 @@ class TrainNet(object):
         wd.d_dout, wd.dout_ld, wd.Cout = dz.ptr, dz.ld, Co
         wd.dout_pad_h, wd.dout_pad_w = dz.pad
         wd.dtype = dt
+
+        if self.deterministic:
+            self._det_need = max(self._det_need, int(self.lib.ifcb_conv_wgrad_workspace_bytes(C.byref(wd))))
 
         def wgrad():
             wd.d_dweight = pw.gptr

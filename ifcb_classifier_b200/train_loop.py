@@ -199,7 +199,7 @@ def do_training(args):
         print('pretrained=True: torchvision weights are taken from the local cache (no network on this host)')
     B = args.batch_size
     net = TrainNet(args.MODEL, classifier.model.state_dict(), B, device=dev, dtype=getattr(args, 'train_dtype', 'bf16'), seed=args.seed,
-                   R=args.resize, transform_input=classifier.model.transform_input)
+                   R=args.resize, transform_input=classifier.model.transform_input, deterministic=getattr(args, 'deterministic', False))
     net.enable_cuda_graph()                                       # replay the step's ~10^3 launches from CUDA graphs
     train_loader = ImageBatcher(train_ds, B, dev, args.loaders, rank, world, shuffle=True, seed=args.seed, drop_last=False)
     val_loader = ImageBatcher(val_ds, B, dev, args.loaders, 0, 1, shuffle=False, seed=args.seed)
@@ -209,6 +209,7 @@ def do_training(args):
     log_rows, best_val, best_epoch, best_path, wait = [], np.inf, 0, None, 0
     hp = {k: v for k, v in vars(args).items()}
     tail_nets = {}                                                # plans for the short last batch of an epoch (shared arenas)
+    ev = None                                                     # eval-mode plan of the validation pass
     for epoch in range(args.emax):
         t0 = time.time()
         agg_train_loss, losses = 0.0, []
@@ -219,7 +220,8 @@ def do_training(args):
                 # n samples): a second plan of that size over the SAME parameter / Adam arenas
                 if n not in tail_nets:
                     tail_nets[n] = TrainNet(args.MODEL, classifier.model.state_dict(), n, device=dev, dtype=getattr(args, 'train_dtype', 'bf16'),
-                                            seed=args.seed, R=args.resize, transform_input=classifier.model.transform_input, share=net)
+                                            seed=args.seed, R=args.resize, transform_input=classifier.model.transform_input, share=net,
+                                            deterministic=getattr(args, 'deterministic', False))
                 tail = tail_nets[n]
                 tail.repack()                                     # its 16-bit operands are stale: the main plan has stepped since
                 losses.append(tail.step(x, y).clone())
@@ -236,8 +238,11 @@ def do_training(args):
                 if b_.is_cuda:
                     torch.distributed.broadcast(b_, 0)
         sd = net.state_dict()
-        ev = CompiledNet(args.MODEL, sd, B, in_kind='f32', R=args.resize, device=dev, dtype=getattr(args, 'dtype', 'fp16'),
-                         transform_input=classifier.model.transform_input)
+        if ev is None:                            # one eval plan for the whole run; later epochs refresh its weights in place
+            ev = CompiledNet(args.MODEL, sd, B, in_kind='f32', R=args.resize, device=dev, dtype=getattr(args, 'dtype', 'fp16'),
+                             transform_input=classifier.model.transform_input)
+        else:
+            ev.load_state_dict(sd)
         val_loss, outs, ins, srcs = 0.0, [], [], []
         for x, y, paths in val_loader:
             n = int(x.shape[0])
@@ -247,7 +252,6 @@ def do_training(args):
             outs.append(scores.cpu().numpy().copy())
             ins.append(y.cpu().numpy())
             srcs.extend(paths)
-        del ev
         outputs, input_classes = np.concatenate(outs), np.concatenate(ins)
         stats = _validation_stats(input_classes, np.argmax(outputs, 1), len(args.classes))
         if world > 1:

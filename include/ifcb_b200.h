@@ -116,6 +116,9 @@ int ifcb_plan_run(ifcb_plan* plan, int batch, void* stream);
 int ifcb_plan_run_at(ifcb_plan* plan, int batch, int out_row, void* stream);
 /* Runs layers [first, last) only (layer-level tests, profiling). */
 int ifcb_plan_run_range(ifcb_plan* plan, int first, int last, int batch, void* stream);
+/* Call after rewriting a plan's weights / folded BN vectors in place (same buffers, e.g. the current weights of a TRAIN run
+ * before each validation pass, neuston_models.py:94-103): refreshes the values the plan caches on the host.  Synchronous. */
+int ifcb_plan_refresh(ifcb_plan* plan);
 int ifcb_plan_num_layers(const ifcb_plan* plan);
 /* Kernel launches one ifcb_plan_run performs. */
 int ifcb_plan_num_launches(const ifcb_plan* plan);
@@ -222,6 +225,13 @@ typedef struct {
   int32_t dout_pad_h, dout_pad_w; /* zero border of the d_dout tensor (d_dout = its first border pixel) */
 } ifcb_wgrad_desc;
 int ifcb_conv_wgrad(const ifcb_wgrad_desc* desc, void* stream);
+/* Deterministic TRAIN mode (the reference runs Trainer(deterministic=True), neuston_net.py:101): while a caller-owned device
+ * workspace is set, ifcb_conv_wgrad STORES its split-K partial sums there and adds them into d_dweight in split order, and the
+ * BatchNorm reductions (ifcb_bn_stats / ifcb_bn_backward) store per-block partials and sum them in block order -- no
+ * floating-point atomics on the parameter path: a step is bitwise reproducible.  Process-wide; NULL / 0 switches it off.
+ * ifcb_conv_wgrad_workspace_bytes: what one layer needs (the BatchNorm partials need < 2 MB). */
+int ifcb_train_deterministic(void* d_workspace, int64_t bytes);
+int64_t ifcb_conv_wgrad_workspace_bytes(const ifcb_wgrad_desc* desc);
 
 /* A channel slice of an NHWC 16-bit activation (or gradient) tensor, as the Python host's
  * graph.View: logical extent [batch, H, W, C], stored with a zero border of pad_h / pad_w pixels

@@ -303,3 +303,28 @@ def test_run_cli_default_outfile_is_h5(cuda, tmp_path, capsys):
         assert f['output_scores'].shape == (n, 5) and f['metadata'].attrs['bin_id'] == lid and f['metadata'].attrs['model_id'] == 'm5'
         assert np.array_equal(f['output_scores'].data, np.asarray(j['output_scores'], np.float32).astype(np.float16))
         assert f['roi_numbers'].data.tolist() == j['roi_numbers'] and f['class_labels'].data.tolist() == hp.classes
+
+
+def test_weight_refresh_in_place_matches_a_fresh_plan(cuda):
+    """CompiledNet.load_state_dict rewrites packed weights / folded BN vectors in the existing buffers (TRAIN's per-epoch
+    validation): scores equal those of a plan built from scratch with the new weights, for both input kinds (the u8 plan's
+    constant-bank stem caches weights on the host: ifcb_plan_refresh) and with captured CUDA graphs."""
+    from ifcb_classifier_b200.graph import CompiledNet
+    arch = 'inception_v3'
+    m1, m2 = fixtures.ref_model(arch, 12, seed=1), fixtures.ref_model(arch, 12, seed=2)
+    g = torch.Generator().manual_seed(0)
+    xu = torch.randint(0, 256, (8, 299, 299), generator=g, dtype=torch.uint8).to(cuda)
+    for m in (m1, m2):
+        fixtures.calibrate_bn(m, xu[:8].float().div(255)[:, None].repeat(1, 3, 1, 1).cpu(), 'cpu')
+    for kind in ('u8', 'f32'):
+        a = CompiledNet(arch, m1.state_dict(), 8, in_kind=kind, device=cuda)
+        if kind == 'u8':
+            a.enable_cuda_graph()
+        b = CompiledNet(arch, m2.state_dict(), 8, in_kind=kind, device=cuda)
+        x = xu if kind == 'u8' else xu.float().div(255)[:, None].repeat(1, 3, 1, 1)
+        a.inp.copy_(x); b.inp.copy_(x)
+        before = a.forward(8)[0].clone()
+        a.load_state_dict(m2.state_dict())
+        after, want = a.forward(8)[0].clone(), b.forward(8)[0].clone()
+        torch.cuda.synchronize()
+        assert torch.equal(after, want) and not torch.equal(before, want), kind

@@ -692,3 +692,37 @@ def test_short_last_batch_plan_shares_the_model(cuda):
     sd, rsd = net.state_dict(), ref.state_dict()
     assert int(sd['bn1.num_batches_tracked']) == 3
     assert torch.allclose(sd['bn1.running_mean'], rsd['bn1.running_mean'].cpu(), rtol=5e-2, atol=5e-3)
+
+
+def test_deterministic_mode_is_bitwise_reproducible(cuda):
+    """Trainer(deterministic=True) upstream (neuston_net.py:101): with the deterministic workspace set, the weight gradient's
+    split-K partials and the BatchNorm reductions are summed in a fixed order, so two runs of the same steps from the same
+    state give bit-identical parameters (the default path combines them with floating-point atomics); and the deterministic
+    result agrees with the default one to rounding."""
+    from tests.fixtures import ref_model
+    from ifcb_classifier_b200 import _lib
+    from ifcb_classifier_b200.train import TrainNet
+    B, R, C = 16, 96, 7
+    g = torch.Generator().manual_seed(21)
+    model = ref_model('resnet50', C, seed=9)
+    xs = [torch.rand(B, 3, R, R, generator=g).to(cuda) for _ in range(3)]
+    ys = [torch.randint(0, C, (B,), generator=g).to(cuda) for _ in range(3)]
+
+    def run(det):
+        net = TrainNet('resnet50', model.state_dict(), B, device=cuda, R=R, deterministic=det, dropout=False)
+        losses = [float(net.step(x, y)) for x, y in zip(xs, ys)]
+        torch.cuda.synchronize()
+        p, rm = net.params.clone(), net.buffers['layer3.2.bn2.running_var'].clone()
+        del net
+        return p, rm, losses
+
+    try:
+        a, ra, la = run(True)
+        b, rb, lb = run(True)
+        assert torch.equal(a, b) and torch.equal(ra, rb), 'deterministic mode is not reproducible'
+    finally:
+        _lib.check(_lib.lib().ifcb_train_deterministic(None, 0), 'train_deterministic off')
+    c, rc_, lc = run(False)
+    # same arithmetic up to the order of the split-K / block sums: three Adam steps stay close
+    assert abs(la[0] - lc[0]) <= 1e-4 * abs(lc[0]) and torch.allclose(ra, rc_, rtol=5e-2, atol=1e-4)
+    assert float((a - c).abs().max()) <= 1e-2            # (an Adam step moves a weight by ~lr whatever the gradient size: sign flips of ~0 gradients)
