@@ -124,6 +124,10 @@ _SIGNATURES = {
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     'ifcb_bn_backward': (C.c_int, [_V, _V, _V, _V, _V, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'ifcb_bn_backward_accumulate': (C.c_int, [_V, _V, _V, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'ifcb_bias_relu_backward': (C.c_int, [_V, _V, _V, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'ifcb_scale_elems': (C.c_int, [_V, _V, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     'ifcb_maxpool_fwd_train': (C.c_int, [_V, _V, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     'ifcb_maxpool_bwd': (C.c_int, [_V, C.c_void_p, _V, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     'ifcb_avgpool_fwd': (C.c_int, [_V, _V, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),

@@ -394,7 +394,7 @@ __global__ void __launch_bounds__(256, 3) bn_apply_sums_kernel(DV z, DV out, DV 
 // dz = A * dy' + Bz * z + D with dy' = relu-masked dy; optionally routes dy' to the residual branch
 // (RES 1: written, 2: accumulated).  dz may alias dy (in place).  Same thread mapping as bn_apply_kernel,
 // two rows in flight (the six per-channel vectors already take 48 registers).
-template <int MASK, int RES>
+template <int MASK, int RES, bool ACC = false>
 __global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(DV dy, DV a, DV z, DV dz, DV dres, const float* __restrict__ mean,
                                                               const float* __restrict__ invstd, const float* __restrict__ gamma,
                                                               const float* __restrict__ beta, const float* __restrict__ coef,
@@ -452,9 +452,110 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(DV dy, DV a, DV z,
         float o[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = fmaf(A[j], g[j], fmaf(Bz[j], zv[j], D[j]));
+        if (ACC) {                       // dz += ... (the target already holds other consumers' contributions)
+          float old[8];
+          load8(dz.p + pix_off_m(dz, m) + c8 * 8, fp16, old);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] += old[j];
+        }
         store8(dz.p + pix_off_m(dz, m) + c8 * 8, fp16, o);
       }
     }
+  }
+}
+
+// Backward of (conv + bias -> [ReLU]) for the families without BatchNorm (AlexNet, VGG, SqueezeNet; torchvision alexnet.py /
+// vgg.py / squeezenet.py reached from NeustonModel.training_step, neuston_models.py:80-86): dz = dy * [a > 0] written (dz may
+// alias dy), dbias[c] += sum over pixels of dz.  One pass; the same (pixel splits x channel blocks) grid and float64 / ordered
+// partial-sum machinery as channel_reduce_kernel.
+template <bool RELU>
+__global__ void __launch_bounds__(256, 2) bias_relu_bwd_kernel(DV dy, DV a, DV dz, long long M, int rows, int fp16, double* __restrict__ acc,
+                                                               float* __restrict__ dbias, unsigned int* __restrict__ counter,
+                                                               float* __restrict__ det_part, int c8b) {
+  __shared__ float red[256 * 8];
+  __shared__ int s_last;
+  const int tid = threadIdx.x;
+  const int row = tid / c8b, c8 = blockIdx.y * c8b + (tid - row * c8b);
+  float s1[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s1[j] = 0.f;
+  if (row < rows) {
+    const long long stride = (long long)gridDim.x * rows;
+    for (long long m0 = (long long)blockIdx.x * rows + row; m0 < M; m0 += stride * kUnroll) {
+      uint4 gr[kUnroll], ar[kUnroll];
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const long long m = m0 + u * stride;
+        if (m < M) {
+          gr[u] = ld16(dy.p + pix_off_m(dy, m) + c8 * 8);
+          if (RELU) ar[u] = ld16(a.p + pix_off_m(a, m) + c8 * 8);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const long long m = m0 + u * stride;
+        if (m < M) {
+          float g[8];
+          cvt8(gr[u], fp16, g);
+          if (RELU) {
+            float av[8];
+            cvt8(ar[u], fp16, av);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) g[j] = av[j] > 0.f ? g[j] : 0.f;
+            store8(dz.p + pix_off_m(dz, m) + c8 * 8, fp16, g);
+          } else if (dz.p != dy.p) {
+            store8(dz.p + pix_off_m(dz, m) + c8 * 8, fp16, g);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) s1[j] += g[j];
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[tid * 8 + j] = s1[j];
+  __syncthreads();
+  const int C = dy.C, cb = 8 * c8b, c_lo = blockIdx.y * cb;
+  for (int t = tid; t < cb; t += 256) {
+    const int cc8 = t >> 3, j = t & 7;
+    float s = 0.f;
+    for (int r = 0; r < rows; ++r) s += red[(r * c8b + cc8) * 8 + j];
+    if (det_part) det_part[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * cb + t] = s;
+    else atomicAdd(acc + c_lo + t, (double)s);
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(counter + blockIdx.y, 1u) == gridDim.x - 1) ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  for (int c = c_lo + tid; c < c_lo + cb && c < C; c += 256) {
+    double s = 0.0;
+    if (det_part) {
+      const float* pp = det_part + (size_t)blockIdx.y * gridDim.x * cb + (c - c_lo);
+      for (unsigned b = 0; b < gridDim.x; ++b) s += (double)__ldcg(pp + (size_t)b * cb);
+    } else {
+      s = __ldcg(acc + c);
+      acc[c] = 0.0;
+    }
+    dbias[c] += (float)s;
+  }
+  if (tid == 0) counter[blockIdx.y] = 0u;
+}
+
+// y = x * scale, element-wise, scale float32 in the logical [batch, H, W, C] order (dropout masks of the classifier stacks:
+// alexnet.py / vgg.py / squeezenet.py nn.Dropout in train mode; the backward pass applies the same scale to the gradient)
+__global__ void __launch_bounds__(256) scale_elems_kernel(DV x, DV y, const float* __restrict__ scale, uint32_t total,
+                                                          unsigned long long magic_c8, int fp16) {
+  const uint32_t c8n = (uint32_t)(x.C >> 3);
+  for (uint32_t t = blockIdx.x * 256u + threadIdx.x; t < total; t += gridDim.x * 256u) {
+    const uint32_t m = fast_div(t, magic_c8);
+    const int c8 = (int)(t - m * c8n);
+    float v[8], sc[8];
+    load8(x.p + pix_off_m(x, m) + c8 * 8, fp16, v);
+    ldg8(scale + (long long)m * x.C + c8 * 8, sc);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] *= sc[j];
+    store8(y.p + pix_off_m(y, m) + c8 * 8, fp16, v);
   }
 }
 
@@ -1219,10 +1320,30 @@ extern "C" int ifcb_bn_apply_sums(const ifcb_view* z, const ifcb_view* out, cons
   return 0;
 }
 
+static int bn_backward_impl(const ifcb_view* dy, const ifcb_view* a, const ifcb_view* z, const ifcb_view* dz,
+                            const ifcb_view* dres, int dres_accumulate, int relu, int batch, int dtype, const float* d_mean,
+                            const float* d_invstd, const float* d_gamma, const float* d_beta, double* d_acc, float* d_dgamma,
+                            float* d_dbeta, int dz_accumulate, void* stream);
+
 extern "C" int ifcb_bn_backward(const ifcb_view* dy, const ifcb_view* a, const ifcb_view* z, const ifcb_view* dz,
                                 const ifcb_view* dres, int dres_accumulate, int relu, int batch, int dtype, const float* d_mean,
                                 const float* d_invstd, const float* d_gamma, const float* d_beta, double* d_acc, float* d_dgamma,
                                 float* d_dbeta, void* stream) {
+  return bn_backward_impl(dy, a, z, dz, dres, dres_accumulate, relu, batch, dtype, d_mean, d_invstd, d_gamma, d_beta, d_acc, d_dgamma,
+                          d_dbeta, 0, stream);
+}
+
+extern "C" int ifcb_bn_backward_accumulate(const ifcb_view* dy, const ifcb_view* z, const ifcb_view* dz, int relu, int batch, int dtype,
+                                           const float* d_mean, const float* d_invstd, const float* d_gamma, const float* d_beta,
+                                           double* d_acc, float* d_dgamma, float* d_dbeta, void* stream) {
+  return bn_backward_impl(dy, nullptr, z, dz, nullptr, 0, relu, batch, dtype, d_mean, d_invstd, d_gamma, d_beta, d_acc, d_dgamma, d_dbeta, 1,
+                          stream);
+}
+
+static int bn_backward_impl(const ifcb_view* dy, const ifcb_view* a, const ifcb_view* z, const ifcb_view* dz,
+                            const ifcb_view* dres, int dres_accumulate, int relu, int batch, int dtype, const float* d_mean,
+                            const float* d_invstd, const float* d_gamma, const float* d_beta, double* d_acc, float* d_dgamma,
+                            float* d_dbeta, int dz_accumulate, void* stream) {
   IFCB_ARG_CHECK(view_ok(dy) && view_ok(z) && view_ok(dz) && batch > 0 && DT_OK(dtype), "bn_backward: bad view / batch / dtype");
   IFCB_ARG_CHECK(z->C <= 2048, "bn_backward: C=%d > 2048", z->C);
   IFCB_ARG_CHECK(dy->C == z->C && dz->C == z->C && dy->H == z->H && dy->W == z->W && dz->H == z->H && dz->W == z->W,
@@ -1264,6 +1385,11 @@ extern "C" int ifcb_bn_backward(const ifcb_view* dy, const ifcb_view* a, const i
 #undef IFCB_REDUCE1
 #define IFCB_BWD_APPLY(MK, RS) \
   bn_bwd_apply_kernel<MK, RS><<<grid, 256, 0, st>>>(dyy, av, zz, dzv, drv, d_mean, d_invstd, d_gamma, d_beta, coef, M, rows, dtype)
+  if (dz_accumulate) {
+    IFCB_ARG_CHECK(!dres && dz->d != dy->d, "bn_backward_accumulate: no residual route, dz must not alias dy");
+    if (mask_mode == kMaskFromZ) bn_bwd_apply_kernel<kMaskFromZ, 0, true><<<grid, 256, 0, st>>>(dyy, av, zz, dzv, drv, d_mean, d_invstd, d_gamma, d_beta, coef, M, rows, dtype);
+    else bn_bwd_apply_kernel<kMaskNone, 0, true><<<grid, 256, 0, st>>>(dyy, av, zz, dzv, drv, d_mean, d_invstd, d_gamma, d_beta, coef, M, rows, dtype);
+  } else
   if (mask_mode == kMaskFromZ) IFCB_BWD_APPLY(kMaskFromZ, 0);               // (a residual always comes with kMaskFromA / kMaskNone)
   else if (mask_mode == kMaskFromA) { if (res_mode == 2) IFCB_BWD_APPLY(kMaskFromA, 2); else if (res_mode == 1) IFCB_BWD_APPLY(kMaskFromA, 1); else IFCB_BWD_APPLY(kMaskFromA, 0); }
   else { if (res_mode == 2) IFCB_BWD_APPLY(kMaskNone, 2); else if (res_mode == 1) IFCB_BWD_APPLY(kMaskNone, 1); else IFCB_BWD_APPLY(kMaskNone, 0); }
@@ -1273,14 +1399,55 @@ extern "C" int ifcb_bn_backward(const ifcb_view* dy, const ifcb_view* a, const i
 }
 
 static int pool_out(int in, int k, int s, int p) { return (in + 2 * p - k) / s + 1; }
+// torch's ceil_mode output size: one more window when it still starts inside the (left-padded) input
+static int pool_out_ceil(int in, int k, int s, int p) {
+  int o = (in + 2 * p - k + s - 1) / s + 1;
+  if ((o - 1) * s >= in + p) --o;
+  return o;
+}
+static bool pool_dim_ok(int out, int in, int k, int s, int p) { return out == pool_out(in, k, s, p) || out == pool_out_ceil(in, k, s, p); }
+
+extern "C" int ifcb_bias_relu_backward(const ifcb_view* dy, const ifcb_view* a, const ifcb_view* dz, int relu, int batch, int dtype,
+                                       double* d_acc, float* d_dbias, void* stream) {
+  IFCB_ARG_CHECK(view_ok(dy) && view_ok(dz) && batch > 0 && DT_OK(dtype), "bias_relu_backward: bad view / batch / dtype");
+  IFCB_ARG_CHECK(dz->C == dy->C && dz->H == dy->H && dz->W == dy->W, "bias_relu_backward: extents differ");
+  IFCB_ARG_CHECK(!relu || (view_ok(a) && a->C == dy->C && a->H == dy->H && a->W == dy->W), "bias_relu_backward: ReLU needs the forward output");
+  IFCB_ARG_CHECK(d_acc && d_dbias && dy->C <= 4096, "bias_relu_backward: null pointer / C > 4096");
+  const long long M = (long long)batch * dy->H * dy->W;
+  IFCB_ARG_CHECK(M * (dy->C / 8) < (1ll << 31), "bias_relu_backward: tensor too large for 32-bit indexing");
+  const ReduceCfg rc = reduce_cfg(M, dy->C);
+  float* det = nullptr;
+  if (det_enabled()) {
+    const long long need = 4ll * rc.grid.x * rc.grid.y * 8 * rc.c8b;
+    det = static_cast<float*>(det_workspace(need));
+    IFCB_ARG_CHECK(det != nullptr, "bias_relu_backward: the deterministic workspace is smaller than %lld bytes", need);
+  }
+  unsigned int* counter = reinterpret_cast<unsigned int*>(d_acc + 7680);
+  DV dyy = dv(dy), dzz = dv(dz), aa = relu ? dv(a) : dyy;
+  if (relu) bias_relu_bwd_kernel<true><<<rc.grid, 256, 0, STREAM(stream)>>>(dyy, aa, dzz, M, rc.rows, dtype, d_acc, d_dbias, counter, det, rc.c8b);
+  else bias_relu_bwd_kernel<false><<<rc.grid, 256, 0, STREAM(stream)>>>(dyy, aa, dzz, M, rc.rows, dtype, d_acc, d_dbias, counter, det, rc.c8b);
+  IFCB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int ifcb_scale_elems(const ifcb_view* x, const ifcb_view* y, const float* d_scale, int batch, int dtype, void* stream) {
+  IFCB_ARG_CHECK(view_ok(x) && view_ok(y) && d_scale && batch > 0 && DT_OK(dtype), "scale_elems: bad argument");
+  IFCB_ARG_CHECK(x->C == y->C && x->H == y->H && x->W == y->W, "scale_elems: extents differ");
+  IFCB_ARG_CHECK((reinterpret_cast<uintptr_t>(d_scale) & 15) == 0, "scale_elems: scale must be 16-byte aligned");
+  const long long total = (long long)batch * x->H * x->W * (x->C / 8);
+  IFCB_ARG_CHECK(total < (1ll << 31), "scale_elems: tensor too large for 32-bit indexing");
+  scale_elems_kernel<<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(dv(x), dv(y), d_scale, (uint32_t)total, div_magic(x->C / 8), dtype);
+  IFCB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
 
 extern "C" int ifcb_maxpool_fwd_train(const ifcb_view* x, const ifcb_view* y, uint8_t* d_idx, int batch, int k, int stride, int pad,
                                       int dtype, void* stream) {
   IFCB_ARG_CHECK(view_ok(x) && view_ok(y) && d_idx && batch > 0 && DT_OK(dtype), "maxpool_fwd_train: bad argument");
   IFCB_ARG_CHECK(k >= 1 && k <= 15 && stride >= 1 && pad >= 0 && pad < k, "maxpool_fwd_train: bad window");
-  const int P = pool_out(x->H, k, stride, pad), Q = pool_out(x->W, k, stride, pad);
-  IFCB_ARG_CHECK(y->C == x->C && y->H == P && y->W == Q, "maxpool_fwd_train: output extent %dx%dx%d, expected %dx%dx%d", y->H, y->W, y->C,
-                 P, Q, x->C);
+  const int P = y->H, Q = y->W;        // floor or ceil_mode extent (torch.nn.MaxPool2d(ceil_mode=True): squeezenet.py)
+  IFCB_ARG_CHECK(y->C == x->C && pool_dim_ok(P, x->H, k, stride, pad) && pool_dim_ok(Q, x->W, k, stride, pad),
+                 "maxpool_fwd_train: output extent %dx%dx%d does not fit input %dx%dx%d", y->H, y->W, y->C, x->H, x->W, x->C);
   const long long total = (long long)batch * P * Q * (x->C / 8);
   IFCB_ARG_CHECK(total < (1ll << 31), "maxpool_fwd_train: tensor too large for 32-bit indexing");
   if (k == 3)
@@ -1297,8 +1464,8 @@ extern "C" int ifcb_maxpool_bwd(const ifcb_view* dy, const uint8_t* d_idx, const
                                 int stride, int pad, int dtype, void* stream) {
   IFCB_ARG_CHECK(view_ok(dy) && view_ok(dx) && d_idx && batch > 0 && DT_OK(dtype), "maxpool_bwd: bad argument");
   IFCB_ARG_CHECK(k >= 1 && k <= 15 && stride >= 1 && pad >= 0 && pad < k, "maxpool_bwd: bad window");
-  const int P = pool_out(dx->H, k, stride, pad), Q = pool_out(dx->W, k, stride, pad);
-  IFCB_ARG_CHECK(dy->C == dx->C && dy->H == P && dy->W == Q, "maxpool_bwd: gradient extent differs");
+  const int P = dy->H, Q = dy->W;
+  IFCB_ARG_CHECK(dy->C == dx->C && pool_dim_ok(P, dx->H, k, stride, pad) && pool_dim_ok(Q, dx->W, k, stride, pad), "maxpool_bwd: gradient extent differs");
   const long long total = (long long)batch * dx->H * dx->W * (dx->C / 8);
   IFCB_ARG_CHECK(total < (1ll << 31), "maxpool_bwd: tensor too large for 32-bit indexing");
   if (k == 3 && stride == 2)

@@ -151,7 +151,7 @@ class PlanBuilder(object):
         return tuple(pad) if algo == _lib.IFCB_CONV_WINDOW else (0, 0)
 
     # -- layers ---------------------------------------------------------------
-    def conv(self, x, members, stride=(1, 1), pad=(0, 0), residual=None, tile_n=0, name='conv', algo=0, stats=None):
+    def conv(self, x, members, stride=(1, 1), pad=(0, 0), residual=None, tile_n=0, name='conv', algo=0, stats=None, shift_ptr=None):
         """One implicit-GEMM launch.  ``members``: list of dicts
         (weight [Co,Ci,kh,kw] fp32, scale [Co], shift [Co], relu bool, out View) --
         more than one member = horizontally fused convs sharing input ``x``."""
@@ -189,6 +189,8 @@ class PlanBuilder(object):
         d.kh, d.kw, d.stride_h, d.stride_w, d.pad_h, d.pad_w = kh, kw, stride[0], stride[1], pad[0], pad[1]
         d.Cout = Co
         d.d_weight, d.d_scale, d.d_shift = wdev.data_ptr(), sdev.data_ptr(), hdev.data_ptr()
+        if shift_ptr is not None:        # TRAIN, conv with bias: the epilogue reads the bias straight from the fp32 parameter arena
+            d.d_shift = int(shift_ptr)
         d.n_seg = len(members)
         n0 = 0
         for i, m in enumerate(members):

@@ -24,7 +24,7 @@ import torch
 
 from . import _lib
 from ._lib import ViewDesc, WgradDesc
-from .graph import PlanBuilder, View, RESNET_CFG
+from .graph import PlanBuilder, View, RESNET_CFG, PLAIN_ARCHS, VGG_CFG, ALEXNET_CFG
 from .sharding import plan_buckets, GradReducer
 
 
@@ -126,8 +126,8 @@ class TrainNet(object):
         self.fp = PlanBuilder(batch, self.device, dtype)       # forward convs (+ stem)
         self.bp = PlanBuilder(batch, self.device, dtype)       # data-gradient convs
         self.cdtype, self.tdtype = self.fp.cdtype, self.fp.tdtype
-        total = sum(((v.numel() * (3 if v.dim() == 4 and v.shape[1] == 3 else 1) + 63) // 64) * 64
-                    for v in sd.values() if v.is_floating_point())
+        total = sum(((v.numel() * (3 if v.dim() == 4 and v.shape[1] == 3 else 1) + 63) // 64) * 64 + 64
+                    for v in sd.values() if v.is_floating_point()) + (1 << 20)
         self.params = share.params if share is not None else torch.zeros(total, dtype=torch.float32, device=self.device)
         self._cursor = 0
         self.plist = []                 # _Param in forward order
@@ -162,9 +162,13 @@ class TrainNet(object):
             _build_inception_train(self, sd)
         elif arch in RESNET_CFG:
             _build_resnet_train(self, sd, arch)
+        elif arch in PLAIN_ARCHS:
+            _build_plain_train(self, sd, arch)
+        elif arch == 'squeezenet':
+            _build_squeezenet_train(self, sd)
+        elif arch.startswith('densenet'):
+            _build_densenet_train(self, sd)
         else:
-            if arch in ('alexnet', 'squeezenet') or arch.startswith(('vgg', 'densenet')):
-                raise NotImplementedError('TRAIN on the B200 kernels covers inception_v3 and resnet18/34/50/101/152; %s has a RUN plan only' % arch)
             raise KeyError('model unknown!')
         self.n_params = self._cursor
         if share is not None:
@@ -237,7 +241,7 @@ class TrainNet(object):
         """For every conv output tensor: the border (k-1-pad) its stride-1 data-gradient conv reads as padding when
         the library will run that conv with the WINDOW scheme (max over the producers of a concat buffer)."""
         for rec in self.records:
-            if rec['kind'] != 'conv_bn' or rec['stem'] is not None or rec['pool_after'] is not None or not self.window:
+            if rec['kind'] not in ('conv_bn', 'conv_act') or rec['stem'] is not None or rec['pool_after'] is not None or not self.window:
                 continue
             if tuple(rec['stride']) != (1, 1):
                 continue                                             # strided: the dilated copy carries the border
@@ -249,7 +253,7 @@ class TrainNet(object):
 
     # ---- graph construction (forward order) -------------------------------------------------------
     def conv_bn(self, x, sd, conv, bn, stride=(1, 1), pad=(0, 0), relu=True, residual=None, out=None, out_pad=(0, 0),
-                eps=1e-5, stem=False, pool_after=None):
+                eps=1e-5, stem=False, pool_after=None, conv_bias=False):
         """Conv2d(bias=False) -> BatchNorm2d(train) [-> + residual] [-> ReLU]; returns the activation view.
 
         ``pool_after=(k, stride, pad)``: the module computes avg_pool2d(x) -> 1x1 conv (Inception's
@@ -292,6 +296,9 @@ class TrainNet(object):
         z = self.alloc(P, Q, Co)
         master = w.permute(0, 2, 3, 1).reshape(Co, kh * kw, Ci).contiguous()
         pw = self._param(conv + '.weight', master, 'stem' if stem else 'conv', dict(Ci=Ci, kh=kh, kw=kw, stem=stem_geom))
+        # vgg*_bn: Conv2d(bias=True) in front of a BatchNorm.  The bias is added in the epilogue; its gradient is the per-channel sum
+        # of the BatchNorm's dz, which is identically zero, so it is left at zero (torch's comes out as ~1e-9 rounding noise)
+        pcb = self._param(conv + '.bias', sd[conv + '.bias'].float(), 'vec') if conv_bias else None
         pg = self._param(bn + '.weight', sd[bn + '.weight'], 'vec')
         pb = self._param(bn + '.bias', sd[bn + '.bias'], 'vec')
         if self._share is not None:
@@ -310,7 +317,7 @@ class TrainNet(object):
             sums_ptr = self.stat_sums.data_ptr() + 8 * self._stat_cursor
             self._stat_cursor += 2 * Co + (-(2 * Co) % 2)
         self.fp.conv(x, [dict(weight=w, scale=ones, shift=zeros, relu=False, out=z if raw is None else raw)], stride, pad, name=conv,
-                     stats=sums_ptr)
+                     stats=sums_ptr, shift_ptr=pcb.wptr if pcb is not None else None)
         wf = self.fp.last_weight                                     # packed [Cout_pad, K_pad] 16-bit operand
         rawd = _vd(raw) if raw is not None else None
         zd, od = _vd(z), _vd(out)
@@ -337,9 +344,107 @@ class TrainNet(object):
                                  H=H, W=W, name=conv, raw=raw, pool_after=pool_after))
         return out
 
-    def maxpool(self, x, k, stride, pad, out=None, out_pad=(0, 0)):
+    def conv_act(self, x, sd, conv, stride=(1, 1), pad=(0, 0), relu=True, out=None, out_pad=(0, 0), stem=False, bias=True, weight=None,
+                 linear=False, co_pad=None):
+        """Conv2d(+bias) [-> ReLU] WITHOUT BatchNorm (AlexNet / VGG / SqueezeNet convs and their Linear layers run as convs,
+        DenseNet's raw convs).  The epilogue adds the bias and applies the ReLU; the backward pass masks the gradient with the
+        stored output and sums it into the bias gradient (ifcb_bias_relu_backward).  ``weight``: override (a Linear weight
+        viewed as a conv filter); ``co_pad``: pad the output channels with zero filters up to a multiple of 8."""
+        w = (weight if weight is not None else sd[conv + '.weight']).float()
+        b = sd[conv + '.bias'].float() if bias else None
+        Co_real = int(w.shape[0])
+        if co_pad is not None and co_pad > Co_real:
+            w = torch.cat([w, torch.zeros((co_pad - Co_real,) + tuple(w.shape[1:]))], 0)
+            if b is not None:
+                b = torch.cat([b, torch.zeros(co_pad - Co_real)])
+        Co, Ci, kh, kw = [int(v) for v in w.shape]
+        stem_geom = None
+        if stem:
+            assert Ci == 3 and stride[0] == stride[1] and pad[0] == pad[1]
+            P = (self.R + 2 * pad[0] - kh) // stride[0] + 1
+            K8 = ((kh * kw * 3 + 7) // 8) * 8
+            x = self.alloc(P, P, K8)
+            xd_ = _vd(x)
+            stem_geom = dict(kh=kh, kw=kw, stride=stride, pad=pad)
+            st, pd_, R_ = stride[0], pad[0], self.R
+            self.fwd.append(lambda kh=kh, kw=kw: self._call('ifcb_stem_im2col', self.inp.data_ptr(), R_, R_, C.byref(xd_), self.batch, kh, kw,
+                                                            st, pd_, None, None, self.cdtype, self._stream()))
+            w1 = torch.zeros((Co, K8, 1, 1))
+            w1[:, :kh * kw * 3, 0, 0] = w.permute(0, 2, 3, 1).reshape(Co, kh * kw * 3)
+            w, Ci, kh, kw, stride, pad = w1, K8, 1, 1, (1, 1), (0, 0)
+        H, W = x.H, x.W
+        P = (H + 2 * pad[0] - kh) // stride[0] + 1
+        Q = (W + 2 * pad[1] - kw) // stride[1] + 1
+        if out is None:
+            out = self.alloc(P, Q, Co, out_pad)
+        master = w.permute(0, 2, 3, 1).reshape(Co, kh * kw, Ci).contiguous()
+        pw = self._param(conv + '.weight', master, 'stem' if stem else 'conv',
+                         dict(Ci=Ci, kh=kh, kw=kw, stem=stem_geom, linear=linear, Co_real=Co_real))
+        pb = self._param(conv + '.bias', b, 'vec', dict(Co_real=Co_real)) if b is not None else None
+        li = len(self.fp.layer_names)
+        self.fp.conv(x, [dict(weight=w, scale=torch.ones(Co), shift=torch.zeros(Co), relu=relu, out=out)], stride, pad, name=conv,
+                     shift_ptr=pb.wptr if pb is not None else None)
+        wf = self.fp.last_weight
+        B = self.batch
+        self.fwd.append(lambda: self.fp.run(B, li, li + 1))
+        self.records.append(dict(kind='conv_act', x=x, out=out, relu=relu, stride=stride, pad=pad, pw=pw, pb=pb, wf=wf, Co=Co, Ci=Ci, kh=kh,
+                                 kw=kw, stem=stem_geom, H=H, W=W, name=conv, pool_after=None, residual=None))
+        return out
+
+    def bn_act(self, x, sd, bn, relu=True, eps=1e-5, first=False):
+        """BatchNorm2d(train) [-> ReLU] over an EXISTING tensor view (DenseNet's pre-activation norms over the growing
+        concatenation).  ``first``: this is the first unit of the backward pass to write the input's gradient (it covers the
+        whole tensor); every other norm ADDS its contribution (ifcb_bn_backward_accumulate)."""
+        Cc = x.C
+        out = self.alloc(x.H, x.W, Cc)
+        pg = self._param(bn + '.weight', sd[bn + '.weight'], 'vec')
+        pb = self._param(bn + '.bias', sd[bn + '.bias'], 'vec')
+        if self._share is not None:
+            rm, rv = self._share.buffers[bn + '.running_mean'], self._share.buffers[bn + '.running_var']
+            self.buffers[bn + '.num_batches_tracked'] = self._share.buffers[bn + '.num_batches_tracked']
+        else:
+            rm = self._f32(Cc); rm.copy_(sd[bn + '.running_mean'])
+            rv = self._f32(Cc); rv.copy_(sd[bn + '.running_var'])
+            self.buffers[bn + '.num_batches_tracked'] = sd.get(bn + '.num_batches_tracked', torch.zeros((), dtype=torch.long)).clone()
+        self.buffers[bn + '.running_mean'], self.buffers[bn + '.running_var'] = rm, rv
+        mean, invstd = self._f32(Cc), self._f32(Cc)
+        xd, od, B, dt = _vd(x), _vd(out), self.batch, self.cdtype
+
+        def fwd():
+            self._call('ifcb_bn_stats', C.byref(xd), B, dt, eps, 0.1, self.acc.data_ptr(), mean.data_ptr(), invstd.data_ptr(),
+                       rm.data_ptr(), rv.data_ptr(), self._stream())
+            self._call('ifcb_bn_apply', C.byref(xd), C.byref(od), None, B, dt, mean.data_ptr(), invstd.data_ptr(), pg.wptr, pb.wptr,
+                       1 if relu else 0, self._stream())
+        self.fwd.append(fwd)
+        self._nbt_keys.append(bn + '.num_batches_tracked')
+        self.records.append(dict(kind='bn_act', x=x, out=out, relu=relu, pg=pg, pb=pb, mean=mean, invstd=invstd, first=first, name=bn))
+        return out
+
+    def drop(self, x, p, tag):
+        """nn.Dropout(p) in train mode on an activation tensor (classifier stacks of AlexNet / VGG / SqueezeNet): the mask times
+        1/(1-p) comes from the counter-based generator (ifcb_dropout_scale) once per step; identity when dropout is switched off."""
+        if not self.dropout or p <= 0:
+            return x
+        out = self.alloc(x.H, x.W, x.C)
+        n = self.batch * x.H * x.W * x.C
+        scale = self._f32(n, 1.0)
+        xd, od, B, dt = _vd(x), _vd(out), self.batch, self.cdtype
+        salt = len(self.pre) + 7
+
+        def pre():
+            seed = (self.seed * 1000003 + self.step_count * 7919 + salt) & ((1 << 63) - 1)
+            self._call('ifcb_dropout_scale', scale.data_ptr(), n, p, seed, self._stream())
+        self.pre.append(pre)
+        self.fwd.append(lambda: self._call('ifcb_scale_elems', C.byref(xd), C.byref(od), scale.data_ptr(), B, dt, self._stream()))
+        self.records.append(dict(kind='drop', x=x, out=out, scale=scale, name=tag))
+        return out
+
+    def maxpool(self, x, k, stride, pad, out=None, out_pad=(0, 0), ceil_mode=False):
         P = (x.H + 2 * pad - k) // stride + 1
         Q = (x.W + 2 * pad - k) // stride + 1
+        if ceil_mode:                                  # torch: one more window if it still starts inside the input
+            ce = lambda n: (lambda o: o - 1 if (o - 1) * stride >= n + pad else o)((n + 2 * pad - k + stride - 1) // stride + 1)
+            P, Q = ce(x.H), ce(x.W)
         if out is None:
             out = self.alloc(P, Q, x.C, out_pad)
         idx = torch.zeros((self.batch, P, Q, x.C), dtype=torch.uint8, device=self.device)
@@ -360,13 +465,26 @@ class TrainNet(object):
         self.records.append(dict(kind='avgpool', x=x, out=out, k=k, stride=stride, pad=pad))
         return out
 
-    def head(self, x, sd, fc, loss_weight=1.0, dropout_p=0.0, which='main'):
-        """adaptive_avg_pool2d(1) -> dropout -> Linear -> loss_weight * CrossEntropyLoss."""
-        Wt, bias = sd[fc + '.weight'].float(), sd[fc + '.bias'].float()
-        n_classes, Cc = int(Wt.shape[0]), int(Wt.shape[1])
-        assert Cc == x.C
-        pw = self._param(fc + '.weight', Wt, 'fc')
-        pb = self._param(fc + '.bias', bias, 'vec')
+    def head(self, x, sd, fc, loss_weight=1.0, dropout_p=0.0, which='main', identity_classes=None):
+        """adaptive_avg_pool2d(1) -> dropout -> Linear -> loss_weight * CrossEntropyLoss.  ``identity_classes`` = n: there is no
+        Linear (SqueezeNet: the pooled outputs of the last conv ARE the logits) -- a fixed identity matrix stands in, outside the
+        parameter arena, and its gradient is discarded."""
+        if identity_classes is not None:
+            n_classes, Cc = int(identity_classes), x.C
+            eye = torch.zeros((n_classes, Cc)); eye[:, :n_classes] = torch.eye(n_classes)
+            wt_, gt_ = self._f32(n_classes * Cc), self._f32(n_classes * Cc + n_classes)
+            wt_.copy_(eye.reshape(-1))
+            bz_ = self._f32(n_classes)
+
+            class _Fixed(object):                      # quacks like a _Param for the head kernels
+                def __init__(s_, w, g): s_.wptr, s_.gptr, s_.off = w, g, None
+            pw, pb = _Fixed(wt_.data_ptr(), gt_.data_ptr()), _Fixed(bz_.data_ptr(), gt_.data_ptr() + 4 * n_classes * Cc)
+        else:
+            Wt, bias = sd[fc + '.weight'].float(), sd[fc + '.bias'].float()
+            n_classes, Cc = int(Wt.shape[0]), int(Wt.shape[1])
+            assert Cc == x.C
+            pw = self._param(fc + '.weight', Wt, 'fc')
+            pb = self._param(fc + '.bias', bias, 'vec')
         B, dt = self.batch, self.cdtype
         pooled = self._f32(B * Cc)
         logits = self._f32(B * n_classes)
@@ -441,6 +559,43 @@ class TrainNet(object):
                     self.bwd.append(lambda dyd=dyd, dxd=dxd, acc=acc, k=k, s=s, p=p: self._call(
                         'ifcb_avgpool_bwd', C.byref(dyd), C.byref(dxd), 1 if acc else 0, B, k, s, p, dt, self._stream()))
                 lo = None
+            elif kind == 'conv_act':
+                out, pb, relu = rec['out'], rec['pb'], rec['relu']
+                dy = self.grad_of(out)
+                rec['dy'] = rec['dz'] = dy
+                if pb is not None or relu:
+                    dyd, od = _vd(dy), _vd(out)
+                    if pb is None:
+                        pb = rec['pb_dummy'] = self._f32(rec['Co'])
+                        gptr = pb.data_ptr()
+                    else:
+                        gptr = pb.gptr
+                    self.bwd.append(lambda dyd=dyd, od=od, relu=relu, gptr=gptr: self._call(
+                        'ifcb_bias_relu_backward', C.byref(dyd), C.byref(od) if relu else None, C.byref(dyd), 1 if relu else 0, B, dt,
+                        self.acc.data_ptr(), gptr, self._stream()))
+                lo = self._conv_grads(rec, dy, claim)
+            elif kind == 'bn_act':
+                x, out, relu = rec['x'], rec['out'], rec['relu']
+                dy, dx = self.grad_of(out), self.grad_of(x)
+                dyd, xd, dxd = _vd(dy), _vd(x), _vd(dx)
+                pg, pb_, mean, invstd = rec['pg'], rec['pb'], rec['mean'], rec['invstd']
+                if rec['first']:          # covers the whole tensor and comes first in the backward pass: plain write
+                    self.bwd.append(lambda dyd=dyd, xd=xd, dxd=dxd, relu=relu, pg=pg, pb_=pb_, mean=mean, invstd=invstd: self._call(
+                        'ifcb_bn_backward', C.byref(dyd), None, C.byref(xd), C.byref(dxd), None, 0, 1 if relu else 0, B, dt, mean.data_ptr(),
+                        invstd.data_ptr(), pg.wptr, pb_.wptr, self.acc.data_ptr(), pg.gptr, pb_.gptr, self._stream()))
+                else:
+                    self.bwd.append(lambda dyd=dyd, xd=xd, dxd=dxd, relu=relu, pg=pg, pb_=pb_, mean=mean, invstd=invstd: self._call(
+                        'ifcb_bn_backward_accumulate', C.byref(dyd), C.byref(xd), C.byref(dxd), 1 if relu else 0, B, dt, mean.data_ptr(),
+                        invstd.data_ptr(), pg.wptr, pb_.wptr, self.acc.data_ptr(), pg.gptr, pb_.gptr, self._stream()))
+                lo = pg.off
+            elif kind == 'drop':
+                x, out, scale = rec['x'], rec['out'], rec['scale']
+                dy, dx = self.grad_of(out), self.grad_of(x)
+                assert not claim(x), 'dropout input with several consumers'
+                dyd, dxd = _vd(dy), _vd(dx)
+                self.bwd.append(lambda dyd=dyd, dxd=dxd, scale=scale: self._call('ifcb_scale_elems', C.byref(dyd), C.byref(dxd), scale.data_ptr(),
+                                                                                 B, dt, self._stream()))
+                lo = None
             else:
                 lo = self._finalize_conv(rec, claim)
             unit_lo.extend([None] * (len(self.bwd) - len(unit_lo) - 1) + [lo])
@@ -483,6 +638,14 @@ class TrainNet(object):
             self.bwd.append(lambda: self._call('ifcb_avgpool_bwd', C.byref(dzd), C.byref(drd), 0, B, pa[0], pa[1], pa[2], dt, self._stream()))
             rec['dr'] = dr
             dz = dr
+        return self._conv_grads(rec, dz, claim)
+
+    def _conv_grads(self, rec, dz, claim):
+        """Weight gradient and data gradient of a conv unit from the gradient ``dz`` of its (pre-activation) output."""
+        B, dt = self.batch, self.cdtype
+        x, pw = rec['x'], rec['pw']
+        Co, Ci, kh, kw = rec['Co'], rec['Ci'], rec['kh'], rec['kw']
+        stride, pad = rec['stride'], rec['pad']
         # weight gradient: dW[co, tap, ci] += sum dz * x
         wd = WgradDesc()
         xin = x
@@ -642,9 +805,15 @@ class TrainNet(object):
             if p.kind == 'conv':
                 Ci, kh, kw = p.meta['Ci'], p.meta['kh'], p.meta['kw']
                 t = t[:, :, :Ci].reshape(p.shape[0], kh, kw, Ci).permute(0, 3, 1, 2)
+                t = t[:p.meta.get('Co_real', p.shape[0])]
+                if p.meta.get('linear'):                         # a Linear layer run as a conv over its whole input map
+                    t = t.reshape(t.shape[0], -1)
+            elif p.kind == 'vec' and 'Co_real' in p.meta:
+                t = t[:p.meta['Co_real']]
             elif p.kind == 'stem':                               # [Co, 1, K8], k = (r*kw + s)*3 + c
                 g = p.meta['stem']
                 t = t[:, 0, :g['kh'] * g['kw'] * 3].reshape(p.shape[0], g['kh'], g['kw'], 3).permute(0, 3, 1, 2)
+                t = t[:p.meta.get('Co_real', p.shape[0])]
             out[p.name] = t.detach().clone().contiguous()
         return out
 
@@ -781,3 +950,109 @@ def _build_inception_train(tn, sd):
         cb(x, blk + '.branch_pool', out=out.slice(1856, 2048), pool_after=(3, 1, 1))
         x = out
     tn.head(x, sd, 'fc', dropout_p=0.5)
+
+
+# ---- AlexNet / VGG (torchvision alexnet.py, vgg.py): conv(+bias)(+BN)+ReLU stacks, max pools, Dropout / Linear classifier ----
+def _build_plain_train(tn, sd, arch):
+    if arch == 'alexnet':
+        seq, pool_k, pool_s = list(ALEXNET_CFG), 3, 2
+    else:
+        bn = arch.endswith('_bn')
+        seq, idx = [], 0
+        for v in VGG_CFG[arch[:-3] if bn else arch]:
+            if v == 'M':
+                seq.append('M'); idx += 1
+            else:
+                seq.append((idx, 3, 1, 1, idx + 1 if bn else None)); idx += 3 if bn else 2
+        pool_k, pool_s = 2, 2
+    x, first, H = None, True, tn.R
+    for pos, item in enumerate(seq):
+        if item == 'M':
+            x = tn.maxpool(x, pool_k, pool_s, 0)
+            H = x.H
+            continue
+        idx, k, stride, pad = item[:4]
+        bn_idx = item[4] if len(item) > 4 else None
+        conv = 'features.%d' % idx
+        Co = int(sd[conv + '.weight'].shape[0])
+        Ho = (H + 2 * pad - k) // stride + 1
+        nxt = seq[pos + 1] if pos + 1 < len(seq) else 'M'
+        opad = (0, 0)
+        if nxt != 'M':
+            nCo = int(sd['features.%d.weight' % nxt[0]].shape[0])
+            opad = tn.border(Ho, Ho, Co, nCo, (nxt[1], nxt[1]), (nxt[2], nxt[2]), (nxt[3], nxt[3]))
+        if bn_idx is not None:
+            x = tn.conv_bn(x, sd, conv, 'features.%d' % bn_idx, (stride, stride), (pad, pad), out_pad=opad, stem=first, conv_bias=True)
+        else:
+            x = tn.conv_act(x, sd, conv, (stride, stride), (pad, pad), out_pad=opad, stem=first)
+        first, H = False, Ho
+    lin = sorted(int(k.split('.')[1]) for k in sd if k.startswith('classifier.') and k.endswith('.weight'))
+    assert len(lin) == 3
+    feat = int(sd['classifier.%d.weight' % lin[0]].shape[1])
+    assert feat == x.C * H * H, '%s: a %d px input gives a %dx%d feature map; the classifier expects %d features (224 px)' % (
+        arch, tn.R, H, H, feat)
+    if arch == 'alexnet':                                            # Dropout, Linear, ReLU, Dropout, Linear, ReLU, Linear
+        x = tn.drop(x, 0.5, 'classifier.0')
+    w1 = sd['classifier.%d.weight' % lin[0]]
+    x = tn.conv_act(x, sd, 'classifier.%d' % lin[0], weight=w1.view(int(w1.shape[0]), -1, H, H), linear=True)
+    x = tn.drop(x, 0.5, 'classifier.drop1')
+    w2 = sd['classifier.%d.weight' % lin[1]]
+    x = tn.conv_act(x, sd, 'classifier.%d' % lin[1], weight=w2.view(int(w2.shape[0]), int(w2.shape[1]), 1, 1), linear=True)
+    tn.head(x, sd, 'classifier.%d' % lin[2], dropout_p=0.0 if arch == 'alexnet' else 0.5)
+
+
+# ---- SqueezeNet 1.1 (torchvision squeezenet.py; reference neuston_models.py:30-33 swaps classifier[1]) ----
+def _build_squeezenet_train(tn, sd):
+    x = tn.conv_act(None, sd, 'features.0', (2, 2), (0, 0), stem=True)
+    for idx in (2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12):
+        if idx in (2, 5, 8):
+            x = tn.maxpool(x, 3, 2, 0, ceil_mode=True)
+            continue
+        pre = 'features.%d' % idx
+        sq = int(sd[pre + '.squeeze.weight'].shape[0])
+        e1, e3 = int(sd[pre + '.expand1x1.weight'].shape[0]), int(sd[pre + '.expand3x3.weight'].shape[0])
+        t = tn.conv_act(x, sd, pre + '.squeeze', out_pad=tn.border(x.H, x.W, sq, e3, (3, 3), pad=(1, 1)))
+        out = tn.alloc(x.H, x.W, e1 + e3)
+        tn.conv_act(t, sd, pre + '.expand1x1', out=out.slice(0, e1))
+        tn.conv_act(t, sd, pre + '.expand3x3', pad=(1, 1), out=out.slice(e1, e1 + e3))
+        x = out
+    x = tn.drop(x, 0.5, 'classifier.0')
+    n_classes = int(sd['classifier.1.weight'].shape[0])
+    y = tn.conv_act(x, sd, 'classifier.1', co_pad=(n_classes + 7) // 8 * 8)
+    tn.head(y, None, None, identity_classes=n_classes)
+
+
+# ---- DenseNet (torchvision densenet.py): pre-activation dense layers over a growing concatenation ----
+def _build_densenet_train(tn, sd):
+    blocks, b = [], 1
+    while ('features.denseblock%d.denselayer1.conv1.weight' % b) in sd:
+        n = 1
+        while ('features.denseblock%d.denselayer%d.conv1.weight' % (b, n + 1)) in sd:
+            n += 1
+        blocks.append(n)
+        b += 1
+    growth = int(sd['features.denseblock1.denselayer1.conv2.weight'].shape[0])
+    C_in = int(sd['features.conv0.weight'].shape[0])
+    a = tn.conv_bn(None, sd, 'features.conv0', 'features.norm0', (2, 2), (3, 3), stem=True)
+    H = (a.H + 2 - 3) // 2 + 1
+    buf = tn.alloc(H, H, C_in + blocks[0] * growth)
+    tn.maxpool(a, 3, 2, 1, out=buf.slice(0, C_in))
+    for bi, n_layers in enumerate(blocks):
+        for li in range(n_layers):
+            pre = 'features.denseblock%d.denselayer%d' % (bi + 1, li + 1)
+            t1 = tn.bn_act(buf.slice(0, C_in), sd, pre + '.norm1')
+            mid = int(sd[pre + '.conv1.weight'].shape[0])
+            t2 = tn.conv_bn(t1, sd, pre + '.conv1', pre + '.norm2', out_pad=tn.border(H, H, mid, growth, (3, 3), pad=(1, 1)))
+            tn.conv_act(t2, sd, pre + '.conv2', pad=(1, 1), relu=False, bias=False, out=buf.slice(C_in, C_in + growth))
+            C_in += growth
+        if bi + 1 < len(blocks):                       # transition: norm -> relu -> conv 1x1 -> avg_pool 2x2
+            pre = 'features.transition%d' % (bi + 1)
+            t1 = tn.bn_act(buf, sd, pre + '.norm', first=True)
+            t2 = tn.conv_act(t1, sd, pre + '.conv', relu=False, bias=False)
+            Co = t2.C
+            H = (H - 2) // 2 + 1
+            nbuf = tn.alloc(H, H, Co + blocks[bi + 1] * growth)
+            tn.avgpool(t2, 2, 2, 0, out=nbuf.slice(0, Co))
+            buf, C_in = nbuf, Co
+    t = tn.bn_act(buf, sd, 'features.norm5', first=True)
+    tn.head(t, sd, 'classifier')

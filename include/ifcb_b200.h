@@ -284,6 +284,20 @@ int ifcb_bn_backward(const ifcb_view* dy, const ifcb_view* a, const ifcb_view* z
                      const ifcb_view* dres, int dres_accumulate, int relu, int batch, int dtype,
                      const float* d_mean, const float* d_invstd, const float* d_gamma, const float* d_beta,
                      double* d_acc, float* d_dgamma, float* d_dbeta, void* stream);
+/* The same backward when the BatchNorm read a tensor that OTHER layers read too (DenseNet's pre-activation norm over the
+ * growing concatenation, torchvision densenet.py _DenseLayer): dz is ADDED to what the target already holds (dz must not alias dy;
+ * no residual route; the ReLU mask is recomputed from z). */
+int ifcb_bn_backward_accumulate(const ifcb_view* dy, const ifcb_view* z, const ifcb_view* dz, int relu, int batch, int dtype,
+                                const float* d_mean, const float* d_invstd, const float* d_gamma, const float* d_beta,
+                                double* d_acc, float* d_dgamma, float* d_dbeta, void* stream);
+/* Backward of (Conv2d with bias -> [ReLU]) for the families without BatchNorm (AlexNet, VGG, SqueezeNet; alexnet.py, vgg.py,
+ * squeezenet.py under NeustonModel.training_step, neuston_models.py:80-86): dz = dy * [a > 0] (dz may alias dy; relu = 0 copies),
+ * d_dbias[C] += sum over pixels of dz.  d_acc: the 64 KB scratch of ifcb_bn_stats. */
+int ifcb_bias_relu_backward(const ifcb_view* dy, const ifcb_view* a, const ifcb_view* dz, int relu, int batch, int dtype,
+                            double* d_acc, float* d_dbias, void* stream);
+/* y = x * scale element-wise; scale float32 [batch, H, W, C] dense (nn.Dropout of the classifier stacks in train mode: the mask
+ * times 1/(1-p) from ifcb_dropout_scale; the backward pass applies the same scale to the gradient). */
+int ifcb_scale_elems(const ifcb_view* x, const ifcb_view* y, const float* d_scale, int batch, int dtype, void* stream);
 
 /* Pooling for the TRAIN step.  max: F.max_pool2d forward recording the winning tap (first maximum
  * in row-major window order, uint8 [batch,P,Q,C]) and its backward; avg: F.avg_pool2d with

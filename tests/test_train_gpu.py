@@ -726,3 +726,49 @@ def test_deterministic_mode_is_bitwise_reproducible(cuda):
     # same arithmetic up to the order of the split-K / block sums: three Adam steps stay close
     assert abs(la[0] - lc[0]) <= 1e-4 * abs(lc[0]) and torch.allclose(ra, rc_, rtol=5e-2, atol=1e-4)
     assert float((a - c).abs().max()) <= 1e-2            # (an Adam step moves a weight by ~lr whatever the gradient size: sign flips of ~0 gradients)
+
+
+OTHER_FAMILIES = [('alexnet', 224, 8, 0.98), ('vgg11', 224, 4, 0.98), ('vgg11_bn', 224, 4, None), ('squeezenet', 96, 8, 0.97),
+                  ('densenet121', 64, 8, None)]
+
+
+@pytest.mark.parametrize('arch,R,B,min_cos', OTHER_FAMILIES, ids=[c[0] for c in OTHER_FAMILIES])
+def test_train_step_other_families(cuda, arch, R, B, min_cos):
+    """TRAIN for the remaining names get_namebrand_model resolves (reference neuston_models.py:27-42: alexnet, vgg*, squeezenet,
+    densenet*): conv + bias + ReLU units without BatchNorm, Linear layers run as convolutions, Dropout, ceil-mode pools, DenseNet's
+    pre-activation norms over the growing concatenation.  One training_step against the oracle (fp32 autograd of the same
+    torchvision module, dropout off on both sides): loss within 2 %, every parameter has a gradient of the right shape, and for
+    the BatchNorm-free families (no batch statistics to amplify 16-bit storage rounding) the whole gradient agrees with fp32
+    (cosine); then a few Adam steps on the same batch bring the loss down, and state_dict() has torchvision's keys and shapes."""
+    from oracle import train_ref
+    from tests.fixtures import ref_model
+    from ifcb_classifier_b200.train import TrainNet
+    n_classes = 10
+    model = ref_model(arch, n_classes, seed=3).to(cuda)
+    g = torch.Generator().manual_seed(5)
+    x = torch.rand(B, 3, R, R, generator=g).to(cuda)
+    y = torch.randint(0, n_classes, (B,), generator=g).to(cuda)
+    net = TrainNet(arch, model.state_dict(), B, device=cuda, dtype='bf16', dropout=False, R=R)
+    loss = float(net.forward_backward(x, y))
+    grads = {k: v.to(cuda).float() for k, v in net.grad_dict().items()}
+    f_loss, f_grads = train_ref.forward_backward(model, x, y, dropout=False)
+    assert sorted(grads) == sorted(f_grads)
+    for k in f_grads:
+        assert grads[k].shape == f_grads[k].shape, (k, grads[k].shape, f_grads[k].shape)
+    dot = sum((grads[k] * f_grads[k]).sum() for k in f_grads)
+    cos = float(dot / (torch.sqrt(sum((v ** 2).sum() for v in grads.values())) * torch.sqrt(sum((v ** 2).sum() for v in f_grads.values()))))
+    print('%s: loss %.5f, fp32 oracle %.5f, gradient cosine %.4f' % (arch, loss, float(f_loss), cos))
+    assert abs(loss - float(f_loss)) <= 2e-2 * abs(float(f_loss)), (loss, float(f_loss))
+    if min_cos is not None:
+        assert cos >= min_cos, cos
+    sd, rsd = net.state_dict(), model.state_dict()
+    assert list(sd.keys()) == list(rsd.keys())
+    for k in rsd:
+        assert tuple(sd[k].shape) == tuple(rsd[k].shape), k
+    net.adam()
+    losses = [float(net.step(x, y)) for _ in range(8)]
+    assert losses[-1] < 0.7 * loss, (loss, losses)
+    # with dropout on the step still runs and trains (mask from the counter-based generator)
+    net2 = TrainNet(arch, model.state_dict(), B, device=cuda, dtype='bf16', dropout=True, R=R, seed=11)
+    l2 = [float(net2.step(x, y)) for _ in range(3)]
+    assert all(v == v and v < 50 for v in l2), l2
