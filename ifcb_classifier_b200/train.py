@@ -243,6 +243,8 @@ class TrainNet(object):
         for rec in self.records:
             if rec['kind'] not in ('conv_bn', 'conv_act') or rec['stem'] is not None or rec['pool_after'] is not None or not self.window:
                 continue
+            if rec.get('group') is not None:
+                continue
             if tuple(rec['stride']) != (1, 1):
                 continue                                             # strided: the dilated copy carries the border
             kh, kw, pad, out = rec['kh'], rec['kw'], rec['pad'], rec['out']
@@ -343,6 +345,71 @@ class TrainNet(object):
                                  pw=pw, pg=pg, pb=pb, mean=mean, invstd=invstd, wf=wf, Co=Co, Ci=Ci, kh=kh, kw=kw, stem=stem_geom,
                                  H=H, W=W, name=conv, raw=raw, pool_after=pool_after))
         return out
+
+    def conv_bn_group(self, x, sd, specs, eps=1e-5, name='group'):
+        """Sibling 1x1 conv + BN + ReLU units that read the SAME input (the branches of an Inception block): ONE forward GEMM with
+        the filters concatenated along N, ONE weight-gradient launch and ONE data-gradient launch (K = all branches' channels)
+        instead of one each per branch -- the block input is read once per pass instead of once per branch, and its gradient is
+        written once instead of read-modify-written by every branch.  BatchNorm stays per branch (slices of the fused conv
+        output / gradient tensors).  ``specs``: dicts(conv, bn, out=None, out_pad=(0, 0), pool_after=None); returns the
+        activation views.  Records stay per branch (same fields as conv_bn), so the teacher-forced checker sees ordinary units."""
+        B, dt = self.batch, self.cdtype
+        ws = [sd[sp['conv'] + '.weight'].float() for sp in specs]
+        assert all(tuple(w.shape[2:]) == (1, 1) and int(w.shape[1]) == x.C for w in ws)
+        Cos, Ci, H, W = [int(w.shape[0]) for w in ws], x.C, x.H, x.W
+        Ctot = sum(Cos)
+        Zf = self.alloc(H, W, Ctot)                                  # fused conv output [.., sum Co]
+        DZf = View(torch.zeros((B, H, W, Ctot), dtype=self.tdtype, device=self.device))     # its gradient
+        self.keep.append(DZf.t)
+        # the conv weights back to back in the arena (one [sum Co][1][Ci] block for the fused weight gradient), then the BN vectors
+        pws = [self._param(sp['conv'] + '.weight', w.permute(0, 2, 3, 1).reshape(co, 1, Ci).contiguous(), 'conv',
+                           dict(Ci=Ci, kh=1, kw=1, stem=None)) for sp, w, co in zip(specs, ws, Cos)]
+        for a, b in zip(pws[:-1], pws[1:]):
+            assert b.off == a.off + a.n, 'group weights must be contiguous'
+        li = len(self.fp.layer_names)
+        self.fp.conv(x, [dict(weight=torch.cat(ws, 0), scale=torch.ones(Ctot), shift=torch.zeros(Ctot), relu=False, out=Zf)], name=name)
+        wf = self.fp.last_weight
+        self.fwd.append(lambda: self.fp.run(B, li, li + 1))
+        group = dict(x=x, Zf=Zf, DZf=DZf, pws=pws, Cos=Cos, Ci=Ci, wf=wf, H=H, W=W, n=len(specs), done=0, name=name)
+        outs, c0 = [], 0
+        for sp, co, pw in zip(specs, Cos, pws):
+            bn, pool_after = sp['bn'], sp.get('pool_after')
+            zs = Zf.slice(c0, c0 + co)
+            raw, z = (zs, self.alloc(H, W, co)) if pool_after is not None else (None, zs)
+            if pool_after is not None:
+                assert tuple(pool_after) == (3, 1, 1)
+            out = sp.get('out')
+            if out is None:
+                out = self.alloc(H, W, co, sp.get('out_pad', (0, 0)))
+            pg = self._param(bn + '.weight', sd[bn + '.weight'], 'vec')
+            pb = self._param(bn + '.bias', sd[bn + '.bias'], 'vec')
+            if self._share is not None:
+                rm, rv = self._share.buffers[bn + '.running_mean'], self._share.buffers[bn + '.running_var']
+                self.buffers[bn + '.num_batches_tracked'] = self._share.buffers[bn + '.num_batches_tracked']
+            else:
+                rm = self._f32(co); rm.copy_(sd[bn + '.running_mean'])
+                rv = self._f32(co); rv.copy_(sd[bn + '.running_var'])
+                self.buffers[bn + '.num_batches_tracked'] = sd.get(bn + '.num_batches_tracked', torch.zeros((), dtype=torch.long)).clone()
+            self.buffers[bn + '.running_mean'], self.buffers[bn + '.running_var'] = rm, rv
+            mean, invstd = self._f32(co), self._f32(co)
+            rawd = _vd(raw) if raw is not None else None
+            zd, od = _vd(z), _vd(out)
+
+            def fwd(rawd=rawd, zd=zd, od=od, mean=mean, invstd=invstd, rm=rm, rv=rv, pg=pg, pb=pb, pa=pool_after):
+                if rawd is not None:
+                    self._call('ifcb_avgpool_fwd', C.byref(rawd), C.byref(zd), B, pa[0], pa[1], pa[2], dt, self._stream())
+                self._call('ifcb_bn_stats', C.byref(zd), B, dt, eps, 0.1, self.acc.data_ptr(), mean.data_ptr(), invstd.data_ptr(),
+                           rm.data_ptr(), rv.data_ptr(), self._stream())
+                self._call('ifcb_bn_apply', C.byref(zd), C.byref(od), None, B, dt, mean.data_ptr(), invstd.data_ptr(), pg.wptr, pb.wptr, 1,
+                           self._stream())
+            self.fwd.append(fwd)
+            self._nbt_keys.append(bn + '.num_batches_tracked')
+            self.records.append(dict(kind='conv_bn', x=x, z=z, out=out, residual=None, relu=True, stride=(1, 1), pad=(0, 0), pw=pw, pg=pg, pb=pb,
+                                     mean=mean, invstd=invstd, wf=wf, Co=co, Ci=Ci, kh=1, kw=1, stem=None, H=H, W=W, name=sp['conv'],
+                                     raw=raw, pool_after=pool_after, group=group, gslice=(c0, c0 + co)))
+            outs.append(out)
+            c0 += co
+        return outs
 
     def conv_act(self, x, sd, conv, stride=(1, 1), pad=(0, 0), relu=True, out=None, out_pad=(0, 0), stem=False, bias=True, weight=None,
                  linear=False, co_pad=None):
@@ -602,7 +669,72 @@ class TrainNet(object):
         # contiguous arena ranges to all-reduce as soon as the backward pass has finished them
         self.bucket_marks = plan_buckets(unit_lo, self.n_params, bucket_bytes // 4)
 
+    def _finalize_group_member(self, rec, claim):
+        """BatchNorm backward of one branch of a conv_bn_group into its slice of the fused gradient tensor; after the last branch
+        (the first in forward order) the fused weight-gradient and data-gradient launches."""
+        B, dt = self.batch, self.cdtype
+        g, (c0, c1) = rec['group'], rec['gslice']
+        z, out, Co = rec['z'], rec['out'], rec['Co']
+        dy = self.grad_of(out)
+        target = g['DZf'].slice(c0, c1)
+        pa = rec['pool_after']
+        if pa is not None:                                           # BN's dz is w.r.t. the POOLED tensor: own buffer, then avg-pool backward
+            dz = View(torch.zeros((B, z.H, z.W, Co), dtype=self.tdtype, device=self.device))
+            self.keep.append(dz.t)
+        else:
+            dz = target
+        rec['dy'], rec['dz'] = dy, dz
+        dyd, zd, dzd, td = _vd(dy), _vd(z), _vd(dz), _vd(target)
+        pg, pb, mean, invstd = rec['pg'], rec['pb'], rec['mean'], rec['invstd']
+
+        def bn_bwd():
+            self._call('ifcb_bn_backward', C.byref(dyd), None, C.byref(zd), C.byref(dzd), None, 0, 1, B, dt, mean.data_ptr(), invstd.data_ptr(),
+                       pg.wptr, pb.wptr, self.acc.data_ptr(), pg.gptr, pb.gptr, self._stream())
+            if pa is not None:
+                self._call('ifcb_avgpool_bwd', C.byref(dzd), C.byref(td), 0, B, pa[0], pa[1], pa[2], dt, self._stream())
+        self.bwd.append(bn_bwd)
+        if pa is not None:
+            rec['dr'] = target
+        g['done'] += 1
+        if g['done'] < g['n']:
+            return pg.off
+        # ---- all branches have written their slice of DZf: fused weight gradient + data gradient ----
+        x, Ci, Ctot, pws = g['x'], g['Ci'], sum(g['Cos']), g['pws']
+        DZf = g['DZf']
+        wd = WgradDesc()
+        wd.d_in, wd.in_ld, wd.Cin = x.ptr, x.ld, x.C
+        wd.batch, wd.H, wd.W = B, g['H'], g['W']
+        wd.in_pad_h, wd.in_pad_w = x.pad
+        wd.kh, wd.kw, wd.stride_h, wd.stride_w, wd.pad_h, wd.pad_w = 1, 1, 1, 1, 0, 0
+        wd.d_dout, wd.dout_ld, wd.Cout = DZf.ptr, DZf.ld, Ctot
+        wd.dout_pad_h, wd.dout_pad_w = DZf.pad
+        wd.dtype = dt
+        if self.deterministic:
+            self._det_need = max(self._det_need, int(self.lib.ifcb_conv_wgrad_workspace_bytes(C.byref(wd))))
+        gptr0 = pws[0].gptr
+
+        def wgrad():
+            wd.d_dweight = gptr0
+            self._call('ifcb_conv_wgrad', C.byref(wd), self._stream())
+        self.bwd.append(wgrad)
+        dx = self.grad_of(x)
+        acc = claim(x)
+        dg = build_dgrad(self.bp, DZf, dx, Ctot, Ci, 1, 1, (1, 1), (0, 0), acc, name='dgrad.' + g['name'])
+        self.bwd.extend(dg['run'])
+        geo_f = _lib.conv_geometry(Ci, Ctot, 1, 1)
+        wf, wdg = g['wf'], dg['weight']
+        assert wf.shape[1] == geo_f['Cin_pad']
+        co0 = 0
+        for pw, co in zip(pws, g['Cos']):
+            self.repacks.append((pw, co, 1, Ci, wf.data_ptr() + 2 * co0 * geo_f['Cin_pad'], geo_f['Cin_pad'],
+                                 wdg.data_ptr() + 2 * co0, dg['Cin_pad']))
+            co0 += co
+        self.keep.extend([wf, wdg])
+        return pws[0].off
+
     def _finalize_conv(self, rec, claim):
+        if rec.get('group') is not None:
+            return self._finalize_group_member(rec, claim)
         B, dt = self.batch, self.cdtype
         x, z, out, residual = rec['x'], rec['z'], rec['out'], rec['residual']
         Co, Ci, kh, kw = rec['Co'], rec['Ci'], rec['kh'], rec['kw']
@@ -687,7 +819,8 @@ class TrainNet(object):
             import numpy as np
             items = (_lib.RepackItem * len(self.repacks))()
             for it, (pw, Co, taps, Ci, wf, cin_pad, wdg, cout_padk) in zip(items, self.repacks):
-                it.d_master, it.d_wfwd, it.d_wdgrad = pw.wptr, wf.data_ptr(), (wdg.data_ptr() if wdg is not None else None)
+                ptr = lambda t: t if (t is None or isinstance(t, int)) else t.data_ptr()
+                it.d_master, it.d_wfwd, it.d_wdgrad = pw.wptr, ptr(wf), ptr(wdg)
                 it.Cout, it.taps, it.Cin, it.Cin_pad, it.Cout_padk = Co, taps, Ci, cin_pad, cout_padk
             raw = np.frombuffer(bytes(items), dtype=np.uint8).copy()
             self._repack_table = torch.from_numpy(raw).to(self.device)
@@ -884,9 +1017,28 @@ def _build_inception_train(tn, sd):
     a = cb(a, 'Conv2d_3b_1x1')
     a = cb(a, 'Conv2d_4a_3x3')
     x = tn.maxpool(a, 3, 2, 0)
+    fuse = os.environ.get('IFCB_TRAIN_FUSE_SIBLINGS', '1') != '0'        # sibling 1x1 convs of a block as one GEMM (A/B switch)
+
+    def spec(prefix, out=None, nxt=None, pool_after=None, Hh=None):
+        sp = dict(conv=prefix + '.conv', bn=prefix + '.bn', out=out, pool_after=pool_after)
+        if nxt is not None and out is None:
+            sp['out_pad'] = tn.border(Hh, Hh, int(sd[prefix + '.conv.weight'].shape[0]), nxt[0], nxt[1], pad=nxt[2])
+        return sp
+
     for blk, pf in (('Mixed_5b', 32), ('Mixed_5c', 64), ('Mixed_5d', 64)):
         H = x.H
         out = tn.alloc(H, H, 224 + pf)
+        if fuse:
+            _, t5, t3, _ = tn.conv_bn_group(x, sd, [spec(blk + '.branch1x1', out=out.slice(0, 64)),
+                                                    spec(blk + '.branch5x5_1', nxt=(64, (5, 5), (2, 2)), Hh=H),
+                                                    spec(blk + '.branch3x3dbl_1', nxt=(96, (3, 3), (1, 1)), Hh=H),
+                                                    spec(blk + '.branch_pool', out=out.slice(224, 224 + pf), pool_after=(3, 1, 1))],
+                                            eps=eps, name=blk + '.1x1s')
+            cb(t5, blk + '.branch5x5_2', pad=(2, 2), out=out.slice(64, 128))
+            t = cb(t3, blk + '.branch3x3dbl_2', pad=(1, 1), nxt=(96, (3, 3), (1, 1)))
+            cb(t, blk + '.branch3x3dbl_3', pad=(1, 1), out=out.slice(128, 224))
+            x = out
+            continue
         cb(x, blk + '.branch1x1', out=out.slice(0, 64))
         t = cb(x, blk + '.branch5x5_1', nxt=(64, (5, 5), (2, 2)))
         cb(t, blk + '.branch5x5_2', pad=(2, 2), out=out.slice(64, 128))
@@ -908,6 +1060,20 @@ def _build_inception_train(tn, sd):
         H = x.H
         out = tn.alloc(H, H, 768)
         w17, w71 = (1, 7), (7, 1)
+        if fuse:
+            _, t7, td, _ = tn.conv_bn_group(x, sd, [spec(blk + '.branch1x1', out=out.slice(0, 192)),
+                                                    spec(blk + '.branch7x7_1', nxt=(c7, w17, (0, 3)), Hh=H),
+                                                    spec(blk + '.branch7x7dbl_1', nxt=(c7, w71, (3, 0)), Hh=H),
+                                                    spec(blk + '.branch_pool', out=out.slice(576, 768), pool_after=(3, 1, 1))],
+                                            eps=eps, name=blk + '.1x1s')
+            t = cb(t7, blk + '.branch7x7_2', pad=(0, 3), nxt=(192, w71, (3, 0)))
+            cb(t, blk + '.branch7x7_3', pad=(3, 0), out=out.slice(192, 384))
+            t = cb(td, blk + '.branch7x7dbl_2', pad=(3, 0), nxt=(c7, w17, (0, 3)))
+            t = cb(t, blk + '.branch7x7dbl_3', pad=(0, 3), nxt=(c7, w71, (3, 0)))
+            t = cb(t, blk + '.branch7x7dbl_4', pad=(3, 0), nxt=(192, w17, (0, 3)))
+            cb(t, blk + '.branch7x7dbl_5', pad=(0, 3), out=out.slice(384, 576))
+            x = out
+            continue
         cb(x, blk + '.branch1x1', out=out.slice(0, 192))
         t = cb(x, blk + '.branch7x7_1', nxt=(c7, w17, (0, 3)))
         t = cb(t, blk + '.branch7x7_2', pad=(0, 3), nxt=(192, w71, (3, 0)))
@@ -928,9 +1094,14 @@ def _build_inception_train(tn, sd):
     blk = 'Mixed_7a'
     H2 = (x.H - 3) // 2 + 1
     out = tn.alloc(H2, H2, 1280)
-    t = cb(x, blk + '.branch3x3_1')
+    if fuse:
+        t, t7 = tn.conv_bn_group(x, sd, [spec(blk + '.branch3x3_1'), spec(blk + '.branch7x7x3_1', nxt=(192, (1, 7), (0, 3)), Hh=x.H)],
+                                 eps=eps, name=blk + '.1x1s')
+    else:
+        t = cb(x, blk + '.branch3x3_1')
+        t7 = cb(x, blk + '.branch7x7x3_1', nxt=(192, (1, 7), (0, 3)))
     cb(t, blk + '.branch3x3_2', (2, 2), out=out.slice(0, 320))
-    t = cb(x, blk + '.branch7x7x3_1', nxt=(192, (1, 7), (0, 3)))
+    t = t7
     t = cb(t, blk + '.branch7x7x3_2', pad=(0, 3), nxt=(192, (7, 1), (3, 0)))
     t = cb(t, blk + '.branch7x7x3_3', pad=(3, 0))
     cb(t, blk + '.branch7x7x3_4', (2, 2), out=out.slice(320, 512))
@@ -939,6 +1110,19 @@ def _build_inception_train(tn, sd):
     for blk in ('Mixed_7b', 'Mixed_7c'):
         H = x.H
         out = tn.alloc(H, H, 2048)
+        if fuse:
+            _, t, td, _ = tn.conv_bn_group(x, sd, [spec(blk + '.branch1x1', out=out.slice(0, 320)),
+                                                   spec(blk + '.branch3x3_1', nxt=(384, (3, 3), (1, 1)), Hh=H),
+                                                   spec(blk + '.branch3x3dbl_1', nxt=(384, (3, 3), (1, 1)), Hh=H),
+                                                   spec(blk + '.branch_pool', out=out.slice(1856, 2048), pool_after=(3, 1, 1))],
+                                           eps=eps, name=blk + '.1x1s')
+            cb(t, blk + '.branch3x3_2a', pad=(0, 1), out=out.slice(320, 704))
+            cb(t, blk + '.branch3x3_2b', pad=(1, 0), out=out.slice(704, 1088))
+            t = cb(td, blk + '.branch3x3dbl_2', pad=(1, 1), nxt=(384, (3, 3), (1, 1)))
+            cb(t, blk + '.branch3x3dbl_3a', pad=(0, 1), out=out.slice(1088, 1472))
+            cb(t, blk + '.branch3x3dbl_3b', pad=(1, 0), out=out.slice(1472, 1856))
+            x = out
+            continue
         cb(x, blk + '.branch1x1', out=out.slice(0, 320))
         t = cb(x, blk + '.branch3x3_1', nxt=(384, (3, 3), (1, 1)))        # read by the 1x3 and the 3x1 sibling
         cb(t, blk + '.branch3x3_2a', pad=(0, 1), out=out.slice(320, 704))
