@@ -22,6 +22,12 @@ WGRAD_CASES = [
     ('3x3p1_128_192', 5, 128, 17, 17, 192, 3, 3, (1, 1), (1, 1)),
     ('1x7_160_160', 2, 160, 17, 17, 160, 1, 7, (1, 1), (0, 3)),
     ('7x7s2p3_8_64', 2, 8, 32, 32, 64, 7, 7, (2, 2), (3, 3)),
+    # Cin <= 32: 32-channel x blocks (64-byte rows), four per M = 128
+    ('3x3_32_32', 3, 32, 21, 21, 32, 3, 3, (1, 1), (0, 0)),
+    ('3x3p1_32_64', 2, 32, 19, 19, 64, 3, 3, (1, 1), (1, 1)),
+    ('1x1_32_80', 4, 32, 11, 13, 80, 1, 1, (1, 1), (0, 0)),
+    ('3x3s2_24_48', 2, 24, 23, 23, 48, 3, 3, (2, 2), (0, 0)),
+    ('5x5p2_16_32', 2, 16, 12, 12, 32, 5, 5, (1, 1), (2, 2)),
 ]
 
 
