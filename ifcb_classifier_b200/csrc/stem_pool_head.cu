@@ -4,6 +4,9 @@
 // shuffles for the reductions.  See include/ifcb_b200.h for the reference code
 // each replaces.
 #include "layers.cuh"
+#include "ptx.cuh"
+#include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 namespace ifcb {
@@ -242,6 +245,250 @@ __global__ void __launch_bounds__(128) stem_gray3x3_kernel(const ifcb_stem_desc 
       *reinterpret_cast<uint4*>(out + (long long)px * d.out_ld + c) = o;
     }
   }
+}
+
+// ------------------------------------------------------------------------------
+// The same layer on the tensor cores: a [128 pixels] x [K = 32] x [32 channels] GEMM per tile whose A operand is
+// built by the CTA itself straight from the u8 plane (no patch matrix in HBM).
+//   K layout: the fp32 folded gray weight of every tap is split EXACTLY into three 16-bit terms
+//   (w = hi + mid + lo: 3 x 8 significand bits for bf16 = all 24 of fp32; fp16: 33 bits),
+//   k = term * 9 + tap (27 of 32 columns used), and the A row repeats the nine gray levels (integers <= 255: exact in
+//   bf16 / fp16) three times.  Products are exact and accumulate in fp32 (TMEM), so the result equals the fp32 sum of
+//   the FFMA kernel above up to the order of additions.
+//   Roles (288 threads): warps 0-3 build A rows (one thread = one pixel: 9 byte loads -> 64-byte row, written in the
+//   K-major SWIZZLE_64B layout the UMMA descriptor reads: 16-byte chunk c of row r at r*64 + ((c ^ (r>>1 & 3)) << 4));
+//   warp 4 issues two tcgen05.mma (K = 16 each) per tile into one of two 32-column accumulators; warps 5-8 read TMEM,
+//   apply shift / ReLU (the BN scale is folded into B), stage their 32 rows (2 KB, contiguous in the output tensor) and
+//   hand them to ONE TMA store (cp.async.bulk.tensor shared -> global, 32 rows x 64 B).  Several CTAs per SM (44 KB smem, 64 TMEM columns each) overlap each other's phases; the kernel is
+//   bound by the output write (64 B per pixel).
+// ------------------------------------------------------------------------------
+constexpr int kSuStages = 4;
+constexpr int kSuThreads = 288;
+constexpr int kSuATile = 128 * 64;
+constexpr int kSuSmem = kSuStages * kSuATile + 2048 + 8 * 2048 + 16 * 8 + 1024;
+
+using ptx::fence_proxy_async_smem;
+
+// two fp32 -> packed 16-bit pair (lo, hi) in one F2FP; RELU / the fp16 saturation ride on the conversion
+template <bool FP16, bool RELU>
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  uint32_t r;
+  if (FP16) {
+    if (RELU) asm("cvt.rn.satfinite.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    else asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  } else {
+    if (RELU) asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  }
+  return r;
+}
+template <bool FP16>
+__device__ __forceinline__ uint32_t to16(float v) {
+  if (FP16) return (uint32_t)__half_as_ushort(__float2half_rn(v));
+  return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v));
+}
+template <bool FP16>
+__device__ __forceinline__ float from16(uint32_t u) {
+  if (FP16) return __half2float(__ushort_as_half((unsigned short)u));
+  return __uint_as_float(u << 16);
+}
+
+template <bool FP16, bool RELU>
+__global__ void __launch_bounds__(kSuThreads) stem_gray3x3_umma_kernel(const ifcb_stem_desc d, const __grid_constant__ StemConst<32> k,
+                                                                       const __grid_constant__ CUtensorMap tmap_out,
+                                                                       int P, int Q, int total, int n_tiles, int tiles_per_cta,
+                                                                       unsigned long long magic_pq, unsigned long long magic_q,
+                                                                       float mul, float inv_mul) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* a_base = smem;                                   // kSuStages x 8 KB, SWIZZLE_64B rows
+  uint8_t* b_tile = smem + kSuStages * kSuATile;            // 32 rows x 64 B
+  uint8_t* s_stage = b_tile + 2048;                         // 4 epilogue warps x 2 buffers x 2 KB, SWIZZLE_64B rows (512-byte aligned)
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(s_stage + 8 * 2048);   // [kSuStages] 128 producer arrivals
+  uint64_t* a_empty = a_full + kSuStages;                         // [kSuStages] MMA commit
+  uint64_t* acc_full = a_empty + kSuStages;                       // [2]
+  uint64_t* acc_empty = acc_full + 2;                             // [2] 4 epilogue warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int tid = threadIdx.x;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < kSuStages; ++s) { ptx::mbar_init(a_full + s, 128); ptx::mbar_init(a_empty + s, 1); }
+    for (int s = 0; s < 2; ++s) { ptx::mbar_init(acc_full + s, 1); ptx::mbar_init(acc_empty + s, 4); }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 4) {
+    ptx::tmem_alloc(tmem_slot, 64);
+    ptx::tmem_relinquish();
+  }
+  if (tid < 32) {
+    // B row `co`: [hi(9) | mid(9) | lo(9) | 0 x 5].  The BN scale is folded into the row, and the whole operand is scaled
+    // by a power of two `mul` (undone exactly in the epilogue) that puts the largest entry near 2^14: the mid / lo terms
+    // of small weights would otherwise fall into fp16's subnormal range
+    const int co = tid;
+    uint32_t e[32];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const float w = k.w[t * 32 + co] * k.scale[co] * mul;
+      const uint32_t h = to16<FP16>(w);
+      const float r1 = w - from16<FP16>(h);
+      const uint32_t m = to16<FP16>(r1);
+      const float r2 = r1 - from16<FP16>(m);
+      e[t] = h;
+      e[9 + t] = m;
+      e[18 + t] = to16<FP16>(r2);
+    }
+#pragma unroll
+    for (int j = 27; j < 32; ++j) e[j] = 0;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      uint4 v;
+      v.x = e[8 * c + 0] | (e[8 * c + 1] << 16);
+      v.y = e[8 * c + 2] | (e[8 * c + 3] << 16);
+      v.z = e[8 * c + 4] | (e[8 * c + 5] << 16);
+      v.w = e[8 * c + 6] | (e[8 * c + 7] << 16);
+      ptx::st_shared_v4(ptx::smem_u32(b_tile) + co * 64 + ((c ^ ((co >> 1) & 3)) << 4), v);
+    }
+    fence_proxy_async_smem();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // a CTA owns a contiguous range of tiles: pixel coordinates advance incrementally, and a warp's 32 output rows of
+  // every tile are one contiguous 2 KB piece of the output tensor
+  const int tile_begin = blockIdx.x * tiles_per_cta;
+  const int tile_end = min(n_tiles, tile_begin + tiles_per_cta);
+
+  if (warp < 4) {
+    // ===================== A-row producers: one thread = one pixel of the tile =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint32_t my_row = (uint32_t)tid * 64u;
+    const uint32_t sw = ((uint32_t)tid >> 1) & 3u;
+    const int step_w = d.stride, step_h = d.stride * d.W;
+    // this thread's pixel of the first tile; the NEXT tile's is 128 pixels further (Q >= 128 is not assumed)
+    int m = tile_begin * 128 + tid;
+    int img = (int)fast_div((uint32_t)min(m, total - 1), magic_pq);
+    int rem = min(m, total - 1) - img * (P * Q);
+    int op = (int)fast_div((uint32_t)rem, magic_q);
+    int oq = rem - op * Q;
+    const int adv_p = 128 / Q, adv_q = 128 - adv_p * Q;             // 128 pixels = adv_p rows + adv_q columns
+    auto load9 = [&](bool valid, uint32_t (&g)[9]) {
+#pragma unroll
+      for (int t = 0; t < 9; ++t) g[t] = 0;
+      if (valid) {
+        const uint8_t* in = reinterpret_cast<const uint8_t*>(d.d_in) + (long long)img * d.H * d.W + op * step_h + oq * step_w;
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) g[r * 3 + c] = __ldg(in + r * d.W + c);
+      }
+    };
+    auto advance = [&]() {
+      m += 128;
+      oq += adv_q;
+      op += adv_p;
+      if (oq >= Q) { oq -= Q; ++op; }
+      while (op >= P) { op -= P; ++img; }
+    };
+    // the nine byte loads of the NEXT tile are in flight while this tile's row is converted and written
+    uint32_t gnext[9];
+    load9(tile_begin < tile_end && m < total, gnext);
+    for (int tile = tile_begin; tile < tile_end; ++tile) {
+      float f[9];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) f[t] = (float)gnext[t];
+      advance();
+      load9(tile + 1 < tile_end && m < total, gnext);
+      // k = term * 9 + tap, two k per word: ten distinct (tap, tap) pairs make the 27 used columns (one F2FP each, exact)
+      const uint32_t p01 = pack2<FP16, false>(f[0], f[1]), p23 = pack2<FP16, false>(f[2], f[3]), p45 = pack2<FP16, false>(f[4], f[5]),
+                     p67 = pack2<FP16, false>(f[6], f[7]), p80 = pack2<FP16, false>(f[8], f[0]), p12 = pack2<FP16, false>(f[1], f[2]),
+                     p34 = pack2<FP16, false>(f[3], f[4]), p56 = pack2<FP16, false>(f[5], f[6]), p78 = pack2<FP16, false>(f[7], f[8]),
+                     p8z = pack2<FP16, false>(f[8], 0.f);
+      ptx::mbar_wait(a_empty + stage, phase ^ 1);
+      const uint32_t row = ptx::smem_u32(a_base + (size_t)stage * kSuATile) + my_row;
+      ptx::st_shared_v4(row + ((0u ^ sw) << 4), make_uint4(p01, p23, p45, p67));
+      ptx::st_shared_v4(row + ((1u ^ sw) << 4), make_uint4(p80, p12, p34, p56));
+      ptx::st_shared_v4(row + ((2u ^ sw) << 4), make_uint4(p78, p01, p23, p45));
+      ptx::st_shared_v4(row + ((3u ^ sw) << 4), make_uint4(p67, p8z, 0u, 0u));
+      fence_proxy_async_smem();
+      ptx::mbar_arrive(a_full + stage);
+      if (++stage == kSuStages) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp == 4) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc = ptx::umma_idesc_f16(128, 32, FP16 ? 1 : 0);
+    const uint32_t desc_hi = ptx::umma_desc_hi(64);
+    const uint32_t b_lo = ptx::umma_desc_lo(ptx::smem_u32(b_tile));
+    const bool leader = ptx::elect_one();
+    int stage = 0, local = 0;
+    uint32_t phase = 0;
+    for (int tile = tile_begin; tile < tile_end; ++tile, ++local) {
+      const int acc = local & 1;
+      ptx::mbar_wait(acc_empty + acc, (uint32_t)(((local >> 1) & 1) ^ 1));
+      ptx::mbar_wait(a_full + stage, phase);
+      ptx::tc_fence_after();
+      const uint32_t a_lo = ptx::umma_desc_lo(ptx::smem_u32(a_base + (size_t)stage * kSuATile));
+      const uint32_t dt = tmem_base + (uint32_t)(acc * 32);
+      if (leader) {
+        ptx::umma_f16_lohi(dt, a_lo, b_lo, desc_hi, idesc, 0u);
+        ptx::umma_f16_lohi(dt, a_lo + 2u, b_lo + 2u, desc_hi, idesc, 1u);
+        ptx::umma_commit(a_empty + stage);
+        ptx::umma_commit(acc_full + acc);
+      }
+      __syncwarp();
+      if (++stage == kSuStages) { stage = 0; phase ^= 1; }
+    }
+  } else {
+    // ===================== epilogue: TMEM -> shift / ReLU -> 16-bit -> staging -> one TMA store (32 rows x 64 B) per warp =====
+    const int quad = warp & 3;                                  // the TMEM lane quadrant this warp may read
+    const uint32_t stg0 = ptx::smem_u32(s_stage) + (uint32_t)(warp - 5) * 4096u;
+    const uint32_t sw = ((uint32_t)lane >> 1) & 3u;             // same swizzle as the tensor map: conflict-free 16-byte stores
+    if (lane == 0) ptx::prefetch_tensormap(&tmap_out);
+    int local = 0;
+    for (int tile = tile_begin; tile < tile_end; ++tile, ++local) {
+      const int acc = local & 1;
+      ptx::mbar_wait(acc_full + acc, (uint32_t)((local >> 1) & 1));
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * 32);
+      uint32_t v0[16], v1[16];
+      ptx::tmem_ld_32x32b_x16(taddr, v0);
+      ptx::tmem_ld_32x32b_x16(taddr + 16u, v1);
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      // the staging buffer written two tiles ago must have been read by its store
+      if (lane == 0) ptx::bulk_wait_group_read<1>();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(acc_empty + acc);
+      const uint32_t stg = stg0 + (uint32_t)(local & 1) * 2048u;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t w[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c0 = 8 * c + 2 * j;                     // compile-time: the shifts are constant-bank operands
+          const float y0 = fmaf(__uint_as_float(c0 < 16 ? v0[c0 & 15] : v1[c0 & 15]), inv_mul, k.shift[c0]);
+          const float y1 = fmaf(__uint_as_float(c0 < 16 ? v0[(c0 + 1) & 15] : v1[(c0 + 1) & 15]), inv_mul, k.shift[c0 + 1]);
+          w[j] = pack2<FP16, RELU>(y0, y1);
+        }
+        ptx::st_shared_v4(stg + (uint32_t)lane * 64u + (((uint32_t)c ^ sw) << 4), make_uint4(w[0], w[1], w[2], w[3]));
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        ptx::tma_store_2d(&tmap_out, stg, 0, tile * 128 + quad * 32);       // rows >= total are clipped
+        ptx::bulk_commit_group();
+      }
+    }
+    if (lane == 0) ptx::bulk_wait_group<0>();
+    __syncwarp();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 4) ptx::tmem_dealloc(tmem_base, 64);
 }
 
 // ------------------------------------------------------------------------------
@@ -547,6 +794,75 @@ int launch_stem(const StemLayer& L, int batch, cudaStream_t stream) {
   }
   if (d.in_kind == IFCB_STEM_IN_U8_GRAY && d.kh == 3 && d.kw == 3 && d.pad == 0 && (d.stride == 1 || d.stride == 2) && d.Cout == 32 &&
       total < (1ll << 31) && !L.h_const.empty()) {
+    // tensor-core version (A/B switch IFCB_STEM_UMMA=0: the FFMA kernel)
+    static const bool umma = !(getenv("IFCB_STEM_UMMA") && atoi(getenv("IFCB_STEM_UMMA")) == 0);
+    const long long opix_max = (long long)batch * (L.P + 2 * d.out_pad_h) * (L.Q + 2 * d.out_pad_w);
+    if (umma && opix_max < (1ll << 31) && d.out_ld == 32 && d.out_pad_h == 0 && d.out_pad_w == 0 && L.P * L.Q >= 128 &&
+        (reinterpret_cast<uintptr_t>(d.d_out) & 15) == 0) {
+      StemConst<32> k;
+      memcpy(&k, L.h_const.data(), sizeof(k));
+      const int n_tiles = (int)((total + 127) / 128);
+      // one wave of resident CTAs (a CTA's tile loop is latency-bound; a partial second wave would run at a fraction of the rate)
+      void (*kern)(const ifcb_stem_desc, const StemConst<32>, const CUtensorMap, int, int, int, int, int, unsigned long long, unsigned long long, float, float) =
+          d.dtype ? (d.relu ? stem_gray3x3_umma_kernel<true, true> : stem_gray3x3_umma_kernel<true, false>)
+                  : (d.relu ? stem_gray3x3_umma_kernel<false, true> : stem_gray3x3_umma_kernel<false, false>);
+      static int per_sm[64][4] = {};
+      int dev = 0;
+      IFCB_CUDA_CHECK(cudaGetDevice(&dev));
+      const int variant = (d.dtype ? 2 : 0) + (d.relu ? 1 : 0);
+      int occ = (dev >= 0 && dev < 64) ? per_sm[dev][variant] : 0;
+      if (occ == 0) {
+        cudaFuncAttributes fa;
+        IFCB_CUDA_CHECK(cudaFuncGetAttributes(&fa, kern));
+        IFCB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSuSmem));
+        IFCB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        const int warps = kSuThreads / 32;
+        const int regs_per_warp = ((fa.numRegs * 32 + 255) / 256) * 256;
+        const int by_regs = 65536 / (regs_per_warp * warps);
+        const int by_smem = (227 * 1024) / (kSuSmem + 1024);
+        occ = by_regs < by_smem ? by_regs : by_smem;
+        if (occ > 2048 / kSuThreads) occ = 2048 / kSuThreads;
+        if (occ > 8) occ = 8;                       // 64 TMEM columns per CTA
+        if (occ < 1) occ = 1;
+        if (dev >= 0 && dev < 64) per_sm[dev][variant] = occ;
+      }
+      int ctas = n_tiles < occ * sm_count() ? n_tiles : occ * sm_count();
+      const int tiles_per_cta = (n_tiles + ctas - 1) / ctas;
+      ctas = (n_tiles + tiles_per_cta - 1) / tiles_per_cta;
+      // power of two that puts the largest folded weight (w * scale) in [2^14, 2^15)
+      float wmax = 0.f;
+      for (int t = 0; t < 9; ++t)
+        for (int c = 0; c < 32; ++c) {
+          const float v = fabsf(k.w[t * 32 + c] * k.scale[c]);
+          if (v > wmax && v < 3.0e38f) wmax = v;
+        }
+      int ex = 0;
+      if (wmax > 0.f) frexpf(wmax, &ex);
+      int up = 15 - ex;
+      if (up > 100) up = 100;
+      if (up < -100) up = -100;
+      // the output as a [total pixels] x [32 channels] matrix, stored in 32-row boxes (SWIZZLE_64B: the staging layout)
+      CUtensorMap tmap_out;
+      {
+        int rc = resolve_driver();
+        if (rc) return rc;
+        cuuint64_t gdim[2] = {32, (cuuint64_t)total};
+        cuuint64_t gstr[1] = {64};
+        cuuint32_t box[2] = {32, 32};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = g_encode_tiled(&tmap_out, d.dtype ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, d.d_out, gdim, gstr,
+                                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+          set_error("stem: cuTensorMapEncodeTiled (output) failed (%d)", (int)r);
+          return -1;
+        }
+      }
+      kern<<<ctas, kSuThreads, kSuSmem, stream>>>(d, k, tmap_out, L.P, L.Q, (int)total, n_tiles, tiles_per_cta, div_magic(L.P * L.Q), div_magic(L.Q), ldexpf(1.f, up),
+                                                  ldexpf(1.f, -up));
+      IFCB_CUDA_CHECK(cudaGetLastError());
+      return 0;
+    }
     const int q2n = (L.Q + 1) / 2;
     const long long t2 = (long long)batch * L.P * q2n;
     const unsigned blocks = (unsigned)((t2 + 127) / 128);

@@ -125,9 +125,16 @@ def test_plain_cnn_parity(cuda, arch):
     fixtures.brief_train(model, x[:128], labels[:128], cuda, steps=30, batch=32, lr=1e-4)
     ref = _ref_scores(cuda, model, x)
     got = _pipeline_scores(cuda, arch, model, imgs, None)
-    agree = float((ref.argmax(1) == got.argmax(1)).float().mean())
+    # 192 ROIs leave no room for a single flip under the 99.5 % gate, and the fixture is trained on the GPU (cuDNN picks its
+    # algorithms per run), so a ROI whose two best reference scores are within 1e-3 of each other is a coin toss for the
+    # reference itself: such ties are left out of the agreement (and must be rare); the score gate covers every ROI
+    top2 = ref.topk(2, dim=1).values
+    decided = (top2[:, 0] - top2[:, 1]) > 1e-3
+    agree = float((ref.argmax(1) == got.argmax(1))[decided].float().mean())
     dmax = float((ref - got).abs().max())
-    print('%s fixture C: top-1 agreement %.4f, max|dscore| %.2e' % (arch, agree, dmax))
+    print('%s fixture C: top-1 agreement %.4f (%d of %d ROIs decided by > 1e-3), max|dscore| %.2e' %
+          (arch, agree, int(decided.sum()), len(decided), dmax))
+    assert float(decided.float().mean()) >= 0.9                 # vgg16 after 30 steps: 181 of 192
     assert agree >= 0.995 and dmax <= 1e-2, (agree, dmax)
 
 
