@@ -45,6 +45,17 @@ struct WgradParams {
   int dz_slots, x_stages;   // x_stages is even: a pair occupies two adjacent stages
   int fp16;
   int dz_im2col;            // dz is loaded through a 4-D (1x1 window) im2col map: the gradient tensor has a zero border
+  // WINDOW variant (stride 1, large feature maps): a pixel tile is a TH x TW rectangle of output pixels (TW a multiple of
+  // 16, TH * TW = 128).  ONE tiled 4-D TMA box per channel block brings the (TH + kh - 1) x (TW + kw - 1) input patch --
+  // every filter tap is then a UMMA descriptor whose start address is shifted by (r * pitch + s) patch rows, and the K = 16
+  // step k reads the 16 pixels of patch row k (+ r).  The input is read from L2 once per tile instead of kh * kw times,
+  // in long contiguous rows instead of 128 separate 64/128-byte im2col rows.
+  int window;
+  int th, tw;               // tile rectangle
+  int tiles_w, tiles_hw;    // tiles per output row of tiles, per image
+  int pitch;                // tw + kw - 1 patch pixels per patch row
+  int patch_stride;         // bytes of one channel block's patch in shared memory (1024-aligned)
+  int total_ptiles;         // pixel tiles of the whole batch
   float* dW;                // [Cout][taps][Cin] fp32, accumulated into
   float* ws;                // deterministic mode: [splits][Cout][taps][Cin] partials, STORED (each element by exactly one item)
   long long ws_stride;      // Cout * taps * Cin
@@ -66,7 +77,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_cons
   const int dz_slot_bytes = p.nblk_n * kBlk;
   uint8_t* dz_base = smem;
   uint8_t* x_base = smem + (size_t)p.dz_slots * dz_slot_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(x_base + (size_t)p.x_stages * kBlk);
+  const int x_stage_bytes = p.window ? p.cblocks * p.patch_stride : kBlk;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(x_base + (size_t)p.x_stages * x_stage_bytes);
   uint64_t* dz_full = bars;           // [dz_slots]
   uint64_t* dz_empty = bars + 4;
   uint64_t* x_full = bars + 8;        // [x_stages]
@@ -96,7 +108,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_cons
   const uint32_t tmem_base = *tmem_slot;
 
   const int items = p.n_cotiles * p.n_groups * p.splits;
-  const int total_ptiles = (p.rows + kPix - 1) / kPix;
+  const int total_ptiles = p.total_ptiles;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -111,6 +123,32 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_cons
       const int npair = min(p.group_size, p.n_mpairs - pair0);
       const int t_begin = split * p.tiles_per_split;
       const int t_end = min(total_ptiles, t_begin + p.tiles_per_split);
+      if (p.window) {
+        for (int pt = t_begin; pt < t_end; ++pt) {
+          const int img = pt / p.tiles_hw;
+          const int rem = pt - img * p.tiles_hw;
+          const int ty = rem / p.tiles_w, tx = rem - ty * p.tiles_w;
+          const int q0 = tx * p.tw, p0 = ty * p.th;
+          ptx::mbar_wait(dz_empty + dslot, dphase ^ 1);
+          if (ptx::elect_one()) {
+            uint8_t* dst = dz_base + (size_t)dslot * dz_slot_bytes;
+            ptx::mbar_arrive_expect_tx(dz_full + dslot, (uint32_t)dz_slot_bytes);
+            for (int bb = 0; bb < p.nblk_n; ++bb) ptx::tma_load_4d(dst + bb * kBlk, &tmap_dz, dz_full + dslot, co0 + bb * 64, q0, p0, img);
+          }
+          __syncwarp();
+          if (++dslot == p.dz_slots) { dslot = 0; dphase ^= 1; }
+          ptx::mbar_wait(x_empty + xstage, xphase ^ 1);
+          if (ptx::elect_one()) {
+            uint8_t* dst = x_base + (size_t)xstage * x_stage_bytes;
+            ptx::mbar_arrive_expect_tx(x_full + xstage, (uint32_t)(p.cblocks * (p.th + p.kh - 1) * p.pitch * 128));
+            for (int cb = 0; cb < p.cblocks; ++cb)
+              ptx::tma_load_4d(dst + (size_t)cb * p.patch_stride, &tmap_x, x_full + xstage, cb * 64, q0 - p.pad_w, p0 - p.pad_h, img);
+          }
+          __syncwarp();
+          if (++xstage == p.x_stages) { xstage = 0; xphase ^= 1; }
+        }
+        continue;
+      }
       for (int pt = t_begin; pt < t_end; ++pt) {
         const int m0 = pt * kPix;
         const int img = m0 / p.rows_per_img;
@@ -175,6 +213,49 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_cons
       const int t_end = min(total_ptiles, t_begin + p.tiles_per_split);
       ptx::mbar_wait(acc_empty, (uint32_t)((local & 1) ^ 1));
       ptx::tc_fence_after();
+      if (p.window) {
+        // K = 16 step k = the 16 pixels at column (k % kpr) * 16 of tile row k / kpr (kpr = tw / 16 steps per tile row)
+        const int kpr_shift = p.tw == 16 ? 0 : p.tw == 32 ? 1 : p.tw == 64 ? 2 : 3;
+        uint32_t koff[kPix / 16];
+#pragma unroll
+        for (int k = 0; k < kPix / 16; ++k)
+          koff[k] = (uint32_t)((k >> kpr_shift) * p.pitch + (k & ((1 << kpr_shift) - 1)) * 16) * 8u;      // 128-byte pixels, in 16-byte units
+        for (int pt = t_begin; pt < t_end; ++pt) {
+          ptx::mbar_wait(dz_full + dslot, dphase);
+          ptx::mbar_wait(x_full + xstage, xphase);
+          ptx::tc_fence_after();
+          const uint32_t b_lo0 = ((ptx::smem_u32(dz_base + (size_t)dslot * dz_slot_bytes) & 0x3FFFFu) >> 4) | lbo;
+          const uint32_t slot = ptx::smem_u32(x_base + (size_t)xstage * x_stage_bytes);
+          for (int g = 0; g < npair; ++g) {
+            // the pair's two 64-channel blocks: (tap, channel block) each; the second sits LBO bytes after the first
+            const int blk0 = (pair0 + g) * 2;
+            const int tap0 = blk0 / p.cblocks, cb0 = blk0 - tap0 * p.cblocks;
+            const int r0 = tap0 / p.kw, s0 = tap0 - r0 * p.kw;
+            const uint32_t addr0 = slot + (uint32_t)(cb0 * p.patch_stride + (r0 * p.pitch + s0) * 128);
+            uint32_t delta = 0;                                            // odd block count: rows 64-127 repeat block 0 (never stored)
+            if (blk0 + 1 < p.n_blocks) {
+              const int tap1 = (blk0 + 1) / p.cblocks, cb1 = blk0 + 1 - tap1 * p.cblocks;
+              const int r1 = tap1 / p.kw, s1 = tap1 - r1 * p.kw;
+              delta = slot + (uint32_t)(cb1 * p.patch_stride + (r1 * p.pitch + s1) * 128) - addr0;     // > 0: cblocks <= 2
+            }
+            const uint32_t a_lo0 = ((addr0 & 0x3FFFFu) >> 4) | ((delta >> 4) << 16);
+            const uint32_t d = tmem_base + (uint32_t)(g * p.tile_n);
+#pragma unroll
+            for (int k = 0; k < kPix / 16; ++k)
+              if (leader) ptx::umma_f16_lohi(d, a_lo0 + koff[k], b_lo0 + (uint32_t)(k * 128), hi, idesc, (pt > t_begin || k > 0) ? 1u : 0u);
+          }
+          if (leader) {
+            ptx::umma_commit(x_empty + xstage);
+            ptx::umma_commit(dz_empty + dslot);
+          }
+          __syncwarp();
+          if (++xstage == p.x_stages) { xstage = 0; xphase ^= 1; }
+          if (++dslot == p.dz_slots) { dslot = 0; dphase ^= 1; }
+        }
+        if (leader) ptx::umma_commit(acc_full);
+        __syncwarp();
+        continue;
+      }
       for (int pt = t_begin; pt < t_end; ++pt) {
         ptx::mbar_wait(dz_full + dslot, dphase);
         const uint32_t b_lo0 = ((ptx::smem_u32(dz_base + (size_t)dslot * dz_slot_bytes) & 0x3FFFFu) >> 4) | lbo;
@@ -257,6 +338,125 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_cons
   if (warp == 1) ptx::tmem_dealloc(tmem_base, 512);
 }
 
+
+// Geometry of a launch (everything but pointers and tensor maps): shared by ifcb_conv_wgrad and
+// ifcb_conv_wgrad_workspace_bytes so that the two always agree on the number of pixel-range splits.
+void set_tile_n(WgradParams& p, int tile_n) {
+  p.tile_n = tile_n;
+  p.n_cotiles = (p.Cout + tile_n - 1) / tile_n;
+  p.nblk_n = (tile_n + 63) / 64;
+  int n_acc = 512 / tile_n;
+  if (n_acc > 16) n_acc = 16;
+  p.n_groups = (p.n_mpairs + n_acc - 1) / n_acc;
+  p.group_size = (p.n_mpairs + p.n_groups - 1) / p.n_groups;
+  p.n_groups = (p.n_mpairs + p.group_size - 1) / p.group_size;
+}
+
+bool plan_wgrad(const ifcb_wgrad_desc* d, WgradParams& p, bool allow_window = true) {
+  const int P = (d->H + 2 * d->pad_h - d->kh) / d->stride_h + 1, Q = (d->W + 2 * d->pad_w - d->kw) / d->stride_w + 1;
+  if (P <= 0 || Q <= 0) return false;
+  const long long rows = (long long)d->batch * P * Q;
+  p.rows = (int)rows;
+  p.rows_per_img = P * Q;
+  p.row_w = Q;
+  p.kh = d->kh; p.kw = d->kw;
+  p.stride_h = d->stride_h; p.stride_w = d->stride_w;
+  p.pad_h = d->pad_h; p.pad_w = d->pad_w;
+  p.Cin = d->Cin; p.Cout = d->Cout;
+  p.cblocks = (d->Cin + 63) / 64;
+  p.taps = d->kh * d->kw;
+  p.n_blocks = p.taps * p.cblocks;
+  p.n_mpairs = (p.n_blocks + 1) / 2;
+  const int c16 = (d->Cout + 15) & ~15;
+  {
+    const int t = (c16 + 255) / 256;
+    set_tile_n(p, (((c16 + t - 1) / t) + 15) & ~15);
+  }
+  // ---- WINDOW variant: stride 1, more than one tap, <= 128 input channels, a feature map that TH x TW rectangles tile
+  // with little waste (A/B switch IFCB_WGRAD_WINDOW=0)
+  const char* wenv = getenv("IFCB_WGRAD_WINDOW");                 // read per call (tests flip it)
+  const bool window_on = !(wenv && atoi(wenv) == 0);
+  p.window = 0;
+  // Measured (B200, batch 256): the three 147^2 / 73^2 layers of Inception-v3 go from 905 / 897 / 889 us to 820 / 790 / 738 us;
+  // on ResNet-50's 56^2 / 28^2 layers the 14 % of padded tile area costs more than the fill saves (the MN-major MMA stream
+  // itself runs at ~110 clk per M = 128 x K = 16 step whatever N is, so every extra tile is paid in full): large maps only,
+  // unless IFCB_WGRAD_WINDOW=2 forces it wherever it is eligible (tests).
+  const bool window_all = wenv && atoi(wenv) == 2;
+  if (allow_window && window_on && d->stride_h == 1 && d->stride_w == 1 && p.taps > 1 && p.cblocks <= 2 && (window_all || P * Q >= 4096)) {
+    double best = 1e30;
+    for (int tw = 16; tw <= 128; tw *= 2) {
+      const int th = kPix / tw;
+      const int tiles_w = (Q + tw - 1) / tw, tiles_h = (P + th - 1) / th;
+      const double waste = (double)tiles_w * tw * tiles_h * th / ((double)P * Q);
+      const int patch_rows = (th + d->kh - 1) * (tw + d->kw - 1);
+      if (waste > 1.35 || tw + d->kw - 1 > 256 || th + d->kh - 1 > 256) continue;
+      const double cost = waste * (patch_rows * p.cblocks + kPix);
+      if (cost < best) {
+        best = cost;
+        p.window = 1;
+        p.tw = tw; p.th = th;
+        p.tiles_w = tiles_w;
+        p.tiles_hw = tiles_w * tiles_h;
+        p.pitch = tw + d->kw - 1;
+        p.patch_stride = (patch_rows * 128 + 1023) & ~1023;
+      }
+    }
+  }
+  if (p.window) {
+    // output-channel tile: the split of Cout that minimises, per pixel tile and summed over the work items that sweep it,
+    // max(MMA issue, shared-memory fill at ~40 B/clk) -- a wide tile leaves few TMEM accumulators, so the pixel range is
+    // swept (and dz re-read) once per group of block pairs
+    double best = 1e30;
+    int best_tn = p.tile_n;
+    for (int t = (c16 + 255) / 256; t <= 4; ++t) {
+      const int tn = (((c16 + t - 1) / t) + 15) & ~15;
+      set_tile_n(p, tn);
+      const double t_mma = tn / 2 > 32 + tn / 4 ? tn / 2 : 32 + tn / 4;
+      const double fill = (p.nblk_n * kBlk + p.cblocks * p.patch_stride) / 40.0;
+      double total = 0;
+      for (int g = 0; g < p.n_groups; ++g) {
+        int np = p.n_mpairs - g * p.group_size;
+        if (np > p.group_size) np = p.group_size;
+        const double mma = np * (kPix / 16) * t_mma;
+        total += mma > fill ? mma : fill;
+      }
+      total *= p.n_cotiles;
+      if (total < best) { best = total; best_tn = tn; }
+    }
+    set_tile_n(p, best_tn);
+    p.total_ptiles = d->batch * p.tiles_hw;
+  } else {
+    p.total_ptiles = (int)((rows + kPix - 1) / kPix);
+  }
+  const int ptiles = p.total_ptiles;
+  const int base_items = p.n_cotiles * p.n_groups;
+  static const int waves = getenv("IFCB_WGRAD_WAVES") ? atoi(getenv("IFCB_WGRAD_WAVES")) : 1;   // tuning knob (measured: 1 wave 28.3 / 37.5 ms per step, 2 waves 28.8 / 37.9, 4 waves 30.3 / 40.0)
+  int splits = (waves * sm_count() + base_items - 1) / base_items;     // about one wave of work items: every extra split adds a full tile of red.global traffic
+  if (splits > ptiles) splits = ptiles;
+  if (splits < 1) splits = 1;
+  p.tiles_per_split = (ptiles + splits - 1) / splits;
+  p.splits = (ptiles + p.tiles_per_split - 1) / p.tiles_per_split;
+  p.dz_slots = 2;
+  if (p.window) {
+    const int budget = 216 * 1024 - p.dz_slots * p.nblk_n * kBlk;
+    int st = budget / (p.cblocks * p.patch_stride);
+    if (st > 4) st = 4;
+    if (st < 2) {                      // no room for a double-buffered patch: the im2col variant
+      return plan_wgrad(d, p, false);
+    }
+    p.x_stages = st;
+  } else {
+    const int budget = 216 * 1024 - p.dz_slots * p.nblk_n * kBlk;
+    int st = budget / kBlk;
+    st &= ~1;
+    if (st > kMaxXStages) st = kMaxXStages;
+    if (st < 2) st = 2;
+    p.x_stages = st;
+  }
+  p.ws_stride = (long long)d->Cout * p.taps * d->Cin;
+  return true;
+}
+
 }  // namespace
 }  // namespace ifcb
 
@@ -282,8 +482,35 @@ extern "C" int ifcb_conv_wgrad(const ifcb_wgrad_desc* d, void* stream_v) {
   IFCB_ARG_CHECK(rows < (1ll << 31) - 256, "wgrad: too many output pixels");
   const CUtensorMapDataType dt = d->dtype == IFCB_ACT_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   CUtensorMap tmap_dz, tmap_x;
+  WgradParams p{};
+  IFCB_ARG_CHECK(plan_wgrad(d, p), "wgrad: empty output");
   const bool dz_border = d->dout_pad_h > 0 || d->dout_pad_w > 0;
-  if (dz_border) {
+  if (p.window) {
+    // tiled 4-D maps over the INTERIOR of both tensors (dims C, W, H, N; the physical borders only enter the strides): boxes that
+    // start at negative coordinates or run past the extent are zero-filled -- the conv's padding, and the ragged last tiles
+    {
+      const int Pp = P + 2 * d->dout_pad_h, Qp = Q + 2 * d->dout_pad_w;
+      const char* base = reinterpret_cast<const char*>(d->d_dout) + ((size_t)d->dout_pad_h * Qp + d->dout_pad_w) * d->dout_ld * 2;
+      cuuint64_t gdim[4] = {(cuuint64_t)d->Cout, (cuuint64_t)Q, (cuuint64_t)P, (cuuint64_t)d->batch};
+      cuuint64_t gstr[3] = {(cuuint64_t)d->dout_ld * 2, (cuuint64_t)Qp * d->dout_ld * 2, (cuuint64_t)Pp * Qp * d->dout_ld * 2};
+      cuuint32_t box[4] = {64, (cuuint32_t)p.tw, (cuuint32_t)p.th, 1};
+      cuuint32_t estr[4] = {1, 1, 1, 1};
+      CUresult r = g_encode_tiled(&tmap_dz, dt, 4, const_cast<char*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      IFCB_ARG_CHECK(r == CUDA_SUCCESS, "wgrad: cuTensorMapEncodeTiled (dz window) failed (%d)", (int)r);
+    }
+    {
+      const int Hp = d->H + 2 * d->in_pad_h, Wp = d->W + 2 * d->in_pad_w;
+      const char* base = reinterpret_cast<const char*>(d->d_in) + ((size_t)d->in_pad_h * Wp + d->in_pad_w) * d->in_ld * 2;
+      cuuint64_t gdim[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->batch};
+      cuuint64_t gstr[3] = {(cuuint64_t)d->in_ld * 2, (cuuint64_t)Wp * d->in_ld * 2, (cuuint64_t)Hp * Wp * d->in_ld * 2};
+      cuuint32_t box[4] = {64, (cuuint32_t)p.pitch, (cuuint32_t)(p.th + d->kh - 1), 1};
+      cuuint32_t estr[4] = {1, 1, 1, 1};
+      CUresult r = g_encode_tiled(&tmap_x, dt, 4, const_cast<char*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      IFCB_ARG_CHECK(r == CUDA_SUCCESS, "wgrad: cuTensorMapEncodeTiled (x window) failed (%d)", (int)r);
+    }
+  } else if (dz_border) {
     // bordered gradient tensor [batch, P+2ph, Q+2pw, ld]: enumerate its interior pixels with a 1x1-window im2col map
     const int Pp = P + 2 * d->dout_pad_h, Qp = Q + 2 * d->dout_pad_w;
     const char* base = reinterpret_cast<const char*>(d->d_dout) + ((size_t)d->dout_pad_h * Qp + d->dout_pad_w) * d->dout_ld * 2;
@@ -308,7 +535,7 @@ extern "C" int ifcb_conv_wgrad(const ifcb_wgrad_desc* d, void* stream_v) {
                                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     IFCB_ARG_CHECK(r == CUDA_SUCCESS, "wgrad: cuTensorMapEncodeTiled failed (%d)", (int)r);
   }
-  {
+  if (!p.window) {
     cuuint64_t gdim[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->batch};
     const int Hp = d->H + 2 * d->in_pad_h, Wp = d->W + 2 * d->in_pad_w;
     const char* base = reinterpret_cast<const char*>(d->d_in) + ((size_t)d->in_pad_h * Wp + d->in_pad_w) * d->in_ld * 2;
@@ -325,58 +552,16 @@ extern "C" int ifcb_conv_wgrad(const ifcb_wgrad_desc* d, void* stream_v) {
     cudaDriverGetVersion(&drv);
     if (drv <= 13010 && bytes < 131072ull) reinterpret_cast<uint64_t*>(&tmap_x)[1] &= ~(1ull << 21);
   }
-  WgradParams p{};
-  p.rows = (int)rows;
-  p.rows_per_img = P * Q;
-  p.row_w = Q;
-  p.kh = d->kh; p.kw = d->kw;
-  p.stride_h = d->stride_h; p.stride_w = d->stride_w;
-  p.pad_h = d->pad_h; p.pad_w = d->pad_w;
-  p.Cin = d->Cin; p.Cout = d->Cout;
-  p.cblocks = (d->Cin + 63) / 64;
-  p.taps = d->kh * d->kw;
-  p.n_blocks = p.taps * p.cblocks;
-  p.n_mpairs = (p.n_blocks + 1) / 2;
-  {
-    const int c16 = (d->Cout + 15) & ~15;
-    const int t = (c16 + 255) / 256;
-    p.tile_n = (((c16 + t - 1) / t) + 15) & ~15;
-    p.n_cotiles = (d->Cout + p.tile_n - 1) / p.tile_n;
-    p.nblk_n = (p.tile_n + 63) / 64;
-  }
-  int n_acc = 512 / p.tile_n;
-  if (n_acc > 16) n_acc = 16;
-  p.n_groups = (p.n_mpairs + n_acc - 1) / n_acc;
-  p.group_size = (p.n_mpairs + p.n_groups - 1) / p.n_groups;
-  p.n_groups = (p.n_mpairs + p.group_size - 1) / p.group_size;
-  const int ptiles = (int)((rows + kPix - 1) / kPix);
-  const int base_items = p.n_cotiles * p.n_groups;
-  static const int waves = getenv("IFCB_WGRAD_WAVES") ? atoi(getenv("IFCB_WGRAD_WAVES")) : 1;   // tuning knob (measured: 1 wave 28.3 / 37.5 ms per step, 2 waves 28.8 / 37.9, 4 waves 30.3 / 40.0)
-  int splits = (waves * sm_count() + base_items - 1) / base_items;     // about one wave of work items: every extra split adds a full tile of red.global traffic
-  if (splits > ptiles) splits = ptiles;
-  if (splits < 1) splits = 1;
-  p.tiles_per_split = (ptiles + splits - 1) / splits;
-  p.splits = (ptiles + p.tiles_per_split - 1) / p.tiles_per_split;
-  p.dz_slots = 2;
-  {
-    const int budget = 216 * 1024 - p.dz_slots * p.nblk_n * kBlk;
-    int st = budget / kBlk;
-    st &= ~1;
-    if (st > kMaxXStages) st = kMaxXStages;
-    if (st < 2) st = 2;
-    p.x_stages = st;
-  }
   p.fp16 = d->dtype;
-  p.dz_im2col = dz_border ? 1 : 0;
+  p.dz_im2col = (dz_border && !p.window) ? 1 : 0;
   p.dW = d->d_dweight;
-  p.ws_stride = (long long)d->Cout * p.taps * d->Cin;
   p.ws = nullptr;
   if (det_enabled()) {
     p.ws = static_cast<float*>(det_workspace(4ll * p.splits * p.ws_stride));
     IFCB_ARG_CHECK(p.ws != nullptr, "wgrad: the deterministic workspace is smaller than the %lld bytes this layer needs (ifcb_conv_wgrad_workspace_bytes)",
                    4ll * p.splits * p.ws_stride);
   }
-  const int smem = p.dz_slots * p.nblk_n * kBlk + p.x_stages * kBlk + 512 + 1024;
+  const int smem = p.dz_slots * p.nblk_n * kBlk + p.x_stages * (p.window ? p.cblocks * p.patch_stride : kBlk) + 512 + 1024;
   {   // the opt-in shared-memory limit is a per-device function attribute
     static bool done[64] = {};
     int dev = 0;
@@ -400,27 +585,8 @@ extern "C" int ifcb_conv_wgrad(const ifcb_wgrad_desc* d, void* stream_v) {
 
 // bytes of deterministic workspace ifcb_conv_wgrad needs for this layer (pixel-range splits x the layer's gradient)
 extern "C" int64_t ifcb_conv_wgrad_workspace_bytes(const ifcb_wgrad_desc* d) {
-  if (!d || d->Cin <= 0 || d->Cout <= 0 || d->kh <= 0 || d->kw <= 0) return -1;
-  const int P = (d->H + 2 * d->pad_h - d->kh) / d->stride_h + 1, Q = (d->W + 2 * d->pad_w - d->kw) / d->stride_w + 1;
-  const long long rows = (long long)d->batch * P * Q;
-  const int taps = d->kh * d->kw, cblocks = (d->Cin + 63) / 64;
-  const int n_mpairs = (taps * cblocks + 1) / 2;
-  const int c16 = (d->Cout + 15) & ~15;
-  const int t = (c16 + 255) / 256;
-  const int tile_n = (((c16 + t - 1) / t) + 15) & ~15;
-  const int n_cotiles = (d->Cout + tile_n - 1) / tile_n;
-  int n_acc = 512 / tile_n;
-  if (n_acc > 16) n_acc = 16;
-  int n_groups = (n_mpairs + n_acc - 1) / n_acc;
-  const int group_size = (n_mpairs + n_groups - 1) / n_groups;
-  n_groups = (n_mpairs + group_size - 1) / group_size;
-  const int ptiles = (int)((rows + kPix - 1) / kPix);
-  const int base_items = n_cotiles * n_groups;
-  static const int waves = getenv("IFCB_WGRAD_WAVES") ? atoi(getenv("IFCB_WGRAD_WAVES")) : 1;
-  int splits = (waves * sm_count() + base_items - 1) / base_items;
-  if (splits > ptiles) splits = ptiles;
-  if (splits < 1) splits = 1;
-  const int tiles_per_split = (ptiles + splits - 1) / splits;
-  splits = (ptiles + tiles_per_split - 1) / tiles_per_split;
-  return 4ll * splits * d->Cout * taps * d->Cin;
+  if (!d || d->Cin <= 0 || d->Cout <= 0 || d->kh <= 0 || d->kw <= 0 || d->stride_h <= 0 || d->stride_w <= 0 || d->batch <= 0) return -1;
+  WgradParams p{};
+  if (!plan_wgrad(d, p)) return -1;
+  return 4ll * p.splits * p.ws_stride;
 }

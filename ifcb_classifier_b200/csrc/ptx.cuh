@@ -116,7 +116,14 @@ __device__ __forceinline__ void tma_load_im2col_4d(void* smem_dst, const void* t
       : "memory");
 }
 
-// ---- CTA pairs (cluster of 2, tcgen05 cta_group::2) -------------------------------------
+// tiled-mode load of a 4-D box (dims C, W, H, N; start coordinates may be negative or past the extent: zero fill)
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const void* tmap, uint64_t* bar, int c, int w, int h, int n) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n)
+      : "memory");
+}
 // TMA store of one box from shared memory (bulk async-group completion): coordinates innermost first; rows past the tensor's
 // extent are clipped by the hardware
 __device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t smem_src, int c0, int c1) {
@@ -130,6 +137,7 @@ template <int N>
 __device__ __forceinline__ void bulk_wait_group() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// ---- CTA pairs (cluster of 2, tcgen05 cta_group::2) -------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));

@@ -28,14 +28,23 @@ WGRAD_CASES = [
     ('1x1_32_80', 4, 32, 11, 13, 80, 1, 1, (1, 1), (0, 0)),
     ('3x3s2_24_48', 2, 24, 23, 23, 48, 3, 3, (2, 2), (0, 0)),
     ('5x5p2_16_32', 2, 16, 12, 12, 32, 5, 5, (1, 1), (2, 2)),
+    # stride 1 on feature maps that 128-pixel rectangles tile well: the WINDOW variant (one input patch per tile, taps by
+    # descriptor shift); ragged right / bottom tiles, two channel blocks, 16- and 64-pixel-wide tiles, an odd block count
+    ('3x3_80_192_win', 2, 80, 34, 34, 192, 3, 3, (1, 1), (0, 0)),
+    ('3x3p1_32_64_win', 2, 32, 47, 47, 64, 3, 3, (1, 1), (1, 1)),
+    ('1x7_64_96_win', 1, 64, 30, 62, 96, 1, 7, (1, 1), (0, 3)),
+    ('5x5p2_48_64_win', 2, 48, 31, 31, 64, 5, 5, (1, 1), (2, 2)),
+    ('3x3p1_128_256_win', 1, 128, 28, 28, 256, 3, 3, (1, 1), (1, 1)),
 ]
 
 
 @pytest.mark.parametrize('dt', ['bf16', 'fp16'])
 @pytest.mark.parametrize('case', WGRAD_CASES, ids=[c[0] for c in WGRAD_CASES])
-def test_conv_wgrad(cuda, case, dt):
+def test_conv_wgrad(cuda, case, dt, monkeypatch):
     from ifcb_classifier_b200 import _lib
     name, B, Cin, H, W, Cout, kh, kw, stride, pad = case
+    if name.endswith('_win'):            # the library keeps the WINDOW variant for maps >= 64 x 64 unless forced
+        monkeypatch.setenv('IFCB_WGRAD_WINDOW', '2')
     tdt = torch.bfloat16 if dt == 'bf16' else torch.float16
     g = torch.Generator().manual_seed(sum(name.encode()))
     x = torch.randn(B, Cin, H, W, generator=g).to(tdt).float()
