@@ -42,7 +42,7 @@ struct WgradParams {
   int n_groups, group_size; // block pairs per work item (<= 512 / tile_n accumulators), balanced
   int splits;               // pixel-range splits
   int tiles_per_split;      // 128-pixel tiles per split
-  int dz_slots, x_stages;   // x_stages is even: a pair occupies two adjacent stages
+  int dz_slots, x_stages;   // x ring: stages of one block pair (im2col) or of one tile's patches (WINDOW)
   int fp16;
   int dz_im2col;            // dz is loaded through a 4-D (1x1 window) im2col map: the gradient tensor has a zero border
   // WINDOW variant (stride 1, large feature maps): a pixel tile is a TH x TW rectangle of output pixels (TW a multiple of
@@ -77,7 +77,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_cons
   const int dz_slot_bytes = p.nblk_n * kBlk;
   uint8_t* dz_base = smem;
   uint8_t* x_base = smem + (size_t)p.dz_slots * dz_slot_bytes;
-  const int x_stage_bytes = p.window ? p.cblocks * p.patch_stride : kBlk;
+  const int x_stage_bytes = p.window ? p.cblocks * p.patch_stride : 2 * kBlk;       // WINDOW: a tile's patches; im2col: a pair of blocks
   uint64_t* bars = reinterpret_cast<uint64_t*>(x_base + (size_t)p.x_stages * x_stage_bytes);
   uint64_t* dz_full = bars;           // [dz_slots]
   uint64_t* dz_empty = bars + 4;
@@ -149,6 +149,11 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_cons
         }
         continue;
       }
+      // the item's first (filter tap, channel block): the only divisions besides the tile's pixel coordinates -- per block they
+      // made this warp's instruction stream (not the loads) the bound of the thin layers
+      const int blk_first = pair0 * 2;
+      const int tap_first = blk_first / p.cblocks, cb_first = blk_first - tap_first * p.cblocks;
+      const int r_first = tap_first / p.kw, s_first = tap_first - r_first * p.kw;
       for (int pt = t_begin; pt < t_end; ++pt) {
         const int m0 = pt * kPix;
         const int img = m0 / p.rows_per_img;
@@ -166,40 +171,51 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_cons
         }
         __syncwarp();
         if (++dslot == p.dz_slots) { dslot = 0; dphase ^= 1; }
-        for (int g = 0; g < npair; ++g) {
-#pragma unroll
-          for (int b = 0; b < 2; ++b) {
-            const int blk = (pair0 + g) * 2 + b;
-            const int tap = blk / p.cblocks, cb = blk - tap * p.cblocks;
-            const int r = tap / p.kw, s = tap - r * p.kw;
-            ptx::mbar_wait(x_empty + xstage, xphase ^ 1);
-            if (ptx::elect_one()) {
-              if (blk < p.n_blocks) {
-                ptx::mbar_arrive_expect_tx(x_full + xstage, (uint32_t)kBlk);
-                ptx::tma_load_im2col_4d(x_base + (size_t)xstage * kBlk, &tmap_x, x_full + xstage, cb * 64, w0, h0, img, (uint16_t)s,
-                                        (uint16_t)r);
-              } else {
-                // odd block count: the last pair has one block.  The stage still cycles through its barriers (the MMA
-                // reads whatever the slot holds into rows 64-127, which the epilogue never stores)
-                ptx::mbar_arrive(x_full + xstage);
-              }
-            }
-            __syncwarp();
-            if (++xstage == p.x_stages) { xstage = 0; xphase ^= 1; }
+        int r = r_first, sx = s_first, cb = cb_first, blk = blk_first;
+        for (int g = 0; g < npair; ++g, blk += 2) {
+          // one ring stage = the pair's two blocks under one barrier (an odd block count leaves the last pair with one block: the
+          // MMA reads whatever the second half holds into rows 64-127, which the epilogue never stores)
+          const bool two = blk + 1 < p.n_blocks;
+          int r1 = r, s1 = sx, cb1 = cb + 1;
+          if (cb1 == p.cblocks) { cb1 = 0; if (++s1 == p.kw) { s1 = 0; ++r1; } }
+          ptx::mbar_wait(x_empty + xstage, xphase ^ 1);
+          if (ptx::elect_one()) {
+            uint8_t* dst = x_base + (size_t)xstage * (2 * kBlk);
+            ptx::mbar_arrive_expect_tx(x_full + xstage, (uint32_t)(two ? 2 * kBlk : kBlk));
+            ptx::tma_load_im2col_4d(dst, &tmap_x, x_full + xstage, cb * 64, w0, h0, img, (uint16_t)sx, (uint16_t)r);
+            if (two) ptx::tma_load_im2col_4d(dst + kBlk, &tmap_x, x_full + xstage, cb1 * 64, w0, h0, img, (uint16_t)s1, (uint16_t)r1);
           }
+          __syncwarp();
+          if (++xstage == p.x_stages) { xstage = 0; xphase ^= 1; }
+          r = r1; sx = s1; cb = cb1 + 1;
+          if (cb == p.cblocks) { cb = 0; if (++sx == p.kw) { sx = 0; ++r; } }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
+    // This warp's instruction stream is what bounded the thin layers (ncu source view of Inception's 147^2 layer: ~850 instructions per
+    // 128-pixel tile around 40 MMAs, the warp busy 80 % of the time and never waiting for data), so everything per (item) or per
+    // (tile) is computed there and a pair costs a handful of uniform adds: the dz descriptors of the 8 K steps are built once per tile,
+    // the WINDOW tap offsets advance incrementally (no divisions), and descriptors travel as 64-bit values.
     // both operands MN-major (bits 15/16), fp32 accumulate, M = 128, N = tile_n
     const uint32_t fmt = p.fp16 ? 0u : 1u;
     const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 15) | (1u << 16) | (((uint32_t)p.tile_n >> 3) << 17) | ((128u >> 4) << 24);
     // MN-major SWIZZLE_128B: 128-byte rows indexed by k (64 consecutive M/N elements each), groups of
     // 8 k-rows SBO = 1024 B apart, next 64-element M/N block LBO = one 16 KB block away
     const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+    const uint64_t hi64 = (uint64_t)hi << 32;
     const uint32_t lbo = ((uint32_t)kBlk >> 4) << 16;
     const bool leader = ptx::elect_one();
+    // WINDOW: K = 16 step k = the 16 pixels at column (k % kpr) * 16 of tile row k / kpr (kpr = tw / 16 steps per tile row)
+    const int kpr_shift = p.tw == 16 ? 0 : p.tw == 32 ? 1 : p.tw == 64 ? 2 : 3;
+    uint32_t koff[kPix / 16];
+#pragma unroll
+    for (int k = 0; k < kPix / 16; ++k)
+      koff[k] = p.window ? (uint32_t)((k >> kpr_shift) * p.pitch + (k & ((1 << kpr_shift) - 1)) * 16) * 8u      // 128-byte pixels, in 16-byte units
+                         : (uint32_t)k * 128u;                                                                // 16 rows of 128 bytes
+    const uint32_t tap_wrap = (uint32_t)(p.pitch - p.kw) * 8u;     // extra rows when a tap moves to the next filter row
+    const uint32_t cb_delta = ((uint32_t)p.patch_stride >> 4) << 16;
     int dslot = 0, xstage = 0;
     uint32_t dphase = 0, xphase = 0;
     int local = 0;
@@ -211,38 +227,52 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_cons
       const int npair = min(p.group_size, p.n_mpairs - pair0);
       const int t_begin = split * p.tiles_per_split;
       const int t_end = min(total_ptiles, t_begin + p.tiles_per_split);
+      // WINDOW: the pairs' operand offsets inside a patch slot, once per item (registers; the tile loop below is unrolled over the
+      // <= 16 pairs): low descriptor word relative to the slot = first block's tap shift | LBO to the second block
+      uint32_t arel[16];
+      if (p.window) {
+        const int tap_first = p.cblocks == 2 ? pair0 : pair0 * 2;      // the only divisions of the item
+        int sx = tap_first % p.kw;
+        uint32_t rel = (uint32_t)((tap_first / p.kw) * p.pitch + sx) * 8u;
+        int blk = pair0 * 2;
+#pragma unroll
+        for (int g = 0; g < 16; ++g, blk += 2) {
+          uint32_t a = rel;
+          if (p.cblocks == 2) {
+            a |= cb_delta;                                             // (tap, 0), (tap, 1): one patch apart
+          } else {
+            const uint32_t rel0 = rel;                                 // (tap, 0), (tap + 1, 0): the tap shift apart
+            rel += 8u;
+            if (++sx == p.kw) { sx = 0; rel += tap_wrap; }
+            if (blk + 1 < p.n_blocks) a |= (rel - rel0) << 16;         // odd block count: rows 64-127 repeat block 0 (never stored)
+          }
+          rel += 8u;
+          if (++sx == p.kw) { sx = 0; rel += tap_wrap; }
+          arel[g] = a;
+        }
+      }
       ptx::mbar_wait(acc_empty, (uint32_t)((local & 1) ^ 1));
       ptx::tc_fence_after();
-      if (p.window) {
-        // K = 16 step k = the 16 pixels at column (k % kpr) * 16 of tile row k / kpr (kpr = tw / 16 steps per tile row)
-        const int kpr_shift = p.tw == 16 ? 0 : p.tw == 32 ? 1 : p.tw == 64 ? 2 : 3;
-        uint32_t koff[kPix / 16];
+      for (int pt = t_begin; pt < t_end; ++pt) {
+        const uint32_t acc_first = pt > t_begin ? 1u : 0u;
+        ptx::mbar_wait(dz_full + dslot, dphase);
+        if (p.window) ptx::mbar_wait(x_full + xstage, xphase);
+        ptx::tc_fence_after();
+        const uint32_t b_lo0 = ((ptx::smem_u32(dz_base + (size_t)dslot * dz_slot_bytes) & 0x3FFFFu) >> 4) | lbo;
+        uint64_t bdesc[kPix / 16];
 #pragma unroll
-        for (int k = 0; k < kPix / 16; ++k)
-          koff[k] = (uint32_t)((k >> kpr_shift) * p.pitch + (k & ((1 << kpr_shift) - 1)) * 16) * 8u;      // 128-byte pixels, in 16-byte units
-        for (int pt = t_begin; pt < t_end; ++pt) {
-          ptx::mbar_wait(dz_full + dslot, dphase);
-          ptx::mbar_wait(x_full + xstage, xphase);
-          ptx::tc_fence_after();
-          const uint32_t b_lo0 = ((ptx::smem_u32(dz_base + (size_t)dslot * dz_slot_bytes) & 0x3FFFFu) >> 4) | lbo;
-          const uint32_t slot = ptx::smem_u32(x_base + (size_t)xstage * x_stage_bytes);
-          for (int g = 0; g < npair; ++g) {
-            // the pair's two 64-channel blocks: (tap, channel block) each; the second sits LBO bytes after the first
-            const int blk0 = (pair0 + g) * 2;
-            const int tap0 = blk0 / p.cblocks, cb0 = blk0 - tap0 * p.cblocks;
-            const int r0 = tap0 / p.kw, s0 = tap0 - r0 * p.kw;
-            const uint32_t addr0 = slot + (uint32_t)(cb0 * p.patch_stride + (r0 * p.pitch + s0) * 128);
-            uint32_t delta = 0;                                            // odd block count: rows 64-127 repeat block 0 (never stored)
-            if (blk0 + 1 < p.n_blocks) {
-              const int tap1 = (blk0 + 1) / p.cblocks, cb1 = blk0 + 1 - tap1 * p.cblocks;
-              const int r1 = tap1 / p.kw, s1 = tap1 - r1 * p.kw;
-              delta = slot + (uint32_t)(cb1 * p.patch_stride + (r1 * p.pitch + s1) * 128) - addr0;     // > 0: cblocks <= 2
+        for (int k = 0; k < kPix / 16; ++k) bdesc[k] = hi64 | (uint64_t)(b_lo0 + (uint32_t)(k * 128));
+        if (p.window) {
+          const uint32_t slot_lo = (ptx::smem_u32(x_base + (size_t)xstage * x_stage_bytes) & 0x3FFFFu) >> 4;
+#pragma unroll
+          for (int g = 0; g < 16; ++g) {
+            if (g < npair) {                                               // warp-uniform
+              const uint32_t a_lo0 = slot_lo + arel[g];
+              const uint32_t d = tmem_base + (uint32_t)(g * p.tile_n);
+#pragma unroll
+              for (int k = 0; k < kPix / 16; ++k)
+                if (leader) ptx::umma_f16(d, hi64 | (uint64_t)(a_lo0 + koff[k]), bdesc[k], idesc, k > 0 ? 1u : acc_first);
             }
-            const uint32_t a_lo0 = ((addr0 & 0x3FFFFu) >> 4) | ((delta >> 4) << 16);
-            const uint32_t d = tmem_base + (uint32_t)(g * p.tile_n);
-#pragma unroll
-            for (int k = 0; k < kPix / 16; ++k)
-              if (leader) ptx::umma_f16_lohi(d, a_lo0 + koff[k], b_lo0 + (uint32_t)(k * 128), hi, idesc, (pt > t_begin || k > 0) ? 1u : 0u);
           }
           if (leader) {
             ptx::umma_commit(x_empty + xstage);
@@ -250,37 +280,22 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_cons
           }
           __syncwarp();
           if (++xstage == p.x_stages) { xstage = 0; xphase ^= 1; }
-          if (++dslot == p.dz_slots) { dslot = 0; dphase ^= 1; }
-        }
-        if (leader) ptx::umma_commit(acc_full);
-        __syncwarp();
-        continue;
-      }
-      for (int pt = t_begin; pt < t_end; ++pt) {
-        ptx::mbar_wait(dz_full + dslot, dphase);
-        const uint32_t b_lo0 = ((ptx::smem_u32(dz_base + (size_t)dslot * dz_slot_bytes) & 0x3FFFFu) >> 4) | lbo;
-        for (int g = 0; g < npair; ++g) {
-          const int st0 = xstage;
-          ptx::mbar_wait(x_full + st0, xphase);
-          ptx::mbar_wait(x_full + st0 + 1, xphase);                // x_stages is even: both stages share the ring phase
-          ptx::tc_fence_after();
-          const uint32_t a_lo0 = ((ptx::smem_u32(x_base + (size_t)st0 * kBlk) & 0x3FFFFu) >> 4) | lbo;
-          const uint32_t d = tmem_base + (uint32_t)(g * p.tile_n);
+        } else {
+          for (int g = 0; g < npair; ++g) {
+            ptx::mbar_wait(x_full + xstage, xphase);
+            ptx::tc_fence_after();
+            const uint32_t a_lo0 = ((ptx::smem_u32(x_base + (size_t)xstage * (2 * kBlk)) & 0x3FFFFu) >> 4) | lbo;
+            const uint32_t d = tmem_base + (uint32_t)(g * p.tile_n);
 #pragma unroll
-          for (int k = 0; k < kPix / 16; ++k)
-            if (leader)
-              ptx::umma_f16_lohi(d, a_lo0 + (uint32_t)(k * 128), b_lo0 + (uint32_t)(k * 128), hi, idesc,
-                                 (pt > t_begin || k > 0) ? 1u : 0u);
-          if (leader) {
-            ptx::umma_commit(x_empty + st0);
-            ptx::umma_commit(x_empty + st0 + 1);
+            for (int k = 0; k < kPix / 16; ++k)
+              if (leader) ptx::umma_f16(d, hi64 | (uint64_t)(a_lo0 + koff[k]), bdesc[k], idesc, k > 0 ? 1u : acc_first);
+            if (leader) ptx::umma_commit(x_empty + xstage);
+            __syncwarp();
+            if (++xstage == p.x_stages) { xstage = 0; xphase ^= 1; }
           }
+          if (leader) ptx::umma_commit(dz_empty + dslot);
           __syncwarp();
-          xstage += 2;
-          if (xstage == p.x_stages) { xstage = 0; xphase ^= 1; }
         }
-        if (leader) ptx::umma_commit(dz_empty + dslot);
-        __syncwarp();
         if (++dslot == p.dz_slots) { dslot = 0; dphase ^= 1; }
       }
       if (leader) ptx::umma_commit(acc_full);
@@ -438,19 +453,21 @@ bool plan_wgrad(const ifcb_wgrad_desc* d, WgradParams& p, bool allow_window = tr
   p.splits = (ptiles + p.tiles_per_split - 1) / p.tiles_per_split;
   p.dz_slots = 2;
   if (p.window) {
-    const int budget = 216 * 1024 - p.dz_slots * p.nblk_n * kBlk;
-    int st = budget / (p.cblocks * p.patch_stride);
-    if (st > 4) st = 4;
-    if (st < 2) {                      // no room for a double-buffered patch: the im2col variant
+    // a tile's loads are two TMA boxes (dz, patch) whose LATENCY (not bytes) is what the MMA warp waits for: as many tiles in flight as
+    // fit (<= 4: the barrier block holds four dz slots)
+    int depth = (216 * 1024) / (p.nblk_n * kBlk + p.cblocks * p.patch_stride);
+    if (depth > 4) depth = 4;
+    if (const char* e = getenv("IFCB_WGRAD_DEPTH")) depth = atoi(e) < depth ? atoi(e) : depth;       // A/B knob
+    if (depth < 2) {                   // no room for double buffering: the im2col variant
       return plan_wgrad(d, p, false);
     }
-    p.x_stages = st;
+    p.dz_slots = depth;
+    p.x_stages = depth;
   } else {
     const int budget = 216 * 1024 - p.dz_slots * p.nblk_n * kBlk;
-    int st = budget / kBlk;
-    st &= ~1;
+    int st = budget / (2 * kBlk);                      // ring stages of one block PAIR
     if (st > kMaxXStages) st = kMaxXStages;
-    if (st < 2) st = 2;
+    if (st < 1) st = 1;
     p.x_stages = st;
   }
   p.ws_stride = (long long)d->Cout * p.taps * d->Cin;
@@ -561,7 +578,7 @@ extern "C" int ifcb_conv_wgrad(const ifcb_wgrad_desc* d, void* stream_v) {
     IFCB_ARG_CHECK(p.ws != nullptr, "wgrad: the deterministic workspace is smaller than the %lld bytes this layer needs (ifcb_conv_wgrad_workspace_bytes)",
                    4ll * p.splits * p.ws_stride);
   }
-  const int smem = p.dz_slots * p.nblk_n * kBlk + p.x_stages * (p.window ? p.cblocks * p.patch_stride : kBlk) + 512 + 1024;
+  const int smem = p.dz_slots * p.nblk_n * kBlk + p.x_stages * (p.window ? p.cblocks * p.patch_stride : 2 * kBlk) + 512 + 1024;
   {   // the opt-in shared-memory limit is a per-device function attribute
     static bool done[64] = {};
     int dev = 0;
