@@ -56,6 +56,7 @@ struct WgradParams {
   int pitch;                // tw + kw - 1 patch pixels per patch row
   int patch_stride;         // bytes of one channel block's patch in shared memory (1024-aligned)
   int total_ptiles;         // pixel tiles of the whole batch
+  unsigned long long magic_img, magic_w, magic_thw, magic_tw;   // fast_div magics: rows_per_img, row_w, tiles_hw, tiles_w
   float* dW;                // [Cout][taps][Cin] fp32, accumulated into
   float* ws;                // deterministic mode: [splits][Cout][taps][Cin] partials, STORED (each element by exactly one item)
   long long ws_stride;      // Cout * taps * Cin
@@ -125,9 +126,9 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_cons
       const int t_end = min(total_ptiles, t_begin + p.tiles_per_split);
       if (p.window) {
         for (int pt = t_begin; pt < t_end; ++pt) {
-          const int img = pt / p.tiles_hw;
+          const int img = (int)fast_div((uint32_t)pt, p.magic_thw);
           const int rem = pt - img * p.tiles_hw;
-          const int ty = rem / p.tiles_w, tx = rem - ty * p.tiles_w;
+          const int ty = (int)fast_div((uint32_t)rem, p.magic_tw), tx = rem - ty * p.tiles_w;
           const int q0 = tx * p.tw, p0 = ty * p.th;
           ptx::mbar_wait(dz_empty + dslot, dphase ^ 1);
           if (ptx::elect_one()) {
@@ -156,9 +157,9 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_cons
       const int r_first = tap_first / p.kw, s_first = tap_first - r_first * p.kw;
       for (int pt = t_begin; pt < t_end; ++pt) {
         const int m0 = pt * kPix;
-        const int img = m0 / p.rows_per_img;
+        const int img = (int)fast_div((uint32_t)m0, p.magic_img);
         const int rem = m0 - img * p.rows_per_img;
-        const int op = rem / p.row_w, oq = rem - op * p.row_w;
+        const int op = (int)fast_div((uint32_t)rem, p.magic_w), oq = rem - op * p.row_w;
         const int w0 = oq * p.stride_w - p.pad_w, h0 = op * p.stride_h - p.pad_h;
         ptx::mbar_wait(dz_empty + dslot, dphase ^ 1);
         if (ptx::elect_one()) {
@@ -471,6 +472,10 @@ bool plan_wgrad(const ifcb_wgrad_desc* d, WgradParams& p, bool allow_window = tr
     p.x_stages = st;
   }
   p.ws_stride = (long long)d->Cout * p.taps * d->Cin;
+  p.magic_img = div_magic(p.rows_per_img);
+  p.magic_w = div_magic(p.row_w);
+  p.magic_thw = div_magic(p.window ? p.tiles_hw : 1);
+  p.magic_tw = div_magic(p.window ? p.tiles_w : 1);
   return true;
 }
 
