@@ -605,11 +605,32 @@ __global__ void __launch_bounds__(256) maxpool_fwd_kernel(DV x, DV y, uint8_t* _
   }
 }
 
-// the same for 3x3 windows (every max pool of ResNet / Inception-v3): the nine 16-byte loads are issued together, then reduced in
-// window-scan order (same winner as the generic kernel: first maximum, NaN propagates)
+// the same for 3x3 windows (every max pool of ResNet / Inception-v3), in PACKED 16-bit arithmetic: these kernels are bound by
+// instruction issue, not by memory (the float version spent ~360 instructions per 16 output bytes and ran at 2.4 TB/s).  The nine
+// 16-byte loads are issued together; per filter tap and pair of channels: one packed compare mask (v > best, false when unordered),
+// one packed max (NaN propagates) and one LOP3 that moves the tap number into the lanes that won -- strict '>' in window-scan
+// order keeps the FIRST maximum, as torch.nn.functional.max_pool2d.  Values are never converted: the output is bit-exact.
+template <bool FP16>
+__device__ __forceinline__ uint32_t gt2_mask(uint32_t a, uint32_t b) {
+  if (FP16) return __hgt2_mask(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
+  return __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+}
+template <bool FP16>
+__device__ __forceinline__ uint32_t max2_nan(uint32_t a, uint32_t b) {
+  if (FP16) {
+    const __half2 r = __hmax2_nan(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
+    return *reinterpret_cast<const uint32_t*>(&r);
+  }
+  const __nv_bfloat162 r = __hmax2_nan(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
+
+template <bool FP16>
 __global__ void __launch_bounds__(256) maxpool3_fwd_kernel(DV x, DV y, uint8_t* __restrict__ idx, int stride, int pad, int P, int Q,
-                                                           uint32_t total, unsigned long long magic_c8, int fp16) {
+                                                           uint32_t total, unsigned long long magic_c8) {
   const uint32_t c8n = (uint32_t)(x.C >> 3);
+  const long long row_pitch = (long long)(x.W + 2 * x.pw) * x.ld;
+  const uint32_t neg_inf = FP16 ? 0xfc00fc00u : 0xff80ff80u;
   for (uint32_t t = blockIdx.x * 256u + threadIdx.x; t < total; t += gridDim.x * 256u) {
     const uint32_t m = fast_div(t, magic_c8);
     const int c8 = (int)(t - m * c8n);
@@ -618,38 +639,35 @@ __global__ void __launch_bounds__(256) maxpool3_fwd_kernel(DV x, DV y, uint8_t* 
     const uint32_t nn = fast_div(t2, y.magic_h);
     const int op = (int)(t2 - nn * (uint32_t)P), n = (int)nn;
     const int h0 = op * stride - pad, w0 = oq * stride - pad;
+    const uint16_t* base = x.p + pix_off(x, n, h0, w0) + c8 * 8;      // dereferenced only where the tap is inside the image
     uint4 v[9];
     bool ok[9];
 #pragma unroll
     for (int r = 0; r < 3; ++r)
 #pragma unroll
       for (int s2 = 0; s2 < 3; ++s2) {
-        const int hh = h0 + r, ww = w0 + s2;
-        ok[r * 3 + s2] = (unsigned)hh < (unsigned)x.H && (unsigned)ww < (unsigned)x.W;
-        if (ok[r * 3 + s2]) v[r * 3 + s2] = ld16(x.p + pix_off(x, n, hh, ww) + c8 * 8);
+        ok[r * 3 + s2] = (unsigned)(h0 + r) < (unsigned)x.H && (unsigned)(w0 + s2) < (unsigned)x.W;
+        if (ok[r * 3 + s2]) v[r * 3 + s2] = ld16(base + r * row_pitch + s2 * x.ld);
       }
-    float best[8];
-    int bi[8];
-    bool first = true;
+    uint32_t best[4] = {neg_inf, neg_inf, neg_inf, neg_inf};
+    uint32_t bi[4] = {0u, 0u, 0u, 0u};                 // winning tap per 16-bit lane
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap) {
       if (ok[tap]) {
-        float f[8];
-        cvt8(v[tap], fp16, f);
+        const uint32_t u[4] = {v[tap].x, v[tap].y, v[tap].z, v[tap].w};
+        const uint32_t tapc = (uint32_t)tap * 0x00010001u;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (first || f[j] > best[j] || f[j] != f[j]) {
-            best[j] = f[j];
-            bi[j] = tap;
-          }
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t won = gt2_mask<FP16>(u[j], best[j]);
+          best[j] = max2_nan<FP16>(best[j], u[j]);
+          bi[j] = (bi[j] & ~won) | (tapc & won);
         }
-        first = false;
       }
     }
-    store8(y.p + pix_off(y, n, op, oq) + c8 * 8, fp16, best);
-    uint2 pk;
-    pk.x = (uint32_t)bi[0] | ((uint32_t)bi[1] << 8) | ((uint32_t)bi[2] << 16) | ((uint32_t)bi[3] << 24);
-    pk.y = (uint32_t)bi[4] | ((uint32_t)bi[5] << 8) | ((uint32_t)bi[6] << 16) | ((uint32_t)bi[7] << 24);
+    *reinterpret_cast<uint4*>(y.p + pix_off(y, n, op, oq) + c8 * 8) = make_uint4(best[0], best[1], best[2], best[3]);
+    uint2 pk;                                          // 16-bit lanes -> bytes
+    pk.x = __byte_perm(bi[0], bi[1], 0x6420);
+    pk.y = __byte_perm(bi[2], bi[3], 0x6420);
     *reinterpret_cast<uint2*>(idx + (long long)m * x.C + c8 * 8) = pk;
   }
 }
@@ -716,9 +734,13 @@ __global__ void __launch_bounds__(256) pool_bwd_kernel(DV dy, const uint8_t* __r
 
 // max-pool backward, 3x3 window / stride 2 (every max pool of ResNet and Inception-v3): an input pixel lies in at most 2 x 2
 // windows, so the four (gradient, winner-index) loads are issued together and combined afterwards -- the generic gather above
-// walks the windows one by one (1.2 TB/s; this one streams).  Same result bit for bit (same summation order: rows, then columns).
+// walks the windows one by one.  Issue-bound like the forward kernel: the winner test is one SIMD byte compare per four channels
+// (__vcmpeq4 against the tap this pixel is in that window), the byte masks are widened to 16-bit lanes (PRMT) and ANDed onto
+// the packed gradients, and only then converted and summed in fp32 -- same sum, same order (rows, then columns) as the generic
+// kernel, ~2x fewer instructions.
+template <bool FP16>
 __global__ void __launch_bounds__(256) maxpool3s2_bwd_kernel(DV dy, const uint8_t* __restrict__ idx, DV dx, int accumulate, int pad, int P,
-                                                             int Q, uint32_t total, unsigned long long magic_c8, int fp16) {
+                                                             int Q, uint32_t total, unsigned long long magic_c8) {
   const uint32_t c8n = (uint32_t)(dx.C >> 3);
   for (uint32_t t = blockIdx.x * 256u + threadIdx.x; t < total; t += gridDim.x * 256u) {
     const uint32_t m = fast_div(t, magic_c8);
@@ -734,7 +756,7 @@ __global__ void __launch_bounds__(256) maxpool3s2_bwd_kernel(DV dy, const uint8_
     uint4 gv[4];
     uint2 iv[4];
     bool ok[4];
-    int tap[4];
+    uint32_t tapb[4];
 #pragma unroll
     for (int a = 0; a < 2; ++a)
 #pragma unroll
@@ -742,7 +764,7 @@ __global__ void __launch_bounds__(256) maxpool3s2_bwd_kernel(DV dy, const uint8_
         const int op = a ? p1 : p0, oq = b ? q1 : q0;
         const int k = a * 2 + b;
         ok[k] = op >= 0 && op < P && oq >= 0 && oq < Q && (a == 1 || p0 != p1) && (b == 1 || q0 != q1);
-        tap[k] = (hp - 2 * op) * 3 + (wp - 2 * oq);
+        tapb[k] = (uint32_t)((hp - 2 * op) * 3 + (wp - 2 * oq)) * 0x01010101u;
         if (ok[k]) {
           gv[k] = ld16(dy.p + pix_off(dy, n, op, oq) + c8 * 8);
           iv[k] = *reinterpret_cast<const uint2*>(idx + (((long long)n * P + op) * Q + oq) * dx.C + c8 * 8);
@@ -752,23 +774,75 @@ __global__ void __launch_bounds__(256) maxpool3s2_bwd_kernel(DV dy, const uint8_
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       if (ok[k]) {
-        float v[8];
-        cvt8(gv[k], fp16, v);
+        const uint32_t m0 = __vcmpeq4(iv[k].x, tapb[k]), m1 = __vcmpeq4(iv[k].y, tapb[k]);     // 0xff per channel this pixel won
+        const uint32_t u[4] = {gv[k].x & __byte_perm(m0, 0, 0x1100), gv[k].y & __byte_perm(m0, 0, 0x3322),
+                               gv[k].z & __byte_perm(m1, 0, 0x1100), gv[k].w & __byte_perm(m1, 0, 0x3322)};
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int w8 = (int)(((j < 4 ? iv[k].x : iv[k].y) >> (8 * (j & 3))) & 0xffu);
-          if (w8 == tap[k]) g[j] += v[j];
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = unpack_act2(u[j], FP16 ? 1 : 0);
+          g[2 * j] += f.x;
+          g[2 * j + 1] += f.y;
         }
       }
     }
     uint16_t* dst = dx.p + pix_off(dx, n, h, w) + c8 * 8;
     if (accumulate) {
       float o[8];
-      load8(dst, fp16, o);
+      load8(dst, FP16 ? 1 : 0, o);
 #pragma unroll
       for (int j = 0; j < 8; ++j) g[j] += o[j];
     }
-    store8(dst, fp16, g);
+    store8(dst, FP16 ? 1 : 0, g);
+  }
+}
+
+// 3x3 / stride 1 / pad 1 box mean (count_include_pad: divisor 9) -- the forward AND the backward of every avg pool inside the
+// Inception blocks (the backward of this pool is the same box mean of the gradient).  All nine 16-byte loads in flight, fp32 sum in
+// window-scan order (the generic kernels below walk the window with one dependent load at a time: 0.9-1.1 TB/s).
+template <bool FP16>
+__global__ void __launch_bounds__(256) box3_kernel(DV in, DV out, int accumulate, uint32_t total, unsigned long long magic_c8) {
+  const uint32_t c8n = (uint32_t)(in.C >> 3);
+  const long long row_pitch = (long long)(in.W + 2 * in.pw) * in.ld;
+  for (uint32_t t = blockIdx.x * 256u + threadIdx.x; t < total; t += gridDim.x * 256u) {
+    const uint32_t m = fast_div(t, magic_c8);
+    const int c8 = (int)(t - m * c8n);
+    const uint32_t t2 = fast_div(m, in.magic_w);
+    const int w = (int)(m - t2 * (uint32_t)in.W);
+    const uint32_t nn = fast_div(t2, in.magic_h);
+    const int h = (int)(t2 - nn * (uint32_t)in.H), n = (int)nn;
+    const uint16_t* base = in.p + pix_off(in, n, h - 1, w - 1) + c8 * 8;      // dereferenced only where the tap is inside the image
+    uint4 v[9];
+    bool ok[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int s2 = 0; s2 < 3; ++s2) {
+        ok[r * 3 + s2] = (unsigned)(h - 1 + r) < (unsigned)in.H && (unsigned)(w - 1 + s2) < (unsigned)in.W;
+        if (ok[r * 3 + s2]) v[r * 3 + s2] = ld16(base + r * row_pitch + s2 * in.ld);
+      }
+    float g[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      if (ok[tap]) {
+        const uint32_t u[4] = {v[tap].x, v[tap].y, v[tap].z, v[tap].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = unpack_act2(u[j], FP16 ? 1 : 0);
+          g[2 * j] += f.x;
+          g[2 * j + 1] += f.y;
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] *= (1.f / 9.f);
+    uint16_t* dst = out.p + pix_off(out, n, h, w) + c8 * 8;
+    if (accumulate) {
+      float o[8];
+      load8(dst, FP16 ? 1 : 0, o);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] += o[j];
+    }
+    store8(dst, FP16 ? 1 : 0, g);
   }
 }
 
@@ -1450,9 +1524,12 @@ extern "C" int ifcb_maxpool_fwd_train(const ifcb_view* x, const ifcb_view* y, ui
                  "maxpool_fwd_train: output extent %dx%dx%d does not fit input %dx%dx%d", y->H, y->W, y->C, x->H, x->W, x->C);
   const long long total = (long long)batch * P * Q * (x->C / 8);
   IFCB_ARG_CHECK(total < (1ll << 31), "maxpool_fwd_train: tensor too large for 32-bit indexing");
-  if (k == 3)
-    maxpool3_fwd_kernel<<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(dv(x), dv(y), d_idx, stride, pad, P, Q, (uint32_t)total,
-                                                                           div_magic(x->C / 8), dtype);
+  if (k == 3 && dtype)
+    maxpool3_fwd_kernel<true><<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(dv(x), dv(y), d_idx, stride, pad, P, Q, (uint32_t)total,
+                                                                                 div_magic(x->C / 8));
+  else if (k == 3)
+    maxpool3_fwd_kernel<false><<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(dv(x), dv(y), d_idx, stride, pad, P, Q, (uint32_t)total,
+                                                                                  div_magic(x->C / 8));
   else
     maxpool_fwd_kernel<<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(dv(x), dv(y), d_idx, k, stride, pad, P, Q, (uint32_t)total,
                                                                           div_magic(x->C / 8), dtype);
@@ -1468,9 +1545,12 @@ extern "C" int ifcb_maxpool_bwd(const ifcb_view* dy, const uint8_t* d_idx, const
   IFCB_ARG_CHECK(dy->C == dx->C && pool_dim_ok(P, dx->H, k, stride, pad) && pool_dim_ok(Q, dx->W, k, stride, pad), "maxpool_bwd: gradient extent differs");
   const long long total = (long long)batch * dx->H * dx->W * (dx->C / 8);
   IFCB_ARG_CHECK(total < (1ll << 31), "maxpool_bwd: tensor too large for 32-bit indexing");
-  if (k == 3 && stride == 2)
-    maxpool3s2_bwd_kernel<<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(dv(dy), d_idx, dv(dx), accumulate, pad, P, Q, (uint32_t)total,
-                                                                             div_magic(dx->C / 8), dtype);
+  if (k == 3 && stride == 2 && dtype)
+    maxpool3s2_bwd_kernel<true><<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(dv(dy), d_idx, dv(dx), accumulate, pad, P, Q,
+                                                                                   (uint32_t)total, div_magic(dx->C / 8));
+  else if (k == 3 && stride == 2)
+    maxpool3s2_bwd_kernel<false><<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(dv(dy), d_idx, dv(dx), accumulate, pad, P, Q,
+                                                                                    (uint32_t)total, div_magic(dx->C / 8));
   else
     pool_bwd_kernel<false><<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(dv(dy), d_idx, dv(dx), accumulate, k, stride, pad, P, Q,
                                                                               (uint32_t)total, div_magic(dx->C / 8), dtype);
@@ -1485,8 +1565,13 @@ extern "C" int ifcb_avgpool_fwd(const ifcb_view* x, const ifcb_view* y, int batc
   IFCB_ARG_CHECK(y->C == x->C && y->H == P && y->W == Q, "avgpool_fwd: output extent differs");
   const long long total = (long long)batch * P * Q * (x->C / 8);
   IFCB_ARG_CHECK(total < (1ll << 31), "avgpool_fwd: tensor too large for 32-bit indexing");
-  avgpool_fwd_kernel<<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(dv(x), dv(y), k, stride, pad, P, Q, (uint32_t)total,
-                                                                        div_magic(x->C / 8), dtype);
+  if (k == 3 && stride == 1 && pad == 1) {
+    if (dtype) box3_kernel<true><<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(dv(x), dv(y), 0, (uint32_t)total, div_magic(x->C / 8));
+    else box3_kernel<false><<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(dv(x), dv(y), 0, (uint32_t)total, div_magic(x->C / 8));
+  } else {
+    avgpool_fwd_kernel<<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(dv(x), dv(y), k, stride, pad, P, Q, (uint32_t)total,
+                                                                          div_magic(x->C / 8), dtype);
+  }
   IFCB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -1499,8 +1584,13 @@ extern "C" int ifcb_avgpool_bwd(const ifcb_view* dy, const ifcb_view* dx, int ac
   IFCB_ARG_CHECK(dy->C == dx->C && dy->H == P && dy->W == Q, "avgpool_bwd: gradient extent differs");
   const long long total = (long long)batch * dx->H * dx->W * (dx->C / 8);
   IFCB_ARG_CHECK(total < (1ll << 31), "avgpool_bwd: tensor too large for 32-bit indexing");
-  pool_bwd_kernel<true><<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(dv(dy), nullptr, dv(dx), accumulate, k, stride, pad, P, Q,
-                                                                           (uint32_t)total, div_magic(dx->C / 8), dtype);
+  if (k == 3 && stride == 1 && pad == 1) {        // the gradient of a 3x3/s1/p1 box mean is the same box mean of dy
+    if (dtype) box3_kernel<true><<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(dv(dy), dv(dx), accumulate, (uint32_t)total, div_magic(dx->C / 8));
+    else box3_kernel<false><<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(dv(dy), dv(dx), accumulate, (uint32_t)total, div_magic(dx->C / 8));
+  } else {
+    pool_bwd_kernel<true><<<grid_for(total, 256), 256, 0, STREAM(stream)>>>(dv(dy), nullptr, dv(dx), accumulate, k, stride, pad, P, Q,
+                                                                             (uint32_t)total, div_magic(dx->C / 8), dtype);
+  }
   IFCB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
