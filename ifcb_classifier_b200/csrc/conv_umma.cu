@@ -341,14 +341,14 @@ __device__ __forceinline__ void issue_tap(bool leader, uint32_t a_lo, uint32_t b
 }
 
 // all taps [t0, t0 + nt) of one weight pipeline stage (WINDOW); (r, s, shift) track the tap
-template <int KS, int MS>
+template <int KS, int MS, bool PAIR = false>
 __device__ __forceinline__ void issue_stage(bool leader, int nt, bool first_stage, uint32_t a_lo0, uint32_t b_lo0,
                                             uint32_t b_tap16, uint32_t row16, uint32_t jstride, uint32_t d0, uint32_t dstep,
                                             uint32_t desc_hi, uint32_t idesc, int kw, int row_w, int& s, int& shift_rows) {
   uint32_t b_lo = b_lo0;
   for (int tt = 0; tt < nt; ++tt) {
     const uint32_t a_lo = a_lo0 + (uint32_t)shift_rows * row16;
-    issue_tap<KS, MS>(leader, a_lo, b_lo, jstride, d0, dstep, desc_hi, idesc, (first_stage && tt == 0) ? 0u : 1u);
+    issue_tap<KS, MS, PAIR>(leader, a_lo, b_lo, jstride, d0, dstep, desc_hi, idesc, (first_stage && tt == 0) ? 0u : 1u);
     b_lo += b_tap16;
     ++shift_rows;
     if (++s == kw) { s = 0; shift_rows += row_w - kw; }
@@ -661,7 +661,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 //   empty[s], tmem_full[a]   in each CTA, armed by multicast tcgen05.commit
 //   tmem_empty[a]   leader only: every epilogue warp of both CTAs arrives on it
 // ---------------------------------------------------------------------------------------
-template <bool FP16, bool STATS>
+// WINDOW on CTA pairs (same kernel, WINDOW = true): each CTA loads the input patch of ITS m accumulators' rows and half of every
+// weight tile (per SM half the weight bytes written to and kept in shared memory -- the shared-memory port is what bounds these
+// layers); the leader's M = 256 MMAs take rows [0, 128) of accumulator j from the leader's patch and rows [128, 256) from the
+// peer's patch at the same offset, so every tap is the same shifted descriptor as in the single-CTA kernel.
+//   a_full[s]   leader only, like full[s]: both CTAs' patch loads signal it;   a_empty[s]   in each CTA (multicast commit)
+template <bool WINDOW, bool FP16, bool STATS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 conv_umma_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                       const ConvKernelParams p) {
@@ -671,11 +676,16 @@ conv_umma_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
   const int row_bytes = p.row_bytes;
   const int a_tile_bytes = kBlockM * row_bytes;
   const int b_half_bytes = (p.tile_n >> 1) * row_bytes;
-  const int kb_bytes = a_tile_bytes + b_half_bytes;                   // one k-block of this CTA
-  const int stage_bytes = p.b_group * kb_bytes;                       // p.b_group k-blocks per pipeline stage
-  uint8_t* bar_base = smem + (size_t)p.stages * stage_bytes;
+  const int kb_bytes = a_tile_bytes + b_half_bytes;                   // IM2COL: one k-block of this CTA
+  // IM2COL: `stages` x b_group x [A | B half]        WINDOW: a_slots x A patch, then `stages` x (b_group B half tiles)
+  const int stage_bytes = WINDOW ? p.b_group * b_half_bytes : p.b_group * kb_bytes;
+  uint8_t* a_base = smem;
+  uint8_t* b_base = WINDOW ? smem + (size_t)p.a_slots * p.a_slot_bytes : smem;
+  uint8_t* bar_base = b_base + (size_t)p.stages * stage_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_base);
   uint64_t* empty_bar = full_bar + kMaxStages;
+  uint64_t* a_full = full_bar + 2 * kMaxStages;                       // [a_slots] (WINDOW)
+  uint64_t* a_empty = a_full + 4;
   uint64_t* tmem_full = full_bar + 2 * kMaxStages + 8;
   uint64_t* tmem_empty = full_bar + 2 * kMaxStages + 10;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(full_bar + 2 * kMaxStages + 12);
@@ -700,6 +710,11 @@ conv_umma_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       ptx::mbar_init(full_bar + s, 1);
       ptx::mbar_init(empty_bar + s, 1);
     }
+    if (WINDOW)
+      for (int s = 0; s < p.a_slots; ++s) {
+        ptx::mbar_init(a_full + s, 1);
+        ptx::mbar_init(a_empty + s, 1);
+      }
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(tmem_full + s, 1);
       ptx::mbar_init(tmem_empty + s, 2 * kEpiWarps);
@@ -717,7 +732,8 @@ conv_umma_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
   const uint32_t tmem_base = *tmem_slot;
 
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
-  const int m_tiles = (int)((p.rows + 2 * kBlockM - 1) / (2 * kBlockM));
+  const int tile_rows = kBlockM * p.m_sub;                            // rows of ONE CTA per tile (m_sub = 1 for IM2COL)
+  const int m_tiles = (int)((p.rows + 2 * tile_rows - 1) / (2 * tile_rows));
   const int total_tiles = m_tiles * p.n_tiles;
   const int taps = p.kh * p.kw;
   const int row_elems = row_bytes >> 1;
@@ -728,10 +744,50 @@ conv_umma_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
     // ===================== TMA producer (both CTAs) =====================
     int stage = 0;
     uint32_t phase = 0;
+    int aslot = 0;
+    uint32_t aphase = 0;
     for (int tile = pair; tile < total_tiles; tile += npairs) {
       int m_tile, n_tile;
       decode_tile(p, tile, m_tiles, m_tile, n_tile);
       const int n0 = n_tile * p.tile_n + (int)rank * (p.tile_n >> 1);
+      if (WINDOW) {
+        const int i0 = (m_tile * 2 + (int)rank) * tile_rows;
+        for (int cb = 0; cb < p.cblocks; ++cb) {
+          ptx::mbar_wait(a_empty + aslot, aphase ^ 1);
+          const uint32_t lead_afull = ptx::mapa(ptx::smem_u32(a_full + aslot), 0u);
+          const bool el = ptx::elect_one();
+          if (el) {
+            uint8_t* dst = a_base + (size_t)aslot * p.a_slot_bytes;
+            if (rank == 0) {
+              if (skip_loads) ptx::mbar_arrive(a_full + aslot);
+              else ptx::mbar_arrive_expect_tx(a_full + aslot, (uint32_t)(2 * p.n_boxes * p.box_rows * row_bytes));
+            }
+            if (!skip_loads)
+              for (int b = 0; b < p.n_boxes; ++b)
+                ptx::tma_load_2d_pair(dst + (size_t)b * p.box_rows * row_bytes, &tmap_a, lead_afull, cb * row_elems, i0 + b * p.box_rows);
+          }
+          __syncwarp();
+          if (++aslot == p.a_slots) { aslot = 0; aphase ^= 1; }
+          for (int t0 = 0; t0 < taps; t0 += p.b_group) {
+            const int nt = min(p.b_group, taps - t0);
+            ptx::mbar_wait(empty_bar + stage, phase ^ 1);
+            const uint32_t lead_full = ptx::mapa(ptx::smem_u32(full_bar + stage), 0u);
+            if (ptx::elect_one()) {
+              uint8_t* dst = b_base + (size_t)stage * stage_bytes;
+              if (rank == 0) {
+                if (skip_loads) ptx::mbar_arrive(full_bar + stage);
+                else ptx::mbar_arrive_expect_tx(full_bar + stage, (uint32_t)(2 * nt * b_half_bytes));
+              }
+              if (!skip_loads)
+                for (int tt = 0; tt < nt; ++tt)
+                  ptx::tma_load_2d_pair(dst + (size_t)tt * b_half_bytes, &tmap_b, lead_full, ((t0 + tt) * p.cblocks + cb) * row_elems, n0);
+            }
+            __syncwarp();
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
+        }
+        continue;
+      }
       const int m0 = m_tile * 2 * kBlockM + (int)rank * kBlockM;
       const int img = m0 / p.rows_per_img;
       const int rem = m0 - img * p.rows_per_img;
@@ -776,12 +832,63 @@ conv_umma_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       int local = 0;
       const int kblocks = taps * p.cblocks;
       const uint32_t kb16 = (uint32_t)kb_bytes >> 4;
+      int aslot = 0;
+      uint32_t aphase = 0;
+      const uint32_t row16 = (uint32_t)row_bytes >> 4;
+      const uint32_t b_tap16 = (uint32_t)b_half_bytes >> 4;
+      const uint32_t jstride = (uint32_t)(kBlockM * row_bytes) >> 4;
       for (int tile = pair; tile < total_tiles; tile += npairs, ++local) {
         const int acc = local & 1;
         const uint32_t acc_phase = (local >> 1) & 1;
         ptx::mbar_wait(tmem_empty + acc, acc_phase ^ 1);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kAccBufCols);
+        if (WINDOW) {
+          for (int cb = 0; cb < p.cblocks; ++cb) {
+            ptx::mbar_wait(a_full + aslot, aphase);
+            const uint32_t a_lo0 = ptx::umma_desc_lo(ptx::smem_u32(a_base + (size_t)aslot * p.a_slot_bytes));
+            const int ksteps = (cb == p.cblocks - 1) ? p.last_ksteps : full_ksteps;
+            int s = 0, shift_rows = p.win_shift0;
+            for (int t0 = 0; t0 < taps; t0 += p.b_group) {
+              const int nt = min(p.b_group, taps - t0);
+              if (!ready) ptx::mbar_wait(full_bar + stage, phase);
+              ptx::tc_fence_after();
+              const uint32_t b_lo0 = ptx::umma_desc_lo(ptx::smem_u32(b_base + (size_t)stage * stage_bytes));
+              const bool first_stage = (cb == 0 && t0 == 0);
+              const int cur = stage;
+              if (++stage == p.stages) { stage = 0; phase ^= 1; }
+              ready = ptx::mbar_test_wait(full_bar + stage, phase) != 0;
+              if (!skip_mma) {
+#define IFCB_ISSUE(KS, MS)                                                                                              \
+  issue_stage<KS, MS, true>(leader, nt, first_stage, a_lo0, b_lo0, b_tap16, row16, jstride, d_tmem, (uint32_t)p.tile_n, \
+                            desc_hi, idesc, p.kw, p.row_w, s, shift_rows)
+                switch (ksteps * 8 + p.m_sub) {
+                  case 1 * 8 + 1: IFCB_ISSUE(1, 1); break;
+                  case 2 * 8 + 1: IFCB_ISSUE(2, 1); break;
+                  case 3 * 8 + 1: IFCB_ISSUE(3, 1); break;
+                  case 4 * 8 + 1: IFCB_ISSUE(4, 1); break;
+                  case 1 * 8 + 2: IFCB_ISSUE(1, 2); break;
+                  case 2 * 8 + 2: IFCB_ISSUE(2, 2); break;
+                  case 3 * 8 + 2: IFCB_ISSUE(3, 2); break;
+                  case 4 * 8 + 2: IFCB_ISSUE(4, 2); break;
+                  case 1 * 8 + 4: IFCB_ISSUE(1, 4); break;
+                  case 2 * 8 + 4: IFCB_ISSUE(2, 4); break;
+                  case 3 * 8 + 4: IFCB_ISSUE(3, 4); break;
+                  default: IFCB_ISSUE(4, 4); break;
+                }
+#undef IFCB_ISSUE
+              }
+              if (leader) ptx::umma_commit_pair(empty_bar + cur);
+              __syncwarp();
+            }
+            if (leader) ptx::umma_commit_pair(a_empty + aslot);
+            __syncwarp();
+            if (++aslot == p.a_slots) { aslot = 0; aphase ^= 1; }
+          }
+          if (leader) ptx::umma_commit_pair(tmem_full + acc);
+          __syncwarp();
+          continue;
+        }
         int cb = 0;
         for (int kb = 0; kb < kblocks; kb += p.b_group) {
           const int nk = min(p.b_group, kblocks - kb);
@@ -840,7 +947,7 @@ conv_umma_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_c
       ptx::tc_fence_after();
       if (!(p.debug_flags & 4)) {
         const uint32_t tmem_acc = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * kAccBufCols);
-        epilogue_tile<FP16, STATS>(p, tmem_acc, m_tile * 2 * kBlockM + (int)rank * kBlockM + quad * 32, n_tile * p.tile_n, lane, sub, stage,
+        epilogue_tile<FP16, STATS>(p, tmem_acc, (m_tile * 2 + (int)rank) * tile_rows + quad * 32, n_tile * p.tile_n, lane, sub, stage,
                                    s_scale, s_shift, reinterpret_cast<float(&)[3][16]>(sacc));
       }
       ptx::tc_fence_before();
@@ -892,10 +999,12 @@ bool conv_plan_smem(ConvKernelParams& kp, bool window, bool pair, int halo_rows)
     return s >= 2;
   }
   // WINDOW: enumerate (m accumulators per tile, A slots, taps per weight stage) and keep the
-  // cheapest by a small cycle model per 128 output rows (constants measured on B200):
+  // cheapest by a small cycle model per 128 output rows (constants measured on B200); on CTA pairs every SM holds and fills
+  // half of each weight tile:
   //   MMA      taps * ksteps * max(N/2, 32 + N/4)           (smem operand port: 128 B/clk)
   //   loads    smem fill bytes / 60 B/clk                   (L2 -> SM)
   //   barriers ~250 clk of issue stall per pipeline stage   (4 MMAs of run-ahead)
+  const int b_tap_w = pair ? b_tap / 2 : b_tap;          // weight-tile bytes per CTA and tap
   const int full_ks = row_bytes >> 5;
   const int ks_total = (kp.cblocks - 1) * full_ks + kp.last_ksteps;
   const int t_mma = kp.tile_n / 2 > 32 + kp.tile_n / 4 ? kp.tile_n / 2 : 32 + kp.tile_n / 4;
@@ -911,18 +1020,18 @@ bool conv_plan_smem(ConvKernelParams& kp, bool window, bool pair, int halo_rows)
     const int slot = (n_boxes * box_rows * row_bytes + 1023) & ~1023;
     for (int slots = kp.a_slots_pref; slots >= 1; --slots) {
       const int left = kSmemBudget - fixed - slots * slot;
-      int gmax = 49152 / b_tap;
+      int gmax = 49152 / b_tap_w;
       if (gmax < 1) gmax = 1;
       if (gmax > taps) gmax = taps;
       if (kp.b_group_cap > 0 && gmax > kp.b_group_cap) gmax = kp.b_group_cap;
       for (int g = gmax; g >= 1; --g) {
         const int n_groups = (taps + g - 1) / g;
         const int gb = (taps + n_groups - 1) / n_groups;      // balanced group size
-        const int b_stage = gb * b_tap;
+        const int b_stage = gb * b_tap_w;
         int s = left / b_stage;
         if (s > 6) s = 6;
         if (s < 2) continue;
-        const double load_clk = ((double)kp.cblocks * slot + (double)kp.cblocks * taps * b_tap) / m / 60.0;
+        const double load_clk = ((double)kp.cblocks * slot + (double)kp.cblocks * taps * b_tap_w) / m / 60.0;
         const double bar_clk = (double)kp.cblocks * (n_groups + 1) * 250.0 / m;
         double score = (mma_clk > load_clk ? mma_clk : load_clk) + bar_clk;
         if (slots == 1) score += (double)kp.cblocks * slot / m / 60.0;     // A load not overlapped
@@ -946,7 +1055,7 @@ bool conv_plan_smem(ConvKernelParams& kp, bool window, bool pair, int halo_rows)
 
 int conv_smem_bytes(const ConvKernelParams& kp, bool window, bool pair) {
   const int b_tap = kp.tile_n * kp.row_bytes;
-  const int ops = window ? kp.a_slots * kp.a_slot_bytes + kp.stages * kp.b_group * b_tap
+  const int ops = window ? kp.a_slots * kp.a_slot_bytes + kp.stages * kp.b_group * (pair ? b_tap / 2 : b_tap)
                          : kp.stages * kp.b_group * (kBlockM * kp.row_bytes + (pair ? b_tap / 2 : b_tap));
   return ops + epilogue_smem(kp.cout_pad, kp.stats != nullptr) + 1024;
 }
@@ -975,12 +1084,12 @@ int launch_variant(const ConvLayer& L, const ConvKernelParams& p, int grid, int 
 }  // namespace
 
 namespace {
-template <bool FP16, bool STATS>
+template <bool WINDOW, bool FP16, bool STATS>
 int launch_pair(const ConvLayer& L, const ConvKernelParams& p, int grid, int smem, cudaStream_t stream) {
   static bool done[64] = {};
-  if (int rc = ensure_smem_attr(conv_umma_pair_kernel<FP16, STATS>, done)) return rc;
+  if (int rc = ensure_smem_attr(conv_umma_pair_kernel<WINDOW, FP16, STATS>, done)) return rc;
   // cluster dimensions (2,1,1) are compiled into the kernel (__cluster_dims__); grid is even
-  conv_umma_pair_kernel<FP16, STATS><<<grid, kThreads, smem, stream>>>(L.tmap_a, L.tmap_b, p);
+  conv_umma_pair_kernel<WINDOW, FP16, STATS><<<grid, kThreads, smem, stream>>>(L.tmap_a, L.tmap_b, p);
   IFCB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -1002,8 +1111,10 @@ int launch_conv(const ConvLayer& L, int batch, cudaStream_t stream) {
   if (L.pair) {
     const int pairs = sm_count() / 2;
     const int grid = 2 * (int)(total < pairs ? total : pairs);
-    if (st) return p.fp16 ? launch_pair<true, true>(L, p, grid, smem, stream) : launch_pair<false, true>(L, p, grid, smem, stream);
-    return p.fp16 ? launch_pair<true, false>(L, p, grid, smem, stream) : launch_pair<false, false>(L, p, grid, smem, stream);
+#define IFCB_LAUNCH_PAIR(W, S) (p.fp16 ? launch_pair<W, true, S>(L, p, grid, smem, stream) : launch_pair<W, false, S>(L, p, grid, smem, stream))
+    if (L.window) return st ? IFCB_LAUNCH_PAIR(true, true) : IFCB_LAUNCH_PAIR(true, false);
+    return st ? IFCB_LAUNCH_PAIR(false, true) : IFCB_LAUNCH_PAIR(false, false);
+#undef IFCB_LAUNCH_PAIR
   }
   const int grid = (int)(total < sm_count() ? total : sm_count());
 #define IFCB_LAUNCH(W, S) (p.fp16 ? launch_variant<W, true, S>(L, p, grid, smem, stream) : launch_variant<W, false, S>(L, p, grid, smem, stream))

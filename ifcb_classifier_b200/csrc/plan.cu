@@ -63,8 +63,19 @@ int pick_tile_n(int Cout, int hint) {
 //    so WINDOW layers wider than 128 channels are split into N tiles <= 128 to make room in
 //    TMEM for two accumulators per weight tile.
 //  * IM2COL runs on CTA pairs (256-pixel tiles, N tile <= 256 split over the two SMs).
+// WINDOW layers with >= 64 output channels run on CTA pairs (an internal refinement of IFCB_CONV_WINDOW: same requirements on the
+// input; each SM holds and fills half of every weight tile, and layers wider than 128 channels keep ONE N tile of up to 256
+// channels instead of two).  Measured at batch 1024 (profiles/r02_conv_window_pair_ab.txt): Conv2d_4a 1757 -> 1348 us -- the 20 % the
+// shared-memory-port model of tools/conv_rooflines.py predicts --, the 35^2 3x3 / 5x5 layers -12 ... -20 %; the 64-byte-row layers
+// (Cin <= 32: Conv2d_2b) lose 17 % and stay on one CTA.  IFCB_CONV_WINDOW_PAIR=0 switches it off.
+bool window_pair(int Cout, int Cin) {
+  static const bool on = !(getenv("IFCB_CONV_WINDOW_PAIR") && atoi(getenv("IFCB_CONV_WINDOW_PAIR")) == 0);
+  return on && (Cout >= 128 || (Cout >= 64 && Cin > 32));
+}
+
 int auto_tile_n(int Cout, int algo) {
   const int c16 = (Cout + 15) & ~15;
+  if (algo == IFCB_CONV_WINDOW && window_pair(Cout, 64) && Cout >= 128) algo = IFCB_CONV_IM2COL_PAIR;      // one N tile of up to 256 channels
   if (algo == IFCB_CONV_WINDOW && c16 > 128) {
     const int t = (c16 + 127) / 128;
     return (((c16 + t - 1) / t) + 15) & ~15;
@@ -171,7 +182,8 @@ extern "C" int ifcb_plan_add_conv(ifcb_plan* plan, const ifcb_conv_desc* d) {
   int auto_algo = IFCB_CONV_IM2COL, auto_tile_n = 0;
   auto_config(d->H, d->W, d->Cin, d->Cout, d->kh, d->kw, d->stride_h, d->stride_w, d->pad_h, d->pad_w, &auto_algo, &auto_tile_n);
   const bool window = d->algo == IFCB_CONV_WINDOW || (d->algo == IFCB_CONV_AUTO && can_window && auto_algo == IFCB_CONV_WINDOW);
-  const bool pair = !window && (d->algo == IFCB_CONV_IM2COL_PAIR || (d->algo == IFCB_CONV_AUTO && auto_algo == IFCB_CONV_IM2COL_PAIR));
+  const bool wpair = window && window_pair(d->Cout, d->Cin);
+  const bool pair = wpair || (!window && (d->algo == IFCB_CONV_IM2COL_PAIR || (d->algo == IFCB_CONV_AUTO && auto_algo == IFCB_CONV_IM2COL_PAIR)));
   const int tile_n_req = d->tile_n ? d->tile_n
                                    : ifcb::auto_tile_n(d->Cout, window ? IFCB_CONV_WINDOW : pair ? IFCB_CONV_IM2COL_PAIR : IFCB_CONV_IM2COL);
 

@@ -63,7 +63,7 @@ ALGO = {_lib.IFCB_CONV_IM2COL: 'im2col', _lib.IFCB_CONV_WINDOW: 'window', _lib.I
 hbm_b_per_clk = 6545.6e9 / 148 / (a.mhz * 1e6)
 print(__doc__.split('Model per')[0].strip().split('\n')[0])
 print('clock %.0f MHz, batch %d; times in us; bound = largest of the three\n' % (a.mhz, a.batch))
-print('%-28s %-7s %4s %2s | %8s | %8s %8s %8s | %-5s %6s' % ('layer', 'algo', 'N', 'm', 'measured', 'MMA', 'smem', 'HBM', 'bound', 'meas/b'))
+print('%-28s %-11s %4s %2s | %8s | %8s %8s %8s | %-5s %6s' % ('layer', 'algo', 'N', 'm', 'measured', 'MMA', 'smem', 'HBM', 'bound', 'meas/b'))
 tot_meas = tot_bound = 0.0
 for line in open(a.table):
     f = line.split()
@@ -80,7 +80,8 @@ for line in open(a.table):
     ksteps = (cblocks - 1) * (row_b // 32) + (last + 15) // 16
     n_tiles = (cout + tn - 1) // tn
     window = algo == _lib.IFCB_CONV_WINDOW
-    pair = algo == _lib.IFCB_CONV_IM2COL_PAIR
+    # WINDOW layers with >= 64 output channels and 128-byte rows run on CTA pairs too (plan.cu: window_pair)
+    pair = algo == _lib.IFCB_CONV_IM2COL_PAIR or (window and (cout >= 128 or (cout >= 64 and cin > 32)))
     m = 1
     if window:
         m = 4 if 4 * tn <= 256 else 2 if 2 * tn <= 256 else 1
@@ -102,6 +103,6 @@ for line in open(a.table):
     which = 'MMA' if b == mma else 'smem' if b == smem else 'HBM'
     tot_meas += meas
     tot_bound += us(b)
-    print('%-28s %-7s %4d %2d | %8.1f | %8.1f %8.1f %8.1f | %-5s %6.2f' % (f[0], ALGO[algo], tn, m, meas, us(mma), us(smem), us(hbm), which,
+    print('%-28s %-11s %4d %2d | %8.1f | %8.1f %8.1f %8.1f | %-5s %6.2f' % (f[0], (ALGO[algo] + ('+pair' if window and pair else ''))[:11], tn, m, meas, us(mma), us(smem), us(hbm), which,
                                                                              meas / us(b)))
 print('\nall %s conv launches: measured %.0f us, sum of the binding bounds %.0f us -> %.2f x' % ('listed', tot_meas, tot_bound, tot_meas / tot_bound))
