@@ -20,7 +20,9 @@
 //    instead of kh*kw times, and m (1..4) accumulators of 128 rows share each weight tile.
 //    Weight tiles of several taps travel as one pipeline stage (one barrier round trip per
 //    `b_group` taps).  Rows whose anchor falls in the padding produce junk that the
-//    epilogue drops.
+//    epilogue drops.  Layers with >= 64 output channels run this scheme on CTA PAIRS
+//    (conv_umma_pair_kernel<WINDOW = true>): the shared-memory port bounds these layers, and a
+//    pair halves the weight bytes every SM writes and keeps.
 //
 // Operand rows are one swizzle span wide: 128 bytes (64 channels, SWIZZLE_128B) or, for
 // Cin <= 32, 64 bytes (32 channels, SWIZZLE_64B) -- halves the shared-memory footprint of

@@ -148,7 +148,8 @@ enum { IFCB_CONV_AUTO = 0, IFCB_CONV_IM2COL = 1, IFCB_CONV_WINDOW = 2, IFCB_CONV
  *               IFCB_CONV_IM2COL_PAIR: the same on CTA pairs (cluster of 2, tcgen05
  *               cta_group::2): 256-pixel tiles, each SM loads half of every weight tile;
  *               IFCB_CONV_WINDOW: stride 1 and in_pad == pad -- the padded input patch
- *               of a tile is loaded ONCE and filter taps are shifted UMMA descriptors;
+ *               of a tile is loaded ONCE and filter taps are shifted UMMA descriptors (the
+ *               library runs it on CTA pairs when the layer has >= 64 output channels);
  *               IFCB_CONV_AUTO picks per shape (ifcb_conv_auto_config) among those that apply
  *   d_residual  view with the output's logical extent and its own zero border res_pad_*
  *   d_weight    16-bit [Cout_pad, kh*kw*Cin_pad] packed by the host: K index =
